@@ -1,0 +1,370 @@
+// env_kernels.cu - CUDA kernels + C-ABI for the T1 environment step (include/b200_t1.h, "env" half).
+//
+// Mapping: ONE THREAD PER ENVIRONMENT over structure-of-arrays state (coalesced rows).  The physics kernel runs
+// the whole decimated loop (10 ticks of FK/CRBA/RNE/LTDL/contact, t1_dynamics.cuh) with the 18x18 mass matrix of each
+// thread in shared memory (interleaved by lane: bank-conflict free), one warp per CTA so that N = 4096 envs spread
+// over 128 of the 148 SMs.  Model and config travel as __grid_constant__ kernel parameters (constant bank, so the
+// FFMA pipe reads them as immediate-like operands instead of issuing loads).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "t1_env.cuh"
+
+using namespace b200;
+
+struct B200T1Handle {
+    B200T1ModelF model;
+    B200T1Config cfg;
+    int num_envs, device;
+    uint64_t seed;
+    int env_base, total_envs;
+    float* fstate;
+    int32_t* istate;
+    int16_t* hf_dev;
+    int hf_rows, hf_cols;
+    long long* ctr_dev;   // [0] rng step, [1] common_step_counter, [2..3] any-reset flags (parity)
+    double* stats_dev;    // [1 + n_rew + 1] episode sums, then count as double
+};
+
+static TerrainView make_terrain(const B200T1Handle* h) {
+    TerrainView t;
+    t.hf = (h->cfg.terrain_type == 0) ? nullptr : h->hf_dev;
+    t.rows = h->hf_rows;
+    t.cols = h->hf_cols;
+    t.border_pixels = h->cfg.border_pixels;
+    t.horizontal_scale = h->cfg.horizontal_scale;
+    t.vertical_scale = (double)h->cfg.vertical_scale;
+    return t;
+}
+static EnvView make_view(const B200T1Handle* h) {
+    EnvView v;
+    v.f = h->fstate;
+    v.is = h->istate;
+    v.n = h->num_envs;
+    v.env_base = h->env_base;
+    v.seed = h->seed;
+    return v;
+}
+
+// ---- mass-matrix storage in shared memory: element idx of lane l at sm[idx * 32 + l] -------------------------------
+struct MShared {
+    float* base;
+    __device__ __forceinline__ float& operator()(int i, int j) { return base[(i * (i + 1) / 2 + j) * PHYS_BLOCK]; }
+};
+
+__global__ void __launch_bounds__(PHYS_BLOCK)
+k_physics(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c, TerrainView terr,
+          const float* __restrict__ actions, int n_substeps, int apply_pd, float* __restrict__ qacc_out,
+          long long* ctr, long long common_step, int advance) {
+    __shared__ float sM[PHYS_BLOCK * (B200_NV * (B200_NV + 1) / 2)];
+    if (advance && blockIdx.x == 0 && threadIdx.x == 0) {
+        // start of a T1.step(): common_step_counter += 1 (envs/t1.py:477), new RNG epoch, clear the stale any-reset flag
+        ctr[1] = (common_step >= 0) ? common_step : ctr[1] + 1;
+        const long long s = ctr[0] + 1;
+        ctr[0] = s;
+        ctr[2 + ((s + 1) & 1)] = 0;
+    }
+    const int e = blockIdx.x * PHYS_BLOCK + threadIdx.x;
+    if (e >= v.n) return;
+    MShared M;
+    M.base = sM + threadIdx.x;
+    float act[12];
+    const float4* a4 = reinterpret_cast<const float4*>(actions + (size_t)e * 12);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 t = a4[k];
+        act[4 * k] = t.x; act[4 * k + 1] = t.y; act[4 * k + 2] = t.z; act[4 * k + 3] = t.w;
+    }
+    float qacc[B200_NV];
+    env_physics(v, e, m, c, terr, act, n_substeps, apply_pd, M, qacc_out ? qacc : nullptr);
+    if (qacc_out) {
+#pragma unroll
+        for (int i = 0; i < B200_NV; ++i) qacc_out[(size_t)i * v.n + e] = qacc[i];
+    }
+}
+
+__global__ void k_advance(long long* ctr, long long common_step, int bump_common) {
+    if (bump_common) ctr[1] = (common_step >= 0) ? common_step : ctr[1] + 1;
+    const long long s = ctr[0] + 1;
+    ctr[0] = s;
+    ctr[2 + ((s + 1) & 1)] = 0;
+}
+
+#define POST_BLOCK 128
+#define POST_ROW (B200_NOBS + B200_NPRIV)
+
+// coalesced write-out of the [N,47] / [N,14] row-major API tensors through shared memory
+__device__ __forceinline__ void store_obs_rows(float* sbuf, const float* obs_l, const float* priv_l, int e0, int n,
+                                               float* __restrict__ obs, float* __restrict__ priv) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < B200_NOBS; ++i) sbuf[t * POST_ROW + i] = obs_l[i];
+#pragma unroll
+    for (int i = 0; i < B200_NPRIV; ++i) sbuf[t * POST_ROW + B200_NOBS + i] = priv_l[i];
+    __syncthreads();
+    const int cnt = min(POST_BLOCK, n - e0);
+    for (int idx = t; idx < cnt * B200_NOBS; idx += POST_BLOCK) {
+        const int el = idx / B200_NOBS, i = idx - el * B200_NOBS;
+        obs[(size_t)e0 * B200_NOBS + idx] = sbuf[el * POST_ROW + i];
+    }
+    for (int idx = t; idx < cnt * B200_NPRIV; idx += POST_BLOCK) {
+        const int el = idx / B200_NPRIV, i = idx - el * B200_NPRIV;
+        priv[(size_t)e0 * B200_NPRIV + idx] = sbuf[el * POST_ROW + B200_NOBS + i];
+    }
+}
+
+__global__ void __launch_bounds__(POST_BLOCK)
+k_post(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c, TerrainView terr,
+       const long long* __restrict__ ctr, int noise_on, float* __restrict__ obs, float* __restrict__ priv,
+       float* __restrict__ rew, uint8_t* __restrict__ done, float* __restrict__ rew_terms, long long* flags,
+       double* stats) {
+    __shared__ float sbuf[POST_BLOCK * POST_ROW];
+    const int e0 = blockIdx.x * POST_BLOCK;
+    const int e = e0 + threadIdx.x;
+    const long long step = ctr[0], common_step = ctr[1];
+    float obs_l[B200_NOBS], priv_l[B200_NPRIV];
+    if (e < v.n) {
+        const StepOut o = env_post_physics(v, e, m, c, terr, common_step, (uint64_t)step, noise_on, obs_l, priv_l, rew_terms);
+        rew[e] = o.rew;
+        done[e] = (uint8_t)o.done;
+        if (o.done) {
+            flags[step & 1] = 1;  // benign race: every writer stores 1
+            // device episode statistics (utils/recorder.py:36-62): flush this episode's sums
+            float* f = v.f;
+            int32_t* is = v.is;
+            const int n = v.n;
+            for (int k = 0; k < 1 + c.n_rew; ++k) {
+                atomicAdd(&stats[k], (double)FS(F_episode_sums + k));
+                FS(F_episode_sums + k) = 0.0f;
+            }
+            atomicAdd(&stats[1 + c.n_rew], (double)IS(I_episode_steps));
+            atomicAdd(&stats[2 + c.n_rew], 1.0);
+            IS(I_episode_steps) = 0;
+        }
+    }
+    store_obs_rows(sbuf, obs_l, priv_l, e0, v.n, obs, priv);
+}
+
+// extras["time_outs"] is rebound only on steps where at least one env resets (envs/t1.py:317 vs :556, SURVEY 8a note 1)
+__global__ void k_finalize_timeouts(const int32_t* __restrict__ is, int n, const long long* __restrict__ ctr,
+                                    const long long* __restrict__ flags, uint8_t* __restrict__ time_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (flags[ctr[0] & 1]) time_out[e] = (uint8_t)is[(size_t)I_time_out_buf * n + e];
+}
+
+__global__ void __launch_bounds__(POST_BLOCK)
+k_reset_all(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c, TerrainView terr,
+            const long long* __restrict__ ctr, float* __restrict__ obs, float* __restrict__ priv) {
+    __shared__ float sbuf[POST_BLOCK * POST_ROW];
+    const int e0 = blockIdx.x * POST_BLOCK;
+    const int e = e0 + threadIdx.x;
+    const uint64_t step = (uint64_t)ctr[0];
+    float obs_l[B200_NOBS], priv_l[B200_NPRIV];
+    if (e < v.n) {
+        // T1.reset(): _reset_idx(all) ; _resample_commands ; _compute_observations   (envs/t1.py:294-299)
+        env_reset_one(v, e, c, terr, step);
+        float* f = v.f;
+        int32_t* is = v.is;
+        const int n = v.n;
+        if (IS(I_episode_length_buf) == IS(I_cmd_resample_time)) env_resample_command(v, e, c, step);
+        env_observations(v, e, c, terr, step, 1, obs_l, priv_l);
+    }
+    store_obs_rows(sbuf, obs_l, priv_l, e0, v.n, obs, priv);
+}
+
+__global__ void k_init_params(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < v.n) env_init_params(v, e, m, c);
+}
+
+__global__ void k_terrain_heights(TerrainView terr, const float* __restrict__ xy, int stride, int count, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = terr(xy[(size_t)i * stride], xy[(size_t)i * stride + 1]);
+}
+
+__global__ void k_rng_fill(uint64_t seed, int env_base, int n, uint64_t step, int purpose, int sub, int kind, float* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const Philox4 p = rng_words(seed, (uint32_t)(env_base + e), step, purpose, sub);
+    const Rand4 r = rand4(p);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        float val = (kind == 0) ? r.u[l] : ((kind == 1) ? r.n[l] : __uint_as_float(p.w[l]));
+        out[(size_t)l * n + e] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200_t1_num_float_rows(void) { return F_ROWS; }
+int b200_t1_num_int_rows(void) { return I_ROWS; }
+int b200_t1_num_fields(int kind) {
+    return kind == 0 ? (int)(sizeof(kFloatFields) / sizeof(FieldInfo)) : (int)(sizeof(kIntFields) / sizeof(FieldInfo));
+}
+int b200_t1_field_info(int kind, int idx, const char** name, int* row, int* count) {
+    if (idx < 0 || idx >= b200_t1_num_fields(kind)) return B200_ERR_ARG;
+    const FieldInfo& fi = (kind == 0) ? kFloatFields[idx] : kIntFields[idx];
+    if (name) *name = fi.name;
+    if (row) *row = fi.row;
+    if (count) *count = fi.count;
+    return B200_OK;
+}
+
+int b200_t1_create(const B200T1ModelF* model, const B200T1Config* cfg, const int16_t* hf_host, int hf_rows, int hf_cols,
+                   int num_envs, int device, uint64_t seed, B200T1Handle** out) {
+    if (!model || !cfg || !out || num_envs <= 0) return set_error(B200_ERR_ARG, "b200_t1_create: bad argument");
+    if (cfg->terrain_type != 0 && cfg->terrain_type != 1) return set_error(B200_ERR_ARG, "Invalid terrain type");
+    if (cfg->terrain_type == 1 && (!hf_host || hf_rows <= 1 || hf_cols <= 1))
+        return set_error(B200_ERR_ARG, "trimesh terrain needs a heightfield");
+    if (cfg->n_rew < 0 || cfg->n_rew > B200_MAX_REW) return set_error(B200_ERR_ARG, "bad reward count");
+    if (cfg->decimation <= 0 || cfg->resample_hi <= cfg->resample_lo) return set_error(B200_ERR_ARG, "bad control/command config");
+    if (cfg->curriculum) return set_error(B200_ERR_UNSUPPORTED, "command curriculum is not built yet (SURVEY 8 f4)");
+    CUDA_TRY(cudaSetDevice(device));
+    B200T1Handle* h = new (std::nothrow) B200T1Handle();
+    if (!h) return set_error(B200_ERR_ARG, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->model = *model;
+    h->cfg = *cfg;
+    h->num_envs = num_envs;
+    h->device = device;
+    h->seed = seed;
+    h->env_base = 0;
+    h->total_envs = num_envs;
+    h->hf_rows = hf_rows;
+    h->hf_cols = hf_cols;
+    if (cfg->terrain_type == 1) {
+        const size_t bytes = (size_t)hf_rows * hf_cols * sizeof(int16_t);
+        CUDA_TRY(cudaMalloc(&h->hf_dev, bytes));
+        CUDA_TRY(cudaMemcpy(h->hf_dev, hf_host, bytes, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMalloc(&h->ctr_dev, 4 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(h->ctr_dev, 0, 4 * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&h->stats_dev, (B200_MAX_REW + 4) * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->stats_dev, 0, (B200_MAX_REW + 4) * sizeof(double)));
+    *out = h;
+    return B200_OK;
+}
+
+int b200_t1_destroy(B200T1Handle* h) {
+    if (!h) return B200_OK;
+    cudaSetDevice(h->device);
+    if (h->hf_dev) cudaFree(h->hf_dev);
+    if (h->ctr_dev) cudaFree(h->ctr_dev);
+    if (h->stats_dev) cudaFree(h->stats_dev);
+    delete h;
+    return B200_OK;
+}
+
+int b200_t1_bind_state(B200T1Handle* h, float* fstate, int32_t* istate) {
+    if (!h || !fstate || !istate) return set_error(B200_ERR_ARG, "b200_t1_bind_state: null pointer");
+    h->fstate = fstate;
+    h->istate = istate;
+    return B200_OK;
+}
+int b200_t1_num_envs(const B200T1Handle* h) { return h ? h->num_envs : B200_ERR_ARG; }
+
+#define NEED_STATE(h)                                                                  \
+    if (!(h)) return set_error(B200_ERR_ARG, "null handle");                           \
+    if (!(h)->fstate || !(h)->istate) return set_error(B200_ERR_STATE, "state not bound")
+
+int b200_t1_init_params(B200T1Handle* h, int env_index_base, int total_envs, void* stream) {
+    NEED_STATE(h);
+    h->env_base = env_index_base;
+    h->total_envs = total_envs;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_init_params<<<(h->num_envs + 127) / 128, 128, 0, st>>>(make_view(h), h->model, h->cfg);
+    return launch_status("k_init_params");
+}
+
+int b200_t1_reset(B200T1Handle* h, float* obs, float* priv, void* stream) {
+    NEED_STATE(h);
+    if (!obs || !priv) return set_error(B200_ERR_ARG, "b200_t1_reset: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_advance<<<1, 1, 0, st>>>(h->ctr_dev, -1, 0);
+    k_reset_all<<<(h->num_envs + POST_BLOCK - 1) / POST_BLOCK, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg,
+                                                                                    make_terrain(h), h->ctr_dev, obs, priv);
+    return launch_status("k_reset_all");
+}
+
+int b200_t1_physics(B200T1Handle* h, const float* actions, int n_substeps, int apply_pd, float* qacc_out, void* stream) {
+    NEED_STATE(h);
+    if (!actions || n_substeps < 0) return set_error(B200_ERR_ARG, "b200_t1_physics: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_physics<<<(h->num_envs + PHYS_BLOCK - 1) / PHYS_BLOCK, PHYS_BLOCK, 0, st>>>(
+        make_view(h), h->model, h->cfg, make_terrain(h), actions, n_substeps, apply_pd, qacc_out, h->ctr_dev, -1, 0);
+    return launch_status("k_physics");
+}
+
+static int launch_post(B200T1Handle* h, float* obs, float* priv, float* rew, uint8_t* done, uint8_t* time_out,
+                       float* rew_terms, int noise_on, cudaStream_t st) {
+    k_post<<<(h->num_envs + POST_BLOCK - 1) / POST_BLOCK, POST_BLOCK, 0, st>>>(
+        make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done, rew_terms,
+        h->ctr_dev + 2, h->stats_dev);
+    k_finalize_timeouts<<<(h->num_envs + 255) / 256, 256, 0, st>>>(h->istate, h->num_envs, h->ctr_dev, h->ctr_dev + 2, time_out);
+    return launch_status("k_post");
+}
+
+int b200_t1_post_physics(B200T1Handle* h, float* obs, float* priv, float* rew, uint8_t* done, uint8_t* time_out,
+                         float* rew_terms, int64_t common_step, int noise_on, void* stream) {
+    NEED_STATE(h);
+    if (!obs || !priv || !rew || !done || !time_out) return set_error(B200_ERR_ARG, "b200_t1_post_physics: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_advance<<<1, 1, 0, st>>>(h->ctr_dev, (long long)common_step, 1);
+    return launch_post(h, obs, priv, rew, done, time_out, rew_terms, noise_on, st);
+}
+
+int b200_t1_step(B200T1Handle* h, const float* actions, float* obs, float* priv, float* rew, uint8_t* done,
+                 uint8_t* time_out, float* rew_terms, int64_t common_step, void* stream) {
+    NEED_STATE(h);
+    if (!actions || !obs || !priv || !rew || !done || !time_out) return set_error(B200_ERR_ARG, "b200_t1_step: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_physics<<<(h->num_envs + PHYS_BLOCK - 1) / PHYS_BLOCK, PHYS_BLOCK, 0, st>>>(
+        make_view(h), h->model, h->cfg, make_terrain(h), actions, h->cfg.decimation, 1, nullptr, h->ctr_dev,
+        (long long)common_step, 1);
+    return launch_post(h, obs, priv, rew, done, time_out, rew_terms, 1, st);
+}
+
+int b200_t1_episode_stats(B200T1Handle* h, double* sums_host, int64_t* count_host, void* stream) {
+    if (!h || !sums_host || !count_host) return set_error(B200_ERR_ARG, "b200_t1_episode_stats: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    double tmp[B200_MAX_REW + 4];
+    const int k = h->cfg.n_rew + 3;
+    CUDA_TRY(cudaMemcpyAsync(tmp, h->stats_dev, k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemsetAsync(h->stats_dev, 0, k * sizeof(double), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < k - 1; ++i) sums_host[i] = tmp[i];
+    *count_host = (int64_t)(tmp[k - 1] + 0.5);
+    return B200_OK;
+}
+
+int b200_terrain_heights(const B200T1Handle* h, const float* xy, int stride, int count, float* out, void* stream) {
+    if (!h || !xy || !out || stride < 2 || count < 0) return set_error(B200_ERR_ARG, "b200_terrain_heights: bad argument");
+    if (count == 0) return B200_OK;
+    k_terrain_heights<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_terrain(h), xy, stride, count, out);
+    return launch_status("k_terrain_heights");
+}
+
+int b200_rng_fill(const B200T1Handle* h, uint64_t step, int purpose, int sub, int kind, float* out, void* stream) {
+    if (!h || !out) return set_error(B200_ERR_ARG, "b200_rng_fill: null pointer");
+    k_rng_fill<<<(h->num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->seed, h->env_base, h->num_envs, step, purpose, sub, kind, out);
+    return launch_status("k_rng_fill");
+}
+
+/* current (rng step, common_step) as seen by the NEXT kernel in the stream; synchronises. Test helper. */
+int b200_t1_counters(B200T1Handle* h, int64_t* rng_step, int64_t* common_step, void* stream) {
+    if (!h) return set_error(B200_ERR_ARG, "null handle");
+    long long tmp[2];
+    CUDA_TRY(cudaMemcpyAsync(tmp, h->ctr_dev, sizeof tmp, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (rng_step) *rng_step = tmp[0];
+    if (common_step) *common_step = tmp[1];
+    return B200_OK;
+}
+
+}  // extern "C"

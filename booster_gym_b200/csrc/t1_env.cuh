@@ -1,0 +1,615 @@
+// t1_env.cuh - per-environment bodies of T1.step()/reset() (envs/t1.py:294-603) as __host__ __device__ functions over
+// the structure-of-arrays state (t1_state.h).  One call handles ONE environment `e`; the CUDA kernels map one thread
+// per environment so every state access `f[row * n + e]` is coalesced across the warp.
+//
+// Order of operations, quirks and fp32 operation order follow the reference line by line (citations inline;
+// SURVEY 8a notes 1-11).  The host build in tests/hostcheck is test infrastructure only.
+#pragma once
+#include "rng.cuh"
+#include "t1_dynamics.cuh"
+#include "t1_state.h"
+#include "terrain.cuh"
+
+namespace b200 {
+
+#define FS(row) f[(size_t)(row) * (size_t)n + (size_t)e]
+#define IS(row) is[(size_t)(row) * (size_t)n + (size_t)e]
+
+struct EnvView {
+    float* f;
+    int32_t* is;
+    int n;             // envs in this shard
+    int env_base;      // global index of env 0 of this shard (RNG counter)
+    uint64_t seed;
+};
+
+// ---- Isaac Gym torch_utils semantics (third-party, restated) ---------------------------------------
+B200_HD void quat_rotate_inverse(const float* q, const float* v, float* o) {
+    const float qw = q[3];
+    const float s = 2.0f * qw * qw - 1.0f;
+    float c[3];
+    cross3(q, v, c);
+    const float d = q[0] * v[0] + q[1] * v[1] + q[2] * v[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = v[i] * s - c[i] * qw * 2.0f + q[i] * d * 2.0f;
+}
+B200_HD void quat_rotate(const float* q, const float* v, float* o) {
+    const float qw = q[3];
+    const float s = 2.0f * qw * qw - 1.0f;
+    float c[3];
+    cross3(q, v, c);
+    const float d = q[0] * v[0] + q[1] * v[1] + q[2] * v[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = v[i] * s + c[i] * qw * 2.0f + q[i] * d * 2.0f;
+}
+B200_HD float py_mod(float a, float b) {  // torch.remainder / Python % for b > 0
+    float r = fmodf(a, b);
+    if (r != 0.0f && r < 0.0f) r += b;
+    return r;
+}
+#define B200_PI_F 3.14159265358979323846f
+#define B200_2PI_F 6.28318530717958647692f
+B200_HD void get_euler_xyz(const float* q, float& roll, float& pitch, float& yaw) {
+    const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+    const float sinr_cosp = 2.0f * (qw * qx + qy * qz);
+    const float cosr_cosp = qw * qw - qx * qx - qy * qy + qz * qz;
+    roll = atan2f(sinr_cosp, cosr_cosp);
+    const float sinp = 2.0f * (qw * qy - qz * qx);
+    pitch = (fabsf(sinp) >= 1.0f) ? copysignf(B200_PI_F / 2.0f, sinp) : asinf(sinp);
+    const float siny_cosp = 2.0f * (qw * qz + qx * qy);
+    const float cosy_cosp = qw * qw + qx * qx - qy * qy - qz * qz;
+    yaw = atan2f(siny_cosp, cosy_cosp);
+    roll = py_mod(roll, B200_2PI_F);
+    pitch = py_mod(pitch, B200_2PI_F);
+    yaw = py_mod(yaw, B200_2PI_F);
+}
+B200_HD float wrap_pi(float a) { return py_mod(a + B200_PI_F, B200_2PI_F) - B200_PI_F; }
+
+// utils/utils.py:5-30.  For the uniform law `r.b` holds (hi - lo) evaluated in fp64 on the host, like Python does.
+B200_HD float apply_rand(float x, const B200Rand& r, float u, float nrm) {
+    if (!r.enabled) return x;
+    const float nv = (r.dist == 0) ? (r.a + r.b * nrm) : (r.a + r.b * u);
+    return (r.op == 0) ? (x + nv) : (x * nv);
+}
+B200_HD float raw_rand(const B200Rand& r, float u, float nrm) { return (r.dist == 0) ? nrm : u; }
+
+// ---- envs/t1.py:439-456 + the physics engine: the decimated PD-torque loop ----------------------------------------
+// act: this env's 12 actions (policy output, unclipped) or raw torques if !apply_pd.
+template <typename Model, typename MS>
+B200_HD void env_physics(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr,
+                         const float* act, int n_substeps, int apply_pd, MS& M, float* qacc_out /*18 or null*/) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+    DynState<float> s;
+    DynParams<float> par;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { s.pos[i] = FS(F_root_states + i); s.vlin[i] = FS(F_root_states + 7 + i); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s.quat[i] = FS(F_root_states + 3 + i);
+    {
+        float ww[3] = {FS(F_root_states + 10), FS(F_root_states + 11), FS(F_root_states + 12)};
+        float R0[3][3];
+        quat_to_mat(s.quat, R0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s.wb[k] = R0[0][k] * ww[0] + R0[1][k] * ww[1] + R0[2][k] * ww[2];
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { s.q[j] = FS(F_dof_pos + j); s.qd[j] = FS(F_dof_vel + j); }
+#pragma unroll
+    for (int b = 0; b < B200_NB; ++b) {
+        par.mass[b] = FS(F_body_mass + b);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) par.com[b][r] = FS(F_body_com + 3 * b + r);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        par.mu[k] = FS(F_foot_friction + k);
+        par.kscale[k] = FS(F_foot_kscale + k);
+        par.cscale[k] = FS(F_foot_cscale + k);
+    }
+    float push_f[3], push_t[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { push_f[r] = FS(F_pushing_forces + r); push_t[r] = FS(F_pushing_torques + r); }
+
+    float target[12], last_target[12], tsum[12], kp[12], kd[12], fr[12];
+    const int delay = IS(I_delay_steps);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        if (apply_pd) {
+            const float a = fminf(fmaxf(act[j], -c.clip_actions), c.clip_actions);  // envs/t1.py:439
+            FS(F_actions + j) = a;
+            target[j] = c.default_dof_pos[j] + c.action_scale * a;                  // :440
+        } else {
+            target[j] = act[j];
+        }
+        last_target[j] = FS(F_last_dof_targets + j);
+        kp[j] = FS(F_dof_stiffness + j);
+        kd[j] = FS(F_dof_damping + j);
+        fr[j] = FS(F_dof_friction + j);
+        tsum[j] = 0.0f;
+    }
+    DynAux<float> aux;
+    aux.foot_fn[0] = aux.foot_fn[1] = 0.0f;
+    for (int i = 0; i < n_substeps; ++i) {
+        float tau[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            if (apply_pd) {
+                if (delay == i) last_target[j] = target[j];                            // :445
+                float t = kp[j] * (last_target[j] - s.q[j]) - kd[j] * s.qd[j];         // :446
+                const float fric = fminf(fr[j], fabsf(t)) * ((t > 0.0f) ? 1.0f : ((t < 0.0f) ? -1.0f : 0.0f));  // :447
+                t = fminf(fmaxf(t - fric, -c.torque_limits[j]), c.torque_limits[j]);   // :448
+                tau[j] = t;
+                tsum[j] += t;                                                          // :449
+            } else {
+                tau[j] = target[j];
+            }
+        }
+        t1_tick<float>(m, par, s, tau, push_f, push_t, terr, M, aux, true);
+    }
+    // write back (refresh_* tensors of envs/t1.py:454,460-462)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { FS(F_root_states + i) = s.pos[i]; FS(F_root_states + 7 + i) = s.vlin[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) FS(F_root_states + 3 + i) = s.quat[i];
+    {
+        float R0[3][3];
+        quat_to_mat(s.quat, R0);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) FS(F_root_states + 10 + r) = R0[r][0] * s.wb[0] + R0[r][1] * s.wb[1] + R0[r][2] * s.wb[2];
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        FS(F_dof_pos + j) = s.q[j];
+        FS(F_dof_vel + j) = s.qd[j];
+        if (apply_pd) {
+            FS(F_last_dof_targets + j) = last_target[j];
+            FS(F_torques + j) = tsum[j] / (float)n_substeps;                           // :456
+        }
+    }
+    float fp[2][3], fq[2][4];
+    t1_feet_fk<float>(m, s, fp, fq);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) FS(F_feet_pos + 3 * k + r) = fp[k][r];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) FS(F_feet_quat + 4 * k + r) = fq[k][r];
+        FS(F_feet_force + k) = aux.foot_fn[k];
+    }
+    if (qacc_out) {
+#pragma unroll
+        for (int i = 0; i < B200_NV; ++i) qacc_out[i] = aux.qacc[i];
+    }
+}
+
+// ---- envs/t1.py:529-549 ------------------------------------------------------------------------------------------
+template <typename Model>
+B200_HD void env_refresh_feet(const EnvView& v, int e, const Model& m, const TerrainView& terr) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float q[4], p[3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) q[r] = FS(F_feet_quat + 4 * k + r);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) p[r] = FS(F_feet_pos + 3 * k + r);
+        float roll, pitch, yaw;
+        get_euler_xyz(q, roll, pitch, yaw);
+        FS(F_feet_roll + k) = wrap_pi(roll);  // :533
+        FS(F_feet_yaw + k) = wrap_pi(yaw);    // :534
+        bool contact = false;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+            const float rel[3] = {m.foot_corner[cidx][0], m.foot_corner[cidx][1], m.foot_corner[cidx][2]};
+            float w[3];
+            quat_rotate(q, rel, w);
+            const float ex = p[0] + w[0], ey = p[1] + w[1], ez = p[2] + w[2];  // :543
+            contact = contact || (ez - terr(ex, ey) < 0.01f);               // :544-549
+        }
+        IS(I_feet_contact + k) = contact ? 1 : 0;
+    }
+}
+
+// reward term k of envs/t1.py:606-730 (unscaled); `h_base` = terrain height under the base
+B200_HD float reward_term(int id, const EnvView& v, int e, const B200T1Config& c, float h_base) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+    switch (id) {
+        case B200_REW_SURVIVAL: return 1.0f;
+        case B200_REW_TRACK_LIN_X: { const float d = FS(F_commands + 0) - FS(F_filtered_lin_vel + 0); return expf(-(d * d) / c.tracking_sigma); }
+        case B200_REW_TRACK_LIN_Y: { const float d = FS(F_commands + 1) - FS(F_filtered_lin_vel + 1); return expf(-(d * d) / c.tracking_sigma); }
+        case B200_REW_TRACK_ANG: { const float d = FS(F_commands + 2) - FS(F_filtered_ang_vel + 2); return expf(-(d * d) / c.tracking_sigma); }
+        case B200_REW_BASE_HEIGHT: { const float bh = FS(F_root_states + 2) - h_base; const float d = bh - c.base_height_target; return d * d; }
+        case B200_REW_ORIENTATION: { const float a = FS(F_projected_gravity + 0), b = FS(F_projected_gravity + 1); return a * a + b * b; }
+        case B200_REW_TORQUES: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_torques + j); s += t * t; } return s; }
+        case B200_REW_TORQUE_TIREDNESS: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_torques + j) / c.torque_limits[j]; s += fminf(t * t, 1.0f); } return s; }
+        case B200_REW_POWER: { float s = 0; for (int j = 0; j < 12; ++j) s += fmaxf(FS(F_torques + j) * FS(F_dof_vel + j), 0.0f); return s; }
+        case B200_REW_LIN_VEL_Z: { const float a = FS(F_filtered_lin_vel + 2); return a * a; }
+        case B200_REW_ANG_VEL_XY: { const float a = FS(F_base_ang_vel + 0), b = FS(F_base_ang_vel + 1); return a * a + b * b; }
+        case B200_REW_DOF_VEL: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_dof_vel + j); s += t * t; } return s; }
+        case B200_REW_DOF_ACC: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = (FS(F_last_dof_vel + j) - FS(F_dof_vel + j)) / c.env_dt; s += t * t; } return s; }
+        case B200_REW_ROOT_ACC: { float s = 0; for (int j = 0; j < 6; ++j) { const float t = (FS(F_last_root_vel + j) - FS(F_root_states + 7 + j)) / c.env_dt; s += t * t; } return s; }
+        case B200_REW_ACTION_RATE: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_last_actions + j) - FS(F_actions + j); s += t * t; } return s; }
+        case B200_REW_DOF_POS_LIMITS: { float s = 0; for (int j = 0; j < 12; ++j) { const float q = FS(F_dof_pos + j); s += ((q < c.dof_pos_soft_lower[j]) || (q > c.dof_pos_soft_upper[j])) ? 1.0f : 0.0f; } return s; }
+        case B200_REW_DOF_VEL_LIMITS: { float s = 0; for (int j = 0; j < 12; ++j) s += fminf(fmaxf(fabsf(FS(F_dof_vel + j)) - c.dof_vel_limits[j] * c.soft_dof_vel_limit, 0.0f), 1.0f); return s; }
+        case B200_REW_TORQUE_LIMITS: { float s = 0; for (int j = 0; j < 12; ++j) s += fmaxf(fabsf(FS(F_torques + j)) - c.torque_limits[j] * c.soft_torque_limit, 0.0f); return s; }
+        case B200_REW_COLLISION: return 0.0f;  // only the feet carry contact points in this build; feet are not penalised bodies
+        case B200_REW_FEET_SLIP: {
+            float s = 0;
+            for (int k = 0; k < 2; ++k) {
+                float q = 0;
+                for (int r = 0; r < 3; ++r) { const float t = (FS(F_last_feet_pos + 3 * k + r) - FS(F_feet_pos + 3 * k + r)) / c.env_dt; q += t * t; }
+                s += q * (IS(I_feet_contact + k) ? 1.0f : 0.0f);
+            }
+            return s * ((IS(I_episode_length_buf) > 1) ? 1.0f : 0.0f);
+        }
+        case B200_REW_FEET_VEL_Z: { float s = 0; for (int k = 0; k < 2; ++k) { const float t = (FS(F_last_feet_pos + 3 * k + 2) - FS(F_feet_pos + 3 * k + 2)) / c.env_dt; s += t * t; } return s; }
+        case B200_REW_FEET_YAW_DIFF: { const float d = wrap_pi(FS(F_feet_yaw + 1) - FS(F_feet_yaw + 0)); return d * d; }
+        case B200_REW_FEET_YAW_MEAN: {
+            const float y0 = FS(F_feet_yaw + 0), y1 = FS(F_feet_yaw + 1);
+            const float mean = (y0 + y1) / 2.0f + B200_PI_F * ((fabsf(y1 - y0) > B200_PI_F) ? 1.0f : 0.0f);
+            float q[4] = {FS(F_root_states + 3), FS(F_root_states + 4), FS(F_root_states + 5), FS(F_root_states + 6)};
+            float r, p, y;
+            get_euler_xyz(q, r, p, y);
+            const float d = wrap_pi(y - mean);
+            return d * d;
+        }
+        case B200_REW_FEET_ROLL: { const float a = FS(F_feet_roll + 0), b = FS(F_feet_roll + 1); return a * a + b * b; }
+        case B200_REW_FEET_DISTANCE: {
+            float q[4] = {FS(F_root_states + 3), FS(F_root_states + 4), FS(F_root_states + 5), FS(F_root_states + 6)};
+            float r, p, y;
+            get_euler_xyz(q, r, p, y);
+            const float dist = fabsf(cosf(y) * (FS(F_feet_pos + 3 + 1) - FS(F_feet_pos + 1)) - sinf(y) * (FS(F_feet_pos + 3 + 0) - FS(F_feet_pos + 0)));
+            return fminf(fmaxf(c.feet_distance_ref - dist, 0.0f), 0.1f);
+        }
+        case B200_REW_FEET_SWING: {
+            const float gp = FS(F_gait_process);
+            const bool moving = FS(F_gait_frequency) > 1.0e-8f;
+            const bool ls = (fabsf(gp - 0.25f) < 0.5f * c.swing_period) && moving;
+            const bool rs = (fabsf(gp - 0.75f) < 0.5f * c.swing_period) && moving;
+            return ((ls && !IS(I_feet_contact + 0)) ? 1.0f : 0.0f) + ((rs && !IS(I_feet_contact + 1)) ? 1.0f : 0.0f);
+        }
+    }
+    return 0.0f;
+}
+
+// envs/t1.py:301-341 for ONE env (always resets; the caller decides).  `step` = RNG counter of this call.
+B200_HD void env_reset_one(const EnvView& v, int e, const B200T1Config& c, const TerrainView& terr, uint64_t step) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+    const uint32_t ge = (uint32_t)(v.env_base + e);
+    // _reset_dofs :319-325
+#pragma unroll
+    for (int sub = 0; sub < 3; ++sub) {
+        const Rand4 r = rand4(rng_words(v.seed, ge, step, RP_RESET_DOF, sub));
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int j = 4 * sub + l;
+            FS(F_dof_pos + j) = apply_rand(c.default_dof_pos[j], c.init_dof_pos, r.u[l], r.n[l]);
+            FS(F_dof_vel + j) = 0.0f;
+        }
+    }
+    // _reset_root_states :327-341
+    const Rand4 r0 = rand4(rng_words(v.seed, ge, step, RP_RESET_ROOT, 0));
+    const Rand4 r1 = rand4(rng_words(v.seed, ge, step, RP_RESET_ROOT, 1));
+    float x = c.init_root[0] + FS(F_env_origins + 0);
+    float y = c.init_root[1] + FS(F_env_origins + 1);
+    x = apply_rand(x, c.init_base_pos_xy, r0.u[0], r0.n[0]);
+    y = apply_rand(y, c.init_base_pos_xy, r0.u[1], r0.n[1]);
+    FS(F_root_states + 0) = x;
+    FS(F_root_states + 1) = y;
+    FS(F_root_states + 2) = c.init_root[2] + terr(x, y);
+    {
+        // quat_from_euler_xyz(0, 0, yaw), yaw = rand * 2 pi  (:332-336)
+        const float yaw = r0.u[2] * B200_2PI_F;
+        const float cy = cosf(yaw * 0.5f), sy = sinf(yaw * 0.5f);
+        // cr = cp = 1, sr = sp = 0  (cos(0) = 1 exactly)
+        FS(F_root_states + 3) = 0.0f;  // qx = cy*sr*cp - sy*cr*sp
+        FS(F_root_states + 4) = 0.0f;  // qy = cy*cr*sp + sy*sr*cp
+        FS(F_root_states + 5) = sy;    // qz = sy*cr*cp - cy*sr*sp
+        FS(F_root_states + 6) = cy;    // qw = cy*cr*cp + sy*sr*sp
+    }
+    FS(F_root_states + 7) = apply_rand(0.0f, c.init_base_lin_vel_xy, r1.u[0], r1.n[0]);
+    FS(F_root_states + 8) = apply_rand(0.0f, c.init_base_lin_vel_xy, r1.u[1], r1.n[1]);
+    FS(F_root_states + 9) = c.init_root[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) FS(F_root_states + 10 + r) = c.init_root[10 + r];
+    // :309-316
+#pragma unroll
+    for (int j = 0; j < 12; ++j) FS(F_last_dof_targets + j) = FS(F_dof_pos + j);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) FS(F_last_root_vel + j) = FS(F_root_states + 7 + j);
+    IS(I_episode_length_buf) = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { FS(F_filtered_lin_vel + r) = 0.0f; FS(F_filtered_ang_vel + r) = 0.0f; }
+    IS(I_cmd_resample_time) = 0;
+    const Philox4 d = rng_words(v.seed, ge, step, RP_RESET_DELAY, 0);
+    IS(I_delay_steps) = (int32_t)(d.w[0] % (uint32_t)c.decimation);
+}
+
+// envs/t1.py:362-389 (non-curriculum branch) for one env whose episode_length == cmd_resample_time
+B200_HD void env_resample_command(const EnvView& v, int e, const B200T1Config& c, uint64_t step) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+    const uint32_t ge = (uint32_t)(v.env_base + e);
+    const Philox4 w0 = rng_words(v.seed, ge, step, RP_COMMAND, 0);
+    const Philox4 w1 = rng_words(v.seed, ge, step, RP_COMMAND, 1);
+    // torch_rand_float(lo, hi) = (hi - lo) * rand + lo
+    float cx = (c.lin_vel_x[1] - c.lin_vel_x[0]) * u01(w0.w[0]) + c.lin_vel_x[0];
+    float cy = (c.lin_vel_y[1] - c.lin_vel_y[0]) * u01(w0.w[1]) + c.lin_vel_y[0];
+    float cz = (c.ang_vel_yaw[1] - c.ang_vel_yaw[0]) * u01(w0.w[2]) + c.ang_vel_yaw[0];
+    float gf = (c.gait_frequency[1] - c.gait_frequency[0]) * u01(w0.w[3]) + c.gait_frequency[0];
+    // reference: an exact still_proportion of the resampled envs via randperm (:381); here an independent Bernoulli
+    // draw per env (no cross-env dependency on the device) - DESIGN.md "deviations"
+    if (u01(w1.w[0]) < c.still_proportion) { cx = cy = cz = 0.0f; gf = 0.0f; }
+    FS(F_commands + 0) = cx; FS(F_commands + 1) = cy; FS(F_commands + 2) = cz;
+    FS(F_gait_frequency) = gf;
+    IS(I_cmd_resample_time) += c.resample_lo + (int32_t)(w1.w[1] % (uint32_t)(c.resample_hi - c.resample_lo));
+}
+
+// envs/t1.py:574-603.  obs[47], priv[14] are this env's rows.
+B200_HD void env_observations(const EnvView& v, int e, const B200T1Config& c, const TerrainView& terr, uint64_t step,
+                              int noise_on, float* obs, float* priv) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    (void)is;
+    const int n = v.n;
+    const uint32_t ge = (uint32_t)(v.env_base + e);
+    float un[36], nn[36];
+    if (noise_on) {
+#pragma unroll
+        for (int sub = 0; sub < 9; ++sub) {
+            const Rand4 r = rand4(rng_words(v.seed, ge, step, RP_OBS_NOISE, sub));
+#pragma unroll
+            for (int l = 0; l < 4; ++l) { un[4 * sub + l] = r.u[l]; nn[4 * sub + l] = r.n[l]; }
+        }
+    }
+    B200Rand off;
+    off.enabled = 0; off.dist = 0; off.op = 0; off.a = 0; off.b = 0;
+    const B200Rand& ng = noise_on ? c.noise_gravity : off;
+    const B200Rand& na = noise_on ? c.noise_ang_vel : off;
+    const B200Rand& np_ = noise_on ? c.noise_dof_pos : off;
+    const B200Rand& nv = noise_on ? c.noise_dof_vel : off;
+    const B200Rand& nl = noise_on ? c.noise_lin_vel : off;
+    const B200Rand& nh = noise_on ? c.noise_height : off;
+    if (!noise_on) {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) { un[i] = 0.0f; nn[i] = 0.0f; }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        obs[r] = apply_rand(FS(F_projected_gravity + r), ng, un[r], nn[r]) * c.norm_gravity;
+        obs[3 + r] = apply_rand(FS(F_base_ang_vel + r), na, un[3 + r], nn[3 + r]) * c.norm_ang_vel;
+    }
+    obs[6] = FS(F_commands + 0) * c.norm_lin_vel;
+    obs[7] = FS(F_commands + 1) * c.norm_lin_vel;
+    obs[8] = FS(F_commands + 2) * c.norm_ang_vel;
+    {
+        const float ph = B200_2PI_F * FS(F_gait_process);
+        const float on = (FS(F_gait_frequency) > 1.0e-8f) ? 1.0f : 0.0f;
+        obs[9] = cosf(ph) * on;
+        obs[10] = sinf(ph) * on;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        obs[11 + j] = apply_rand(FS(F_dof_pos + j) - c.default_dof_pos[j], np_, un[6 + j], nn[6 + j]) * c.norm_dof_pos;
+        obs[23 + j] = apply_rand(FS(F_dof_vel + j), nv, un[18 + j], nn[18 + j]) * c.norm_dof_vel;
+        obs[35 + j] = FS(F_actions + j);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) priv[r] = FS(F_base_mass_scaled + r);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) priv[4 + r] = apply_rand(FS(F_base_lin_vel + r), nl, un[30 + r], nn[30 + r]) * c.norm_lin_vel;
+    priv[7] = apply_rand(FS(F_root_states + 2) - terr(FS(F_root_states + 0), FS(F_root_states + 1)), nh, un[33], nn[33]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        priv[8 + r] = FS(F_pushing_forces + r) * c.norm_push_force;
+        priv[11 + r] = FS(F_pushing_torques + r) * c.norm_push_torque;
+    }
+}
+
+// envs/t1.py:343-360 (trimesh only)
+B200_HD void env_teleport(const EnvView& v, int e, const B200T1Config& c) {
+    if (c.terrain_type == 0) return;
+    float* f = v.f;
+    int32_t* is = v.is;
+    (void)is;
+    const int n = v.n;
+    const float x = FS(F_root_states + 0), y = FS(F_root_states + 1);
+    float dx = 0.0f, dy = 0.0f;
+    bool xmin = x < -0.75f * c.border_size, xmax = x > c.env_width + 0.75f * c.border_size;
+    bool ymin = y < -0.75f * c.border_size, ymax = y > c.env_length + 0.75f * c.border_size;
+    if (xmin) dx += c.env_width + c.border_size;
+    if (xmax) dx -= c.env_width + c.border_size;
+    if (ymin) dy += c.env_length + c.border_size;
+    if (ymax) dy -= c.env_length + c.border_size;
+    if (xmin || xmax) { FS(F_root_states + 0) = x + dx; FS(F_feet_pos + 0) += dx; FS(F_feet_pos + 3) += dx; }
+    if (ymin || ymax) { FS(F_root_states + 1) = y + dy; FS(F_feet_pos + 1) += dy; FS(F_feet_pos + 4) += dy; }
+}
+
+struct StepOut {
+    float rew;
+    int done, time_out;
+};
+
+// envs/t1.py:460-497 for one env.  common_step = common_step_counter after the increment (:477); step = RNG counter.
+// stats (nullable): double[1 + n_rew + 1] sums + int64 count at stats_count, accumulated with atomics on the device.
+template <typename Model>
+B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr,
+                                 int64_t common_step, uint64_t step, int noise_on, float* obs, float* priv,
+                                 float* rew_terms /* [n_rew][n] or null */) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+    const uint32_t ge = (uint32_t)(v.env_base + e);
+    // :463-473
+    float q[4] = {FS(F_root_states + 3), FS(F_root_states + 4), FS(F_root_states + 5), FS(F_root_states + 6)};
+    {
+        const float vl[3] = {FS(F_root_states + 7), FS(F_root_states + 8), FS(F_root_states + 9)};
+        const float va[3] = {FS(F_root_states + 10), FS(F_root_states + 11), FS(F_root_states + 12)};
+        const float g[3] = {0.0f, 0.0f, -1.0f};
+        float bl[3], ba[3], pg[3];
+        quat_rotate_inverse(q, vl, bl);
+        quat_rotate_inverse(q, va, ba);
+        quat_rotate_inverse(q, g, pg);
+        const float w = c.filter_weight, w1 = (float)(1.0 - (double)c.filter_weight);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            FS(F_base_lin_vel + r) = bl[r];
+            FS(F_base_ang_vel + r) = ba[r];
+            FS(F_projected_gravity + r) = pg[r];
+            FS(F_filtered_lin_vel + r) = bl[r] * w + FS(F_filtered_lin_vel + r) * w1;
+            FS(F_filtered_ang_vel + r) = ba[r] * w + FS(F_filtered_ang_vel + r) * w1;
+        }
+    }
+    env_refresh_feet(v, e, m, terr);  // :474
+    // :476-478
+    const int ep_len = IS(I_episode_length_buf) + 1;
+    IS(I_episode_length_buf) = ep_len;
+    FS(F_gait_process) = fmodf(FS(F_gait_process) + c.env_dt * FS(F_gait_frequency), 1.0f);
+    // _kick_robots :499-504
+    if (c.kick_interval > 0 && (common_step % c.kick_interval) == 0) {
+        const Rand4 a = rand4(rng_words(v.seed, ge, step, RP_KICK, 0));
+        const Rand4 b = rand4(rng_words(v.seed, ge, step, RP_KICK, 1));
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            FS(F_root_states + 7 + r) = apply_rand(FS(F_root_states + 7 + r), c.kick_lin_vel, a.u[r], a.n[r]);
+            FS(F_root_states + 10 + r) = apply_rand(FS(F_root_states + 10 + r), c.kick_ang_vel, b.u[r], b.n[r]);
+        }
+    }
+    // _push_robots :506-527
+    if (c.push_interval > 0) {
+        const int64_t ph = common_step % c.push_interval;
+        if (ph == 0) {
+            const Rand4 a = rand4(rng_words(v.seed, ge, step, RP_PUSH, 0));
+            const Rand4 b = rand4(rng_words(v.seed, ge, step, RP_PUSH, 1));
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                FS(F_pushing_forces + r) = apply_rand(0.0f, c.push_force, a.u[r], a.n[r]);
+                FS(F_pushing_torques + r) = apply_rand(0.0f, c.push_torque, b.u[r], b.n[r]);
+            }
+        } else if (ph == c.push_duration) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { FS(F_pushing_forces + r) = 0.0f; FS(F_pushing_torques + r) = 0.0f; }
+        }
+    }
+    // _check_termination :551-558
+    const float h_base = terr(FS(F_root_states + 0), FS(F_root_states + 1));
+    float vsq = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { const float t = FS(F_root_states + 7 + r); vsq += t * t; }
+    bool finite = (vsq == vsq) && (fabsf(vsq) <= 3.0e38f) && (FS(F_root_states + 2) == FS(F_root_states + 2));
+    bool reset = (vsq > c.terminate_vel) || (FS(F_root_states + 2) - h_base < c.terminate_height);
+    if (!finite) { reset = true; IS(I_nan_resets) += 1; }  // a diverged env is reset, not propagated
+    bool time_out = ep_len > c.max_episode_length;
+    reset = reset || time_out;
+    time_out = time_out || (ep_len == IS(I_cmd_resample_time));
+    IS(I_reset_buf) = reset ? 1 : 0;
+    IS(I_time_out_buf) = time_out ? 1 : 0;
+    // _compute_reward :560-572
+    float rew = 0.0f;
+    for (int k = 0; k < c.n_rew; ++k) {
+        float r = reward_term(c.rew_id[k], v, e, c, h_base) * c.rew_scale[k];
+        if (!finite) r = 0.0f;
+        rew += r;
+        if (rew_terms) rew_terms[(size_t)k * (size_t)n + (size_t)e] = r;
+        FS(F_episode_sums + 1 + k) += r;
+    }
+    if (c.only_positive_rewards) rew = fmaxf(rew, 0.0f);
+    FS(F_episode_sums + 0) += rew;
+    IS(I_episode_steps) += 1;
+    // :485-488
+    if (reset) env_reset_one(v, e, c, terr, step);
+    env_teleport(v, e, c);
+    if (IS(I_episode_length_buf) == IS(I_cmd_resample_time)) env_resample_command(v, e, c, step);
+    // :490
+    env_observations(v, e, c, terr, step, noise_on, obs, priv);
+    // :492-495
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { FS(F_last_actions + j) = FS(F_actions + j); FS(F_last_dof_vel + j) = FS(F_dof_vel + j); }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { FS(F_last_root_vel + j) = FS(F_root_states + 7 + j); FS(F_last_feet_pos + j) = FS(F_feet_pos + j); }
+    StepOut o;
+    o.rew = rew;
+    o.done = reset ? 1 : 0;
+    o.time_out = time_out ? 1 : 0;
+    return o;
+}
+
+// One-off per-env model randomisation + buffer initialisation: envs/t1.py:69-83,139-167,187-272.
+template <typename Model>
+B200_HD void env_init_params(const EnvView& v, int e, const Model& m, const B200T1Config& c) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+    const uint32_t ge = (uint32_t)(v.env_base + e);
+#pragma unroll
+    for (int sub = 0; sub < 3; ++sub) {
+        const Rand4 a = rand4(rng_words(v.seed, ge, 0, RP_INIT_GAINS, sub));
+        const Rand4 b = rand4(rng_words(v.seed, ge, 0, RP_INIT_GAINS, 3 + sub));
+        const Rand4 d = rand4(rng_words(v.seed, ge, 0, RP_INIT_GAINS, 6 + sub));
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int j = 4 * sub + l;
+            FS(F_dof_stiffness + j) = apply_rand(c.kp_nominal[j], c.dof_stiffness, a.u[l], a.n[l]);
+            FS(F_dof_damping + j) = apply_rand(c.kd_nominal[j], c.dof_damping, b.u[l], b.n[l]);
+            FS(F_dof_friction + j) = apply_rand(0.0f, c.dof_friction, d.u[l], d.n[l]);
+        }
+    }
+    for (int b = 0; b < B200_NB; ++b) {
+        const Rand4 r = rand4(rng_words(v.seed, ge, 0, RP_INIT_BODY, b));
+        const B200Rand& rc = (b == 0) ? c.base_com : c.other_com;
+        const B200Rand& rm = (b == 0) ? c.base_mass : c.other_mass;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) FS(F_body_com + 3 * b + k) = apply_rand((float)m.ipos[b][k], rc, r.u[k], r.n[k]);
+        FS(F_body_mass + b) = apply_rand((float)m.mass[b], rm, r.u[3], r.n[3]);
+        if (b == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) FS(F_base_mass_scaled + k) = rc.enabled ? raw_rand(rc, r.u[k], r.n[k]) : 0.0f;
+            FS(F_base_mass_scaled + 3) = rm.enabled ? raw_rand(rm, r.u[3], r.n[3]) : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const Rand4 r = rand4(rng_words(v.seed, ge, 0, RP_INIT_FOOT, k));
+        // PhysX material of the foot shapes (envs/t1.py:162-167): friction is combined with the ground by averaging
+        // (PhysX default combine mode); compliance / restitution scale this build's contact spring / damper.
+        const float mu_foot = c.friction.enabled ? apply_rand(0.0f, c.friction, r.u[0], r.n[0]) : c.terrain_friction;
+        FS(F_foot_friction + k) = 0.5f * (mu_foot + c.terrain_friction);
+        const float comp = c.compliance.enabled ? apply_rand(0.0f, c.compliance, r.u[1], r.n[1]) : 1.0f;
+        FS(F_foot_kscale + k) = 1.0f / fmaxf(comp, 0.1f);
+        const float rest = c.restitution.enabled ? apply_rand(0.0f, c.restitution, r.u[2], r.n[2]) : 0.0f;
+        FS(F_foot_cscale + k) = 1.0f - 0.5f * fminf(fmaxf(rest, 0.0f), 1.0f);
+    }
+    // _init_buffers :193-272 (the values a freshly created sim reports: identity pose at the env origin, at rest)
+#pragma unroll
+    for (int r = 0; r < 13; ++r) FS(F_root_states + r) = c.init_root[r];
+    FS(F_root_states + 0) += FS(F_env_origins + 0);
+    FS(F_root_states + 1) += FS(F_env_origins + 1);
+    FS(F_root_states + 2) += FS(F_env_origins + 2);
+    const int zero_rows[] = {F_dof_pos, F_dof_vel, F_actions, F_last_actions, F_last_dof_vel, F_last_dof_targets, F_torques};
+    for (int zr = 0; zr < 7; ++zr)
+        for (int j = 0; j < 12; ++j) FS(zero_rows[zr] + j) = 0.0f;
+    for (int j = 0; j < 6; ++j) { FS(F_last_root_vel + j) = 0.0f; FS(F_feet_pos + j) = 0.0f; FS(F_last_feet_pos + j) = 0.0f; }
+    for (int j = 0; j < 8; ++j) FS(F_feet_quat + j) = (j % 4 == 3) ? 1.0f : 0.0f;
+    for (int r = 0; r < 3; ++r) {
+        FS(F_commands + r) = 0.0f; FS(F_base_lin_vel + r) = 0.0f; FS(F_base_ang_vel + r) = 0.0f;
+        FS(F_projected_gravity + r) = (r == 2) ? -1.0f : 0.0f;
+        FS(F_filtered_lin_vel + r) = 0.0f; FS(F_filtered_ang_vel + r) = 0.0f;
+        FS(F_pushing_forces + r) = 0.0f; FS(F_pushing_torques + r) = 0.0f;
+    }
+    FS(F_gait_frequency) = 0.0f; FS(F_gait_process) = 0.0f;
+    for (int k = 0; k < 2; ++k) { FS(F_feet_roll + k) = 0.0f; FS(F_feet_yaw + k) = 0.0f; FS(F_feet_force + k) = 0.0f; IS(I_feet_contact + k) = 0; }
+    for (int k = 0; k < 27; ++k) FS(F_episode_sums + k) = 0.0f;
+    IS(I_episode_length_buf) = 0; IS(I_cmd_resample_time) = 0; IS(I_delay_steps) = 0;
+    IS(I_reset_buf) = 1; IS(I_time_out_buf) = 0; IS(I_episode_steps) = 0; IS(I_nan_resets) = 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,63 @@
+// hostcheck.cpp - TEST-ONLY host build of the shared __host__ __device__ kernel bodies (csrc/*.cuh).
+// Lets `pytest -m "not gpu"` exercise the exact arithmetic the CUDA kernels run, in float and double, against
+// oracle/ without a GPU.  Never loaded by the product package (booster_gym_b200/_lib.py only loads libb200t1.so).
+#include <string.h>
+
+#include "../../booster_gym_b200/csrc/t1_dynamics.cuh"
+#include "../../booster_gym_b200/csrc/terrain.cuh"
+
+using namespace b200;
+
+template <typename T> struct FlatEnv {  // mirrors oracle T1OEnv field order, in scalar type T
+    T pos[3], quat[4], vlin[3], wb[3], q[12], qd[12];
+    T mass[B200_NB], com[B200_NB][3];
+    T mu[2], kscale[2], cscale[2];
+};
+
+template <typename T, typename Model>
+static int tick_impl(const Model* m, FlatEnv<T>* e, const T* tau, const T* push_f, const T* push_t, const int16_t* hf,
+                     int rows, int cols, int border_pixels, float hscale, double vscale, T* qacc, T* foot_fn,
+                     int integrate) {
+    DynState<T> s;
+    DynParams<T> p;
+    memcpy(s.pos, e->pos, sizeof(T) * 3); memcpy(s.quat, e->quat, sizeof(T) * 4);
+    memcpy(s.vlin, e->vlin, sizeof(T) * 3); memcpy(s.wb, e->wb, sizeof(T) * 3);
+    memcpy(s.q, e->q, sizeof(T) * 12); memcpy(s.qd, e->qd, sizeof(T) * 12);
+    memcpy(p.mass, e->mass, sizeof(p.mass)); memcpy(p.com, e->com, sizeof(p.com));
+    memcpy(p.mu, e->mu, sizeof(p.mu)); memcpy(p.kscale, e->kscale, sizeof(p.kscale)); memcpy(p.cscale, e->cscale, sizeof(p.cscale));
+    TerrainView tv{hf, rows, cols, border_pixels, hscale, vscale};
+    MLocal<T> M;
+    DynAux<T> aux;
+    t1_tick<T>(*m, p, s, tau, push_f, push_t, tv, M, aux, integrate != 0);
+    memcpy(e->pos, s.pos, sizeof(T) * 3); memcpy(e->quat, s.quat, sizeof(T) * 4);
+    memcpy(e->vlin, s.vlin, sizeof(T) * 3); memcpy(e->wb, s.wb, sizeof(T) * 3);
+    memcpy(e->q, s.q, sizeof(T) * 12); memcpy(e->qd, s.qd, sizeof(T) * 12);
+    if (qacc) memcpy(qacc, aux.qacc, sizeof(T) * B200_NV);
+    if (foot_fn) { foot_fn[0] = aux.foot_fn[0]; foot_fn[1] = aux.foot_fn[1]; }
+    return 0;
+}
+
+extern "C" {
+int hc_tick_d(const B200T1ModelD* m, void* env, const double* tau, const double* push_f, const double* push_t,
+              const int16_t* hf, int rows, int cols, int border_pixels, float hscale, double vscale, double* qacc,
+              double* foot_fn, int integrate) {
+    return tick_impl<double>(m, (FlatEnv<double>*)env, tau, push_f, push_t, hf, rows, cols, border_pixels, hscale, vscale, qacc, foot_fn, integrate);
+}
+int hc_tick_f(const B200T1ModelF* m, void* env, const float* tau, const float* push_f, const float* push_t,
+              const int16_t* hf, int rows, int cols, int border_pixels, float hscale, double vscale, float* qacc,
+              float* foot_fn, int integrate) {
+    return tick_impl<float>(m, (FlatEnv<float>*)env, tau, push_f, push_t, hf, rows, cols, border_pixels, hscale, vscale, qacc, foot_fn, integrate);
+}
+float hc_terrain_height(const int16_t* hf, int rows, int cols, int border_pixels, float hscale, double vscale, float x, float y) {
+    TerrainView tv{hf, rows, cols, border_pixels, hscale, vscale};
+    return tv(x, y);
+}
+void hc_feet_d(const B200T1ModelD* m, void* env, double* pos, double* quat) {
+    FlatEnv<double>* e = (FlatEnv<double>*)env;
+    DynState<double> s;
+    memcpy(s.pos, e->pos, 24); memcpy(s.quat, e->quat, 32); memcpy(s.q, e->q, 96);
+    double fp[2][3], fq[2][4];
+    t1_feet_fk<double>(*m, s, fp, fq);
+    memcpy(pos, fp, sizeof fp); memcpy(quat, fq, sizeof fq);
+}
+}
