@@ -6,7 +6,7 @@ This is the binding a maintainer of the reference would add: th
 import ctypes as C
 
 NB, NV, NQ, NU, NCON, NOBS, NPRIV, MAX_REW = 13, 18, 19, 12, 8, 47, 14, 26
-NPARAMS, ACTOR_PARAMS, CRITIC_PARAMS = 177945, 63244, 114689
+NPARAMS, NPARAMS_PADDED, ACTOR_PARAMS, CRITIC_PARAMS = 177945, 177948, 63244, 114689
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
@@ -18,7 +18,10 @@ REW_NAMES = [  # enum order of B200_REW_* (envs/t1.py:606-730)
 ]
 
 SC = dict(LR=0, ADAM_STEP=1, VALUE_LOSS=2, ACTOR_LOSS=3, BOUND_LOSS=4, ENTROPY=5, KL=6, ADV_MEAN=7, ADV_STD=8,
-          GRAD_NORM=9, COUNT=32)
+          GRAD_NORM=9, SUM_VALUE_LOSS=10, SUM_ACTOR_LOSS=11, SUM_BOUND_LOSS=12, SUM_ENTROPY=13, EPOCHS=14,
+          OLD_LOGSTD=16, COUNT=32)
+DS = dict(ADV_SUM=0, ADV_SUMSQ=1, ADV_COUNT=2, VALUE_LOSS=4, ACTOR_LOSS=5, BOUND_LOSS=6, ENTROPY=7, KL=8, SAMPLES=9,
+          GRAD_SQ=10, DLOGSTD=16, COUNT=32)
 
 
 def _model_fields(real):
@@ -70,16 +73,19 @@ class T1Config(C.Structure):
         ("dof_vel_limits", C.c_float * NU), ("torque_limits", C.c_float * NU),
         ("penalized_body_mask", C.c_int32), ("termination_body_mask", C.c_int32),
         ("terrain_type", C.c_int32), ("border_pixels", C.c_int32),
-        ("horizontal_scale", C.c_float), ("vertical_scale", C.c_float), ("env_width", C.c_float),
+        ("horizontal_scale", C.c_float), ("env_width", C.c_float),
         ("env_length", C.c_float), ("border_size", C.c_float), ("terrain_friction", C.c_float), ("pad1", C.c_int32),
+        ("pad2", C.c_int32), ("vertical_scale", C.c_double),
     ]
 
 
 class PpoConfig(C.Structure):
     _fields_ = [
-        ("gamma", C.c_float), ("lam", C.c_float), ("e_clip", C.c_float), ("bound_coef", C.c_float),
+        ("gamma", C.c_double), ("lam", C.c_double),
+        ("e_clip", C.c_float), ("bound_coef", C.c_float),
         ("entropy_coef", C.c_float), ("desired_kl", C.c_float), ("max_grad_norm", C.c_float),
         ("lr_min", C.c_float), ("lr_max", C.c_float), ("lr_factor", C.c_float),
         ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
-        ("horizon", C.c_int32), ("num_envs", C.c_int32), ("world_size", C.c_int32),
+        ("horizon", C.c_int32), ("num_envs", C.c_int32), ("world_size", C.c_int32), ("env_base", C.c_int32),
+        ("pad0", C.c_int32),
     ]

@@ -1,0 +1,83 @@
+"""In-tree build of libb200t1.so (the C-ABI shared library of include/b200_t1.h) with nvcc for sm_100a.
+
+The `.so` is git-ignored but lives in the tree (booster_gym_b200/libb200t1.so) so that it travels to the GPU box with
+the repo snapshot.  There is no JIT and no fallback: if the library is missing on a machine without nvcc the package
+raises at import of `_lib`.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libb200t1.so")
+OBJ_DIR = os.path.join(ROOT, "build", "obj")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
+          "-diag-suppress", "550,177"]
+
+# translation unit -> extra flags
+UNITS = {
+    "common.cu": [],
+    "physics_kernels.cu": [],                   # FP32-pipe bound: keep FMA contraction
+    "env_kernels.cu": ["--fmad=false"],         # rounds like the reference's separate torch ops (bit-exact masks)
+    "learner_kernels.cu": [],
+}
+
+
+def _nvcc():
+    nv = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nv):
+        raise RuntimeError("nvcc not found: libb200t1.so cannot be built on this machine")
+    return nv
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "b200_t1.h")]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False, ptxas_info=False):
+    """Compile every CUDA translation unit for sm_100a and link libb200t1.so. Returns the library path."""
+    units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u))]
+    deps = _deps()
+    if not force and not _stale(LIB, deps):
+        return LIB
+    nv = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = []
+    procs = []
+    for u in units:
+        src = os.path.join(CSRC, u)
+        obj = os.path.join(OBJ_DIR, u.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and not _stale(obj, deps):
+            continue
+        cmd = [nv] + ARCH + COMMON + UNITS[u] + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        procs.append((u, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for u, p in procs:
+        out, _ = p.communicate()
+        if ptxas_info or verbose or p.returncode != 0:
+            sys.stdout.write(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {u}")
+    cmd = [nv] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))

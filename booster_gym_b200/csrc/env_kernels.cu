@@ -1,91 +1,17 @@
-// env_kernels.cu - CUDA kernels + C-ABI for the T1 environment step (include/b200_t1.h, "env" half).
-//
-// Mapping: ONE THREAD PER ENVIRONMENT over structure-of-arrays state (coalesced rows).  The physics kernel runs
-// the whole decimated loop (10 ticks of FK/CRBA/RNE/LTDL/contact, t1_dynamics.cuh) with the 18x18 mass matrix of each
-// thread in shared memory (interleaved by lane: bank-conflict free), one warp per CTA so that N = 4096 envs spread
-// over 128 of the 148 SMs.  Model and config travel as __grid_constant__ kernel parameters (constant bank, so the
-// FFMA pipe reads them as immediate-like operands instead of issuing loads).
+// env_kernels.cu - CUDA kernels + C-ABI for the T1 environment step (include/b200_t1.h, "env" half) except the physics
+// loop (physics_kernels.cu): K2 post-physics (derived state, feet, kicks/pushes, termination, 23 reward terms, reset,
+// command resampling, observations) and K3 reset/DR, one thread per environment over structure-of-arrays rows.
+// Compiled with --fmad=false: every fp32 operation rounds separately, like the reference's eager torch ops, which is
+// what makes the masks (feet_contact, reset, dof_pos_limits counts) bit-exact.  These passes are HBM-bound.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <new>
 
-#include "common.cuh"
-#include "t1_env.cuh"
+#include "env_handle.cuh"
 
 using namespace b200;
-
-struct B200T1Handle {
-    B200T1ModelF model;
-    B200T1Config cfg;
-    int num_envs, device;
-    uint64_t seed;
-    int env_base, total_envs;
-    float* fstate;
-    int32_t* istate;
-    int16_t* hf_dev;
-    int hf_rows, hf_cols;
-    long long* ctr_dev;   // [0] rng step, [1] common_step_counter, [2..3] any-reset flags (parity)
-    double* stats_dev;    // [1 + n_rew + 1] episode sums, then count as double
-};
-
-static TerrainView make_terrain(const B200T1Handle* h) {
-    TerrainView t;
-    t.hf = (h->cfg.terrain_type == 0) ? nullptr : h->hf_dev;
-    t.rows = h->hf_rows;
-    t.cols = h->hf_cols;
-    t.border_pixels = h->cfg.border_pixels;
-    t.horizontal_scale = h->cfg.horizontal_scale;
-    t.vertical_scale = (double)h->cfg.vertical_scale;
-    return t;
-}
-static EnvView make_view(const B200T1Handle* h) {
-    EnvView v;
-    v.f = h->fstate;
-    v.is = h->istate;
-    v.n = h->num_envs;
-    v.env_base = h->env_base;
-    v.seed = h->seed;
-    return v;
-}
-
-// ---- mass-matrix storage in shared memory: element idx of lane l at sm[idx * 32 + l] -------------------------------
-struct MShared {
-    float* base;
-    __device__ __forceinline__ float& operator()(int i, int j) { return base[(i * (i + 1) / 2 + j) * PHYS_BLOCK]; }
-};
-
-__global__ void __launch_bounds__(PHYS_BLOCK)
-k_physics(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c, TerrainView terr,
-          const float* __restrict__ actions, int n_substeps, int apply_pd, float* __restrict__ qacc_out,
-          long long* ctr, long long common_step, int advance) {
-    __shared__ float sM[PHYS_BLOCK * (B200_NV * (B200_NV + 1) / 2)];
-    if (advance && blockIdx.x == 0 && threadIdx.x == 0) {
-        // start of a T1.step(): common_step_counter += 1 (envs/t1.py:477), new RNG epoch, clear the stale any-reset flag
-        ctr[1] = (common_step >= 0) ? common_step : ctr[1] + 1;
-        const long long s = ctr[0] + 1;
-        ctr[0] = s;
-        ctr[2 + ((s + 1) & 1)] = 0;
-    }
-    const int e = blockIdx.x * PHYS_BLOCK + threadIdx.x;
-    if (e >= v.n) return;
-    MShared M;
-    M.base = sM + threadIdx.x;
-    float act[12];
-    const float4* a4 = reinterpret_cast<const float4*>(actions + (size_t)e * 12);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float4 t = a4[k];
-        act[4 * k] = t.x; act[4 * k + 1] = t.y; act[4 * k + 2] = t.z; act[4 * k + 3] = t.w;
-    }
-    float qacc[B200_NV];
-    env_physics(v, e, m, c, terr, act, n_substeps, apply_pd, M, qacc_out ? qacc : nullptr);
-    if (qacc_out) {
-#pragma unroll
-        for (int i = 0; i < B200_NV; ++i) qacc_out[(size_t)i * v.n + e] = qacc[i];
-    }
-}
 
 __global__ void k_advance(long long* ctr, long long common_step, int bump_common) {
     if (bump_common) ctr[1] = (common_step >= 0) ? common_step : ctr[1] + 1;
@@ -296,9 +222,7 @@ int b200_t1_physics(B200T1Handle* h, const float* actions, int n_substeps, int a
     NEED_STATE(h);
     if (!actions || n_substeps < 0) return set_error(B200_ERR_ARG, "b200_t1_physics: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    k_physics<<<(h->num_envs + PHYS_BLOCK - 1) / PHYS_BLOCK, PHYS_BLOCK, 0, st>>>(
-        make_view(h), h->model, h->cfg, make_terrain(h), actions, n_substeps, apply_pd, qacc_out, h->ctr_dev, -1, 0);
-    return launch_status("k_physics");
+    return launch_physics(h, actions, n_substeps, apply_pd, qacc_out, -1, 0, st);
 }
 
 static int launch_post(B200T1Handle* h, float* obs, float* priv, float* rew, uint8_t* done, uint8_t* time_out,
@@ -324,9 +248,8 @@ int b200_t1_step(B200T1Handle* h, const float* actions, float* obs, float* priv,
     NEED_STATE(h);
     if (!actions || !obs || !priv || !rew || !done || !time_out) return set_error(B200_ERR_ARG, "b200_t1_step: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    k_physics<<<(h->num_envs + PHYS_BLOCK - 1) / PHYS_BLOCK, PHYS_BLOCK, 0, st>>>(
-        make_view(h), h->model, h->cfg, make_terrain(h), actions, h->cfg.decimation, 1, nullptr, h->ctr_dev,
-        (long long)common_step, 1);
+    const int rc = launch_physics(h, actions, h->cfg.decimation, 1, nullptr, (long long)common_step, 1, st);
+    if (rc != B200_OK) return rc;
     return launch_post(h, obs, priv, rew, done, time_out, rew_terms, 1, st);
 }
 

@@ -29,6 +29,9 @@ struct GemmArgs {
     int r_valid_b;      // reduction indices >= this read B as 0 (K = 47/61 of a padded X); <=0 = R
 };
 
+#ifndef G_ACC_SPLIT
+#define G_ACC_SPLIT 1
+#endif
 #define G_BM 128
 #define G_BN 128
 #define G_BK 32
@@ -182,9 +185,21 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm3x(const GemmArgs g) {
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
+#if G_ACC_SPLIT
+                    // the tensor core adds into its fp32 accumulator with truncation; keeping each k-step's partial sum
+                    // in a fresh accumulator and adding it with a round-to-nearest FADD removes the bias that otherwise
+                    // grows linearly with the reduction length (measured: 8x the fp32 SGEMM error at K = 256)
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_tf32(t, al[mi], bh[ni]);
+                    mma_tf32(t, ah[mi], bl[ni]);
+                    mma_tf32(t, ah[mi], bh[ni]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[mi][ni][q] += t[q];
+#else
                     mma_tf32(acc[mi][ni], al[mi], bh[ni]);
                     mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
                     mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
+#endif
                 }
         }
         if (kt + 1 < nk) store_tiles(buf ^ 1);

@@ -1,0 +1,692 @@
+// learner_kernels.cu - the PPO learner half of include/b200_t1.h: actor/critic MLPs (utils/model.py:9-36), rollout
+// action sampling (utils/runner.py:109-111), GAE with time-out bootstrap (utils/utils.py:33-44, utils/runner.py:135-145),
+// the full-batch epoch body with all five loss terms and their hand-derived backward (utils/runner.py:146-161), and
+// clip_grad_norm_ + Adam + KL-adaptive learning rate (utils/runner.py:162-180) - all device-resident, no host sync.
+//
+// Dense contractions go through k_gemm3x (gemm3x.cuh): tensor-core TF32 MMAs with an error-compensated 3-term split so
+// results stay within fp32 rounding of the reference's SGEMM (parity bar 1e-5 relative).  Activations are kept in a
+// caller-provided workspace, [M, width] row-major, post-ELU (ELU' = h > 0 ? 1 : h + 1 needs no pre-activation copy).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "gemm3x.cuh"
+#include "rng.cuh"
+
+using namespace b200;
+
+// ---- flat parameter layout: state_dict tensors in the order critic.*, actor.*, logstd, each start 16-byte aligned ----
+struct ParamEntry {
+    const char* name;
+    int offset, rows, cols;
+};
+static const ParamEntry kParams[] = {
+    {"critic.0.weight", 0, 256, 61},      {"critic.0.bias", 15616, 256, 1},   {"critic.2.weight", 15872, 256, 256},
+    {"critic.2.bias", 81408, 256, 1},     {"critic.4.weight", 81664, 128, 256}, {"critic.4.bias", 114432, 128, 1},
+    {"critic.6.weight", 114560, 1, 128},  {"critic.6.bias", 114688, 1, 1},    {"actor.0.weight", 114692, 256, 47},
+    {"actor.0.bias", 126724, 256, 1},     {"actor.2.weight", 126980, 128, 256}, {"actor.2.bias", 159748, 128, 1},
+    {"actor.4.weight", 159876, 128, 128}, {"actor.4.bias", 176260, 128, 1},   {"actor.6.weight", 176388, 12, 128},
+    {"actor.6.bias", 177924, 12, 1},      {"logstd", 177936, 1, 12},
+};
+enum { P_CW0 = 0, P_CB0, P_CW1, P_CB1, P_CW2, P_CB2, P_CW3, P_CB3, P_AW0, P_AB0, P_AW1, P_AB1, P_AW2, P_AB2, P_AW3, P_AB3, P_LOGSTD, P_COUNT };
+#define NPARAMS_PADDED 177948
+
+// double accumulators (caller-owned device double[32], "dstats"): the allreduce targets of a multi-GPU run
+// [0..3] advantage moments (all-reduced between epoch_a and epoch_b), [4..9] loss sums + sample count (all-reduced with
+// the gradient), [10] local sum of squared gradients, [16..27] d loss / d logstd.  Cleared at the start of every epoch.
+enum { DS_ADV_SUM = B200_DS_ADV_SUM, DS_ADV_SUMSQ = B200_DS_ADV_SUMSQ, DS_ADV_COUNT = B200_DS_ADV_COUNT, DS_VALUE_LOSS = B200_DS_VALUE_LOSS,
+       DS_ACTOR_LOSS = B200_DS_ACTOR_LOSS, DS_BOUND_LOSS = B200_DS_BOUND_LOSS, DS_ENTROPY = B200_DS_ENTROPY, DS_KL = B200_DS_KL,
+       DS_SAMPLES = B200_DS_SAMPLES, DS_GRAD_SQ = B200_DS_GRAD_SQ, DS_DLOGSTD = B200_DS_DLOGSTD, DS_COUNT = B200_DS_COUNT };
+
+struct Workspace {  // offsets in floats
+    size_t Xa, Xc, C1, C2, C3, V, A1, A2, A3, MU, ADV, RET, DV, DMU, G1, G2;
+    size_t LXa, LXc, L1, L2, L3, LV, LMU;
+    size_t total;
+};
+static Workspace make_workspace(int T, int N) {
+    Workspace w;
+    const size_t M = (size_t)T * N, n = (size_t)N;
+    size_t o = 0;
+    auto take = [&](size_t cnt) { size_t r = o; o += (cnt + 63) & ~(size_t)63; return r; };
+    w.Xa = take(M * 48); w.Xc = take(M * 64);
+    w.C1 = take(M * 256); w.C2 = take(M * 256); w.C3 = take(M * 128); w.V = take(M);
+    w.A1 = take(M * 256); w.A2 = take(M * 128); w.A3 = take(M * 128); w.MU = take(M * 12);
+    w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
+    w.G1 = take(M * 256); w.G2 = take(M * 256);
+    w.LXa = take(n * 48); w.LXc = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
+    w.LV = take(n); w.LMU = take(n * 12);
+    w.total = o;
+    return w;
+}
+
+struct B200Ppo {
+    B200PpoConfig cfg;
+    int device;
+    float *params, *grads, *adam_m, *adam_v, *scalars;
+    double* dstats;
+    float* ws;
+    Workspace w;
+    float* P(int i) const { return params + kParams[i].offset; }
+    float* G(int i) const { return grads + kParams[i].offset; }
+};
+
+// =====================================================================================================================
+// small kernels
+// =====================================================================================================================
+
+// obs [n,47] (+ priv [n,14]) -> zero-padded GEMM operands Xa [n,48], Xc [n,64] (either output may be null)
+__global__ void k_pack_inputs(const float* __restrict__ obs, const float* __restrict__ priv, int n, float* __restrict__ Xa,
+                              float* __restrict__ Xc) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * 64;
+    if (idx >= total) return;
+    const size_t r = idx >> 6;
+    const int c = (int)(idx & 63);
+    float v = 0.0f;
+    if (c < 47) v = obs[r * 47 + c];
+    else if (c < 61 && priv) v = priv[r * 14 + (c - 47)];
+    if (Xc) Xc[idx] = v;
+    if (Xa && c < 48) Xa[r * 48 + c] = (c < 47) ? v : 0.0f;
+}
+
+// critic head: V[m] = b + sum_k H[m,k] w[k], one warp per row (H rows are 128 floats = one float4 per lane)
+__global__ void k_value_head(const float* __restrict__ H, const float* __restrict__ w, const float* __restrict__ b, int n,
+                             float* __restrict__ V) {
+    const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const float4 h = reinterpret_cast<const float4*>(H + (size_t)warp * 128)[lane];
+    const float4 ww = reinterpret_cast<const float4*>(w)[lane];
+    float s = h.x * ww.x + h.y * ww.y + h.z * ww.z + h.w * ww.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) V[warp] = s + b[0];
+}
+
+// backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m]
+#define VH_ROWS 128
+__global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict__ H, const float* __restrict__ w,
+                                                        const float* __restrict__ dV, int n, float* __restrict__ dH,
+                                                        float* __restrict__ dw, float* __restrict__ db) {
+    const int k = threadIdx.x;
+    const int r0 = blockIdx.x * VH_ROWS, r1 = min(n, r0 + VH_ROWS);
+    const float wk = w[k];
+    double acc = 0.0, accb = 0.0;  // fp64 partial sums: these are 98k-term reductions judged at 1e-5 relative
+    for (int r = r0; r < r1; ++r) {
+        const float g = dV[r];
+        const float h = H[(size_t)r * 128 + k];
+        dH[(size_t)r * 128 + k] = g * wk * ((h > 0.0f) ? 1.0f : (h + 1.0f));
+        acc += (double)g * (double)h;
+        accb += (double)g;
+    }
+    atomicAdd(dw + k, (float)acc);
+    if (k == 0) atomicAdd(db, (float)accb);
+}
+
+// bias gradient: db[c] += sum over rows of dY[r,c]   (C <= 256; 256 threads, rows split over blockDim/Cp row-lanes)
+#define CS_ROWS 1024
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, int n, int C, int ld, float* __restrict__ db) {
+    __shared__ double red[256];
+    int Cp = 1;
+    while (Cp < C) Cp <<= 1;           // 16, 128 or 256
+    const int lanes = 256 / Cp;
+    const int c = threadIdx.x % Cp, rl = threadIdx.x / Cp;
+    const int r0 = blockIdx.x * CS_ROWS, r1 = min(n, r0 + CS_ROWS);
+    double acc = 0.0;
+    if (c < C)
+        for (int r = r0 + rl; r < r1; r += lanes) acc += (double)dY[(size_t)r * ld + c];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        double s = 0.0;
+        for (int l = 0; l < lanes; ++l) s += red[l * Cp + c];
+        atomicAdd(db + c, (float)s);
+    }
+}
+
+// rollout sampling (utils/runner.py:110-111): act = mu + exp(logstd) * eps
+__global__ void k_sample(const float* __restrict__ mu, const float* __restrict__ logstd, const float* __restrict__ eps_in,
+                         int n, uint64_t seed, uint64_t step, int env_base, int deterministic, float* __restrict__ act,
+                         float* __restrict__ mu_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float eps[12];
+    if (deterministic) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) eps[j] = 0.0f;
+    } else if (eps_in) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) eps[j] = eps_in[(size_t)e * 12 + j];
+    } else {
+#pragma unroll
+        for (int sub = 0; sub < 3; ++sub) {
+            const Rand4 r = rand4(rng_words(seed, (uint32_t)(env_base + e), step, RP_POLICY, sub));
+#pragma unroll
+            for (int l = 0; l < 4; ++l) eps[4 * sub + l] = r.n[l];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const float m = mu[(size_t)e * 12 + j];
+        const float a = deterministic ? m : __fadd_rn(m, __fmul_rn(expf(logstd[j]), eps[j]));
+        act[(size_t)e * 12 + j] = a;
+        if (mu_out) mu_out[(size_t)e * 12 + j] = m;
+    }
+}
+
+#define LOG_SQRT_2PI 0.91893853320467274178f
+
+// Normal(mu, exp(logstd)).log_prob(a).sum(-1)  (torch.distributions.Normal.log_prob, summed left to right)
+__device__ __forceinline__ float normal_logp12(const float* a, const float* mu, const float* sigma, const float* log_sigma) {
+    float lp = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const float d = __fsub_rn(a[j], mu[j]);
+        const float var = __fmul_rn(sigma[j], sigma[j]);
+        const float t = __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.0f, var)), log_sigma[j]), LOG_SQRT_2PI);
+        lp = __fadd_rn(lp, t);
+    }
+    return lp;
+}
+
+// utils/runner.py:123-125: log-prob of the stored actions under the pre-update policy; also snapshots logstd
+__global__ void k_old_logp(const float* __restrict__ mu, const float* __restrict__ actions, const float* __restrict__ logstd,
+                           int M, float* __restrict__ old_mu, float* __restrict__ old_logp, float* __restrict__ scalars) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m == 0) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) scalars[B200_SC_OLD_LOGSTD + j] = logstd[j];
+    }
+    if (m >= M) return;
+    float a[12], u[12], sg[12], ls[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        a[j] = actions[(size_t)m * 12 + j];
+        u[j] = mu[(size_t)m * 12 + j];
+        sg[j] = expf(logstd[j]);
+        ls[j] = logf(sg[j]);
+        old_mu[(size_t)m * 12 + j] = u[j];
+    }
+    old_logp[m] = normal_logp12(a, u, sg, ls);
+}
+
+// utils/runner.py:135-144 + utils/utils.py:33-44: one thread per env walks t = T-1..0.
+//   rewards[time_outs] = values[time_outs] (in place); done = done | time_out;
+//   delta = r + gamma*nnt*V[t+1] - V[t];  A[t] = delta + gamma*lam*nnt*A[t+1];  returns = V + A
+// and accumulates sum / sum of squares / count of the raw advantages (double) for the normalisation of :145.
+__global__ void __launch_bounds__(128) k_gae(float* __restrict__ rewards, const uint8_t* __restrict__ dones,
+                                             const uint8_t* __restrict__ time_outs, const float* __restrict__ values,
+                                             const float* __restrict__ last_values, float gamma, float gamma_lam, int T,
+                                             int N, float* __restrict__ adv, float* __restrict__ ret,
+                                             double* __restrict__ stats) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0, s2 = 0.0;
+    if (e < N) {
+        float next_v = last_values[e], last_adv = 0.0f;
+        for (int t = T - 1; t >= 0; --t) {
+            const size_t i = (size_t)t * N + e;
+            const float v = values[i];
+            const bool to = time_outs[i] != 0;
+            float r = rewards[i];
+            if (to) { r = v; rewards[i] = v; }
+            const float nnt = (dones[i] != 0 || to) ? 0.0f : 1.0f;
+            const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nnt), next_v)), v);
+            last_adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last_adv));
+            adv[i] = last_adv;
+            ret[i] = __fadd_rn(v, last_adv);
+            s += (double)last_adv;
+            s2 += (double)last_adv * (double)last_adv;
+            next_v = v;
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        __shared__ double sh[2][4];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) { sh[0][warp] = s; sh[1][warp] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0, b = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; }
+            atomicAdd(stats + DS_ADV_SUM, a);
+            atomicAdd(stats + DS_ADV_SUMSQ, b);
+            if (blockIdx.x == 0) atomicAdd(stats + DS_ADV_COUNT, (double)T * (double)N);
+        }
+    }
+}
+
+// Loss terms of utils/runner.py:146-161 and their gradients w.r.t. V, mu and logstd, one thread per sample.
+//   value_loss = mean((V - returns)^2)                      dV   = 2 (V - returns) / M
+//   ratio = exp(logp - old_logp); actor = mean(max(-A ratio, -A clamp(ratio, 1-e, 1+e)))   (utils/utils.py:47-52)
+//   bound = mean(relu(mu - 1)^2) + mean(min(mu + 1, 0)^2) over M*12 elements
+//   entropy = sum_j(0.5 + 0.5 log 2pi + logstd_j);  loss += entropy_coef * mean(entropy)
+//   kl = sum_j [log(sigma/sigma_old) + (sigma_old^2 + (mu - mu_old)^2) / (2 sigma^2) - 0.5]    (no gradient)
+#define LOSS_BLOCK 256
+#define LOSS_NRED (6 + 12)
+__global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V, const float* __restrict__ ret,
+                                                     const float* __restrict__ adv, const float* __restrict__ mu,
+                                                     const float* __restrict__ actions, const float* __restrict__ old_mu,
+                                                     const float* __restrict__ old_logp, const float* __restrict__ logstd,
+                                                     const float* __restrict__ scalars, double* __restrict__ dstats, int M,
+                                                     float e_clip, float bound_coef, float* __restrict__ dV,
+                                                     float* __restrict__ dMU) {
+    const int m = blockIdx.x * LOSS_BLOCK + threadIdx.x;
+    const double cnt = dstats[DS_ADV_COUNT];
+    const double mean_d = dstats[DS_ADV_SUM] / cnt;
+    const double var_d = fmax((dstats[DS_ADV_SUMSQ] - dstats[DS_ADV_SUM] * mean_d) / (cnt - 1.0), 0.0);
+    const float a_mean = (float)mean_d, a_std = (float)sqrt(var_d);
+    const float invM = 1.0f / (float)M;
+    float red[LOSS_NRED];
+#pragma unroll
+    for (int i = 0; i < LOSS_NRED; ++i) red[i] = 0.0f;
+    if (m < M) {
+        float sg[12], ls[12], sg_old[12], a[12], u[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            sg[j] = expf(logstd[j]);
+            ls[j] = logf(sg[j]);
+            sg_old[j] = expf(scalars[B200_SC_OLD_LOGSTD + j]);
+            a[j] = actions[(size_t)m * 12 + j];
+            u[j] = mu[(size_t)m * 12 + j];
+        }
+        // value loss
+        const float v = V[m], rt = ret[m];
+        const float dv = __fsub_rn(v, rt);
+        red[0] = dv * dv;
+        dV[m] = 2.0f * dv * invM;
+        // surrogate
+        const float A = __fdiv_rn(__fsub_rn(adv[m], a_mean), __fadd_rn(a_std, 1.0e-8f));
+        const float lp = normal_logp12(a, u, sg, ls);
+        const float ratio = expf(__fsub_rn(lp, old_logp[m]));
+        const float lo = 1.0f - e_clip, hi = 1.0f + e_clip;
+        const float rc = fminf(fmaxf(ratio, lo), hi);
+        const float s1 = -A * ratio, s2 = -A * rc;
+        red[1] = fmaxf(s1, s2);
+        float dr;  // d surrogate / d ratio  (torch.max splits ties evenly; clamp passes gradient on [lo, hi])
+        const bool inside = (ratio >= lo) && (ratio <= hi);
+        if (inside) dr = -A;
+        else if (s1 > s2) dr = -A;
+        else if (s1 < s2) dr = 0.0f;
+        else dr = -0.5f * A;
+        const float dlp = dr * ratio * invM;
+        // bound loss, entropy, kl, gradients
+        float bsum = 0.0f, ent = 0.0f, kl = 0.0f;
+        const float bscale = bound_coef * 2.0f / ((float)M * 12.0f);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const float d = a[j] - u[j];
+            const float var = sg[j] * sg[j];
+            const float up = fmaxf(u[j] - 1.0f, 0.0f), dn = fminf(u[j] + 1.0f, 0.0f);
+            bsum += up * up + dn * dn;
+            ent += 0.5f + LOG_SQRT_2PI + ls[j];
+            const float dm = u[j] - old_mu[(size_t)m * 12 + j];
+            kl += logf(sg[j] / sg_old[j]) + 0.5f * (sg_old[j] * sg_old[j] + dm * dm) / var - 0.5f;
+            dMU[(size_t)m * 12 + j] = dlp * d / var + bscale * (up + dn);
+            red[6 + j] = dlp * (d * d / var - 1.0f);
+        }
+        red[2] = bsum;
+        red[3] = ent;
+        red[4] = kl;
+        red[5] = 1.0f;
+    } else {
+        // nothing: contributes zeros
+    }
+    // block reduction (shuffle, then shared) -> one double atomic per quantity per block
+    __shared__ float sh[LOSS_BLOCK / 32][LOSS_NRED];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < LOSS_NRED; ++i) {
+        float x = red[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[warp][i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < LOSS_NRED) {
+        double s = 0.0;
+        for (int w = 0; w < LOSS_BLOCK / 32; ++w) s += (double)sh[w][threadIdx.x];
+        const int i = threadIdx.x;
+        const int slot = (i < 6) ? (DS_VALUE_LOSS + i) : (DS_DLOGSTD + (i - 6));
+        atomicAdd(dstats + slot, s);
+    }
+}
+
+
+// logstd gradient = reduced surrogate part + entropy_coef * d mean(entropy) / d logstd_j (= entropy_coef)
+__global__ void k_finalize_logstd(const double* __restrict__ dstats, float entropy_coef, float* __restrict__ g_logstd) {
+    const int j = threadIdx.x;
+    if (j < 12) g_logstd[j] = (float)dstats[DS_DLOGSTD + j] + entropy_coef;
+}
+
+// clip_grad_norm_ part 1 (utils/runner.py:164): sum of squares of the (world-averaged) flat gradient
+__global__ void __launch_bounds__(256) k_grad_sumsq(const float* __restrict__ grads, int n, float inv_world,
+                                                    double* __restrict__ dstats) {
+    float s = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float g = grads[i] * inv_world;
+        s += g * g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += (double)sh[w];
+        atomicAdd(dstats + DS_GRAD_SQ, t);
+    }
+}
+
+// clip + torch.optim.Adam step (default single-tensor math: lerp for m, mul/addcmul for v, bias corrections in fp64)
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m1,
+                                              float* __restrict__ m2, int n, const float* __restrict__ scalars,
+                                              const double* __restrict__ dstats, float inv_world, float max_norm,
+                                              float beta1, float beta2, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float total_norm = (float)sqrt(dstats[DS_GRAD_SQ]);
+    const float coef = fminf(__fdiv_rn(max_norm, __fadd_rn(total_norm, 1.0e-6f)), 1.0f);
+    const double step = (double)scalars[B200_SC_ADAM_STEP] + 1.0;
+    const double lr = (double)scalars[B200_SC_LR];
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    const float step_size = (float)(lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float g = __fmul_rn(__fmul_rn(grads[i], inv_world), coef);
+    grads[i] = g;  // the reference leaves the clipped gradient in .grad
+    float m = m1[i], v = m2[i];
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.0f - beta1));
+    v = __fadd_rn(__fmul_rn(v, beta2), __fmul_rn(__fmul_rn(g, g), 1.0f - beta2));
+    m1[i] = m;
+    m2[i] = v;
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
+    params[i] = __fsub_rn(params[i], __fmul_rn(step_size, __fdiv_rn(m, denom)));
+}
+
+// epoch scalars + KL-adaptive learning rate (utils/runner.py:167-184), one thread
+__global__ void k_post_apply(float* __restrict__ scalars, const double* __restrict__ dstats, float desired_kl, float lr_min,
+                             float lr_max, float lr_factor) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double S = dstats[DS_SAMPLES];
+    const float vl = (float)(dstats[DS_VALUE_LOSS] / S), al = (float)(dstats[DS_ACTOR_LOSS] / S);
+    const float bl = (float)(dstats[DS_BOUND_LOSS] / (S * 12.0)), en = (float)(dstats[DS_ENTROPY] / S);
+    const float kl = (float)(dstats[DS_KL] / S);
+    scalars[B200_SC_VALUE_LOSS] = vl;
+    scalars[B200_SC_ACTOR_LOSS] = al;
+    scalars[B200_SC_BOUND_LOSS] = bl;
+    scalars[B200_SC_ENTROPY] = en;
+    scalars[B200_SC_KL] = kl;
+    const double cnt = dstats[DS_ADV_COUNT], mean = dstats[DS_ADV_SUM] / cnt;
+    scalars[B200_SC_ADV_MEAN] = (float)mean;
+    scalars[B200_SC_ADV_STD] = (float)sqrt(fmax((dstats[DS_ADV_SUMSQ] - dstats[DS_ADV_SUM] * mean) / (cnt - 1.0), 0.0));
+    scalars[B200_SC_GRAD_NORM] = (float)sqrt(dstats[DS_GRAD_SQ]);
+    scalars[B200_SC_SUM_VALUE_LOSS] += vl;
+    scalars[B200_SC_SUM_ACTOR_LOSS] += al;
+    scalars[B200_SC_SUM_BOUND_LOSS] += bl;
+    scalars[B200_SC_SUM_ENTROPY] += en;
+    scalars[B200_SC_EPOCHS] += 1.0f;
+    scalars[B200_SC_ADAM_STEP] += 1.0f;
+    double lr = (double)scalars[B200_SC_LR];
+    if (kl > desired_kl * 2.0f) lr = fmax((double)lr_min, lr / (double)lr_factor);
+    else if (kl < desired_kl / 2.0f) lr = fmin((double)lr_max, lr * (double)lr_factor);
+    scalars[B200_SC_LR] = (float)lr;
+}
+
+// =====================================================================================================================
+// dense layers on k_gemm3x
+// =====================================================================================================================
+#define CU_TRY(expr)                                                   \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return set_cuda_error(_e, #expr);       \
+    } while (0)
+
+// Y[n, n_out] = act(X[n, k_pad] W[n_out, k_valid]^T + b)
+static cudaError_t linear_fwd(const float* X, int ldx, int k_pad, const float* W, int k_valid, const float* b, float* Y,
+                              int ldy, int n, int n_out, bool elu, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = X; g.B = W; g.C = Y; g.bias = b; g.aux = nullptr;
+    g.I = n; g.Cn = n_out; g.R = k_pad;
+    g.lda = ldx; g.ldb = k_valid; g.ldc = ldy; g.ldaux = 0;
+    g.cn_store = n_out; g.r_chunk = 0; g.r_valid_b = k_valid;
+    return elu ? launch_gemm3x<false, false, EPI_BIAS_ELU>(g, 1, st) : launch_gemm3x<false, false, EPI_BIAS>(g, 1, st);
+}
+// dX[n, k] = (dY[n, n_out] W[n_out, k]) * ELU'(H[n, k])
+static cudaError_t linear_dgrad(const float* dY, int ldy, int n_out, const float* W, int k, const float* H, int ldh,
+                                float* dX, int ldx, int n, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = dY; g.B = W; g.C = dX; g.bias = nullptr; g.aux = H;
+    g.I = n; g.Cn = k; g.R = n_out;
+    g.lda = ldy; g.ldb = k; g.ldc = ldx; g.ldaux = ldh;
+    g.cn_store = k; g.r_chunk = 0; g.r_valid_b = 0;
+    return launch_gemm3x<false, true, EPI_ELU_GRAD>(g, 1, st);
+}
+// dW[n_out, k_valid] += dY[n, n_out]^T X[n, k_pad]   (split over n, atomic accumulate; dW must be zeroed by the caller)
+#define WGRAD_CHUNK 1024
+static cudaError_t linear_wgrad(const float* dY, int ldy, int n_out, const float* X, int ldx, int k_pad, int k_valid,
+                                float* dW, int n, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = dY; g.B = X; g.C = dW; g.bias = nullptr; g.aux = nullptr;
+    g.I = n_out; g.Cn = k_pad; g.R = n;
+    g.lda = ldy; g.ldb = ldx; g.ldc = k_valid; g.ldaux = 0;
+    g.cn_store = k_valid; g.r_chunk = WGRAD_CHUNK; g.r_valid_b = 0;
+    return launch_gemm3x<true, true, EPI_ATOMIC>(g, (n + WGRAD_CHUNK - 1) / WGRAD_CHUNK, st);
+}
+static cudaError_t bias_grad(const float* dY, int ld, int C, int n, float* db, cudaStream_t st) {
+    k_colsum<<<(n + CS_ROWS - 1) / CS_ROWS, 256, 0, st>>>(dY, n, C, ld, db);
+    return cudaPeekAtLastError();
+}
+
+// actor 47 -> 256 -> 128 -> 128 -> 12 (utils/model.py:18-26)
+static int actor_forward(const B200Ppo* p, const float* X, int ldx, int k_pad, int n, float* H1, float* H2, float* H3,
+                         float* MU, cudaStream_t st) {
+    CU_TRY(linear_fwd(X, ldx, k_pad, p->P(P_AW0), 47, p->P(P_AB0), H1, 256, n, 256, true, st));
+    CU_TRY(linear_fwd(H1, 256, 256, p->P(P_AW1), 256, p->P(P_AB1), H2, 128, n, 128, true, st));
+    CU_TRY(linear_fwd(H2, 128, 128, p->P(P_AW2), 128, p->P(P_AB2), H3, 128, n, 128, true, st));
+    CU_TRY(linear_fwd(H3, 128, 128, p->P(P_AW3), 128, p->P(P_AB3), MU, 12, n, 12, false, st));
+    return B200_OK;
+}
+// critic 61 -> 256 -> 256 -> 128 -> 1 (utils/model.py:9-17); Xc is the packed [n,64] cat(obs, priv)
+static int critic_forward(const B200Ppo* p, const float* Xc, int n, float* H1, float* H2, float* H3, float* V,
+                          cudaStream_t st) {
+    CU_TRY(linear_fwd(Xc, 64, 64, p->P(P_CW0), 61, p->P(P_CB0), H1, 256, n, 256, true, st));
+    CU_TRY(linear_fwd(H1, 256, 256, p->P(P_CW1), 256, p->P(P_CB1), H2, 256, n, 256, true, st));
+    CU_TRY(linear_fwd(H2, 256, 256, p->P(P_CW2), 256, p->P(P_CB2), H3, 128, n, 128, true, st));
+    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(H3, p->P(P_CW3), p->P(P_CB3), n, V);
+    return launch_status("k_value_head");
+}
+
+// =====================================================================================================================
+extern "C" {
+
+int b200_ppo_num_params(void) { return NPARAMS_PADDED; }
+int b200_ppo_num_param_tensors(void) { return P_COUNT; }
+int b200_ppo_param_info(int idx, const char** name, int* offset, int* rows, int* cols) {
+    if (idx < 0 || idx >= P_COUNT) return set_error(B200_ERR_ARG, "b200_ppo_param_info: bad index");
+    if (name) *name = kParams[idx].name;
+    if (offset) *offset = kParams[idx].offset;
+    if (rows) *rows = kParams[idx].rows;
+    if (cols) *cols = kParams[idx].cols;
+    return B200_OK;
+}
+
+int64_t b200_ppo_workspace_bytes(int horizon, int num_envs) {
+    if (horizon <= 0 || num_envs <= 0) return 0;
+    return (int64_t)(make_workspace(horizon, num_envs).total * sizeof(float));
+}
+
+int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float* adam_m, float* adam_v, float* scalars,
+                    double* dstats, void* workspace, int device, B200Ppo** out) {
+    if (!cfg || !params || !grads || !adam_m || !adam_v || !scalars || !dstats || !workspace || !out)
+        return set_error(B200_ERR_ARG, "b200_ppo_create: null pointer");
+    if (cfg->horizon <= 0 || cfg->num_envs <= 0 || cfg->world_size <= 0) return set_error(B200_ERR_ARG, "b200_ppo_create: bad sizes");
+    if ((reinterpret_cast<uintptr_t>(params) & 15) || (reinterpret_cast<uintptr_t>(grads) & 15) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255))
+        return set_error(B200_ERR_ARG, "b200_ppo_create: params/grads must be 16-byte and workspace 256-byte aligned");
+    CUDA_TRY(cudaSetDevice(device));
+    B200Ppo* p = new (std::nothrow) B200Ppo();
+    if (!p) return set_error(B200_ERR_ARG, "out of host memory");
+    p->cfg = *cfg;
+    p->device = device;
+    p->params = params; p->grads = grads; p->adam_m = adam_m; p->adam_v = adam_v; p->scalars = scalars;
+    p->dstats = dstats;
+    p->ws = (float*)workspace;
+    p->w = make_workspace(cfg->horizon, cfg->num_envs);
+    *out = p;
+    return B200_OK;
+}
+int b200_ppo_destroy(B200Ppo* p) {
+    delete p;
+    return B200_OK;
+}
+
+#define NEED_PPO(p) if (!(p)) return set_error(B200_ERR_ARG, "null learner handle")
+
+int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* mu_out, const float* eps_in,
+                    uint64_t seed, uint64_t step, int deterministic, void* stream) {
+    NEED_PPO(p);
+    if (!obs || !actions || n <= 0 || n > p->cfg.num_envs) return set_error(B200_ERR_ARG, "b200_policy_act: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = p->ws;
+    const int rc = actor_forward(p, obs, 47, 47, n, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, ws + p->w.LMU, st);
+    if (rc != B200_OK) return rc;
+    k_sample<<<(n + 127) / 128, 128, 0, st>>>(ws + p->w.LMU, p->P(P_LOGSTD), eps_in, n, seed, step, p->cfg.env_base,
+                                              deterministic, actions, mu_out);
+    return launch_status("k_sample");
+}
+
+int b200_critic_value(B200Ppo* p, const float* obs, const float* priv, int n, float* values, void* stream) {
+    NEED_PPO(p);
+    if (!obs || !priv || !values || n <= 0 || n > p->cfg.num_envs) return set_error(B200_ERR_ARG, "b200_critic_value: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = p->ws;
+    k_pack_inputs<<<(int)(((size_t)n * 64 + 255) / 256), 256, 0, st>>>(obs, priv, n, nullptr, ws + p->w.LXc);
+    return critic_forward(p, ws + p->w.LXc, n, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, values, st);
+}
+
+int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const float* actions, float* old_mu,
+                      float* old_logp, void* stream) {
+    NEED_PPO(p);
+    if (!obses || !privs || !actions || !old_mu || !old_logp) return set_error(B200_ERR_ARG, "b200_ppo_old_dist: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = p->ws;
+    const int M = p->cfg.horizon * p->cfg.num_envs;
+    k_pack_inputs<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(obses, privs, M, ws + p->w.Xa, ws + p->w.Xc);
+    const int rc = actor_forward(p, ws + p->w.Xa, 48, 48, M, ws + p->w.A1, ws + p->w.A2, ws + p->w.A3, ws + p->w.MU, st);
+    if (rc != B200_OK) return rc;
+    k_old_logp<<<(M + 255) / 256, 256, 0, st>>>(ws + p->w.MU, actions, p->P(P_LOGSTD), M, old_mu, old_logp, p->scalars);
+    return launch_status("k_old_logp");
+}
+
+int b200_gae(float* rewards, const uint8_t* dones, const uint8_t* time_outs, const float* values, const float* last_values,
+             double gamma, double lam, float* advantages, float* returns, double* stats, int horizon, int num_envs,
+             void* stream) {
+    if (!rewards || !dones || !time_outs || !values || !last_values || !advantages || !returns || horizon <= 0 || num_envs <= 0)
+        return set_error(B200_ERR_ARG, "b200_gae: bad argument");
+    k_gae<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, dones, time_outs, values, last_values,
+                                                                      (float)gamma, (float)(gamma * lam), horizon,
+                                                                      num_envs, advantages, returns, stats);
+    return launch_status("k_gae");
+}
+
+int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uint8_t* time_outs, const float* last_obs,
+                     const float* last_priv, void* stream) {
+    NEED_PPO(p);
+    if (!rewards || !dones || !time_outs || !last_obs || !last_priv) return set_error(B200_ERR_ARG, "b200_ppo_epoch_a: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = p->ws;
+    const int T = p->cfg.horizon, N = p->cfg.num_envs, M = T * N;
+    CUDA_TRY(cudaMemsetAsync(p->dstats, 0, DS_COUNT * sizeof(double), st));
+    int rc = critic_forward(p, ws + p->w.Xc, M, ws + p->w.C1, ws + p->w.C2, ws + p->w.C3, ws + p->w.V, st);
+    if (rc != B200_OK) return rc;
+    k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(last_obs, last_priv, N, nullptr, ws + p->w.LXc);
+    rc = critic_forward(p, ws + p->w.LXc, N, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, ws + p->w.LV, st);
+    if (rc != B200_OK) return rc;
+    k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.LV, (float)p->cfg.gamma,
+                                           (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
+    return launch_status("k_gae");
+}
+
+int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, const float* old_logp, void* stream) {
+    NEED_PPO(p);
+    if (!actions || !old_mu || !old_logp) return set_error(B200_ERR_ARG, "b200_ppo_epoch_b: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = p->ws;
+    const int M = p->cfg.horizon * p->cfg.num_envs;
+    float *Xa = ws + p->w.Xa, *Xc = ws + p->w.Xc, *C1 = ws + p->w.C1, *C2 = ws + p->w.C2, *C3 = ws + p->w.C3;
+    float *A1 = ws + p->w.A1, *A2 = ws + p->w.A2, *A3 = ws + p->w.A3, *MU = ws + p->w.MU;
+    float *DV = ws + p->w.DV, *DMU = ws + p->w.DMU, *G1 = ws + p->w.G1, *G2 = ws + p->w.G2;
+    int rc = actor_forward(p, Xa, 48, 48, M, A1, A2, A3, MU, st);
+    if (rc != B200_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(p->grads, 0, NPARAMS_PADDED * sizeof(float), st));
+    k_loss<<<(M + LOSS_BLOCK - 1) / LOSS_BLOCK, LOSS_BLOCK, 0, st>>>(ws + p->w.V, ws + p->w.RET, ws + p->w.ADV, MU, actions,
+                                                                    old_mu, old_logp, p->P(P_LOGSTD), p->scalars, p->dstats,
+                                                                    M, p->cfg.e_clip, p->cfg.bound_coef, DV, DMU);
+    k_finalize_logstd<<<1, 32, 0, st>>>(p->dstats, p->cfg.entropy_coef, p->G(P_LOGSTD));
+    if ((rc = launch_status("k_loss")) != B200_OK) return rc;
+    // ---- actor backward
+    CU_TRY(linear_wgrad(DMU, 12, 12, A3, 128, 128, 128, p->G(P_AW3), M, st));
+    CU_TRY(bias_grad(DMU, 12, 12, M, p->G(P_AB3), st));
+    CU_TRY(linear_dgrad(DMU, 12, 12, p->P(P_AW3), 128, A3, 128, G1, 128, M, st));
+    CU_TRY(linear_wgrad(G1, 128, 128, A2, 128, 128, 128, p->G(P_AW2), M, st));
+    CU_TRY(bias_grad(G1, 128, 128, M, p->G(P_AB2), st));
+    CU_TRY(linear_dgrad(G1, 128, 128, p->P(P_AW2), 128, A2, 128, G2, 128, M, st));
+    CU_TRY(linear_wgrad(G2, 128, 128, A1, 256, 256, 256, p->G(P_AW1), M, st));
+    CU_TRY(bias_grad(G2, 128, 128, M, p->G(P_AB1), st));
+    CU_TRY(linear_dgrad(G2, 128, 128, p->P(P_AW1), 256, A1, 256, G1, 256, M, st));
+    CU_TRY(linear_wgrad(G1, 256, 256, Xa, 48, 48, 47, p->G(P_AW0), M, st));
+    CU_TRY(bias_grad(G1, 256, 256, M, p->G(P_AB0), st));
+    // ---- critic backward
+    k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3));
+    if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
+    CU_TRY(linear_wgrad(G1, 128, 128, C2, 256, 256, 256, p->G(P_CW2), M, st));
+    CU_TRY(bias_grad(G1, 128, 128, M, p->G(P_CB2), st));
+    CU_TRY(linear_dgrad(G1, 128, 128, p->P(P_CW2), 256, C2, 256, G2, 256, M, st));
+    CU_TRY(linear_wgrad(G2, 256, 256, C1, 256, 256, 256, p->G(P_CW1), M, st));
+    CU_TRY(bias_grad(G2, 256, 256, M, p->G(P_CB1), st));
+    CU_TRY(linear_dgrad(G2, 256, 256, p->P(P_CW1), 256, C1, 256, G1, 256, M, st));
+    CU_TRY(linear_wgrad(G1, 256, 256, Xc, 64, 64, 61, p->G(P_CW0), M, st));
+    CU_TRY(bias_grad(G1, 256, 256, M, p->G(P_CB0), st));
+    return B200_OK;
+}
+
+int b200_ppo_epoch(B200Ppo* p, const float* actions, float* rewards, const uint8_t* dones, const uint8_t* time_outs,
+                   const float* last_obs, const float* last_priv, const float* old_mu, const float* old_logp, void* stream) {
+    const int rc = b200_ppo_epoch_a(p, rewards, dones, time_outs, last_obs, last_priv, stream);
+    if (rc != B200_OK) return rc;
+    return b200_ppo_epoch_b(p, actions, old_mu, old_logp, stream);
+}
+
+int b200_ppo_apply(B200Ppo* p, void* stream) {
+    NEED_PPO(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float inv_world = 1.0f / (float)p->cfg.world_size;
+    k_grad_sumsq<<<148, 256, 0, st>>>(p->grads, NPARAMS_PADDED, inv_world, p->dstats);
+    k_adam<<<(NPARAMS_PADDED + 255) / 256, 256, 0, st>>>(p->params, p->grads, p->adam_m, p->adam_v, NPARAMS_PADDED, p->scalars,
+                                                         p->dstats, inv_world, p->cfg.max_grad_norm, p->cfg.adam_beta1,
+                                                         p->cfg.adam_beta2, p->cfg.adam_eps);
+    k_post_apply<<<1, 32, 0, st>>>(p->scalars, p->dstats, p->cfg.desired_kl, p->cfg.lr_min, p->cfg.lr_max, p->cfg.lr_factor);
+    return launch_status("b200_ppo_apply");
+}
+
+float* b200_ppo_buffer(B200Ppo* p, int which) {
+    if (!p) return nullptr;
+    switch (which) {
+        case 0: return p->ws + p->w.V;
+        case 1: return p->ws + p->w.ADV;
+        case 2: return p->ws + p->w.RET;
+        case 3: return p->ws + p->w.MU;
+        case 4: return p->ws + p->w.LV;
+        case 5: return p->ws + p->w.DV;
+        case 6: return p->ws + p->w.DMU;
+    }
+    return nullptr;
+}
+
+}  // extern "C"

@@ -34,6 +34,8 @@ enum RngPurpose {
     RP_POLICY = 11       // action sampling noise: sub 0-2 (12 normals)
 };
 
+#define B200_RNG_SHARED_ENV 0xFFFFFFFFu  /* env id of draws shared by all envs of a call (reset dof noise) */
+
 struct Philox4 {
     uint32_t w[4];
 };

@@ -284,10 +284,12 @@ B200_HD void env_reset_one(const EnvView& v, int e, const B200T1Config& c, const
     int32_t* is = v.is;
     const int n = v.n;
     const uint32_t ge = (uint32_t)(v.env_base + e);
-    // _reset_dofs :319-325
+    // _reset_dofs :319-325.  Reference quirk (SURVEY 8a note 12): the noise has the shape of default_dof_pos, [1,12],
+    // so every env that resets in the same call receives the SAME 12 joint offsets -> the draw is keyed by the step
+    // only (env id B200_RNG_SHARED_ENV), not by the env.
 #pragma unroll
     for (int sub = 0; sub < 3; ++sub) {
-        const Rand4 r = rand4(rng_words(v.seed, ge, step, RP_RESET_DOF, sub));
+        const Rand4 r = rand4(rng_words(v.seed, B200_RNG_SHARED_ENV, step, RP_RESET_DOF, sub));
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const int j = 4 * sub + l;
@@ -415,8 +417,10 @@ B200_HD void env_observations(const EnvView& v, int e, const B200T1Config& c, co
     }
 }
 
-// envs/t1.py:343-360 (trimesh only)
-B200_HD void env_teleport(const EnvView& v, int e, const B200T1Config& c) {
+// envs/t1.py:343-360 (trimesh only).  The reference re-runs _refresh_feet_state for everyone when any env moved
+// (:358-360); for an env that did not move that recomputation is the identity, so it is done per moved env here.
+template <typename Model>
+B200_HD void env_teleport(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr) {
     if (c.terrain_type == 0) return;
     float* f = v.f;
     int32_t* is = v.is;
@@ -432,6 +436,7 @@ B200_HD void env_teleport(const EnvView& v, int e, const B200T1Config& c) {
     if (ymax) dy -= c.env_length + c.border_size;
     if (xmin || xmax) { FS(F_root_states + 0) = x + dx; FS(F_feet_pos + 0) += dx; FS(F_feet_pos + 3) += dx; }
     if (ymin || ymax) { FS(F_root_states + 1) = y + dy; FS(F_feet_pos + 1) += dy; FS(F_feet_pos + 4) += dy; }
+    if (xmin || xmax || ymin || ymax) env_refresh_feet(v, e, m, terr);
 }
 
 struct StepOut {
@@ -527,7 +532,7 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     IS(I_episode_steps) += 1;
     // :485-488
     if (reset) env_reset_one(v, e, c, terr, step);
-    env_teleport(v, e, c);
+    env_teleport(v, e, m, c, terr);
     if (IS(I_episode_length_buf) == IS(I_cmd_resample_time)) env_resample_command(v, e, c, step);
     // :490
     env_observations(v, e, c, terr, step, noise_on, obs, priv);

@@ -119,9 +119,10 @@ typedef struct B200T1Config {
     /* terrain (utils/terrain.py:30-45) */
     int32_t terrain_type;             /* 0 plane, 1 trimesh (heightfield) */
     int32_t border_pixels;
-    float horizontal_scale, vertical_scale, env_width, env_length, border_size;
+    float horizontal_scale, env_width, env_length, border_size;
     float terrain_friction;           /* static friction of the ground (envs/T1.yaml:99) */
-    int32_t pad1;
+    int32_t pad1, pad2;
+    double vertical_scale;            /* fp64: the reference multiplies the fp64 interpolant by the Python float */
 } B200T1Config;
 
 typedef struct B200T1Handle B200T1Handle;
@@ -181,57 +182,77 @@ int b200_t1_counters(B200T1Handle* h, int64_t* rng_step, int64_t* common_step, v
 /* ---- learner: policy inference, GAE, PPO epoch (utils/model.py, utils/utils.py, utils/runner.py:123-185) ---- */
 #define B200_ACTOR_PARAMS 63244
 #define B200_CRITIC_PARAMS 114689
-#define B200_NPARAMS 177945 /* critic, actor, logstd in state_dict order (utils/model.py:9-27) */
+#define B200_NPARAMS 177945        /* trainable scalars of ActorCritic(12, 47, 14) (utils/model.py:9-27) */
+#define B200_NPARAMS_PADDED 177948 /* length of the flat param/grad/Adam buffers: every tensor starts 16-byte aligned */
 
 typedef struct B200PpoConfig {
-    float gamma, lam, e_clip, bound_coef, entropy_coef, desired_kl, max_grad_norm;
+    double gamma, lam;  /* kept in fp64 like the Python floats they replace (gamma*lam is formed in fp64, utils/utils.py:43) */
+    float e_clip, bound_coef, entropy_coef, desired_kl, max_grad_norm;
     float lr_min, lr_max, lr_factor;
     float adam_beta1, adam_beta2, adam_eps;
     int32_t horizon, num_envs, world_size;
+    int32_t env_base; /* global index of env 0 of this rank's shard (keys the action-sampling RNG) */
+    int32_t pad0;
 } B200PpoConfig;
 
 typedef struct B200Ppo B200Ppo;
 
-/* workspace_bytes: caller allocates one device scratch buffer of that size and passes it to create */
+/* flat parameter layout: tensor idx -> state_dict name, offset (floats) into the flat buffers, shape */
+int b200_ppo_num_params(void);        /* B200_NPARAMS_PADDED */
+int b200_ppo_num_param_tensors(void); /* 17 */
+int b200_ppo_param_info(int idx, const char** name, int* offset, int* rows, int* cols);
+
+/* workspace_bytes: caller allocates one device scratch buffer of that size (256-byte aligned) and passes it to create */
 int64_t b200_ppo_workspace_bytes(int horizon, int num_envs);
-int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float* adam_m, float* adam_v,
-                    float* scalars /* device float[32], see B200_SC_* */, void* workspace, int device, B200Ppo** out);
+/* params/grads/adam_m/adam_v: device float[B200_NPARAMS_PADDED]; scalars: device float[32] (B200_SC_*; the caller
+ * writes B200_SC_LR before the first epoch); dstats: device double[32] (B200_DS_*: reduction targets, the buffers a
+ * multi-GPU caller all-reduces). */
+int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float* adam_m, float* adam_v, float* scalars,
+                    double* dstats, void* workspace, int device, B200Ppo** out);
 int b200_ppo_destroy(B200Ppo* p);
 
 enum { /* rows of the device `scalars` array */
     B200_SC_LR = 0, B200_SC_ADAM_STEP, B200_SC_VALUE_LOSS, B200_SC_ACTOR_LOSS, B200_SC_BOUND_LOSS, B200_SC_ENTROPY,
-    B200_SC_KL, B200_SC_ADV_MEAN, B200_SC_ADV_STD, B200_SC_GRAD_NORM, B200_SC_COUNT = 32
+    B200_SC_KL, B200_SC_ADV_MEAN, B200_SC_ADV_STD, B200_SC_GRAD_NORM,
+    /* running sums over the epochs since the caller last zeroed them (utils/runner.py:182-189) */
+    B200_SC_SUM_VALUE_LOSS = 10, B200_SC_SUM_ACTOR_LOSS, B200_SC_SUM_BOUND_LOSS, B200_SC_SUM_ENTROPY, B200_SC_EPOCHS,
+    B200_SC_OLD_LOGSTD = 16, /* 12 entries: logstd at old_dist time (utils/runner.py:123-125) */
+    B200_SC_COUNT = 32
+};
+enum { /* rows of the device `dstats` array (sums; cleared by b200_ppo_epoch_a) */
+    B200_DS_ADV_SUM = 0, B200_DS_ADV_SUMSQ, B200_DS_ADV_COUNT, B200_DS_PAD, B200_DS_VALUE_LOSS, B200_DS_ACTOR_LOSS,
+    B200_DS_BOUND_LOSS, B200_DS_ENTROPY, B200_DS_KL, B200_DS_SAMPLES, B200_DS_GRAD_SQ, B200_DS_DLOGSTD = 16,
+    B200_DS_COUNT = 32
 };
 
 /* replaces model.act(obs).sample() (utils/runner.py:109-111): mu = actor(obs); act = mu + exp(logstd)*eps.
- * eps drawn in-kernel (Philox, keyed by seed/step) unless eps_in != NULL. deterministic != 0 -> act = mu (play). */
+ * eps drawn in-kernel (Philox, keyed by seed/env/step) unless eps_in != NULL. deterministic != 0 -> act = mu (play). */
 int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* mu_out /*nullable*/,
                     const float* eps_in /*nullable*/, uint64_t seed, uint64_t step, int deterministic, void* stream);
 /* replaces est_value (utils/model.py:34-36) */
 int b200_critic_value(B200Ppo* p, const float* obs, const float* priv, int n, float* values, void* stream);
-/* replaces utils/runner.py:123-125: old mu [M,12] and old log-prob [M] of the stored actions */
-int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* actions, float* old_mu, float* old_logp,
-                      void* stream);
+/* replaces utils/runner.py:123-125: old mu [M,12] and old log-prob [M] of the stored actions. Also stages the rollout
+ * observations (obses [T,N,47], privs [T,N,14]) as the padded GEMM operands every following epoch reads. */
+int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const float* actions, float* old_mu,
+                      float* old_logp, void* stream);
 /* replaces utils/utils.py:33-44 + utils/runner.py:135,144 (time-out bootstrap in place, GAE, returns) and the
- * advantage moments of :145. rewards is modified in place like the reference. stats (device double[4]) receives
- * sum, sum of squares and count of the raw advantages of this shard. */
+ * advantage moments of :145. rewards is modified in place like the reference. stats (nullable; device double[>=3])
+ * accumulates sum, sum of squares and count of the raw advantages. */
 int b200_gae(float* rewards, const uint8_t* dones, const uint8_t* time_outs, const float* values,
-             const float* last_values, float gamma, float lam, float* advantages, float* returns, double* stats,
+             const float* last_values, double gamma, double lam, float* advantages, float* returns, double* stats,
              int horizon, int num_envs, void* stream);
 /* one full-batch epoch body, utils/runner.py:132-161 + backward: fills grads (flat, mean over local samples) and
- * loss scalars; the optional allreduce between this and b200_ppo_apply is done by the caller (NCCL) */
-int b200_ppo_epoch(B200Ppo* p, const float* obses, const float* privs, const float* actions, float* rewards,
-                   const uint8_t* dones, const uint8_t* time_outs, const float* last_obs, const float* last_priv,
-                   const float* old_mu, const float* old_logp, void* stream);
-/* the two halves of b200_ppo_epoch for multi-GPU runs: stage A ends after the advantage moments (so they can be
- * all-reduced), stage B is actor forward, losses and backward */
-int b200_ppo_epoch_a(B200Ppo* p, const float* obses, const float* privs, float* rewards, const uint8_t* dones,
-                     const uint8_t* time_outs, const float* last_obs, const float* last_priv, void* stream);
-int b200_ppo_epoch_b(B200Ppo* p, const float* obses, const float* privs, const float* actions, const float* old_mu,
-                     const float* old_logp, void* stream);
-double* b200_ppo_adv_stats(B200Ppo* p); /* device double[4]: sum, sumsq, count, (pad) - allreduce target */
+ * the loss sums; the optional allreduce between this and b200_ppo_apply is done by the caller (NCCL) */
+int b200_ppo_epoch(B200Ppo* p, const float* actions, float* rewards, const uint8_t* dones, const uint8_t* time_outs,
+                   const float* last_obs, const float* last_priv, const float* old_mu, const float* old_logp,
+                   void* stream);
+/* the two halves of b200_ppo_epoch for multi-GPU runs: stage A = critic forward, time-out bootstrap, GAE and the
+ * advantage moments (dstats[0..2], all-reduced by the caller); stage B = actor forward, losses, backward */
+int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uint8_t* time_outs, const float* last_obs,
+                     const float* last_priv, void* stream);
+int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, const float* old_logp, void* stream);
 /* views into the workspace for parity tests (device pointers, valid after an epoch): 0 values [M], 1 advantages
- * (raw) [M], 2 returns [M], 3 mu [M,12], 4 last_values [N] */
+ * (raw) [M], 2 returns [M], 3 mu [M,12], 4 last_values [N], 5 dL/dV [M], 6 dL/dmu [M,12] */
 float* b200_ppo_buffer(B200Ppo* p, int which);
 /* replaces utils/runner.py:162-180: clip_grad_norm_(1.0), Adam step, KL-adaptive learning rate (all on device) */
 int b200_ppo_apply(B200Ppo* p, void* stream);

@@ -1,0 +1,250 @@
+"""GPU tests of the environment kernels through the C-ABI: physics against the FP64 C oracle (oracle/physics_oracle.c),
+terrain lookup bit-exact, and rollout invariants.  Post-physics parity against the pinned numpy oracle lives in
+tests/test_gpu_env_post.py."""
+import copy
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(t1_cfg, n, terrain="plane", seed=42, **over):
+    from booster_gym_b200.envs import T1
+
+    cfg = copy.deepcopy(t1_cfg)
+    cfg["env"]["num_envs"] = n
+    cfg["terrain"]["type"] = terrain
+    cfg["basic"]["seed"] = seed
+    cfg["basic"]["headless"] = True
+    for k, v in over.items():
+        sec, key = k.split("__")
+        cfg[sec][key] = v
+    np.random.seed(seed)
+    return T1(cfg)
+
+
+def oracle_envs(env, idx):
+    """FP64 oracle copies of the physics state + per-env model parameters of the selected envs"""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    md = robot.model_d(foot_corner=[list(map(float, r)) for r in env.cfg["asset"]["feet_edge_pos"]])
+    f = env._fstate.cpu().double().numpy()
+    ff = env._ffields
+    out = []
+    for e in idx:
+        def row(name):
+            r, c = ff[name]
+            return f[r:r + c, e]
+        rs = row("root_states")
+        quat = rs[3:7] / np.linalg.norm(rs[3:7])
+        x, y, z, w = quat
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        oe = op.make_env(md, pos=rs[0:3], quat=quat, vlin=rs[7:10], wb=R.T @ rs[10:13], q=row("dof_pos"), qd=row("dof_vel"))
+        oe.mass[:] = row("body_mass")
+        com = row("body_com")
+        for b in range(13):
+            for r in range(3):
+                oe.com[b][r] = com[3 * b + r]
+        oe.mu[:] = row("foot_friction")
+        oe.kscale[:] = row("foot_kscale")
+        oe.cscale[:] = row("foot_cscale")
+        out.append(oe)
+    return md, out
+
+
+def randomize_state(env, seed, airborne):
+    n = env.num_envs
+    g = torch.Generator().manual_seed(seed)
+    rs = torch.zeros(n, 13)
+    rs[:, 0:2] = torch.randn(n, 2, generator=g)
+    rs[:, 2] = 2.0 if airborne else 0.645
+    axis = torch.randn(n, 3, generator=g)
+    axis /= axis.norm(dim=1, keepdim=True)
+    ang = (torch.rand(n, generator=g) - 0.5) * (2.0 if airborne else 0.1)
+    rs[:, 3:6] = axis * torch.sin(ang / 2).unsqueeze(1)
+    rs[:, 6] = torch.cos(ang / 2)
+    rs[:, 7:10] = torch.randn(n, 3, generator=g) * (1.0 if airborne else 0.2)
+    rs[:, 10:13] = torch.randn(n, 3, generator=g) * (2.0 if airborne else 0.3)
+    env.root_states.copy_(rs.cuda())
+    q0 = env.default_dof_pos.cpu()
+    env.dof_pos.copy_((q0 + (torch.rand(n, 12, generator=g) - 0.5) * (0.8 if airborne else 0.1)).cuda())
+    env.dof_vel.copy_((torch.randn(n, 12, generator=g) * (3.0 if airborne else 0.3)).cuda())
+    return g
+
+
+@pytest.mark.parametrize("airborne", [True, False])
+def test_one_tick_qacc_against_fp64_oracle(t1_cfg, airborne):
+    """one physics tick with given joint torques: generalised acceleration vs the independent-algorithm FP64 oracle.
+    Tolerance (fp32 kernel vs fp64 oracle, stated): 2e-4 * max(1, |qacc|_inf) contact-free, 2e-3 with foot contact."""
+    from oracle import physics as op
+
+    n = 64
+    env = make_env(t1_cfg, n)
+    g = randomize_state(env, 11, airborne)
+    tau = torch.randn(n, 12, generator=g) * 10.0
+    md, oenvs = oracle_envs(env, range(n))
+    qacc = torch.zeros(18, n, device="cuda")
+    env.physics(tau.cuda(), 1, apply_pd=False, qacc_out=qacc)
+    torch.cuda.synchronize()
+    qa = qacc.cpu().double().numpy()
+    worst = 0.0
+    n_contact = 0
+    for e in range(n):
+        st, ref, fn = op.tick(md, oenvs[e], tau[e].double().numpy(), integrate=False)
+        assert st == 0
+        n_contact += int(fn.sum() > 0)
+        err = np.abs(qa[:, e] - ref).max() / max(1.0, np.abs(ref).max())
+        worst = max(worst, err)
+    print("worst relative qacc error", worst, "envs in contact", n_contact)
+    assert (n_contact > 0) == (not airborne)
+    assert worst < (2e-4 if airborne else 2e-3)
+
+
+def test_decimated_loop_against_fp64_oracle(t1_cfg):
+    """T1.step's 10-tick PD loop (action delay, joint friction, torque clip; envs/t1.py:439-456) on airborne robots:
+    joint positions / base pose after 10 ticks within 1e-4, mean torques within 1e-3 of the FP64 oracle."""
+    from oracle import physics as op
+
+    n = 32
+    env = make_env(t1_cfg, n)
+    g = randomize_state(env, 5, True)
+    env.delay_steps.copy_(torch.randint(0, 10, (n,), generator=g).int().cuda())
+    env.last_dof_targets.copy_(env.dof_pos)
+    act = (torch.rand(n, 12, generator=g) * 2.4 - 1.2)
+    md, oenvs = oracle_envs(env, range(n))
+    arr = (op.Env * n)(*oenvs)
+    kp = env.dof_stiffness.cpu().double().numpy().copy()
+    kd = env.dof_damping.cpu().double().numpy().copy()
+    fr = env.dof_friction.cpu().double().numpy().copy()
+    lt = env.last_dof_targets.cpu().double().numpy().copy()
+    delay = env.delay_steps.cpu().numpy().astype(np.int32).copy()
+    a = act.clamp(-1, 1).double().numpy().copy()
+    q0 = env.default_dof_pos.cpu().double().numpy().ravel().copy()
+    lim = env.torque_limits.cpu().double().numpy().copy()
+    pf = np.zeros((n, 3)); pt = np.zeros((n, 3)); tm = np.zeros((n, 12))
+    terr = op.make_terrain()
+    lib = op.lib()
+    P = lambda x: x.ctypes.data_as(C.c_void_p)
+    bad = lib.t1o_env_physics(C.byref(md), arr, n, P(a), P(q0), C.c_double(1.0), P(kp), P(kd), P(fr), P(lim), P(delay), P(lt),
+                              P(pf), P(pt), C.byref(terr), 10, P(tm), 0)
+    assert bad == 0
+    env.physics(act.cuda(), 10, apply_pd=True)
+    torch.cuda.synchronize()
+    q = env.dof_pos.cpu().double().numpy()
+    pos = env.root_states.cpu().double().numpy()
+    tq = env.torques.cpu().double().numpy()
+    for e in range(n):
+        assert np.abs(q[e] - np.array(arr[e].q[:])).max() < 1e-4
+        assert np.abs(pos[e, 0:3] - np.array(arr[e].pos[:])).max() < 1e-4
+        assert np.abs(np.abs(pos[e, 3:7] @ np.array(arr[e].quat[:])) - 1.0) < 1e-6
+        assert np.abs(tq[e] - tm[e]).max() < 1e-3 * max(1.0, np.abs(tm[e]).max())
+    assert np.abs(env.last_dof_targets.cpu().double().numpy() - lt).max() < 1e-6
+
+
+def test_free_fall_and_momentum(t1_cfg):
+    """physical invariants (SURVEY 8c ii): zero-torque free fall has base qacc (0,0,-g); feet FK matches the oracle"""
+    from oracle import physics as op
+
+    n = 32
+    env = make_env(t1_cfg, n)
+    randomize_state(env, 3, True)
+    env.root_states[:, 7:13] = 0
+    env.dof_vel[:] = 0
+    env.dof_pos.copy_(env.default_dof_pos + 0.1 * (torch.rand(n, 12, device="cuda") - 0.5))  # inside the joint limits: no limit forces
+    qacc = torch.zeros(18, n, device="cuda")
+    md, oenvs = oracle_envs(env, range(n))
+    env.physics(torch.zeros(n, 12, device="cuda"), 1, apply_pd=False, qacc_out=qacc)
+    torch.cuda.synchronize()
+    qa = qacc.cpu().numpy()
+    assert np.abs(qa[0:2]).max() < 2e-3 and np.abs(qa[2] + 9.81).max() < 2e-3
+    # feet pose rows written by the physics kernel (rigid_body_state of the foot links)
+    fp = env.feet_pos.cpu().double().numpy()
+    for e in range(n):
+        op.tick(md, oenvs[e], integrate=True)
+        p, R = op.feet(md, oenvs[e])
+        assert np.abs(fp[e] - p).max() < 1e-5
+
+
+def test_terrain_heights_bit_exact(t1_cfg):
+    """Terrain.terrain_heights on the device vs the reference's numpy arithmetic (utils/terrain.py:101-121), bit-exact,
+    including negative-index wrap and cell-boundary positions (SURVEY 7 hard part 6)."""
+    env = make_env(t1_cfg, 64, terrain="trimesh")
+    hf = env.terrain.height_field_raw
+    assert hf.shape == (900, 200) and hf.dtype == np.int16
+    g = np.random.default_rng(0)
+    K = 200000
+    xy = np.stack([g.uniform(-4.9, 84.7, K), g.uniform(-4.9, 14.7, K)], axis=1).astype(np.float32)
+    xy[:1000] = (np.round(xy[:1000] * 10) / 10).astype(np.float32)       # exactly on cell boundaries
+    xy[1000:2000, 0] = g.uniform(-5.09, -5.0, 1000).astype(np.float32)  # x index -1: numpy wraps to the last row
+    out = env.terrain.terrain_heights(torch.from_numpy(xy).cuda()).cpu().numpy()
+    bp, hs, vs = env.terrain.border_pixels, env.terrain.horizontal_scale, env.terrain.vertical_scale
+    x = bp + xy[:, 0] / hs
+    y = bp + xy[:, 1] / hs
+    assert x.dtype == np.float32
+    x1 = np.floor(x).astype(int); x2 = x1 + 1
+    y1 = np.floor(y).astype(int); y2 = y1 + 1
+    ref = (((x2 - x) * (y2 - y) * hf[x1, y1] + (x - x1) * (y2 - y) * hf[x2, y1] + (x2 - x) * (y - y1) * hf[x1, y2]
+            + (x - x1) * (y - y1) * hf[x2, y2]) * vs).astype(np.float32)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def test_standing_rollout_stays_up(t1_cfg):
+    """zero actions = PD to the default pose.  With the YAML's ankle gains (50 N m/rad) the stance is statically unstable
+    in any simulator (m g h ~ 186 N m/rad > 2 * 50), so this test stiffens the ankles and switches the model
+    randomisation off: then the robots must settle on their soles at z ~ 0.665 (FP64 oracle: 0.664-0.669, 155 N per
+    foot) and stay there, carrying their weight."""
+    n = 512
+    cfg = copy.deepcopy(t1_cfg)
+    for k in list(cfg["randomization"].keys()):
+        if isinstance(cfg["randomization"][k], dict):
+            cfg["randomization"][k] = None
+    env = make_env(cfg, n, control__stiffness={"Hip": 200.0, "Knee": 200.0, "Ankle": 400.0},
+                   control__damping={"Hip": 5.0, "Knee": 5.0, "Ankle": 5.0})
+    obs, extras = env.reset()
+    act = torch.zeros(n, 12, device="cuda")
+    dones = 0
+    for _ in range(100):
+        obs, rew, done, extras = env.step(act)
+        dones += int(done.sum().item())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    z = env.root_states[:, 2]
+    ff = env._fview("feet_force").sum(dim=1)
+    weight = 9.81 * env._fview("body_mass").sum(dim=1)
+    print("base z after 100 steps: min %.3f mean %.3f, resets %d, mean rew %.4f, foot force / weight %.3f"
+          % (z.min().item(), z.mean().item(), dones, rew.mean().item(), (ff / weight).mean().item()))
+    assert env._iview("nan_resets").sum().item() == 0
+    assert dones == 0
+    assert z.min().item() > 0.64 and z.max().item() < 0.69
+    assert abs((ff / weight).mean().item() - 1.0) < 0.05
+    assert env.feet_contact.bool().all()
+
+
+def test_randomised_rollout_is_finite_and_resets(t1_cfg):
+    """T1.yaml defaults (all DR, kicks, pushes, noise) with random actions on the heightfield: obs / rewards stay finite,
+    no env diverges (NaN guard counter stays 0), falls are caught by the termination rules and reset to the reference's
+    reset distribution, API tensors have the reference's shapes and dtypes."""
+    n = 1024
+    env = make_env(t1_cfg, n, terrain="trimesh")
+    obs, extras = env.reset()
+    assert obs.shape == (n, 47) and extras["privileged_obs"].shape == (n, 14)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dones = 0
+    for s in range(300):
+        act = torch.randn(n, 12, device="cuda", generator=g) * 0.5
+        obs, rew, done, extras = env.step(act)
+        dones += int(done.sum().item())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and torch.isfinite(extras["privileged_obs"]).all()
+        assert (rew >= 0).all()  # only_positive_rewards
+    assert done.dtype == torch.bool and extras["time_outs"].dtype == torch.bool and rew.dtype == torch.float32
+    assert env._iview("nan_resets").sum().item() == 0
+    assert dones > 0
+    assert set(extras["rew_terms"].keys()) == set(env.reward_names) and len(env.reward_names) == 23
+    assert (env.episode_length_buf <= 300).all() and (env.episode_length_buf >= 0).all()
+    stats, cnt = env.episode_stats()
+    assert cnt == dones and stats["steps"] > 0
