@@ -51,6 +51,9 @@ PROTOTYPES = {
     "b200_ppo_epoch_b": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_ppo_buffer": (_vp, [_vp, _i]),
     "b200_ppo_apply": (_i, [_vp, _vp]),
+    "b200_launch_count": (C.c_longlong, []),
+    "b200_profile_gemm": (_i, [_i]),
+    "b200_profile_gemm_read": (_i, [C.POINTER(_d), C.POINTER(_d), _ip]),
 }
 
 

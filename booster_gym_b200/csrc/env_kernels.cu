@@ -12,6 +12,7 @@
 #include "env_handle.cuh"
 
 using namespace b200;
+namespace b200 { extern long long g_launches; }
 
 __global__ void k_advance(long long* ctr, long long common_step, int bump_common) {
     if (bump_common) ctr[1] = (common_step >= 0) ? common_step : ctr[1] + 1;
@@ -205,6 +206,7 @@ int b200_t1_init_params(B200T1Handle* h, int env_index_base, int total_envs, voi
     h->total_envs = total_envs;
     cudaStream_t st = (cudaStream_t)stream;
     k_init_params<<<(h->num_envs + 127) / 128, 128, 0, st>>>(make_view(h), h->model, h->cfg);
+    g_launches += 1;
     return launch_status("k_init_params");
 }
 
@@ -215,6 +217,7 @@ int b200_t1_reset(B200T1Handle* h, float* obs, float* priv, void* stream) {
     k_advance<<<1, 1, 0, st>>>(h->ctr_dev, -1, 0);
     k_reset_all<<<(h->num_envs + POST_BLOCK - 1) / POST_BLOCK, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg,
                                                                                     make_terrain(h), h->ctr_dev, obs, priv);
+    g_launches += 2;
     return launch_status("k_reset_all");
 }
 
@@ -231,6 +234,7 @@ static int launch_post(B200T1Handle* h, float* obs, float* priv, float* rew, uin
         make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done, rew_terms,
         h->ctr_dev + 2, h->stats_dev);
     k_finalize_timeouts<<<(h->num_envs + 255) / 256, 256, 0, st>>>(h->istate, h->num_envs, h->ctr_dev, h->ctr_dev + 2, time_out);
+    g_launches += 2;
     return launch_status("k_post");
 }
 
@@ -240,6 +244,7 @@ int b200_t1_post_physics(B200T1Handle* h, float* obs, float* priv, float* rew, u
     if (!obs || !priv || !rew || !done || !time_out) return set_error(B200_ERR_ARG, "b200_t1_post_physics: null output");
     cudaStream_t st = (cudaStream_t)stream;
     k_advance<<<1, 1, 0, st>>>(h->ctr_dev, (long long)common_step, 1);
+    g_launches += 1;
     return launch_post(h, obs, priv, rew, done, time_out, rew_terms, noise_on, st);
 }
 
@@ -270,6 +275,7 @@ int b200_terrain_heights(const B200T1Handle* h, const float* xy, int stride, int
     if (!h || !xy || !out || stride < 2 || count < 0) return set_error(B200_ERR_ARG, "b200_terrain_heights: bad argument");
     if (count == 0) return B200_OK;
     k_terrain_heights<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_terrain(h), xy, stride, count, out);
+    g_launches += 1;
     return launch_status("k_terrain_heights");
 }
 

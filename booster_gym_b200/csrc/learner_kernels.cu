@@ -68,6 +68,7 @@ struct B200Ppo {
     float *params, *grads, *adam_m, *adam_v, *scalars;
     double* dstats;
     float* ws;
+    unsigned long long* act_ctr;  // device counter of b200_policy_act calls (RNG step when the caller passes B200_STEP_AUTO)
     Workspace w;
     float* P(int i) const { return params + kParams[i].offset; }
     float* G(int i) const { return grads + kParams[i].offset; }
@@ -148,10 +149,11 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, in
 
 // rollout sampling (utils/runner.py:110-111): act = mu + exp(logstd) * eps
 __global__ void k_sample(const float* __restrict__ mu, const float* __restrict__ logstd, const float* __restrict__ eps_in,
-                         int n, uint64_t seed, uint64_t step, int env_base, int deterministic, float* __restrict__ act,
-                         float* __restrict__ mu_out) {
+                         int n, uint64_t seed, uint64_t step, const unsigned long long* __restrict__ ctr, int env_base,
+                         int deterministic, float* __restrict__ act, float* __restrict__ mu_out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
+    if (ctr) step = (uint64_t)(*ctr);
     float eps[12];
     if (deterministic) {
 #pragma unroll
@@ -175,6 +177,8 @@ __global__ void k_sample(const float* __restrict__ mu, const float* __restrict__
         if (mu_out) mu_out[(size_t)e * 12 + j] = m;
     }
 }
+
+__global__ void k_bump(unsigned long long* ctr) { *ctr += 1ull; }
 
 #define LOG_SQRT_2PI 0.91893853320467274178f
 
@@ -439,6 +443,32 @@ __global__ void k_post_apply(float* __restrict__ scalars, const double* __restri
 }
 
 // =====================================================================================================================
+// measurement hooks: launch counter (bench.py "gpu_launches") and CUDA-event timing of every k_gemm3x launch on the
+// launching stream (bench.py "roofline": algorithmic FLOPs / measured duration of the dominant kernel)
+// =====================================================================================================================
+namespace b200 {
+long long g_launches = 0;
+}
+struct GemmProfile {
+    bool on = false;
+    int used = 0;
+    static const int kMax = 8192;
+    cudaEvent_t* ev = nullptr;  // 2 * kMax
+    double flops = 0.0;
+} g_prof;
+
+static void prof_begin(cudaStream_t st, double flops) {
+    if (!g_prof.on || g_prof.used >= GemmProfile::kMax) return;
+    cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
+    g_prof.flops += flops;
+}
+static void prof_end(cudaStream_t st) {
+    if (!g_prof.on || g_prof.used >= GemmProfile::kMax) return;
+    cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st);
+    g_prof.used += 1;
+}
+
+// =====================================================================================================================
 // dense layers on k_gemm3x
 // =====================================================================================================================
 #define CU_TRY(expr)                                                   \
@@ -455,7 +485,11 @@ static cudaError_t linear_fwd(const float* X, int ldx, int k_pad, const float* W
     g.I = n; g.Cn = n_out; g.R = k_pad;
     g.lda = ldx; g.ldb = k_valid; g.ldc = ldy; g.ldaux = 0;
     g.cn_store = n_out; g.r_chunk = 0; g.r_valid_b = k_valid;
-    return elu ? launch_gemm3x<false, false, EPI_BIAS_ELU>(g, 1, st) : launch_gemm3x<false, false, EPI_BIAS>(g, 1, st);
+    prof_begin(st, 2.0 * n * (double)n_out * k_valid);
+    const cudaError_t e = elu ? launch_gemm3x<false, false, EPI_BIAS_ELU>(g, 1, st) : launch_gemm3x<false, false, EPI_BIAS>(g, 1, st);
+    prof_end(st);
+    g_launches += 1;
+    return e;
 }
 // dX[n, k] = (dY[n, n_out] W[n_out, k]) * ELU'(H[n, k])
 static cudaError_t linear_dgrad(const float* dY, int ldy, int n_out, const float* W, int k, const float* H, int ldh,
@@ -465,7 +499,11 @@ static cudaError_t linear_dgrad(const float* dY, int ldy, int n_out, const float
     g.I = n; g.Cn = k; g.R = n_out;
     g.lda = ldy; g.ldb = k; g.ldc = ldx; g.ldaux = ldh;
     g.cn_store = k; g.r_chunk = 0; g.r_valid_b = 0;
-    return launch_gemm3x<false, true, EPI_ELU_GRAD>(g, 1, st);
+    prof_begin(st, 2.0 * n * (double)n_out * k);
+    const cudaError_t e = launch_gemm3x<false, true, EPI_ELU_GRAD>(g, 1, st);
+    prof_end(st);
+    g_launches += 1;
+    return e;
 }
 // dW[n_out, k_valid] += dY[n, n_out]^T X[n, k_pad]   (split over n, atomic accumulate; dW must be zeroed by the caller)
 #define WGRAD_CHUNK 1024
@@ -476,10 +514,15 @@ static cudaError_t linear_wgrad(const float* dY, int ldy, int n_out, const float
     g.I = n_out; g.Cn = k_pad; g.R = n;
     g.lda = ldy; g.ldb = ldx; g.ldc = k_valid; g.ldaux = 0;
     g.cn_store = k_valid; g.r_chunk = WGRAD_CHUNK; g.r_valid_b = 0;
-    return launch_gemm3x<true, true, EPI_ATOMIC>(g, (n + WGRAD_CHUNK - 1) / WGRAD_CHUNK, st);
+    prof_begin(st, 2.0 * n * (double)n_out * k_valid);
+    const cudaError_t e = launch_gemm3x<true, true, EPI_ATOMIC>(g, (n + WGRAD_CHUNK - 1) / WGRAD_CHUNK, st);
+    prof_end(st);
+    g_launches += 1;
+    return e;
 }
 static cudaError_t bias_grad(const float* dY, int ld, int C, int n, float* db, cudaStream_t st) {
     k_colsum<<<(n + CS_ROWS - 1) / CS_ROWS, 256, 0, st>>>(dY, n, C, ld, db);
+    g_launches += 1;
     return cudaPeekAtLastError();
 }
 
@@ -499,6 +542,7 @@ static int critic_forward(const B200Ppo* p, const float* Xc, int n, float* H1, f
     CU_TRY(linear_fwd(H1, 256, 256, p->P(P_CW1), 256, p->P(P_CB1), H2, 256, n, 256, true, st));
     CU_TRY(linear_fwd(H2, 256, 256, p->P(P_CW2), 256, p->P(P_CB2), H3, 128, n, 128, true, st));
     k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(H3, p->P(P_CW3), p->P(P_CB3), n, V);
+    g_launches += 1;
     return launch_status("k_value_head");
 }
 
@@ -538,10 +582,15 @@ int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float
     p->dstats = dstats;
     p->ws = (float*)workspace;
     p->w = make_workspace(cfg->horizon, cfg->num_envs);
+    p->act_ctr = nullptr;
+    cudaError_t ce = cudaMalloc(&p->act_ctr, sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(p->act_ctr, 0, sizeof(unsigned long long));
+    if (ce != cudaSuccess) { delete p; return set_cuda_error(ce, "b200_ppo_create: counter allocation"); }
     *out = p;
     return B200_OK;
 }
 int b200_ppo_destroy(B200Ppo* p) {
+    if (p && p->act_ctr) cudaFree(p->act_ctr);
     delete p;
     return B200_OK;
 }
@@ -556,8 +605,11 @@ int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* 
     float* ws = p->ws;
     const int rc = actor_forward(p, obs, 47, 47, n, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, ws + p->w.LMU, st);
     if (rc != B200_OK) return rc;
-    k_sample<<<(n + 127) / 128, 128, 0, st>>>(ws + p->w.LMU, p->P(P_LOGSTD), eps_in, n, seed, step, p->cfg.env_base,
-                                              deterministic, actions, mu_out);
+    const bool auto_step = (step == B200_STEP_AUTO);
+    k_sample<<<(n + 127) / 128, 128, 0, st>>>(ws + p->w.LMU, p->P(P_LOGSTD), eps_in, n, seed, step,
+                                              auto_step ? p->act_ctr : nullptr, p->cfg.env_base, deterministic, actions, mu_out);
+    if (auto_step) k_bump<<<1, 1, 0, st>>>(p->act_ctr);
+    g_launches += auto_step ? 2 : 1;
     return launch_status("k_sample");
 }
 
@@ -567,6 +619,7 @@ int b200_critic_value(B200Ppo* p, const float* obs, const float* priv, int n, fl
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     k_pack_inputs<<<(int)(((size_t)n * 64 + 255) / 256), 256, 0, st>>>(obs, priv, n, nullptr, ws + p->w.LXc);
+    g_launches += 1;
     return critic_forward(p, ws + p->w.LXc, n, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, values, st);
 }
 
@@ -581,6 +634,7 @@ int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const 
     const int rc = actor_forward(p, ws + p->w.Xa, 48, 48, M, ws + p->w.A1, ws + p->w.A2, ws + p->w.A3, ws + p->w.MU, st);
     if (rc != B200_OK) return rc;
     k_old_logp<<<(M + 255) / 256, 256, 0, st>>>(ws + p->w.MU, actions, p->P(P_LOGSTD), M, old_mu, old_logp, p->scalars);
+    g_launches += 2;  // + k_pack_inputs
     return launch_status("k_old_logp");
 }
 
@@ -592,6 +646,7 @@ int b200_gae(float* rewards, const uint8_t* dones, const uint8_t* time_outs, con
     k_gae<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, dones, time_outs, values, last_values,
                                                                       (float)gamma, (float)(gamma * lam), horizon,
                                                                       num_envs, advantages, returns, stats);
+    g_launches += 1;
     return launch_status("k_gae");
 }
 
@@ -610,6 +665,7 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     if (rc != B200_OK) return rc;
     k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.LV, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
+    g_launches += 3;  // memset, k_pack_inputs, k_gae
     return launch_status("k_gae");
 }
 
@@ -629,6 +685,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
                                                                     old_mu, old_logp, p->P(P_LOGSTD), p->scalars, p->dstats,
                                                                     M, p->cfg.e_clip, p->cfg.bound_coef, DV, DMU);
     k_finalize_logstd<<<1, 32, 0, st>>>(p->dstats, p->cfg.entropy_coef, p->G(P_LOGSTD));
+    g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
     // ---- actor backward
     CU_TRY(linear_wgrad(DMU, 12, 12, A3, 128, 128, 128, p->G(P_AW3), M, st));
@@ -644,6 +701,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     CU_TRY(bias_grad(G1, 256, 256, M, p->G(P_AB0), st));
     // ---- critic backward
     k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3));
+    g_launches += 1;
     if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
     CU_TRY(linear_wgrad(G1, 128, 128, C2, 256, 256, 256, p->G(P_CW2), M, st));
     CU_TRY(bias_grad(G1, 128, 128, M, p->G(P_CB2), st));
@@ -672,7 +730,35 @@ int b200_ppo_apply(B200Ppo* p, void* stream) {
                                                          p->dstats, inv_world, p->cfg.max_grad_norm, p->cfg.adam_beta1,
                                                          p->cfg.adam_beta2, p->cfg.adam_eps);
     k_post_apply<<<1, 32, 0, st>>>(p->scalars, p->dstats, p->cfg.desired_kl, p->cfg.lr_min, p->cfg.lr_max, p->cfg.lr_factor);
+    g_launches += 3;
     return launch_status("b200_ppo_apply");
+}
+
+long long b200_launch_count(void) { return g_launches; }
+
+int b200_profile_gemm(int enable) {
+    if (enable && !g_prof.ev) {
+        g_prof.ev = new (std::nothrow) cudaEvent_t[2 * GemmProfile::kMax];
+        if (!g_prof.ev) return set_error(B200_ERR_ARG, "out of host memory");
+        for (int i = 0; i < 2 * GemmProfile::kMax; ++i) CUDA_TRY(cudaEventCreate(&g_prof.ev[i]));
+    }
+    g_prof.on = enable != 0;
+    g_prof.used = 0;
+    g_prof.flops = 0.0;
+    return B200_OK;
+}
+int b200_profile_gemm_read(double* total_ms, double* total_flops, int* launches) {
+    double ms = 0.0;
+    for (int i = 0; i < g_prof.used; ++i) {
+        CUDA_TRY(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+        ms += (double)t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = g_prof.flops;
+    if (launches) *launches = g_prof.used;
+    return B200_OK;
 }
 
 float* b200_ppo_buffer(B200Ppo* p, int which) {

@@ -8,6 +8,7 @@
 #include "env_handle.cuh"
 
 using namespace b200;
+namespace b200 { extern long long g_launches; }
 
 // ---- mass-matrix storage in shared memory: element idx of lane l at sm[idx * 32 + l] -------------------------------
 struct MShared {
@@ -53,6 +54,7 @@ int launch_physics(B200T1Handle* h, const float* actions, int n_substeps, int ap
     k_physics<<<(h->num_envs + PHYS_BLOCK - 1) / PHYS_BLOCK, PHYS_BLOCK, 0, st>>>(
         make_view(h), h->model, h->cfg, make_terrain(h), actions, n_substeps, apply_pd, qacc_out, h->ctr_dev,
         common_step, advance);
+    g_launches += 1;
     return launch_status("k_physics");
 }
 }  // namespace b200

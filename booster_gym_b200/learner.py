@@ -72,8 +72,7 @@ class Learner:
     # ---- kernels -------------------------------------------------------------------------------------------------------
     def act(self, obs, actions_out, mu_out=None, eps=None, deterministic=False, step=None):
         if step is None:
-            step = self.act_step
-            self.act_step += 1
+            step = 0xFFFFFFFFFFFFFFFF  # B200_STEP_AUTO: device-side counter, so captured graphs draw fresh noise on replay
         _lib.check(self._lib.b200_policy_act(self._h, obs.data_ptr(), obs.shape[0], actions_out.data_ptr(),
                                              mu_out.data_ptr() if mu_out is not None else None,
                                              eps.data_ptr() if eps is not None else None, self.seed, int(step),

@@ -1,0 +1,261 @@
+"""Runner: the PPO training / play loop behind the interface of utils/runner.py:19-245.
+
+Same constructor (`Runner(test)`; argparse flags `--task --checkpoint --num_envs --headless --sim_device --rl_device
+--seed --max_iterations`, YAML `envs/<task>.yaml`), same `train()` / `play()`, same checkpoint dict, same logged scalar
+keys.  What differs is WHERE the arithmetic runs: every tensor operation between `train()` entry and the optimizer step
+is a kernel of libb200t1.so launched on torch's current stream (policy forward + sampling, env step, GAE, the epoch's
+forward / losses / backward, clip + Adam + KL learning-rate rule); the host reads device scalars once per iteration.
+
+Multi-GPU: launched with torchrun, one process per GPU; rank r simulates envs [r*N, (r+1)*N) of a global
+layout of world*N envs; per epoch the advantage moments (3 doubles) are sum-all-reduced before the loss and the flat
+gradient buffer plus the loss sums (for the KL rule) after the backward pass; every rank then applies the identical
+clip + Adam step.  NCCL over NVLink; nothing else crosses ranks.
+"""
+import argparse
+import glob
+import os
+import random
+import time
+
+import numpy as np
+import torch
+import yaml
+
+from .. import _abi
+from ..envs import T1  # noqa: F401  (task classes are resolved by name)
+from ..learner import Learner
+from .buffer import ExperienceBuffer
+from .model import ActorCritic
+from .recorder import Recorder
+
+TASKS = {"T1": T1}
+
+
+class FlatAdam:
+    """torch.optim.Adam-shaped facade over the learner's flat Adam buffers: `state_dict()` / `load_state_dict()` use the
+    layout torch.optim.Adam(model.parameters()) produces for the reference model, so `.pth` files interchange."""
+
+    def __init__(self, model, learner):
+        self.model, self.learner = model, learner
+
+    @property
+    def param_groups(self):
+        lr = float(self.learner.scalars[_abi.SC["LR"]].item())
+        n = len(list(self.model.parameters()))
+        return [dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                     capturable=False, differentiable=False, fused=None, params=list(range(n)))]
+
+    def state_dict(self):
+        m, v = self.learner.views(self.learner.adam_m), self.learner.views(self.learner.adam_v)
+        step = self.learner.scalars[_abi.SC["ADAM_STEP"]].detach().cpu().clone()
+        state = {}
+        if step.item() > 0:
+            for i, (name, _) in enumerate(self.model.named_parameters()):
+                state[i] = {"step": step.clone(), "exp_avg": m[name].clone().reshape(getattr_path(self.model, name).shape),
+                            "exp_avg_sq": v[name].clone().reshape(getattr_path(self.model, name).shape)}
+        return {"state": state, "param_groups": self.param_groups}
+
+    def load_state_dict(self, sd):
+        m, v = self.learner.views(self.learner.adam_m), self.learner.views(self.learner.adam_v)
+        names = [n for n, _ in self.model.named_parameters()]
+        for i, st in sd["state"].items():
+            name = names[int(i)]
+            m[name].copy_(st["exp_avg"].to(m[name].device).reshape(m[name].shape))
+            v[name].copy_(st["exp_avg_sq"].to(v[name].device).reshape(v[name].shape))
+            self.learner.scalars[_abi.SC["ADAM_STEP"]] = float(st["step"])
+        if sd.get("param_groups"):
+            self.learner.set_lr(sd["param_groups"][0]["lr"])
+
+
+def getattr_path(obj, path):
+    for part in path.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+class Runner:
+
+    def __init__(self, test=False, argv=None, cfg_overrides=None):
+        self.test = test
+        self._get_args(argv)
+        self._update_cfg_from_args()
+        for section, values in (cfg_overrides or {}).items():  # programmatic use (bench.py, tests): {"terrain": {"type": "plane"}}
+            self.cfg[section].update(values)
+        self._init_distributed()
+        self._set_seed()
+        task_class = TASKS.get(self.cfg["basic"]["task"])
+        if task_class is None:
+            raise NameError(f"name '{self.cfg['basic']['task']}' is not defined")
+        n = self.cfg["env"]["num_envs"]
+        self.env = task_class(self.cfg, env_index_base=self.rank * n, total_envs=self.world_size * n)
+
+        self.device = self.cfg["basic"]["rl_device"]
+        if torch.device(self.device) != torch.device(self.env.device):
+            raise ValueError("rl_device must equal sim_device: rollout tensors never leave the GPU in this implementation")
+        self.learning_rate = self.cfg["algorithm"]["learning_rate"]
+        self.learner = Learner(self.cfg, self.env.num_envs, self.device, world_size=self.world_size,
+                               env_base=self.rank * n, learning_rate=self.learning_rate, seed=self.cfg["basic"]["seed"])
+        self.model = ActorCritic(self.env.num_actions, self.env.num_obs, self.env.num_privileged_obs).bind(self.learner)
+        if self.world_size > 1:
+            torch.distributed.broadcast(self.learner.params, src=0)
+        self.optimizer = FlatAdam(self.model, self.learner)
+        self._load()
+
+        self.buffer = ExperienceBuffer(self.cfg["runner"]["horizon_length"], self.env.num_envs, self.device)
+        self.buffer.add_buffer("actions", (self.env.num_actions,))
+        self.buffer.add_buffer("obses", (self.env.num_obs,))
+        self.buffer.add_buffer("privileged_obses", (self.env.num_privileged_obs,))
+        self.buffer.add_buffer("rewards", ())
+        self.buffer.add_buffer("dones", (), dtype=bool)
+        self.buffer.add_buffer("time_outs", (), dtype=bool)
+
+    # ---- configuration (same flags / YAML handling as the reference) ---------------------------------------------
+    def _get_args(self, argv=None):
+        parser = argparse.ArgumentParser()
+        parser.add_argument("--task", required=True, type=str, help="Name of the task to run.")
+        parser.add_argument("--checkpoint", type=str, help="Path of the model checkpoint to load. Overrides config file if provided.")
+        parser.add_argument("--num_envs", type=int, help="Number of environments to create. Overrides config file if provided.")
+        parser.add_argument("--headless", type=bool, help="Run headless without creating a viewer window. Overrides config file if provided.")
+        parser.add_argument("--sim_device", type=str, help="Device for physics simulation. Overrides config file if provided.")
+        parser.add_argument("--rl_device", type=str, help="Device for the RL algorithm. Overrides config file if provided.")
+        parser.add_argument("--seed", type=int, help="Random seed. Overrides config file if provided.")
+        parser.add_argument("--max_iterations", type=int, help="Maximum number of training iterations. Overrides config file if provided.")
+        self.args = parser.parse_args(argv)
+
+    def _update_cfg_from_args(self):
+        cfg_file = os.path.join("envs", "{}.yaml".format(self.args.task))
+        with open(cfg_file, "r", encoding="utf-8") as f:
+            self.cfg = yaml.load(f.read(), Loader=yaml.FullLoader)
+        for arg, val in vars(self.args).items():
+            if val is None:
+                continue
+            section = "env" if arg == "num_envs" else "basic"
+            self.cfg[section][arg] = val
+        if not self.test:
+            self.cfg["viewer"]["record_video"] = False
+
+    def _init_distributed(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        if self.world_size > 1:
+            local = int(os.environ.get("LOCAL_RANK", str(self.rank)))
+            dev = f"cuda:{local}"
+            self.cfg["basic"]["sim_device"] = dev
+            self.cfg["basic"]["rl_device"] = dev
+            torch.cuda.set_device(local)
+            if not torch.distributed.is_initialized():
+                torch.distributed.init_process_group(backend="nccl", device_id=torch.device(dev))
+
+    def _set_seed(self):
+        if self.cfg["basic"]["seed"] == -1:
+            self.cfg["basic"]["seed"] = np.random.randint(0, 10000)
+        seed = self.cfg["basic"]["seed"]
+        if self.rank == 0:
+            print("Setting seed: {}".format(seed))
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        os.environ["PYTHONHASHSEED"] = str(seed)
+        torch.cuda.manual_seed_all(seed)
+
+    def _load(self):
+        ckpt = self.cfg["basic"]["checkpoint"]
+        if not ckpt:
+            return
+        if ckpt == "-1" or ckpt == -1:
+            ckpt = sorted(glob.glob(os.path.join("logs", "**/*.pth"), recursive=True), key=os.path.getmtime)[-1]
+            self.cfg["basic"]["checkpoint"] = ckpt
+        print("Loading model from {}".format(ckpt))
+        model_dict = torch.load(ckpt, map_location=self.device, weights_only=True)
+        self.model.load_state_dict(model_dict["model"], strict=False)
+        try:
+            self.env.curriculum_prob = model_dict["curriculum"]
+        except Exception as e:
+            print(f"Failed to load curriculum: {e}")
+        try:
+            self.optimizer.load_state_dict(model_dict["optimizer"])
+        except Exception as e:
+            print(f"Failed to load optimizer: {e}")
+
+    # ---- the loop ----------------------------------------------------------------------------------------------------
+    def rollout(self, obs, privileged_obs):
+        """utils/runner.py:106-121: horizon_length x [store obs, act, env.step, store transition]"""
+        buf, env, lrn = self.buffer, self.env, self.learner
+        for n in range(self.cfg["runner"]["horizon_length"]):
+            buf.update_data("obses", n, obs)
+            buf.update_data("privileged_obses", n, privileged_obs)
+            act = buf["actions"][n]
+            lrn.act(obs, act)                      # mu = actor(obs); act = mu + sigma * eps, written into the buffer row
+            obs, rew, done, infos = env.step(act, _device_counter=True)
+            privileged_obs = infos["privileged_obs"]
+            buf.update_data("rewards", n, rew)
+            buf.update_data("dones", n, done)
+            buf.update_data("time_outs", n, infos["time_outs"])
+        return obs, privileged_obs
+
+    def update(self, obs, privileged_obs):
+        """utils/runner.py:123-185: old distribution, then mini_epochs x [values, GAE, losses, backward, clip, Adam, KL]"""
+        buf, lrn = self.buffer, self.learner
+        lrn.old_dist(buf["obses"], buf["privileged_obses"], buf["actions"])
+        dones, touts = buf.raw("dones"), buf.raw("time_outs")
+        multi = self.world_size > 1
+        for _ in range(self.cfg["runner"]["mini_epochs"]):
+            lrn.epoch_a(buf["rewards"], dones, touts, obs, privileged_obs)
+            if multi:
+                torch.distributed.all_reduce(lrn.dstats[0:4])
+            lrn.epoch_b(buf["actions"])
+            if multi:
+                torch.distributed.all_reduce(lrn.grads)
+                torch.distributed.all_reduce(lrn.dstats[4:10])
+            lrn.apply()
+
+    def train(self):
+        self.recorder = Recorder(self.cfg) if self.rank == 0 else None
+        obs, infos = self.env.reset()
+        privileged_obs = infos["privileged_obs"]
+        SC = _abi.SC
+        for it in range(self.cfg["basic"]["max_iterations"]):
+            obs, privileged_obs = self.rollout(obs, privileged_obs)
+            self.learner.scalars[SC["SUM_VALUE_LOSS"]:SC["EPOCHS"] + 1].zero_()
+            self.update(obs, privileged_obs)
+            sc = self.learner.scalars.cpu()  # the one host sync of the iteration
+            epochs = max(1.0, sc[SC["EPOCHS"]].item())
+            self.learning_rate = sc[SC["LR"]].item()
+            kl_mean = sc[SC["KL"]].item()
+            ep_means, ep_count = self.env.episode_stats()
+            self.env.common_step_counter = self.env.counters()[1]
+            if self.recorder is not None:
+                self.recorder.record_episode_summary(ep_means, ep_count, it)
+                self.recorder.record_statistics(
+                    {
+                        "value_loss": sc[SC["SUM_VALUE_LOSS"]].item() / epochs,
+                        "actor_loss": sc[SC["SUM_ACTOR_LOSS"]].item() / epochs,
+                        "bound_loss": sc[SC["SUM_BOUND_LOSS"]].item() / epochs,
+                        "entropy": sc[SC["SUM_ENTROPY"]].item() / epochs,
+                        "kl_mean": kl_mean,
+                        "lr": self.learning_rate,
+                        "curriculum/mean_lin_vel_level": self.env.mean_lin_vel_level,
+                        "curriculum/mean_ang_vel_level": self.env.mean_ang_vel_level,
+                        "curriculum/max_lin_vel_level": self.env.max_lin_vel_level,
+                        "curriculum/max_ang_vel_level": self.env.max_ang_vel_level,
+                    },
+                    it,
+                )
+                if (it + 1) % self.cfg["runner"]["save_interval"] == 0:
+                    self.recorder.save(
+                        {"model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(),
+                         "curriculum": self.env.curriculum_prob},
+                        it + 1,
+                    )
+                print("epoch: {}/{}".format(it + 1, self.cfg["basic"]["max_iterations"]))
+
+    def play(self, max_steps=None):
+        obs, infos = self.env.reset()
+        act = torch.empty(self.env.num_envs, self.env.num_actions, dtype=torch.float32, device=self.device)
+        steps = 0
+        if self.cfg["viewer"]["record_video"]:
+            print("record_video is ignored: this implementation has no renderer")
+        while max_steps is None or steps < max_steps:
+            self.learner.act(obs, act, deterministic=True)   # dist.loc (utils/runner.py:226-227)
+            obs, rew, done, infos = self.env.step(act)
+            steps += 1

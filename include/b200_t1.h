@@ -226,7 +226,9 @@ enum { /* rows of the device `dstats` array (sums; cleared by b200_ppo_epoch_a) 
 };
 
 /* replaces model.act(obs).sample() (utils/runner.py:109-111): mu = actor(obs); act = mu + exp(logstd)*eps.
- * eps drawn in-kernel (Philox, keyed by seed/env/step) unless eps_in != NULL. deterministic != 0 -> act = mu (play). */
+ * eps drawn in-kernel (Philox, keyed by seed/env/step) unless eps_in != NULL. deterministic != 0 -> act = mu (play).
+ * step = B200_STEP_AUTO: the RNG step is a device-side counter incremented by every such call (CUDA-graph replayable). */
+#define B200_STEP_AUTO 0xFFFFFFFFFFFFFFFFull
 int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* mu_out /*nullable*/,
                     const float* eps_in /*nullable*/, uint64_t seed, uint64_t step, int deterministic, void* stream);
 /* replaces est_value (utils/model.py:34-36) */
@@ -256,6 +258,15 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
 float* b200_ppo_buffer(B200Ppo* p, int which);
 /* replaces utils/runner.py:162-180: clip_grad_norm_(1.0), Adam step, KL-adaptive learning rate (all on device) */
 int b200_ppo_apply(B200Ppo* p, void* stream);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------------------
+ * b200_launch_count: kernels (and memset nodes) this library has launched in the calling process so far.
+ * b200_profile_gemm(1): bracket every following tensor-core GEMM launch with CUDA events on its stream (up to 8192
+ * launches); b200_profile_gemm_read() synchronises them and returns summed duration, algorithmic FLOPs
+ * (2 * rows * out * reduction, unpadded, counted once - not 3x for the split) and the number of launches. */
+long long b200_launch_count(void);
+int b200_profile_gemm(int enable);
+int b200_profile_gemm_read(double* total_ms, double* total_flops, int* launches);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,8 @@ def epoch(sd, adam, buf, last_obs, last_priv, old_mu, old_sigma, old_logp, lr, g
         adv = (adv_raw - adv_raw.mean()) / (adv_raw.std() + 1e-8)
     value_loss = ((values - returns) ** 2).mean()
     mu = actor_mean(params, obses)
+    mu.retain_grad()
+    values.retain_grad()
     sigma = torch.exp(params["logstd"]).expand_as(mu)
     logp = normal_log_prob(actions, mu, sigma).sum(dim=-1)
     actor_loss = surrogate(old_logp, logp, adv)
@@ -150,7 +152,7 @@ def epoch(sd, adam, buf, last_obs, last_priv, old_mu, old_sigma, old_logp, lr, g
     return dict(values=values.detach(), last_values=last_values.detach(), adv_raw=adv_raw, returns=returns, adv=adv,
                 mu=mu.detach(), logp=logp.detach(), value_loss=value_loss.item(), actor_loss=actor_loss.item(),
                 bound_loss=bound_loss.item(), entropy=entropy.mean().item(), kl=kl_mean.item(), grads=grads,
-                grad_norm=float(total_norm), lr=new_lr)
+                grad_norm=float(total_norm), lr=new_lr, dmu=mu.grad.detach().clone(), dvalues=values.grad.detach().clone())
 
 
 def new_adam(sd):

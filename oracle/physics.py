@@ -16,6 +16,28 @@ def build(force=False):
     return _SO
 
 
+_PORT_SO = os.path.join(_HERE, "liboracle_port.so")
+
+
+def build_port(force=False):
+    """the -O3 host build of the product's recursion used ONLY as the timed CPU baseline (oracle/physics_port.cpp)"""
+    src = os.path.join(_HERE, "physics_port.cpp")
+    deps = [src, os.path.join(_HERE, "..", "booster_gym_b200", "csrc", "t1_dynamics.cuh")]
+    if force or not os.path.exists(_PORT_SO) or any(os.path.getmtime(_PORT_SO) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", _PORT_SO, src, "-lm"])
+    return _PORT_SO
+
+
+_port = None
+
+
+def port_lib():
+    global _port
+    if _port is None:
+        _port = C.CDLL(build_port())
+    return _port
+
+
 class Env(C.Structure):
     _fields_ = [("pos", C.c_double * 3), ("quat", C.c_double * 4), ("vlin", C.c_double * 3), ("wb", C.c_double * 3),
                 ("q", C.c_double * 12), ("qd", C.c_double * 12), ("mass", C.c_double * 13), ("com", C.c_double * 3 * 13),
