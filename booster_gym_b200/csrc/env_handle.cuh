@@ -19,6 +19,7 @@ struct B200T1Handle {
     int hf_rows, hf_cols;
     long long* ctr_dev;   // [0] rng step, [1] common_step_counter, [2..3] any-reset flags (parity)
     double* stats_dev;    // [1 + n_rew + 1] episode sums, then count as double
+    const uint32_t* inject;  // parity-test hook (b200_t1_inject_rng); null in production
 };
 
 namespace b200 {
@@ -39,6 +40,7 @@ inline EnvView make_view(const B200T1Handle* h) {
     v.n = h->num_envs;
     v.env_base = h->env_base;
     v.seed = h->seed;
+    v.inject = h->inject;
     return v;
 }
 // defined in physics_kernels.cu

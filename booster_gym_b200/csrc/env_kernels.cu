@@ -194,6 +194,12 @@ int b200_t1_bind_state(B200T1Handle* h, float* fstate, int32_t* istate) {
     h->istate = istate;
     return B200_OK;
 }
+int b200_t1_inject_rng(B200T1Handle* h, const uint32_t* table) {
+    if (!h) return set_error(B200_ERR_ARG, "null handle");
+    h->inject = table;
+    return B200_OK;
+}
+int b200_t1_rng_slots(void) { return B200_RNG_SLOTS; }
 int b200_t1_num_envs(const B200T1Handle* h) { return h ? h->num_envs : B200_ERR_ARG; }
 
 #define NEED_STATE(h)                                                                  \

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict_
 }
 
 // bias gradient: db[c] += sum over rows of dY[r,c]   (C <= 256; 256 threads, rows split over blockDim/Cp row-lanes)
-#define CS_ROWS 1024
+#define CS_ROWS 256
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, int n, int C, int ld, float* __restrict__ db) {
     __shared__ double red[256];
     int Cp = 1;

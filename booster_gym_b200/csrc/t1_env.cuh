@@ -5,6 +5,8 @@
 // Order of operations, quirks and fp32 operation order follow the reference line by line (citations inline;
 // SURVEY 8a notes 1-11).  The host build in tests/hostcheck is test infrastructure only.
 #pragma once
+#include <string.h>
+
 #include "rng.cuh"
 #include "t1_dynamics.cuh"
 #include "t1_state.h"
@@ -21,7 +23,57 @@ struct EnvView {
     int n;             // envs in this shard
     int env_base;      // global index of env 0 of this shard (RNG counter)
     uint64_t seed;
+    // Parity-test hook: when non-null, step-time random draws are READ from this table instead of generated, so the
+    // kernel, the CPU oracle and the reference (with torch.randn_like & co. patched) run on identical samples.
+    // Layout: uint32 [B200_RNG_SLOTS][12][n]: per slot 4 raw words, 4 uniforms (float bits), 4 normals (float bits).
+    const uint32_t* inject;
 };
+
+// slot of a step-time draw in the injection table; -1 for the one-off construction draws (never injected)
+B200_HD int rng_slot(int purpose, int sub) {
+    switch (purpose) {
+        case RP_RESET_DOF: return 0 + sub;   // 0..2
+        case RP_RESET_ROOT: return 3 + sub;  // 3..4
+        case RP_RESET_DELAY: return 5;
+        case RP_COMMAND: return 6 + sub;     // 6..7
+        case RP_KICK: return 8 + sub;        // 8..9
+        case RP_PUSH: return 10 + sub;       // 10..11
+        case RP_OBS_NOISE: return 12 + sub;  // 12..20
+    }
+    return -1;
+}
+#define B200_RNG_SLOTS 21
+
+struct Draw {
+    Philox4 p;
+    Rand4 r;
+};
+B200_HD float bits_to_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+B200_HD Draw env_draw(const EnvView& v, int e, uint32_t env_key, uint64_t step, int purpose, int sub) {
+    Draw d;
+    const int slot = v.inject ? rng_slot(purpose, sub) : -1;
+    if (slot >= 0) {
+        const uint32_t* base = v.inject + ((size_t)slot * 12) * (size_t)v.n + (size_t)e;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            d.p.w[l] = base[(size_t)l * v.n];
+            d.r.u[l] = bits_to_float(base[(size_t)(4 + l) * v.n]);
+            d.r.n[l] = bits_to_float(base[(size_t)(8 + l) * v.n]);
+        }
+    } else {
+        d.p = rng_words(v.seed, env_key, step, purpose, sub);
+        d.r = rand4(d.p);
+    }
+    return d;
+}
 
 // ---- Isaac Gym torch_utils semantics (third-party, restated) ---------------------------------------
 B200_HD void quat_rotate_inverse(const float* q, const float* v, float* o) {
@@ -289,7 +341,7 @@ B200_HD void env_reset_one(const EnvView& v, int e, const B200T1Config& c, const
     // only (env id B200_RNG_SHARED_ENV), not by the env.
 #pragma unroll
     for (int sub = 0; sub < 3; ++sub) {
-        const Rand4 r = rand4(rng_words(v.seed, B200_RNG_SHARED_ENV, step, RP_RESET_DOF, sub));
+        const Rand4 r = env_draw(v, e, B200_RNG_SHARED_ENV, step, RP_RESET_DOF, sub).r;
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const int j = 4 * sub + l;
@@ -298,8 +350,8 @@ B200_HD void env_reset_one(const EnvView& v, int e, const B200T1Config& c, const
         }
     }
     // _reset_root_states :327-341
-    const Rand4 r0 = rand4(rng_words(v.seed, ge, step, RP_RESET_ROOT, 0));
-    const Rand4 r1 = rand4(rng_words(v.seed, ge, step, RP_RESET_ROOT, 1));
+    const Rand4 r0 = env_draw(v, e, ge, step, RP_RESET_ROOT, 0).r;
+    const Rand4 r1 = env_draw(v, e, ge, step, RP_RESET_ROOT, 1).r;
     float x = c.init_root[0] + FS(F_env_origins + 0);
     float y = c.init_root[1] + FS(F_env_origins + 1);
     x = apply_rand(x, c.init_base_pos_xy, r0.u[0], r0.n[0]);
@@ -331,7 +383,7 @@ B200_HD void env_reset_one(const EnvView& v, int e, const B200T1Config& c, const
 #pragma unroll
     for (int r = 0; r < 3; ++r) { FS(F_filtered_lin_vel + r) = 0.0f; FS(F_filtered_ang_vel + r) = 0.0f; }
     IS(I_cmd_resample_time) = 0;
-    const Philox4 d = rng_words(v.seed, ge, step, RP_RESET_DELAY, 0);
+    const Philox4 d = env_draw(v, e, ge, step, RP_RESET_DELAY, 0).p;
     IS(I_delay_steps) = (int32_t)(d.w[0] % (uint32_t)c.decimation);
 }
 
@@ -341,19 +393,19 @@ B200_HD void env_resample_command(const EnvView& v, int e, const B200T1Config& c
     int32_t* is = v.is;
     const int n = v.n;
     const uint32_t ge = (uint32_t)(v.env_base + e);
-    const Philox4 w0 = rng_words(v.seed, ge, step, RP_COMMAND, 0);
-    const Philox4 w1 = rng_words(v.seed, ge, step, RP_COMMAND, 1);
+    const Draw d0 = env_draw(v, e, ge, step, RP_COMMAND, 0);
+    const Draw d1 = env_draw(v, e, ge, step, RP_COMMAND, 1);
     // torch_rand_float(lo, hi) = (hi - lo) * rand + lo
-    float cx = (c.lin_vel_x[1] - c.lin_vel_x[0]) * u01(w0.w[0]) + c.lin_vel_x[0];
-    float cy = (c.lin_vel_y[1] - c.lin_vel_y[0]) * u01(w0.w[1]) + c.lin_vel_y[0];
-    float cz = (c.ang_vel_yaw[1] - c.ang_vel_yaw[0]) * u01(w0.w[2]) + c.ang_vel_yaw[0];
-    float gf = (c.gait_frequency[1] - c.gait_frequency[0]) * u01(w0.w[3]) + c.gait_frequency[0];
+    float cx = (c.lin_vel_x[1] - c.lin_vel_x[0]) * d0.r.u[0] + c.lin_vel_x[0];
+    float cy = (c.lin_vel_y[1] - c.lin_vel_y[0]) * d0.r.u[1] + c.lin_vel_y[0];
+    float cz = (c.ang_vel_yaw[1] - c.ang_vel_yaw[0]) * d0.r.u[2] + c.ang_vel_yaw[0];
+    float gf = (c.gait_frequency[1] - c.gait_frequency[0]) * d0.r.u[3] + c.gait_frequency[0];
     // reference: an exact still_proportion of the resampled envs via randperm (:381); here an independent Bernoulli
     // draw per env (no cross-env dependency on the device) - DESIGN.md "deviations"
-    if (u01(w1.w[0]) < c.still_proportion) { cx = cy = cz = 0.0f; gf = 0.0f; }
+    if (d1.r.u[0] < c.still_proportion) { cx = cy = cz = 0.0f; gf = 0.0f; }
     FS(F_commands + 0) = cx; FS(F_commands + 1) = cy; FS(F_commands + 2) = cz;
     FS(F_gait_frequency) = gf;
-    IS(I_cmd_resample_time) += c.resample_lo + (int32_t)(w1.w[1] % (uint32_t)(c.resample_hi - c.resample_lo));
+    IS(I_cmd_resample_time) += c.resample_lo + (int32_t)(d1.p.w[1] % (uint32_t)(c.resample_hi - c.resample_lo));
 }
 
 // envs/t1.py:574-603.  obs[47], priv[14] are this env's rows.
@@ -368,7 +420,7 @@ B200_HD void env_observations(const EnvView& v, int e, const B200T1Config& c, co
     if (noise_on) {
 #pragma unroll
         for (int sub = 0; sub < 9; ++sub) {
-            const Rand4 r = rand4(rng_words(v.seed, ge, step, RP_OBS_NOISE, sub));
+            const Rand4 r = env_draw(v, e, ge, step, RP_OBS_NOISE, sub).r;
 #pragma unroll
             for (int l = 0; l < 4; ++l) { un[4 * sub + l] = r.u[l]; nn[4 * sub + l] = r.n[l]; }
         }
@@ -481,8 +533,8 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     FS(F_gait_process) = fmodf(FS(F_gait_process) + c.env_dt * FS(F_gait_frequency), 1.0f);
     // _kick_robots :499-504
     if (c.kick_interval > 0 && (common_step % c.kick_interval) == 0) {
-        const Rand4 a = rand4(rng_words(v.seed, ge, step, RP_KICK, 0));
-        const Rand4 b = rand4(rng_words(v.seed, ge, step, RP_KICK, 1));
+        const Rand4 a = env_draw(v, e, ge, step, RP_KICK, 0).r;
+        const Rand4 b = env_draw(v, e, ge, step, RP_KICK, 1).r;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             FS(F_root_states + 7 + r) = apply_rand(FS(F_root_states + 7 + r), c.kick_lin_vel, a.u[r], a.n[r]);
@@ -493,8 +545,8 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     if (c.push_interval > 0) {
         const int64_t ph = common_step % c.push_interval;
         if (ph == 0) {
-            const Rand4 a = rand4(rng_words(v.seed, ge, step, RP_PUSH, 0));
-            const Rand4 b = rand4(rng_words(v.seed, ge, step, RP_PUSH, 1));
+            const Rand4 a = env_draw(v, e, ge, step, RP_PUSH, 0).r;
+            const Rand4 b = env_draw(v, e, ge, step, RP_PUSH, 1).r;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 FS(F_pushing_forces + r) = apply_rand(0.0f, c.push_force, a.u[r], a.n[r]);

@@ -175,6 +175,13 @@ int b200_terrain_heights(const B200T1Handle* h, const float* xy, int stride, int
  * out is DEVICE float/uint32 [4][N]. */
 int b200_rng_fill(const B200T1Handle* h, uint64_t step, int purpose, int sub, int kind, float* out, void* stream);
 
+/* Parity-test hook: table = DEVICE uint32 [b200_t1_rng_slots()][12][N] (per slot: 4 raw words, 4 uniforms and 4 normals
+ * as float bits); while set, reset()/step() READ their random draws from it instead of generating them, so kernel,
+ * CPU oracle and the reference (torch.randn_like & co. patched) see identical samples. NULL restores Philox.
+ * Slots: 0-2 reset dof noise, 3-4 reset root, 5 delay, 6-7 command, 8-9 kick, 10-11 push, 12-20 observation noise. */
+int b200_t1_inject_rng(B200T1Handle* h, const uint32_t* table);
+int b200_t1_rng_slots(void);
+
 /* current (rng step, common_step_counter) of the handle; synchronises the stream. Used by parity tests to ask
  * b200_rng_fill() for the samples a given reset()/step() call drew. */
 int b200_t1_counters(B200T1Handle* h, int64_t* rng_step, int64_t* common_step, void* stream);

@@ -1,0 +1,314 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE's own code (read-only /root/reference).
+
+    python tools/make_golden.py            # needs the reference tree; run in the build container
+
+Fixtures (small .npz files, committed; the GPU box has no reference tree):
+  env_step_{plane,trimesh}.npz  reference T1.step() with physics = identity on a seeded synthetic state, RNG injected
+  env_reset_trimesh.npz         reference T1.reset()
+  terrain_lookup.npz            reference Terrain.terrain_heights on a seeded heightfield
+  learner_small.npz             reference ActorCritic + discount_values + surrogate_loss + the loop body of
+                                utils/runner.py:123-180 (two epochs, torch.optim.Adam, clip_grad_norm_)
+  gae_small.npz                 reference discount_values alone
+  t1_actor_known_answer.npz     the shipped TorchScript actor deploy/models/T1.pt: weights + input/output pairs
+The oracle (oracle/*.py, oracle/physics_oracle.c) and the CUDA kernels are both tested against these files.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as H  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_cfg(terrain):
+    cfg = yaml.load(open(os.path.join(ROOT, "envs", "T1.yaml")).read(), Loader=yaml.FullLoader)
+    cfg = copy.deepcopy(cfg)
+    cfg["terrain"]["type"] = terrain
+    cfg["viewer"]["record_video"] = False
+    cfg["basic"]["headless"] = True
+    return cfg
+
+
+def synthetic_state(n, seed, trimesh, ep_case=True):
+    """plausible but adversarial env state: some envs below the termination height, some too fast, some at the episode /
+    command-resample boundaries, joint angles beyond limits, feet near the ground on both sides of the contact band."""
+    g = np.random.default_rng(seed)
+    f = np.float32
+    st = {}
+    rs = np.zeros((n, 13), f)
+    if trimesh:
+        rs[:, 0] = g.uniform(-3.0, 83.0, n)
+        rs[:, 1] = g.uniform(-3.0, 13.0, n)
+        rs[: n // 8, 0] = g.uniform(-4.9, -3.8, n // 8)          # outside the x border: teleport
+        rs[n // 8: n // 4, 1] = g.uniform(13.8, 14.5, n // 8)    # outside the y border
+    else:
+        rs[:, 0:2] = g.uniform(-5, 60, (n, 2))
+    rs[:, 2] = g.uniform(0.40, 0.80, n)
+    ax = g.normal(size=(n, 3)); ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = g.uniform(-0.6, 0.6, n)
+    rs[:, 3:6] = ax * np.sin(ang / 2)[:, None]
+    rs[:, 6] = np.cos(ang / 2)
+    rs[:, 7:13] = g.normal(0, 1.0, (n, 6))
+    rs[::7, 7:10] *= 6.0                                          # terminate_vel
+    st["root_states"] = rs
+    q0 = np.array([-0.2, 0, 0, 0.4, -0.25, 0] * 2, f)
+    st["dof_pos"] = (q0 + g.normal(0, 0.5, (n, 12))).astype(f)
+    st["dof_vel"] = g.normal(0, 3.0, (n, 12)).astype(f)
+    st["actions"] = np.zeros((n, 12), f)                          # overwritten by step()
+    st["last_actions"] = g.uniform(-1, 1, (n, 12)).astype(f)
+    st["last_dof_vel"] = g.normal(0, 3.0, (n, 12)).astype(f)
+    st["last_root_vel"] = g.normal(0, 1.0, (n, 6)).astype(f)
+    st["last_dof_targets"] = (q0 + g.normal(0, 0.3, (n, 12))).astype(f)
+    st["torques"] = np.zeros((n, 12), f)
+    st["commands"] = g.uniform(-1, 1, (n, 3)).astype(f)
+    gf = g.uniform(1, 2, n).astype(f); gf[::5] = 0.0
+    st["gait_frequency"] = gf
+    st["gait_process"] = g.uniform(0, 1, n).astype(f)
+    st["filtered_lin_vel"] = g.normal(0, 0.5, (n, 3)).astype(f)
+    st["filtered_ang_vel"] = g.normal(0, 0.5, (n, 3)).astype(f)
+    st["pushing_forces"] = g.normal(0, 10, (n, 3)).astype(f)
+    st["pushing_torques"] = g.normal(0, 2, (n, 3)).astype(f)
+    fp = np.zeros((n, 2, 3), f)
+    fp[:, :, 0:2] = rs[:, None, 0:2] + g.normal(0, 0.15, (n, 2, 2))
+    fp[:, :, 2] = g.uniform(0.0, 0.12, (n, 2))
+    st["feet_pos"] = fp.reshape(n, 6)
+    fq = g.normal(size=(n, 2, 4)) * np.array([0.1, 0.1, 0.5, 1.0])
+    fq /= np.linalg.norm(fq, axis=2, keepdims=True)
+    st["feet_quat"] = fq.reshape(n, 8).astype(f)
+    st["last_feet_pos"] = (fp + g.normal(0, 0.01, (n, 2, 3))).reshape(n, 6).astype(f)
+    st["dof_stiffness"] = (np.array([200, 200, 200, 200, 50, 50] * 2, f) * g.uniform(0.95, 1.05, (n, 12))).astype(f)
+    st["dof_damping"] = (np.array([5, 5, 5, 5, 1, 1] * 2, f) * g.uniform(0.95, 1.05, (n, 12))).astype(f)
+    st["dof_friction"] = g.uniform(0, 2, (n, 12)).astype(f)
+    st["base_mass_scaled"] = g.uniform(0, 1, (n, 4)).astype(f)
+    eo = np.zeros((n, 3), f)
+    if trimesh:
+        eo[:, 0] = g.uniform(5, 75, n)
+        eo[:, 1] = g.uniform(1.5, 8.5, n)
+    else:
+        eo[:, 0:2] = g.uniform(0, 60, (n, 2))
+    st["env_origins"] = eo
+    ep = g.integers(0, 1400, n)
+    crt = ep + g.integers(1, 500, n)
+    if ep_case:
+        ep[1::9] = 1500                 # -> 1501 after the increment: episode time-out
+        k = np.arange(2, n, 3)
+        crt[k] = ep[k] + 1              # command resample boundary (time_out without reset)
+        ep[3::11] = 0                   # feet_slip mask (episode_length_buf > 1)
+        crt[3::11] = 400
+    st["episode_length_buf"] = ep.astype(np.int64)
+    st["cmd_resample_time"] = crt.astype(np.int64)
+    st["delay_steps"] = g.integers(0, 10, n).astype(np.int64)
+    return st
+
+
+def run_reference_step(mods, cfg, state, hf, common_step_before, actions, table_seed):
+    n = state["root_states"].shape[0]
+    e = H.build_reference_env(mods, cfg, state, hf)
+    e.common_step_counter = common_step_before
+    # which envs will resample a command this step is decided inside step(); the 'still' set must have exactly
+    # int(still_proportion * len) members (randperm semantics) -> pre-compute it with a dry run without randomness use
+    dry = H.build_reference_env(mods, cfg, state, hf)
+    dry.common_step_counter = common_step_before
+    inj0 = H.Injector(H.make_table(n, table_seed), n)
+    H.instrument(dry, inj0, cfg)
+    inj0.randperm = lambda m, **kw: torch.arange(m)
+    with H.patched_rng(inj0):
+        torch.randperm = inj0.randperm
+        dry.step(torch.from_numpy(actions))
+    # envs that resampled = those whose cmd_resample_time changed (or reset to 0 then advanced)
+    resampled = (dry.cmd_resample_time.numpy() != state["cmd_resample_time"]) | \
+                ((dry.episode_length_buf.numpy() == 0) & (dry.cmd_resample_time.numpy() > 0))
+    ids = np.nonzero(resampled)[0]
+    still = np.zeros(n, bool)
+    still[ids[: int(cfg["commands"]["still_proportion"] * len(ids))]] = True
+    table = H.make_table(n, table_seed, still_envs=still, still_proportion=cfg["commands"]["still_proportion"])
+    inj = H.Injector(table, n)
+    cap = H.instrument(e, inj, cfg)
+    with H.patched_rng(inj):
+        e.step(torch.from_numpy(actions))
+    assert np.array_equal((e.cmd_resample_time.numpy() != state["cmd_resample_time"]) |
+                          ((e.episode_length_buf.numpy() == 0) & (e.cmd_resample_time.numpy() > 0)), resampled)
+    out = H.snapshot(e)
+    return table, cap, out, inj.log
+
+
+def gen_env(mods):
+    rngs = {"plane": 11, "trimesh": 12}
+    for terrain in ("plane", "trimesh"):
+        cfg = load_cfg(terrain)
+        hf = None
+        if terrain == "trimesh":
+            np.random.seed(42)
+            t = mods[1].Terrain.__new__(mods[1].Terrain)
+            t.terrain_cfg = cfg["terrain"]
+            t.gym, t.sim, t.device, t.type = H.NullGym({}), None, "cpu", "trimesh"
+            t._create_trimesh()
+            hf = t.height_field_raw.copy()
+        n = 96
+        state = synthetic_state(n, rngs[terrain], terrain == "trimesh")
+        actions = np.random.default_rng(5).uniform(-1.4, 1.4, (n, 12)).astype(np.float32)
+        # common_step_counter becomes 500 inside step(): kick (100 | 500) and push (250 | 500) both fire
+        table, cap, out, log = run_reference_step(mods, cfg, state, hf, 499, actions, 77)
+        save = {"in_" + k: v for k, v in state.items()}
+        save.update({"out_" + k: v for k, v in out.items()})
+        save.update(actions_raw=actions, table=table, common_step=np.int64(500), post_loop_torques=cap["torques"],
+                    post_loop_last_dof_targets=cap["last_dof_targets"], post_loop_actions=cap["actions"])
+        if hf is not None:
+            save["hf"] = hf
+        np.savez_compressed(os.path.join(OUT, f"env_step_{terrain}.npz"), **save)
+        print(terrain, "step: resets", int(out["reset_buf"].sum()), "time_outs", int(out["time_out_buf"].sum()),
+              "contacts", int(out["feet_contact"].sum()), "rng calls", len(log))
+        # a second case: push phase == push_duration (forces zeroed), no kick, nobody resets -> extras["time_outs"] stays stale
+        st2 = synthetic_state(n, rngs[terrain] + 100, terrain == "trimesh", ep_case=False)
+        st2["root_states"][:, 2] = 0.7 + (0.0 if hf is None else 0.2)
+        st2["root_states"][:, 7:13] *= 0.3
+        st2["root_states"][: n // 4, 0] = np.random.default_rng(1).uniform(10, 60, n // 4)
+        st2["root_states"][: n // 4, 1] = np.random.default_rng(2).uniform(2, 8, n // 4)
+        table, cap, out, log = run_reference_step(mods, cfg, st2, hf, 299, actions, 78)
+        assert out["reset_buf"].sum() == 0
+        save = {"in_" + k: v for k, v in st2.items()}
+        save.update({"out_" + k: v for k, v in out.items()})
+        save.update(actions_raw=actions, table=table, common_step=np.int64(300), post_loop_torques=cap["torques"],
+                    post_loop_last_dof_targets=cap["last_dof_targets"], post_loop_actions=cap["actions"])
+        if hf is not None:
+            save["hf"] = hf
+        np.savez_compressed(os.path.join(OUT, f"env_step_{terrain}_noreset.npz"), **save)
+        print(terrain, "no-reset step: time_outs", int(out["time_out_buf"].sum()), "extras", int(out["extras_time_outs"].sum()))
+        if terrain == "trimesh":
+            # reset(): every env resets, commands resampled for all, observations
+            state3 = synthetic_state(n, 33, True)
+            e = H.build_reference_env(mods, cfg, state3, hf)
+            still = np.zeros(n, bool); still[: int(0.1 * n)] = True
+            table = H.make_table(n, 79, still_envs=still)
+            inj = H.Injector(table, n)
+            H.instrument(e, inj, cfg)
+            with H.patched_rng(inj):
+                e.reset()
+            out = H.snapshot(e)
+            save = {"in_" + k: v for k, v in state3.items()}
+            save.update({"out_" + k: v for k, v in out.items()})
+            save.update(table=table, hf=hf)
+            np.savez_compressed(os.path.join(OUT, "env_reset_trimesh.npz"), **save)
+            # terrain lookup alone
+            gg = np.random.default_rng(0)
+            K = 4096
+            xy = np.stack([gg.uniform(-4.9, 84.7, K), gg.uniform(-4.9, 14.7, K), gg.uniform(0, 1, K)], axis=1).astype(np.float32)
+            xy[:256, 0:2] = (np.round(xy[:256, 0:2] * 10) / 10).astype(np.float32)
+            xy[256:320, 0] = gg.uniform(-5.09, -5.0, 64).astype(np.float32)
+            h = e.terrain.terrain_heights(torch.from_numpy(xy)).numpy()
+            np.savez_compressed(os.path.join(OUT, "terrain_lookup.npz"), hf=hf, xy=xy, heights=h)
+
+
+def gen_learner(mods):
+    import torch.nn.functional as F
+
+    _, _, U, M = mods
+    sys.path.insert(0, ROOT)
+    from oracle import learner as L
+
+    torch.manual_seed(123)
+    T, N = 6, 80
+    buf, last_obs, last_priv = L.synthetic_rollout(T, N, seed=9, done_rate=0.05, timeout_rate=0.06)
+    model = M.ActorCritic(12, 47, 14)
+    with torch.no_grad():
+        model.actor[6].weight.mul_(6.0)
+        model.logstd.add_(torch.linspace(-0.3, 0.3, 12).view(1, 12))
+        buf["actions"] = model.act(buf["obses"]).sample()
+    sd0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    lr = 1e-3
+    save = {"T": T, "N": N, "last_obs": last_obs.numpy(), "last_priv": last_priv.numpy()}
+    save.update({"buf_" + k: v.numpy() for k, v in buf.items()})
+    save.update({"sd0_" + k: v for k, v in sd0.items()})
+    # --- the body of utils/runner.py:123-180, driven through the reference's own classes and helpers
+    with torch.no_grad():
+        old_dist = model.act(buf["obses"])
+        old_logp = old_dist.log_prob(buf["actions"]).sum(dim=-1)
+    save["old_logp"] = old_logp.numpy()
+    save["old_mu"] = old_dist.loc.numpy()
+    rewards = buf["rewards"].clone()
+    for ep in range(2):
+        values = model.est_value(buf["obses"], buf["privileged_obses"])
+        last_values = model.est_value(last_obs, last_priv)
+        with torch.no_grad():
+            rewards[buf["time_outs"]] = values[buf["time_outs"]]
+            adv = U.discount_values(rewards, buf["dones"] | buf["time_outs"], values, last_values, 0.995, 0.95)
+            returns = values + adv
+            advn = (adv - adv.mean()) / (adv.std() + 1e-8)
+        value_loss = F.mse_loss(values, returns)
+        dist = model.act(buf["obses"])
+        logp = dist.log_prob(buf["actions"]).sum(dim=-1)
+        actor_loss = U.surrogate_loss(old_logp, logp, advn)
+        bound_loss = torch.clip(dist.loc - 1.0, min=0.0).square().mean() + torch.clip(dist.loc + 1.0, max=0.0).square().mean()
+        entropy = dist.entropy().sum(dim=-1)
+        loss = value_loss + actor_loss + 1.0 * bound_loss + (-0.01) * entropy.mean()
+        opt.zero_grad()
+        loss.backward()
+        grads = {k: p.grad.detach().clone().numpy() for k, p in model.named_parameters()}
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        with torch.no_grad():
+            kl = torch.sum(torch.log(dist.scale / old_dist.scale)
+                           + 0.5 * (torch.square(old_dist.scale) + torch.square(dist.loc - old_dist.loc)) / torch.square(dist.scale) - 0.5, axis=-1)
+            kl_mean = torch.mean(kl)
+            if kl_mean > 0.01 * 2:
+                lr = max(1e-5, lr / 1.5)
+            elif kl_mean < 0.01 / 2:
+                lr = min(1e-2, lr * 1.5)
+            for pg in opt.param_groups:
+                pg["lr"] = lr
+        p = f"ep{ep}_"
+        save.update({p + "values": values.detach().numpy(), p + "last_values": last_values.detach().numpy(), p + "adv": adv.numpy(),
+                     p + "returns": returns.numpy(), p + "advn": advn.numpy(), p + "mu": dist.loc.detach().numpy(),
+                     p + "value_loss": value_loss.item(), p + "actor_loss": actor_loss.item(), p + "bound_loss": bound_loss.item(),
+                     p + "entropy": entropy.mean().item(), p + "kl": kl_mean.item(), p + "lr": lr, p + "rewards": rewards.numpy().copy()})
+        save.update({p + "grad_" + k: v for k, v in grads.items()})
+        save.update({p + "param_" + k: v.detach().clone().numpy() for k, v in model.state_dict().items()})
+    np.savez_compressed(os.path.join(OUT, "learner_small.npz"), **save)
+    print("learner: value_loss", save["ep0_value_loss"], "kl", save["ep1_kl"], "lr", save["ep1_lr"])
+    # GAE alone, with edge cases (all done, none done, T = 1)
+    g = torch.Generator().manual_seed(4)
+    cases = {}
+    for name, (T_, N_, pd) in {"a": (24, 64, 0.1), "b": (1, 5, 0.5), "c": (7, 3, 1.0), "d": (7, 3, 0.0)}.items():
+        r = torch.rand(T_, N_, generator=g); v = torch.randn(T_, N_, generator=g); lv = torch.randn(N_, generator=g)
+        d = torch.rand(T_, N_, generator=g) < pd
+        a = U.discount_values(r, d, v, lv, 0.995, 0.95)
+        cases.update({f"{name}_r": r.numpy(), f"{name}_v": v.numpy(), f"{name}_lv": lv.numpy(), f"{name}_d": d.numpy(), f"{name}_adv": a.numpy()})
+    np.savez_compressed(os.path.join(OUT, "gae_small.npz"), **cases)
+
+
+def gen_actor(ref):
+    path = os.path.join(ref, "deploy", "models", "T1.pt")
+    m = torch.jit.load(path, map_location="cpu")
+    sd = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+    names = sorted(sd.keys())
+    print("T1.pt tensors:", names)
+    g = torch.Generator().manual_seed(0)
+    obs = torch.cat([torch.zeros(1, 47), torch.randn(63, 47, generator=g)])
+    with torch.no_grad():
+        mu = m(obs).numpy()
+    out = {"obs": obs.numpy(), "mu": mu}
+    for k, v in sd.items():  # TorchScript of model.actor: keys "0.weight" ... "6.bias"
+        out["actor." + k] = v
+    np.savez_compressed(os.path.join(OUT, "t1_actor_known_answer.npz"), **out)
+    print("actor(zeros) =", mu[0])
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ref = H.reference_dir()
+    if ref is None:
+        raise SystemExit("reference tree not found")
+    mods = H.import_reference()
+    gen_env(mods)
+    gen_learner(mods)
+    gen_actor(ref)
+    print("fixtures written to", OUT)
