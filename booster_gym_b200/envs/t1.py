@@ -18,8 +18,15 @@ from .base_task import BaseTask
 
 class T1(BaseTask):
 
-    def __init__(self, cfg, env_index_base=0, total_envs=None):
+    def __init__(self, cfg, env_index_base=0, total_envs=None, height_field=None):
         super().__init__(cfg)
+        if height_field is not None:  # a given int16 heightfield instead of the generated one (BASELINE config 3: an input)
+            if self.terrain.type == "plane":
+                raise ValueError("height_field given but terrain.type is 'plane'")
+            hf = np.ascontiguousarray(height_field, dtype=np.int16)
+            if hf.shape != self.terrain.height_field_raw.shape:
+                raise ValueError(f"height_field must have shape {self.terrain.height_field_raw.shape}")
+            self.terrain.height_field_raw = hf
         self._lib = _lib.load()
         self._env_index_base = int(env_index_base)
         self._create_envs(total_envs)
@@ -195,6 +202,11 @@ class T1(BaseTask):
         for i, name in enumerate(self.reward_names):
             out[name] = sums[1 + i] / k
         return out, cnt.value
+
+    def inject_rng(self, table):
+        """parity-test hook: int32/uint32 tensor [slots, 12, N] on the device (or None to restore the Philox draws)"""
+        self._inject = table
+        _lib.check(self._lib.b200_t1_inject_rng(self._h, table.data_ptr() if table is not None else None), "inject_rng")
 
     def rng_samples(self, step, purpose, sub, kind):
         out = torch.empty(4, self.num_envs, dtype=torch.float32, device=self.device)

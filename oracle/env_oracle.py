@@ -134,6 +134,15 @@ class EnvOracle:
         self.s.setdefault("feet_contact", np.zeros((self.n, 2), bool))
         self.extras_time_outs = np.zeros(self.n, bool)
 
+    def init_derived(self):
+        """envs/t1.py:240-244: base-frame vectors from the state the env is constructed with"""
+        s, n = self.s, self.n
+        rs = s["root_states"]
+        g = np.tile(np.array([0.0, 0.0, -1.0], f32), (n, 1))
+        s["base_lin_vel"] = quat_rotate_inverse(rs[:, 3:7], rs[:, 7:10])
+        s["base_ang_vel"] = quat_rotate_inverse(rs[:, 3:7], rs[:, 10:13])
+        s["projected_gravity"] = quat_rotate_inverse(rs[:, 3:7], g)
+
     def h(self, pos):
         return terrain_heights(pos, self.hf if self.trimesh else None, self.bp, self.hs, self.vs)
 

@@ -3,8 +3,7 @@
 // oracle/ without a GPU.  Never loaded by the product package (booster_gym_b200/_lib.py only loads libb200t1.so).
 #include <string.h>
 
-#include "../../booster_gym_b200/csrc/t1_dynamics.cuh"
-#include "../../booster_gym_b200/csrc/terrain.cuh"
+#include "../../booster_gym_b200/csrc/t1_env.cuh"
 
 using namespace b200;
 
@@ -59,5 +58,46 @@ void hc_feet_d(const B200T1ModelD* m, void* env, double* pos, double* quat) {
     double fp[2][3], fq[2][4];
     t1_feet_fk<double>(*m, s, fp, fq);
     memcpy(pos, fp, sizeof fp); memcpy(quat, fq, sizeof fq);
+}
+
+// ---- the env bodies (t1_env.cuh) on host arrays: what k_post + k_finalize_timeouts / k_reset_all do, serially ----------
+static TerrainView make_tv(const B200T1Config* c, const int16_t* hf, int rows, int cols) {
+    TerrainView tv{(c->terrain_type == 0) ? nullptr : hf, rows, cols, c->border_pixels, c->horizontal_scale, c->vertical_scale};
+    return tv;
+}
+int hc_env_post(const B200T1ModelF* m, const B200T1Config* c, const int16_t* hf, int rows, int cols, float* fstate,
+                int32_t* istate, int n, const uint32_t* inject, long long common_step, unsigned long long step, int noise_on,
+                float* obs, float* priv, float* rew, uint8_t* done, uint8_t* time_out_extras, float* rew_terms) {
+    EnvView v{fstate, istate, n, 0, 42ull, inject};
+    const TerrainView tv = make_tv(c, hf, rows, cols);
+    int any = 0;
+    for (int e = 0; e < n; ++e) {
+        const StepOut o = env_post_physics(v, e, *m, *c, tv, common_step, step, noise_on, obs + (size_t)e * B200_NOBS,
+                                           priv + (size_t)e * B200_NPRIV, rew_terms);
+        rew[e] = o.rew;
+        done[e] = (uint8_t)o.done;
+        any |= o.done;
+    }
+    if (any)
+        for (int e = 0; e < n; ++e) time_out_extras[e] = (uint8_t)istate[(size_t)I_time_out_buf * n + e];
+    return any;
+}
+int hc_env_reset_all(const B200T1ModelF* m, const B200T1Config* c, const int16_t* hf, int rows, int cols, float* fstate,
+                     int32_t* istate, int n, const uint32_t* inject, unsigned long long step, float* obs, float* priv) {
+    EnvView v{fstate, istate, n, 0, 42ull, inject};
+    const TerrainView tv = make_tv(c, hf, rows, cols);
+    (void)m;
+    for (int e = 0; e < n; ++e) {
+        env_reset_one(v, e, *c, tv, step);
+        if (istate[(size_t)I_episode_length_buf * n + e] == istate[(size_t)I_cmd_resample_time * n + e]) env_resample_command(v, e, *c, step);
+        env_observations(v, e, *c, tv, step, 1, obs + (size_t)e * B200_NOBS, priv + (size_t)e * B200_NPRIV);
+    }
+    return 0;
+}
+void hc_philox(unsigned long long seed, unsigned int env, unsigned long long step, int purpose, int sub, unsigned int* words,
+               float* uni, float* nrm) {
+    const Philox4 p = rng_words(seed, env, step, purpose, sub);
+    const Rand4 r = rand4(p);
+    for (int i = 0; i < 4; ++i) { words[i] = p.w[i]; uni[i] = r.u[i]; nrm[i] = r.n[i]; }
 }
 }

@@ -1,0 +1,150 @@
+"""The exact `__host__ __device__` bodies the CUDA kernels execute (csrc/t1_env.cuh, t1_dynamics.cuh, terrain.cuh), compiled
+for the HOST by tests/hostcheck (g++, no FMA contraction), against the golden fixtures from the reference and the FP64
+physics oracle.  Runs without a GPU; the same comparisons run on the device in tests/test_gpu_env*.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from golden_util import OUT_EXACT, OUT_FLOAT, STATE_KEYS, close, load, load_cfg, step_inputs
+from hostcheck_util import lib, pack_state, unpack
+
+
+def _cfg_structs(cfg):
+    from booster_gym_b200 import config, robot
+
+    c = config.t1_config(cfg)
+    sp = config.sim_params(cfg)
+    m = robot.model_f(foot_corner=config.feet_edge_pos(cfg), dt=sp["dt"], gravity=sp["gravity"])
+    return m, c
+
+
+def run_host_step(z, terrain):
+    cfg = load_cfg(terrain)
+    m, c = _cfg_structs(cfg)
+    st = step_inputs(z)
+    n = st["root_states"].shape[0]
+    f, i, ff, fi = pack_state(st, n)
+    hf = np.ascontiguousarray(z["hf"]) if "hf" in z.files else None
+    table = np.ascontiguousarray(z["table"])
+    obs = np.zeros((n, 47), np.float32); priv = np.zeros((n, 14), np.float32); rew = np.zeros(n, np.float32)
+    done = np.zeros(n, np.uint8); touts = np.zeros(n, np.uint8); terms = np.zeros((c.n_rew, n), np.float32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None  # noqa: E731
+    lib().hc_env_post(C.byref(m), C.byref(c), P(hf), hf.shape[0] if hf is not None else 0, hf.shape[1] if hf is not None else 0,
+                      P(f), P(i), n, P(table), C.c_longlong(int(z["common_step"])), C.c_ulonglong(1), 1, P(obs), P(priv), P(rew),
+                      P(done), P(touts), P(terms))
+    got = unpack(f, i, ff, fi)
+    got.update(obs=obs, priv=priv, rew=rew, reset_buf=done, extras_time_outs=touts)
+    return cfg, got, terms
+
+
+@pytest.mark.parametrize("name,terrain", [("env_step_plane.npz", "plane"), ("env_step_trimesh.npz", "trimesh"),
+                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_trimesh_noreset.npz", "trimesh")])
+def test_post_physics_body_matches_reference(name, terrain):
+    from booster_gym_b200 import config
+
+    z = load(name)
+    cfg, got, terms = run_host_step(z, terrain)
+    for k in OUT_EXACT:   # masks, counters, indices: bit-exact
+        assert np.array_equal(np.asarray(got[k]).astype(np.int64).reshape(z["out_" + k].shape), z["out_" + k].astype(np.int64)), k
+    for k in OUT_FLOAT:   # fp32: 1e-5 relative (north_star)
+        assert close(np.asarray(got[k]).reshape(z["out_" + k].shape), z["out_" + k]), k
+    names = [nm for nm, _ in config.reward_terms(cfg)]
+    assert len(names) == 23
+    for j, nm in enumerate(names):
+        assert close(terms[j], z["out_term_" + nm]), nm
+
+
+def test_reset_body_matches_reference():
+    z = load("env_reset_trimesh.npz")
+    cfg = load_cfg("trimesh")
+    m, c = _cfg_structs(cfg)
+    st = {k: z["in_" + k].copy() for k in STATE_KEYS}
+    # envs/t1.py:240-242: base-frame vectors exist from construction and are NOT refreshed by reset()
+    from oracle.env_oracle import quat_rotate_inverse
+
+    rs = st["root_states"]
+    n = rs.shape[0]
+    st["base_lin_vel"] = quat_rotate_inverse(rs[:, 3:7], rs[:, 7:10])
+    st["base_ang_vel"] = quat_rotate_inverse(rs[:, 3:7], rs[:, 10:13])
+    st["projected_gravity"] = quat_rotate_inverse(rs[:, 3:7], np.tile(np.array([0, 0, -1], np.float32), (n, 1)))
+    f, i, ff, fi = pack_state(st, n)
+    hf = np.ascontiguousarray(z["hf"]); table = np.ascontiguousarray(z["table"])
+    obs = np.zeros((n, 47), np.float32); priv = np.zeros((n, 14), np.float32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().hc_env_reset_all(C.byref(m), C.byref(c), P(hf), hf.shape[0], hf.shape[1], P(f), P(i), n, P(table), C.c_ulonglong(1), P(obs), P(priv))
+    got = unpack(f, i, ff, fi)
+    assert close(obs, z["out_obs"]) and close(priv, z["out_priv"])
+    for k in ("root_states", "dof_pos", "dof_vel", "commands", "gait_frequency", "last_dof_targets", "last_root_vel"):
+        assert close(got[k].reshape(z["out_" + k].shape), z["out_" + k]), k
+    for k in ("episode_length_buf", "cmd_resample_time", "delay_steps"):
+        assert np.array_equal(got[k].astype(np.int64), z["out_" + k]), k
+
+
+def test_terrain_body_bit_exact():
+    z = load("terrain_lookup.npz")
+    hf = np.ascontiguousarray(z["hf"])
+    L = lib()
+    out = np.array([L.hc_terrain_height(hf.ctypes.data_as(C.c_void_p), hf.shape[0], hf.shape[1], 50, C.c_float(0.1), C.c_double(0.005),
+                                        C.c_float(x), C.c_float(y)) for x, y in z["xy"][:, :2]], dtype=np.float32)
+    assert np.array_equal(out.view(np.uint32), z["heights"].view(np.uint32))
+
+
+def test_dynamics_body_matches_fp64_oracle():
+    """kernel recursion (CRBA + RNE + sparse LTDL, common-reference-point spatial algebra) in double vs the independent
+    dense-Jacobian oracle: agreement to 1e-10 on qacc, with and without foot contact, pushes, randomised inertias"""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    md = robot.model_d()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    n_contact = 0
+    for it in range(60):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        airborne = it % 2 == 0
+        e = op.make_env(md, pos=(rng.normal(), rng.normal(), 2.0 if airborne else 0.64), quat=q if airborne else (0, 0, 0, 1),
+                        vlin=rng.normal(size=3), wb=rng.normal(size=3) * 2, q=rng.uniform(-0.5, 0.5, 12), qd=rng.normal(size=12) * 3)
+        for b in range(13):
+            e.mass[b] *= rng.uniform(0.8, 1.2)
+            for r in range(3):
+                e.com[b][r] += rng.uniform(-0.01, 0.01)
+        tau = rng.normal(size=12) * 10; pf = rng.normal(size=3) * 10; pt = rng.normal(size=3) * 2
+        st, qa_o, fn_o = op.tick(md, op.Env.from_buffer_copy(e), tau, pf, pt, integrate=False)
+        assert st == 0
+        e2 = op.Env.from_buffer_copy(e)
+        qacc = (C.c_double * 18)(); fn = (C.c_double * 2)()
+        lib().hc_tick_d(C.byref(md), C.byref(e2), op._d(tau), op._d(pf), op._d(pt), None, 0, 0, 50, C.c_float(0.1), C.c_double(0.005), qacc, fn, 0)
+        worst = max(worst, np.max(np.abs(qa_o - np.array(qacc))) / max(1.0, np.max(np.abs(qa_o))))
+        n_contact += int(fn_o.sum() > 0)
+        assert not (airborne and fn_o.sum() > 0)
+        assert np.allclose(fn_o, np.array(fn), rtol=1e-9, atol=1e-9)
+    assert worst < 1e-10 and n_contact >= 10
+
+
+def test_physics_oracle_invariants():
+    """free fall, momentum conservation in flight, energy drift bound, symmetric positive-definite M"""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    md = robot.model_d()
+    e = op.make_env(md, pos=(0, 0, 2.0))
+    st, qa, _ = op.tick(md, e, integrate=False)
+    assert np.allclose(qa[:3], [0, 0, -9.81], atol=1e-12) and np.abs(qa[3:]).max() < 1e-9
+    M = op.mass_matrix(md, e)
+    assert np.allclose(M, M.T, atol=1e-12) and np.linalg.eigvalsh(M).min() > 0
+    assert abs(M[0, 0] - 31.6144) < 1e-9 and abs(M[6 + 0, 12 + 0]) < 1e-15  # total mass; the legs do not couple
+    md2 = robot.model_d(enable_contact=False, enable_limits=False, gravity=0.0)
+    rng = np.random.default_rng(1)
+    e = op.make_env(md2, pos=(0, 0, 5.0), vlin=rng.normal(size=3), wb=rng.normal(size=3), q=rng.uniform(-0.2, 0.2, 12) + np.array([-0.2, 0, 0, 0.6, -0.25, 0] * 2),
+                    qd=rng.normal(size=12))
+    E0, P0, L0 = op.energy_momentum(md2, e)
+    for _ in range(200):
+        op.tick(md2, e)
+    E1, P1, L1 = op.energy_momentum(md2, e)
+    # linear momentum (no gravity, no contact): conserved by the continuous dynamics; semi-implicit Euler in generalised
+    # coordinates keeps it to O(dt) (the momentum map A(q) moves within a step) - 0.4 s at dt = 2 ms: < 0.5 %
+    assert np.allclose(P0, P1, rtol=5e-3, atol=5e-2)
+    c0 = L0; c1 = L1
+    assert np.allclose(c0, c1, rtol=5e-3, atol=0.2)             # angular momentum about the origin, same O(dt) argument
+    assert abs(E1 - E0) < 0.05 * abs(E0)                      # semi-implicit Euler energy drift over 0.4 s
