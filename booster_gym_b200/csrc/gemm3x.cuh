@@ -27,6 +27,8 @@ struct GemmArgs {
     int cn_store;       // columns actually stored (<= Cn), e.g. 47 of a 48-wide padded tile
     int r_chunk;        // reduction rows per CTA along blockIdx.z (split-R); 0 = whole R
     int r_valid_b;      // reduction indices >= this read B as 0 (K = 47/61 of a padded X); <=0 = R
+    float* C_hi;        // optional (EPI_BIAS_ELU): tf32 hi / lo halves of the stored value, same layout as C - the operand
+    float* C_lo;        //                          format of the tcgen05 kernels (gemm_tc.cuh)
 };
 
 #ifndef G_ACC_SPLIT
@@ -233,6 +235,11 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm3x(const GemmArgs g) {
                     } else if (EPI == EPI_ELU_GRAD) {
                         if (c < g.cn_store) { const float h = g.aux[(size_t)i * g.ldaux + c]; v0 *= (h > 0.f) ? 1.f : (h + 1.f); }
                         if (c + 1 < g.cn_store) { const float h = g.aux[(size_t)i * g.ldaux + c + 1]; v1 *= (h > 0.f) ? 1.f : (h + 1.f); }
+                    }
+                    if (EPI == EPI_BIAS_ELU && g.C_hi) {
+                        const float h0 = __uint_as_float(f2tf32(v0)), h1 = __uint_as_float(f2tf32(v1));
+                        if (c < g.cn_store) { g.C_hi[(size_t)i * g.ldc + c] = h0; g.C_lo[(size_t)i * g.ldc + c] = __uint_as_float(f2tf32(v0 - h0)); }
+                        if (c + 1 < g.cn_store) { g.C_hi[(size_t)i * g.ldc + c + 1] = h1; g.C_lo[(size_t)i * g.ldc + c + 1] = __uint_as_float(f2tf32(v1 - h1)); }
                     }
                     if (c + 1 < g.cn_store && ((g.ldc & 1) == 0)) {
                         *reinterpret_cast<float2*>(g.C + (size_t)i * g.ldc + c) = make_float2(v0, v1);

@@ -1,0 +1,425 @@
+// gemm_tc.cuh - Blackwell-native fp32-accurate GEMMs for the actor/critic MLP (utils/model.py:9-26): tcgen05.mma
+// (kind::tf32) with TMEM accumulators, TMA-staged operands (cp.async.bulk.tensor, 128-byte swizzle), mbarrier pipelines.
+//
+// Precision: every fp32 operand x is carried as a PRE-SPLIT pair (hi = tf32(x), lo = tf32(x - hi)) produced by the
+// epilogue of the kernel that wrote it, and every product is evaluated as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  - three
+// tcgen05.mma per k-step into the same TMEM accumulator (3xTF32; SASS: UTCHMMA, UTMALDG, LDTM).
+//
+// Two kernels:
+//   k_tc_rowmajor<BN, STAGES, EPI>   C[M, Nout] = epi(A[M, K] * B[Nout, K]^T)     both operands K-major (reduction contiguous)
+//        persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer (single elected thread), 2..5 =
+//        epilogue; TMEM accumulator double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop of
+//        tile i+1.  EPI_FWD: +bias, ELU, split, store hi/lo (+ optional fp32 copy).  EPI_DGRAD: * ELU'(h) with h = hi+lo
+//        of the layer's stored post-activation, split, store hi/lo.  Stores are staged through shared memory so that
+//        every global store instruction writes one full 128-byte row segment.
+//   k_tc_wgrad<BN, STAGES>           dW[Nout, Kin] += dY[m, Nout]^T X[m, Kin] over a chunk of rows m (split-M, atomics)
+//        the reduction index is the ROW index of both operands -> MN-major operands; for 32-bit elements the only legal
+//        MN-major shared-memory layout is SWIZZLE_128B_BASE32B (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <tuple>
+
+namespace b200 {
+namespace tc {
+
+static constexpr int BM = 128;  // rows of the output tile = TMEM lanes = UMMA M
+static constexpr int BK = 32;   // fp32 elements per k-block = one 128-byte swizzle row
+
+enum { EPI_FWD = 0, EPI_DGRAD = 1 };
+
+struct RowArgs {
+    float* out_hi;
+    float* out_lo;
+    float* out_f32;      // nullable
+    const float* bias;   // EPI_FWD
+    const float* aux_hi; // EPI_DGRAD: post-activation of the layer whose input gradient is produced
+    const float* aux_lo;
+    int M, Nout, K;      // rows, output columns (multiple of 32), reduction length (TMA zero-fills beyond the tensor)
+    int ldo;             // leading dimension of out_* and aux_* (floats)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t cnt) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done;
+    const uint32_t a = smem_u32(b);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout; version 1 = Blackwell)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {   // K-major, SWIZZLE_128B: 8-row groups 1024 B apart
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {  // MN-major, SWIZZLE_128B_BASE32B: 32-float chunks 4096 B apart, 4-row k groups 512 B apart
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, dense, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int n, bool mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+static constexpr int EPI_WARPS = 16;                   // 4 per TMEM lane quarter, each takes a quarter of the tile's columns
+static constexpr int ROW_THREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
+template <int BN, int STAGES>
+struct RowSmem {
+    static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+};
+
+// The epilogue is instruction-bound (ELU's expm1f, two tf32 roundings, address math: ~40 instructions per element),
+// so it gets 16 warps; each thread owns one output row (its TMEM lane) and 32 consecutive columns per step, which it
+// reads / writes as eight 16-byte vectors: every 32-byte sector is touched by two back-to-back instructions of the same
+// thread (L1 / L2 merge them), no shared-memory staging is needed.
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(ROW_THREADS, 1)
+k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+              const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const RowArgs g) {
+    using S = RowSmem<BN, STAGES>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;   // [2]
+    uint64_t* tempty = tfull + 2;       // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.Nout + BN - 1) / BN, tiles = m_tiles * n_tiles;
+    const int nk = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+                    mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                    tma_load_2d(&mAh, &full[s], st, kb * BK, m0);
+                    tma_load_2d(&mAl, &full[s], st + S::A_BYTES, kb * BK, m0);
+                    tma_load_2d(&mBh, &full[s], st + 2 * S::A_BYTES, kb * BK, n0);
+                    tma_load_2d(&mBl, &full[s], st + 2 * S::A_BYTES + S::B_BYTES, kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(BN, false);
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+                const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
+                mbar_wait(&tempty[a], aph ^ 1);  // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t tacc = tmem_base + a * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES,
+                                   b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint32_t off = k * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                        umma_tf32(tacc, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                        umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), idesc, 1u);
+                        umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+                }
+                umma_commit(&tfull[a]);      // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter q = warp % 4, column group cg = (warp - 2) / 4 =====
+        const int q = warp & 3, cg = (warp - 2) >> 2;
+        constexpr int CHUNKS = BN / 32, PER = CHUNKS / (EPI_WARPS / 4) > 0 ? CHUNKS / (EPI_WARPS / 4) : 1;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
+            mbar_wait(&tfull[a], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int cc = 0; cc < PER; ++cc) {
+                const int c = cg * PER + cc;
+                if (c >= CHUNKS) break;
+                const int col0 = n0 + c * 32;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + a * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                if (row >= g.M || col0 >= g.Nout) continue;
+                const size_t base = (size_t)row * g.ldo + col0;
+                float v[32];
+                if (EPI == EPI_FWD) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float x = __uint_as_float(r[j + t]) + bb[t];
+                            v[j + t] = (x > 0.0f) ? x : expm1f(x);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 h4 = *reinterpret_cast<const float4*>(g.aux_hi + base + j);
+                        const float4 l4 = *reinterpret_cast<const float4*>(g.aux_lo + base + j);
+                        const float hh[4] = {h4.x + l4.x, h4.y + l4.y, h4.z + l4.z, h4.w + l4.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) v[j + t] = __uint_as_float(r[j + t]) * ((hh[t] > 0.0f) ? 1.0f : (hh[t] + 1.0f));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { hi[t] = tf32_rna(v[j + t]); lo[t] = tf32_rna(v[j + t] - hi[t]); }
+                    *reinterpret_cast<float4*>(g.out_hi + base + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(g.out_lo + base + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + base + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+}
+
+// ---- weight gradient: D[Nout, Kin] += sum over rows m of dY[m, Nout]^T X[m, Kin] ------------------------------------
+struct WgradArgs {
+    float* D;         // [Nout, ldd] fp32, accumulated with atomics (zeroed by the caller)
+    int M, Nout, Kin; // Kin = columns stored (<= padded width covered by the tensor map boxes)
+    int ldd;
+    int chunk;        // rows per CTA along blockIdx.x (multiple of 32)
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUtensorMap mYl, const __grid_constant__ CUtensorMap mXh,
+           const __grid_constant__ CUtensorMap mXl, const WgradArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r_begin = blockIdx.x * g.chunk, r_end = min(g.M, r_begin + g.chunk);
+    const int n0 = blockIdx.y * BM, k0 = blockIdx.z * BN;
+    const int nk = (r_end - r_begin + BK - 1) / BK;
+    constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                const int r = r_begin + kb * BK;
+#pragma unroll
+                for (int c = 0; c < BM / 32; ++c) {
+                    tma_load_2d(&mYh, &full[s], st + c * 4096, n0 + c * 32, r);
+                    tma_load_2d(&mYl, &full[s], st + A_BYTES + c * 4096, n0 + c * 32, r);
+                }
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    tma_load_2d(&mXh, &full[s], st + 2 * A_BYTES + c * 4096, k0 + c * 32, r);
+                    tma_load_2d(&mXl, &full[s], st + 2 * A_BYTES + B_BYTES + c * 4096, k0 + c * 32, r);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(BN, true);
+            for (int kb = 0; kb < nk; ++kb) {
+                const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint32_t off = k * 1024;  // 8 rows (samples) = two 4-row swizzle groups
+                    umma_tf32(tmem_base, desc_mnmajor(a_lo + off), desc_mnmajor(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                    umma_tf32(tmem_base, desc_mnmajor(a_hi + off), desc_mnmajor(b_lo + off), idesc, 1u);
+                    umma_tf32(tmem_base, desc_mnmajor(a_hi + off), desc_mnmajor(b_hi + off), idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int row = n0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            if (row < g.Nout) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = k0 + c * 32 + j;
+                    if (col < g.Kin) atomicAdd(g.D + (size_t)row * g.ldd + col, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+}
+
+// ---- host side: tensor-map cache + launchers -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapCache {
+    EncodeTiledFn enc = nullptr;
+    std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> maps;
+    const char* error = nullptr;
+
+    // fp32 matrix [rows, cols] with leading dimension ld (floats); box = 32 floats x box_rows; kmajor -> SWIZZLE_128B,
+    // otherwise the MN-major (BASE32B) swizzle
+    const CUtensorMap* get(const float* base, int rows, int cols, int ld, int box_rows, bool kmajor) {
+        if (!enc) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+                error = "cuTensorMapEncodeTiled is unavailable";
+                return nullptr;
+            }
+            enc = (EncodeTiledFn)fn;
+        }
+        auto key = std::make_tuple((const void*)base, rows, cols, ld, box_rows, kmajor ? 1 : 0);
+        auto it = maps.find(key);
+        if (it != maps.end()) return &it->second;
+        CUtensorMap m;
+        cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+        cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+        cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            error = "cuTensorMapEncodeTiled failed";
+            return nullptr;
+        }
+        return &(maps[key] = m);
+    }
+};
+
+template <int BN, int STAGES, int EPI>
+inline cudaError_t launch_rowmajor(const CUtensorMap* Ah, const CUtensorMap* Al, const CUtensorMap* Bh, const CUtensorMap* Bl,
+                                   const RowArgs& g, int num_sms, cudaStream_t st) {
+    using S = RowSmem<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(k_tc_rowmajor<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = ((g.M + BM - 1) / BM) * ((g.Nout + BN - 1) / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    k_tc_rowmajor<BN, STAGES, EPI><<<grid, ROW_THREADS, S::TOTAL, st>>>(*Ah, *Al, *Bh, *Bl, g);
+    return cudaPeekAtLastError();
+}
+
+template <int BN, int STAGES>
+inline cudaError_t launch_wgrad(const CUtensorMap* Yh, const CUtensorMap* Yl, const CUtensorMap* Xh, const CUtensorMap* Xl,
+                                const WgradArgs& g, int kin_padded, cudaStream_t st) {
+    constexpr int SMEM = STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((g.M + g.chunk - 1) / g.chunk, (g.Nout + BM - 1) / BM, (kin_padded + BN - 1) / BN);
+    k_tc_wgrad<BN, STAGES><<<grid, 192, SMEM, st>>>(*Yh, *Yl, *Xh, *Xl, g);
+    return cudaPeekAtLastError();
+}
+
+}  // namespace tc
+}  // namespace b200

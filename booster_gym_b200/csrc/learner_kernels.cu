@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "gemm3x.cuh"
+#include "gemm_tc.cuh"
 #include "rng.cuh"
 
 using namespace b200;
@@ -41,21 +42,36 @@ enum { DS_ADV_SUM = B200_DS_ADV_SUM, DS_ADV_SUMSQ = B200_DS_ADV_SUMSQ, DS_ADV_CO
        DS_ACTOR_LOSS = B200_DS_ACTOR_LOSS, DS_BOUND_LOSS = B200_DS_BOUND_LOSS, DS_ENTROPY = B200_DS_ENTROPY, DS_KL = B200_DS_KL,
        DS_SAMPLES = B200_DS_SAMPLES, DS_GRAD_SQ = B200_DS_GRAD_SQ, DS_DLOGSTD = B200_DS_DLOGSTD, DS_COUNT = B200_DS_COUNT };
 
-struct Workspace {  // offsets in floats
-    size_t Xa, Xc, C1, C2, C3, V, A1, A2, A3, MU, ADV, RET, DV, DMU, G1, G2;
-    size_t LXa, LXc, L1, L2, L3, LV, LMU;
+// Workspace (offsets in floats).  "h"/"l" = the tf32 hi / lo halves of a fp32 tensor (gemm_tc.cuh): activations and
+// their gradients live ONLY as pre-split pairs (x == hi + lo to 2^-23), which is what the tcgen05 GEMMs consume.
+struct Workspace {
+    size_t Xah, Xal, Xch, Xcl;                          // packed inputs [M,48], [M,64]
+    size_t C1h, C1l, C2h, C2l, C3h, C3l;                // critic post-ELU activations [M,256],[M,256],[M,128]
+    size_t A1h, A1l, A2h, A2l, A3h, A3l, A1f, A2f, A3f, Xaf;  // actor post-ELU activations [M,256],[M,128],[M,128]: pairs + the fp32 originals
+    size_t V, MU, ADV, RET, DV, DMU;
+    size_t G1h, G1l, G2h, G2l, GF;                      // gradient ping-pong [M,256] pairs; GF = fp32 dA3 from the head's dgrad
+    size_t Wc0h, Wc0l, Wc1h, Wc1l, Wc2h, Wc2l, Wa0h, Wa0l, Wa1h, Wa1l, Wa2h, Wa2l;   // split weights, K padded to 64 for layer 0
+    size_t Wc1Th, Wc1Tl, Wc2Th, Wc2Tl, Wa1Th, Wa1Tl, Wa2Th, Wa2Tl;                  // transposed split weights for dgrad
+    size_t LXa, LXc, L1, L2, L3, LV, LMU;               // rollout-sized (N rows) fp32 buffers of the mma.sync path
     size_t total;
 };
 static Workspace make_workspace(int T, int N) {
     Workspace w;
     const size_t M = (size_t)T * N, n = (size_t)N;
     size_t o = 0;
-    auto take = [&](size_t cnt) { size_t r = o; o += (cnt + 63) & ~(size_t)63; return r; };
-    w.Xa = take(M * 48); w.Xc = take(M * 64);
-    w.C1 = take(M * 256); w.C2 = take(M * 256); w.C3 = take(M * 128); w.V = take(M);
-    w.A1 = take(M * 256); w.A2 = take(M * 128); w.A3 = take(M * 128); w.MU = take(M * 12);
-    w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
-    w.G1 = take(M * 256); w.G2 = take(M * 256);
+    auto take = [&](size_t cnt) { size_t r = o; o += (cnt + 255) & ~(size_t)255; return r; };  // 1 KiB aligned (TMA needs 16 B)
+    w.Xah = take(M * 48); w.Xal = take(M * 48); w.Xch = take(M * 64); w.Xcl = take(M * 64);
+    w.C1h = take(M * 256); w.C1l = take(M * 256); w.C2h = take(M * 256); w.C2l = take(M * 256); w.C3h = take(M * 128); w.C3l = take(M * 128);
+    w.A1h = take(M * 256); w.A1l = take(M * 256); w.A2h = take(M * 128); w.A2l = take(M * 128);
+    w.A3h = take(M * 128); w.A3l = take(M * 128); w.A3f = take(M * 128);
+    w.A1f = take(M * 256); w.A2f = take(M * 128); w.Xaf = take(M * 48);
+    w.V = take(M); w.MU = take(M * 12); w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
+    w.G1h = take(M * 256); w.G1l = take(M * 256); w.G2h = take(M * 256); w.G2l = take(M * 256); w.GF = take(M * 128);
+    w.Wc0h = take(256 * 64); w.Wc0l = take(256 * 64); w.Wc1h = take(256 * 256); w.Wc1l = take(256 * 256);
+    w.Wc2h = take(128 * 256); w.Wc2l = take(128 * 256); w.Wa0h = take(256 * 64); w.Wa0l = take(256 * 64);
+    w.Wa1h = take(128 * 256); w.Wa1l = take(128 * 256); w.Wa2h = take(128 * 128); w.Wa2l = take(128 * 128);
+    w.Wc1Th = take(256 * 256); w.Wc1Tl = take(256 * 256); w.Wc2Th = take(256 * 128); w.Wc2Tl = take(256 * 128);
+    w.Wa1Th = take(256 * 128); w.Wa1Tl = take(256 * 128); w.Wa2Th = take(128 * 128); w.Wa2Tl = take(128 * 128);
     w.LXa = take(n * 48); w.LXc = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
     w.LV = take(n); w.LMU = take(n * 12);
     w.total = o;
@@ -70,6 +86,8 @@ struct B200Ppo {
     float* ws;
     unsigned long long* act_ctr;  // device counter of b200_policy_act calls (RNG step when the caller passes B200_STEP_AUTO)
     Workspace w;
+    tc::MapCache* maps;           // TMA tensor maps of the (fixed) workspace buffers, built lazily on first use
+    int num_sms;
     float* P(int i) const { return params + kParams[i].offset; }
     float* G(int i) const { return grads + kParams[i].offset; }
 };
@@ -93,12 +111,69 @@ __global__ void k_pack_inputs(const float* __restrict__ obs, const float* __rest
     if (Xa && c < 48) Xa[r * 48 + c] = (c < 47) ? v : 0.0f;
 }
 
-// critic head: V[m] = b + sum_k H[m,k] w[k], one warp per row (H rows are 128 floats = one float4 per lane)
-__global__ void k_value_head(const float* __restrict__ H, const float* __restrict__ w, const float* __restrict__ b, int n,
-                             float* __restrict__ V) {
+__device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
+    hi = tc::tf32_rna(x);
+    lo = tc::tf32_rna(x - hi);
+}
+
+// obs [n,47] + priv [n,14] -> pre-split GEMM operands Xa [n,48] (hi, lo) and Xc [n,64] (hi, lo), zero padded
+__global__ void k_pack_inputs_split(const float* __restrict__ obs, const float* __restrict__ priv, int n, float* __restrict__ Xah,
+                                    float* __restrict__ Xal, float* __restrict__ Xch, float* __restrict__ Xcl, float* __restrict__ Xaf) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * 64) return;
+    const size_t r = idx >> 6;
+    const int c = (int)(idx & 63);
+    float v = 0.0f;
+    if (c < 47) v = obs[r * 47 + c];
+    else if (c < 61) v = priv[r * 14 + (c - 47)];
+    float hi, lo;
+    split_tf32f(v, hi, lo);
+    Xch[idx] = hi;
+    Xcl[idx] = lo;
+    if (c < 48) {
+        split_tf32f(c < 47 ? v : 0.0f, hi, lo);
+        Xah[r * 48 + c] = hi;
+        Xal[r * 48 + c] = lo;
+        Xaf[r * 48 + c] = (c < 47) ? v : 0.0f;
+    }
+}
+
+// W [rows, cols] fp32 -> split copies: K-major [rows, cols_pad] (zero padded) and, if WTh != null, transposed [cols, rows]
+__global__ void k_weight_prep(const float* __restrict__ W, int rows, int cols, int cols_pad, float* __restrict__ Wh,
+                              float* __restrict__ Wl, float* __restrict__ WTh, float* __restrict__ WTl) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols_pad) return;
+    const int r = idx / cols_pad, c = idx - r * cols_pad;
+    float hi, lo;
+    split_tf32f(c < cols ? W[(size_t)r * cols + c] : 0.0f, hi, lo);
+    Wh[idx] = hi;
+    Wl[idx] = lo;
+    if (WTh && c < cols) {
+        WTh[(size_t)c * rows + r] = hi;
+        WTl[(size_t)c * rows + r] = lo;
+    }
+}
+
+// fp32 -> (hi, lo)
+__global__ void k_split(const float* __restrict__ x, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float h, l;
+    split_tf32f(x[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+}
+
+// critic head: V[m] = b + sum_k H[m,k] w[k], one warp per row (H rows are 128 floats = one float4 per lane); Hl nullable
+__global__ void k_value_head(const float* __restrict__ H, const float* __restrict__ Hl, const float* __restrict__ w,
+                             const float* __restrict__ b, int n, float* __restrict__ V) {
     const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (warp >= n) return;
-    const float4 h = reinterpret_cast<const float4*>(H + (size_t)warp * 128)[lane];
+    float4 h = reinterpret_cast<const float4*>(H + (size_t)warp * 128)[lane];
+    if (Hl) {
+        const float4 l = reinterpret_cast<const float4*>(Hl + (size_t)warp * 128)[lane];
+        h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
+    }
     const float4 ww = reinterpret_cast<const float4*>(w)[lane];
     float s = h.x * ww.x + h.y * ww.y + h.z * ww.z + h.w * ww.w;
 #pragma unroll
@@ -106,19 +181,23 @@ __global__ void k_value_head(const float* __restrict__ H, const float* __restric
     if (lane == 0) V[warp] = s + b[0];
 }
 
-// backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m]
+// backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]) (written pre-split); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m]
 #define VH_ROWS 128
-__global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict__ H, const float* __restrict__ w,
-                                                        const float* __restrict__ dV, int n, float* __restrict__ dH,
-                                                        float* __restrict__ dw, float* __restrict__ db) {
+__global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict__ Hh, const float* __restrict__ Hl,
+                                                        const float* __restrict__ w, const float* __restrict__ dV, int n,
+                                                        float* __restrict__ dHh, float* __restrict__ dHl, float* __restrict__ dw,
+                                                        float* __restrict__ db) {
     const int k = threadIdx.x;
     const int r0 = blockIdx.x * VH_ROWS, r1 = min(n, r0 + VH_ROWS);
     const float wk = w[k];
     double acc = 0.0, accb = 0.0;  // fp64 partial sums: these are 98k-term reductions judged at 1e-5 relative
     for (int r = r0; r < r1; ++r) {
         const float g = dV[r];
-        const float h = H[(size_t)r * 128 + k];
-        dH[(size_t)r * 128 + k] = g * wk * ((h > 0.0f) ? 1.0f : (h + 1.0f));
+        const float h = Hh[(size_t)r * 128 + k] + Hl[(size_t)r * 128 + k];
+        float hi, lo;
+        split_tf32f(g * wk * ((h > 0.0f) ? 1.0f : (h + 1.0f)), hi, lo);
+        dHh[(size_t)r * 128 + k] = hi;
+        dHl[(size_t)r * 128 + k] = lo;
         acc += (double)g * (double)h;
         accb += (double)g;
     }
@@ -126,9 +205,10 @@ __global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict_
     if (k == 0) atomicAdd(db, (float)accb);
 }
 
-// bias gradient: db[c] += sum over rows of dY[r,c]   (C <= 256; 256 threads, rows split over blockDim/Cp row-lanes)
+// bias gradient: db[c] += sum over rows of (dYh + dYl)[r,c]   (C <= 256; 256 threads, rows split over blockDim/Cp row-lanes)
 #define CS_ROWS 256
-__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, int n, int C, int ld, float* __restrict__ db) {
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, const float* __restrict__ dYl, int n, int C, int ld,
+                                                float* __restrict__ db) {
     __shared__ double red[256];
     int Cp = 1;
     while (Cp < C) Cp <<= 1;           // 16, 128 or 256
@@ -136,8 +216,10 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, in
     const int c = threadIdx.x % Cp, rl = threadIdx.x / Cp;
     const int r0 = blockIdx.x * CS_ROWS, r1 = min(n, r0 + CS_ROWS);
     double acc = 0.0;
-    if (c < C)
-        for (int r = r0 + rl; r < r1; r += lanes) acc += (double)dY[(size_t)r * ld + c];
+    if (c < C) {
+        if (dYl) for (int r = r0 + rl; r < r1; r += lanes) acc += (double)dY[(size_t)r * ld + c] + (double)dYl[(size_t)r * ld + c];
+        else for (int r = r0 + rl; r < r1; r += lanes) acc += (double)dY[(size_t)r * ld + c];
+    }
     red[threadIdx.x] = acc;
     __syncthreads();
     if (rl == 0 && c < C) {
@@ -479,8 +561,9 @@ static void prof_end(cudaStream_t st) {
 
 // Y[n, n_out] = act(X[n, k_pad] W[n_out, k_valid]^T + b)
 static cudaError_t linear_fwd(const float* X, int ldx, int k_pad, const float* W, int k_valid, const float* b, float* Y,
-                              int ldy, int n, int n_out, bool elu, cudaStream_t st) {
+                              int ldy, int n, int n_out, bool elu, cudaStream_t st, float* Yh = nullptr, float* Yl = nullptr) {
     GemmArgs g{};
+    g.C_hi = Yh; g.C_lo = Yl;
     g.A = X; g.B = W; g.C = Y; g.bias = b; g.aux = nullptr;
     g.I = n; g.Cn = n_out; g.R = k_pad;
     g.lda = ldx; g.ldb = k_valid; g.ldc = ldy; g.ldaux = 0;
@@ -520,10 +603,115 @@ static cudaError_t linear_wgrad(const float* dY, int ldy, int n_out, const float
     g_launches += 1;
     return e;
 }
-static cudaError_t bias_grad(const float* dY, int ld, int C, int n, float* db, cudaStream_t st) {
-    k_colsum<<<(n + CS_ROWS - 1) / CS_ROWS, 256, 0, st>>>(dY, n, C, ld, db);
+static cudaError_t bias_grad(const float* dY, const float* dYl, int ld, int C, int n, float* db, cudaStream_t st) {
+    k_colsum<<<(n + CS_ROWS - 1) / CS_ROWS, 256, 0, st>>>(dY, dYl, n, C, ld, db);
     g_launches += 1;
     return cudaPeekAtLastError();
+}
+
+// ---- tcgen05 layers (gemm_tc.cuh) over pre-split operands ----------------------------------------------------------
+#define TC_MAP(var, ptr, rows, cols, ld, box, kmajor)                                                      \
+    const CUtensorMap* var = p->maps->get(ptr, rows, cols, ld, box, kmajor);                               \
+    if (!var) return set_error(B200_ERR_CUDA, p->maps->error ? p->maps->error : "tensor map creation failed")
+
+// Y(h,l[,f]) [n, n_out] = ELU(X(h,l) [n, k] W(h,l) [n_out, k_pad]^T + b)
+static int tc_fwd(const B200Ppo* p, const float* Xh, const float* Xl, int k, int ldx, const float* Wh, const float* Wl, int k_pad,
+                  const float* b, float* Yh, float* Yl, float* Yf, int n, int n_out, cudaStream_t st) {
+    const int bn = (n_out >= 256) ? 256 : 128;
+    TC_MAP(mAh, Xh, n, k, ldx, tc::BM, true);
+    TC_MAP(mAl, Xl, n, k, ldx, tc::BM, true);
+    TC_MAP(mBh, Wh, n_out, k_pad, k_pad, bn, true);
+    TC_MAP(mBl, Wl, n_out, k_pad, k_pad, bn, true);
+    tc::RowArgs g{};
+    g.out_hi = Yh; g.out_lo = Yl; g.out_f32 = Yf; g.bias = b; g.aux_hi = nullptr; g.aux_lo = nullptr;
+    g.M = n; g.Nout = n_out; g.K = k_pad; g.ldo = n_out;
+    prof_begin(st, 2.0 * n * (double)n_out * k);
+    const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
+                                      : tc::launch_rowmajor<128, 3, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st);
+    prof_end(st);
+    g_launches += 1;
+    if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<fwd>");
+    return B200_OK;
+}
+// dX(h,l) [n, k_in] = (dY(h,l) [n, n_out] WT(h,l) [k_in, n_out]^T) * ELU'(H(h,l) [n, k_in])
+static int tc_dgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_out, const float* WTh, const float* WTl, int k_in,
+                    const float* Hh, const float* Hl, float* dXh, float* dXl, int n, cudaStream_t st) {
+    const int bn = (k_in >= 256) ? 256 : 128;
+    TC_MAP(mAh, dYh, n, n_out, n_out, tc::BM, true);
+    TC_MAP(mAl, dYl, n, n_out, n_out, tc::BM, true);
+    TC_MAP(mBh, WTh, k_in, n_out, n_out, bn, true);
+    TC_MAP(mBl, WTl, k_in, n_out, n_out, bn, true);
+    tc::RowArgs g{};
+    g.out_hi = dXh; g.out_lo = dXl; g.out_f32 = nullptr; g.bias = nullptr; g.aux_hi = Hh; g.aux_lo = Hl;
+    g.M = n; g.Nout = k_in; g.K = n_out; g.ldo = k_in;
+    prof_begin(st, 2.0 * n * (double)n_out * k_in);
+    const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_DGRAD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
+                                      : tc::launch_rowmajor<128, 3, tc::EPI_DGRAD>(mAh, mAl, mBh, mBl, g, p->num_sms, st);
+    prof_end(st);
+    g_launches += 1;
+    if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<dgrad>");
+    return B200_OK;
+}
+// dW [n_out, k_valid] += dY(h,l) [n, n_out]^T X(h,l) [n, k_cols]   (k_pad = 64 / 128 / 256 = tile width along k)
+#define TC_WGRAD_CHUNK 512
+static int tc_wgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_out, const float* Xh, const float* Xl, int k_cols,
+                    int k_pad, int k_valid, float* dW, int n, cudaStream_t st) {
+    TC_MAP(mYh, dYh, n, n_out, n_out, 32, false);
+    TC_MAP(mYl, dYl, n, n_out, n_out, 32, false);
+    TC_MAP(mXh, Xh, n, k_cols, k_cols, 32, false);
+    TC_MAP(mXl, Xl, n, k_cols, k_cols, 32, false);
+    tc::WgradArgs g{};
+    g.D = dW; g.M = n; g.Nout = n_out; g.Kin = k_valid; g.ldd = k_valid; g.chunk = TC_WGRAD_CHUNK;
+    prof_begin(st, 2.0 * n * (double)n_out * k_valid);
+    cudaError_t e;
+    if (k_pad == 256) e = tc::launch_wgrad<256, 2>(mYh, mYl, mXh, mXl, g, k_pad, st);
+    else if (k_pad == 128) e = tc::launch_wgrad<128, 3>(mYh, mYl, mXh, mXl, g, k_pad, st);
+    else e = tc::launch_wgrad<64, 3>(mYh, mYl, mXh, mXl, g, k_pad, st);
+    prof_end(st);
+    g_launches += 1;
+    if (e != cudaSuccess) return set_cuda_error(e, "k_tc_wgrad");
+    return B200_OK;
+}
+// split copies of the six hidden-layer weight matrices (they change every epoch)
+static int weight_prep(const B200Ppo* p, cudaStream_t st) {
+    float* ws = p->ws;
+    const Workspace& w = p->w;
+    struct Job { int pi, rows, cols, pad; size_t h, l, th, tl; bool tr; };
+    const Job jobs[6] = {
+        {P_CW0, 256, 61, 64, w.Wc0h, w.Wc0l, 0, 0, false},        {P_CW1, 256, 256, 256, w.Wc1h, w.Wc1l, w.Wc1Th, w.Wc1Tl, true},
+        {P_CW2, 128, 256, 256, w.Wc2h, w.Wc2l, w.Wc2Th, w.Wc2Tl, true}, {P_AW0, 256, 47, 64, w.Wa0h, w.Wa0l, 0, 0, false},
+        {P_AW1, 128, 256, 256, w.Wa1h, w.Wa1l, w.Wa1Th, w.Wa1Tl, true}, {P_AW2, 128, 128, 128, w.Wa2h, w.Wa2l, w.Wa2Th, w.Wa2Tl, true}};
+    for (const Job& j : jobs) {
+        const int total = j.rows * j.pad;
+        k_weight_prep<<<(total + 255) / 256, 256, 0, st>>>(p->P(j.pi), j.rows, j.cols, j.pad, ws + j.h, ws + j.l,
+                                                           j.tr ? ws + j.th : nullptr, j.tr ? ws + j.tl : nullptr);
+    }
+    g_launches += 6;
+    return launch_status("k_weight_prep");
+}
+// full-batch forward passes over the M = T*N stored samples (pre-split operands, activations kept for the backward pass)
+// The ACTOR forward stays on the mma.sync kernel: log-prob sensitivity to mu is 1/sigma ~ 7.4 per unit (sigma = e^-2),
+// so mu wants the per-k-step round-to-nearest accumulation of gemm3x.cuh (measured 2.9e-7 of scale against fp64) rather
+// than the TMEM accumulator's truncating adds (2.3e-6).  Its epilogue also writes the tf32 pairs the tcgen05 backward reads.
+static int actor_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
+    float* ws = p->ws;
+    const Workspace& w = p->w;
+    CU_TRY(linear_fwd(ws + w.Xaf, 48, 48, p->P(P_AW0), 47, p->P(P_AB0), ws + w.A1f, 256, M, 256, true, st, ws + w.A1h, ws + w.A1l));
+    CU_TRY(linear_fwd(ws + w.A1f, 256, 256, p->P(P_AW1), 256, p->P(P_AB1), ws + w.A2f, 128, M, 128, true, st, ws + w.A2h, ws + w.A2l));
+    CU_TRY(linear_fwd(ws + w.A2f, 128, 128, p->P(P_AW2), 128, p->P(P_AB2), ws + w.A3f, 128, M, 128, true, st, ws + w.A3h, ws + w.A3l));
+    CU_TRY(linear_fwd(ws + w.A3f, 128, 128, p->P(P_AW3), 128, p->P(P_AB3), ws + w.MU, 12, M, 12, false, st));
+    return B200_OK;
+}
+static int critic_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
+    float* ws = p->ws;
+    const Workspace& w = p->w;
+    int rc;
+    if ((rc = tc_fwd(p, ws + w.Xch, ws + w.Xcl, 64, 64, ws + w.Wc0h, ws + w.Wc0l, 64, p->P(P_CB0), ws + w.C1h, ws + w.C1l, nullptr, M, 256, st))) return rc;
+    if ((rc = tc_fwd(p, ws + w.C1h, ws + w.C1l, 256, 256, ws + w.Wc1h, ws + w.Wc1l, 256, p->P(P_CB1), ws + w.C2h, ws + w.C2l, nullptr, M, 256, st))) return rc;
+    if ((rc = tc_fwd(p, ws + w.C2h, ws + w.C2l, 256, 256, ws + w.Wc2h, ws + w.Wc2l, 256, p->P(P_CB2), ws + w.C3h, ws + w.C3l, nullptr, M, 128, st))) return rc;
+    k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3h, ws + w.C3l, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
+    g_launches += 1;
+    return launch_status("k_value_head");
 }
 
 // actor 47 -> 256 -> 128 -> 128 -> 12 (utils/model.py:18-26)
@@ -541,7 +729,7 @@ static int critic_forward(const B200Ppo* p, const float* Xc, int n, float* H1, f
     CU_TRY(linear_fwd(Xc, 64, 64, p->P(P_CW0), 61, p->P(P_CB0), H1, 256, n, 256, true, st));
     CU_TRY(linear_fwd(H1, 256, 256, p->P(P_CW1), 256, p->P(P_CB1), H2, 256, n, 256, true, st));
     CU_TRY(linear_fwd(H2, 256, 256, p->P(P_CW2), 256, p->P(P_CB2), H3, 128, n, 128, true, st));
-    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(H3, p->P(P_CW3), p->P(P_CB3), n, V);
+    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(H3, nullptr, p->P(P_CW3), p->P(P_CB3), n, V);
     g_launches += 1;
     return launch_status("k_value_head");
 }
@@ -571,8 +759,8 @@ int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float
         return set_error(B200_ERR_ARG, "b200_ppo_create: null pointer");
     if (cfg->horizon <= 0 || cfg->num_envs <= 0 || cfg->world_size <= 0) return set_error(B200_ERR_ARG, "b200_ppo_create: bad sizes");
     if ((reinterpret_cast<uintptr_t>(params) & 15) || (reinterpret_cast<uintptr_t>(grads) & 15) ||
-        (reinterpret_cast<uintptr_t>(workspace) & 255))
-        return set_error(B200_ERR_ARG, "b200_ppo_create: params/grads must be 16-byte and workspace 256-byte aligned");
+        (reinterpret_cast<uintptr_t>(workspace) & 1023))
+        return set_error(B200_ERR_ARG, "b200_ppo_create: params/grads must be 16-byte and workspace 1024-byte aligned");
     CUDA_TRY(cudaSetDevice(device));
     B200Ppo* p = new (std::nothrow) B200Ppo();
     if (!p) return set_error(B200_ERR_ARG, "out of host memory");
@@ -583,6 +771,10 @@ int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float
     p->ws = (float*)workspace;
     p->w = make_workspace(cfg->horizon, cfg->num_envs);
     p->act_ctr = nullptr;
+    p->maps = new (std::nothrow) tc::MapCache();
+    if (!p->maps) { delete p; return set_error(B200_ERR_ARG, "out of host memory"); }
+    p->num_sms = 148;
+    cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t ce = cudaMalloc(&p->act_ctr, sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(p->act_ctr, 0, sizeof(unsigned long long));
     if (ce != cudaSuccess) { delete p; return set_cuda_error(ce, "b200_ppo_create: counter allocation"); }
@@ -591,6 +783,7 @@ int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float
 }
 int b200_ppo_destroy(B200Ppo* p) {
     if (p && p->act_ctr) cudaFree(p->act_ctr);
+    if (p) delete p->maps;
     delete p;
     return B200_OK;
 }
@@ -630,11 +823,13 @@ int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const 
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     const int M = p->cfg.horizon * p->cfg.num_envs;
-    k_pack_inputs<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(obses, privs, M, ws + p->w.Xa, ws + p->w.Xc);
-    const int rc = actor_forward(p, ws + p->w.Xa, 48, 48, M, ws + p->w.A1, ws + p->w.A2, ws + p->w.A3, ws + p->w.MU, st);
+    k_pack_inputs_split<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(obses, privs, M, ws + p->w.Xah, ws + p->w.Xal,
+                                                                              ws + p->w.Xch, ws + p->w.Xcl, ws + p->w.Xaf);
+    int rc = weight_prep(p, st);
     if (rc != B200_OK) return rc;
+    if ((rc = actor_forward_tc(p, M, st)) != B200_OK) return rc;
     k_old_logp<<<(M + 255) / 256, 256, 0, st>>>(ws + p->w.MU, actions, p->P(P_LOGSTD), M, old_mu, old_logp, p->scalars);
-    g_launches += 2;  // + k_pack_inputs
+    g_launches += 2;  // + k_pack_inputs_split
     return launch_status("k_old_logp");
 }
 
@@ -658,8 +853,9 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     float* ws = p->ws;
     const int T = p->cfg.horizon, N = p->cfg.num_envs, M = T * N;
     CUDA_TRY(cudaMemsetAsync(p->dstats, 0, DS_COUNT * sizeof(double), st));
-    int rc = critic_forward(p, ws + p->w.Xc, M, ws + p->w.C1, ws + p->w.C2, ws + p->w.C3, ws + p->w.V, st);
+    int rc = weight_prep(p, st);  // the parameters changed in the previous epoch's b200_ppo_apply
     if (rc != B200_OK) return rc;
+    if ((rc = critic_forward_tc(p, M, st)) != B200_OK) return rc;
     k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(last_obs, last_priv, N, nullptr, ws + p->w.LXc);
     rc = critic_forward(p, ws + p->w.LXc, N, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, ws + p->w.LV, st);
     if (rc != B200_OK) return rc;
@@ -674,43 +870,46 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     if (!actions || !old_mu || !old_logp) return set_error(B200_ERR_ARG, "b200_ppo_epoch_b: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
+    const Workspace& w = p->w;
     const int M = p->cfg.horizon * p->cfg.num_envs;
-    float *Xa = ws + p->w.Xa, *Xc = ws + p->w.Xc, *C1 = ws + p->w.C1, *C2 = ws + p->w.C2, *C3 = ws + p->w.C3;
-    float *A1 = ws + p->w.A1, *A2 = ws + p->w.A2, *A3 = ws + p->w.A3, *MU = ws + p->w.MU;
-    float *DV = ws + p->w.DV, *DMU = ws + p->w.DMU, *G1 = ws + p->w.G1, *G2 = ws + p->w.G2;
-    int rc = actor_forward(p, Xa, 48, 48, M, A1, A2, A3, MU, st);
+    float *MU = ws + w.MU, *DV = ws + w.DV, *DMU = ws + w.DMU, *GF = ws + w.GF;
+    float *G1h = ws + w.G1h, *G1l = ws + w.G1l, *G2h = ws + w.G2h, *G2l = ws + w.G2l;
+    int rc = actor_forward_tc(p, M, st);
     if (rc != B200_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(p->grads, 0, NPARAMS_PADDED * sizeof(float), st));
-    k_loss<<<(M + LOSS_BLOCK - 1) / LOSS_BLOCK, LOSS_BLOCK, 0, st>>>(ws + p->w.V, ws + p->w.RET, ws + p->w.ADV, MU, actions,
-                                                                    old_mu, old_logp, p->P(P_LOGSTD), p->scalars, p->dstats,
-                                                                    M, p->cfg.e_clip, p->cfg.bound_coef, DV, DMU);
+    k_loss<<<(M + LOSS_BLOCK - 1) / LOSS_BLOCK, LOSS_BLOCK, 0, st>>>(ws + w.V, ws + w.RET, ws + w.ADV, MU, actions, old_mu, old_logp,
+                                                                    p->P(P_LOGSTD), p->scalars, p->dstats, M, p->cfg.e_clip,
+                                                                    p->cfg.bound_coef, DV, DMU);
     k_finalize_logstd<<<1, 32, 0, st>>>(p->dstats, p->cfg.entropy_coef, p->G(P_LOGSTD));
     g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
-    // ---- actor backward
-    CU_TRY(linear_wgrad(DMU, 12, 12, A3, 128, 128, 128, p->G(P_AW3), M, st));
-    CU_TRY(bias_grad(DMU, 12, 12, M, p->G(P_AB3), st));
-    CU_TRY(linear_dgrad(DMU, 12, 12, p->P(P_AW3), 128, A3, 128, G1, 128, M, st));
-    CU_TRY(linear_wgrad(G1, 128, 128, A2, 128, 128, 128, p->G(P_AW2), M, st));
-    CU_TRY(bias_grad(G1, 128, 128, M, p->G(P_AB2), st));
-    CU_TRY(linear_dgrad(G1, 128, 128, p->P(P_AW2), 128, A2, 128, G2, 128, M, st));
-    CU_TRY(linear_wgrad(G2, 128, 128, A1, 256, 256, 256, p->G(P_AW1), M, st));
-    CU_TRY(bias_grad(G2, 128, 128, M, p->G(P_AB1), st));
-    CU_TRY(linear_dgrad(G2, 128, 128, p->P(P_AW1), 256, A1, 256, G1, 256, M, st));
-    CU_TRY(linear_wgrad(G1, 256, 256, Xa, 48, 48, 47, p->G(P_AW0), M, st));
-    CU_TRY(bias_grad(G1, 256, 256, M, p->G(P_AB0), st));
+    // ---- actor backward: the 12-wide head on the mma.sync path (fp32 operands), the hidden layers on tcgen05
+    CU_TRY(linear_wgrad(DMU, 12, 12, ws + w.A3f, 128, 128, 128, p->G(P_AW3), M, st));
+    CU_TRY(bias_grad(DMU, nullptr, 12, 12, M, p->G(P_AB3), st));
+    CU_TRY(linear_dgrad(DMU, 12, 12, p->P(P_AW3), 128, ws + w.A3f, 128, GF, 128, M, st));
+    k_split<<<(int)(((size_t)M * 128 + 255) / 256), 256, 0, st>>>(GF, (size_t)M * 128, G1h, G1l);
+    g_launches += 1;
+    if ((rc = tc_wgrad(p, G1h, G1l, 128, ws + w.A2h, ws + w.A2l, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
+    CU_TRY(bias_grad(G1h, G1l, 128, 128, M, p->G(P_AB2), st));
+    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wa2Th, ws + w.Wa2Tl, 128, ws + w.A2h, ws + w.A2l, G2h, G2l, M, st))) return rc;
+    if ((rc = tc_wgrad(p, G2h, G2l, 128, ws + w.A1h, ws + w.A1l, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
+    CU_TRY(bias_grad(G2h, G2l, 128, 128, M, p->G(P_AB1), st));
+    if ((rc = tc_dgrad(p, G2h, G2l, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1h, ws + w.A1l, G1h, G1l, M, st))) return rc;
+    if ((rc = tc_wgrad(p, G1h, G1l, 256, ws + w.Xah, ws + w.Xal, 48, 64, 47, p->G(P_AW0), M, st))) return rc;
+    CU_TRY(bias_grad(G1h, G1l, 256, 256, M, p->G(P_AB0), st));
     // ---- critic backward
-    k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3));
+    k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(ws + w.C3h, ws + w.C3l, p->P(P_CW3), DV, M, G1h, G1l, p->G(P_CW3),
+                                                                  p->G(P_CB3));
     g_launches += 1;
     if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
-    CU_TRY(linear_wgrad(G1, 128, 128, C2, 256, 256, 256, p->G(P_CW2), M, st));
-    CU_TRY(bias_grad(G1, 128, 128, M, p->G(P_CB2), st));
-    CU_TRY(linear_dgrad(G1, 128, 128, p->P(P_CW2), 256, C2, 256, G2, 256, M, st));
-    CU_TRY(linear_wgrad(G2, 256, 256, C1, 256, 256, 256, p->G(P_CW1), M, st));
-    CU_TRY(bias_grad(G2, 256, 256, M, p->G(P_CB1), st));
-    CU_TRY(linear_dgrad(G2, 256, 256, p->P(P_CW1), 256, C1, 256, G1, 256, M, st));
-    CU_TRY(linear_wgrad(G1, 256, 256, Xc, 64, 64, 61, p->G(P_CW0), M, st));
-    CU_TRY(bias_grad(G1, 256, 256, M, p->G(P_CB0), st));
+    if ((rc = tc_wgrad(p, G1h, G1l, 128, ws + w.C2h, ws + w.C2l, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
+    CU_TRY(bias_grad(G1h, G1l, 128, 128, M, p->G(P_CB2), st));
+    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wc2Th, ws + w.Wc2Tl, 256, ws + w.C2h, ws + w.C2l, G2h, G2l, M, st))) return rc;
+    if ((rc = tc_wgrad(p, G2h, G2l, 256, ws + w.C1h, ws + w.C1l, 256, 256, 256, p->G(P_CW1), M, st))) return rc;
+    CU_TRY(bias_grad(G2h, G2l, 256, 256, M, p->G(P_CB1), st));
+    if ((rc = tc_dgrad(p, G2h, G2l, 256, ws + w.Wc1Th, ws + w.Wc1Tl, 256, ws + w.C1h, ws + w.C1l, G1h, G1l, M, st))) return rc;
+    if ((rc = tc_wgrad(p, G1h, G1l, 256, ws + w.Xch, ws + w.Xcl, 64, 64, 61, p->G(P_CW0), M, st))) return rc;
+    CU_TRY(bias_grad(G1h, G1l, 256, 256, M, p->G(P_CB0), st));
     return B200_OK;
 }
 
