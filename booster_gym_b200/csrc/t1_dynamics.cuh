@@ -143,7 +143,432 @@ B200_HD void si_from_body(const T R[3][3], const T* x /*body origin rel. ref*/, 
     o.I[5] = iscale * Iyz - mass * c[1] * c[2];
 }
 
-// ---- per-environment data ---------------------------------------------------------------------------------------
+// ---- leg-parallel formulation ------------------------------------------------------------------------------------
+// The two legs never couple except through the 6 base DoFs (M[left, right] = 0, also through foot contact), so one
+// physics tick splits into
+//   phase 1 (per leg, independent): kinematics / inertias / bias wrenches / foot contact of the leg, its rows of the
+//            mass matrix, its share of the base block and base right-hand side, L^T D L elimination of its 6 DoFs
+//            (leaf to root) and the matching part of the forward substitution;
+//   exchange: the two legs' partial base blocks (21 values) and base right-hand sides (6 values) are ADDED;
+//   phase 2: factor / solve the 6x6 base system (done redundantly by both), back-substitute the leg, integrate.
+// On the device the two phases of an environment run on a PAIR of adjacent lanes and the exchange is 27
+// __shfl_xor_sync(.., 1); on the host (tests, CPU port) t1_tick() runs the two legs one after the other - same code,
+// and a + b is commutative, so both produce bit-identical results for a given scalar type.
+template <typename T> struct LegState {   // what one lane integrates: the base (redundantly) and its own leg
+    T pos[3], quat[4], vlin[3], wb[3];
+    T q[6], qd[6];
+};
+template <typename T> struct LegParams {  // domain-randomised per env (envs/t1.py:139-167): trunk + the 6 bodies of this leg
+    T mass0, com0[3];
+    T mass[6], com[6][3];
+    T mu, kscale, cscale;
+};
+template <typename T> struct LegWork {
+    T Mbb[21];     // base-base block, lower-tri, order v(3), w_body(3): partial after phase 1, total after the exchange
+    T rb[6];       // base right-hand side: partial / total
+    T Mlb[6][6];   // leg row k x base column j  (L factors after phase 1)
+    T Mll[21];     // leg-leg lower-tri (D on the diagonal, L below, after phase 1)
+    T xl[6];       // leg right-hand side after the leg's part of the forward substitution
+    T foot_fn;     // explicit normal-force estimate of this foot [N]
+    T foot_pos[3]; // foot link origin, world
+    T Rf[3][3];    // foot rotation
+};
+B200_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+template <typename T, typename Model, typename Terr>
+B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>& s, int side, const T* tau /*6*/, const T* push_f,
+                           const T* push_t, const Terr& terr, LegWork<T>& W) {
+    const T dt = m.dt;
+    {
+        const T n = b_sqrt(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
+        const T inv = T(1) / n;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s.quat[i] *= inv;
+    }
+    T R0[3][3];
+    quat_to_mat(s.quat, R0);
+    const T zero3[3] = {0, 0, 0};
+    const bool own_trunk = (side == 0);  // the trunk's own inertia / bias wrench / push is counted once, by the left leg
+
+    // --- trunk -------------------------------------------------------------------------------------------------
+    SpInertia<T> Ic0;
+    si_from_body(R0, zero3, par.com0, m.inertia[0], par.mass0, par.mass0 / m.mass[0], Ic0);
+    T w0[3], v0[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        w0[r] = R0[r][0] * s.wb[0] + R0[r][1] * s.wb[1] + R0[r][2] * s.wb[2];
+        v0[r] = s.vlin[r];
+    }
+    T al0[3] = {0, 0, 0}, av0[3];
+    cross3(v0, w0, av0);  // spatial acceleration of the base with qacc = 0: [0 ; v x w] (+ gravity as fictitious acceleration)
+    av0[2] += m.gravity;
+    T f0n[3] = {0, 0, 0}, f0f[3] = {0, 0, 0};  // this lane's share of the bias wrench on the trunk about the reference point
+    if (own_trunk) {
+        T n1[3], f1[3], n2[3], f2[3], t1[3], t2[3];
+        si_mul(Ic0, al0, av0, n1, f1);
+        si_mul(Ic0, w0, v0, n2, f2);
+        cross3(w0, n2, t1);
+        cross3(v0, f2, t2);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) f0n[r] = n1[r] + t1[r] + t2[r];
+        cross3(w0, f2, t1);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) f0f[r] = f1[r] + t1[r];
+        // push on the trunk (local frame, at the CoM; envs/t1.py:522-527): subtract from the bias wrench
+        T Tl[3];
+        cross3(par.com0, push_f, Tl);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Tl[r] += push_t[r];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            f0f[r] -= R0[r][0] * push_f[0] + R0[r][1] * push_f[1] + R0[r][2] * push_f[2];
+            f0n[r] -= R0[r][0] * Tl[0] + R0[r][1] * Tl[1] + R0[r][2] * Tl[2];
+        }
+    } else {
+        Ic0.m = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Ic0.h[r] = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Ic0.I[r] = 0;
+    }
+
+    // --- leg: forward pass (kinematics, inertias, bias wrenches) ------------------------------------------------------
+    T ax[6][3], xj[6][3];  // world joint axis, joint anchor relative to the reference point (trunk origin)
+    SpInertia<T> Ic[6];
+    T fn[6][3], ff[6][3];  // bias wrench per body (angular, linear)
+    T R[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r][c] = R0[r][c];
+    T xp[3] = {0, 0, 0};
+    T wp[3] = {w0[0], w0[1], w0[2]}, vp[3] = {v0[0], v0[1], v0[2]};
+    T alp[3] = {al0[0], al0[1], al0[2]}, avp[3] = {av0[0], av0[1], av0[2]};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int b = 1 + 6 * side + k;
+        const int axis = (k == 0 || k == 3 || k == 4) ? 1 : (k == 2 ? 2 : 0);  // y x z y y x (t1_model.json "axis")
+        const T* off = m.body_pos[b];
+        T x[3], a[3], sl[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            x[r] = xp[r] + R[r][0] * off[0] + R[r][1] * off[1] + R[r][2] * off[2];
+            a[r] = R[r][axis];
+        }
+        rotate_about_axis(R, axis, s.q[k]);
+        cross3(x, a, sl);  // linear part of the motion axis about the reference point
+        const T qd = s.qd[k];
+        T t1[3], t2[3], t3[3];
+        cross3(wp, a, t1);
+        cross3(wp, sl, t2);
+        cross3(vp, a, t3);
+        T al[3], av[3], w[3], v[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            al[r] = alp[r] + qd * t1[r];
+            av[r] = avp[r] + qd * (t2[r] + t3[r]);
+            w[r] = wp[r] + qd * a[r];
+            v[r] = vp[r] + qd * sl[r];
+        }
+        si_from_body(R, x, par.com[k], m.inertia[b], par.mass[k], par.mass[k] / m.mass[b], Ic[k]);
+        T n1[3], f1[3], n2[3], f2[3];
+        si_mul(Ic[k], al, av, n1, f1);
+        si_mul(Ic[k], w, v, n2, f2);
+        cross3(w, n2, t1);
+        cross3(v, f2, t2);
+        cross3(w, f2, t3);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            fn[k][r] = n1[r] + t1[r] + t2[r];
+            ff[k][r] = f1[r] + t3[r];
+            ax[k][r] = a[r];
+            xj[k][r] = x[r];
+            xp[r] = x[r]; wp[r] = w[r]; vp[r] = v[r]; alp[r] = al[r]; avp[r] = av[r];
+        }
+    }
+    // --- foot contact: 4 sole corners against the heightfield --------------------------------------------------------
+    T Kc[21];  // implicit contact matrix of this foot (6x6 symmetric, lower-tri, order [ang; lin]), already * dt
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Kc[i] = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        W.foot_pos[r] = s.pos[r] + xp[r];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) W.Rf[r][c] = R[r][c];
+    }
+    bool foot_active = false;
+    W.foot_fn = 0;
+    if (m.enable_contact) {
+        T Wn[3] = {0, 0, 0}, Wf[3] = {0, 0, 0};
+        const T kn = m.contact_k * par.kscale, cn = m.contact_c * par.cscale;
+        const T dn = cn + dt * kn;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const T* rc = m.foot_corner[c];
+            T p[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) p[r] = xp[r] + R[r][0] * rc[0] + R[r][1] * rc[1] + R[r][2] * rc[2];
+            const T ground = (T)terr((float)(s.pos[0] + p[0]), (float)(s.pos[1] + p[1]));
+            const T depth = ground - (s.pos[2] + p[2]);
+            if (depth > 0) {
+                T wxp[3];
+                cross3(wp, p, wxp);
+                const T vc[3] = {vp[0] + wxp[0], vp[1] + wxp[1], vp[2] + wxp[2]};
+                const T fn0 = kn * depth - cn * vc[2];
+                if (fn0 > 0) {
+                    foot_active = true;
+                    W.foot_fn += fn0;
+                    const T vt = b_sqrt(vc[0] * vc[0] + vc[1] * vc[1]);
+                    const T dtan = par.mu * fn0 / b_max(vt, m.stiction_vel);
+                    const T Fe[3] = {-dtan * vc[0], -dtan * vc[1], kn * depth - dn * vc[2]};
+                    T pxF[3];
+                    cross3(p, Fe, pxF);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) { Wn[r] += pxF[r]; Wf[r] += Fe[r]; }
+                    // K += dt * sum_d D_d r_d^T r_d with rows r_x = [0, pz, -py | 1 0 0], r_y = [-pz, 0, px | 0 1 0],
+                    // r_z = [py, -px, 0 | 0 0 1]   (point velocity = v + w x p)
+                    const T Dx = dt * dtan, Dy = dt * dtan, Dz = dt * dn;
+                    Kc[0] += Dy * p[2] * p[2] + Dz * p[1] * p[1];   // (0,0)
+                    Kc[1] += -Dz * p[0] * p[1];                     // (1,0)
+                    Kc[2] += Dx * p[2] * p[2] + Dz * p[0] * p[0];   // (1,1)
+                    Kc[3] += -Dy * p[0] * p[2];                     // (2,0)
+                    Kc[4] += -Dx * p[1] * p[2];                     // (2,1)
+                    Kc[5] += Dx * p[1] * p[1] + Dy * p[0] * p[0];   // (2,2)
+                    Kc[7] += Dx * p[2];                             // (3,1)
+                    Kc[8] += -Dx * p[1];                            // (3,2)
+                    Kc[9] += Dx;                                    // (3,3)
+                    Kc[10] += -Dy * p[2];                           // (4,0)
+                    Kc[12] += Dy * p[0];                            // (4,2)
+                    Kc[14] += Dy;                                   // (4,4)
+                    Kc[15] += Dz * p[1];                            // (5,0)
+                    Kc[16] += -Dz * p[0];                           // (5,1)
+                    Kc[20] += Dz;                                   // (5,5)
+                }
+            }
+        }
+        if (foot_active) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { fn[5][r] -= Wn[r]; ff[5][r] -= Wf[r]; }
+        }
+    }
+
+    // --- backward pass: composite inertias, accumulated wrenches, leg right-hand side ------------------------------
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+        T sl[3];
+        cross3(xj[k], ax[k], sl);
+        W.xl[k] = tau[k] - (dot3(ax[k], fn[k]) + dot3(sl, ff[k]));
+        if (k > 0) {
+            si_add(Ic[k - 1], Ic[k]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { fn[k - 1][r] += fn[k][r]; ff[k - 1][r] += ff[k][r]; }
+        } else {
+            si_add(Ic0, Ic[0]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { f0n[r] += fn[0][r]; f0f[r] += ff[0][r]; }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        W.rb[r] = -f0f[r];
+        W.rb[3 + r] = -(R0[0][r] * f0n[0] + R0[1][r] * f0n[1] + R0[2][r] * f0n[2]);
+    }
+
+    // --- mass matrix (CRBA) + implicit contact term ------------------------------------------------------------
+    {
+        // base block share: S_lin,k = [0; e_k], S_ang,k = [R0[:,k]; 0] through (trunk share +) this leg's composite inertia (+ K)
+        T Fn[6][3], Ff[6][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            T e[3] = {0, 0, 0};
+            e[k] = 1;
+            si_mul(Ic0, zero3, e, Fn[k], Ff[k]);
+            const T a[3] = {R0[0][k], R0[1][k], R0[2][k]};
+            si_mul(Ic0, a, zero3, Fn[3 + k], Ff[3 + k]);
+            if (foot_active) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int ci = 3 + k;
+                    Fn[k][r] += Kc[tri(ci, r)];
+                    const int lo = (r < k) ? r : k, hi = (r < k) ? k : r;
+                    Ff[k][r] += Kc[tri(3 + hi, 3 + lo)];
+                    T accn = 0, accf = 0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int l2 = (r < c) ? r : c, h2 = (r < c) ? c : r;
+                        accn += Kc[tri(h2, l2)] * a[c];
+                        accf += Kc[tri(3 + r, c)] * a[c];
+                    }
+                    Fn[3 + k][r] += accn;
+                    Ff[3 + k][r] += accf;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                if (j < 3) W.Mbb[tri(i, j)] = Ff[i][j];
+                else W.Mbb[tri(i, j)] = R0[0][j - 3] * Fn[i][0] + R0[1][j - 3] * Fn[i][1] + R0[2][j - 3] * Fn[i][2];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        T sl[3], Fn[3], Ff[3];
+        cross3(xj[k], ax[k], sl);
+        si_mul(Ic[k], ax[k], sl, Fn, Ff);
+        if (foot_active) {
+            const T S6[6] = {ax[k][0], ax[k][1], ax[k][2], sl[0], sl[1], sl[2]};
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                T acc = 0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const int lo = (r < c) ? r : c, hi = (r < c) ? c : r;
+                    acc += Kc[tri(hi, lo)] * S6[c];
+                }
+                if (r < 3) Fn[r] += acc; else Ff[r - 3] += acc;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            W.Mlb[k][j] = Ff[j];
+            W.Mlb[k][3 + j] = R0[0][j] * Fn[0] + R0[1][j] * Fn[1] + R0[2][j] * Fn[2];
+        }
+#pragma unroll
+        for (int j = 0; j <= k; ++j) {
+            T slj[3];
+            cross3(xj[j], ax[j], slj);
+            W.Mll[tri(k, j)] = dot3(ax[j], Fn) + dot3(slj, Ff);
+        }
+    }
+    // --- joint limits: spring explicit + linearly-implicit damper on the diagonal -------------------------------------
+    if (m.enable_limits) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int j = 6 * side + k;
+            const T q = s.q[k], qd = s.qd[k];
+            T viol = 0;
+            if (q < m.jnt_lower[j]) viol = m.jnt_lower[j] - q;
+            else if (q > m.jnt_upper[j]) viol = m.jnt_upper[j] - q;
+            if (viol != 0) {
+                const T ke = m.limit_k * m.dof_inertia[j], ce = m.limit_c * m.dof_inertia[j];
+                const T de = ce + dt * ke;
+                W.xl[k] += ke * viol - de * qd;
+                W.Mll[tri(k, k)] += dt * de;
+            }
+        }
+    }
+    // --- L^T D L elimination of the leg DoFs, leaf to root (MuJoCo mj_factorM order: no fill-in) ------------------------
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+        const T inv = T(1) / W.Mll[tri(k, k)];
+        // rows i = leg DoFs below k
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+            const T l = W.Mll[tri(k, i)] * inv;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) W.Mlb[i][j] -= l * W.Mlb[k][j];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) W.Mll[tri(i, j)] -= l * W.Mll[tri(k, j)];
+        }
+        // rows i = base DoFs
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const T l = W.Mlb[k][i] * inv;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) W.Mbb[tri(i, j)] -= l * W.Mlb[k][j];
+        }
+#pragma unroll
+        for (int i = 0; i < k; ++i) W.Mll[tri(k, i)] *= inv;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) W.Mlb[k][j] *= inv;
+    }
+    // forward substitution, leg part: x_j -= L_ij x_i for i = leg DoFs (descending)
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) W.xl[j] -= W.Mll[tri(i, j)] * W.xl[i];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) W.rb[j] -= W.Mlb[i][j] * W.xl[i];
+    }
+}
+
+// phase 2: W.Mbb / W.rb now hold the SUM over both legs.  Produces qacc (base 6 + this leg 6) and integrates.
+template <typename T, typename Model>
+B200_HD void t1_leg_phase2(const Model& m, LegState<T>& s, LegWork<T>& W, T* qacc_base, T* qacc_leg, bool integrate) {
+    const T dt = m.dt;
+    T* B = W.Mbb;
+    T* x = W.rb;
+    // factor the 6x6 base block
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+        const T inv = T(1) / B[tri(k, k)];
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+            const T l = B[tri(k, i)] * inv;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) B[tri(i, j)] -= l * B[tri(k, j)];
+        }
+#pragma unroll
+        for (int i = 0; i < k; ++i) B[tri(k, i)] *= inv;
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) x[j] -= B[tri(i, j)] * x[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] /= B[tri(i, i)];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) x[i] -= B[tri(i, j)] * x[j];
+    // leg: scale by D, then x_i -= sum_j L_ij x_j over base and lower leg DoFs
+#pragma unroll
+    for (int i = 0; i < 6; ++i) W.xl[i] /= W.Mll[tri(i, i)];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) W.xl[i] -= W.Mlb[i][j] * x[j];
+#pragma unroll
+        for (int j = 0; j < i; ++j) W.xl[i] -= W.Mll[tri(i, j)] * W.xl[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { qacc_base[i] = x[i]; qacc_leg[i] = W.xl[i]; }
+    if (!integrate) return;
+    // semi-implicit Euler (MuJoCo mj_Euler): velocities first, positions with the NEW velocities
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        s.vlin[r] += dt * x[r];
+        s.wb[r] += dt * x[3 + r];
+        s.pos[r] += dt * s.vlin[r];
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        s.qd[j] += dt * W.xl[j];
+        s.q[j] += dt * s.qd[j];
+    }
+    {
+        // quat <- quat (x) exp(dt * wb / 2)   (body-frame angular velocity: right multiplication)
+        const T wn = b_sqrt(s.wb[0] * s.wb[0] + s.wb[1] * s.wb[1] + s.wb[2] * s.wb[2]);
+        T sh, ch, k;
+        b_sincos(T(0.5) * dt * wn, sh, ch);
+        k = (wn > T(1e-9)) ? sh / wn : T(0.5) * dt;
+        const T dx = k * s.wb[0], dy = k * s.wb[1], dz = k * s.wb[2], dw = ch;
+        const T qx = s.quat[0], qy = s.quat[1], qz = s.quat[2], qw = s.quat[3];
+        T nq[4];
+        nq[0] = qw * dx + qx * dw + qy * dz - qz * dy;
+        nq[1] = qw * dy - qx * dz + qy * dw + qz * dx;
+        nq[2] = qw * dz + qx * dy - qy * dx + qz * dw;
+        nq[3] = qw * dw - qx * dx - qy * dy - qz * dz;
+        const T inv = T(1) / b_sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s.quat[i] = nq[i] * inv;
+    }
+}
+
+// ---- whole-robot wrapper (host tests, CPU port): both legs one after the other ----------------------------------------
 template <typename T> struct DynState {
     T pos[3];   // trunk origin, world
     T quat[4];  // xyzw
@@ -162,404 +587,74 @@ template <typename T> struct DynAux {  // by-products of the last tick
     T qacc[B200_NV];
     T foot_fn[2];  // explicit normal-force estimate per foot [N]
 };
-
-// mass matrix storage: plain lower-triangular array (host / local memory variant)
-template <typename T> struct MLocal {
-    T a[B200_NV * (B200_NV + 1) / 2];
-    B200_HD T& operator()(int i, int j) { return a[i * (i + 1) / 2 + j]; }
+template <typename T> struct MLocal {  // kept for source compatibility of callers; the leg-parallel tick needs no external storage
+    T unused;
 };
 
-B200_HD constexpr bool dof_coupled(int i, int j) {
-    // base 0..5, left leg 6..11, right leg 12..17: the two legs never couple (also not through foot contact)
-    return !((i >= 6 && i < 12 && j >= 12) || (j >= 6 && j < 12 && i >= 12));
+template <typename T> B200_HD void leg_split(const DynState<T>& s, const DynParams<T>& par, int side, LegState<T>& ls, LegParams<T>& lp) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { ls.pos[r] = s.pos[r]; ls.vlin[r] = s.vlin[r]; ls.wb[r] = s.wb[r]; lp.com0[r] = par.com[0][r]; }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ls.quat[r] = s.quat[r];
+    lp.mass0 = par.mass[0];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        ls.q[k] = s.q[6 * side + k];
+        ls.qd[k] = s.qd[6 * side + k];
+        lp.mass[k] = par.mass[1 + 6 * side + k];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) lp.com[k][r] = par.com[1 + 6 * side + k][r];
+    }
+    lp.mu = par.mu[side]; lp.kscale = par.kscale[side]; lp.cscale = par.cscale[side];
 }
 
-// Sparse L^T D L in place (MuJoCo mj_factorM order: eliminate from the last DoF down, so the tree causes no fill-in).
-// Afterwards M(k,k) holds D_k and M(k,i), i<k holds L_ki.
-template <typename T, typename MS> B200_HD void factor_ltdl(MS& M) {
-#pragma unroll
-    for (int k = B200_NV - 1; k >= 0; --k) {
-        T inv = T(1) / M(k, k);
-#pragma unroll
-        for (int i = 0; i < k; ++i) {
-            if (!dof_coupled(k, i)) continue;
-            T l = M(k, i) * inv;
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                if (!dof_coupled(k, j) || !dof_coupled(i, j)) continue;
-                M(i, j) -= l * M(k, j);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < k; ++i)
-            if (dof_coupled(k, i)) M(k, i) *= inv;
-    }
-}
-template <typename T, typename MS> B200_HD void solve_ltdl(MS& M, T* x) {
-#pragma unroll
-    for (int i = B200_NV - 1; i >= 0; --i) {
-#pragma unroll
-        for (int j = 0; j < i; ++j)
-            if (dof_coupled(i, j)) x[j] -= M(i, j) * x[i];
-    }
-#pragma unroll
-    for (int i = 0; i < B200_NV; ++i) x[i] /= M(i, i);
-#pragma unroll
-    for (int i = 0; i < B200_NV; ++i) {
-#pragma unroll
-        for (int j = 0; j < i; ++j)
-            if (dof_coupled(i, j)) x[i] -= M(i, j) * x[j];
-    }
-}
-
-// One tick.  `tau` = 12 joint torques (already clipped), push_f/push_t = force/torque on the trunk in its LOCAL frame
-// applied at the trunk CoM (envs/t1.py:522-527, gymapi.LOCAL_SPACE).  terr(xw, yw) returns the ground height.
-// If `integrate` is false only qacc is produced (used by the one-step parity tests).
+// One tick of the whole robot.  `tau` = 12 joint torques (already clipped), push_f/push_t = force/torque on the trunk in
+// its LOCAL frame applied at the trunk CoM.  terr(xw, yw) returns the ground height.  If `integrate` is false only qacc is
+// produced (one-step parity tests).
 template <typename T, typename Model, typename Terr, typename MS>
-B200_HD void t1_tick(const Model& m, const DynParams<T>& par, DynState<T>& s, const T* tau, const T* push_f,
-                     const T* push_t, const Terr& terr, MS& M, DynAux<T>& aux, bool integrate) {
-    const T dt = m.dt;
-    // --- normalise the base quaternion, base rotation ---------------------------------------------------------
-    {
-        T n = b_sqrt(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
-        T inv = T(1) / n;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s.quat[i] *= inv;
+B200_HD void t1_tick(const Model& m, const DynParams<T>& par, DynState<T>& s, const T* tau, const T* push_f, const T* push_t,
+                     const Terr& terr, MS&, DynAux<T>& aux, bool integrate) {
+    LegState<T> ls[2];
+    LegParams<T> lp[2];
+    LegWork<T> W[2];
+    for (int side = 0; side < 2; ++side) {
+        leg_split(s, par, side, ls[side], lp[side]);
+        t1_leg_phase1<T>(m, lp[side], ls[side], side, tau + 6 * side, push_f, push_t, terr, W[side]);
     }
-    T R0[3][3];
-    quat_to_mat(s.quat, R0);
-    const T zero3[3] = {0, 0, 0};
+    for (int i = 0; i < 21; ++i) { const T t = W[0].Mbb[i] + W[1].Mbb[i]; W[0].Mbb[i] = t; W[1].Mbb[i] = t; }
+    for (int i = 0; i < 6; ++i) { const T t = W[0].rb[i] + W[1].rb[i]; W[0].rb[i] = t; W[1].rb[i] = t; }
+    for (int side = 0; side < 2; ++side) {
+        T qb[6], ql[6];
+        t1_leg_phase2<T>(m, ls[side], W[side], qb, ql, integrate);
+        for (int i = 0; i < 6; ++i) { aux.qacc[i] = qb[i]; aux.qacc[6 + 6 * side + i] = ql[i]; }
+        aux.foot_fn[side] = W[side].foot_fn;
+        for (int k = 0; k < 6; ++k) { s.q[6 * side + k] = ls[side].q[k]; s.qd[6 * side + k] = ls[side].qd[k]; }
+    }
+    for (int r = 0; r < 3; ++r) { s.pos[r] = ls[0].pos[r]; s.vlin[r] = ls[0].vlin[r]; s.wb[r] = ls[0].wb[r]; }
+    for (int r = 0; r < 4; ++r) s.quat[r] = ls[0].quat[r];
+}
 
-    // --- trunk: spatial inertia, velocity, bias acceleration -----------------------------------------------------
-    SpInertia<T> Ic0;
-    si_from_body(R0, zero3, par.com[0], m.inertia[0], par.mass[0], par.mass[0] / m.mass[0], Ic0);
-    T w0[3], v0[3];
+// Pose (world position + quaternion xyzw) of ONE foot link from a lane's state.
+template <typename T, typename Model>
+B200_HD void t1_foot_fk(const Model& m, const LegState<T>& s, int side, T* foot_pos, T* foot_quat) {
+    T R[3][3];
+    quat_to_mat(s.quat, R);
+    T x[3] = {s.pos[0], s.pos[1], s.pos[2]};
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        w0[r] = R0[r][0] * s.wb[0] + R0[r][1] * s.wb[1] + R0[r][2] * s.wb[2];
-        v0[r] = s.vlin[r];
-    }
-    T al0[3] = {0, 0, 0}, av0[3];
-    cross3(v0, w0, av0);  // spatial acceleration of the base with qacc = 0:  [0 ; v x w]  (+ gravity as fictitious accel)
-    av0[2] += m.gravity;
-    T f0n[3], f0f[3];  // accumulated bias wrench on the trunk about the reference point
-    {
-        T n1[3], f1[3], n2[3], f2[3], t1[3], t2[3];
-        si_mul(Ic0, al0, av0, n1, f1);
-        si_mul(Ic0, w0, v0, n2, f2);
-        cross3(w0, n2, t1);
-        cross3(v0, f2, t2);
+    for (int k = 0; k < 6; ++k) {
+        const int b = 1 + 6 * side + k;
+        const int axis = (k == 0 || k == 3 || k == 4) ? 1 : (k == 2 ? 2 : 0);
+        const T* off = m.body_pos[b];
+        T nx[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) f0n[r] = n1[r] + t1[r] + t2[r];
-        cross3(w0, f2, t1);
+        for (int r = 0; r < 3; ++r) nx[r] = x[r] + R[r][0] * off[0] + R[r][1] * off[1] + R[r][2] * off[2];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) f0f[r] = f1[r] + t1[r];
-    }
-    // push on the trunk (local frame, at the CoM): subtract from the bias wrench
-    {
-        T Fw[3], Tl[3], Tw[3], cw[3], cxF[3];
-        cross3(par.com[0], push_f, Tl);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) Tl[r] += push_t[r];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            Fw[r] = R0[r][0] * push_f[0] + R0[r][1] * push_f[1] + R0[r][2] * push_f[2];
-            Tw[r] = R0[r][0] * Tl[0] + R0[r][1] * Tl[1] + R0[r][2] * Tl[2];
-        }
-        (void)cw; (void)cxF;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { f0f[r] -= Fw[r]; f0n[r] -= Tw[r]; }
-    }
-
-    // --- legs: forward pass (kinematics, inertias, bias wrenches, foot contact) -----------------------------------
-    T ax[2][6][3], xj[2][6][3];  // world joint axis, joint anchor rel. reference point
-    SpInertia<T> Ic[2][6];
-    T fn[2][6][3], ff[2][6][3];  // bias wrench per body (angular, linear)
-    T Kc[2][21];                 // implicit contact matrix per foot (6x6 sym, lower-tri, order [ang; lin]), already * dt
-    T Rf[2][3][3];               // foot rotation (for the feet outputs)
-    bool foot_active[2];
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        T R[3][3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) R[r][c] = R0[r][c];
-        T xp[3] = {0, 0, 0};
-        T wp[3] = {w0[0], w0[1], w0[2]}, vp[3] = {v0[0], v0[1], v0[2]};
-        T alp[3] = {al0[0], al0[1], al0[2]}, avp[3] = {av0[0], av0[1], av0[2]};
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int b = 1 + 6 * sgn + k;
-            const int axis = (k == 0 || k == 3 || k == 4) ? 1 : (k == 2 ? 2 : 0);  // y x z y y x (t1_model.json "axis")
-            const T* off = m.body_pos[b];
-            T x[3], a[3], sl[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                x[r] = xp[r] + R[r][0] * off[0] + R[r][1] * off[1] + R[r][2] * off[2];
-                a[r] = R[r][axis];
-            }
-            rotate_about_axis(R, axis, s.q[6 * sgn + k]);
-            cross3(x, a, sl);  // linear part of the motion axis about the reference point
-            const T qd = s.qd[6 * sgn + k];
-            // velocity-product acceleration: a_b = a_p + qd * (V_p x S)
-            T t1[3], t2[3], t3[3];
-            cross3(wp, a, t1);
-            cross3(wp, sl, t2);
-            cross3(vp, a, t3);
-            T al[3], av[3], w[3], v[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                al[r] = alp[r] + qd * t1[r];
-                av[r] = avp[r] + qd * (t2[r] + t3[r]);
-                w[r] = wp[r] + qd * a[r];
-                v[r] = vp[r] + qd * sl[r];
-            }
-            si_from_body(R, x, par.com[b], m.inertia[b], par.mass[b], par.mass[b] / m.mass[b], Ic[sgn][k]);
-            T n1[3], f1[3], n2[3], f2[3];
-            si_mul(Ic[sgn][k], al, av, n1, f1);
-            si_mul(Ic[sgn][k], w, v, n2, f2);
-            cross3(w, n2, t1);
-            cross3(v, f2, t2);
-            cross3(w, f2, t3);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                fn[sgn][k][r] = n1[r] + t1[r] + t2[r];
-                ff[sgn][k][r] = f1[r] + t3[r];
-                ax[sgn][k][r] = a[r];
-                xj[sgn][k][r] = x[r];
-                xp[r] = x[r]; wp[r] = w[r]; vp[r] = v[r]; alp[r] = al[r]; avp[r] = av[r];
-            }
-        }
-        // ---- foot contact: 4 sole corners against the heightfield -------------------------------------------
-#pragma unroll
-        for (int i = 0; i < 21; ++i) Kc[sgn][i] = 0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Rf[sgn][r][c] = R[r][c];
-        foot_active[sgn] = false;
-        aux.foot_fn[sgn] = 0;
-        if (m.enable_contact) {
-            T Wn[3] = {0, 0, 0}, Wf[3] = {0, 0, 0};
-            const T kn = m.contact_k * par.kscale[sgn], cn = m.contact_c * par.cscale[sgn];
-            const T dn = cn + dt * kn;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const T* rc = m.foot_corner[c];
-                T p[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) p[r] = xp[r] + R[r][0] * rc[0] + R[r][1] * rc[1] + R[r][2] * rc[2];
-                const T ground = (T)terr((float)(s.pos[0] + p[0]), (float)(s.pos[1] + p[1]));
-                const T depth = ground - (s.pos[2] + p[2]);
-                if (depth > 0) {
-                    T wxp[3];
-                    cross3(wp, p, wxp);
-                    const T vc[3] = {vp[0] + wxp[0], vp[1] + wxp[1], vp[2] + wxp[2]};
-                    const T fn0 = kn * depth - cn * vc[2];
-                    if (fn0 > 0) {
-                        foot_active[sgn] = true;
-                        aux.foot_fn[sgn] += fn0;
-                        const T vt = b_sqrt(vc[0] * vc[0] + vc[1] * vc[1]);
-                        const T dtan = par.mu[sgn] * fn0 / b_max(vt, m.stiction_vel);
-                        const T Fe[3] = {-dtan * vc[0], -dtan * vc[1], kn * depth - dn * vc[2]};
-                        T pxF[3];
-                        cross3(p, Fe, pxF);
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) { Wn[r] += pxF[r]; Wf[r] += Fe[r]; }
-                        // K += dt * sum_d D_d r_d^T r_d with rows r_x = [0, pz, -py | 1 0 0], r_y = [-pz, 0, px | 0 1 0],
-                        // r_z = [py, -px, 0 | 0 0 1]   (point velocity = v + w x p)
-                        const T Dx = dt * dtan, Dy = dt * dtan, Dz = dt * dn;
-                        T* K = Kc[sgn];
-                        // lower-tri index (i,j) -> i(i+1)/2+j ; order: 0 wx,1 wy,2 wz,3 vx,4 vy,5 vz
-                        K[0] += Dy * p[2] * p[2] + Dz * p[1] * p[1];                      // (0,0)
-                        K[1] += -Dz * p[0] * p[1];                                        // (1,0)
-                        K[2] += Dx * p[2] * p[2] + Dz * p[0] * p[0];                      // (1,1)
-                        K[3] += -Dy * p[0] * p[2];                                        // (2,0)
-                        K[4] += -Dx * p[1] * p[2];                                        // (2,1)
-                        K[5] += Dx * p[1] * p[1] + Dy * p[0] * p[0];                      // (2,2)
-                        K[7] += Dx * p[2];                                                // (3,1)
-                        K[8] += -Dx * p[1];                                               // (3,2)
-                        K[9] += Dx;                                                       // (3,3)
-                        K[10] += -Dy * p[2];                                              // (4,0)
-                        K[12] += Dy * p[0];                                               // (4,2)
-                        K[14] += Dy;                                                      // (4,4)
-                        K[15] += Dz * p[1];                                               // (5,0)
-                        K[16] += -Dz * p[0];                                              // (5,1)
-                        K[20] += Dz;                                                      // (5,5)
-                    }
-                }
-            }
-            if (foot_active[sgn]) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { fn[sgn][5][r] -= Wn[r]; ff[sgn][5][r] -= Wf[r]; }
-            }
-        }
-    }
-
-    // --- backward pass: composite inertias and accumulated wrenches, bias forces ----------------------------------
-    T rhs[B200_NV];
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-#pragma unroll
-        for (int k = 5; k >= 0; --k) {
-            const int d = 6 + 6 * sgn + k;
-            T sl[3];
-            cross3(xj[sgn][k], ax[sgn][k], sl);
-            rhs[d] = tau[6 * sgn + k] - (dot3(ax[sgn][k], fn[sgn][k]) + dot3(sl, ff[sgn][k]));
-            if (k > 0) {
-                si_add(Ic[sgn][k - 1], Ic[sgn][k]);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { fn[sgn][k - 1][r] += fn[sgn][k][r]; ff[sgn][k - 1][r] += ff[sgn][k][r]; }
-            } else {
-                si_add(Ic0, Ic[sgn][0]);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { f0n[r] += fn[sgn][0][r]; f0f[r] += ff[sgn][0][r]; }
-            }
-        }
+        for (int r = 0; r < 3; ++r) x[r] = nx[r];
+        rotate_about_axis(R, axis, s.q[k]);
     }
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        rhs[r] = -f0f[r];
-        rhs[3 + r] = -(R0[0][r] * f0n[0] + R0[1][r] * f0n[1] + R0[2][r] * f0n[2]);
-    }
-
-    // --- mass matrix (CRBA) + implicit contact term ------------------------------------------------------------
-    // base block: S_lin,k = [0; e_k], S_ang,k = [R0[:,k]; 0]
-    {
-        // F for the 6 base DoFs through the total composite inertia (+ both feet's K)
-        T Fn[6][3], Ff[6][3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            T e[3] = {0, 0, 0};
-            e[k] = 1;
-            si_mul(Ic0, zero3, e, Fn[k], Ff[k]);
-            const T a[3] = {R0[0][k], R0[1][k], R0[2][k]};
-            si_mul(Ic0, a, zero3, Fn[3 + k], Ff[3 + k]);
-#pragma unroll
-            for (int sgn = 0; sgn < 2; ++sgn) {
-                if (!foot_active[sgn]) continue;
-                const T* K = Kc[sgn];
-                // K * [0; e_k]  -> column 3+k of K ; K * [a; 0]
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const int ci = 3 + k;
-                    // symmetric fetch K(r, ci) with ci > r
-                    Fn[k][r] += K[ci * (ci + 1) / 2 + r];
-                    const int lo = (r < k) ? r : k, hi = (r < k) ? k : r;
-                    Ff[k][r] += K[(3 + hi) * (3 + hi + 1) / 2 + 3 + lo];
-                    T accn = 0, accf = 0;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int l2 = (r < c) ? r : c, h2 = (r < c) ? c : r;
-                        accn += K[h2 * (h2 + 1) / 2 + l2] * a[c];
-                        accf += K[(3 + r) * (3 + r + 1) / 2 + c] * a[c];
-                    }
-                    Fn[3 + k][r] += accn;
-                    Ff[3 + k][r] += accf;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                // M(i,j) = S_j . F_i
-                if (j < 3) M(i, j) = Ff[i][j];
-                else M(i, j) = R0[0][j - 3] * Fn[i][0] + R0[1][j - 3] * Fn[i][1] + R0[2][j - 3] * Fn[i][2];
-            }
-        }
-    }
-#pragma unroll
-    for (int sgn = 0; sgn < 2; ++sgn) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int d = 6 + 6 * sgn + k;
-            T sl[3], Fn[3], Ff[3];
-            cross3(xj[sgn][k], ax[sgn][k], sl);
-            si_mul(Ic[sgn][k], ax[sgn][k], sl, Fn, Ff);
-            if (foot_active[sgn]) {
-                const T* K = Kc[sgn];
-                const T S6[6] = {ax[sgn][k][0], ax[sgn][k][1], ax[sgn][k][2], sl[0], sl[1], sl[2]};
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    T acc = 0;
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) {
-                        const int lo = (r < c) ? r : c, hi = (r < c) ? c : r;
-                        acc += K[hi * (hi + 1) / 2 + lo] * S6[c];
-                    }
-                    if (r < 3) Fn[r] += acc; else Ff[r - 3] += acc;
-                }
-            }
-            // with the base
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                M(d, j) = Ff[j];
-                M(d, 3 + j) = R0[0][j] * Fn[0] + R0[1][j] * Fn[1] + R0[2][j] * Fn[2];
-            }
-            // with the ancestors in the same leg (and itself)
-#pragma unroll
-            for (int j = 0; j <= k; ++j) {
-                T slj[3];
-                cross3(xj[sgn][j], ax[sgn][j], slj);
-                M(d, 6 + 6 * sgn + j) = dot3(ax[sgn][j], Fn) + dot3(slj, Ff);
-            }
-        }
-    }
-    // the left/right block is structurally zero and never touched by factor/solve
-
-    // --- joint limits: spring explicit + linearly-implicit damper on the diagonal ---------------------------------
-    if (m.enable_limits) {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            const T q = s.q[j], qd = s.qd[j];
-            T viol = 0;
-            if (q < m.jnt_lower[j]) viol = m.jnt_lower[j] - q;
-            else if (q > m.jnt_upper[j]) viol = m.jnt_upper[j] - q;
-            if (viol != 0) {
-                const T ke = m.limit_k * m.dof_inertia[j], ce = m.limit_c * m.dof_inertia[j];
-                const T de = ce + dt * ke;
-                rhs[6 + j] += ke * viol - de * qd;
-                M(6 + j, 6 + j) += dt * de;
-            }
-        }
-    }
-
-    // --- solve, integrate (semi-implicit Euler, MuJoCo mj_Euler) --------------------------------------------------
-    factor_ltdl<T>(M);
-    solve_ltdl<T>(M, rhs);
-#pragma unroll
-    for (int i = 0; i < B200_NV; ++i) aux.qacc[i] = rhs[i];
-    if (!integrate) return;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        s.vlin[r] += dt * rhs[r];
-        s.wb[r] += dt * rhs[3 + r];
-        s.pos[r] += dt * s.vlin[r];
-    }
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        s.qd[j] += dt * rhs[6 + j];
-        s.q[j] += dt * s.qd[j];
-    }
-    {
-        // quat <- quat (x) exp(dt * wb / 2)   (body-frame angular velocity: right multiplication)
-        const T wn = b_sqrt(s.wb[0] * s.wb[0] + s.wb[1] * s.wb[1] + s.wb[2] * s.wb[2]);
-        T sh, ch, k;
-        b_sincos(T(0.5) * dt * wn, sh, ch);
-        k = (wn > T(1e-9)) ? sh / wn : T(0.5) * dt;
-        const T dx = k * s.wb[0], dy = k * s.wb[1], dz = k * s.wb[2], dw = ch;
-        const T x = s.quat[0], y = s.quat[1], z = s.quat[2], w = s.quat[3];
-        T nq[4];
-        nq[0] = w * dx + x * dw + y * dz - z * dy;
-        nq[1] = w * dy - x * dz + y * dw + z * dx;
-        nq[2] = w * dz + x * dy - y * dx + z * dw;
-        nq[3] = w * dw - x * dx - y * dy - z * dz;
-        const T inv = T(1) / b_sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s.quat[i] = nq[i] * inv;
-    }
+    for (int r = 0; r < 3; ++r) foot_pos[r] = x[r];
+    mat_to_quat(R, foot_quat);
 }
 
 // Feet poses (world position + quaternion xyzw) from the current configuration: the rigid_body_state rows that

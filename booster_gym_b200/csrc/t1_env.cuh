@@ -126,115 +126,130 @@ B200_HD float apply_rand(float x, const B200Rand& r, float u, float nrm) {
 B200_HD float raw_rand(const B200Rand& r, float u, float nrm) { return (r.dist == 0) ? nrm : u; }
 
 // ---- envs/t1.py:439-456 + the physics engine: the decimated PD-torque loop ----------------------------------------
-// act: this env's 12 actions (policy output, unclipped) or raw torques if !apply_pd.
-template <typename Model, typename MS>
-B200_HD void env_physics(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr,
-                         const float* act, int n_substeps, int apply_pd, MS& M, float* qacc_out /*18 or null*/) {
+// Device only: one environment runs on a PAIR of adjacent lanes (side = lane & 1 = left / right leg, see the leg-parallel
+// formulation in t1_dynamics.cuh); both lanes carry the base redundantly.  act6: this leg's 6 actions (policy output,
+// unclipped) or raw torques if !apply_pd.  Lanes whose env index is out of range compute on a clamped index and store
+// nothing (they must still take part in the shuffles).
+#if defined(__CUDACC__)
+template <typename T> __device__ __forceinline__ T pair_sum(T x) { return x + __shfl_xor_sync(0xffffffffu, x, 1); }
+
+template <typename Model>
+__device__ __forceinline__ void env_physics_pair(const EnvView& v, int e, bool valid, int side, const Model& m, const B200T1Config& c,
+                                                 const TerrainView& terr, const float* act6, int n_substeps, int apply_pd,
+                                                 float* qacc_out /*[18][n] or null*/) {
     float* f = v.f;
     int32_t* is = v.is;
     const int n = v.n;
-    DynState<float> s;
-    DynParams<float> par;
+    LegState<float> s;
+    LegParams<float> par;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s.pos[i] = FS(F_root_states + i); s.vlin[i] = FS(F_root_states + 7 + i); }
 #pragma unroll
     for (int i = 0; i < 4; ++i) s.quat[i] = FS(F_root_states + 3 + i);
     {
-        float ww[3] = {FS(F_root_states + 10), FS(F_root_states + 11), FS(F_root_states + 12)};
+        const float ww[3] = {FS(F_root_states + 10), FS(F_root_states + 11), FS(F_root_states + 12)};
         float R0[3][3];
         quat_to_mat(s.quat, R0);
 #pragma unroll
         for (int k = 0; k < 3; ++k) s.wb[k] = R0[0][k] * ww[0] + R0[1][k] * ww[1] + R0[2][k] * ww[2];
     }
+    const int j0 = 6 * side, b0 = 1 + 6 * side;
+    par.mass0 = FS(F_body_mass);
 #pragma unroll
-    for (int j = 0; j < 12; ++j) { s.q[j] = FS(F_dof_pos + j); s.qd[j] = FS(F_dof_vel + j); }
+    for (int r = 0; r < 3; ++r) par.com0[r] = FS(F_body_com + r);
 #pragma unroll
-    for (int b = 0; b < B200_NB; ++b) {
-        par.mass[b] = FS(F_body_mass + b);
+    for (int k = 0; k < 6; ++k) {
+        s.q[k] = FS(F_dof_pos + j0 + k);
+        s.qd[k] = FS(F_dof_vel + j0 + k);
+        par.mass[k] = FS(F_body_mass + b0 + k);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) par.com[b][r] = FS(F_body_com + 3 * b + r);
+        for (int r = 0; r < 3; ++r) par.com[k][r] = FS(F_body_com + 3 * (b0 + k) + r);
     }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        par.mu[k] = FS(F_foot_friction + k);
-        par.kscale[k] = FS(F_foot_kscale + k);
-        par.cscale[k] = FS(F_foot_cscale + k);
-    }
+    par.mu = FS(F_foot_friction + side);
+    par.kscale = FS(F_foot_kscale + side);
+    par.cscale = FS(F_foot_cscale + side);
     float push_f[3], push_t[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) { push_f[r] = FS(F_pushing_forces + r); push_t[r] = FS(F_pushing_torques + r); }
 
-    float target[12], last_target[12], tsum[12], kp[12], kd[12], fr[12];
+    float target[6], last_target[6], tsum[6], kp[6], kd[6], fr[6], tlim[6];
     const int delay = IS(I_delay_steps);
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
+    for (int k = 0; k < 6; ++k) {
         if (apply_pd) {
-            const float a = fminf(fmaxf(act[j], -c.clip_actions), c.clip_actions);  // envs/t1.py:439
-            FS(F_actions + j) = a;
-            target[j] = c.default_dof_pos[j] + c.action_scale * a;                  // :440
+            const float a = fminf(fmaxf(act6[k], -c.clip_actions), c.clip_actions);  // envs/t1.py:439
+            if (valid) FS(F_actions + j0 + k) = a;
+            target[k] = c.default_dof_pos[j0 + k] + c.action_scale * a;             // :440
         } else {
-            target[j] = act[j];
+            target[k] = act6[k];
         }
-        last_target[j] = FS(F_last_dof_targets + j);
-        kp[j] = FS(F_dof_stiffness + j);
-        kd[j] = FS(F_dof_damping + j);
-        fr[j] = FS(F_dof_friction + j);
-        tsum[j] = 0.0f;
+        last_target[k] = FS(F_last_dof_targets + j0 + k);
+        kp[k] = FS(F_dof_stiffness + j0 + k);
+        kd[k] = FS(F_dof_damping + j0 + k);
+        fr[k] = FS(F_dof_friction + j0 + k);
+        tlim[k] = c.torque_limits[j0 + k];
+        tsum[k] = 0.0f;
     }
-    DynAux<float> aux;
-    aux.foot_fn[0] = aux.foot_fn[1] = 0.0f;
+    LegWork<float> W;
+    float qb[6], ql[6];
     for (int i = 0; i < n_substeps; ++i) {
-        float tau[12];
+        float tau[6];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
+        for (int k = 0; k < 6; ++k) {
             if (apply_pd) {
-                if (delay == i) last_target[j] = target[j];                            // :445
-                float t = kp[j] * (last_target[j] - s.q[j]) - kd[j] * s.qd[j];         // :446
-                const float fric = fminf(fr[j], fabsf(t)) * ((t > 0.0f) ? 1.0f : ((t < 0.0f) ? -1.0f : 0.0f));  // :447
-                t = fminf(fmaxf(t - fric, -c.torque_limits[j]), c.torque_limits[j]);   // :448
-                tau[j] = t;
-                tsum[j] += t;                                                          // :449
+                if (delay == i) last_target[k] = target[k];                                 // :445
+                float t = kp[k] * (last_target[k] - s.q[k]) - kd[k] * s.qd[k];             // :446
+                const float fric = fminf(fr[k], fabsf(t)) * ((t > 0.0f) ? 1.0f : ((t < 0.0f) ? -1.0f : 0.0f));  // :447
+                t = fminf(fmaxf(t - fric, -tlim[k]), tlim[k]);                             // :448
+                tau[k] = t;
+                tsum[k] += t;                                                              // :449
             } else {
-                tau[j] = target[j];
+                tau[k] = target[k];
             }
         }
-        t1_tick<float>(m, par, s, tau, push_f, push_t, terr, M, aux, true);
+        t1_leg_phase1<float>(m, par, s, side, tau, push_f, push_t, terr, W);
+#pragma unroll
+        for (int q = 0; q < 21; ++q) W.Mbb[q] = pair_sum(W.Mbb[q]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) W.rb[q] = pair_sum(W.rb[q]);
+        t1_leg_phase2<float>(m, s, W, qb, ql, true);
     }
-    // write back (refresh_* tensors of envs/t1.py:454,460-462)
+    if (!valid) return;
+    // write back (refresh_* tensors of envs/t1.py:454,460-462): the left-leg lane stores the base
+    if (side == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { FS(F_root_states + i) = s.pos[i]; FS(F_root_states + 7 + i) = s.vlin[i]; }
+        for (int i = 0; i < 3; ++i) { FS(F_root_states + i) = s.pos[i]; FS(F_root_states + 7 + i) = s.vlin[i]; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) FS(F_root_states + 3 + i) = s.quat[i];
-    {
+        for (int i = 0; i < 4; ++i) FS(F_root_states + 3 + i) = s.quat[i];
         float R0[3][3];
         quat_to_mat(s.quat, R0);
 #pragma unroll
         for (int r = 0; r < 3; ++r) FS(F_root_states + 10 + r) = R0[r][0] * s.wb[0] + R0[r][1] * s.wb[1] + R0[r][2] * s.wb[2];
-    }
+        if (qacc_out) {
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        FS(F_dof_pos + j) = s.q[j];
-        FS(F_dof_vel + j) = s.qd[j];
-        if (apply_pd) {
-            FS(F_last_dof_targets + j) = last_target[j];
-            FS(F_torques + j) = tsum[j] / (float)n_substeps;                           // :456
+            for (int i = 0; i < 6; ++i) qacc_out[(size_t)i * n + e] = qb[i];
         }
     }
-    float fp[2][3], fq[2][4];
-    t1_feet_fk<float>(m, s, fp, fq);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) FS(F_feet_pos + 3 * k + r) = fp[k][r];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) FS(F_feet_quat + 4 * k + r) = fq[k][r];
-        FS(F_feet_force + k) = aux.foot_fn[k];
+    for (int k = 0; k < 6; ++k) {
+        FS(F_dof_pos + j0 + k) = s.q[k];
+        FS(F_dof_vel + j0 + k) = s.qd[k];
+        if (apply_pd) {
+            FS(F_last_dof_targets + j0 + k) = last_target[k];
+            FS(F_torques + j0 + k) = tsum[k] / (float)n_substeps;                          // :456
+        }
+        if (qacc_out) qacc_out[(size_t)(6 + j0 + k) * n + e] = ql[k];
     }
-    if (qacc_out) {
+    // pose of this foot link after the last tick (rigid_body_state rows read at envs/t1.py:223-224,530-531)
+    float fp[3], fq[4];
+    t1_foot_fk<float>(m, s, side, fp, fq);
 #pragma unroll
-        for (int i = 0; i < B200_NV; ++i) qacc_out[i] = aux.qacc[i];
-    }
+    for (int r = 0; r < 3; ++r) FS(F_feet_pos + 3 * side + r) = fp[r];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) FS(F_feet_quat + 4 * side + r) = fq[r];
+    FS(F_feet_force + side) = W.foot_fn;
 }
+#endif  // __CUDACC__
 
 // ---- envs/t1.py:529-549 ------------------------------------------------------------------------------------------
 template <typename Model>
