@@ -55,7 +55,7 @@ PROTOTYPES = {
     "b200_ppo_apply": (_i, [_vp, _vp]),
     "b200_launch_count": (C.c_longlong, []),
     "b200_profile_gemm": (_i, [_i]),
-    "b200_profile_gemm_read": (_i, [C.POINTER(_d), C.POINTER(_d), _ip]),
+    "b200_profile_gemm_read": (_i, [_i, C.POINTER(_d), C.POINTER(_d), _ip]),
 }
 
 

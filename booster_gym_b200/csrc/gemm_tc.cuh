@@ -100,6 +100,33 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+__device__ __forceinline__ void ldg_v8(const float* p, float* a) {  // 256-bit global load (sm_100: LDG.E.256), 32-byte aligned
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(float* p, const float* a) {  // 256-bit global store: one full 32-byte sector per thread
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
+}
+// ELU for the tcgen05 forward epilogue (critic): x > 0 ? x : expm1(x).  expm1 for x <= 0 as a degree-7 Taylor polynomial on
+// [-0.25, 0] (truncation < 2e-9 relative) and ex2.approx(x * log2 e) - 1 below (|result| >= 0.22, absolute error of
+// ex2.approx <= 2^-22.5 * e^x -> < 1e-6 relative): branch-free, ~12 instructions instead of ~30 for expm1f.
+__device__ __forceinline__ float elu_fast(float x) {
+    const float xm = fminf(x, 0.0f);
+    float p = 1.0f / 5040.0f;
+    p = fmaf(p, xm, 1.0f / 720.0f);
+    p = fmaf(p, xm, 1.0f / 120.0f);
+    p = fmaf(p, xm, 1.0f / 24.0f);
+    p = fmaf(p, xm, 1.0f / 6.0f);
+    p = fmaf(p, xm, 0.5f);
+    p = fmaf(p, xm, 1.0f);
+    p = p * xm;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xm * 1.4426950408889634f));
+    const float neg = (xm > -0.25f) ? p : (e - 1.0f);
+    return (x > 0.0f) ? x : neg;
+}
+
 static constexpr int EPI_WARPS = 16;                   // 4 per TMEM lane quarter, each takes a quarter of the tile's columns
 static constexpr int ROW_THREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 template <int BN, int STAGES>
@@ -112,7 +139,7 @@ struct RowSmem {
 // so it gets 16 warps; each thread owns one output row (its TMEM lane) and 32 consecutive columns per step, which it
 // reads / writes as eight 16-byte vectors: every 32-byte sector is touched by two back-to-back instructions of the same
 // thread (L1 / L2 merge them), no shared-memory staging is needed.
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int NACC>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
 k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
               const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const RowArgs g) {
@@ -127,6 +154,11 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.Nout + BN - 1) / BN, tiles = m_tiles * n_tiles;
     const int nk = (g.K + BK - 1) / BK;
+    // NACC accumulators per tile (k-blocks rotate over them; the epilogue adds them with round-to-nearest FADDs, which
+    // shortens the truncating TMEM accumulation chains NACC-fold); double-buffered across tiles when TMEM has room
+    constexpr int NBUF = (2 * BN * NACC <= 512) ? 2 : 1;
+    constexpr uint32_t TCOLS = NBUF * BN * NACC;
+    static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM allocation must be a power of two <= 512 columns");
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -134,7 +166,7 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -166,20 +198,21 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
             constexpr uint32_t idesc = idesc_tf32(BN, false);
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-                const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
-                mbar_wait(&tempty[a], aph ^ 1);  // the epilogue has drained this accumulator
+                const uint32_t a = (NBUF == 2) ? (tl & 1) : 0, aph = (NBUF == 2) ? ((tl >> 1) & 1) : (tl & 1);
+                mbar_wait(&tempty[a], aph ^ 1);  // the epilogue has drained this accumulator set
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t tacc = tmem_base + a * BN;
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES,
                                    b_lo = b_hi + S::B_BYTES;
+                    const uint32_t tacc = tmem_base + (a * NACC + (uint32_t)(kb % NACC)) * BN;
+                    const bool first = kb < NACC;  // the first k-block of an accumulator overwrites it
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint32_t off = k * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                        umma_tf32(tacc, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                        umma_tf32(tacc, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), idesc, (first && k == 0) ? 0u : 1u);
                         umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), idesc, 1u);
                         umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), idesc, 1u);
                     }
@@ -195,17 +228,26 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
+            const uint32_t a = (NBUF == 2) ? (tl & 1) : 0, aph = (NBUF == 2) ? ((tl >> 1) & 1) : (tl & 1);
             mbar_wait(&tfull[a], aph);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int row = m0 + q * 32 + lane;
+            const int nacc_used = nk < NACC ? nk : NACC;
 #pragma unroll 1
             for (int cc = 0; cc < PER; ++cc) {
                 const int c = cg * PER + cc;
                 if (c >= CHUNKS) break;
                 const int col0 = n0 + c * 32;
                 uint32_t r[32];
-                tmem_ld32(tmem_base + a * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                tmem_ld32(tmem_base + a * NACC * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                if (NACC > 1) {
+                    for (int aa = 1; aa < nacc_used; ++aa) {
+                        uint32_t r2[32];
+                        tmem_ld32(tmem_base + (a * NACC + aa) * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                    }
+                }
                 if (row >= g.M || col0 >= g.Nout) continue;
                 const size_t base = (size_t)row * g.ldo + col0;
                 float v[32];
@@ -217,27 +259,30 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const float x = __uint_as_float(r[j + t]) + bb[t];
-                            v[j + t] = (x > 0.0f) ? x : expm1f(x);
+                            v[j + t] = (NACC > 1) ? ((x > 0.0f) ? x : expm1f(x)) : elu_fast(x);  // the accurate (multi-accumulator) variant keeps expm1f
                         }
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 h4 = *reinterpret_cast<const float4*>(g.aux_hi + base + j);
-                        const float4 l4 = *reinterpret_cast<const float4*>(g.aux_lo + base + j);
-                        const float hh[4] = {h4.x + l4.x, h4.y + l4.y, h4.z + l4.z, h4.w + l4.w};
+                    for (int j = 0; j < 32; j += 8) {
+                        float h8[8], l8[8];
+                        ldg_v8(g.aux_hi + base + j, h8);
+                        ldg_v8(g.aux_lo + base + j, l8);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) v[j + t] = __uint_as_float(r[j + t]) * ((hh[t] > 0.0f) ? 1.0f : (hh[t] + 1.0f));
+                        for (int t = 0; t < 8; ++t) {
+                            const float hh = h8[t] + l8[t];
+                            v[j + t] = __uint_as_float(r[j + t]) * ((hh > 0.0f) ? 1.0f : (hh + 1.0f));
+                        }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float hi[4], lo[4];
+                for (int j = 0; j < 32; j += 8) {
+                    float hi[8], lo[8];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) { hi[t] = tf32_rna(v[j + t]); lo[t] = tf32_rna(v[j + t] - hi[t]); }
-                    *reinterpret_cast<float4*>(g.out_hi + base + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(g.out_lo + base + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + base + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int t = 0; t < 8; ++t) { hi[t] = tf32_rna(v[j + t]); lo[t] = tf32_rna(v[j + t] - hi[t]); }
+                    stg_v8(g.out_hi + base + j, hi);
+                    stg_v8(g.out_lo + base + j, lo);
+                    if (g.out_f32) stg_v8(g.out_f32 + base + j, v + j);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -247,7 +292,7 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
 }
 
 // ---- weight gradient: D[Nout, Kin] += sum over rows m of dY[m, Nout]^T X[m, Kin] ------------------------------------
@@ -258,6 +303,10 @@ struct WgradArgs {
     int chunk;        // rows per CTA along blockIdx.x (multiple of 32)
 };
 
+// Each CTA owns ONE output tile and a contiguous range of `chunk` rows of the reduction (so a single wave of ~148 CTAs
+// covers the problem and every tile element receives one atomic per CTA of its tile).  To keep the truncating TMEM
+// accumulation chains short, k-blocks rotate over NACC = 512 / BN (<= 4) accumulators that the epilogue adds with
+// round-to-nearest FADDs before the atomics.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUtensorMap mYl, const __grid_constant__ CUtensorMap mXh,
@@ -265,6 +314,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUte
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);
+    constexpr uint32_t TCOLS = NACC * BN < 32 ? 32 : NACC * BN;
     uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
@@ -272,8 +323,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUte
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r_begin = blockIdx.x * g.chunk, r_end = min(g.M, r_begin + g.chunk);
     const int n0 = blockIdx.y * BM, k0 = blockIdx.z * BN;
-    const int nk = (r_end - r_begin + BK - 1) / BK;
-    constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
+    const int nk = (r_end > r_begin) ? (r_end - r_begin + BK - 1) / BK : 0;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tfull, 1);
@@ -287,59 +337,72 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUte
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nk; ++kb) {
-                const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                const int r = r_begin + kb * BK;
+    if (nk > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int kb = 0; kb < nk; ++kb) {
+                    const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    const int r = r_begin + kb * BK;
 #pragma unroll
-                for (int c = 0; c < BM / 32; ++c) {
-                    tma_load_2d(&mYh, &full[s], st + c * 4096, n0 + c * 32, r);
-                    tma_load_2d(&mYl, &full[s], st + A_BYTES + c * 4096, n0 + c * 32, r);
-                }
+                    for (int c = 0; c < BM / 32; ++c) {
+                        tma_load_2d(&mYh, &full[s], st + c * 4096, n0 + c * 32, r);
+                        tma_load_2d(&mYl, &full[s], st + A_BYTES + c * 4096, n0 + c * 32, r);
+                    }
 #pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
-                    tma_load_2d(&mXh, &full[s], st + 2 * A_BYTES + c * 4096, k0 + c * 32, r);
-                    tma_load_2d(&mXl, &full[s], st + 2 * A_BYTES + B_BYTES + c * 4096, k0 + c * 32, r);
+                    for (int c = 0; c < BN / 32; ++c) {
+                        tma_load_2d(&mXh, &full[s], st + 2 * A_BYTES + c * 4096, k0 + c * 32, r);
+                        tma_load_2d(&mXl, &full[s], st + 2 * A_BYTES + B_BYTES + c * 4096, k0 + c * 32, r);
+                    }
                 }
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_tf32(BN, true);
-            for (int kb = 0; kb < nk; ++kb) {
-                const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = idesc_tf32(BN, true);
+                for (int kb = 0; kb < nk; ++kb) {
+                    const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                    const uint32_t tacc = tmem_base + (uint32_t)(kb % NACC) * BN;
+                    const bool first = kb < NACC;  // first k-block of this accumulator overwrites it
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    const uint32_t off = k * 1024;  // 8 rows (samples) = two 4-row swizzle groups
-                    umma_tf32(tmem_base, desc_mnmajor(a_lo + off), desc_mnmajor(b_hi + off), idesc, (kb | k) ? 1u : 0u);
-                    umma_tf32(tmem_base, desc_mnmajor(a_hi + off), desc_mnmajor(b_lo + off), idesc, 1u);
-                    umma_tf32(tmem_base, desc_mnmajor(a_hi + off), desc_mnmajor(b_hi + off), idesc, 1u);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint32_t off = k * 1024;  // 8 rows (samples) = two 4-row swizzle groups
+                        umma_tf32(tacc, desc_mnmajor(a_lo + off), desc_mnmajor(b_hi + off), idesc, (first && k == 0) ? 0u : 1u);
+                        umma_tf32(tacc, desc_mnmajor(a_hi + off), desc_mnmajor(b_lo + off), idesc, 1u);
+                        umma_tf32(tacc, desc_mnmajor(a_hi + off), desc_mnmajor(b_hi + off), idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(tfull);
             }
-            umma_commit(tfull);
-        }
-    } else {
-        const int q = warp & 3;
-        mbar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        const int row = n0 + q * 32 + lane;
+        } else {
+            const int q = warp & 3;
+            mbar_wait(tfull, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int row = n0 + q * 32 + lane;
+            const int nacc_used = nk < NACC ? nk : NACC;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            if (row < g.Nout) {
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                float acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = k0 + c * 32 + j;
-                    if (col < g.Kin) atomicAdd(g.D + (size_t)row * g.ldd + col, __uint_as_float(r[j]));
+                for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+                for (int a = 1; a < nacc_used; ++a) {
+                    tmem_ld32(tmem_base + (uint32_t)a * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+                }
+                if (row < g.Nout) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = k0 + c * 32 + j;
+                        if (col < g.Kin) atomicAdd(g.D + (size_t)row * g.ldd + col, acc[j]);
+                    }
                 }
             }
         }
@@ -390,19 +453,19 @@ struct MapCache {
     }
 };
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int NACC = 1>
 inline cudaError_t launch_rowmajor(const CUtensorMap* Ah, const CUtensorMap* Al, const CUtensorMap* Bh, const CUtensorMap* Bl,
                                    const RowArgs& g, int num_sms, cudaStream_t st) {
     using S = RowSmem<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(k_tc_rowmajor<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        const cudaError_t e = cudaFuncSetAttribute(k_tc_rowmajor<BN, STAGES, EPI, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = ((g.M + BM - 1) / BM) * ((g.Nout + BN - 1) / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    k_tc_rowmajor<BN, STAGES, EPI><<<grid, ROW_THREADS, S::TOTAL, st>>>(*Ah, *Al, *Bh, *Bl, g);
+    k_tc_rowmajor<BN, STAGES, EPI, NACC><<<grid, ROW_THREADS, S::TOTAL, st>>>(*Ah, *Al, *Bh, *Bl, g);
     return cudaPeekAtLastError();
 }
 

@@ -229,6 +229,74 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, co
     }
 }
 
+// actor head (utils/model.py:25): MU[m, 0..11] = b + H[m, :] W[12,128]^T, one warp per row, plain fp32 FMAs (the 12-wide
+// layer is 2 % of the MLP's FLOPs: a tensor-core tile would be 90 % padding).  H = Hf, or Hh + Hl when Hl != null.
+__global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf, const float* __restrict__ Hl, const float* __restrict__ W,
+                                                    const float* __restrict__ b, int n, float* __restrict__ MU) {
+    __shared__ float4 sW[12][32];
+    for (int i = threadIdx.x; i < 12 * 32; i += blockDim.x) sW[i >> 5][i & 31] = reinterpret_cast<const float4*>(W)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n; row += warps) {
+        float4 h = reinterpret_cast<const float4*>(Hf + (size_t)row * 128)[lane];
+        if (Hl) {
+            const float4 l = reinterpret_cast<const float4*>(Hl + (size_t)row * 128)[lane];
+            h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
+        }
+        float out = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const float4 w = sW[j][lane];
+            float s = h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == j) out = s + b[j];
+        }
+        if (lane < 12) MU[(size_t)row * 12 + lane] = out;
+    }
+}
+
+// backward of the actor head, fused: dH[m,k] = (sum_j dMU[m,j] W[j,k]) ELU'(H[m,k]) written pre-split (hi, lo);
+// dW[j,k] += sum_m dMU[m,j] H[m,k]; db[j] += sum_m dMU[m,j].   128 threads = the 128 hidden units, rows in chunks.
+#define AH_ROWS 128
+__global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ Hl, const float* __restrict__ W,
+                                                        const float* __restrict__ dMU, int n, float* __restrict__ dHh,
+                                                        float* __restrict__ dHl, float* __restrict__ dW, float* __restrict__ db) {
+    __shared__ float sd[AH_ROWS][12];
+    const int k = threadIdx.x;
+    const int r0 = blockIdx.x * AH_ROWS, r1 = min(n, r0 + AH_ROWS);
+    for (int i = threadIdx.x; i < (r1 - r0) * 12; i += 128) sd[i / 12][i % 12] = dMU[(size_t)r0 * 12 + i];
+    float w[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) w[j] = W[j * 128 + k];
+    __syncthreads();
+    double acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 0.0;
+    for (int r = r0; r < r1; ++r) {
+        const float h = Hf[(size_t)r * 128 + k] + Hl[(size_t)r * 128 + k];
+        float g = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const float d = sd[r - r0][j];
+            g = fmaf(d, w[j], g);
+            acc[j] += (double)d * (double)h;
+        }
+        float hi, lo;
+        split_tf32f(g * ((h > 0.0f) ? 1.0f : (h + 1.0f)), hi, lo);
+        dHh[(size_t)r * 128 + k] = hi;
+        dHl[(size_t)r * 128 + k] = lo;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) atomicAdd(dW + j * 128 + k, (float)acc[j]);
+    if (k < 12) {
+        double s = 0.0;
+        for (int r = r0; r < r1; ++r) s += (double)sd[r - r0][k];
+        atomicAdd(db + k, (float)s);
+    }
+}
+
 // rollout sampling (utils/runner.py:110-111): act = mu + exp(logstd) * eps
 __global__ void k_sample(const float* __restrict__ mu, const float* __restrict__ logstd, const float* __restrict__ eps_in,
                          int n, uint64_t seed, uint64_t step, const unsigned long long* __restrict__ ctr, int env_base,
@@ -531,18 +599,21 @@ __global__ void k_post_apply(float* __restrict__ scalars, const double* __restri
 namespace b200 {
 long long g_launches = 0;
 }
+enum { PK_MMA_SYNC = 0, PK_TC_ROW = 1, PK_TC_WGRAD = 2, PK_COUNT = 3 };  // kernel families timed by b200_profile_gemm
 struct GemmProfile {
     bool on = false;
     int used = 0;
     static const int kMax = 8192;
     cudaEvent_t* ev = nullptr;  // 2 * kMax
-    double flops = 0.0;
+    unsigned char* kind = nullptr;
+    double flops[PK_COUNT] = {0.0, 0.0, 0.0};
 } g_prof;
 
-static void prof_begin(cudaStream_t st, double flops) {
+static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC) {
     if (!g_prof.on || g_prof.used >= GemmProfile::kMax) return;
     cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
-    g_prof.flops += flops;
+    g_prof.kind[g_prof.used] = (unsigned char)kind;
+    g_prof.flops[kind] += flops;
 }
 static void prof_end(cudaStream_t st) {
     if (!g_prof.on || g_prof.used >= GemmProfile::kMax) return;
@@ -616,8 +687,8 @@ static cudaError_t bias_grad(const float* dY, const float* dYl, int ld, int C, i
 
 // Y(h,l[,f]) [n, n_out] = ELU(X(h,l) [n, k] W(h,l) [n_out, k_pad]^T + b)
 static int tc_fwd(const B200Ppo* p, const float* Xh, const float* Xl, int k, int ldx, const float* Wh, const float* Wl, int k_pad,
-                  const float* b, float* Yh, float* Yl, float* Yf, int n, int n_out, cudaStream_t st) {
-    const int bn = (n_out >= 256) ? 256 : 128;
+                  const float* b, float* Yh, float* Yl, float* Yf, int n, int n_out, cudaStream_t st, bool accurate = false) {
+    const int bn = (n_out >= 256 && !accurate) ? 256 : 128;
     TC_MAP(mAh, Xh, n, k, ldx, tc::BM, true);
     TC_MAP(mAl, Xl, n, k, ldx, tc::BM, true);
     TC_MAP(mBh, Wh, n_out, k_pad, k_pad, bn, true);
@@ -625,9 +696,10 @@ static int tc_fwd(const B200Ppo* p, const float* Xh, const float* Xl, int k, int
     tc::RowArgs g{};
     g.out_hi = Yh; g.out_lo = Yl; g.out_f32 = Yf; g.bias = b; g.aux_hi = nullptr; g.aux_lo = nullptr;
     g.M = n; g.Nout = n_out; g.K = k_pad; g.ldo = n_out;
-    prof_begin(st, 2.0 * n * (double)n_out * k);
-    const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
-                                      : tc::launch_rowmajor<128, 3, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st);
+    prof_begin(st, 2.0 * n * (double)n_out * k, PK_TC_ROW);
+    const cudaError_t e = accurate    ? tc::launch_rowmajor<128, 3, tc::EPI_FWD, 4>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
+                          : (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
+                                        : tc::launch_rowmajor<128, 3, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<fwd>");
@@ -644,7 +716,7 @@ static int tc_dgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_
     tc::RowArgs g{};
     g.out_hi = dXh; g.out_lo = dXl; g.out_f32 = nullptr; g.bias = nullptr; g.aux_hi = Hh; g.aux_lo = Hl;
     g.M = n; g.Nout = k_in; g.K = n_out; g.ldo = k_in;
-    prof_begin(st, 2.0 * n * (double)n_out * k_in);
+    prof_begin(st, 2.0 * n * (double)n_out * k_in, PK_TC_ROW);
     const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_DGRAD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
                                       : tc::launch_rowmajor<128, 3, tc::EPI_DGRAD>(mAh, mAl, mBh, mBl, g, p->num_sms, st);
     prof_end(st);
@@ -653,7 +725,6 @@ static int tc_dgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_
     return B200_OK;
 }
 // dW [n_out, k_valid] += dY(h,l) [n, n_out]^T X(h,l) [n, k_cols]   (k_pad = 64 / 128 / 256 = tile width along k)
-#define TC_WGRAD_CHUNK 512
 static int tc_wgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_out, const float* Xh, const float* Xl, int k_cols,
                     int k_pad, int k_valid, float* dW, int n, cudaStream_t st) {
     TC_MAP(mYh, dYh, n, n_out, n_out, 32, false);
@@ -661,8 +732,15 @@ static int tc_wgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_
     TC_MAP(mXh, Xh, n, k_cols, k_cols, 32, false);
     TC_MAP(mXl, Xl, n, k_cols, k_cols, 32, false);
     tc::WgradArgs g{};
-    g.D = dW; g.M = n; g.Nout = n_out; g.Kin = k_valid; g.ldd = k_valid; g.chunk = TC_WGRAD_CHUNK;
-    prof_begin(st, 2.0 * n * (double)n_out * k_valid);
+    g.D = dW; g.M = n; g.Nout = n_out; g.Kin = k_valid; g.ldd = k_valid;
+    {
+        // one wave: the CTAs of an output tile split the rows evenly (multiples of the 32-row k-block)
+        const int tiles = ((n_out + tc::BM - 1) / tc::BM) * ((k_pad + (k_pad >= 256 ? 256 : k_pad) - 1) / (k_pad >= 256 ? 256 : k_pad));
+        const int per_tile = p->num_sms / tiles > 0 ? p->num_sms / tiles : 1;
+        const int rows = (n + per_tile - 1) / per_tile;
+        g.chunk = ((rows + 31) / 32) * 32;
+    }
+    prof_begin(st, 2.0 * n * (double)n_out * k_valid, PK_TC_WGRAD);
     cudaError_t e;
     if (k_pad == 256) e = tc::launch_wgrad<256, 2>(mYh, mYl, mXh, mXl, g, k_pad, st);
     else if (k_pad == 128) e = tc::launch_wgrad<128, 3>(mYh, mYl, mXh, mXl, g, k_pad, st);
@@ -690,17 +768,18 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
     return launch_status("k_weight_prep");
 }
 // full-batch forward passes over the M = T*N stored samples (pre-split operands, activations kept for the backward pass)
-// The ACTOR forward stays on the mma.sync kernel: log-prob sensitivity to mu is 1/sigma ~ 7.4 per unit (sigma = e^-2),
-// so mu wants the per-k-step round-to-nearest accumulation of gemm3x.cuh (measured 2.9e-7 of scale against fp64) rather
-// than the TMEM accumulator's truncating adds (2.3e-6).  Its epilogue also writes the tf32 pairs the tcgen05 backward reads.
+// The ACTOR forward uses the 4-accumulator variant with the exact expm1f: log-prob sensitivity to mu is 1/sigma ~ 7.4 per
+// unit (sigma = e^-2), so mu wants short accumulation chains (TMEM adds truncate) - see gemm_tc.cuh.
 static int actor_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
-    CU_TRY(linear_fwd(ws + w.Xaf, 48, 48, p->P(P_AW0), 47, p->P(P_AB0), ws + w.A1f, 256, M, 256, true, st, ws + w.A1h, ws + w.A1l));
-    CU_TRY(linear_fwd(ws + w.A1f, 256, 256, p->P(P_AW1), 256, p->P(P_AB1), ws + w.A2f, 128, M, 128, true, st, ws + w.A2h, ws + w.A2l));
-    CU_TRY(linear_fwd(ws + w.A2f, 128, 128, p->P(P_AW2), 128, p->P(P_AB2), ws + w.A3f, 128, M, 128, true, st, ws + w.A3h, ws + w.A3l));
-    CU_TRY(linear_fwd(ws + w.A3f, 128, 128, p->P(P_AW3), 128, p->P(P_AB3), ws + w.MU, 12, M, 12, false, st));
-    return B200_OK;
+    int rc;
+    if ((rc = tc_fwd(p, ws + w.Xah, ws + w.Xal, 48, 48, ws + w.Wa0h, ws + w.Wa0l, 64, p->P(P_AB0), ws + w.A1h, ws + w.A1l, nullptr, M, 256, st, true))) return rc;
+    if ((rc = tc_fwd(p, ws + w.A1h, ws + w.A1l, 256, 256, ws + w.Wa1h, ws + w.Wa1l, 256, p->P(P_AB1), ws + w.A2h, ws + w.A2l, nullptr, M, 128, st, true))) return rc;
+    if ((rc = tc_fwd(p, ws + w.A2h, ws + w.A2l, 128, 128, ws + w.Wa2h, ws + w.Wa2l, 128, p->P(P_AB2), ws + w.A3h, ws + w.A3l, nullptr, M, 128, st, true))) return rc;
+    k_actor_head<<<1184, 256, 0, st>>>(ws + w.A3h, ws + w.A3l, p->P(P_AW3), p->P(P_AB3), M, ws + w.MU);
+    g_launches += 1;
+    return launch_status("k_actor_head");
 }
 static int critic_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
@@ -720,8 +799,9 @@ static int actor_forward(const B200Ppo* p, const float* X, int ldx, int k_pad, i
     CU_TRY(linear_fwd(X, ldx, k_pad, p->P(P_AW0), 47, p->P(P_AB0), H1, 256, n, 256, true, st));
     CU_TRY(linear_fwd(H1, 256, 256, p->P(P_AW1), 256, p->P(P_AB1), H2, 128, n, 128, true, st));
     CU_TRY(linear_fwd(H2, 128, 128, p->P(P_AW2), 128, p->P(P_AB2), H3, 128, n, 128, true, st));
-    CU_TRY(linear_fwd(H3, 128, 128, p->P(P_AW3), 128, p->P(P_AB3), MU, 12, n, 12, false, st));
-    return B200_OK;
+    k_actor_head<<<(n * 32 + 255) / 256 < 1184 ? (n * 32 + 255) / 256 : 1184, 256, 0, st>>>(H3, nullptr, p->P(P_AW3), p->P(P_AB3), n, MU);
+    g_launches += 1;
+    return launch_status("k_actor_head");
 }
 // critic 61 -> 256 -> 256 -> 128 -> 1 (utils/model.py:9-17); Xc is the packed [n,64] cat(obs, priv)
 static int critic_forward(const B200Ppo* p, const float* Xc, int n, float* H1, float* H2, float* H3, float* V,
@@ -872,7 +952,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     float* ws = p->ws;
     const Workspace& w = p->w;
     const int M = p->cfg.horizon * p->cfg.num_envs;
-    float *MU = ws + w.MU, *DV = ws + w.DV, *DMU = ws + w.DMU, *GF = ws + w.GF;
+    float *MU = ws + w.MU, *DV = ws + w.DV, *DMU = ws + w.DMU;
     float *G1h = ws + w.G1h, *G1l = ws + w.G1l, *G2h = ws + w.G2h, *G2l = ws + w.G2l;
     int rc = actor_forward_tc(p, M, st);
     if (rc != B200_OK) return rc;
@@ -884,11 +964,9 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
     // ---- actor backward: the 12-wide head on the mma.sync path (fp32 operands), the hidden layers on tcgen05
-    CU_TRY(linear_wgrad(DMU, 12, 12, ws + w.A3f, 128, 128, 128, p->G(P_AW3), M, st));
-    CU_TRY(bias_grad(DMU, nullptr, 12, 12, M, p->G(P_AB3), st));
-    CU_TRY(linear_dgrad(DMU, 12, 12, p->P(P_AW3), 128, ws + w.A3f, 128, GF, 128, M, st));
-    k_split<<<(int)(((size_t)M * 128 + 255) / 256), 256, 0, st>>>(GF, (size_t)M * 128, G1h, G1l);
+    k_actor_head_bwd<<<(M + AH_ROWS - 1) / AH_ROWS, 128, 0, st>>>(ws + w.A3h, ws + w.A3l, p->P(P_AW3), DMU, M, G1h, G1l, p->G(P_AW3), p->G(P_AB3));
     g_launches += 1;
+    if ((rc = launch_status("k_actor_head_bwd")) != B200_OK) return rc;
     if ((rc = tc_wgrad(p, G1h, G1l, 128, ws + w.A2h, ws + w.A2l, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
     CU_TRY(bias_grad(G1h, G1l, 128, 128, M, p->G(P_AB2), st));
     if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wa2Th, ws + w.Wa2Tl, 128, ws + w.A2h, ws + w.A2l, G2h, G2l, M, st))) return rc;
@@ -938,25 +1016,32 @@ long long b200_launch_count(void) { return g_launches; }
 int b200_profile_gemm(int enable) {
     if (enable && !g_prof.ev) {
         g_prof.ev = new (std::nothrow) cudaEvent_t[2 * GemmProfile::kMax];
-        if (!g_prof.ev) return set_error(B200_ERR_ARG, "out of host memory");
+        g_prof.kind = new (std::nothrow) unsigned char[GemmProfile::kMax];
+        if (!g_prof.ev || !g_prof.kind) return set_error(B200_ERR_ARG, "out of host memory");
         for (int i = 0; i < 2 * GemmProfile::kMax; ++i) CUDA_TRY(cudaEventCreate(&g_prof.ev[i]));
     }
     g_prof.on = enable != 0;
     g_prof.used = 0;
-    g_prof.flops = 0.0;
+    for (int k = 0; k < PK_COUNT; ++k) g_prof.flops[k] = 0.0;
     return B200_OK;
 }
-int b200_profile_gemm_read(double* total_ms, double* total_flops, int* launches) {
-    double ms = 0.0;
+/* kind: 0 = k_gemm3x (mma.sync), 1 = k_tc_rowmajor (tcgen05 fwd / dgrad), 2 = k_tc_wgrad (tcgen05), -1 = all */
+int b200_profile_gemm_read(int kind, double* total_ms, double* total_flops, int* launches) {
+    double ms = 0.0, fl = 0.0;
+    int cnt = 0;
     for (int i = 0; i < g_prof.used; ++i) {
+        if (kind >= 0 && g_prof.kind[i] != kind) continue;
         CUDA_TRY(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
         float t = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
         ms += (double)t;
+        cnt += 1;
     }
+    for (int k = 0; k < PK_COUNT; ++k)
+        if (kind < 0 || kind == k) fl += g_prof.flops[k];
     if (total_ms) *total_ms = ms;
-    if (total_flops) *total_flops = g_prof.flops;
-    if (launches) *launches = g_prof.used;
+    if (total_flops) *total_flops = fl;
+    if (launches) *launches = cnt;
     return B200_OK;
 }
 

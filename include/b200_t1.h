@@ -273,7 +273,8 @@ int b200_ppo_apply(B200Ppo* p, void* stream);
  * (2 * rows * out * reduction, unpadded, counted once - not 3x for the split) and the number of launches. */
 long long b200_launch_count(void);
 int b200_profile_gemm(int enable);
-int b200_profile_gemm_read(double* total_ms, double* total_flops, int* launches);
+/* kind: 0 = k_gemm3x (mma.sync), 1 = k_tc_rowmajor (tcgen05 forward / dgrad), 2 = k_tc_wgrad (tcgen05), -1 = all */
+int b200_profile_gemm_read(int kind, double* total_ms, double* total_flops, int* launches);
 
 #ifdef __cplusplus
 }
