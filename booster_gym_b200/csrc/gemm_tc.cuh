@@ -38,6 +38,8 @@ struct RowArgs {
     const float* bias;   // EPI_FWD
     const float* aux_hi; // EPI_DGRAD: post-activation of the layer whose input gradient is produced
     const float* aux_lo;
+    float* colsum;       // nullable (EPI_DGRAD): colsum[c] += sum over rows of the stored output column c = the bias gradient of the
+                         // layer this dX feeds (utils/runner.py:163 autograd of nn.Linear.bias)
     int M, Nout, K;      // rows, output columns (multiple of 32), reduction length (TMA zero-fills beyond the tensor)
     int ldo;             // leading dimension of out_* and aux_* (floats)
 };
@@ -248,8 +250,9 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
                         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
                     }
                 }
-                if (row >= g.M || col0 >= g.Nout) continue;
-                const size_t base = (size_t)row * g.ldo + col0;
+                if (col0 >= g.Nout) continue;           // warp-uniform
+                const bool row_ok = row < g.M;          // per lane; invalid rows compute on row 0 and contribute / store nothing
+                const size_t base = (size_t)(row_ok ? row : 0) * g.ldo + col0;
                 float v[32];
                 if (EPI == EPI_FWD) {
 #pragma unroll
@@ -280,9 +283,29 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
                     float hi[8], lo[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) { hi[t] = tf32_rna(v[j + t]); lo[t] = tf32_rna(v[j + t] - hi[t]); }
-                    stg_v8(g.out_hi + base + j, hi);
-                    stg_v8(g.out_lo + base + j, lo);
-                    if (g.out_f32) stg_v8(g.out_f32 + base + j, v + j);
+                    if (row_ok) {
+                        stg_v8(g.out_hi + base + j, hi);
+                        stg_v8(g.out_lo + base + j, lo);
+                        if (g.out_f32) stg_v8(g.out_f32 + base + j, v + j);
+                    }
+                }
+                if (EPI == EPI_DGRAD && g.colsum) {
+                    if (!row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+                    }
+                    // column sums over this warp's 32 rows: butterfly reduce-scatter (31 shuffle+add), lane j ends with column j
+#pragma unroll
+                    for (int half = 16; half >= 1; half >>= 1) {
+                        const bool upper = (lane & half) != 0;
+#pragma unroll
+                        for (int j = 0; j < half; ++j) {
+                            const float send = upper ? v[j] : v[j + half];
+                            const float keep = upper ? v[j + half] : v[j];
+                            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+                        }
+                    }
+                    atomicAdd(g.colsum + col0 + lane, v[0]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");

@@ -60,12 +60,13 @@ static Workspace make_workspace(int T, int N) {
     const size_t M = (size_t)T * N, n = (size_t)N;
     size_t o = 0;
     auto take = [&](size_t cnt) { size_t r = o; o += (cnt + 255) & ~(size_t)255; return r; };  // 1 KiB aligned (TMA needs 16 B)
-    w.Xah = take(M * 48); w.Xal = take(M * 48); w.Xch = take(M * 64); w.Xcl = take(M * 64);
-    w.C1h = take(M * 256); w.C1l = take(M * 256); w.C2h = take(M * 256); w.C2l = take(M * 256); w.C3h = take(M * 128); w.C3l = take(M * 128);
+    const size_t Mc = M + n;  // the critic also evaluates the N post-rollout observations (last_values, utils/runner.py:133) in the same pass
+    w.Xah = take(M * 48); w.Xal = take(M * 48); w.Xch = take(Mc * 64); w.Xcl = take(Mc * 64);
+    w.C1h = take(Mc * 256); w.C1l = take(Mc * 256); w.C2h = take(Mc * 256); w.C2l = take(Mc * 256); w.C3h = take(Mc * 128); w.C3l = take(Mc * 128);
     w.A1h = take(M * 256); w.A1l = take(M * 256); w.A2h = take(M * 128); w.A2l = take(M * 128);
     w.A3h = take(M * 128); w.A3l = take(M * 128); w.A3f = take(M * 128);
     w.A1f = take(M * 256); w.A2f = take(M * 128); w.Xaf = take(M * 48);
-    w.V = take(M); w.MU = take(M * 12); w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
+    w.V = take(Mc); w.MU = take(M * 12); w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
     w.G1h = take(M * 256); w.G1l = take(M * 256); w.G2h = take(M * 256); w.G2l = take(M * 256); w.GF = take(M * 128);
     w.Wc0h = take(256 * 64); w.Wc0l = take(256 * 64); w.Wc1h = take(256 * 256); w.Wc1l = take(256 * 256);
     w.Wc2h = take(128 * 256); w.Wc2l = take(128 * 256); w.Wa0h = take(256 * 64); w.Wa0l = take(256 * 64);
@@ -130,11 +131,11 @@ __global__ void k_pack_inputs_split(const float* __restrict__ obs, const float* 
     split_tf32f(v, hi, lo);
     Xch[idx] = hi;
     Xcl[idx] = lo;
-    if (c < 48) {
+    if (Xah && c < 48) {
         split_tf32f(c < 47 ? v : 0.0f, hi, lo);
         Xah[r * 48 + c] = hi;
         Xal[r * 48 + c] = lo;
-        Xaf[r * 48 + c] = (c < 47) ? v : 0.0f;
+        if (Xaf) Xaf[r * 48 + c] = (c < 47) ? v : 0.0f;
     }
 }
 
@@ -186,21 +187,25 @@ __global__ void k_value_head(const float* __restrict__ H, const float* __restric
 __global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict__ Hh, const float* __restrict__ Hl,
                                                         const float* __restrict__ w, const float* __restrict__ dV, int n,
                                                         float* __restrict__ dHh, float* __restrict__ dHl, float* __restrict__ dw,
-                                                        float* __restrict__ db) {
+                                                        float* __restrict__ db, float* __restrict__ db_prev) {
     const int k = threadIdx.x;
     const int r0 = blockIdx.x * VH_ROWS, r1 = min(n, r0 + VH_ROWS);
     const float wk = w[k];
     double acc = 0.0, accb = 0.0;  // fp64 partial sums: these are 98k-term reductions judged at 1e-5 relative
+    float accp = 0.0f;             // column sum of dH = bias gradient of the layer below
     for (int r = r0; r < r1; ++r) {
         const float g = dV[r];
         const float h = Hh[(size_t)r * 128 + k] + Hl[(size_t)r * 128 + k];
         float hi, lo;
-        split_tf32f(g * wk * ((h > 0.0f) ? 1.0f : (h + 1.0f)), hi, lo);
+        const float dh = g * wk * ((h > 0.0f) ? 1.0f : (h + 1.0f));
+        split_tf32f(dh, hi, lo);
         dHh[(size_t)r * 128 + k] = hi;
         dHl[(size_t)r * 128 + k] = lo;
+        accp += dh;
         acc += (double)g * (double)h;
         accb += (double)g;
     }
+    atomicAdd(db_prev + k, accp);
     atomicAdd(dw + k, (float)acc);
     if (k == 0) atomicAdd(db, (float)accb);
 }
@@ -262,7 +267,8 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf
 #define AH_ROWS 128
 __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ Hl, const float* __restrict__ W,
                                                         const float* __restrict__ dMU, int n, float* __restrict__ dHh,
-                                                        float* __restrict__ dHl, float* __restrict__ dW, float* __restrict__ db) {
+                                                        float* __restrict__ dHl, float* __restrict__ dW, float* __restrict__ db,
+                                                        float* __restrict__ db_prev) {
     __shared__ float sd[AH_ROWS][12];
     const int k = threadIdx.x;
     const int r0 = blockIdx.x * AH_ROWS, r1 = min(n, r0 + AH_ROWS);
@@ -271,9 +277,10 @@ __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 12; ++j) w[j] = W[j * 128 + k];
     __syncthreads();
-    double acc[12];
+    float acc[12];   // 128-row partial sums in fp32, combined across the 768 blocks by fp32 atomics
 #pragma unroll
-    for (int j = 0; j < 12; ++j) acc[j] = 0.0;
+    for (int j = 0; j < 12; ++j) acc[j] = 0.0f;
+    float accp = 0.0f;
     for (int r = r0; r < r1; ++r) {
         const float h = Hf[(size_t)r * 128 + k] + Hl[(size_t)r * 128 + k];
         float g = 0.0f;
@@ -281,15 +288,18 @@ __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict_
         for (int j = 0; j < 12; ++j) {
             const float d = sd[r - r0][j];
             g = fmaf(d, w[j], g);
-            acc[j] += (double)d * (double)h;
+            acc[j] = fmaf(d, h, acc[j]);
         }
+        const float dh = g * ((h > 0.0f) ? 1.0f : (h + 1.0f));
         float hi, lo;
-        split_tf32f(g * ((h > 0.0f) ? 1.0f : (h + 1.0f)), hi, lo);
+        split_tf32f(dh, hi, lo);
         dHh[(size_t)r * 128 + k] = hi;
         dHl[(size_t)r * 128 + k] = lo;
+        accp += dh;
     }
+    atomicAdd(db_prev + k, accp);
 #pragma unroll
-    for (int j = 0; j < 12; ++j) atomicAdd(dW + j * 128 + k, (float)acc[j]);
+    for (int j = 0; j < 12; ++j) atomicAdd(dW + j * 128 + k, acc[j]);
     if (k < 12) {
         double s = 0.0;
         for (int r = r0; r < r1; ++r) s += (double)sd[r - r0][k];
@@ -694,7 +704,7 @@ static int tc_fwd(const B200Ppo* p, const float* Xh, const float* Xl, int k, int
     TC_MAP(mBh, Wh, n_out, k_pad, k_pad, bn, true);
     TC_MAP(mBl, Wl, n_out, k_pad, k_pad, bn, true);
     tc::RowArgs g{};
-    g.out_hi = Yh; g.out_lo = Yl; g.out_f32 = Yf; g.bias = b; g.aux_hi = nullptr; g.aux_lo = nullptr;
+    g.out_hi = Yh; g.out_lo = Yl; g.out_f32 = Yf; g.bias = b; g.aux_hi = nullptr; g.aux_lo = nullptr; g.colsum = nullptr;
     g.M = n; g.Nout = n_out; g.K = k_pad; g.ldo = n_out;
     prof_begin(st, 2.0 * n * (double)n_out * k, PK_TC_ROW);
     const cudaError_t e = accurate    ? tc::launch_rowmajor<128, 3, tc::EPI_FWD, 4>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
@@ -707,14 +717,14 @@ static int tc_fwd(const B200Ppo* p, const float* Xh, const float* Xl, int k, int
 }
 // dX(h,l) [n, k_in] = (dY(h,l) [n, n_out] WT(h,l) [k_in, n_out]^T) * ELU'(H(h,l) [n, k_in])
 static int tc_dgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_out, const float* WTh, const float* WTl, int k_in,
-                    const float* Hh, const float* Hl, float* dXh, float* dXl, int n, cudaStream_t st) {
+                    const float* Hh, const float* Hl, float* dXh, float* dXl, float* colsum, int n, cudaStream_t st) {
     const int bn = (k_in >= 256) ? 256 : 128;
     TC_MAP(mAh, dYh, n, n_out, n_out, tc::BM, true);
     TC_MAP(mAl, dYl, n, n_out, n_out, tc::BM, true);
     TC_MAP(mBh, WTh, k_in, n_out, n_out, bn, true);
     TC_MAP(mBl, WTl, k_in, n_out, n_out, bn, true);
     tc::RowArgs g{};
-    g.out_hi = dXh; g.out_lo = dXl; g.out_f32 = nullptr; g.bias = nullptr; g.aux_hi = Hh; g.aux_lo = Hl;
+    g.out_hi = dXh; g.out_lo = dXl; g.out_f32 = nullptr; g.bias = nullptr; g.aux_hi = Hh; g.aux_lo = Hl; g.colsum = colsum;
     g.M = n; g.Nout = k_in; g.K = n_out; g.ldo = k_in;
     prof_begin(st, 2.0 * n * (double)n_out * k_in, PK_TC_ROW);
     const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_DGRAD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
@@ -935,11 +945,11 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     CUDA_TRY(cudaMemsetAsync(p->dstats, 0, DS_COUNT * sizeof(double), st));
     int rc = weight_prep(p, st);  // the parameters changed in the previous epoch's b200_ppo_apply
     if (rc != B200_OK) return rc;
-    if ((rc = critic_forward_tc(p, M, st)) != B200_OK) return rc;
-    k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(last_obs, last_priv, N, nullptr, ws + p->w.LXc);
-    rc = critic_forward(p, ws + p->w.LXc, N, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, ws + p->w.LV, st);
-    if (rc != B200_OK) return rc;
-    k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.LV, (float)p->cfg.gamma,
+    // last_values = critic(post-rollout obs): appended as rows [M, M+N) of the critic batch, evaluated in the same GEMMs
+    k_pack_inputs_split<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(last_obs, last_priv, N, nullptr, nullptr,
+                                                                              ws + p->w.Xch + (size_t)M * 64, ws + p->w.Xcl + (size_t)M * 64, nullptr);
+    if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
+    k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
     g_launches += 3;  // memset, k_pack_inputs, k_gae
     return launch_status("k_gae");
@@ -964,30 +974,26 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
     // ---- actor backward: the 12-wide head on the mma.sync path (fp32 operands), the hidden layers on tcgen05
-    k_actor_head_bwd<<<(M + AH_ROWS - 1) / AH_ROWS, 128, 0, st>>>(ws + w.A3h, ws + w.A3l, p->P(P_AW3), DMU, M, G1h, G1l, p->G(P_AW3), p->G(P_AB3));
+    k_actor_head_bwd<<<(M + AH_ROWS - 1) / AH_ROWS, 128, 0, st>>>(ws + w.A3h, ws + w.A3l, p->P(P_AW3), DMU, M, G1h, G1l, p->G(P_AW3), p->G(P_AB3),
+                                                                 p->G(P_AB2));
     g_launches += 1;
     if ((rc = launch_status("k_actor_head_bwd")) != B200_OK) return rc;
+    // (each bias gradient = column sum of the layer's output gradient, accumulated by the kernel that produces it)
     if ((rc = tc_wgrad(p, G1h, G1l, 128, ws + w.A2h, ws + w.A2l, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
-    CU_TRY(bias_grad(G1h, G1l, 128, 128, M, p->G(P_AB2), st));
-    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wa2Th, ws + w.Wa2Tl, 128, ws + w.A2h, ws + w.A2l, G2h, G2l, M, st))) return rc;
+    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wa2Th, ws + w.Wa2Tl, 128, ws + w.A2h, ws + w.A2l, G2h, G2l, p->G(P_AB1), M, st))) return rc;
     if ((rc = tc_wgrad(p, G2h, G2l, 128, ws + w.A1h, ws + w.A1l, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
-    CU_TRY(bias_grad(G2h, G2l, 128, 128, M, p->G(P_AB1), st));
-    if ((rc = tc_dgrad(p, G2h, G2l, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1h, ws + w.A1l, G1h, G1l, M, st))) return rc;
+    if ((rc = tc_dgrad(p, G2h, G2l, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1h, ws + w.A1l, G1h, G1l, p->G(P_AB0), M, st))) return rc;
     if ((rc = tc_wgrad(p, G1h, G1l, 256, ws + w.Xah, ws + w.Xal, 48, 64, 47, p->G(P_AW0), M, st))) return rc;
-    CU_TRY(bias_grad(G1h, G1l, 256, 256, M, p->G(P_AB0), st));
     // ---- critic backward
     k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(ws + w.C3h, ws + w.C3l, p->P(P_CW3), DV, M, G1h, G1l, p->G(P_CW3),
-                                                                  p->G(P_CB3));
+                                                                  p->G(P_CB3), p->G(P_CB2));
     g_launches += 1;
     if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
     if ((rc = tc_wgrad(p, G1h, G1l, 128, ws + w.C2h, ws + w.C2l, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
-    CU_TRY(bias_grad(G1h, G1l, 128, 128, M, p->G(P_CB2), st));
-    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wc2Th, ws + w.Wc2Tl, 256, ws + w.C2h, ws + w.C2l, G2h, G2l, M, st))) return rc;
+    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wc2Th, ws + w.Wc2Tl, 256, ws + w.C2h, ws + w.C2l, G2h, G2l, p->G(P_CB1), M, st))) return rc;
     if ((rc = tc_wgrad(p, G2h, G2l, 256, ws + w.C1h, ws + w.C1l, 256, 256, 256, p->G(P_CW1), M, st))) return rc;
-    CU_TRY(bias_grad(G2h, G2l, 256, 256, M, p->G(P_CB1), st));
-    if ((rc = tc_dgrad(p, G2h, G2l, 256, ws + w.Wc1Th, ws + w.Wc1Tl, 256, ws + w.C1h, ws + w.C1l, G1h, G1l, M, st))) return rc;
+    if ((rc = tc_dgrad(p, G2h, G2l, 256, ws + w.Wc1Th, ws + w.Wc1Tl, 256, ws + w.C1h, ws + w.C1l, G1h, G1l, p->G(P_CB0), M, st))) return rc;
     if ((rc = tc_wgrad(p, G1h, G1l, 256, ws + w.Xch, ws + w.Xcl, 64, 64, 61, p->G(P_CW0), M, st))) return rc;
-    CU_TRY(bias_grad(G1h, G1l, 256, 256, M, p->G(P_CB0), st));
     return B200_OK;
 }
 
@@ -1052,7 +1058,7 @@ float* b200_ppo_buffer(B200Ppo* p, int which) {
         case 1: return p->ws + p->w.ADV;
         case 2: return p->ws + p->w.RET;
         case 3: return p->ws + p->w.MU;
-        case 4: return p->ws + p->w.LV;
+        case 4: return p->ws + p->w.V + (size_t)p->cfg.horizon * p->cfg.num_envs;
         case 5: return p->ws + p->w.DV;
         case 6: return p->ws + p->w.DMU;
     }
