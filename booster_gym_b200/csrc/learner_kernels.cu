@@ -340,6 +340,158 @@ __global__ void k_sample(const float* __restrict__ mu, const float* __restrict__
 
 __global__ void k_bump(unsigned long long* ctr) { *ctr += 1ull; }
 
+// ---- K4: fused rollout policy (utils/runner.py:109-111; utils/model.py:18-32) -----------------------------------------
+// One launch per env step: act = actor(obs) + exp(logstd) * eps for PF_ROWS observations per CTA.  All four layers run
+// inside the CTA with the activations resident in shared memory (47 -> 256 -> 128 -> 128 -> 12); the weights stream
+// from L2 in [N][32] k-tiles.  Hidden layers: mma.sync m16n8k8 3xTF32 with a fresh accumulator per k-step (round-to-
+// nearest adds, same arithmetic as gemm3x.cuh); head + sampling: one warp per row, fp32 FMAs + in-kernel Philox.
+#define PF_ROWS 32
+#define PF_THREADS 256
+#define PF_WT_LD 36   // k-tile row stride (floats): 36 % 32 = 4 -> conflict-free fragment reads
+struct PolicyFusedArgs {
+    const float* obs;      // [n, 47]
+    const float *W0, *b0, *W1, *b1, *W2, *b2, *W3, *b3, *logstd;
+    const float* eps_in;   // nullable [n, 12]
+    const unsigned long long* ctr;  // nullable: device-side RNG step
+    float* actions;        // [n, 12]
+    float* mu_out;         // nullable [n, 12]
+    uint64_t seed, step;
+    int n, env_base, deterministic;
+};
+
+template <int K, int KP, int N, int LDA, int LDO>
+__device__ __forceinline__ void pf_layer(const float* __restrict__ W, const float* __restrict__ bias, const float* As, float* Os,
+                                         float* Ws /* [2][N][PF_WT_LD] */) {
+    // As: [32][LDA] fp32 (K valid columns, zero padded to KP); Os: [32][LDO]; W: [N][K] row-major in global memory
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    constexpr int NW = N / 8;        // columns per warp
+    constexpr int NT = NW / 8;       // n8 tiles per warp
+    constexpr int KT = KP / 32;      // k-tiles
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.0f;
+    auto load_tile = [&](int kt, float* dst) {
+        // [N][32] floats of W starting at column kt*32 (guarded against K), coalesced along k
+        for (int idx = tid; idx < N * 32; idx += PF_THREADS) {
+            const int nrow = idx >> 5, kk = idx & 31;
+            const int kcol = kt * 32 + kk;
+            dst[nrow * PF_WT_LD + kk] = (kcol < K) ? __ldg(W + (size_t)nrow * K + kcol) : 0.0f;
+        }
+    };
+    load_tile(0, Ws);
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+        const float* Wt = Ws + (kt & 1) * N * PF_WT_LD;
+        if (kt + 1 < KT) load_tile(kt + 1, Ws + ((kt + 1) & 1) * N * PF_WT_LD);
+#pragma unroll
+        for (int kb = 0; kb < 32; kb += 8) {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                const int rb = mi * 16;
+                const int kc = kt * 32 + kb;
+                split_tf32(As[(rb + gq) * LDA + kc + tq], ah[mi][0], al[mi][0]);
+                split_tf32(As[(rb + gq + 8) * LDA + kc + tq], ah[mi][1], al[mi][1]);
+                split_tf32(As[(rb + gq) * LDA + kc + tq + 4], ah[mi][2], al[mi][2]);
+                split_tf32(As[(rb + gq + 8) * LDA + kc + tq + 4], ah[mi][3], al[mi][3]);
+            }
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) {
+                const int cb = warp * NW + ni * 8;
+                uint32_t bh[2], bl[2];
+                split_tf32(Wt[(cb + gq) * PF_WT_LD + kb + tq], bh[0], bl[0]);
+                split_tf32(Wt[(cb + gq) * PF_WT_LD + kb + tq + 4], bh[1], bl[1]);
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_tf32(t, al[mi], bh);
+                    mma_tf32(t, ah[mi], bl);
+                    mma_tf32(t, ah[mi], bh);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[mi][ni][q] += t[q];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // bias + ELU -> next activation buffer
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            const int c = warp * NW + ni * 8 + 2 * tq;
+            const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = mi * 16 + gq + 8 * half;
+                float v0 = acc[mi][ni][2 * half] + b0, v1 = acc[mi][ni][2 * half + 1] + b1;
+                v0 = (v0 > 0.f) ? v0 : expm1f(v0);
+                v1 = (v1 > 0.f) ? v1 : expm1f(v1);
+                Os[r * LDO + c] = v0;
+                Os[r * LDO + c + 1] = v1;
+            }
+        }
+    __syncthreads();
+}
+
+#define PF_LD0 68    // 64 + 4
+#define PF_LD1 260   // 256 + 4
+#define PF_LD2 132   // 128 + 4
+#define PF_SMEM_FLOATS (PF_ROWS * (PF_LD0 + PF_LD1 + PF_LD2 + PF_LD2) + 2 * 256 * PF_WT_LD + 12 * 128)
+__global__ void __launch_bounds__(PF_THREADS) k_policy_fused(const PolicyFusedArgs a) {
+    extern __shared__ __align__(16) float pf_smem[];
+    float* X0 = pf_smem;
+    float* H1 = X0 + PF_ROWS * PF_LD0;
+    float* H2 = H1 + PF_ROWS * PF_LD1;
+    float* H3 = H2 + PF_ROWS * PF_LD2;
+    float* Ws = H3 + PF_ROWS * PF_LD2;
+    float* W3s = Ws + 2 * 256 * PF_WT_LD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * PF_ROWS;
+    for (int idx = tid; idx < PF_ROWS * 64; idx += PF_THREADS) {
+        const int r = idx >> 6, c = idx & 63;
+        const int row = row0 + r;
+        X0[r * PF_LD0 + c] = (c < 47 && row < a.n) ? a.obs[(size_t)row * 47 + c] : 0.0f;
+    }
+    for (int idx = tid; idx < 12 * 128; idx += PF_THREADS) W3s[idx] = a.W3[idx];
+    __syncthreads();
+    pf_layer<47, 64, 256, PF_LD0, PF_LD1>(a.W0, a.b0, X0, H1, Ws);
+    pf_layer<256, 256, 128, PF_LD1, PF_LD2>(a.W1, a.b1, H1, H2, Ws);
+    pf_layer<128, 128, 128, PF_LD2, PF_LD2>(a.W2, a.b2, H2, H3, Ws);
+    // head + sampling: warp w handles rows w, w + 8, ...
+    const uint64_t step = a.ctr ? (uint64_t)(*a.ctr) : a.step;
+    for (int r = warp; r < PF_ROWS; r += PF_THREADS / 32) {
+        const int row = row0 + r;
+        if (row >= a.n) continue;   // warp-uniform
+        const float4 h = *reinterpret_cast<const float4*>(H3 + r * PF_LD2 + 4 * lane);
+        float out = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(W3s + j * 128 + 4 * lane);
+            float s = h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == j) out = s + a.b3[j];
+        }
+        if (lane < 12) {
+            float act = out;
+            if (!a.deterministic) {
+                float eps;
+                if (a.eps_in) eps = a.eps_in[(size_t)row * 12 + lane];
+                else eps = rand4(rng_words(a.seed, (uint32_t)(a.env_base + row), step, RP_POLICY, lane >> 2)).n[lane & 3];
+                act = __fadd_rn(out, __fmul_rn(expf(a.logstd[lane]), eps));
+            }
+            a.actions[(size_t)row * 12 + lane] = act;
+            if (a.mu_out) a.mu_out[(size_t)row * 12 + lane] = out;
+        }
+    }
+}
+
 #define LOG_SQRT_2PI 0.91893853320467274178f
 
 // Normal(mu, exp(logstd)).log_prob(a).sum(-1)  (torch.distributions.Normal.log_prob, summed left to right)
@@ -883,17 +1035,25 @@ int b200_ppo_destroy(B200Ppo* p) {
 int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* mu_out, const float* eps_in,
                     uint64_t seed, uint64_t step, int deterministic, void* stream) {
     NEED_PPO(p);
-    if (!obs || !actions || n <= 0 || n > p->cfg.num_envs) return set_error(B200_ERR_ARG, "b200_policy_act: bad argument");
+    if (!obs || !actions || n <= 0) return set_error(B200_ERR_ARG, "b200_policy_act: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    float* ws = p->ws;
-    const int rc = actor_forward(p, obs, 47, 47, n, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, ws + p->w.LMU, st);
-    if (rc != B200_OK) return rc;
+    static bool configured = false;
+    constexpr int SMEM = PF_SMEM_FLOATS * (int)sizeof(float);
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_policy_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
     const bool auto_step = (step == B200_STEP_AUTO);
-    k_sample<<<(n + 127) / 128, 128, 0, st>>>(ws + p->w.LMU, p->P(P_LOGSTD), eps_in, n, seed, step,
-                                              auto_step ? p->act_ctr : nullptr, p->cfg.env_base, deterministic, actions, mu_out);
+    PolicyFusedArgs a{};
+    a.obs = obs;
+    a.W0 = p->P(P_AW0); a.b0 = p->P(P_AB0); a.W1 = p->P(P_AW1); a.b1 = p->P(P_AB1); a.W2 = p->P(P_AW2); a.b2 = p->P(P_AB2);
+    a.W3 = p->P(P_AW3); a.b3 = p->P(P_AB3); a.logstd = p->P(P_LOGSTD);
+    a.eps_in = eps_in; a.ctr = auto_step ? p->act_ctr : nullptr; a.actions = actions; a.mu_out = mu_out;
+    a.seed = seed; a.step = step; a.n = n; a.env_base = p->cfg.env_base; a.deterministic = deterministic;
+    k_policy_fused<<<(n + PF_ROWS - 1) / PF_ROWS, PF_THREADS, SMEM, st>>>(a);
     if (auto_step) k_bump<<<1, 1, 0, st>>>(p->act_ctr);
     g_launches += auto_step ? 2 : 1;
-    return launch_status("k_sample");
+    return launch_status("k_policy_fused");
 }
 
 int b200_critic_value(B200Ppo* p, const float* obs, const float* priv, int n, float* values, void* stream) {
