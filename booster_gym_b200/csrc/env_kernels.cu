@@ -21,7 +21,7 @@ __global__ void k_advance(long long* ctr, long long common_step, int bump_common
     ctr[2 + ((s + 1) & 1)] = 0;
 }
 
-#define POST_BLOCK 128
+#define POST_BLOCK 64
 #define POST_ROW (B200_NOBS + B200_NPRIV)
 
 // coalesced write-out of the [N,47] / [N,14] row-major API tensors through shared memory

@@ -6,13 +6,14 @@
 // tcgen05.mma per k-step into the same TMEM accumulator (3xTF32; SASS: UTCHMMA, UTMALDG, LDTM).
 //
 // Two kernels:
-//   k_tc_rowmajor<BN, STAGES, EPI>   C[M, Nout] = epi(A[M, K] * B[Nout, K]^T)     both operands K-major (reduction contiguous)
-//        persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer (single elected thread), 2..5 =
-//        epilogue; TMEM accumulator double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop of
-//        tile i+1.  EPI_FWD: +bias, ELU, split, store hi/lo (+ optional fp32 copy).  EPI_DGRAD: * ELU'(h) with h = hi+lo
-//        of the layer's stored post-activation, split, store hi/lo.  Stores are staged through shared memory so that
-//        every global store instruction writes one full 128-byte row segment.
-//   k_tc_wgrad<BN, STAGES>           dW[Nout, Kin] += dY[m, Nout]^T X[m, Kin] over a chunk of rows m (split-M, atomics)
+//   k_tc_rowmajor<BN, STAGES, EPI, NACC>   C[M, Nout] = epi(A[M, K] * B[Nout, K]^T)   both operands K-major
+//        persistent CTAs (one per SM, 576 threads), warp roles: 0 = TMA producer, 1 = MMA issuer (single elected thread),
+//        2..17 = epilogue.  NACC TMEM accumulators per tile (k-blocks rotate over them and the epilogue adds them with
+//        round-to-nearest FADDs: TMEM accumulation truncates), double-buffered across tiles when 2*BN*NACC <= 512 columns
+//        so the epilogue of tile i overlaps the main loop of tile i+1.  EPI_FWD: +bias, ELU, split, store hi/lo (+ optional
+//        fp32 copy).  EPI_DGRAD: * ELU'(h) with h = hi+lo of the layer's stored post-activation, split, store hi/lo, and
+//        the bias gradient (column sums) of the layer below.  Global IO is 256-bit per thread (one 32-byte sector).
+//   k_tc_wgrad<BN, STAGES>           dW[Nout, Kin] += dY[m, Nout]^T X[m, Kin] over a contiguous range of rows m per CTA
 //        the reduction index is the ROW index of both operands -> MN-major operands; for 32-bit elements the only legal
 //        MN-major shared-memory layout is SWIZZLE_128B_BASE32B (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
 #pragma once

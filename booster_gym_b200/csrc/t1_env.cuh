@@ -281,65 +281,99 @@ B200_HD void env_refresh_feet(const EnvView& v, int e, const Model& m, const Ter
     }
 }
 
-// reward term k of envs/t1.py:606-730 (unscaled); `h_base` = terrain height under the base
-B200_HD float reward_term(int id, const EnvView& v, int e, const B200T1Config& c, float h_base) {
-    float* f = v.f;
-    int32_t* is = v.is;
+// Everything the 26 reward functions read, loaded ONCE into registers after the kick / push / termination bookkeeping:
+// the loads are independent and issue back to back (the pass is latency-bound, not bandwidth-bound), and the stores the
+// reward loop performs cannot force reloads through pointer aliasing.
+struct RewardSnap {
+    float rs[13];   // root_states
+    float dof_pos[12], dof_vel[12], torques[12], actions[12], last_actions[12], last_dof_vel[12];
+    float last_root_vel[6], feet_pos[6], last_feet_pos[6];
+    float commands[3], filt_lin[3], filt_ang[3], base_ang[3], pg[3];
+    float feet_roll[2], feet_yaw[2];
+    int contact[2];
+    float gait_process, gait_frequency;
+    int ep_len;
+};
+B200_HD void reward_snapshot(const EnvView& v, int e, RewardSnap& s) {
+    const float* f = v.f;
+    const int32_t* is = v.is;
     const int n = v.n;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) s.rs[i] = FS(F_root_states + i);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        s.dof_pos[j] = FS(F_dof_pos + j); s.dof_vel[j] = FS(F_dof_vel + j); s.torques[j] = FS(F_torques + j);
+        s.actions[j] = FS(F_actions + j); s.last_actions[j] = FS(F_last_actions + j); s.last_dof_vel[j] = FS(F_last_dof_vel + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        s.last_root_vel[j] = FS(F_last_root_vel + j); s.feet_pos[j] = FS(F_feet_pos + j); s.last_feet_pos[j] = FS(F_last_feet_pos + j);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        s.commands[r] = FS(F_commands + r); s.filt_lin[r] = FS(F_filtered_lin_vel + r); s.filt_ang[r] = FS(F_filtered_ang_vel + r);
+        s.base_ang[r] = FS(F_base_ang_vel + r); s.pg[r] = FS(F_projected_gravity + r);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { s.feet_roll[k] = FS(F_feet_roll + k); s.feet_yaw[k] = FS(F_feet_yaw + k); s.contact[k] = IS(I_feet_contact + k); }
+    s.gait_process = FS(F_gait_process);
+    s.gait_frequency = FS(F_gait_frequency);
+    s.ep_len = IS(I_episode_length_buf);
+}
+
+// reward term k of envs/t1.py:606-730 (unscaled); `h_base` = terrain height under the base
+B200_HD float reward_term(int id, const RewardSnap& s, const B200T1Config& c, float h_base) {
     switch (id) {
         case B200_REW_SURVIVAL: return 1.0f;
-        case B200_REW_TRACK_LIN_X: { const float d = FS(F_commands + 0) - FS(F_filtered_lin_vel + 0); return expf(-(d * d) / c.tracking_sigma); }
-        case B200_REW_TRACK_LIN_Y: { const float d = FS(F_commands + 1) - FS(F_filtered_lin_vel + 1); return expf(-(d * d) / c.tracking_sigma); }
-        case B200_REW_TRACK_ANG: { const float d = FS(F_commands + 2) - FS(F_filtered_ang_vel + 2); return expf(-(d * d) / c.tracking_sigma); }
-        case B200_REW_BASE_HEIGHT: { const float bh = FS(F_root_states + 2) - h_base; const float d = bh - c.base_height_target; return d * d; }
-        case B200_REW_ORIENTATION: { const float a = FS(F_projected_gravity + 0), b = FS(F_projected_gravity + 1); return a * a + b * b; }
-        case B200_REW_TORQUES: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_torques + j); s += t * t; } return s; }
-        case B200_REW_TORQUE_TIREDNESS: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_torques + j) / c.torque_limits[j]; s += fminf(t * t, 1.0f); } return s; }
-        case B200_REW_POWER: { float s = 0; for (int j = 0; j < 12; ++j) s += fmaxf(FS(F_torques + j) * FS(F_dof_vel + j), 0.0f); return s; }
-        case B200_REW_LIN_VEL_Z: { const float a = FS(F_filtered_lin_vel + 2); return a * a; }
-        case B200_REW_ANG_VEL_XY: { const float a = FS(F_base_ang_vel + 0), b = FS(F_base_ang_vel + 1); return a * a + b * b; }
-        case B200_REW_DOF_VEL: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_dof_vel + j); s += t * t; } return s; }
-        case B200_REW_DOF_ACC: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = (FS(F_last_dof_vel + j) - FS(F_dof_vel + j)) / c.env_dt; s += t * t; } return s; }
-        case B200_REW_ROOT_ACC: { float s = 0; for (int j = 0; j < 6; ++j) { const float t = (FS(F_last_root_vel + j) - FS(F_root_states + 7 + j)) / c.env_dt; s += t * t; } return s; }
-        case B200_REW_ACTION_RATE: { float s = 0; for (int j = 0; j < 12; ++j) { const float t = FS(F_last_actions + j) - FS(F_actions + j); s += t * t; } return s; }
-        case B200_REW_DOF_POS_LIMITS: { float s = 0; for (int j = 0; j < 12; ++j) { const float q = FS(F_dof_pos + j); s += ((q < c.dof_pos_soft_lower[j]) || (q > c.dof_pos_soft_upper[j])) ? 1.0f : 0.0f; } return s; }
-        case B200_REW_DOF_VEL_LIMITS: { float s = 0; for (int j = 0; j < 12; ++j) s += fminf(fmaxf(fabsf(FS(F_dof_vel + j)) - c.dof_vel_limits[j] * c.soft_dof_vel_limit, 0.0f), 1.0f); return s; }
-        case B200_REW_TORQUE_LIMITS: { float s = 0; for (int j = 0; j < 12; ++j) s += fmaxf(fabsf(FS(F_torques + j)) - c.torque_limits[j] * c.soft_torque_limit, 0.0f); return s; }
+        case B200_REW_TRACK_LIN_X: { const float d = s.commands[0] - s.filt_lin[0]; return expf(-(d * d) / c.tracking_sigma); }
+        case B200_REW_TRACK_LIN_Y: { const float d = s.commands[1] - s.filt_lin[1]; return expf(-(d * d) / c.tracking_sigma); }
+        case B200_REW_TRACK_ANG: { const float d = s.commands[2] - s.filt_ang[2]; return expf(-(d * d) / c.tracking_sigma); }
+        case B200_REW_BASE_HEIGHT: { const float bh = s.rs[2] - h_base; const float d = bh - c.base_height_target; return d * d; }
+        case B200_REW_ORIENTATION: return s.pg[0] * s.pg[0] + s.pg[1] * s.pg[1];
+        case B200_REW_TORQUES: { float a = 0; for (int j = 0; j < 12; ++j) a += s.torques[j] * s.torques[j]; return a; }
+        case B200_REW_TORQUE_TIREDNESS: { float a = 0; for (int j = 0; j < 12; ++j) { const float t = s.torques[j] / c.torque_limits[j]; a += fminf(t * t, 1.0f); } return a; }
+        case B200_REW_POWER: { float a = 0; for (int j = 0; j < 12; ++j) a += fmaxf(s.torques[j] * s.dof_vel[j], 0.0f); return a; }
+        case B200_REW_LIN_VEL_Z: return s.filt_lin[2] * s.filt_lin[2];
+        case B200_REW_ANG_VEL_XY: return s.base_ang[0] * s.base_ang[0] + s.base_ang[1] * s.base_ang[1];
+        case B200_REW_DOF_VEL: { float a = 0; for (int j = 0; j < 12; ++j) a += s.dof_vel[j] * s.dof_vel[j]; return a; }
+        case B200_REW_DOF_ACC: { float a = 0; for (int j = 0; j < 12; ++j) { const float t = (s.last_dof_vel[j] - s.dof_vel[j]) / c.env_dt; a += t * t; } return a; }
+        case B200_REW_ROOT_ACC: { float a = 0; for (int j = 0; j < 6; ++j) { const float t = (s.last_root_vel[j] - s.rs[7 + j]) / c.env_dt; a += t * t; } return a; }
+        case B200_REW_ACTION_RATE: { float a = 0; for (int j = 0; j < 12; ++j) { const float t = s.last_actions[j] - s.actions[j]; a += t * t; } return a; }
+        case B200_REW_DOF_POS_LIMITS: { float a = 0; for (int j = 0; j < 12; ++j) a += ((s.dof_pos[j] < c.dof_pos_soft_lower[j]) || (s.dof_pos[j] > c.dof_pos_soft_upper[j])) ? 1.0f : 0.0f; return a; }
+        case B200_REW_DOF_VEL_LIMITS: { float a = 0; for (int j = 0; j < 12; ++j) a += fminf(fmaxf(fabsf(s.dof_vel[j]) - c.dof_vel_limits[j] * c.soft_dof_vel_limit, 0.0f), 1.0f); return a; }
+        case B200_REW_TORQUE_LIMITS: { float a = 0; for (int j = 0; j < 12; ++j) a += fmaxf(fabsf(s.torques[j]) - c.torque_limits[j] * c.soft_torque_limit, 0.0f); return a; }
         case B200_REW_COLLISION: return 0.0f;  // only the feet carry contact points in this build; feet are not penalised bodies
         case B200_REW_FEET_SLIP: {
-            float s = 0;
+            float a = 0;
             for (int k = 0; k < 2; ++k) {
                 float q = 0;
-                for (int r = 0; r < 3; ++r) { const float t = (FS(F_last_feet_pos + 3 * k + r) - FS(F_feet_pos + 3 * k + r)) / c.env_dt; q += t * t; }
-                s += q * (IS(I_feet_contact + k) ? 1.0f : 0.0f);
+                for (int r = 0; r < 3; ++r) { const float t = (s.last_feet_pos[3 * k + r] - s.feet_pos[3 * k + r]) / c.env_dt; q += t * t; }
+                a += q * (s.contact[k] ? 1.0f : 0.0f);
             }
-            return s * ((IS(I_episode_length_buf) > 1) ? 1.0f : 0.0f);
+            return a * ((s.ep_len > 1) ? 1.0f : 0.0f);
         }
-        case B200_REW_FEET_VEL_Z: { float s = 0; for (int k = 0; k < 2; ++k) { const float t = (FS(F_last_feet_pos + 3 * k + 2) - FS(F_feet_pos + 3 * k + 2)) / c.env_dt; s += t * t; } return s; }
-        case B200_REW_FEET_YAW_DIFF: { const float d = wrap_pi(FS(F_feet_yaw + 1) - FS(F_feet_yaw + 0)); return d * d; }
+        case B200_REW_FEET_VEL_Z: { float a = 0; for (int k = 0; k < 2; ++k) { const float t = (s.last_feet_pos[3 * k + 2] - s.feet_pos[3 * k + 2]) / c.env_dt; a += t * t; } return a; }
+        case B200_REW_FEET_YAW_DIFF: { const float d = wrap_pi(s.feet_yaw[1] - s.feet_yaw[0]); return d * d; }
         case B200_REW_FEET_YAW_MEAN: {
-            const float y0 = FS(F_feet_yaw + 0), y1 = FS(F_feet_yaw + 1);
+            const float y0 = s.feet_yaw[0], y1 = s.feet_yaw[1];
             const float mean = (y0 + y1) / 2.0f + B200_PI_F * ((fabsf(y1 - y0) > B200_PI_F) ? 1.0f : 0.0f);
-            float q[4] = {FS(F_root_states + 3), FS(F_root_states + 4), FS(F_root_states + 5), FS(F_root_states + 6)};
             float r, p, y;
-            get_euler_xyz(q, r, p, y);
+            get_euler_xyz(s.rs + 3, r, p, y);
             const float d = wrap_pi(y - mean);
             return d * d;
         }
-        case B200_REW_FEET_ROLL: { const float a = FS(F_feet_roll + 0), b = FS(F_feet_roll + 1); return a * a + b * b; }
+        case B200_REW_FEET_ROLL: return s.feet_roll[0] * s.feet_roll[0] + s.feet_roll[1] * s.feet_roll[1];
         case B200_REW_FEET_DISTANCE: {
-            float q[4] = {FS(F_root_states + 3), FS(F_root_states + 4), FS(F_root_states + 5), FS(F_root_states + 6)};
             float r, p, y;
-            get_euler_xyz(q, r, p, y);
-            const float dist = fabsf(cosf(y) * (FS(F_feet_pos + 3 + 1) - FS(F_feet_pos + 1)) - sinf(y) * (FS(F_feet_pos + 3 + 0) - FS(F_feet_pos + 0)));
+            get_euler_xyz(s.rs + 3, r, p, y);
+            const float dist = fabsf(cosf(y) * (s.feet_pos[3 + 1] - s.feet_pos[1]) - sinf(y) * (s.feet_pos[3 + 0] - s.feet_pos[0]));
             return fminf(fmaxf(c.feet_distance_ref - dist, 0.0f), 0.1f);
         }
         case B200_REW_FEET_SWING: {
-            const float gp = FS(F_gait_process);
-            const bool moving = FS(F_gait_frequency) > 1.0e-8f;
-            const bool ls = (fabsf(gp - 0.25f) < 0.5f * c.swing_period) && moving;
-            const bool rs = (fabsf(gp - 0.75f) < 0.5f * c.swing_period) && moving;
-            return ((ls && !IS(I_feet_contact + 0)) ? 1.0f : 0.0f) + ((rs && !IS(I_feet_contact + 1)) ? 1.0f : 0.0f);
+            const bool moving = s.gait_frequency > 1.0e-8f;
+            const bool ls = (fabsf(s.gait_process - 0.25f) < 0.5f * c.swing_period) && moving;
+            const bool rsw = (fabsf(s.gait_process - 0.75f) < 0.5f * c.swing_period) && moving;
+            return ((ls && !s.contact[0]) ? 1.0f : 0.0f) + ((rsw && !s.contact[1]) ? 1.0f : 0.0f);
         }
     }
     return 0.0f;
@@ -587,8 +621,10 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     IS(I_time_out_buf) = time_out ? 1 : 0;
     // _compute_reward :560-572
     float rew = 0.0f;
+    RewardSnap snap;
+    reward_snapshot(v, e, snap);
     for (int k = 0; k < c.n_rew; ++k) {
-        float r = reward_term(c.rew_id[k], v, e, c, h_base) * c.rew_scale[k];
+        float r = reward_term(c.rew_id[k], snap, c, h_base) * c.rew_scale[k];
         if (!finite) r = 0.0f;
         rew += r;
         if (rew_terms) rew_terms[(size_t)k * (size_t)n + (size_t)e] = r;
