@@ -64,6 +64,7 @@ def iteration_sample(num_envs=4096, horizon=24, epochs=20, phys_envs=None, phys_
     t_act = (time.perf_counter() - t0) / 2
     omu, osig, olp = L.old_dist(sd, buf["obses"], buf["actions"])
     adam = L.new_adam(sd)
+    L.epoch(sd, adam, buf, last_obs, last_priv, omu, osig, olp, 1e-5)  # untimed warm-up: allocator, thread pool, page faults
     t0 = time.perf_counter()
     for _ in range(ppo_epochs):
         L.epoch(sd, adam, buf, last_obs, last_priv, omu, osig, olp, 1e-5)
@@ -76,7 +77,7 @@ def iteration_sample(num_envs=4096, horizon=24, epochs=20, phys_envs=None, phys_
         env_steps_per_s=num_envs * horizon / total,
         cores=cores,
         sample=(f"physics: {phys_envs} envs x {phys_steps} env-steps (x10 ticks) of the FP64 -O3 host build of the CRBA/RNE/LTDL recursion (oracle/physics_port.cpp), OpenMP {cores} threads, "
-                f"scaled to {num_envs} envs x {horizon} steps; policy: 2 x actor({num_envs}) torch-CPU; update: {ppo_epochs} of "
+                f"scaled to {num_envs} envs x {horizon} steps; policy: 2 x actor({num_envs}) torch-CPU; update: {ppo_epochs} (after 1 untimed warm-up) of "
                 f"{epochs} full-batch epochs (T={horizon}, N={num_envs}) torch-CPU autograd, scaled x{epochs // ppo_epochs}; "
                 f"obs/reward pass not included"),
         parts=dict(physics_s_per_env_step=phys_per_env_step, policy_s_per_step=t_act, epoch_s=t_epoch,
