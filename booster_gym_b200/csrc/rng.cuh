@@ -17,6 +17,14 @@
 #define B200_HD inline
 #endif
 #endif
+// Large helpers that are called many times per thread are kept OUT of line on the device: the env kernels execute each
+// instruction once per warp with 1-4 warps per SM, so they are bound by serialised instruction-cache misses
+// (ncu: stall_no_instruction dominant); a called function is fetched once and then hits the i-cache.
+#if defined(__CUDACC__)
+#define B200_HD_CALL inline __host__ __device__ __noinline__
+#else
+#define B200_HD_CALL inline
+#endif
 
 namespace b200 {
 
@@ -48,7 +56,7 @@ B200_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-B200_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+B200_HD_CALL Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -77,7 +85,7 @@ struct Rand4 {
     float n[4];  // standard normal (Box-Muller on word pairs)
 };
 
-B200_HD Rand4 rand4(const Philox4& p) {
+B200_HD_CALL Rand4 rand4(const Philox4& p) {
     Rand4 r;
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.u[i] = u01(p.w[i]);

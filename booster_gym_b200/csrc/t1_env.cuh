@@ -76,7 +76,7 @@ B200_HD Draw env_draw(const EnvView& v, int e, uint32_t env_key, uint64_t step, 
 }
 
 // ---- Isaac Gym torch_utils semantics (third-party, restated) ---------------------------------------
-B200_HD void quat_rotate_inverse(const float* q, const float* v, float* o) {
+B200_HD_CALL void quat_rotate_inverse(const float* q, const float* v, float* o) {
     const float qw = q[3];
     const float s = 2.0f * qw * qw - 1.0f;
     float c[3];
@@ -85,7 +85,7 @@ B200_HD void quat_rotate_inverse(const float* q, const float* v, float* o) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) o[i] = v[i] * s - c[i] * qw * 2.0f + q[i] * d * 2.0f;
 }
-B200_HD void quat_rotate(const float* q, const float* v, float* o) {
+B200_HD_CALL void quat_rotate(const float* q, const float* v, float* o) {
     const float qw = q[3];
     const float s = 2.0f * qw * qw - 1.0f;
     float c[3];
@@ -101,7 +101,7 @@ B200_HD float py_mod(float a, float b) {  // torch.remainder / Python % for b > 
 }
 #define B200_PI_F 3.14159265358979323846f
 #define B200_2PI_F 6.28318530717958647692f
-B200_HD void get_euler_xyz(const float* q, float& roll, float& pitch, float& yaw) {
+B200_HD_CALL void get_euler_xyz(const float* q, float& roll, float& pitch, float& yaw) {
     const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
     const float sinr_cosp = 2.0f * (qw * qx + qy * qz);
     const float cosr_cosp = qw * qw - qx * qx - qy * qy + qz * qz;

@@ -11,6 +11,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "rng.cuh"  // B200_HD / B200_HD_CALL
+
 #if defined(__CUDACC__)
 #define B200_HD __host__ __device__ __forceinline__
 #else
@@ -29,6 +31,9 @@ struct TerrainView {
 
     B200_HD float operator()(float px, float py) const {
         if (hf == nullptr) return 0.0f;
+        return lookup(px, py);
+    }
+    B200_HD_CALL float lookup(float px, float py) const {
 #if defined(__CUDA_ARCH__)
         const float x = __fadd_rn((float)border_pixels, __fdiv_rn(px, horizontal_scale));
         const float y = __fadd_rn((float)border_pixels, __fdiv_rn(py, horizontal_scale));
