@@ -17,7 +17,7 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
-          "-diag-suppress", "550,177"]
+          "-diag-suppress", "550,177"] + os.environ.get("B200_NVCC_EXTRA", "").split()
 
 # translation unit -> extra flags
 UNITS = {

@@ -1,21 +1,27 @@
 // gemm_tc.cuh - Blackwell-native fp32-accurate GEMMs for the actor/critic MLP (utils/model.py:9-26): tcgen05.mma
 // (kind::tf32) with TMEM accumulators, TMA-staged operands (cp.async.bulk.tensor, 128-byte swizzle), mbarrier pipelines.
 //
-// Precision: every fp32 operand x is carried as a PRE-SPLIT pair (hi = tf32(x), lo = tf32(x - hi)) produced by the
-// epilogue of the kernel that wrote it, and every product is evaluated as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  - three
-// tcgen05.mma per k-step into the same TMEM accumulator (3xTF32; SASS: UTCHMMA, UTMALDG, LDTM).
+// Precision: every product is evaluated as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  with both halves TF32 - three tcgen05.mma
+// per k-step into the same TMEM accumulator (3xTF32; SASS: UTCHMMA, UTMALDG, LDTM).  Activations and their gradients
+// live in HBM as plain fp32 (4 B / element); the split happens IN SHARED MEMORY: TMA lands the raw fp32 tile, which the
+// tensor core reads directly as the hi half (kind::tf32 ignores the low 13 mantissa bits: measured, truncation), and
+// four converter warps write lo = tf32(x - trunc13(x)) into a second tile of the same (swizzled) layout, publish it with
+// fence.proxy.async and an mbarrier.  Weights are pre-split (hi rounded to nearest, so the dropped lo*lo term has no
+// systematic sign) by k_weight_prep: they are small and shared by all CTAs.
 //
 // Two kernels:
 //   k_tc_rowmajor<BN, STAGES, EPI, NACC>   C[M, Nout] = epi(A[M, K] * B[Nout, K]^T)   both operands K-major
 //        persistent CTAs (one per SM, 576 threads), warp roles: 0 = TMA producer, 1 = MMA issuer (single elected thread),
 //        2..17 = epilogue.  NACC TMEM accumulators per tile (k-blocks rotate over them and the epilogue adds them with
 //        round-to-nearest FADDs: TMEM accumulation truncates), double-buffered across tiles when 2*BN*NACC <= 512 columns
-//        so the epilogue of tile i overlaps the main loop of tile i+1.  EPI_FWD: +bias, ELU, split, store hi/lo (+ optional
-//        fp32 copy).  EPI_DGRAD: * ELU'(h) with h = hi+lo of the layer's stored post-activation, split, store hi/lo, and
-//        the bias gradient (column sums) of the layer below.  Global IO is 256-bit per thread (one 32-byte sector).
+//        so the epilogue of tile i overlaps the main loop of tile i+1.  EPI_FWD: +bias, ELU, store fp32.  EPI_DGRAD:
+//        * ELU'(h) with h = the layer's stored post-activation, store fp32, and the bias gradient (column sums) of the
+//        layer below.  Global IO is 256-bit per thread (one 32-byte sector).  Warps 18..21 are the lo converters.
 //   k_tc_wgrad<BN, STAGES>           dW[Nout, Kin] += dY[m, Nout]^T X[m, Kin] over a contiguous range of rows m per CTA
 //        the reduction index is the ROW index of both operands -> MN-major operands; for 32-bit elements the only legal
-//        MN-major shared-memory layout is SWIZZLE_128B_BASE32B (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+//        MN-major shared-memory layout is SWIZZLE_128B_BASE32B (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Both operands
+//        are activations here, so eight converter warps split both; dY is additionally rounded in place (hi = rna(x)) so
+//        that the dropped lo*lo term of the two truncated operands does not accumulate a signed bias over 98k rows.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -33,16 +39,13 @@ static constexpr int BK = 32;   // fp32 elements per k-block = one 128-byte swiz
 enum { EPI_FWD = 0, EPI_DGRAD = 1 };
 
 struct RowArgs {
-    float* out_hi;
-    float* out_lo;
-    float* out_f32;      // nullable
+    float* out;          // [M, ldo] fp32
     const float* bias;   // EPI_FWD
-    const float* aux_hi; // EPI_DGRAD: post-activation of the layer whose input gradient is produced
-    const float* aux_lo;
+    const float* aux;    // EPI_DGRAD: post-activation (fp32) of the layer whose input gradient is produced
     float* colsum;       // nullable (EPI_DGRAD): colsum[c] += sum over rows of the stored output column c = the bias gradient of the
                          // layer this dX feeds (utils/runner.py:163 autograd of nn.Linear.bias)
     int M, Nout, K;      // rows, output columns (multiple of 32), reduction length (TMA zero-fills beyond the tensor)
-    int ldo;             // leading dimension of out_* and aux_* (floats)
+    int ldo;             // leading dimension of out and aux (floats)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,6 +106,16 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+// lo half of the in-smem split: the tensor core truncates the raw fp32 word to tf32, so lo = x - trunc13(x) (exact, <= 13
+// significant bits), rounded to tf32
+__device__ __forceinline__ float lo_trunc(float x) {
+    return tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+__device__ __forceinline__ float4 lo_trunc4(const float4 x) {
+    return make_float4(lo_trunc(x.x), lo_trunc(x.y), lo_trunc(x.z), lo_trunc(x.w));
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void ldg_v8(const float* p, float* a) {  // 256-bit global load (sm_100: LDG.E.256), 32-byte aligned
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "l"(p));
@@ -131,11 +144,14 @@ __device__ __forceinline__ float elu_fast(float x) {
 }
 
 static constexpr int EPI_WARPS = 16;                   // 4 per TMEM lane quarter, each takes a quarter of the tile's columns
-static constexpr int ROW_THREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
+static constexpr int CONV_WARPS = 4;                   // in-smem lo converters of the A (activation) tile
+static constexpr int CONV_T0 = 64 + 32 * EPI_WARPS;    // first converter thread
+static constexpr int ROW_THREADS = CONV_T0 + 32 * CONV_WARPS;  // TMA warp + MMA warp + epilogue warps + converter warps
 template <int BN, int STAGES>
 struct RowSmem {
     static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+    // stage layout: [A raw fp32 = hi operand][A lo (converter)][B hi][B lo]
 };
 
 // The epilogue is instruction-bound (ELU's expm1f, two tf32 roundings, address math: ~40 instructions per element),
@@ -144,14 +160,15 @@ struct RowSmem {
 // thread (L1 / L2 merge them), no shared-memory staging is needed.
 template <int BN, int STAGES, int EPI, int NACC>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
-k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
-              const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const RowArgs g) {
+k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
+              const RowArgs g) {
     using S = RowSmem<BN, STAGES>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + STAGES * S::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;   // [2]
+    uint64_t* conv = empty + STAGES;    // [STAGES] lo tile written
+    uint64_t* tfull = conv + STAGES;    // [2]
     uint64_t* tempty = tfull + 2;       // [2]
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -164,7 +181,7 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
     static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM allocation must be a power of two <= 512 columns");
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 32 * CONV_WARPS); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -187,9 +204,8 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
-                    mbar_expect_tx(&full[s], S::STAGE_BYTES);
-                    tma_load_2d(&mAh, &full[s], st, kb * BK, m0);
-                    tma_load_2d(&mAl, &full[s], st + S::A_BYTES, kb * BK, m0);
+                    mbar_expect_tx(&full[s], S::A_BYTES + 2 * S::B_BYTES);
+                    tma_load_2d(&mA, &full[s], st, kb * BK, m0);
                     tma_load_2d(&mBh, &full[s], st + 2 * S::A_BYTES, kb * BK, n0);
                     tma_load_2d(&mBl, &full[s], st + 2 * S::A_BYTES + S::B_BYTES, kb * BK, n0);
                 }
@@ -206,7 +222,8 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&full[s], ph);
+                    mbar_wait(&full[s], ph);   // TMA: raw A (= hi operand) and the split B tiles
+                    mbar_wait(&conv[s], ph);   // converter warps: A lo
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES,
                                    b_lo = b_hi + S::B_BYTES;
@@ -222,6 +239,26 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
                     umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
                 }
                 umma_commit(&tfull[a]);      // accumulator complete
+            }
+        }
+    } else if (warp >= CONV_T0 / 32) {
+        // ===== converter warps: A lo = tf32(x - trunc13(x)), same swizzled offsets as the raw tile (elementwise) =====
+        const int t = threadIdx.x - CONV_T0;
+        constexpr int VEC = S::A_BYTES / 16 / (32 * CONV_WARPS);   // float4 per thread per k-block
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                const float4* raw = reinterpret_cast<const float4*>(smem + s * S::STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE_BYTES + S::A_BYTES);
+                float4 x[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) x[i] = raw[t + i * 32 * CONV_WARPS];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) lo[t + i * 32 * CONV_WARPS] = lo_trunc4(x[i]);
+                fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&conv[s]);
             }
         }
     } else {
@@ -269,26 +306,15 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        float h8[8], l8[8];
-                        ldg_v8(g.aux_hi + base + j, h8);
-                        ldg_v8(g.aux_lo + base + j, l8);
+                        float h8[8];
+                        ldg_v8(g.aux + base + j, h8);
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const float hh = h8[t] + l8[t];
-                            v[j + t] = __uint_as_float(r[j + t]) * ((hh > 0.0f) ? 1.0f : (hh + 1.0f));
-                        }
+                        for (int t = 0; t < 8; ++t) v[j + t] = __uint_as_float(r[j + t]) * ((h8[t] > 0.0f) ? 1.0f : (h8[t] + 1.0f));
                     }
                 }
+                if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    float hi[8], lo[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) { hi[t] = tf32_rna(v[j + t]); lo[t] = tf32_rna(v[j + t] - hi[t]); }
-                    if (row_ok) {
-                        stg_v8(g.out_hi + base + j, hi);
-                        stg_v8(g.out_lo + base + j, lo);
-                        if (g.out_f32) stg_v8(g.out_f32 + base + j, v + j);
-                    }
+                    for (int j = 0; j < 32; j += 8) stg_v8(g.out + base + j, v + j);
                 }
                 if (EPI == EPI_DGRAD && g.colsum) {
                     if (!row_ok) {
@@ -331,25 +357,29 @@ struct WgradArgs {
 // covers the problem and every tile element receives one atomic per CTA of its tile).  To keep the truncating TMEM
 // accumulation chains short, k-blocks rotate over NACC = 512 / BN (<= 4) accumulators that the epilogue adds with
 // round-to-nearest FADDs before the atomics.
+static constexpr int WG_CONV_WARPS = 8;
+static constexpr int WG_CONV_T0 = 192;                       // TMA warp, MMA warp, 4 epilogue warps, then the converters
+static constexpr int WG_THREADS = WG_CONV_T0 + 32 * WG_CONV_WARPS;
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUtensorMap mYl, const __grid_constant__ CUtensorMap mXh,
-           const __grid_constant__ CUtensorMap mXl, const WgradArgs g) {
+__global__ void __launch_bounds__(WG_THREADS, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUtensorMap mX, const WgradArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    // stage layout: [dY raw -> hi (rounded in place)][X raw = hi][dY lo][X lo]
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, RAW_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = 2 * RAW_BYTES;
     constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);
     constexpr uint32_t TCOLS = NACC * BN < 32 ? 32 : NACC * BN;
     uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;
+    uint64_t* conv = empty + STAGES;
+    uint64_t* tfull = conv + STAGES;
     uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r_begin = blockIdx.x * g.chunk, r_end = min(g.M, r_begin + g.chunk);
     const int n0 = blockIdx.y * BM, k0 = blockIdx.z * BN;
     const int nk = (r_end > r_begin) ? (r_end - r_begin + BK - 1) / BK : 0;
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 32 * WG_CONV_WARPS); }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -368,18 +398,12 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUte
                     const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    mbar_expect_tx(&full[s], RAW_BYTES);
                     const int r = r_begin + kb * BK;
 #pragma unroll
-                    for (int c = 0; c < BM / 32; ++c) {
-                        tma_load_2d(&mYh, &full[s], st + c * 4096, n0 + c * 32, r);
-                        tma_load_2d(&mYl, &full[s], st + A_BYTES + c * 4096, n0 + c * 32, r);
-                    }
+                    for (int c = 0; c < BM / 32; ++c) tma_load_2d(&mY, &full[s], st + c * 4096, n0 + c * 32, r);
 #pragma unroll
-                    for (int c = 0; c < BN / 32; ++c) {
-                        tma_load_2d(&mXh, &full[s], st + 2 * A_BYTES + c * 4096, k0 + c * 32, r);
-                        tma_load_2d(&mXl, &full[s], st + 2 * A_BYTES + B_BYTES + c * 4096, k0 + c * 32, r);
-                    }
+                    for (int c = 0; c < BN / 32; ++c) tma_load_2d(&mX, &full[s], st + A_BYTES + c * 4096, k0 + c * 32, r);
                 }
             }
         } else if (warp == 1) {
@@ -388,8 +412,9 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUte
                 for (int kb = 0; kb < nk; ++kb) {
                     const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
                     mbar_wait(&full[s], ph);
+                    mbar_wait(&conv[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES, a_lo = a_hi + RAW_BYTES, b_lo = a_lo + A_BYTES;
                     const uint32_t tacc = tmem_base + (uint32_t)(kb % NACC) * BN;
                     const bool first = kb < NACC;  // first k-block of this accumulator overwrites it
 #pragma unroll
@@ -402,6 +427,31 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mYh, const __grid_constant__ CUte
                     umma_commit(&empty[s]);
                 }
                 umma_commit(tfull);
+            }
+        } else if (warp >= WG_CONV_T0 / 32) {
+            // ===== converter warps: split both operands in shared memory (elementwise, layout-agnostic) =====
+            const int t = threadIdx.x - WG_CONV_T0;
+            constexpr int NT = 32 * WG_CONV_WARPS;
+            constexpr int A_VEC = A_BYTES / 16 / NT, B_VEC = B_BYTES / 16 / NT;
+            static_assert(A_VEC * NT * 16 == A_BYTES && B_VEC * NT * 16 == B_BYTES, "converter tiling");
+            for (int kb = 0; kb < nk; ++kb) {
+                const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                float4* raw = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + RAW_BYTES);
+                float4 x[A_VEC + B_VEC];
+#pragma unroll
+                for (int i = 0; i < A_VEC + B_VEC; ++i) x[i] = raw[t + i * NT];
+#pragma unroll
+                for (int i = 0; i < A_VEC; ++i) {   // dY: hi rounded to nearest, written back in place
+                    const float4 h = make_float4(tf32_rna(x[i].x), tf32_rna(x[i].y), tf32_rna(x[i].z), tf32_rna(x[i].w));
+                    raw[t + i * NT] = h;
+                    lo[t + i * NT] = make_float4(tf32_rna(x[i].x - h.x), tf32_rna(x[i].y - h.y), tf32_rna(x[i].z - h.z), tf32_rna(x[i].w - h.w));
+                }
+#pragma unroll
+                for (int i = A_VEC; i < A_VEC + B_VEC; ++i) lo[t + i * NT] = lo_trunc4(x[i]);   // X: the tensor core truncates the raw word
+                fence_async_smem();
+                mbar_arrive(&conv[s]);
             }
         } else {
             const int q = warp & 3;
@@ -478,8 +528,8 @@ struct MapCache {
 };
 
 template <int BN, int STAGES, int EPI, int NACC = 1>
-inline cudaError_t launch_rowmajor(const CUtensorMap* Ah, const CUtensorMap* Al, const CUtensorMap* Bh, const CUtensorMap* Bl,
-                                   const RowArgs& g, int num_sms, cudaStream_t st) {
+inline cudaError_t launch_rowmajor(const CUtensorMap* A, const CUtensorMap* Bh, const CUtensorMap* Bl, const RowArgs& g, int num_sms,
+                                   cudaStream_t st) {
     using S = RowSmem<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -489,13 +539,12 @@ inline cudaError_t launch_rowmajor(const CUtensorMap* Ah, const CUtensorMap* Al,
     }
     const int tiles = ((g.M + BM - 1) / BM) * ((g.Nout + BN - 1) / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    k_tc_rowmajor<BN, STAGES, EPI, NACC><<<grid, ROW_THREADS, S::TOTAL, st>>>(*Ah, *Al, *Bh, *Bl, g);
+    k_tc_rowmajor<BN, STAGES, EPI, NACC><<<grid, ROW_THREADS, S::TOTAL, st>>>(*A, *Bh, *Bl, g);
     return cudaPeekAtLastError();
 }
 
 template <int BN, int STAGES>
-inline cudaError_t launch_wgrad(const CUtensorMap* Yh, const CUtensorMap* Yl, const CUtensorMap* Xh, const CUtensorMap* Xl,
-                                const WgradArgs& g, int kin_padded, cudaStream_t st) {
+inline cudaError_t launch_wgrad(const CUtensorMap* Y, const CUtensorMap* X, const WgradArgs& g, int kin_padded, cudaStream_t st) {
     constexpr int SMEM = STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 256 + 1024;
     static bool configured = false;
     if (!configured) {
@@ -504,7 +553,7 @@ inline cudaError_t launch_wgrad(const CUtensorMap* Yh, const CUtensorMap* Yl, co
         configured = true;
     }
     dim3 grid((g.M + g.chunk - 1) / g.chunk, (g.Nout + BM - 1) / BM, (kin_padded + BN - 1) / BN);
-    k_tc_wgrad<BN, STAGES><<<grid, 192, SMEM, st>>>(*Yh, *Yl, *Xh, *Xl, g);
+    k_tc_wgrad<BN, STAGES><<<grid, WG_THREADS, SMEM, st>>>(*Y, *X, g);
     return cudaPeekAtLastError();
 }
 

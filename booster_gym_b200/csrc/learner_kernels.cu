@@ -42,14 +42,14 @@ enum { DS_ADV_SUM = B200_DS_ADV_SUM, DS_ADV_SUMSQ = B200_DS_ADV_SUMSQ, DS_ADV_CO
        DS_ACTOR_LOSS = B200_DS_ACTOR_LOSS, DS_BOUND_LOSS = B200_DS_BOUND_LOSS, DS_ENTROPY = B200_DS_ENTROPY, DS_KL = B200_DS_KL,
        DS_SAMPLES = B200_DS_SAMPLES, DS_GRAD_SQ = B200_DS_GRAD_SQ, DS_DLOGSTD = B200_DS_DLOGSTD, DS_COUNT = B200_DS_COUNT };
 
-// Workspace (offsets in floats).  "h"/"l" = the tf32 hi / lo halves of a fp32 tensor (gemm_tc.cuh): activations and
-// their gradients live ONLY as pre-split pairs (x == hi + lo to 2^-23), which is what the tcgen05 GEMMs consume.
+// Workspace (offsets in floats).  Activations and their gradients are plain fp32 (4 B / element): the tcgen05 GEMMs split
+// them into tf32 (hi, lo) pairs inside shared memory (gemm_tc.cuh).  Only the weights keep pre-split copies ("h"/"l").
 struct Workspace {
-    size_t Xah, Xal, Xch, Xcl;                          // packed inputs [M,48], [M,64]
-    size_t C1h, C1l, C2h, C2l, C3h, C3l;                // critic post-ELU activations [M,256],[M,256],[M,128]
-    size_t A1h, A1l, A2h, A2l, A3h, A3l, A1f, A2f, A3f, Xaf;  // actor post-ELU activations [M,256],[M,128],[M,128]: pairs + the fp32 originals
+    size_t Xa, Xc;                                      // packed inputs [M,48], [M+N,64]
+    size_t C1, C2, C3;                                  // critic post-ELU activations [M+N,256],[M+N,256],[M+N,128]
+    size_t A1, A2, A3;                                  // actor post-ELU activations [M,256],[M,128],[M,128]
     size_t V, MU, ADV, RET, DV, DMU;
-    size_t G1h, G1l, G2h, G2l, GF;                      // gradient ping-pong [M,256] pairs; GF = fp32 dA3 from the head's dgrad
+    size_t G1, G2;                                      // gradient ping-pong [M,256]
     size_t Wc0h, Wc0l, Wc1h, Wc1l, Wc2h, Wc2l, Wa0h, Wa0l, Wa1h, Wa1l, Wa2h, Wa2l;   // split weights, K padded to 64 for layer 0
     size_t Wc1Th, Wc1Tl, Wc2Th, Wc2Tl, Wa1Th, Wa1Tl, Wa2Th, Wa2Tl;                  // transposed split weights for dgrad
     size_t LXa, LXc, L1, L2, L3, LV, LMU;               // rollout-sized (N rows) fp32 buffers of the mma.sync path
@@ -61,13 +61,11 @@ static Workspace make_workspace(int T, int N) {
     size_t o = 0;
     auto take = [&](size_t cnt) { size_t r = o; o += (cnt + 255) & ~(size_t)255; return r; };  // 1 KiB aligned (TMA needs 16 B)
     const size_t Mc = M + n;  // the critic also evaluates the N post-rollout observations (last_values, utils/runner.py:133) in the same pass
-    w.Xah = take(M * 48); w.Xal = take(M * 48); w.Xch = take(Mc * 64); w.Xcl = take(Mc * 64);
-    w.C1h = take(Mc * 256); w.C1l = take(Mc * 256); w.C2h = take(Mc * 256); w.C2l = take(Mc * 256); w.C3h = take(Mc * 128); w.C3l = take(Mc * 128);
-    w.A1h = take(M * 256); w.A1l = take(M * 256); w.A2h = take(M * 128); w.A2l = take(M * 128);
-    w.A3h = take(M * 128); w.A3l = take(M * 128); w.A3f = take(M * 128);
-    w.A1f = take(M * 256); w.A2f = take(M * 128); w.Xaf = take(M * 48);
+    w.Xa = take(M * 48); w.Xc = take(Mc * 64);
+    w.C1 = take(Mc * 256); w.C2 = take(Mc * 256); w.C3 = take(Mc * 128);
+    w.A1 = take(M * 256); w.A2 = take(M * 128); w.A3 = take(M * 128);
     w.V = take(Mc); w.MU = take(M * 12); w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
-    w.G1h = take(M * 256); w.G1l = take(M * 256); w.G2h = take(M * 256); w.G2l = take(M * 256); w.GF = take(M * 128);
+    w.G1 = take(M * 256); w.G2 = take(M * 256);
     w.Wc0h = take(256 * 64); w.Wc0l = take(256 * 64); w.Wc1h = take(256 * 256); w.Wc1l = take(256 * 256);
     w.Wc2h = take(128 * 256); w.Wc2l = take(128 * 256); w.Wa0h = take(256 * 64); w.Wa0l = take(256 * 64);
     w.Wa1h = take(128 * 256); w.Wa1l = take(128 * 256); w.Wa2h = take(128 * 128); w.Wa2l = take(128 * 128);
@@ -117,27 +115,6 @@ __device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
     lo = tc::tf32_rna(x - hi);
 }
 
-// obs [n,47] + priv [n,14] -> pre-split GEMM operands Xa [n,48] (hi, lo) and Xc [n,64] (hi, lo), zero padded
-__global__ void k_pack_inputs_split(const float* __restrict__ obs, const float* __restrict__ priv, int n, float* __restrict__ Xah,
-                                    float* __restrict__ Xal, float* __restrict__ Xch, float* __restrict__ Xcl, float* __restrict__ Xaf) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)n * 64) return;
-    const size_t r = idx >> 6;
-    const int c = (int)(idx & 63);
-    float v = 0.0f;
-    if (c < 47) v = obs[r * 47 + c];
-    else if (c < 61) v = priv[r * 14 + (c - 47)];
-    float hi, lo;
-    split_tf32f(v, hi, lo);
-    Xch[idx] = hi;
-    Xcl[idx] = lo;
-    if (Xah && c < 48) {
-        split_tf32f(c < 47 ? v : 0.0f, hi, lo);
-        Xah[r * 48 + c] = hi;
-        Xal[r * 48 + c] = lo;
-        if (Xaf) Xaf[r * 48 + c] = (c < 47) ? v : 0.0f;
-    }
-}
 
 // W [rows, cols] fp32 -> split copies: K-major [rows, cols_pad] (zero padded) and, if WTh != null, transposed [cols, rows]
 __global__ void k_weight_prep(const float* __restrict__ W, int rows, int cols, int cols_pad, float* __restrict__ Wh,
@@ -165,16 +142,12 @@ __global__ void k_split(const float* __restrict__ x, size_t n, float* __restrict
     lo[i] = l;
 }
 
-// critic head: V[m] = b + sum_k H[m,k] w[k], one warp per row (H rows are 128 floats = one float4 per lane); Hl nullable
-__global__ void k_value_head(const float* __restrict__ H, const float* __restrict__ Hl, const float* __restrict__ w,
-                             const float* __restrict__ b, int n, float* __restrict__ V) {
+// critic head: V[m] = b + sum_k H[m,k] w[k], one warp per row (H rows are 128 floats = one float4 per lane)
+__global__ void k_value_head(const float* __restrict__ H, const float* __restrict__ w, const float* __restrict__ b, int n,
+                             float* __restrict__ V) {
     const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (warp >= n) return;
-    float4 h = reinterpret_cast<const float4*>(H + (size_t)warp * 128)[lane];
-    if (Hl) {
-        const float4 l = reinterpret_cast<const float4*>(Hl + (size_t)warp * 128)[lane];
-        h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
-    }
+    const float4 h = reinterpret_cast<const float4*>(H + (size_t)warp * 128)[lane];
     const float4 ww = reinterpret_cast<const float4*>(w)[lane];
     float s = h.x * ww.x + h.y * ww.y + h.z * ww.z + h.w * ww.w;
 #pragma unroll
@@ -182,12 +155,11 @@ __global__ void k_value_head(const float* __restrict__ H, const float* __restric
     if (lane == 0) V[warp] = s + b[0];
 }
 
-// backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]) (written pre-split); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m]
+// backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m]
 #define VH_ROWS 128
-__global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict__ Hh, const float* __restrict__ Hl,
-                                                        const float* __restrict__ w, const float* __restrict__ dV, int n,
-                                                        float* __restrict__ dHh, float* __restrict__ dHl, float* __restrict__ dw,
-                                                        float* __restrict__ db, float* __restrict__ db_prev) {
+__global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict__ H, const float* __restrict__ w,
+                                                        const float* __restrict__ dV, int n, float* __restrict__ dH,
+                                                        float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev) {
     const int k = threadIdx.x;
     const int r0 = blockIdx.x * VH_ROWS, r1 = min(n, r0 + VH_ROWS);
     const float wk = w[k];
@@ -195,12 +167,9 @@ __global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict_
     float accp = 0.0f;             // column sum of dH = bias gradient of the layer below
     for (int r = r0; r < r1; ++r) {
         const float g = dV[r];
-        const float h = Hh[(size_t)r * 128 + k] + Hl[(size_t)r * 128 + k];
-        float hi, lo;
+        const float h = H[(size_t)r * 128 + k];
         const float dh = g * wk * ((h > 0.0f) ? 1.0f : (h + 1.0f));
-        split_tf32f(dh, hi, lo);
-        dHh[(size_t)r * 128 + k] = hi;
-        dHl[(size_t)r * 128 + k] = lo;
+        dH[(size_t)r * 128 + k] = dh;
         accp += dh;
         acc += (double)g * (double)h;
         accb += (double)g;
@@ -235,8 +204,8 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, co
 }
 
 // actor head (utils/model.py:25): MU[m, 0..11] = b + H[m, :] W[12,128]^T, one warp per row, plain fp32 FMAs (the 12-wide
-// layer is 2 % of the MLP's FLOPs: a tensor-core tile would be 90 % padding).  H = Hf, or Hh + Hl when Hl != null.
-__global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf, const float* __restrict__ Hl, const float* __restrict__ W,
+// layer is 2 % of the MLP's FLOPs: a tensor-core tile would be 90 % padding).
+__global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf, const float* __restrict__ W,
                                                     const float* __restrict__ b, int n, float* __restrict__ MU) {
     __shared__ float4 sW[12][32];
     for (int i = threadIdx.x; i < 12 * 32; i += blockDim.x) sW[i >> 5][i & 31] = reinterpret_cast<const float4*>(W)[i];
@@ -244,11 +213,7 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n; row += warps) {
-        float4 h = reinterpret_cast<const float4*>(Hf + (size_t)row * 128)[lane];
-        if (Hl) {
-            const float4 l = reinterpret_cast<const float4*>(Hl + (size_t)row * 128)[lane];
-            h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
-        }
+        const float4 h = reinterpret_cast<const float4*>(Hf + (size_t)row * 128)[lane];
         float out = 0.0f;
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
@@ -262,13 +227,12 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf
     }
 }
 
-// backward of the actor head, fused: dH[m,k] = (sum_j dMU[m,j] W[j,k]) ELU'(H[m,k]) written pre-split (hi, lo);
+// backward of the actor head, fused: dH[m,k] = (sum_j dMU[m,j] W[j,k]) ELU'(H[m,k]);
 // dW[j,k] += sum_m dMU[m,j] H[m,k]; db[j] += sum_m dMU[m,j].   128 threads = the 128 hidden units, rows in chunks.
 #define AH_ROWS 128
-__global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ Hl, const float* __restrict__ W,
-                                                        const float* __restrict__ dMU, int n, float* __restrict__ dHh,
-                                                        float* __restrict__ dHl, float* __restrict__ dW, float* __restrict__ db,
-                                                        float* __restrict__ db_prev) {
+__global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ W,
+                                                        const float* __restrict__ dMU, int n, float* __restrict__ dH,
+                                                        float* __restrict__ dW, float* __restrict__ db, float* __restrict__ db_prev) {
     __shared__ float sd[AH_ROWS][12];
     const int k = threadIdx.x;
     const int r0 = blockIdx.x * AH_ROWS, r1 = min(n, r0 + AH_ROWS);
@@ -282,7 +246,7 @@ __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict_
     for (int j = 0; j < 12; ++j) acc[j] = 0.0f;
     float accp = 0.0f;
     for (int r = r0; r < r1; ++r) {
-        const float h = Hf[(size_t)r * 128 + k] + Hl[(size_t)r * 128 + k];
+        const float h = Hf[(size_t)r * 128 + k];
         float g = 0.0f;
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
@@ -291,10 +255,7 @@ __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict_
             acc[j] = fmaf(d, h, acc[j]);
         }
         const float dh = g * ((h > 0.0f) ? 1.0f : (h + 1.0f));
-        float hi, lo;
-        split_tf32f(dh, hi, lo);
-        dHh[(size_t)r * 128 + k] = hi;
-        dHl[(size_t)r * 128 + k] = lo;
+        dH[(size_t)r * 128 + k] = dh;
         accp += dh;
     }
     atomicAdd(db_prev + k, accp);
@@ -847,52 +808,48 @@ static cudaError_t bias_grad(const float* dY, const float* dYl, int ld, int C, i
     const CUtensorMap* var = p->maps->get(ptr, rows, cols, ld, box, kmajor);                               \
     if (!var) return set_error(B200_ERR_CUDA, p->maps->error ? p->maps->error : "tensor map creation failed")
 
-// Y(h,l[,f]) [n, n_out] = ELU(X(h,l) [n, k] W(h,l) [n_out, k_pad]^T + b)
-static int tc_fwd(const B200Ppo* p, const float* Xh, const float* Xl, int k, int ldx, const float* Wh, const float* Wl, int k_pad,
-                  const float* b, float* Yh, float* Yl, float* Yf, int n, int n_out, cudaStream_t st, bool accurate = false) {
+// Y [n, n_out] = ELU(X [n, k] W(h,l) [n_out, k_pad]^T + b)
+static int tc_fwd(const B200Ppo* p, const float* X, int k, int ldx, const float* Wh, const float* Wl, int k_pad, const float* b,
+                  float* Y, int n, int n_out, cudaStream_t st, bool accurate = false) {
     const int bn = (n_out >= 256 && !accurate) ? 256 : 128;
-    TC_MAP(mAh, Xh, n, k, ldx, tc::BM, true);
-    TC_MAP(mAl, Xl, n, k, ldx, tc::BM, true);
+    TC_MAP(mA, X, n, k, ldx, tc::BM, true);
     TC_MAP(mBh, Wh, n_out, k_pad, k_pad, bn, true);
     TC_MAP(mBl, Wl, n_out, k_pad, k_pad, bn, true);
     tc::RowArgs g{};
-    g.out_hi = Yh; g.out_lo = Yl; g.out_f32 = Yf; g.bias = b; g.aux_hi = nullptr; g.aux_lo = nullptr; g.colsum = nullptr;
+    g.out = Y; g.bias = b; g.aux = nullptr; g.colsum = nullptr;
     g.M = n; g.Nout = n_out; g.K = k_pad; g.ldo = n_out;
     prof_begin(st, 2.0 * n * (double)n_out * k, PK_TC_ROW);
-    const cudaError_t e = accurate    ? tc::launch_rowmajor<128, 3, tc::EPI_FWD, 4>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
-                          : (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
-                                        : tc::launch_rowmajor<128, 3, tc::EPI_FWD>(mAh, mAl, mBh, mBl, g, p->num_sms, st);
+    const cudaError_t e = accurate    ? tc::launch_rowmajor<128, 3, tc::EPI_FWD, 4>(mA, mBh, mBl, g, p->num_sms, st)
+                          : (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_FWD>(mA, mBh, mBl, g, p->num_sms, st)
+                                        : tc::launch_rowmajor<128, 3, tc::EPI_FWD>(mA, mBh, mBl, g, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<fwd>");
     return B200_OK;
 }
-// dX(h,l) [n, k_in] = (dY(h,l) [n, n_out] WT(h,l) [k_in, n_out]^T) * ELU'(H(h,l) [n, k_in])
-static int tc_dgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_out, const float* WTh, const float* WTl, int k_in,
-                    const float* Hh, const float* Hl, float* dXh, float* dXl, float* colsum, int n, cudaStream_t st) {
+// dX [n, k_in] = (dY [n, n_out] WT(h,l) [k_in, n_out]^T) * ELU'(H [n, k_in])
+static int tc_dgrad(const B200Ppo* p, const float* dY, int n_out, const float* WTh, const float* WTl, int k_in, const float* H,
+                    float* dX, float* colsum, int n, cudaStream_t st) {
     const int bn = (k_in >= 256) ? 256 : 128;
-    TC_MAP(mAh, dYh, n, n_out, n_out, tc::BM, true);
-    TC_MAP(mAl, dYl, n, n_out, n_out, tc::BM, true);
+    TC_MAP(mA, dY, n, n_out, n_out, tc::BM, true);
     TC_MAP(mBh, WTh, k_in, n_out, n_out, bn, true);
     TC_MAP(mBl, WTl, k_in, n_out, n_out, bn, true);
     tc::RowArgs g{};
-    g.out_hi = dXh; g.out_lo = dXl; g.out_f32 = nullptr; g.bias = nullptr; g.aux_hi = Hh; g.aux_lo = Hl; g.colsum = colsum;
+    g.out = dX; g.bias = nullptr; g.aux = H; g.colsum = colsum;
     g.M = n; g.Nout = k_in; g.K = n_out; g.ldo = k_in;
     prof_begin(st, 2.0 * n * (double)n_out * k_in, PK_TC_ROW);
-    const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_DGRAD>(mAh, mAl, mBh, mBl, g, p->num_sms, st)
-                                      : tc::launch_rowmajor<128, 3, tc::EPI_DGRAD>(mAh, mAl, mBh, mBl, g, p->num_sms, st);
+    const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st)
+                                      : tc::launch_rowmajor<128, 3, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<dgrad>");
     return B200_OK;
 }
-// dW [n_out, k_valid] += dY(h,l) [n, n_out]^T X(h,l) [n, k_cols]   (k_pad = 64 / 128 / 256 = tile width along k)
-static int tc_wgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_out, const float* Xh, const float* Xl, int k_cols,
-                    int k_pad, int k_valid, float* dW, int n, cudaStream_t st) {
-    TC_MAP(mYh, dYh, n, n_out, n_out, 32, false);
-    TC_MAP(mYl, dYl, n, n_out, n_out, 32, false);
-    TC_MAP(mXh, Xh, n, k_cols, k_cols, 32, false);
-    TC_MAP(mXl, Xl, n, k_cols, k_cols, 32, false);
+// dW [n_out, k_valid] += dY [n, n_out]^T X [n, k_cols]   (k_pad = 64 / 128 / 256 = tile width along k)
+static int tc_wgrad(const B200Ppo* p, const float* dY, int n_out, const float* X, int k_cols, int k_pad, int k_valid, float* dW, int n,
+                    cudaStream_t st) {
+    TC_MAP(mY, dY, n, n_out, n_out, 32, false);
+    TC_MAP(mX, X, n, k_cols, k_cols, 32, false);
     tc::WgradArgs g{};
     g.D = dW; g.M = n; g.Nout = n_out; g.Kin = k_valid; g.ldd = k_valid;
     {
@@ -904,9 +861,9 @@ static int tc_wgrad(const B200Ppo* p, const float* dYh, const float* dYl, int n_
     }
     prof_begin(st, 2.0 * n * (double)n_out * k_valid, PK_TC_WGRAD);
     cudaError_t e;
-    if (k_pad == 256) e = tc::launch_wgrad<256, 2>(mYh, mYl, mXh, mXl, g, k_pad, st);
-    else if (k_pad == 128) e = tc::launch_wgrad<128, 3>(mYh, mYl, mXh, mXl, g, k_pad, st);
-    else e = tc::launch_wgrad<64, 3>(mYh, mYl, mXh, mXl, g, k_pad, st);
+    if (k_pad == 256) e = tc::launch_wgrad<256, 2>(mY, mX, g, k_pad, st);
+    else if (k_pad == 128) e = tc::launch_wgrad<128, 3>(mY, mX, g, k_pad, st);
+    else e = tc::launch_wgrad<64, 3>(mY, mX, g, k_pad, st);
     prof_end(st);
     g_launches += 1;
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_wgrad");
@@ -929,17 +886,17 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
     g_launches += 6;
     return launch_status("k_weight_prep");
 }
-// full-batch forward passes over the M = T*N stored samples (pre-split operands, activations kept for the backward pass)
+// full-batch forward passes over the M = T*N stored samples (activations kept in fp32 for the backward pass)
 // The ACTOR forward uses the 4-accumulator variant with the exact expm1f: log-prob sensitivity to mu is 1/sigma ~ 7.4 per
 // unit (sigma = e^-2), so mu wants short accumulation chains (TMEM adds truncate) - see gemm_tc.cuh.
 static int actor_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
     int rc;
-    if ((rc = tc_fwd(p, ws + w.Xah, ws + w.Xal, 48, 48, ws + w.Wa0h, ws + w.Wa0l, 64, p->P(P_AB0), ws + w.A1h, ws + w.A1l, nullptr, M, 256, st, true))) return rc;
-    if ((rc = tc_fwd(p, ws + w.A1h, ws + w.A1l, 256, 256, ws + w.Wa1h, ws + w.Wa1l, 256, p->P(P_AB1), ws + w.A2h, ws + w.A2l, nullptr, M, 128, st, true))) return rc;
-    if ((rc = tc_fwd(p, ws + w.A2h, ws + w.A2l, 128, 128, ws + w.Wa2h, ws + w.Wa2l, 128, p->P(P_AB2), ws + w.A3h, ws + w.A3l, nullptr, M, 128, st, true))) return rc;
-    k_actor_head<<<1184, 256, 0, st>>>(ws + w.A3h, ws + w.A3l, p->P(P_AW3), p->P(P_AB3), M, ws + w.MU);
+    if ((rc = tc_fwd(p, ws + w.Xa, 48, 48, ws + w.Wa0h, ws + w.Wa0l, 64, p->P(P_AB0), ws + w.A1, M, 256, st, true))) return rc;
+    if ((rc = tc_fwd(p, ws + w.A1, 256, 256, ws + w.Wa1h, ws + w.Wa1l, 256, p->P(P_AB1), ws + w.A2, M, 128, st, true))) return rc;
+    if ((rc = tc_fwd(p, ws + w.A2, 128, 128, ws + w.Wa2h, ws + w.Wa2l, 128, p->P(P_AB2), ws + w.A3, M, 128, st, true))) return rc;
+    k_actor_head<<<1184, 256, 0, st>>>(ws + w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + w.MU);
     g_launches += 1;
     return launch_status("k_actor_head");
 }
@@ -947,10 +904,10 @@ static int critic_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
     int rc;
-    if ((rc = tc_fwd(p, ws + w.Xch, ws + w.Xcl, 64, 64, ws + w.Wc0h, ws + w.Wc0l, 64, p->P(P_CB0), ws + w.C1h, ws + w.C1l, nullptr, M, 256, st))) return rc;
-    if ((rc = tc_fwd(p, ws + w.C1h, ws + w.C1l, 256, 256, ws + w.Wc1h, ws + w.Wc1l, 256, p->P(P_CB1), ws + w.C2h, ws + w.C2l, nullptr, M, 256, st))) return rc;
-    if ((rc = tc_fwd(p, ws + w.C2h, ws + w.C2l, 256, 256, ws + w.Wc2h, ws + w.Wc2l, 256, p->P(P_CB2), ws + w.C3h, ws + w.C3l, nullptr, M, 128, st))) return rc;
-    k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3h, ws + w.C3l, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
+    if ((rc = tc_fwd(p, ws + w.Xc, 64, 64, ws + w.Wc0h, ws + w.Wc0l, 64, p->P(P_CB0), ws + w.C1, M, 256, st))) return rc;
+    if ((rc = tc_fwd(p, ws + w.C1, 256, 256, ws + w.Wc1h, ws + w.Wc1l, 256, p->P(P_CB1), ws + w.C2, M, 256, st))) return rc;
+    if ((rc = tc_fwd(p, ws + w.C2, 256, 256, ws + w.Wc2h, ws + w.Wc2l, 256, p->P(P_CB2), ws + w.C3, M, 128, st))) return rc;
+    k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
     g_launches += 1;
     return launch_status("k_value_head");
 }
@@ -961,7 +918,7 @@ static int actor_forward(const B200Ppo* p, const float* X, int ldx, int k_pad, i
     CU_TRY(linear_fwd(X, ldx, k_pad, p->P(P_AW0), 47, p->P(P_AB0), H1, 256, n, 256, true, st));
     CU_TRY(linear_fwd(H1, 256, 256, p->P(P_AW1), 256, p->P(P_AB1), H2, 128, n, 128, true, st));
     CU_TRY(linear_fwd(H2, 128, 128, p->P(P_AW2), 128, p->P(P_AB2), H3, 128, n, 128, true, st));
-    k_actor_head<<<(n * 32 + 255) / 256 < 1184 ? (n * 32 + 255) / 256 : 1184, 256, 0, st>>>(H3, nullptr, p->P(P_AW3), p->P(P_AB3), n, MU);
+    k_actor_head<<<(n * 32 + 255) / 256 < 1184 ? (n * 32 + 255) / 256 : 1184, 256, 0, st>>>(H3, p->P(P_AW3), p->P(P_AB3), n, MU);
     g_launches += 1;
     return launch_status("k_actor_head");
 }
@@ -971,7 +928,7 @@ static int critic_forward(const B200Ppo* p, const float* Xc, int n, float* H1, f
     CU_TRY(linear_fwd(Xc, 64, 64, p->P(P_CW0), 61, p->P(P_CB0), H1, 256, n, 256, true, st));
     CU_TRY(linear_fwd(H1, 256, 256, p->P(P_CW1), 256, p->P(P_CB1), H2, 256, n, 256, true, st));
     CU_TRY(linear_fwd(H2, 256, 256, p->P(P_CW2), 256, p->P(P_CB2), H3, 128, n, 128, true, st));
-    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(H3, nullptr, p->P(P_CW3), p->P(P_CB3), n, V);
+    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(H3, p->P(P_CW3), p->P(P_CB3), n, V);
     g_launches += 1;
     return launch_status("k_value_head");
 }
@@ -1073,13 +1030,12 @@ int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const 
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     const int M = p->cfg.horizon * p->cfg.num_envs;
-    k_pack_inputs_split<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(obses, privs, M, ws + p->w.Xah, ws + p->w.Xal,
-                                                                              ws + p->w.Xch, ws + p->w.Xcl, ws + p->w.Xaf);
+    k_pack_inputs<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(obses, privs, M, ws + p->w.Xa, ws + p->w.Xc);
     int rc = weight_prep(p, st);
     if (rc != B200_OK) return rc;
     if ((rc = actor_forward_tc(p, M, st)) != B200_OK) return rc;
     k_old_logp<<<(M + 255) / 256, 256, 0, st>>>(ws + p->w.MU, actions, p->P(P_LOGSTD), M, old_mu, old_logp, p->scalars);
-    g_launches += 2;  // + k_pack_inputs_split
+    g_launches += 2;  // + k_pack_inputs
     return launch_status("k_old_logp");
 }
 
@@ -1106,8 +1062,7 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     int rc = weight_prep(p, st);  // the parameters changed in the previous epoch's b200_ppo_apply
     if (rc != B200_OK) return rc;
     // last_values = critic(post-rollout obs): appended as rows [M, M+N) of the critic batch, evaluated in the same GEMMs
-    k_pack_inputs_split<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(last_obs, last_priv, N, nullptr, nullptr,
-                                                                              ws + p->w.Xch + (size_t)M * 64, ws + p->w.Xcl + (size_t)M * 64, nullptr);
+    k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(last_obs, last_priv, N, nullptr, ws + p->w.Xc + (size_t)M * 64);
     if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
     k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
@@ -1123,7 +1078,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     const Workspace& w = p->w;
     const int M = p->cfg.horizon * p->cfg.num_envs;
     float *MU = ws + w.MU, *DV = ws + w.DV, *DMU = ws + w.DMU;
-    float *G1h = ws + w.G1h, *G1l = ws + w.G1l, *G2h = ws + w.G2h, *G2l = ws + w.G2l;
+    float *G1 = ws + w.G1, *G2 = ws + w.G2;
     int rc = actor_forward_tc(p, M, st);
     if (rc != B200_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(p->grads, 0, NPARAMS_PADDED * sizeof(float), st));
@@ -1133,27 +1088,25 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     k_finalize_logstd<<<1, 32, 0, st>>>(p->dstats, p->cfg.entropy_coef, p->G(P_LOGSTD));
     g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
-    // ---- actor backward: the 12-wide head on the mma.sync path (fp32 operands), the hidden layers on tcgen05
-    k_actor_head_bwd<<<(M + AH_ROWS - 1) / AH_ROWS, 128, 0, st>>>(ws + w.A3h, ws + w.A3l, p->P(P_AW3), DMU, M, G1h, G1l, p->G(P_AW3), p->G(P_AB3),
-                                                                 p->G(P_AB2));
+    // ---- actor backward: the 12-wide head as a fused FMA kernel, the hidden layers on tcgen05
+    k_actor_head_bwd<<<(M + AH_ROWS - 1) / AH_ROWS, 128, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, G1, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2));
     g_launches += 1;
     if ((rc = launch_status("k_actor_head_bwd")) != B200_OK) return rc;
     // (each bias gradient = column sum of the layer's output gradient, accumulated by the kernel that produces it)
-    if ((rc = tc_wgrad(p, G1h, G1l, 128, ws + w.A2h, ws + w.A2l, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
-    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wa2Th, ws + w.Wa2Tl, 128, ws + w.A2h, ws + w.A2l, G2h, G2l, p->G(P_AB1), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G2h, G2l, 128, ws + w.A1h, ws + w.A1l, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
-    if ((rc = tc_dgrad(p, G2h, G2l, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1h, ws + w.A1l, G1h, G1l, p->G(P_AB0), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G1h, G1l, 256, ws + w.Xah, ws + w.Xal, 48, 64, 47, p->G(P_AW0), M, st))) return rc;
+    if ((rc = tc_wgrad(p, G1, 128, ws + w.A2, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
+    if ((rc = tc_dgrad(p, G1, 128, ws + w.Wa2Th, ws + w.Wa2Tl, 128, ws + w.A2, G2, p->G(P_AB1), M, st))) return rc;
+    if ((rc = tc_wgrad(p, G2, 128, ws + w.A1, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
+    if ((rc = tc_dgrad(p, G2, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1, G1, p->G(P_AB0), M, st))) return rc;
+    if ((rc = tc_wgrad(p, G1, 256, ws + w.Xa, 48, 64, 47, p->G(P_AW0), M, st))) return rc;
     // ---- critic backward
-    k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(ws + w.C3h, ws + w.C3l, p->P(P_CW3), DV, M, G1h, G1l, p->G(P_CW3),
-                                                                  p->G(P_CB3), p->G(P_CB2));
+    k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2));
     g_launches += 1;
     if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
-    if ((rc = tc_wgrad(p, G1h, G1l, 128, ws + w.C2h, ws + w.C2l, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
-    if ((rc = tc_dgrad(p, G1h, G1l, 128, ws + w.Wc2Th, ws + w.Wc2Tl, 256, ws + w.C2h, ws + w.C2l, G2h, G2l, p->G(P_CB1), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G2h, G2l, 256, ws + w.C1h, ws + w.C1l, 256, 256, 256, p->G(P_CW1), M, st))) return rc;
-    if ((rc = tc_dgrad(p, G2h, G2l, 256, ws + w.Wc1Th, ws + w.Wc1Tl, 256, ws + w.C1h, ws + w.C1l, G1h, G1l, p->G(P_CB0), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G1h, G1l, 256, ws + w.Xch, ws + w.Xcl, 64, 64, 61, p->G(P_CW0), M, st))) return rc;
+    if ((rc = tc_wgrad(p, G1, 128, ws + w.C2, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
+    if ((rc = tc_dgrad(p, G1, 128, ws + w.Wc2Th, ws + w.Wc2Tl, 256, ws + w.C2, G2, p->G(P_CB1), M, st))) return rc;
+    if ((rc = tc_wgrad(p, G2, 256, ws + w.C1, 256, 256, 256, p->G(P_CW1), M, st))) return rc;
+    if ((rc = tc_dgrad(p, G2, 256, ws + w.Wc1Th, ws + w.Wc1Tl, 256, ws + w.C1, G1, p->G(P_CB0), M, st))) return rc;
+    if ((rc = tc_wgrad(p, G1, 256, ws + w.Xc, 64, 64, 61, p->G(P_CW0), M, st))) return rc;
     return B200_OK;
 }
 
