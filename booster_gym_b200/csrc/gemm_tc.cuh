@@ -33,6 +33,27 @@
 namespace b200 {
 namespace tc {
 
+// Optional per-CTA timeline (-DB200_TC_TIMELINE, tools/tc_timeline.py): globaltimer stamps / accumulated waits per role, written to
+// a device array that b200_tc_timeline_read copies out.  Compiled out of the product build.
+#ifdef B200_TC_TIMELINE
+#define TL_SLOTS 40
+__device__ unsigned long long g_tl[TL_SLOTS][160][8];
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_SET(kind, slot, v) g_tl[g.tl_slot][blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) < 160 ? blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) : 159][slot] = (v)
+#define TL_DECL(x) unsigned long long x = 0
+#define TL_T0(x) const unsigned long long x = tl_now()
+#define TL_ACC(acc, t0) acc += tl_now() - (t0)
+#else
+#define TL_SET(kind, slot, v)
+#define TL_DECL(x)
+#define TL_T0(x)
+#define TL_ACC(acc, t0)
+#endif
+
 static constexpr int BM = 128;  // rows of the output tile = TMEM lanes = UMMA M
 static constexpr int BK = 32;   // fp32 elements per k-block = one 128-byte swizzle row
 
@@ -46,6 +67,7 @@ struct RowArgs {
                          // layer this dX feeds (utils/runner.py:163 autograd of nn.Linear.bias)
     int M, Nout, K;      // rows, output columns (multiple of 32), reduction length (TMA zero-fills beyond the tensor)
     int ldo;             // leading dimension of out and aux (floats)
+    int tl_slot;         // timeline slot (debug builds only)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,12 +92,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout; version 1 = Blackwell)
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {   // K-major, SWIZZLE_128B: 8-row groups 1024 B apart
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {  // MN-major, SWIZZLE_128B_BASE32B: 32-float chunks 4096 B apart, 4-row k groups 512 B apart
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+// MN-major, SWIZZLE_128B_BASE32B: 32-float column chunks `lbo` bytes apart (= one TMA box of WBK rows x 128 B), 4-row k groups 512 B apart
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, dense, M = 128
 __host__ __device__ constexpr uint32_t idesc_tf32(int n, bool mn_major) {
@@ -113,6 +140,14 @@ __device__ __forceinline__ float lo_trunc(float x) {
 }
 __device__ __forceinline__ float4 lo_trunc4(const float4 x) {
     return make_float4(lo_trunc(x.x), lo_trunc(x.y), lo_trunc(x.z), lo_trunc(x.w));
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -193,16 +228,20 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL_SET(0, 0, tl_now());
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            TL_DECL(w_empty);
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    TL_T0(t0);
                     mbar_wait(&empty[s], ph ^ 1);
+                    TL_ACC(w_empty, t0);
                     const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
                     mbar_expect_tx(&full[s], S::A_BYTES + 2 * S::B_BYTES);
                     tma_load_2d(&mA, &full[s], st, kb * BK, m0);
@@ -210,20 +249,29 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
                     tma_load_2d(&mBl, &full[s], st + 2 * S::A_BYTES + S::B_BYTES, kb * BK, n0);
                 }
             }
+            TL_SET(0, 1, tl_now());
+            TL_SET(0, 2, w_empty);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_tf32(BN, false);
+            TL_DECL(w_tempty); TL_DECL(w_full); TL_DECL(w_conv);
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
                 const uint32_t a = (NBUF == 2) ? (tl & 1) : 0, aph = (NBUF == 2) ? ((tl >> 1) & 1) : (tl & 1);
+                TL_T0(t0);
                 mbar_wait(&tempty[a], aph ^ 1);  // the epilogue has drained this accumulator set
+                TL_ACC(w_tempty, t0);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    TL_T0(t1);
                     mbar_wait(&full[s], ph);   // TMA: raw A (= hi operand) and the split B tiles
+                    TL_ACC(w_full, t1);
+                    TL_T0(t2);
                     mbar_wait(&conv[s], ph);   // converter warps: A lo
+                    TL_ACC(w_conv, t2);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES,
                                    b_lo = b_hi + S::B_BYTES;
@@ -240,6 +288,7 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
                 }
                 umma_commit(&tfull[a]);      // accumulator complete
             }
+            TL_SET(0, 3, w_tempty); TL_SET(0, 4, w_full); TL_SET(0, 5, w_conv);
         }
     } else if (warp >= CONV_T0 / 32) {
         // ===== converter warps: A lo = tf32(x - trunc13(x)), same swizzled offsets as the raw tile (elementwise) =====
@@ -250,13 +299,12 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
             for (int kb = 0; kb < nk; ++kb, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&full[s], ph);
-                const float4* raw = reinterpret_cast<const float4*>(smem + s * S::STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE_BYTES + S::A_BYTES);
+                const uint32_t raw = smem_u32(smem + s * S::STAGE_BYTES) + 16 * t, lo = raw + S::A_BYTES;
                 float4 x[VEC];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) x[i] = raw[t + i * 32 * CONV_WARPS];
+                for (int i = 0; i < VEC; ++i) x[i] = lds_v4(raw + i * 512 * CONV_WARPS);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) lo[t + i * 32 * CONV_WARPS] = lo_trunc4(x[i]);
+                for (int i = 0; i < VEC; ++i) sts_v4(lo + i * 512 * CONV_WARPS, lo_trunc4(x[i]));
                 fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&conv[s]);
             }
@@ -265,11 +313,14 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
         // ===== epilogue warps: TMEM lane quarter q = warp % 4, column group cg = (warp - 2) / 4 =====
         const int q = warp & 3, cg = (warp - 2) >> 2;
         constexpr int CHUNKS = BN / 32, PER = CHUNKS / (EPI_WARPS / 4) > 0 ? CHUNKS / (EPI_WARPS / 4) : 1;
+        TL_DECL(w_tfull);
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
             const uint32_t a = (NBUF == 2) ? (tl & 1) : 0, aph = (NBUF == 2) ? ((tl >> 1) & 1) : (tl & 1);
+            TL_T0(t0);
             mbar_wait(&tfull[a], aph);
+            TL_ACC(w_tfull, t0);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int row = m0 + q * 32 + lane;
             const int nacc_used = nk < NACC ? nk : NACC;
@@ -339,34 +390,38 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
         }
+        if (threadIdx.x == 64) TL_SET(0, 6, w_tfull);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (threadIdx.x == 0) TL_SET(0, 7, tl_now());
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
 }
 
 // ---- weight gradient: D[Nout, Kin] += sum over rows m of dY[m, Nout]^T X[m, Kin] ------------------------------------
 struct WgradArgs {
-    float* D;         // [Nout, ldd] fp32, accumulated with atomics (zeroed by the caller)
+    float* P;         // partial tiles [tile = blockIdx.z * gridDim.y + blockIdx.y][part = blockIdx.x][128][BN] fp32 (plain coalesced
+                      // stores; k_wgrad_reduce sums the parts - 148 CTAs adding into one tile with atomics cost 10-55 us per launch)
     int M, Nout, Kin; // Kin = columns stored (<= padded width covered by the tensor map boxes)
-    int ldd;
     int chunk;        // rows per CTA along blockIdx.x (multiple of 32)
+    int tl_slot;      // timeline slot (debug builds only)
 };
 
 // Each CTA owns ONE output tile and a contiguous range of `chunk` rows of the reduction (so a single wave of ~148 CTAs
-// covers the problem and every tile element receives one atomic per CTA of its tile).  To keep the truncating TMEM
-// accumulation chains short, k-blocks rotate over NACC = 512 / BN (<= 4) accumulators that the epilogue adds with
-// round-to-nearest FADDs before the atomics.
+// covers the problem) and stores its partial tile; k_wgrad_reduce (learner_kernels.cu) sums the parts of all six weight
+// gradients of an epoch in one launch.  To keep the truncating TMEM accumulation chains short, k-blocks rotate over
+// NACC = 512 / BN (<= 4) accumulators that the epilogue adds with round-to-nearest FADDs.
 static constexpr int WG_CONV_WARPS = 8;
 static constexpr int WG_CONV_T0 = 192;                       // TMA warp, MMA warp, 4 epilogue warps, then the converters
 static constexpr int WG_THREADS = WG_CONV_T0 + 32 * WG_CONV_WARPS;
-template <int BN, int STAGES>
+template <int BN, int STAGES, int WBK>   // WBK = rows (samples) per pipeline stage: 16 or 32
 __global__ void __launch_bounds__(WG_THREADS, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUtensorMap mX, const WgradArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // stage layout: [dY raw -> hi (rounded in place)][X raw = hi][dY lo][X lo]
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, RAW_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = 2 * RAW_BYTES;
+    constexpr int A_BYTES = BM * WBK * 4, B_BYTES = BN * WBK * 4, RAW_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = 2 * RAW_BYTES;
+    constexpr int BOX_BYTES = WBK * 128;   // one TMA box: WBK rows of 32 floats
     constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);
     constexpr uint32_t TCOLS = NACC * BN < 32 ? 32 : NACC * BN;
     uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -377,7 +432,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUten
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r_begin = blockIdx.x * g.chunk, r_end = min(g.M, r_begin + g.chunk);
     const int n0 = blockIdx.y * BM, k0 = blockIdx.z * BN;
-    const int nk = (r_end > r_begin) ? (r_end - r_begin + BK - 1) / BK : 0;
+    const int nk = (r_end > r_begin) ? (r_end - r_begin + WBK - 1) / WBK : 0;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 32 * WG_CONV_WARPS); }
         mbar_init(tfull, 1);
@@ -391,42 +446,53 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUten
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL_SET(1, 0, tl_now());
     if (nk > 0) {
         if (warp == 0) {
             if (lane == 0) {
+                TL_DECL(w_empty);
                 for (int kb = 0; kb < nk; ++kb) {
                     const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
+                    TL_T0(t0);
                     mbar_wait(&empty[s], ph ^ 1);
+                    TL_ACC(w_empty, t0);
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
                     mbar_expect_tx(&full[s], RAW_BYTES);
-                    const int r = r_begin + kb * BK;
-#pragma unroll
-                    for (int c = 0; c < BM / 32; ++c) tma_load_2d(&mY, &full[s], st + c * 4096, n0 + c * 32, r);
-#pragma unroll
-                    for (int c = 0; c < BN / 32; ++c) tma_load_2d(&mX, &full[s], st + A_BYTES + c * 4096, k0 + c * 32, r);
+                    const int r = r_begin + kb * WBK;
+                    // 3-D maps (32 floats, rows, 32-float column chunks): ONE bulk copy lands all chunks of a tile, chunk c at c * BOX_BYTES
+                    tma_load_3d(&mY, &full[s], st, 0, r, n0 / 32);
+                    tma_load_3d(&mX, &full[s], st + A_BYTES, 0, r, k0 / 32);
                 }
+                TL_SET(1, 1, tl_now());
+                TL_SET(1, 2, w_empty);
             }
         } else if (warp == 1) {
             if (lane == 0) {
                 constexpr uint32_t idesc = idesc_tf32(BN, true);
+                TL_DECL(w_full); TL_DECL(w_conv);
                 for (int kb = 0; kb < nk; ++kb) {
                     const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
+                    TL_T0(t1);
                     mbar_wait(&full[s], ph);
+                    TL_ACC(w_full, t1);
+                    TL_T0(t2);
                     mbar_wait(&conv[s], ph);
+                    TL_ACC(w_conv, t2);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES, a_lo = a_hi + RAW_BYTES, b_lo = a_lo + A_BYTES;
                     const uint32_t tacc = tmem_base + (uint32_t)(kb % NACC) * BN;
                     const bool first = kb < NACC;  // first k-block of this accumulator overwrites it
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
+                    for (int k = 0; k < WBK / 8; ++k) {
                         const uint32_t off = k * 1024;  // 8 rows (samples) = two 4-row swizzle groups
-                        umma_tf32(tacc, desc_mnmajor(a_lo + off), desc_mnmajor(b_hi + off), idesc, (first && k == 0) ? 0u : 1u);
-                        umma_tf32(tacc, desc_mnmajor(a_hi + off), desc_mnmajor(b_lo + off), idesc, 1u);
-                        umma_tf32(tacc, desc_mnmajor(a_hi + off), desc_mnmajor(b_hi + off), idesc, 1u);
+                        umma_tf32(tacc, desc_mnmajor(a_lo + off, BOX_BYTES), desc_mnmajor(b_hi + off, BOX_BYTES), idesc, (first && k == 0) ? 0u : 1u);
+                        umma_tf32(tacc, desc_mnmajor(a_hi + off, BOX_BYTES), desc_mnmajor(b_lo + off, BOX_BYTES), idesc, 1u);
+                        umma_tf32(tacc, desc_mnmajor(a_hi + off, BOX_BYTES), desc_mnmajor(b_hi + off, BOX_BYTES), idesc, 1u);
                     }
                     umma_commit(&empty[s]);
                 }
                 umma_commit(tfull);
+                TL_SET(1, 3, tl_now()); TL_SET(1, 4, w_full); TL_SET(1, 5, w_conv);
             }
         } else if (warp >= WG_CONV_T0 / 32) {
             // ===== converter warps: split both operands in shared memory (elementwise, layout-agnostic) =====
@@ -437,28 +503,30 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUten
             for (int kb = 0; kb < nk; ++kb) {
                 const uint32_t s = kb % STAGES, ph = (kb / STAGES) & 1;
                 mbar_wait(&full[s], ph);
-                float4* raw = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + RAW_BYTES);
+                const uint32_t raw = smem_u32(smem + s * STAGE_BYTES) + 16 * t, lo = raw + RAW_BYTES;
+#ifndef B200_NO_CONV
                 float4 x[A_VEC + B_VEC];
 #pragma unroll
-                for (int i = 0; i < A_VEC + B_VEC; ++i) x[i] = raw[t + i * NT];
+                for (int i = 0; i < A_VEC + B_VEC; ++i) x[i] = lds_v4(raw + i * 16 * NT);
 #pragma unroll
                 for (int i = 0; i < A_VEC; ++i) {   // dY: hi rounded to nearest, written back in place
                     const float4 h = make_float4(tf32_rna(x[i].x), tf32_rna(x[i].y), tf32_rna(x[i].z), tf32_rna(x[i].w));
-                    raw[t + i * NT] = h;
-                    lo[t + i * NT] = make_float4(tf32_rna(x[i].x - h.x), tf32_rna(x[i].y - h.y), tf32_rna(x[i].z - h.z), tf32_rna(x[i].w - h.w));
+                    sts_v4(raw + i * 16 * NT, h);
+                    sts_v4(lo + i * 16 * NT, make_float4(tf32_rna(x[i].x - h.x), tf32_rna(x[i].y - h.y), tf32_rna(x[i].z - h.z), tf32_rna(x[i].w - h.w)));
                 }
 #pragma unroll
-                for (int i = A_VEC; i < A_VEC + B_VEC; ++i) lo[t + i * NT] = lo_trunc4(x[i]);   // X: the tensor core truncates the raw word
+                for (int i = A_VEC; i < A_VEC + B_VEC; ++i) sts_v4(lo + i * 16 * NT, lo_trunc4(x[i]));   // X: the tensor core truncates the raw word
+#endif
                 fence_async_smem();
                 mbar_arrive(&conv[s]);
             }
         } else {
             const int q = warp & 3;
             mbar_wait(tfull, 0);
+            if (threadIdx.x == 64) TL_SET(1, 6, tl_now());
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const int row = n0 + q * 32 + lane;
             const int nacc_used = nk < NACC ? nk : NACC;
+            float* dst = g.P + (((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * BM + (q * 32 + lane)) * BN;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
@@ -471,18 +539,14 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUten
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
                 }
-                if (row < g.Nout) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = k0 + c * 32 + j;
-                        if (col < g.Kin) atomicAdd(g.D + (size_t)row * g.ldd + col, acc[j]);
-                    }
-                }
+                for (int j = 0; j < 32; j += 8) stg_v8(dst + c * 32 + j, acc + j);
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (threadIdx.x == 0) TL_SET(1, 7, tl_now());
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
 }
 
@@ -525,6 +589,34 @@ struct MapCache {
         }
         return &(maps[key] = m);
     }
+    // MN-major operand tiles of k_tc_wgrad: the fp32 matrix [rows, cols] (cols a multiple of 32, leading dimension ld) viewed as
+    // (32 floats, rows, cols / 32); box = (32, box_rows, box_chunks) with the BASE32B swizzle
+    const CUtensorMap* get3(const float* base, int rows, int cols, int ld, int box_rows, int box_chunks) {
+        if (!enc) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+                error = "cuTensorMapEncodeTiled is unavailable";
+                return nullptr;
+            }
+            enc = (EncodeTiledFn)fn;
+        }
+        auto key = std::make_tuple((const void*)base, rows, cols, ld, box_rows, 1000 + box_chunks);
+        auto it = maps.find(key);
+        if (it != maps.end()) return &it->second;
+        CUtensorMap m;
+        cuuint64_t gdim[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+        cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, 128};
+        cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
+        cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            error = "cuTensorMapEncodeTiled (3-D) failed";
+            return nullptr;
+        }
+        return &(maps[key] = m);
+    }
 };
 
 template <int BN, int STAGES, int EPI, int NACC = 1>
@@ -543,17 +635,17 @@ inline cudaError_t launch_rowmajor(const CUtensorMap* A, const CUtensorMap* Bh, 
     return cudaPeekAtLastError();
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int WBK>
 inline cudaError_t launch_wgrad(const CUtensorMap* Y, const CUtensorMap* X, const WgradArgs& g, int kin_padded, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 256 + 1024;
+    constexpr int SMEM = STAGES * (2 * BM * WBK * 4 + 2 * BN * WBK * 4) + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        const cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad<BN, STAGES, WBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     dim3 grid((g.M + g.chunk - 1) / g.chunk, (g.Nout + BM - 1) / BM, (kin_padded + BN - 1) / BN);
-    k_tc_wgrad<BN, STAGES><<<grid, WG_THREADS, SMEM, st>>>(*Y, *X, g);
+    k_tc_wgrad<BN, STAGES, WBK><<<grid, WG_THREADS, SMEM, st>>>(*Y, *X, g);
     return cudaPeekAtLastError();
 }
 

@@ -44,12 +44,14 @@ enum { DS_ADV_SUM = B200_DS_ADV_SUM, DS_ADV_SUMSQ = B200_DS_ADV_SUMSQ, DS_ADV_CO
 
 // Workspace (offsets in floats).  Activations and their gradients are plain fp32 (4 B / element): the tcgen05 GEMMs split
 // them into tf32 (hi, lo) pairs inside shared memory (gemm_tc.cuh).  Only the weights keep pre-split copies ("h"/"l").
+#define WP_MAX_CTAS 160   // >= CTAs of one k_tc_wgrad launch (one wave: <= SM count)
 struct Workspace {
-    size_t Xa, Xc;                                      // packed inputs [M,48], [M+N,64]
+    size_t Xa, Xc;                                      // packed inputs [M,64] (obs, zero padded), [M+N,64] (obs, priv, zero padded)
     size_t C1, C2, C3;                                  // critic post-ELU activations [M+N,256],[M+N,256],[M+N,128]
     size_t A1, A2, A3;                                  // actor post-ELU activations [M,256],[M,128],[M,128]
     size_t V, MU, ADV, RET, DV, DMU;
     size_t G1, G2;                                      // gradient ping-pong [M,256]
+    size_t WP[6];                                       // partial weight-gradient tiles of the six k_tc_wgrad launches of an epoch
     size_t Wc0h, Wc0l, Wc1h, Wc1l, Wc2h, Wc2l, Wa0h, Wa0l, Wa1h, Wa1l, Wa2h, Wa2l;   // split weights, K padded to 64 for layer 0
     size_t Wc1Th, Wc1Tl, Wc2Th, Wc2Tl, Wa1Th, Wa1Tl, Wa2Th, Wa2Tl;                  // transposed split weights for dgrad
     size_t LXa, LXc, L1, L2, L3, LV, LMU;               // rollout-sized (N rows) fp32 buffers of the mma.sync path
@@ -61,11 +63,12 @@ static Workspace make_workspace(int T, int N) {
     size_t o = 0;
     auto take = [&](size_t cnt) { size_t r = o; o += (cnt + 255) & ~(size_t)255; return r; };  // 1 KiB aligned (TMA needs 16 B)
     const size_t Mc = M + n;  // the critic also evaluates the N post-rollout observations (last_values, utils/runner.py:133) in the same pass
-    w.Xa = take(M * 48); w.Xc = take(Mc * 64);
+    w.Xa = take(M * 64); w.Xc = take(Mc * 64);
     w.C1 = take(Mc * 256); w.C2 = take(Mc * 256); w.C3 = take(Mc * 128);
     w.A1 = take(M * 256); w.A2 = take(M * 128); w.A3 = take(M * 128);
     w.V = take(Mc); w.MU = take(M * 12); w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
     w.G1 = take(M * 256); w.G2 = take(M * 256);
+    for (int j = 0; j < 6; ++j) w.WP[j] = take((size_t)WP_MAX_CTAS * 128 * 256);
     w.Wc0h = take(256 * 64); w.Wc0l = take(256 * 64); w.Wc1h = take(256 * 256); w.Wc1l = take(256 * 256);
     w.Wc2h = take(128 * 256); w.Wc2l = take(128 * 256); w.Wa0h = take(256 * 64); w.Wa0l = take(256 * 64);
     w.Wa1h = take(128 * 256); w.Wa1l = take(128 * 256); w.Wa2h = take(128 * 128); w.Wa2l = take(128 * 128);
@@ -107,7 +110,7 @@ __global__ void k_pack_inputs(const float* __restrict__ obs, const float* __rest
     if (c < 47) v = obs[r * 47 + c];
     else if (c < 61 && priv) v = priv[r * 14 + (c - 47)];
     if (Xc) Xc[idx] = v;
-    if (Xa && c < 48) Xa[r * 48 + c] = (c < 47) ? v : 0.0f;
+    if (Xa) Xa[idx] = (c < 47) ? v : 0.0f;
 }
 
 __device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
@@ -732,6 +735,8 @@ struct GemmProfile {
     double flops[PK_COUNT] = {0.0, 0.0, 0.0};
 } g_prof;
 
+static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
+static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
 static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC) {
     if (!g_prof.on || g_prof.used >= GemmProfile::kMax) return;
     cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
@@ -803,6 +808,45 @@ static cudaError_t bias_grad(const float* dY, const float* dYl, int ld, int C, i
     return cudaPeekAtLastError();
 }
 
+// ---- reduction of the k_tc_wgrad partial tiles: dW[row, col] += sum over parts, all six weight matrices in one launch ----
+struct WgradJob {
+    const float* P;   // [tiles_y * tiles_z][parts][128][bn]
+    float* D;         // [n_out, ldd]
+    int parts, bn, tiles_y, tiles_z, n_out, k_valid, ldd;
+    int first;        // first linear output element of this job in the launch
+};
+struct WgradJobs {
+    WgradJob job[6];
+    int count, total;
+};
+#define WR_SLICES 4
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradJobs J) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= J.total) return;
+    int j = 0;
+#pragma unroll
+    for (int t = 1; t < 6; ++t)
+        if (t < J.count && idx >= J.job[t].first) j = t;
+    const WgradJob& w = J.job[j];
+    const int e = idx - w.first;
+    const int row = e / w.k_valid, col = e - row * w.k_valid;
+    const int ty = row >> 7, tz = col / w.bn;
+    const float* src = w.P + ((size_t)(tz * w.tiles_y + ty) * w.parts * 128 + (row & 127)) * w.bn + (col - tz * w.bn);
+    const size_t stride = (size_t)128 * w.bn;
+    const int per = (w.parts + WR_SLICES - 1) / WR_SLICES;
+    const int p0 = blockIdx.y * per, p1 = min(w.parts, p0 + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int pp = p0;
+    for (; pp + 4 <= p1; pp += 4) {
+        s0 += src[(size_t)pp * stride];
+        s1 += src[(size_t)(pp + 1) * stride];
+        s2 += src[(size_t)(pp + 2) * stride];
+        s3 += src[(size_t)(pp + 3) * stride];
+    }
+    for (; pp < p1; ++pp) s0 += src[(size_t)pp * stride];
+    if (p1 > p0) atomicAdd(w.D + (size_t)row * w.ldd + col, (s0 + s1) + (s2 + s3));
+}
+
 // ---- tcgen05 layers (gemm_tc.cuh) over pre-split operands ----------------------------------------------------------
 #define TC_MAP(var, ptr, rows, cols, ld, box, kmajor)                                                      \
     const CUtensorMap* var = p->maps->get(ptr, rows, cols, ld, box, kmajor);                               \
@@ -812,12 +856,12 @@ static cudaError_t bias_grad(const float* dY, const float* dYl, int ld, int C, i
 static int tc_fwd(const B200Ppo* p, const float* X, int k, int ldx, const float* Wh, const float* Wl, int k_pad, const float* b,
                   float* Y, int n, int n_out, cudaStream_t st, bool accurate = false) {
     const int bn = (n_out >= 256 && !accurate) ? 256 : 128;
-    TC_MAP(mA, X, n, k, ldx, tc::BM, true);
+    TC_MAP(mA, X, n, ldx, ldx, tc::BM, true);   // all ldx columns are stored (zero padded beyond k)
     TC_MAP(mBh, Wh, n_out, k_pad, k_pad, bn, true);
     TC_MAP(mBl, Wl, n_out, k_pad, k_pad, bn, true);
     tc::RowArgs g{};
     g.out = Y; g.bias = b; g.aux = nullptr; g.colsum = nullptr;
-    g.M = n; g.Nout = n_out; g.K = k_pad; g.ldo = n_out;
+    g.M = n; g.Nout = n_out; g.K = k_pad; g.ldo = n_out; g.tl_slot = tl_next();
     prof_begin(st, 2.0 * n * (double)n_out * k, PK_TC_ROW);
     const cudaError_t e = accurate    ? tc::launch_rowmajor<128, 3, tc::EPI_FWD, 4>(mA, mBh, mBl, g, p->num_sms, st)
                           : (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_FWD>(mA, mBh, mBl, g, p->num_sms, st)
@@ -836,7 +880,7 @@ static int tc_dgrad(const B200Ppo* p, const float* dY, int n_out, const float* W
     TC_MAP(mBl, WTl, k_in, n_out, n_out, bn, true);
     tc::RowArgs g{};
     g.out = dX; g.bias = nullptr; g.aux = H; g.colsum = colsum;
-    g.M = n; g.Nout = k_in; g.K = n_out; g.ldo = k_in;
+    g.M = n; g.Nout = k_in; g.K = n_out; g.ldo = k_in; g.tl_slot = tl_next();
     prof_begin(st, 2.0 * n * (double)n_out * k_in, PK_TC_ROW);
     const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st)
                                       : tc::launch_rowmajor<128, 3, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st);
@@ -845,29 +889,47 @@ static int tc_dgrad(const B200Ppo* p, const float* dY, int n_out, const float* W
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<dgrad>");
     return B200_OK;
 }
-// dW [n_out, k_valid] += dY [n, n_out]^T X [n, k_cols]   (k_pad = 64 / 128 / 256 = tile width along k)
-static int tc_wgrad(const B200Ppo* p, const float* dY, int n_out, const float* X, int k_cols, int k_pad, int k_valid, float* dW, int n,
-                    cudaStream_t st) {
-    TC_MAP(mY, dY, n, n_out, n_out, 32, false);
-    TC_MAP(mX, X, n, k_cols, k_cols, 32, false);
+// dW [n_out, k_valid] += dY [n, n_out]^T X [n, k_cols]   (k_pad = 64 / 128 / 256 = tile width along k): launches the partial-tile
+// GEMM into workspace region `slot` and appends the reduction job; wgrad_reduce() then sums all pending jobs in one launch
+static int tc_wgrad(const B200Ppo* p, WgradJobs& jobs, int slot, const float* dY, int n_out, const float* X, int k_cols, int k_pad,
+                    int k_valid, float* dW, int n, cudaStream_t st) {
+    const int wbk = (k_pad == 256) ? 16 : 32;   // rows per pipeline stage (= TMA box rows)
+    const int bn = k_pad >= 256 ? 256 : k_pad;
+    const CUtensorMap* mY = p->maps->get3(dY, n, n_out, n_out, wbk, tc::BM / 32);
+    const CUtensorMap* mX = p->maps->get3(X, n, k_cols, k_cols, wbk, bn / 32);
+    if (!mY || !mX) return set_error(B200_ERR_CUDA, p->maps->error ? p->maps->error : "tensor map creation failed");
     tc::WgradArgs g{};
-    g.D = dW; g.M = n; g.Nout = n_out; g.Kin = k_valid; g.ldd = k_valid;
+    g.P = p->ws + p->w.WP[slot]; g.M = n; g.Nout = n_out; g.Kin = k_valid; g.tl_slot = tl_next();
+    const int tiles_y = (n_out + tc::BM - 1) / tc::BM, tiles_z = (k_pad + bn - 1) / bn;
+    int parts;
     {
         // one wave: the CTAs of an output tile split the rows evenly (multiples of the 32-row k-block)
-        const int tiles = ((n_out + tc::BM - 1) / tc::BM) * ((k_pad + (k_pad >= 256 ? 256 : k_pad) - 1) / (k_pad >= 256 ? 256 : k_pad));
-        const int per_tile = p->num_sms / tiles > 0 ? p->num_sms / tiles : 1;
+        const int tiles = tiles_y * tiles_z;
+        const int sms = p->num_sms < WP_MAX_CTAS ? p->num_sms : WP_MAX_CTAS;
+        const int per_tile = sms / tiles > 0 ? sms / tiles : 1;
         const int rows = (n + per_tile - 1) / per_tile;
         g.chunk = ((rows + 31) / 32) * 32;
+        parts = (n + g.chunk - 1) / g.chunk;
     }
+    WgradJob& j = jobs.job[jobs.count];
+    j.P = g.P; j.D = dW; j.parts = parts; j.bn = bn; j.tiles_y = tiles_y; j.tiles_z = tiles_z; j.n_out = n_out; j.k_valid = k_valid;
+    j.ldd = k_valid; j.first = jobs.total;
+    jobs.count += 1;
+    jobs.total += n_out * k_valid;
     prof_begin(st, 2.0 * n * (double)n_out * k_valid, PK_TC_WGRAD);
     cudaError_t e;
-    if (k_pad == 256) e = tc::launch_wgrad<256, 2>(mY, mX, g, k_pad, st);
-    else if (k_pad == 128) e = tc::launch_wgrad<128, 3>(mY, mX, g, k_pad, st);
-    else e = tc::launch_wgrad<64, 3>(mY, mX, g, k_pad, st);
+    if (k_pad == 256) e = tc::launch_wgrad<256, 4, 16>(mY, mX, g, k_pad, st);
+    else if (k_pad == 128) e = tc::launch_wgrad<128, 3, 32>(mY, mX, g, k_pad, st);
+    else e = tc::launch_wgrad<64, 4, 32>(mY, mX, g, k_pad, st);
     prof_end(st);
     g_launches += 1;
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_wgrad");
     return B200_OK;
+}
+static int wgrad_reduce(const WgradJobs& jobs, cudaStream_t st) {
+    k_wgrad_reduce<<<dim3((jobs.total + 255) / 256, WR_SLICES), 256, 0, st>>>(jobs);
+    g_launches += 1;
+    return launch_status("k_wgrad_reduce");
 }
 // split copies of the six hidden-layer weight matrices (they change every epoch)
 static int weight_prep(const B200Ppo* p, cudaStream_t st) {
@@ -893,7 +955,7 @@ static int actor_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
     int rc;
-    if ((rc = tc_fwd(p, ws + w.Xa, 48, 48, ws + w.Wa0h, ws + w.Wa0l, 64, p->P(P_AB0), ws + w.A1, M, 256, st, true))) return rc;
+    if ((rc = tc_fwd(p, ws + w.Xa, 47, 64, ws + w.Wa0h, ws + w.Wa0l, 64, p->P(P_AB0), ws + w.A1, M, 256, st, true))) return rc;
     if ((rc = tc_fwd(p, ws + w.A1, 256, 256, ws + w.Wa1h, ws + w.Wa1l, 256, p->P(P_AB1), ws + w.A2, M, 128, st, true))) return rc;
     if ((rc = tc_fwd(p, ws + w.A2, 128, 128, ws + w.Wa2h, ws + w.Wa2l, 128, p->P(P_AB2), ws + w.A3, M, 128, st, true))) return rc;
     k_actor_head<<<1184, 256, 0, st>>>(ws + w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + w.MU);
@@ -904,7 +966,7 @@ static int critic_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
     int rc;
-    if ((rc = tc_fwd(p, ws + w.Xc, 64, 64, ws + w.Wc0h, ws + w.Wc0l, 64, p->P(P_CB0), ws + w.C1, M, 256, st))) return rc;
+    if ((rc = tc_fwd(p, ws + w.Xc, 61, 64, ws + w.Wc0h, ws + w.Wc0l, 64, p->P(P_CB0), ws + w.C1, M, 256, st))) return rc;
     if ((rc = tc_fwd(p, ws + w.C1, 256, 256, ws + w.Wc1h, ws + w.Wc1l, 256, p->P(P_CB1), ws + w.C2, M, 256, st))) return rc;
     if ((rc = tc_fwd(p, ws + w.C2, 256, 256, ws + w.Wc2h, ws + w.Wc2l, 256, p->P(P_CB2), ws + w.C3, M, 128, st))) return rc;
     k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
@@ -1079,6 +1141,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     const int M = p->cfg.horizon * p->cfg.num_envs;
     float *MU = ws + w.MU, *DV = ws + w.DV, *DMU = ws + w.DMU;
     float *G1 = ws + w.G1, *G2 = ws + w.G2;
+    WgradJobs jobs{};
     int rc = actor_forward_tc(p, M, st);
     if (rc != B200_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(p->grads, 0, NPARAMS_PADDED * sizeof(float), st));
@@ -1093,21 +1156,21 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     g_launches += 1;
     if ((rc = launch_status("k_actor_head_bwd")) != B200_OK) return rc;
     // (each bias gradient = column sum of the layer's output gradient, accumulated by the kernel that produces it)
-    if ((rc = tc_wgrad(p, G1, 128, ws + w.A2, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
+    if ((rc = tc_wgrad(p, jobs, 0, G1, 128, ws + w.A2, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
     if ((rc = tc_dgrad(p, G1, 128, ws + w.Wa2Th, ws + w.Wa2Tl, 128, ws + w.A2, G2, p->G(P_AB1), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G2, 128, ws + w.A1, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
+    if ((rc = tc_wgrad(p, jobs, 1, G2, 128, ws + w.A1, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
     if ((rc = tc_dgrad(p, G2, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1, G1, p->G(P_AB0), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G1, 256, ws + w.Xa, 48, 64, 47, p->G(P_AW0), M, st))) return rc;
+    if ((rc = tc_wgrad(p, jobs, 2, G1, 256, ws + w.Xa, 64, 64, 47, p->G(P_AW0), M, st))) return rc;
     // ---- critic backward
     k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2));
     g_launches += 1;
     if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
-    if ((rc = tc_wgrad(p, G1, 128, ws + w.C2, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
+    if ((rc = tc_wgrad(p, jobs, 3, G1, 128, ws + w.C2, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
     if ((rc = tc_dgrad(p, G1, 128, ws + w.Wc2Th, ws + w.Wc2Tl, 256, ws + w.C2, G2, p->G(P_CB1), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G2, 256, ws + w.C1, 256, 256, 256, p->G(P_CW1), M, st))) return rc;
+    if ((rc = tc_wgrad(p, jobs, 4, G2, 256, ws + w.C1, 256, 256, 256, p->G(P_CW1), M, st))) return rc;
     if ((rc = tc_dgrad(p, G2, 256, ws + w.Wc1Th, ws + w.Wc1Tl, 256, ws + w.C1, G1, p->G(P_CB0), M, st))) return rc;
-    if ((rc = tc_wgrad(p, G1, 256, ws + w.Xc, 64, 64, 61, p->G(P_CW0), M, st))) return rc;
-    return B200_OK;
+    if ((rc = tc_wgrad(p, jobs, 5, G1, 256, ws + w.Xc, 64, 64, 61, p->G(P_CW0), M, st))) return rc;
+    return wgrad_reduce(jobs, st);
 }
 
 int b200_ppo_epoch(B200Ppo* p, const float* actions, float* rewards, const uint8_t* dones, const uint8_t* time_outs,
@@ -1131,6 +1194,16 @@ int b200_ppo_apply(B200Ppo* p, void* stream) {
 }
 
 long long b200_launch_count(void) { return g_launches; }
+
+#ifdef B200_TC_TIMELINE
+/* debug builds only (tools/tc_timeline.py): per-CTA timelines of the tcgen05 GEMM launches since the last reset, in launch order */
+int b200_tc_timeline_reset(void) { g_tl_slot = 0; return B200_OK; }
+int b200_tc_timeline_read(unsigned long long* out /* [TL_SLOTS][160][8] */) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out, tc::g_tl, sizeof(unsigned long long) * TL_SLOTS * 160 * 8));
+    return g_tl_slot;
+}
+#endif
 
 int b200_profile_gemm(int enable) {
     if (enable && !g_prof.ev) {
