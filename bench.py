@@ -44,7 +44,8 @@ def parse():
 def config_dict(args, world):
     return {"workload": WORKLOAD, "num_envs_per_gpu": args.num_envs, "total_envs": args.num_envs * world, "horizon": 24,
             "mini_epochs": 20, "terrain": "plane", "parallelism": f"env-sharded dp{world}",
-            "l2": "working set (722 MB learner workspace per GPU) is larger than the 126 MB L2; no flush needed",
+            "l2": "working set (the learner streams ~1.9 GB of fp32 activations per epoch through a >400 MB workspace per GPU) is larger than "
+                  "the 126 MB L2; no flush needed",
             "rollout_cuda_graph": bool(args.graphs)}
 
 
@@ -217,13 +218,16 @@ def b200_arm(args):
     lib.b200_profile_gemm(1)
     iteration()
     fams = {}
-    names = {0: "k_gemm3x (mma.sync 3xTF32: actor forward, 12-wide head, rollout policy)",
-             1: "k_tc_rowmajor (tcgen05/TMEM/TMA 3xTF32: MLP forward + dgrad with fused bias/ELU/ELU'/split epilogue)",
-             2: "k_tc_wgrad (tcgen05/TMEM/TMA 3xTF32, MN-major operands: MLP weight gradients)"}
+    names = {0: "k_gemm3x (mma.sync 3xTF32: b200_critic_value only)",
+             1: "k_tc_rowmajor (tcgen05/TMEM/TMA 3xTF32 with in-smem operand split: MLP forward + dgrad, fused bias/ELU/ELU' epilogue)",
+             2: "k_tc_wgrad (tcgen05/TMEM/TMA 3xTF32, MN-major operands, in-smem split: MLP weight gradients)"}
+    fam_bytes = {}
     for kind in (0, 1, 2):
-        ms_g, fl_g, n_g = C.c_double(), C.c_double(), C.c_int()
+        ms_g, fl_g, n_g, by_g = C.c_double(), C.c_double(), C.c_int(), C.c_double()
         lib.b200_profile_gemm_read(kind, C.byref(ms_g), C.byref(fl_g), C.byref(n_g))
+        lib.b200_profile_gemm_bytes(kind, C.byref(by_g))
         fams[kind] = (ms_g.value, fl_g.value, n_g.value)
+        fam_bytes[kind] = by_g.value
     lib.b200_profile_gemm(0)
     top = max(fams, key=lambda k: fams[k][0])
     ms_top, fl_top, n_top = fams[top]
@@ -239,13 +243,22 @@ def b200_arm(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(str(top))
     except Exception:
         pass
-    roofline = {"kernel": names[top], "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained",
+    # the family is bounded by whichever roofline it sits closer to: HBM (fp32 activations in / out, 4 B per element) or the
+    # tensor pipe (measured dense BF16 peak; the 3xTF32 split executes 3x the algorithmic FLOPs at half the BF16 rate)
+    peak_hbm = peaks.get("hbm_gbs", 6500.0)
+    gbs = fam_bytes[top] / (ms_top * 1e-3) / 1e9 if ms_top > 0 else 0.0
+    hbm_bound = gbs / peak_hbm >= achieved / peak_tf
+    roofline = {"kernel": names[top], "bound": "hbm" if hbm_bound else "tensor", "achieved": gbs if hbm_bound else achieved,
+                "peak": peak_hbm if hbm_bound else peak_tf, "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                "frac": gbs / peak_hbm if hbm_bound else achieved / peak_tf, "traffic": traffic,
+                "tensor": {"achieved_tflops": achieved, "peak_tflops": peak_tf, "frac": achieved / peak_tf},
+                "hbm": {"achieved_gbs": gbs, "peak_gbs": peak_hbm, "frac": gbs / peak_hbm, "algorithmic_bytes_per_step": fam_bytes[top]},
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained (measured)" if peaks else "fallback 6.5 TB/s, 1.4 PFLOP/s",
                 "launches_per_step": n_top, "algorithmic_tflop_per_step": fl_top / 1e12, "avg_launch_ms": ms_top / max(1, n_top),
                 "share_of_step": ms_top / ms_step,
                 "families": {names[k].split(" ")[0]: {"ms_per_step": fams[k][0], "algorithmic_tflop": fams[k][1] / 1e12, "launches": fams[k][2],
-                                                      "tflops": (fams[k][1] / (fams[k][0] * 1e-3) / 1e12 if fams[k][0] > 0 else 0.0)} for k in fams},
+                                                      "tflops": (fams[k][1] / (fams[k][0] * 1e-3) / 1e12 if fams[k][0] > 0 else 0.0),
+                                                      "gbs": (fam_bytes[k] / (fams[k][0] * 1e-3) / 1e9 if fams[k][0] > 0 else 0.0)} for k in fams},
                 "note": "algorithmic FLOPs = 2*rows*out*k once per product (the 3-term TF32 split executes 3x that on the tensor pipe); "
                         "peak is the measured dense BF16 figure (TF32 is nominally half of it)"}
 

@@ -37,7 +37,7 @@ namespace tc {
 // a device array that b200_tc_timeline_read copies out.  Compiled out of the product build.
 #ifdef B200_TC_TIMELINE
 #define TL_SLOTS 40
-__device__ unsigned long long g_tl[TL_SLOTS][160][8];
+__device__ unsigned long long g_tl[TL_SLOTS][160][12];
 __device__ __forceinline__ unsigned long long tl_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -135,8 +135,11 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 // lo half of the in-smem split: the tensor core truncates the raw fp32 word to tf32, so lo = x - trunc13(x) (exact, <= 13
 // significant bits), rounded to tf32
+__device__ __forceinline__ float tf32_rna_fast(float x) {   // round-half-away on the bit pattern (finite inputs): 2 ALU ops instead of cvt.rna's ~6
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ float lo_trunc(float x) {
-    return tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+    return tf32_rna_fast(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
 }
 __device__ __forceinline__ float4 lo_trunc4(const float4 x) {
     return make_float4(lo_trunc(x.x), lo_trunc(x.y), lo_trunc(x.z), lo_trunc(x.w));
@@ -181,112 +184,208 @@ __device__ __forceinline__ float elu_fast(float x) {
 static constexpr int EPI_WARPS = 16;                   // 4 per TMEM lane quarter, each takes a quarter of the tile's columns
 static constexpr int CONV_WARPS = 4;                   // in-smem lo converters of the A (activation) tile
 static constexpr int CONV_T0 = 64 + 32 * EPI_WARPS;    // first converter thread
-static constexpr int ROW_THREADS = CONV_T0 + 32 * CONV_WARPS;  // TMA warp + MMA warp + epilogue warps + converter warps
-template <int BN, int STAGES>
+static constexpr int TMAB_T0 = CONV_T0 + 32 * CONV_WARPS;       // the warp that streams the weight (B) tiles
+static constexpr int ROW_THREADS = TMAB_T0 + 32;  // TMA-A warp + MMA warp + epilogue warps + converter warps + TMA-B warp
+// ---- CTA-pair helpers (cta_group::2: two CTAs of a cluster on the two SMs of a TPC share one 256-row MMA) --------------------
+static constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the pair-rank bit of a shared::cluster address -> the leader (even) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* b) {   // arrive on this barrier's twin in the pair's leader CTA
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(b) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {   // waits for arrivals that may come from the peer CTA
+    uint32_t done;
+    const uint32_t a = smem_u32(b);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+// the load lands in THIS CTA's shared memory, its bytes are counted on the leader CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_m(int m, int n) {   // K-major operands, D = f32, A = B = tf32
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// PAIR = 1: a cluster of two CTAs works on a 256-row tile (cta_group::2, UMMA M = 256).  Each CTA stages its own 128 rows of A
+// and HALF of the B (weight) tile; the tensor cores of the two SMs exchange the B halves, so the per-CTA L2 -> shared-memory fill
+// per k-block drops from 16 + 2*32 KB to 16 + 2*16 KB (BN = 256) - the L2 slice throughput (~42 B/clk/SM) was the bound - and
+// a stage shrinks from 96 to 64 KB (3 stages instead of 2).  The leader CTA issues the MMAs; mbarriers that collect work of
+// both CTAs (B landed, A lo converted, accumulator drained) live in the leader and are signalled remotely by the peer.
+// Two rings: the raw activation tiles (from HBM: latency ~1.5 us under load, so NA = 4..8 stages of 16 KB keep 50-100 KB in
+// flight per SM) and the weight tiles + converted A lo tiles (from L2 / produced on chip: NB = 2..3 stages).
+template <int BN, int NA, int NB, int PAIR>
 struct RowSmem {
-    static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
-    // stage layout: [A raw fp32 = hi operand][A lo (converter)][B hi][B lo]
+    static constexpr int A_BYTES = BM * BK * 4, B_BYTES = (BN / (PAIR ? 2 : 1)) * BK * 4, BSTAGE_BYTES = A_BYTES + 2 * B_BYTES;
+    static constexpr int B_RING = NA * A_BYTES;                               // offset of the second ring
+    static constexpr int BAR = B_RING + NB * BSTAGE_BYTES;                   // offset of the mbarriers
+    static constexpr int TOTAL = BAR + 256 + 1024;                            // + barriers + alignment slack
+    // A ring stage: [A raw fp32 = hi operand];  B ring stage: [A lo (converter)][B hi][B lo]   (B = this CTA's half of the rows when PAIR)
 };
 
-// The epilogue is instruction-bound (ELU's expm1f, two tf32 roundings, address math: ~40 instructions per element),
-// so it gets 16 warps; each thread owns one output row (its TMEM lane) and 32 consecutive columns per step, which it
-// reads / writes as eight 16-byte vectors: every 32-byte sector is touched by two back-to-back instructions of the same
-// thread (L1 / L2 merge them), no shared-memory staging is needed.
-template <int BN, int STAGES, int EPI, int NACC>
+// The epilogue is instruction-bound (ELU, address math), so it gets 16 warps; each thread owns one output row (its TMEM
+// lane) and 32 consecutive columns per step, which it reads / writes as 32-byte vectors: one full sector per instruction, no
+// shared-memory staging is needed.
+template <int BN, int NA, int NB, int EPI, int NACC, int PAIR>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
 k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
               const RowArgs g) {
-    using S = RowSmem<BN, STAGES>;
+    using S = RowSmem<BN, NA, NB, PAIR>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(smem + STAGES * S::STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* conv = empty + STAGES;    // [STAGES] lo tile written
-    uint64_t* tfull = conv + STAGES;    // [2]
-    uint64_t* tempty = tfull + 2;       // [2]
+    uint64_t* afull = (uint64_t*)(smem + S::BAR);   // [NA] this CTA's raw A tile landed
+    uint64_t* aempty = afull + NA;      // [NA] the MMAs that read the raw A stage have completed
+    uint64_t* bfull = aempty + NA;      // [NB] B hi / lo landed                         (PAIR: leader's copy counts both CTAs' halves)
+    uint64_t* bempty = bfull + NB;      // [NB] the MMAs that read the B stage (and its A lo tile) have completed
+    uint64_t* conv = bempty + NB;       // [NB] A lo tile(s) written                      (PAIR: leader's copy collects both CTAs)
+    uint64_t* tfull = conv + NB;        // [2]
+    uint64_t* tempty = tfull + 2;       // [2]                                          (PAIR: leader's copy collects both CTAs)
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.Nout + BN - 1) / BN, tiles = m_tiles * n_tiles;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    constexpr int TM = PAIR ? 2 * BM : BM;                       // rows of a work tile
+    const int m_tiles = (g.M + TM - 1) / TM, n_tiles = (g.Nout + BN - 1) / BN, tiles = m_tiles * n_tiles;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int nk = (g.K + BK - 1) / BK;
-    // NACC accumulators per tile (k-blocks rotate over them; the epilogue adds them with round-to-nearest FADDs, which
-    // shortens the truncating TMEM accumulation chains NACC-fold); double-buffered across tiles when TMEM has room
+    // NACC = 2 ("accurate"): TMEM accumulation truncates, so the dominant a_hi*b_hi products get their own accumulator (chain
+    // length K/8) and the two small cross terms a second one; the epilogue adds them with a round-to-nearest FADD.  One MMA of
+    // N = 2*BN over the contiguous [B hi; B lo] tile produces a_hi*b_hi | a_hi*b_lo side by side (A hi is read once), a second
+    // MMA of N = BN adds a_lo*b_hi to the small half.  Accumulators are double-buffered across tiles when TMEM has room.
+    static_assert(NACC == 1 || (NACC == 2 && !PAIR && 2 * BN <= 256), "accumulator layout");
     constexpr int NBUF = (2 * BN * NACC <= 512) ? 2 : 1;
     constexpr uint32_t TCOLS = NBUF * BN * NACC;
     static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM allocation must be a power of two <= 512 columns");
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 32 * CONV_WARPS); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
+        for (int s = 0; s < NA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(&bfull[s], PAIR ? 2 : 1); mbar_init(&bempty[s], 1); mbar_init(&conv[s], 32 * CONV_WARPS * (PAIR ? 2 : 1));
+        }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS * (PAIR ? 2 : 1)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TL_SET(0, 0, tl_now());
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer A: raw activation tiles (HBM) =====
         if (lane == 0) {
             TL_DECL(w_empty);
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            for (int tile = worker; tile < tiles; tile += workers) {
+                const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
                 for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    const uint32_t s = it % NA, ph = (it / NA) & 1;
                     TL_T0(t0);
-                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_wait(&aempty[s], ph ^ 1);
                     TL_ACC(w_empty, t0);
-                    const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
-                    mbar_expect_tx(&full[s], S::A_BYTES + 2 * S::B_BYTES);
-                    tma_load_2d(&mA, &full[s], st, kb * BK, m0);
-                    tma_load_2d(&mBh, &full[s], st + 2 * S::A_BYTES, kb * BK, n0);
-                    tma_load_2d(&mBl, &full[s], st + 2 * S::A_BYTES + S::B_BYTES, kb * BK, n0);
+                    mbar_expect_tx(&afull[s], S::A_BYTES);
+                    tma_load_2d(&mA, &afull[s], smem_u32(smem + s * S::A_BYTES), kb * BK, m0);
                 }
             }
             TL_SET(0, 1, tl_now());
             TL_SET(0, 2, w_empty);
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == TMAB_T0 / 32) {
+        // ===== TMA producer B: pre-split weight tiles (L2) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_tf32(BN, false);
+            uint32_t it = 0;
+            for (int tile = worker; tile < tiles; tile += workers) {
+                const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2) * PAIR;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % NB, ph = (it / NB) & 1;
+                    mbar_wait(&bempty[s], ph ^ 1);
+                    const uint32_t st = smem_u32(smem + S::B_RING + s * S::BSTAGE_BYTES) + S::A_BYTES;
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(&bfull[s], 4 * S::B_BYTES);   // hi + lo halves of both CTAs
+                        else mbar_arrive_leader(&bfull[s]);
+                        tma_load_2d_pair(&mBh, &bfull[s], st, kb * BK, n0);
+                        tma_load_2d_pair(&mBl, &bfull[s], st + S::B_BYTES, kb * BK, n0);
+                    } else {
+                        mbar_expect_tx(&bfull[s], 2 * S::B_BYTES);
+                        tma_load_2d(&mBh, &bfull[s], st, kb * BK, n0);
+                        tma_load_2d(&mBl, &bfull[s], st + S::B_BYTES, kb * BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (PAIR: the leader CTA issues for both) =====
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = idesc_tf32_m(TM, BN);
             TL_DECL(w_tempty); TL_DECL(w_full); TL_DECL(w_conv);
             uint32_t it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+            for (int tile = worker; tile < tiles; tile += workers, ++tl) {
                 const uint32_t a = (NBUF == 2) ? (tl & 1) : 0, aph = (NBUF == 2) ? ((tl >> 1) & 1) : (tl & 1);
                 TL_T0(t0);
-                mbar_wait(&tempty[a], aph ^ 1);  // the epilogue has drained this accumulator set
+                if (PAIR) mbar_wait_cluster(&tempty[a], aph ^ 1); else mbar_wait(&tempty[a], aph ^ 1);  // the epilogue has drained this accumulator set
                 TL_ACC(w_tempty, t0);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    const uint32_t sa = it % NA, s = it % NB, ph = (it / NB) & 1;
                     TL_T0(t1);
-                    mbar_wait(&full[s], ph);   // TMA: raw A (= hi operand) and the split B tiles
+                    if (PAIR) mbar_wait_cluster(&bfull[s], ph); else mbar_wait(&bfull[s], ph);   // TMA: the split B tiles
                     TL_ACC(w_full, t1);
                     TL_T0(t2);
-                    mbar_wait(&conv[s], ph);   // converter warps: A lo
+                    if (PAIR) mbar_wait_cluster(&conv[s], ph); else mbar_wait(&conv[s], ph);    // converter warps: A lo (implies raw A landed)
                     TL_ACC(w_conv, t2);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES,
-                                   b_lo = b_hi + S::B_BYTES;
-                    const uint32_t tacc = tmem_base + (a * NACC + (uint32_t)(kb % NACC)) * BN;
-                    const bool first = kb < NACC;  // the first k-block of an accumulator overwrites it
+                    const uint32_t a_hi = smem_u32(smem + sa * S::A_BYTES), a_lo = smem_u32(smem + S::B_RING + s * S::BSTAGE_BYTES),
+                                   b_hi = a_lo + S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+                    const uint32_t tacc = tmem_base + a * NACC * BN;
+                    const bool first = kb == 0;  // the first k-step of a tile overwrites the accumulator
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint32_t off = k * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                        umma_tf32(tacc, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), idesc, (first && k == 0) ? 0u : 1u);
-                        umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), idesc, 1u);
-                        umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), idesc, 1u);
+                        if (NACC == 2) {
+                            umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), idesc_tf32_m(BM, 2 * BN), (first && k == 0) ? 0u : 1u);
+                            umma_tf32(tacc + BN, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), idesc, 1u);
+                        } else if (PAIR) {
+                            umma_tf32_pair(tacc, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), idesc, (first && k == 0) ? 0u : 1u);
+                            umma_tf32_pair(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), idesc, 1u);
+                            umma_tf32_pair(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), idesc, 1u);
+                        } else {
+                            umma_tf32(tacc, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), idesc, (first && k == 0) ? 0u : 1u);
+                            umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), idesc, 1u);
+                            umma_tf32(tacc, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), idesc, 1u);
+                        }
                     }
-                    umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+                    // free both ring stages (in both CTAs when PAIR) once these MMAs have read them
+                    if (PAIR) { umma_commit_pair(&aempty[sa]); umma_commit_pair(&bempty[s]); } else { umma_commit(&aempty[sa]); umma_commit(&bempty[s]); }
                 }
-                umma_commit(&tfull[a]);      // accumulator complete
+                if (PAIR) umma_commit_pair(&tfull[a]); else umma_commit(&tfull[a]);      // accumulator complete
             }
             TL_SET(0, 3, w_tempty); TL_SET(0, 4, w_full); TL_SET(0, 5, w_conv);
         }
@@ -294,36 +393,59 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
         // ===== converter warps: A lo = tf32(x - trunc13(x)), same swizzled offsets as the raw tile (elementwise) =====
         const int t = threadIdx.x - CONV_T0;
         constexpr int VEC = S::A_BYTES / 16 / (32 * CONV_WARPS);   // float4 per thread per k-block
+        TL_DECL(c_wb); TL_DECL(c_wa); TL_DECL(c_work); TL_DECL(c_sig);
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < tiles; tile += workers) {
             for (int kb = 0; kb < nk; ++kb, ++it) {
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                const uint32_t raw = smem_u32(smem + s * S::STAGE_BYTES) + 16 * t, lo = raw + S::A_BYTES;
+                const uint32_t sa = it % NA, pha = (it / NA) & 1, s = it % NB, ph = (it / NB) & 1;
+                TL_T0(q0);
+                mbar_wait(&bempty[s], ph ^ 1);   // the lo slot is free
+                TL_ACC(c_wb, q0);
+                TL_T0(q1);
+                mbar_wait(&afull[sa], pha);      // the raw tile has landed
+                TL_ACC(c_wa, q1);
+                TL_T0(q2);
+                const uint32_t raw = smem_u32(smem + sa * S::A_BYTES) + 16 * t, lo = smem_u32(smem + S::B_RING + s * S::BSTAGE_BYTES) + 16 * t;
                 float4 x[VEC];
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) x[i] = lds_v4(raw + i * 512 * CONV_WARPS);
+                if (NACC == 2) {
+                    // accurate variant: hi rounded to nearest IN PLACE (|lo| <= 2^-12 |x| instead of the truncation's 2^-10: the lo half's
+                    // own tf32 rounding and the dropped lo*lo term shrink 4x / 16x)
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) sts_v4(lo + i * 512 * CONV_WARPS, lo_trunc4(x[i]));
+                    for (int i = 0; i < VEC; ++i) {
+                        const float4 h = make_float4(tf32_rna_fast(x[i].x), tf32_rna_fast(x[i].y), tf32_rna_fast(x[i].z), tf32_rna_fast(x[i].w));
+                        sts_v4(raw + i * 512 * CONV_WARPS, h);
+                        sts_v4(lo + i * 512 * CONV_WARPS, make_float4(tf32_rna_fast(x[i].x - h.x), tf32_rna_fast(x[i].y - h.y),
+                                                                      tf32_rna_fast(x[i].z - h.z), tf32_rna_fast(x[i].w - h.w)));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) sts_v4(lo + i * 512 * CONV_WARPS, lo_trunc4(x[i]));
+                }
+                TL_ACC(c_work, q2);
+                TL_T0(q3);
                 fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                mbar_arrive(&conv[s]);
+                if (PAIR) mbar_arrive_leader(&conv[s]); else mbar_arrive(&conv[s]);   // (per-thread arrives measured faster than elect + __syncwarp)
+                TL_ACC(c_sig, q3);
             }
         }
+        if (t == 0) { TL_SET(0, 8, c_wb); TL_SET(0, 9, c_wa); TL_SET(0, 10, c_work); TL_SET(0, 11, c_sig); }
     } else {
         // ===== epilogue warps: TMEM lane quarter q = warp % 4, column group cg = (warp - 2) / 4 =====
         const int q = warp & 3, cg = (warp - 2) >> 2;
         constexpr int CHUNKS = BN / 32, PER = CHUNKS / (EPI_WARPS / 4) > 0 ? CHUNKS / (EPI_WARPS / 4) : 1;
         TL_DECL(w_tfull);
         uint32_t tl = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int tile = worker; tile < tiles; tile += workers, ++tl) {
+            const int m0 = (tile / n_tiles) * TM + (int)rank * BM, n0 = (tile % n_tiles) * BN;
             const uint32_t a = (NBUF == 2) ? (tl & 1) : 0, aph = (NBUF == 2) ? ((tl >> 1) & 1) : (tl & 1);
             TL_T0(t0);
             mbar_wait(&tfull[a], aph);
             TL_ACC(w_tfull, t0);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int row = m0 + q * 32 + lane;
-            const int nacc_used = nk < NACC ? nk : NACC;
+            constexpr int nacc_used = NACC;
 #pragma unroll 1
             for (int cc = 0; cc < PER; ++cc) {
                 const int c = cg * PER + cc;
@@ -388,14 +510,18 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[a]); else mbar_arrive(&tempty[a]); }
         }
         if (threadIdx.x == 64) TL_SET(0, 6, w_tfull);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
     if (threadIdx.x == 0) TL_SET(0, 7, tl_now());
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+    if (warp == 1) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+    }
 }
 
 // ---- weight gradient: D[Nout, Kin] += sum over rows m of dY[m, Nout]^T X[m, Kin] ------------------------------------
@@ -510,9 +636,10 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUten
                 for (int i = 0; i < A_VEC + B_VEC; ++i) x[i] = lds_v4(raw + i * 16 * NT);
 #pragma unroll
                 for (int i = 0; i < A_VEC; ++i) {   // dY: hi rounded to nearest, written back in place
-                    const float4 h = make_float4(tf32_rna(x[i].x), tf32_rna(x[i].y), tf32_rna(x[i].z), tf32_rna(x[i].w));
+                    const float4 h = make_float4(tf32_rna_fast(x[i].x), tf32_rna_fast(x[i].y), tf32_rna_fast(x[i].z), tf32_rna_fast(x[i].w));
                     sts_v4(raw + i * 16 * NT, h);
-                    sts_v4(lo + i * 16 * NT, make_float4(tf32_rna(x[i].x - h.x), tf32_rna(x[i].y - h.y), tf32_rna(x[i].z - h.z), tf32_rna(x[i].w - h.w)));
+                    sts_v4(lo + i * 16 * NT, make_float4(tf32_rna_fast(x[i].x - h.x), tf32_rna_fast(x[i].y - h.y), tf32_rna_fast(x[i].z - h.z),
+                                                         tf32_rna_fast(x[i].w - h.w)));
                 }
 #pragma unroll
                 for (int i = A_VEC; i < A_VEC + B_VEC; ++i) sts_v4(lo + i * 16 * NT, lo_trunc4(x[i]));   // X: the tensor core truncates the raw word
@@ -619,19 +746,38 @@ struct MapCache {
     }
 };
 
-template <int BN, int STAGES, int EPI, int NACC = 1>
+template <int BN, int NA, int NB, int EPI, int NACC = 1, int PAIR = 0>
 inline cudaError_t launch_rowmajor(const CUtensorMap* A, const CUtensorMap* Bh, const CUtensorMap* Bl, const RowArgs& g, int num_sms,
                                    cudaStream_t st) {
-    using S = RowSmem<BN, STAGES>;
+    using S = RowSmem<BN, NA, NB, PAIR>;
+    static_assert(S::TOTAL <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(k_tc_rowmajor<BN, STAGES, EPI, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        const cudaError_t e = cudaFuncSetAttribute(k_tc_rowmajor<BN, NA, NB, EPI, NACC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int tiles = ((g.M + BM - 1) / BM) * ((g.Nout + BN - 1) / BN);
+    const int tm = PAIR ? 2 * BM : BM;
+    const int tiles = ((g.M + tm - 1) / tm) * ((g.Nout + BN - 1) / BN);
+    if (PAIR) {
+        // clusters of two CTAs (the two SMs of a TPC): one persistent pair per two SMs
+        const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(ROW_THREADS);
+        cfg.dynamicSmemBytes = S::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_tc_rowmajor<BN, NA, NB, EPI, NACC, PAIR>, *A, *Bh, *Bl, g);
+    }
     const int grid = tiles < num_sms ? tiles : num_sms;
-    k_tc_rowmajor<BN, STAGES, EPI, NACC><<<grid, ROW_THREADS, S::TOTAL, st>>>(*A, *Bh, *Bl, g);
+    k_tc_rowmajor<BN, NA, NB, EPI, NACC, PAIR><<<grid, ROW_THREADS, S::TOTAL, st>>>(*A, *Bh, *Bl, g);
     return cudaPeekAtLastError();
 }
 

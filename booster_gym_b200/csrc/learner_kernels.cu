@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -158,28 +159,56 @@ __global__ void k_value_head(const float* __restrict__ H, const float* __restric
     if (lane == 0) V[warp] = s + b[0];
 }
 
-// backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m]
-#define VH_ROWS 128
-__global__ void __launch_bounds__(128) k_value_head_bwd(const float* __restrict__ H, const float* __restrict__ w,
-                                                        const float* __restrict__ dV, int n, float* __restrict__ dH,
-                                                        float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev) {
-    const int k = threadIdx.x;
-    const int r0 = blockIdx.x * VH_ROWS, r1 = min(n, r0 + VH_ROWS);
-    const float wk = w[k];
-    double acc = 0.0, accb = 0.0;  // fp64 partial sums: these are 98k-term reductions judged at 1e-5 relative
-    float accp = 0.0f;             // column sum of dH = bias gradient of the layer below
+// backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m];
+// db_prev[k] += sum_m dH[m,k] (bias gradient of the layer below).  One warp per row, one float4 (4 hidden units) per lane:
+// every access is a coalesced 512-byte row; 256 rows per block, fp32 partial sums over 32 rows per thread, combined across
+// the block's warps in double.
+#define HB_ROWS 256
+#define HB_THREADS 256
+__global__ void __launch_bounds__(HB_THREADS) k_value_head_bwd(const float* __restrict__ H, const float* __restrict__ w,
+                                                               const float* __restrict__ dV, int n, float* __restrict__ dH,
+                                                               float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev) {
+    __shared__ float4 red[2][HB_THREADS / 32][32];
+    __shared__ float redb[HB_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 w4 = reinterpret_cast<const float4*>(w)[lane];
+    const int r0 = blockIdx.x * HB_ROWS + warp * (HB_ROWS / 8), r1 = min(n, r0 + HB_ROWS / 8);
+    float4 aw = make_float4(0.f, 0.f, 0.f, 0.f), ap = aw;
+    float ab = 0.0f;
+#pragma unroll 4
     for (int r = r0; r < r1; ++r) {
-        const float g = dV[r];
-        const float h = H[(size_t)r * 128 + k];
-        const float dh = g * wk * ((h > 0.0f) ? 1.0f : (h + 1.0f));
-        dH[(size_t)r * 128 + k] = dh;
-        accp += dh;
-        acc += (double)g * (double)h;
-        accb += (double)g;
+        const float g = __ldg(dV + r);
+        const float4 h = reinterpret_cast<const float4*>(H + (size_t)r * 128)[lane];
+        float4 d;
+        d.x = g * w4.x * ((h.x > 0.0f) ? 1.0f : (h.x + 1.0f));
+        d.y = g * w4.y * ((h.y > 0.0f) ? 1.0f : (h.y + 1.0f));
+        d.z = g * w4.z * ((h.z > 0.0f) ? 1.0f : (h.z + 1.0f));
+        d.w = g * w4.w * ((h.w > 0.0f) ? 1.0f : (h.w + 1.0f));
+        reinterpret_cast<float4*>(dH + (size_t)r * 128)[lane] = d;
+        aw.x = fmaf(g, h.x, aw.x); aw.y = fmaf(g, h.y, aw.y); aw.z = fmaf(g, h.z, aw.z); aw.w = fmaf(g, h.w, aw.w);
+        ap.x += d.x; ap.y += d.y; ap.z += d.z; ap.w += d.w;
+        ab += g;
     }
-    atomicAdd(db_prev + k, accp);
-    atomicAdd(dw + k, (float)acc);
-    if (k == 0) atomicAdd(db, (float)accb);
+    red[0][warp][lane] = aw;
+    red[1][warp][lane] = ap;
+    if (lane == 0) redb[warp] = ab;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int k = threadIdx.x;
+        double sw = 0.0, sp = 0.0;
+#pragma unroll
+        for (int v = 0; v < HB_THREADS / 32; ++v) {
+            sw += (double)reinterpret_cast<const float*>(&red[0][v][0])[k];
+            sp += (double)reinterpret_cast<const float*>(&red[1][v][0])[k];
+        }
+        atomicAdd(dw + k, (float)sw);
+        atomicAdd(db_prev + k, (float)sp);
+        if (k == 0) {
+            double sb = 0.0;
+            for (int v = 0; v < HB_THREADS / 32; ++v) sb += (double)redb[v];
+            atomicAdd(db, (float)sb);
+        }
+    }
 }
 
 // bias gradient: db[c] += sum over rows of (dYh + dYl)[r,c]   (C <= 256; 256 threads, rows split over blockDim/Cp row-lanes)
@@ -207,67 +236,111 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, co
 }
 
 // actor head (utils/model.py:25): MU[m, 0..11] = b + H[m, :] W[12,128]^T, one warp per row, plain fp32 FMAs (the 12-wide
-// layer is 2 % of the MLP's FLOPs: a tensor-core tile would be 90 % padding).
+// layer is 2 % of the MLP's FLOPs: a tensor-core tile would be 90 % padding).  Each lane holds 4 hidden units and forms its 12
+// partial dot products; a butterfly reduce-scatter over 16 values (15 + 1 shuffles instead of 12 x 5) leaves output j on
+// lane bitrev4(j) of both half-warps.
+__device__ __forceinline__ float warp_reduce_scatter16(float (&p)[16], int lane) {
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = upper ? p[j] : p[j + half];
+            const float keep = upper ? p[j + half] : p[j];
+            p[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 16);   // lane l (mod 16) now holds output index with bits (l&8 ? 8:0)|(l&4 ? 4:0)|...
+}
 __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf, const float* __restrict__ W,
                                                     const float* __restrict__ b, int n, float* __restrict__ MU) {
-    __shared__ float4 sW[12][32];
-    for (int i = threadIdx.x; i < 12 * 32; i += blockDim.x) sW[i >> 5][i & 31] = reinterpret_cast<const float4*>(W)[i];
-    __syncthreads();
     const int lane = threadIdx.x & 31;
+    float4 w[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) w[j] = reinterpret_cast<const float4*>(W + j * 128)[lane];
+    // after the reduce-scatter lane l holds column j(l): step `half` keeps the upper half of the remaining index range on lanes
+    // with that bit set, so j = (l & 8) | (l & 4) | (l & 2) | (l & 1) = l & 15
+    const int jmine = lane & 15;
+    const float bj = (jmine < 12) ? b[jmine] : 0.0f;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n; row += warps) {
         const float4 h = reinterpret_cast<const float4*>(Hf + (size_t)row * 128)[lane];
-        float out = 0.0f;
+        float p[16];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            const float4 w = sW[j][lane];
-            float s = h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
+        for (int j = 0; j < 12; ++j) p[j] = h.x * w[j].x + h.y * w[j].y + h.z * w[j].z + h.w * w[j].w;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == j) out = s + b[j];
-        }
+        for (int j = 12; j < 16; ++j) p[j] = 0.0f;
+        const float out = warp_reduce_scatter16(p, lane) + bj;
         if (lane < 12) MU[(size_t)row * 12 + lane] = out;
     }
 }
 
 // backward of the actor head, fused: dH[m,k] = (sum_j dMU[m,j] W[j,k]) ELU'(H[m,k]);
-// dW[j,k] += sum_m dMU[m,j] H[m,k]; db[j] += sum_m dMU[m,j].   128 threads = the 128 hidden units, rows in chunks.
-#define AH_ROWS 128
-__global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ W,
-                                                        const float* __restrict__ dMU, int n, float* __restrict__ dH,
-                                                        float* __restrict__ dW, float* __restrict__ db, float* __restrict__ db_prev) {
-    __shared__ float sd[AH_ROWS][12];
-    const int k = threadIdx.x;
-    const int r0 = blockIdx.x * AH_ROWS, r1 = min(n, r0 + AH_ROWS);
-    for (int i = threadIdx.x; i < (r1 - r0) * 12; i += 128) sd[i / 12][i % 12] = dMU[(size_t)r0 * 12 + i];
-    float w[12];
+// dW[j,k] += sum_m dMU[m,j] H[m,k]; db[j] += sum_m dMU[m,j]; db_prev[k] += sum_m dH[m,k].  One warp per row, one float4 of hidden
+// units per lane (coalesced 512-byte rows), W and the 12 x 4 dW partials in registers; block-level combine in shared memory.
+__global__ void __launch_bounds__(HB_THREADS) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ W,
+                                                               const float* __restrict__ dMU, int n, float* __restrict__ dH,
+                                                               float* __restrict__ dW, float* __restrict__ db, float* __restrict__ db_prev) {
+    __shared__ float4 red[HB_THREADS / 32][7][32];    // per-warp partials of 7 of the 13 outputs rows (12 dW rows + the dH column sums) at a time
+    __shared__ float redb[HB_THREADS / 32][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 w[12], acc[12];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) w[j] = W[j * 128 + k];
-    __syncthreads();
-    float acc[12];   // 128-row partial sums in fp32, combined across the 768 blocks by fp32 atomics
-#pragma unroll
-    for (int j = 0; j < 12; ++j) acc[j] = 0.0f;
-    float accp = 0.0f;
+    for (int j = 0; j < 12; ++j) {
+        w[j] = reinterpret_cast<const float4*>(W + j * 128)[lane];
+        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ab = 0.0f;   // lane j < 12 sums dMU[:, j]
+    const int r0 = blockIdx.x * HB_ROWS + warp * (HB_ROWS / 8), r1 = min(n, r0 + HB_ROWS / 8);
+#pragma unroll 2
     for (int r = r0; r < r1; ++r) {
-        const float h = Hf[(size_t)r * 128 + k];
-        float g = 0.0f;
+        const float4 h = reinterpret_cast<const float4*>(Hf + (size_t)r * 128)[lane];
+        const float4* dp = reinterpret_cast<const float4*>(dMU + (size_t)r * 12);
+        const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+        const float d[12] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
-            const float d = sd[r - r0][j];
-            g = fmaf(d, w[j], g);
-            acc[j] = fmaf(d, h, acc[j]);
+            g.x = fmaf(d[j], w[j].x, g.x); g.y = fmaf(d[j], w[j].y, g.y); g.z = fmaf(d[j], w[j].z, g.z); g.w = fmaf(d[j], w[j].w, g.w);
+            acc[j].x = fmaf(d[j], h.x, acc[j].x); acc[j].y = fmaf(d[j], h.y, acc[j].y);
+            acc[j].z = fmaf(d[j], h.z, acc[j].z); acc[j].w = fmaf(d[j], h.w, acc[j].w);
         }
-        const float dh = g * ((h > 0.0f) ? 1.0f : (h + 1.0f));
-        dH[(size_t)r * 128 + k] = dh;
-        accp += dh;
-    }
-    atomicAdd(db_prev + k, accp);
+        float4 dh;
+        dh.x = g.x * ((h.x > 0.0f) ? 1.0f : (h.x + 1.0f));
+        dh.y = g.y * ((h.y > 0.0f) ? 1.0f : (h.y + 1.0f));
+        dh.z = g.z * ((h.z > 0.0f) ? 1.0f : (h.z + 1.0f));
+        dh.w = g.w * ((h.w > 0.0f) ? 1.0f : (h.w + 1.0f));
+        reinterpret_cast<float4*>(dH + (size_t)r * 128)[lane] = dh;
+        ap.x += dh.x; ap.y += dh.y; ap.z += dh.z; ap.w += dh.w;
+        float mine = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 12; ++j) atomicAdd(dW + j * 128 + k, acc[j]);
-    if (k < 12) {
-        double s = 0.0;
-        for (int r = r0; r < r1; ++r) s += (double)sd[r - r0][k];
-        atomicAdd(db + k, (float)s);
+        for (int j = 0; j < 12; ++j) mine = (lane == j) ? d[j] : mine;
+        ab += mine;
+    }
+    if (lane < 12) redb[warp][lane] = ab;
+    // 13 x 128 outputs in two passes (shared-memory budget), 256 threads: thread t sums the 8 warp partials of outputs t, t + 256, ...
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int j0 = pass * 7, cnt = pass ? 6 : 7;
+        if (pass) __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (j < cnt) red[warp][j][lane] = (j0 + j < 12) ? acc[(j0 + j) < 12 ? (j0 + j) : 0] : ap;
+        __syncthreads();
+        for (int o = threadIdx.x; o < cnt * 128; o += HB_THREADS) {
+            const int j = o >> 7, k = o & 127;
+            double sacc = 0.0;
+#pragma unroll
+            for (int v = 0; v < HB_THREADS / 32; ++v) sacc += (double)reinterpret_cast<const float*>(&red[v][j][0])[k];
+            if (j0 + j < 12) atomicAdd(dW + (j0 + j) * 128 + k, (float)sacc);
+            else atomicAdd(db_prev + k, (float)sacc);
+        }
+    }
+    if (threadIdx.x < 12) {
+        double sb = 0.0;
+        for (int v = 0; v < HB_THREADS / 32; ++v) sb += (double)redb[v][threadIdx.x];
+        atomicAdd(db + threadIdx.x, (float)sb);
     }
 }
 
@@ -733,15 +806,18 @@ struct GemmProfile {
     cudaEvent_t* ev = nullptr;  // 2 * kMax
     unsigned char* kind = nullptr;
     double flops[PK_COUNT] = {0.0, 0.0, 0.0};
+    double bytes[PK_COUNT] = {0.0, 0.0, 0.0};   // algorithmic HBM bytes (operands read once + results written once)
 } g_prof;
 
+static bool g_tc_pair = getenv("B200_TC_PAIR") ? atoi(getenv("B200_TC_PAIR")) != 0 : false;   // cta_group::2 GEMMs (b200_tc_set_pair)
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
 static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
-static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC) {
+static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC, double bytes = 0.0) {
     if (!g_prof.on || g_prof.used >= GemmProfile::kMax) return;
     cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
     g_prof.kind[g_prof.used] = (unsigned char)kind;
     g_prof.flops[kind] += flops;
+    g_prof.bytes[kind] += bytes;
 }
 static void prof_end(cudaStream_t st) {
     if (!g_prof.on || g_prof.used >= GemmProfile::kMax) return;
@@ -819,7 +895,7 @@ struct WgradJobs {
     WgradJob job[6];
     int count, total;
 };
-#define WR_SLICES 4
+#define WR_SLICES 8
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradJobs J) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= J.total) return;
@@ -837,11 +913,11 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradJobs J) {
     const int p0 = blockIdx.y * per, p1 = min(w.parts, p0 + per);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int pp = p0;
-    for (; pp + 4 <= p1; pp += 4) {
-        s0 += src[(size_t)pp * stride];
-        s1 += src[(size_t)(pp + 1) * stride];
-        s2 += src[(size_t)(pp + 2) * stride];
-        s3 += src[(size_t)(pp + 3) * stride];
+    for (; pp + 8 <= p1; pp += 8) {
+        const float v0 = src[(size_t)pp * stride], v1 = src[(size_t)(pp + 1) * stride], v2 = src[(size_t)(pp + 2) * stride],
+                    v3 = src[(size_t)(pp + 3) * stride], v4 = src[(size_t)(pp + 4) * stride], v5 = src[(size_t)(pp + 5) * stride],
+                    v6 = src[(size_t)(pp + 6) * stride], v7 = src[(size_t)(pp + 7) * stride];
+        s0 += v0 + v4; s1 += v1 + v5; s2 += v2 + v6; s3 += v3 + v7;
     }
     for (; pp < p1; ++pp) s0 += src[(size_t)pp * stride];
     if (p1 > p0) atomicAdd(w.D + (size_t)row * w.ldd + col, (s0 + s1) + (s2 + s3));
@@ -856,16 +932,20 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradJobs J) {
 static int tc_fwd(const B200Ppo* p, const float* X, int k, int ldx, const float* Wh, const float* Wl, int k_pad, const float* b,
                   float* Y, int n, int n_out, cudaStream_t st, bool accurate = false) {
     const int bn = (n_out >= 256 && !accurate) ? 256 : 128;
+    const bool pair = !accurate && g_tc_pair;   // CTA pairs: each CTA stages half of the weight tile (box = bn / 2 rows)
     TC_MAP(mA, X, n, ldx, ldx, tc::BM, true);   // all ldx columns are stored (zero padded beyond k)
-    TC_MAP(mBh, Wh, n_out, k_pad, k_pad, bn, true);
-    TC_MAP(mBl, Wl, n_out, k_pad, k_pad, bn, true);
+    TC_MAP(mBh, Wh, n_out, k_pad, k_pad, pair ? bn / 2 : bn, true);
+    TC_MAP(mBl, Wl, n_out, k_pad, k_pad, pair ? bn / 2 : bn, true);
     tc::RowArgs g{};
     g.out = Y; g.bias = b; g.aux = nullptr; g.colsum = nullptr;
     g.M = n; g.Nout = n_out; g.K = k_pad; g.ldo = n_out; g.tl_slot = tl_next();
-    prof_begin(st, 2.0 * n * (double)n_out * k, PK_TC_ROW);
-    const cudaError_t e = accurate    ? tc::launch_rowmajor<128, 3, tc::EPI_FWD, 4>(mA, mBh, mBl, g, p->num_sms, st)
-                          : (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_FWD>(mA, mBh, mBl, g, p->num_sms, st)
-                                        : tc::launch_rowmajor<128, 3, tc::EPI_FWD>(mA, mBh, mBl, g, p->num_sms, st);
+    prof_begin(st, 2.0 * n * (double)n_out * k, PK_TC_ROW, 4.0 * n * ((double)ldx + n_out));   // X read, Y written
+    // <BN, NA raw-A stages, NB weight stages, epilogue, accumulators, CTA pair>: every configuration fills the 227 KB of shared memory
+    const cudaError_t e = accurate    ? tc::launch_rowmajor<128, 5, 3, tc::EPI_FWD, 2>(mA, mBh, mBl, g, p->num_sms, st)
+                          : pair ? ((bn == 256) ? tc::launch_rowmajor<256, 5, 3, tc::EPI_FWD, 1, 1>(mA, mBh, mBl, g, p->num_sms, st)
+                                                : tc::launch_rowmajor<128, 8, 3, tc::EPI_FWD, 1, 1>(mA, mBh, mBl, g, p->num_sms, st))
+                          : (bn == 256) ? tc::launch_rowmajor<256, 4, 2, tc::EPI_FWD>(mA, mBh, mBl, g, p->num_sms, st)
+                                        : tc::launch_rowmajor<128, 5, 3, tc::EPI_FWD>(mA, mBh, mBl, g, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<fwd>");
@@ -875,15 +955,18 @@ static int tc_fwd(const B200Ppo* p, const float* X, int k, int ldx, const float*
 static int tc_dgrad(const B200Ppo* p, const float* dY, int n_out, const float* WTh, const float* WTl, int k_in, const float* H,
                     float* dX, float* colsum, int n, cudaStream_t st) {
     const int bn = (k_in >= 256) ? 256 : 128;
+    const bool pair = g_tc_pair;
     TC_MAP(mA, dY, n, n_out, n_out, tc::BM, true);
-    TC_MAP(mBh, WTh, k_in, n_out, n_out, bn, true);
-    TC_MAP(mBl, WTl, k_in, n_out, n_out, bn, true);
+    TC_MAP(mBh, WTh, k_in, n_out, n_out, pair ? bn / 2 : bn, true);
+    TC_MAP(mBl, WTl, k_in, n_out, n_out, pair ? bn / 2 : bn, true);
     tc::RowArgs g{};
     g.out = dX; g.bias = nullptr; g.aux = H; g.colsum = colsum;
     g.M = n; g.Nout = k_in; g.K = n_out; g.ldo = k_in; g.tl_slot = tl_next();
-    prof_begin(st, 2.0 * n * (double)n_out * k_in, PK_TC_ROW);
-    const cudaError_t e = (bn == 256) ? tc::launch_rowmajor<256, 2, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st)
-                                      : tc::launch_rowmajor<128, 3, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st);
+    prof_begin(st, 2.0 * n * (double)n_out * k_in, PK_TC_ROW, 4.0 * n * ((double)n_out + 2.0 * k_in));   // dY, H read, dX written
+    const cudaError_t e = pair ? ((bn == 256) ? tc::launch_rowmajor<256, 5, 3, tc::EPI_DGRAD, 1, 1>(mA, mBh, mBl, g, p->num_sms, st)
+                                              : tc::launch_rowmajor<128, 8, 3, tc::EPI_DGRAD, 1, 1>(mA, mBh, mBl, g, p->num_sms, st))
+                          : (bn == 256) ? tc::launch_rowmajor<256, 2, 2, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st)
+                                        : tc::launch_rowmajor<128, 3, 3, tc::EPI_DGRAD>(mA, mBh, mBl, g, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
     if (e != cudaSuccess) return set_cuda_error(e, "k_tc_rowmajor<dgrad>");
@@ -916,7 +999,7 @@ static int tc_wgrad(const B200Ppo* p, WgradJobs& jobs, int slot, const float* dY
     j.ldd = k_valid; j.first = jobs.total;
     jobs.count += 1;
     jobs.total += n_out * k_valid;
-    prof_begin(st, 2.0 * n * (double)n_out * k_valid, PK_TC_WGRAD);
+    prof_begin(st, 2.0 * n * (double)n_out * k_valid, PK_TC_WGRAD, 4.0 * n * ((double)n_out + k_cols));   // dY, X read
     cudaError_t e;
     if (k_pad == 256) e = tc::launch_wgrad<256, 4, 16>(mY, mX, g, k_pad, st);
     else if (k_pad == 128) e = tc::launch_wgrad<128, 3, 32>(mY, mX, g, k_pad, st);
@@ -1152,7 +1235,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
     // ---- actor backward: the 12-wide head as a fused FMA kernel, the hidden layers on tcgen05
-    k_actor_head_bwd<<<(M + AH_ROWS - 1) / AH_ROWS, 128, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, G1, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2));
+    k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, G1, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2));
     g_launches += 1;
     if ((rc = launch_status("k_actor_head_bwd")) != B200_OK) return rc;
     // (each bias gradient = column sum of the layer's output gradient, accumulated by the kernel that produces it)
@@ -1162,7 +1245,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     if ((rc = tc_dgrad(p, G2, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1, G1, p->G(P_AB0), M, st))) return rc;
     if ((rc = tc_wgrad(p, jobs, 2, G1, 256, ws + w.Xa, 64, 64, 47, p->G(P_AW0), M, st))) return rc;
     // ---- critic backward
-    k_value_head_bwd<<<(M + VH_ROWS - 1) / VH_ROWS, 128, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2));
+    k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2));
     g_launches += 1;
     if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
     if ((rc = tc_wgrad(p, jobs, 3, G1, 128, ws + w.C2, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
@@ -1194,13 +1277,17 @@ int b200_ppo_apply(B200Ppo* p, void* stream) {
 }
 
 long long b200_launch_count(void) { return g_launches; }
+int b200_tc_set_pair(int enable) {
+    g_tc_pair = enable != 0;
+    return B200_OK;
+}
 
 #ifdef B200_TC_TIMELINE
 /* debug builds only (tools/tc_timeline.py): per-CTA timelines of the tcgen05 GEMM launches since the last reset, in launch order */
 int b200_tc_timeline_reset(void) { g_tl_slot = 0; return B200_OK; }
-int b200_tc_timeline_read(unsigned long long* out /* [TL_SLOTS][160][8] */) {
+int b200_tc_timeline_read(unsigned long long* out /* [TL_SLOTS][160][12] */) {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpyFromSymbol(out, tc::g_tl, sizeof(unsigned long long) * TL_SLOTS * 160 * 8));
+    CUDA_TRY(cudaMemcpyFromSymbol(out, tc::g_tl, sizeof(unsigned long long) * TL_SLOTS * 160 * 12));
     return g_tl_slot;
 }
 #endif
@@ -1214,7 +1301,7 @@ int b200_profile_gemm(int enable) {
     }
     g_prof.on = enable != 0;
     g_prof.used = 0;
-    for (int k = 0; k < PK_COUNT; ++k) g_prof.flops[k] = 0.0;
+    for (int k = 0; k < PK_COUNT; ++k) g_prof.flops[k] = g_prof.bytes[k] = 0.0;
     return B200_OK;
 }
 /* kind: 0 = k_gemm3x (mma.sync), 1 = k_tc_rowmajor (tcgen05 fwd / dgrad), 2 = k_tc_wgrad (tcgen05), -1 = all */
@@ -1234,6 +1321,14 @@ int b200_profile_gemm_read(int kind, double* total_ms, double* total_flops, int*
     if (total_ms) *total_ms = ms;
     if (total_flops) *total_flops = fl;
     if (launches) *launches = cnt;
+    return B200_OK;
+}
+
+int b200_profile_gemm_bytes(int kind, double* total_bytes) {
+    double b = 0.0;
+    for (int k = 0; k < PK_COUNT; ++k)
+        if (kind < 0 || kind == k) b += g_prof.bytes[k];
+    if (total_bytes) *total_bytes = b;
     return B200_OK;
 }
 

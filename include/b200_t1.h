@@ -275,6 +275,13 @@ long long b200_launch_count(void);
 int b200_profile_gemm(int enable);
 /* kind: 0 = k_gemm3x (mma.sync), 1 = k_tc_rowmajor (tcgen05 forward / dgrad), 2 = k_tc_wgrad (tcgen05), -1 = all */
 int b200_profile_gemm_read(int kind, double* total_ms, double* total_flops, int* launches);
+/* algorithmic HBM bytes of the same launches: every fp32 operand read once, every result written once (weights excluded:
+ * they stay in L2) - the numerator of the HBM roofline of the GEMM families */
+int b200_profile_gemm_bytes(int kind, double* total_bytes);
+/* k_tc_rowmajor variant for the critic forward and the dgrad GEMMs: 0 (default) = one CTA per 128-row tile, 1 = CTA pairs
+ * (clusters of 2, tcgen05 cta_group::2, 256-row tiles, each CTA stages half of the weight tile).  Same results; the pair
+ * variant halves the per-CTA L2 -> shared-memory weight traffic but measured ~4 % slower on this shape. */
+int b200_tc_set_pair(int enable);
 
 #ifdef __cplusplus
 }

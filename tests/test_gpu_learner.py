@@ -6,6 +6,7 @@ max magnitude against the fp32 oracle.  Reductions over 98k samples (losses, gra
 fp32, so they are judged against the fp64 oracle: |ours - f64| <= 1e-5 * scale + 3 * |f32 oracle - f64|.
 """
 import copy
+import os
 
 import pytest
 import torch
@@ -39,6 +40,8 @@ def judge(name, ours, f32, f64, rel=1e-5, atol=0.0):
     scale = max(f64.abs().max().item(), 1e-30)
     err = (ours - f64).abs().max().item()
     ref_err = (f32 - f64).abs().max().item()
+    if os.environ.get("B200_TEST_REPORT"):
+        print(f"[judge] {name:28s} err {err:.3e}  allowed {rel * scale + 3.0 * ref_err + atol:.3e}  ratio {err / (rel * scale + 3.0 * ref_err + atol):.3f}")
     assert err <= rel * scale + 3.0 * ref_err + atol, f"{name}: err {err:.3e} scale {scale:.3e} ref_err {ref_err:.3e}"
 
 
@@ -146,8 +149,19 @@ def test_gae_bit_exact(T, N):
     assert abs(s[0].item() - adv_ref.double().sum().item()) <= 1e-9 * max(1.0, adv_ref.double().abs().sum().item())
 
 
-@pytest.mark.parametrize("T,N", [(24, 4096), (3, 200)])
-def test_epoch_against_oracle(t1_cfg, T, N):
+@pytest.mark.parametrize("T,N,pair", [(24, 4096, 0), (3, 200, 0), (6, 1000, 1)])
+def test_epoch_against_oracle(t1_cfg, T, N, pair):
+    """pair = 1 runs the critic forward / dgrad GEMMs on CTA pairs (tcgen05 cta_group::2) - same tolerances"""
+    from booster_gym_b200 import _lib
+
+    _lib.load().b200_tc_set_pair(pair)
+    try:
+        _epoch_against_oracle(t1_cfg, T, N)
+    finally:
+        _lib.load().b200_tc_set_pair(0)
+
+
+def _epoch_against_oracle(t1_cfg, T, N):
     LR = 1e-4  # one Adam step of 1e-4 moves the policy by KL ~ 0.1: ratios leave the clip range without making epoch 1 chaotic
     cfg, lrn, sd, L = _mk(t1_cfg, T, N, lr=LR)
     buf, last_obs, last_priv = L.synthetic_rollout(T, N, seed=3, done_rate=0.02, timeout_rate=0.03)
@@ -215,12 +229,25 @@ def test_epoch_against_oracle(t1_cfg, T, N):
         for name, ref in res[torch.float64][1].items():
             # after Adam every parameter moved by at most ~lr; compare the parameters themselves
             pass
-    # parameters after two epochs (Adam's m/sqrt(v) is ill-conditioned where |g| ~ eps: judge against the step size)
+    # parameters after two epochs.  Adam's update lr * m_hat / (sqrt(v_hat) + eps) is ~ lr * sign(g): its sensitivity to a
+    # gradient error dg is lr * O(dg / |g|) per element, so elements with a small gradient amplify the (stated, 2e-4 of the
+    # tensor max) gradient tolerance.  Each parameter is therefore held to the bound that tolerance implies, element by
+    # element: sum over the two steps of lr * min(2, 2 * 2e-4 * max|g| / |g_ij|), on top of 1e-5 relative and 3x the fp32
+    # reference's own distance from fp64.
     p = lrn.views()
     sd64, sd32 = res[torch.float64][1], res[torch.float32][1]
+    outs64 = res[torch.float64][0]
     for name in sd64:
         ours = p[name].cpu().double().reshape(sd64[name].shape)
-        err = (ours - sd64[name]).abs().max().item()
+        err = (ours - sd64[name]).abs()
         ref_err = (sd32[name].double() - sd64[name]).abs().max().item()
-        assert err <= 1e-5 * sd64[name].abs().max().item() + 3 * ref_err + 2e-2 * LR * 2, (name, err, ref_err)
+        bound = torch.zeros_like(err)
+        lr_ep = LR
+        for o in outs64:
+            g = o["grads"][name].double().reshape(err.shape).abs()
+            bound += lr_ep * torch.clamp(2.0 * 2e-4 * g.max() / g.clamp_min(1e-30), max=2.0)
+            lr_ep = o["lr"]
+        tol = 1e-5 * sd64[name].abs().max().item() + 3 * ref_err + bound
+        worst = (err - tol).max().item()
+        assert worst <= 0.0, (name, err.max().item(), ref_err, worst)
     assert int(lrn.scalars[_abi.SC["ADAM_STEP"]].item()) == 2

@@ -54,7 +54,7 @@ def main():
     lib.b200_tc_timeline_reset()
     lrn.epoch_a(dev["rewards"], d8, t8, lo, lp)
     lrn.epoch_b(dev["actions"])
-    out = np.zeros((40, 160, 8), dtype=np.uint64)
+    out = np.zeros((40, 160, 12), dtype=np.uint64)
     n = lib.b200_tc_timeline_read(out.ctypes.data_as(C.c_void_p))
     names = ["c_fwd1", "c_fwd2", "c_fwd3", "a_fwd1", "a_fwd2", "a_fwd3", "a_wg3", "a_dg3", "a_wg2", "a_dg2", "a_wg1", "c_wg3", "c_dg3", "c_wg2",
              "c_dg2", "c_wg1"]
@@ -73,7 +73,8 @@ def main():
         else:
             print(f"{names[i]:7s} rowmajor ctas {live.sum():3d} total {total:7.1f} | tma_done {med(t[:,1]-t[:,0]):6.1f} tma_wait_empty {med(t[:,2]):6.1f} | "
                   f"mma_wait_tempty {med(t[:,3]):6.1f} mma_wait_full {med(t[:,4]):6.1f} mma_wait_conv {med(t[:,5]):6.1f} | epi_wait_tfull {med(t[:,6]):6.1f} "
-                  f"cta_end {med(t[:,7]-t[:,0]):6.1f}")
+                  f"cta_end {med(t[:,7]-t[:,0]):6.1f} | conv: wait_bempty {med(t[:,8]):5.1f} wait_afull {med(t[:,9]):5.1f} work {med(t[:,10]):5.1f} "
+                  f"fence+arrive {med(t[:,11]):5.1f}")
 
 
 if __name__ == "__main__":
