@@ -35,15 +35,28 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200")
-    ap.add_argument("--num-envs", type=int, default=4096)
+    ap.add_argument("--num-envs", type=int, default=None, help="envs per GPU (default: 4096 for --config 1, 8192 for --config 2)")
+    ap.add_argument("--config", type=int, default=1, choices=(1, 2),
+                    help="1 = BASELINE.json configs[1] (flat terrain, 4096 envs/GPU; the bench line); 2 = configs[2]/[3] (rough heightfield "
+                         "terrain + kicks/pushes + domain randomisation, 8192 envs/GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", type=int, default=0, help="replay the rollout from a CUDA graph")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.num_envs is None:
+        args.num_envs = 4096 if args.config == 1 else 8192
+    return args
+
+
+def workload(args):
+    if args.config == 1:
+        return WORKLOAD.replace("4096 envs", f"{args.num_envs} envs")
+    return (f"configs[2]: T1 rough heightfield terrain (trimesh: 4 random-uniform + 4 discrete-obstacle tiles) + kicks/pushes + domain "
+            f"randomisation, {args.num_envs} envs per GPU, 24-step rollout + PPO update (20 full-batch epochs), seed 42")
 
 
 def config_dict(args, world):
-    return {"workload": WORKLOAD, "num_envs_per_gpu": args.num_envs, "total_envs": args.num_envs * world, "horizon": 24,
-            "mini_epochs": 20, "terrain": "plane", "parallelism": f"env-sharded dp{world}",
+    return {"workload": workload(args), "num_envs_per_gpu": args.num_envs, "total_envs": args.num_envs * world, "horizon": 24,
+            "mini_epochs": 20, "terrain": "plane" if args.config == 1 else "trimesh", "parallelism": f"env-sharded dp{world}",
             "l2": "working set (the learner streams ~1.9 GB of fp32 activations per epoch through a >400 MB workspace per GPU) is larger than "
                   "the 126 MB L2; no flush needed",
             "rollout_cuda_graph": bool(args.graphs)}
@@ -132,7 +145,8 @@ def b200_arm(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     lib = _lib.load()
     runner = Runner(test=False, argv=["--task", "T1", "--num_envs", str(args.num_envs), "--headless", "True"],
-                    cfg_overrides={"terrain": {"type": "plane"}, "runner": {"use_wandb": False}})
+                    cfg_overrides={"terrain": {"type": "plane"}, "runner": {"use_wandb": False}} if args.config == 1 else
+                    {"terrain": {"type": "trimesh"}, "runner": {"use_wandb": False}})
     dev = torch.device(runner.device)
     env, lrn = runner.env, runner.learner
     T, N, E = runner.cfg["runner"]["horizon_length"], env.num_envs, runner.cfg["runner"]["mini_epochs"]
