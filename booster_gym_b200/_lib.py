@@ -53,6 +53,8 @@ PROTOTYPES = {
     "b200_ppo_epoch_b": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_ppo_buffer": (_vp, [_vp, _i]),
     "b200_ppo_apply": (_i, [_vp, _vp]),
+    "b200_ppo_peer_buffer_bytes": (C.c_longlong, []),
+    "b200_ppo_bind_peers": (_i, [_vp, C.POINTER(C.c_ulonglong), _i, _i]),
     "b200_launch_count": (C.c_longlong, []),
     "b200_profile_gemm": (_i, [_i]),
     "b200_profile_gemm_read": (_i, [_i, C.POINTER(_d), C.POINTER(_d), _ip]),

@@ -127,6 +127,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -440,11 +448,64 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
         for (int tile = worker; tile < tiles; tile += workers, ++tl) {
             const int m0 = (tile / n_tiles) * TM + (int)rank * BM, n0 = (tile % n_tiles) * BN;
             const uint32_t a = (NBUF == 2) ? (tl & 1) : 0, aph = (NBUF == 2) ? ((tl >> 1) & 1) : (tl & 1);
+            const int row = m0 + q * 32 + lane;
+            if (EPI == EPI_DGRAD) {
+                // dgrad epilogue, software-pipelined over 16-column half-chunks: the h (post-activation) loads of half-chunk i + 1 are in
+                // flight while i is processed, and those of the first half-chunk are issued BEFORE waiting for the accumulator, so
+                // their HBM latency hides behind the tile's main loop
+                constexpr int HC = 2 * PER;
+                const bool row_ok = row < g.M;
+                const size_t rbase = (size_t)(row_ok ? row : 0) * g.ldo;
+                const int cbase = n0 + cg * PER * 32;
+                float hn[16];
+                if (cbase < g.Nout) { ldg_v8(g.aux + rbase + cbase, hn); ldg_v8(g.aux + rbase + cbase + 8, hn + 8); }
+                TL_T0(t0);
+                mbar_wait(&tfull[a], aph);
+                TL_ACC(w_tfull, t0);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll 1
+                for (int i = 0; i < HC; ++i) {
+                    const int col0 = cbase + i * 16;
+                    if (col0 >= g.Nout) break;               // warp-uniform
+                    float hc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hc[j] = hn[j];
+                    if (i + 1 < HC && col0 + 16 < g.Nout) { ldg_v8(g.aux + rbase + col0 + 16, hn); ldg_v8(g.aux + rbase + col0 + 24, hn + 8); }
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + a * NACC * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - n0), r);
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * ((hc[j] > 0.0f) ? 1.0f : (hc[j] + 1.0f));
+                    if (row_ok) { stg_v8(g.out + rbase + col0, v); stg_v8(g.out + rbase + col0 + 8, v + 8); }
+                    if (g.colsum) {
+                        if (!row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+                        }
+                        // column sums over this warp's 32 rows: reduce-scatter over 16 values (15 shuffles) + the other half-warp
+#pragma unroll
+                        for (int half = 8; half >= 1; half >>= 1) {
+                            const bool upper = (lane & half) != 0;
+#pragma unroll
+                            for (int j = 0; j < half; ++j) {
+                                const float send = upper ? v[j] : v[j + half];
+                                const float keep = upper ? v[j + half] : v[j];
+                                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+                            }
+                        }
+                        const float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+                        if (lane < 16) atomicAdd(g.colsum + col0 + lane, tot);   // lane l holds column l (bit i of l picks the upper half at step 2^i)
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[a]); else mbar_arrive(&tempty[a]); }
+                continue;
+            }
             TL_T0(t0);
             mbar_wait(&tfull[a], aph);
             TL_ACC(w_tfull, t0);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const int row = m0 + q * 32 + lane;
             constexpr int nacc_used = NACC;
 #pragma unroll 1
             for (int cc = 0; cc < PER; ++cc) {

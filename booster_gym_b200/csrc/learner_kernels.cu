@@ -81,7 +81,28 @@ static Workspace make_workspace(int T, int N) {
     return w;
 }
 
+// ---- multi-GPU exchange over peer memory (NVLink / NVSwitch): replaces the three NCCL all-reduces of an epoch -----------------
+// Every rank owns one SYMMETRIC buffer (torch.distributed._symmetric_memory: peer-mapped into all ranks of the node):
+//   [0, 1 KiB)            uint32 flag[channel][source rank]   channel 0 = gradients, 1 = advantage moments; written by the peers
+//   2 x slot (epoch parity) { float grads[NPARAMS_PADDED]; double loss_sums[8]; double adv_moments[4]; }
+// post:   copy my contribution into my own slot, __threadfence_system, raise my flag (sequence number) in EVERY rank's buffer
+// reduce: spin on my flags until every rank has posted this sequence number, then sum the peers' slots over NVLink in rank
+//         order (identical result on every rank), fused with what follows (gradient norm for clip_grad_norm_)
+// A slot is rewritten two posts later; a rank gets there only after a reduce that needed every peer's NEXT post, which the peer
+// issues after finishing this reduce (stream order) - so two slots are enough and no second barrier is needed.
+#define XCH_MAX_WORLD 16
+#define XCH_FLAG_FLOATS 256
+#define XCH_SLOT_FLOATS ((NPARAMS_PADDED + 16 + 8 + 63) / 64 * 64)
+struct PeerX {
+    unsigned long long bufs[XCH_MAX_WORLD];
+    int rank, world;
+};
+
 struct B200Ppo {
+    PeerX px;
+    int peers;                    // 1 once b200_ppo_bind_peers succeeded
+    unsigned int seq_grad, seq_stat;
+    unsigned int* xch_counter;    // device: block counter of the post kernels
     B200PpoConfig cfg;
     int device;
     float *params, *grads, *adam_m, *adam_v, *scalars;
@@ -263,33 +284,41 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf
     const int jmine = lane & 15;
     const float bj = (jmine < 12) ? b[jmine] : 0.0f;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n; row += warps) {
-        const float4 h = reinterpret_cast<const float4*>(Hf + (size_t)row * 128)[lane];
-        float p[16];
+    // two rows per iteration (both loads in flight); the second row's 12 outputs ride in the upper half-warp's butterfly slots
+    for (int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; row < n; row += 2 * warps) {
+        const bool two = row + 1 < n;
+        const float4 h0 = reinterpret_cast<const float4*>(Hf + (size_t)row * 128)[lane];
+        const float4 h1 = two ? reinterpret_cast<const float4*>(Hf + (size_t)(row + 1) * 128)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float p[16], q[16];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) p[j] = h.x * w[j].x + h.y * w[j].y + h.z * w[j].z + h.w * w[j].w;
+        for (int j = 0; j < 12; ++j) {
+            p[j] = h0.x * w[j].x + h0.y * w[j].y + h0.z * w[j].z + h0.w * w[j].w;
+            q[j] = h1.x * w[j].x + h1.y * w[j].y + h1.z * w[j].z + h1.w * w[j].w;
+        }
 #pragma unroll
-        for (int j = 12; j < 16; ++j) p[j] = 0.0f;
-        const float out = warp_reduce_scatter16(p, lane) + bj;
-        if (lane < 12) MU[(size_t)row * 12 + lane] = out;
+        for (int j = 12; j < 16; ++j) p[j] = q[j] = 0.0f;
+        const float o0 = warp_reduce_scatter16(p, lane) + bj;
+        const float o1 = warp_reduce_scatter16(q, lane) + bj;
+        if (lane < 12) MU[(size_t)row * 12 + lane] = o0;
+        else if (lane >= 16 && lane < 28 && two) MU[(size_t)(row + 1) * 12 + (lane - 16)] = o1;
     }
 }
 
 // backward of the actor head, fused: dH[m,k] = (sum_j dMU[m,j] W[j,k]) ELU'(H[m,k]);
 // dW[j,k] += sum_m dMU[m,j] H[m,k]; db[j] += sum_m dMU[m,j]; db_prev[k] += sum_m dH[m,k].  One warp per row, one float4 of hidden
 // units per lane (coalesced 512-byte rows), W and the 12 x 4 dW partials in registers; block-level combine in shared memory.
-__global__ void __launch_bounds__(HB_THREADS) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ W,
+__global__ void __launch_bounds__(HB_THREADS, 2) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ W,
                                                                const float* __restrict__ dMU, int n, float* __restrict__ dH,
                                                                float* __restrict__ dW, float* __restrict__ db, float* __restrict__ db_prev) {
     __shared__ float4 red[HB_THREADS / 32][7][32];    // per-warp partials of 7 of the 13 outputs rows (12 dW rows + the dH column sums) at a time
     __shared__ float redb[HB_THREADS / 32][12];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 w[12], acc[12];
+    __shared__ float4 sw[12][32];   // W stays in shared memory (48 registers less: two blocks per SM keep more rows in flight)
+    for (int i = threadIdx.x; i < 12 * 32; i += HB_THREADS) sw[i >> 5][i & 31] = reinterpret_cast<const float4*>(W)[i];
+    __syncthreads();
+    float4 acc[12];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        w[j] = reinterpret_cast<const float4*>(W + j * 128)[lane];
-        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int j = 0; j < 12; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
     float ab = 0.0f;   // lane j < 12 sums dMU[:, j]
     const int r0 = blockIdx.x * HB_ROWS + warp * (HB_ROWS / 8), r1 = min(n, r0 + HB_ROWS / 8);
@@ -302,7 +331,8 @@ __global__ void __launch_bounds__(HB_THREADS) k_actor_head_bwd(const float* __re
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
-            g.x = fmaf(d[j], w[j].x, g.x); g.y = fmaf(d[j], w[j].y, g.y); g.z = fmaf(d[j], w[j].z, g.z); g.w = fmaf(d[j], w[j].w, g.w);
+            const float4 wj = sw[j][lane];
+            g.x = fmaf(d[j], wj.x, g.x); g.y = fmaf(d[j], wj.y, g.y); g.z = fmaf(d[j], wj.z, g.z); g.w = fmaf(d[j], wj.w, g.w);
             acc[j].x = fmaf(d[j], h.x, acc[j].x); acc[j].y = fmaf(d[j], h.y, acc[j].y);
             acc[j].z = fmaf(d[j], h.z, acc[j].z); acc[j].w = fmaf(d[j], h.w, acc[j].w);
         }
@@ -710,6 +740,106 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
     }
 }
 
+
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {   // peer (NVLink) load, not cached in L1
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float* xch_slot(const PeerX& x, int r, int parity) {
+    return reinterpret_cast<float*>(x.bufs[r]) + XCH_FLAG_FLOATS + (size_t)parity * XCH_SLOT_FLOATS;
+}
+__device__ __forceinline__ void xch_raise(const PeerX& x, int channel, unsigned seq) {   // one thread
+    for (int r = 0; r < x.world; ++r) st_release_sys_u32(reinterpret_cast<unsigned*>(x.bufs[r]) + channel * XCH_MAX_WORLD + x.rank, seq);
+}
+__device__ __forceinline__ void xch_wait(const PeerX& x, int channel, unsigned seq) {     // threads [0, world) of a block, then __syncthreads
+    if ((int)threadIdx.x < x.world) {
+        const unsigned* f = reinterpret_cast<const unsigned*>(x.bufs[x.rank]) + channel * XCH_MAX_WORLD + threadIdx.x;
+        while ((int)(ld_acquire_sys_u32(f) - seq) < 0) { }
+    }
+    __syncthreads();
+}
+
+// gradients + loss sums -> my slot; the last block to finish raises the flags
+__global__ void __launch_bounds__(256) k_xchg_post_grads(const PeerX x, const float* __restrict__ grads, const double* __restrict__ dstats,
+                                                         int parity, unsigned seq, unsigned* __restrict__ counter) {
+    float* slot = xch_slot(x, x.rank, parity);
+    const float4* g4 = reinterpret_cast<const float4*>(grads);
+    float4* s4 = reinterpret_cast<float4*>(slot);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NPARAMS_PADDED / 4; i += gridDim.x * blockDim.x) s4[i] = g4[i];
+    if (blockIdx.x == 0 && threadIdx.x < 6) reinterpret_cast<double*>(slot + NPARAMS_PADDED)[threadIdx.x] = dstats[DS_VALUE_LOSS + threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0u;
+            __threadfence_system();
+            xch_raise(x, 0, seq);
+        }
+    }
+}
+// all-reduce (sum) of the gradient and the loss sums over the peers' slots, fused with the gradient norm of clip_grad_norm_
+__global__ void __launch_bounds__(256) k_xchg_reduce_grads(const PeerX x, float* __restrict__ grads, double* __restrict__ dstats, int parity,
+                                                           unsigned seq, float inv_world) {
+    xch_wait(x, 0, seq);
+    float4* g4 = reinterpret_cast<float4*>(grads);
+    float s = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NPARAMS_PADDED / 4; i += gridDim.x * blockDim.x) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < x.world; ++r) {
+            const float4 v = ld_peer_f4(reinterpret_cast<const float4*>(xch_slot(x, r, parity)) + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        g4[i] = a;
+        const float gx = a.x * inv_world, gy = a.y * inv_world, gz = a.z * inv_world, gw = a.w * inv_world;
+        s += gx * gx + gy * gy + gz * gz + gw * gw;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 6) {
+        double t = 0.0;
+        for (int r = 0; r < x.world; ++r) t += ld_peer_f64(reinterpret_cast<const double*>(xch_slot(x, r, parity) + NPARAMS_PADDED) + threadIdx.x);
+        dstats[DS_VALUE_LOSS + threadIdx.x] = t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += (double)sh[w];
+        atomicAdd(dstats + DS_GRAD_SQ, t);
+    }
+}
+// advantage moments (sum, sum of squares, count) of this rank -> my slot, flags raised
+__global__ void k_xchg_post_stats(const PeerX x, const double* __restrict__ dstats, int parity, unsigned seq) {
+    double* d = reinterpret_cast<double*>(xch_slot(x, x.rank, parity) + NPARAMS_PADDED + 16);
+    if (threadIdx.x < 4) d[threadIdx.x] = dstats[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) xch_raise(x, 1, seq);
+}
+__global__ void k_xchg_reduce_stats(const PeerX x, double* __restrict__ dstats, int parity, unsigned seq) {
+    xch_wait(x, 1, seq);
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int r = 0; r < x.world; ++r) t += ld_peer_f64(reinterpret_cast<const double*>(xch_slot(x, r, parity) + NPARAMS_PADDED + 16) + threadIdx.x);
+        dstats[threadIdx.x] = t;
+    }
+}
 
 // logstd gradient = reduced surrogate part + entropy_coef * d mean(entropy) / d logstd_j (= entropy_coef)
 __global__ void k_finalize_logstd(const double* __restrict__ dstats, float entropy_coef, float* __restrict__ g_logstd) {
@@ -1119,14 +1249,20 @@ int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float
     if (!p->maps) { delete p; return set_error(B200_ERR_ARG, "out of host memory"); }
     p->num_sms = 148;
     cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
+    p->peers = 0;
+    p->seq_grad = p->seq_stat = 0;
+    p->xch_counter = nullptr;
     cudaError_t ce = cudaMalloc(&p->act_ctr, sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(p->act_ctr, 0, sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->xch_counter, sizeof(unsigned int));
+    if (ce == cudaSuccess) ce = cudaMemset(p->xch_counter, 0, sizeof(unsigned int));
     if (ce != cudaSuccess) { delete p; return set_cuda_error(ce, "b200_ppo_create: counter allocation"); }
     *out = p;
     return B200_OK;
 }
 int b200_ppo_destroy(B200Ppo* p) {
     if (p && p->act_ctr) cudaFree(p->act_ctr);
+    if (p && p->xch_counter) cudaFree(p->xch_counter);
     if (p) delete p->maps;
     delete p;
     return B200_OK;
@@ -1212,6 +1348,11 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
     g_launches += 3;  // memset, k_pack_inputs, k_gae
+    if (p->peers) {   // this rank's advantage moments -> peers (summed in epoch_b, behind the actor forward)
+        p->seq_stat += 1;
+        k_xchg_post_stats<<<1, 32, 0, st>>>(p->px, p->dstats, (int)(p->seq_stat & 1u), p->seq_stat);
+        g_launches += 1;
+    }
     return launch_status("k_gae");
 }
 
@@ -1228,6 +1369,10 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     int rc = actor_forward_tc(p, M, st);
     if (rc != B200_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(p->grads, 0, NPARAMS_PADDED * sizeof(float), st));
+    if (p->peers) {   // global advantage normalisation (utils/runner.py:145 over all ranks' samples)
+        k_xchg_reduce_stats<<<1, 32, 0, st>>>(p->px, p->dstats, (int)(p->seq_stat & 1u), p->seq_stat);
+        g_launches += 1;
+    }
     k_loss<<<(M + LOSS_BLOCK - 1) / LOSS_BLOCK, LOSS_BLOCK, 0, st>>>(ws + w.V, ws + w.RET, ws + w.ADV, MU, actions, old_mu, old_logp,
                                                                     p->P(P_LOGSTD), p->scalars, p->dstats, M, p->cfg.e_clip,
                                                                     p->cfg.bound_coef, DV, DMU);
@@ -1267,7 +1412,15 @@ int b200_ppo_apply(B200Ppo* p, void* stream) {
     NEED_PPO(p);
     cudaStream_t st = (cudaStream_t)stream;
     const float inv_world = 1.0f / (float)p->cfg.world_size;
-    k_grad_sumsq<<<148, 256, 0, st>>>(p->grads, NPARAMS_PADDED, inv_world, p->dstats);
+    if (p->peers) {   // sum-all-reduce of the gradient + loss sums over NVLink peer memory, fused with the gradient norm
+        p->seq_grad += 1;
+        const int parity = (int)(p->seq_grad & 1u);
+        k_xchg_post_grads<<<64, 256, 0, st>>>(p->px, p->grads, p->dstats, parity, p->seq_grad, p->xch_counter);
+        k_xchg_reduce_grads<<<96, 256, 0, st>>>(p->px, p->grads, p->dstats, parity, p->seq_grad, inv_world);
+        g_launches += 1;
+    } else {
+        k_grad_sumsq<<<148, 256, 0, st>>>(p->grads, NPARAMS_PADDED, inv_world, p->dstats);
+    }
     k_adam<<<(NPARAMS_PADDED + 255) / 256, 256, 0, st>>>(p->params, p->grads, p->adam_m, p->adam_v, NPARAMS_PADDED, p->scalars,
                                                          p->dstats, inv_world, p->cfg.max_grad_norm, p->cfg.adam_beta1,
                                                          p->cfg.adam_beta2, p->cfg.adam_eps);
@@ -1277,6 +1430,22 @@ int b200_ppo_apply(B200Ppo* p, void* stream) {
 }
 
 long long b200_launch_count(void) { return g_launches; }
+
+long long b200_ppo_peer_buffer_bytes(void) { return (long long)(XCH_FLAG_FLOATS + 2 * (size_t)XCH_SLOT_FLOATS) * (long long)sizeof(float); }
+int b200_ppo_bind_peers(B200Ppo* p, const unsigned long long* buffer_ptrs, int rank, int world) {
+    NEED_PPO(p);
+    if (!buffer_ptrs || world < 1 || world > XCH_MAX_WORLD || rank < 0 || rank >= world || world != p->cfg.world_size)
+        return set_error(B200_ERR_ARG, "b200_ppo_bind_peers: bad argument (world must equal the learner's world_size, <= 16)");
+    for (int r = 0; r < world; ++r) {
+        if (!buffer_ptrs[r] || (buffer_ptrs[r] & 15ull)) return set_error(B200_ERR_ARG, "b200_ppo_bind_peers: null / misaligned peer buffer");
+        p->px.bufs[r] = buffer_ptrs[r];
+    }
+    p->px.rank = rank;
+    p->px.world = world;
+    p->peers = 1;
+    p->seq_grad = p->seq_stat = 0;
+    return B200_OK;
+}
 int b200_tc_set_pair(int enable) {
     g_tc_pair = enable != 0;
     return B200_OK;

@@ -44,6 +44,46 @@ class Learner:
         self._h = h
         self.set_lr(cfg["algorithm"]["learning_rate"] if learning_rate is None else learning_rate)
         self.act_step = 0
+        self.peers_bound = False
+        self._peer_buf = self._peer_hdl = None
+
+    def bind_peers(self, group=None):
+        """Multi-GPU: exchange advantage moments / gradients / loss sums over NVLink peer memory inside the library's own kernels
+        (b200_ppo_bind_peers) instead of three NCCL all-reduces per epoch.  Needs torch.distributed (NCCL) initialised and a
+        symmetric-memory allocation peer-mapped across the node's ranks.  Returns False (and leaves the NCCL protocol of
+        Runner.update in charge) if symmetric memory is unavailable."""
+        import torch.distributed as dist
+
+        if self.world_size <= 1 or not dist.is_initialized():
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            group = group or dist.group.WORLD
+            nfloat = self._lib.b200_ppo_peer_buffer_bytes() // 4
+            buf = symm_mem.empty(nfloat, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            hdl = symm_mem.rendezvous(buf, group)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            if len(ptrs) != self.world_size:
+                raise RuntimeError(f"symmetric memory spans {len(ptrs)} ranks, the learner {self.world_size}")
+            arr = (C.c_ulonglong * len(ptrs))(*ptrs)
+            dist.barrier(group)            # every rank's flags are zero before anyone can post
+            _lib.check(self._lib.b200_ppo_bind_peers(self._h, arr, int(hdl.rank), len(ptrs)), "b200_ppo_bind_peers")
+            self._peer_buf, self._peer_hdl = buf, hdl
+            self.peers_bound = True
+        except Exception as ex:  # noqa: BLE001 - any failure keeps the (slower) NCCL protocol
+            import warnings
+
+            warnings.warn(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL all-reduce")
+            self.peers_bound = False
+        # all ranks must agree, otherwise the lockstep protocol deadlocks
+        flag = torch.tensor([1 if self.peers_bound else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0 and self.peers_bound:
+            raise _lib.B200Error("peer-memory exchange bound on this rank but not on all ranks")
+        return self.peers_bound
 
     # ---- parameter plumbing ---------------------------------------------------------------------------------------
     def _stream(self):

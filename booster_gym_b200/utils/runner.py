@@ -98,6 +98,8 @@ class Runner:
         self.model = ActorCritic(self.env.num_actions, self.env.num_obs, self.env.num_privileged_obs).bind(self.learner)
         if self.world_size > 1:
             torch.distributed.broadcast(self.learner.params, src=0)
+            if os.environ.get("B200_PEER_EXCHANGE", "1") != "0":
+                self.learner.bind_peers()   # NVLink peer-memory exchange inside the learner kernels (falls back to NCCL)
         self.optimizer = FlatAdam(self.model, self.learner)
         self._load()
 
@@ -198,7 +200,7 @@ class Runner:
         buf, lrn = self.buffer, self.learner
         lrn.old_dist(buf["obses"], buf["privileged_obses"], buf["actions"])
         dones, touts = buf.raw("dones"), buf.raw("time_outs")
-        multi = self.world_size > 1
+        multi = self.world_size > 1 and not lrn.peers_bound   # peers_bound: the library exchanges over NVLink peer memory itself
         for _ in range(self.cfg["runner"]["mini_epochs"]):
             lrn.epoch_a(buf["rewards"], dones, touts, obs, privileged_obs)
             if multi:

@@ -265,6 +265,14 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
 float* b200_ppo_buffer(B200Ppo* p, int which);
 /* replaces utils/runner.py:162-180: clip_grad_norm_(1.0), Adam step, KL-adaptive learning rate (all on device) */
 int b200_ppo_apply(B200Ppo* p, void* stream);
+/* Multi-GPU exchange over NVLink peer memory instead of three NCCL all-reduces per epoch.  Every rank allocates
+ * one SYMMETRIC device buffer of b200_ppo_peer_buffer_bytes() bytes, zero-filled, peer-mapped into all ranks of the node
+ * (torch.distributed._symmetric_memory.empty + rendezvous), and passes the device addresses of all ranks' buffers, indexed by
+ * rank.  After binding, b200_ppo_epoch_a posts this rank's advantage moments, b200_ppo_epoch_b sums all ranks' moments
+ * before the losses, and b200_ppo_apply sums gradients + loss sums over the peers (fused with the gradient norm): the caller
+ * must NOT all-reduce dstats / grads itself any more.  All ranks must call the epoch functions in lockstep. */
+long long b200_ppo_peer_buffer_bytes(void);
+int b200_ppo_bind_peers(B200Ppo* p, const unsigned long long* buffer_ptrs, int rank, int world);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------------------
  * b200_launch_count: kernels (and memset nodes) this library has launched in the calling process so far.
