@@ -162,10 +162,62 @@ class EnvOracle:
         world = ep + quat_rotate(eq, rel)
         s["feet_contact"] = np.any((world[:, 2] - self.h(world) < f32(0.01)).reshape(n, 2, k), axis=2)
 
+    # ---- envs/t1.py:391-413 (command curriculum): every successful episode raises its grid cell and the 4 neighbours
+    def update_curriculum(self, ids):
+        cm = self.cfg["commands"]
+        if not cm.get("curriculum"):
+            return
+        s = self.s
+        prob, lev = s["curriculum_prob"], s["env_curriculum_level"]
+        success = s["episode_length_buf"][ids].astype(f32) > f32(np.ceil(self.cfg["rewards"]["episode_length_s"] / self.dt) * (1 - cm["episode_length_toler"]))
+        success &= np.abs(s["filtered_lin_vel"][ids, 0] - s["commands"][ids, 0]) < f32(cm["lin_vel_x_toler"])
+        success &= np.abs(s["filtered_lin_vel"][ids, 1] - s["commands"][ids, 1]) < f32(cm["lin_vel_y_toler"])
+        success &= np.abs(s["filtered_ang_vel"][ids, 2] - s["commands"][ids, 2]) < f32(cm["ang_vel_yaw_toler"])
+        rate = f32(cm["update_rate"])
+        for i in np.nonzero(success)[0]:
+            x = int(lev[ids[i], 0]) + cm["lin_vel_levels"]
+            y = int(lev[ids[i], 1]) + cm["ang_vel_levels"]
+            prob[x, y] = f32(prob[x, y] + rate)
+            if x > 0:
+                prob[x - 1, y] = f32(prob[x - 1, y] + rate)
+            if x < prob.shape[0] - 1:
+                prob[x + 1, y] = f32(prob[x + 1, y] + rate)
+            if y > 0:
+                prob[x, y - 1] = f32(prob[x, y - 1] + rate)
+            if y < prob.shape[1] - 1:
+                prob[x, y + 1] = f32(prob[x, y + 1] + rate)
+        np.minimum(prob, f32(1.0), out=prob)
+
+    # torch.multinomial(prob.flatten(), k, replacement=True) restated as the inverse CDF of the SAME distribution on an injected
+    # uniform (torch's sampler cannot be fed samples): sequential fp32 running sum, first cell whose sum exceeds u * total
+    @staticmethod
+    def multinomial_icdf(prob_flat, u):
+        cdf = np.add.accumulate(prob_flat.astype(f32), dtype=f32)
+        target = (u.astype(f32) * cdf[-1]).astype(f32)
+        return np.minimum(np.searchsorted(cdf, target, side="right"), len(cdf) - 1).astype(np.int64)
+
+    # ---- envs/t1.py:415-435
+    def resample_curriculum_commands(self, ids, table):
+        s, cm = self.s, self.cfg["commands"]
+        prob = s["curriculum_prob"]
+        grid_idx = self.multinomial_icdf(prob.reshape(-1), _u(table, 7, 2)[ids])
+        # reference quirk (SURVEY 8a note 13): the flat index of the [lin, ang] grid is decoded as (idx % cols, idx // cols),
+        # i.e. the LINEAR level comes from the column (ang) coordinate and vice versa - a transposition of _update_curriculum's axes
+        lin = grid_idx % prob.shape[1] - cm["lin_vel_levels"]
+        ang = grid_idx // prob.shape[1] - cm["ang_vel_levels"]
+        s["env_curriculum_level"][ids, 0] = lin
+        s["env_curriculum_level"][ids, 1] = ang
+        def rnd(lo, hi, lane):
+            return (f32(hi - lo) * _u(table, 6, lane)[ids] + f32(lo)).astype(f32)
+        s["commands"][ids, 0] = ((lin.astype(f32) + rnd(-0.5, 0.5, 0)).astype(f32) * f32(cm["lin_vel_x_resolution"])).astype(f32)
+        s["commands"][ids, 1] = ((np.abs(lin).astype(f32) * rnd(-1.0, 1.0, 1)).astype(f32) * f32(cm["lin_vel_y_resolution"])).astype(f32)
+        s["commands"][ids, 2] = ((ang.astype(f32) + rnd(-0.5, 0.5, 2)).astype(f32) * f32(cm["ang_vel_resolution"])).astype(f32)
+
     # ---- envs/t1.py:301-341 for the envs in ids
     def reset_idx(self, ids, table):
         if len(ids) == 0:
             return
+        self.update_curriculum(ids)
         s, rz = self.s, self.cfg["randomization"]
         noise12 = np.stack([_n(table, i // 4, i % 4)[ids[0]] for i in range(12)]).astype(f32)  # one [1,12] draw for the whole call
         u12 = np.stack([_u(table, i // 4, i % 4)[ids[0]] for i in range(12)]).astype(f32)
@@ -213,7 +265,7 @@ class EnvOracle:
         if xmin.any() or xmax.any() or ymin.any() or ymax.any():
             self.refresh_feet()
 
-    # ---- envs/t1.py:362-389 (curriculum off)
+    # ---- envs/t1.py:362-389
     def resample_commands(self, table):
         s, cm = self.s, self.cfg["commands"]
         ids = np.nonzero(s["episode_length_buf"] == s["cmd_resample_time"])[0]
@@ -221,9 +273,12 @@ class EnvOracle:
             return
         def rnd(lo, hi, lane):  # torch_rand_float: (upper - lower) * rand + lower
             return (f32(hi - lo) * _u(table, 6, lane)[ids] + f32(lo)).astype(f32)
-        s["commands"][ids, 0] = rnd(*cm["lin_vel_x"], 0)
-        s["commands"][ids, 1] = rnd(*cm["lin_vel_y"], 1)
-        s["commands"][ids, 2] = rnd(*cm["ang_vel_yaw"], 2)
+        if cm.get("curriculum"):
+            self.resample_curriculum_commands(ids, table)
+        else:
+            s["commands"][ids, 0] = rnd(*cm["lin_vel_x"], 0)
+            s["commands"][ids, 1] = rnd(*cm["lin_vel_y"], 1)
+            s["commands"][ids, 2] = rnd(*cm["ang_vel_yaw"], 2)
         s["gait_frequency"][ids] = rnd(*cm["gait_frequency"], 3)
         still = ids[_u(table, 7, 0)[ids] < f32(cm["still_proportion"])]
         s["commands"][still, :] = 0.0

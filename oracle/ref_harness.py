@@ -178,6 +178,16 @@ class Injector:
             raise AssertionError(f"unexpected randint in phase {self.phase}")
         return torch.from_numpy(low + w % (high - low)).reshape(size)
 
+    def multinomial(self, probs, num_samples, replacement=False, **kw):
+        """torch.multinomial cannot be fed samples: served as the inverse CDF of the same distribution on the table's uniform
+        (slot 7, lane 2) - sequential fp32 running sum, first cell whose sum exceeds u * total (oracle/env_oracle.py, t1_env.cuh)"""
+        self._k("multinomial")
+        assert self.phase == "command" and replacement and num_samples == len(self.env_ids)
+        p = probs.detach().numpy().astype(np.float32)
+        cdf = np.add.accumulate(p, dtype=np.float32)
+        target = (tbl_u(self.table, 7, 2)[self.env_ids].astype(np.float32) * cdf[-1]).astype(np.float32)
+        return torch.from_numpy(np.minimum(np.searchsorted(cdf, target, side="right"), len(cdf) - 1).astype(np.int64))
+
     def randperm(self, m, **kw):
         self._k("randperm")
         assert self.phase == "command"
@@ -195,7 +205,7 @@ class patched_rng:
         self.inj = inj
 
     def __enter__(self):
-        self.saved = {k: getattr(torch, k) for k in ("randn_like", "rand_like", "rand", "randint", "randperm")}
+        self.saved = {k: getattr(torch, k) for k in ("randn_like", "rand_like", "rand", "randint", "randperm", "multinomial")}
         for k in self.saved:
             setattr(torch, k, getattr(self.inj, k))
 
@@ -267,6 +277,9 @@ def build_reference_env(mods, cfg, state, hf=None):
     e.last_feet_pos[:] = T(state["last_feet_pos"]).reshape(n, 2, 3)
     for key in STATE_KEYS_I:
         getattr(e, key)[:] = torch.tensor(state[key], dtype=torch.long)
+    if "curriculum_prob" in state:       # command curriculum (envs/t1.py:255-262)
+        e.curriculum_prob[:] = T(state["curriculum_prob"])
+        e.env_curriculum_level[:] = torch.tensor(state["env_curriculum_level"], dtype=torch.long)
     return e
 
 
@@ -316,6 +329,10 @@ def snapshot(e):
         last_feet_pos=e.last_feet_pos.reshape(n, 6), feet_pos=e.feet_pos.reshape(n, 6), episode_length_buf=e.episode_length_buf,
         cmd_resample_time=e.cmd_resample_time, delay_steps=e.delay_steps,
     )
+    if e.cfg["commands"].get("curriculum"):
+        out.update(curriculum_prob=e.curriculum_prob, env_curriculum_level=e.env_curriculum_level,
+                   mean_lin_vel_level=torch.as_tensor(e.mean_lin_vel_level), mean_ang_vel_level=torch.as_tensor(e.mean_ang_vel_level),
+                   max_lin_vel_level=torch.as_tensor(e.max_lin_vel_level), max_ang_vel_level=torch.as_tensor(e.max_ang_vel_level))
     res = {k: v.detach().clone().numpy() for k, v in out.items()}
     for name, v in e.extras["rew_terms"].items():
         res["term_" + name] = v.detach().clone().numpy()

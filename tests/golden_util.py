@@ -38,10 +38,16 @@ def load(name):
     return np.load(os.path.join(GOLD, name))
 
 
+CURRICULUM_KEYS = ["curriculum_prob", "env_curriculum_level"]
+
+
 def step_inputs(z):
     """state dict for the post-physics half: the fixture's input state with what the reference's (identity-physics)
     decimation loop left behind: clipped actions, mean torques, last_dof_targets"""
     st = {k: z["in_" + k].copy() for k in STATE_KEYS}
+    for k in CURRICULUM_KEYS:
+        if "in_" + k in z.files:
+            st[k] = z["in_" + k].copy()
     st["actions"] = z["post_loop_actions"].copy()
     st["torques"] = z["post_loop_torques"].copy()
     st["last_dof_targets"] = z["post_loop_last_dof_targets"].copy()

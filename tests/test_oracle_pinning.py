@@ -30,6 +30,30 @@ def test_env_oracle_step_matches_reference(name, terrain):
         assert close(out["terms"][t], z["out_term_" + t]), t
 
 
+def test_env_oracle_command_curriculum_matches_reference():
+    """SURVEY 8 f4 (envs/t1.py:391-435, `curriculum: true`): grid update on reset (success test, 4-neighbourhood, clamp), level draw
+    (inverse CDF on the injected uniform; the reference's transposed index decoding), level -> command formulas, bit-exact"""
+    from oracle.env_oracle import EnvOracle
+
+    z = load("env_step_curriculum.npz")
+    cfg = load_cfg("plane")
+    cfg["commands"]["curriculum"] = True
+    o = EnvOracle(cfg, step_inputs(z), None, model_json())
+    out = o.step_post(z["table"], int(z["common_step"]))
+    assert np.array_equal(o.s["curriculum_prob"].view(np.uint32), z["out_curriculum_prob"].view(np.uint32))
+    assert np.array_equal(o.s["env_curriculum_level"], z["out_env_curriculum_level"])
+    assert (z["out_curriculum_prob"] != z["in_curriculum_prob"]).sum() >= 10 and z["out_curriculum_prob"].max() == 1.0
+    assert (z["out_env_curriculum_level"] != z["in_env_curriculum_level"]).any(axis=1).sum() >= 20
+    for k in ("commands", "gait_frequency"):
+        assert np.array_equal(o.s[k].view(np.uint32), z["out_" + k].view(np.uint32)), k
+    for k in ("cmd_resample_time", "episode_length_buf"):
+        assert np.array_equal(o.s[k], z["out_" + k]), k
+    assert close(out["obs"], z["out_obs"]) and close(out["rew"], z["out_rew"])
+    lev = z["out_env_curriculum_level"]
+    assert float(z["out_mean_lin_vel_level"]) == pytest.approx(np.abs(lev[:, 0]).astype(np.float32).mean())
+    assert int(z["out_max_ang_vel_level"]) == np.abs(lev[:, 1]).max()
+
+
 def test_env_oracle_reset_matches_reference():
     from golden_util import STATE_KEYS
     from oracle.env_oracle import EnvOracle

@@ -113,6 +113,44 @@ def gen_env(mods):
             save["hf"] = hf
         np.savez_compressed(os.path.join(OUT, f"env_step_{terrain}_noreset.npz"), **save)
         print(terrain, "no-reset step: time_outs", int(out["time_out_buf"].sum()), "extras", int(out["extras_time_outs"].sum()))
+        if terrain == "plane":
+            # command curriculum (envs/t1.py:391-435, `curriculum: true`): successful episodes (time-out with the command tracked)
+            # raise the grid, failures do not; resampling envs draw a cell and derive their command from its levels
+            cfgc = copy.deepcopy(cfg)
+            cfgc["commands"]["curriculum"] = True
+            stc = synthetic_state(n, 41, False)
+            gg = np.random.default_rng(7)
+            L, A = cfgc["commands"]["lin_vel_levels"], cfgc["commands"]["ang_vel_levels"]
+            prob = np.zeros((2 * L + 1, 2 * A + 1), np.float32)
+            prob[L - 2: L + 3, A - 3: A + 4] = gg.uniform(0.0, 1.0, (5, 7)).astype(np.float32)
+            prob[L, A] = 1.0
+            prob[L + 1, A + 1] = 0.95          # += 0.1 must clamp to 1
+            lev = np.stack([gg.integers(-2, 3, n), gg.integers(-3, 4, n)], axis=1).astype(np.int64)
+            lev[0] = (-L, A)                   # grid corner: two neighbours fall outside
+            lev[9] = (1, 1)
+            stc["curriculum_prob"], stc["env_curriculum_level"] = prob, lev
+            # envs 1, 10, 19, ... time out this step (ep_len 1500 -> 1501): make most of them successes, a few near misses
+            stc["root_states"][:, 2] = 0.75
+            stc["root_states"][:, 7:13] *= 0.2
+            to = np.arange(1, n, 9)
+            stc["commands"][to] = gg.uniform(-0.5, 0.5, (len(to), 3)).astype(np.float32)
+            # the step first filters: filtered = 0.1 * base_vel + 0.9 * filtered -> choose filtered so that the error is small
+            stc["filtered_lin_vel"][to, 0:2] = stc["commands"][to, 0:2] / np.float32(0.9)
+            stc["filtered_ang_vel"][to, 2] = stc["commands"][to, 2] / np.float32(0.9)
+            stc["filtered_lin_vel"][to[2], 0] += 0.9      # x error > 0.4: not a success
+            stc["filtered_ang_vel"][to[3], 2] -= 0.5      # yaw error > 0.2: not a success
+            stc["episode_length_buf"][to[4]] = 1340        # early termination below the length tolerance (fails by height below)
+            stc["root_states"][to[4], 2] = 0.3
+            stc["episode_length_buf"][to[5]] = 1360        # terminated by height but long enough and on target: a success
+            stc["root_states"][to[5], 2] = 0.3
+            table, cap, out, log = run_reference_step(mods, cfgc, stc, None, 499, actions, 81)
+            save = {"in_" + k: v for k, v in stc.items()}
+            save.update({"out_" + k: v for k, v in out.items()})
+            save.update(actions_raw=actions, table=table, common_step=np.int64(500), post_loop_torques=cap["torques"],
+                        post_loop_last_dof_targets=cap["last_dof_targets"], post_loop_actions=cap["actions"])
+            np.savez_compressed(os.path.join(OUT, "env_step_curriculum.npz"), **save)
+            print("curriculum step: resets", int(out["reset_buf"].sum()), "grid delta", float((out["curriculum_prob"] - prob).sum()),
+                  "cells raised", int((out["curriculum_prob"] != prob).sum()), "levels changed", int((out["env_curriculum_level"] != lev).any(axis=1).sum()))
         if terrain == "trimesh":
             # reset(): every env resets, commands resampled for all, observations
             state3 = synthetic_state(n, 33, True)
