@@ -64,6 +64,9 @@ class T1Config(C.Structure):
         ("lin_vel_x", C.c_float * 2), ("lin_vel_y", C.c_float * 2), ("ang_vel_yaw", C.c_float * 2),
         ("gait_frequency", C.c_float * 2), ("still_proportion", C.c_float),
         ("resample_lo", C.c_int32), ("resample_hi", C.c_int32), ("curriculum", C.c_int32),
+        ("cur_lin_levels", C.c_int32), ("cur_ang_levels", C.c_int32), ("cur_update_rate", C.c_float),
+        ("cur_res_x", C.c_float), ("cur_res_y", C.c_float), ("cur_res_ang", C.c_float), ("cur_success_len", C.c_float),
+        ("cur_tol_x", C.c_float), ("cur_tol_y", C.c_float), ("cur_tol_yaw", C.c_float),
         ("n_rew", C.c_int32), ("rew_id", C.c_int32 * MAX_REW), ("rew_scale", C.c_float * MAX_REW),
         ("max_episode_length", C.c_int32), ("terminate_height", C.c_float), ("terminate_vel", C.c_float),
         ("only_positive_rewards", C.c_int32),

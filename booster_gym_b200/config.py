@@ -122,6 +122,14 @@ def t1_config(cfg):
     c.resample_lo = int(cm["resampling_time_s"][0] / dt)
     c.resample_hi = int(cm["resampling_time_s"][1] / dt)
     c.curriculum = 1 if cm.get("curriculum") else 0
+    # command curriculum (envs/T1.yaml:123-134, envs/t1.py:391-435); the grid is sized from the levels even when it is off
+    c.cur_lin_levels, c.cur_ang_levels = int(cm.get("lin_vel_levels", 0)), int(cm.get("ang_vel_levels", 0))
+    c.cur_update_rate = float(cm.get("update_rate", 0.0))
+    c.cur_res_x, c.cur_res_y = float(cm.get("lin_vel_x_resolution", 0.0)), float(cm.get("lin_vel_y_resolution", 0.0))
+    c.cur_res_ang = float(cm.get("ang_vel_resolution", 0.0))
+    c.cur_success_len = float(np.ceil(cfg["rewards"]["episode_length_s"] / dt) * (1 - cm.get("episode_length_toler", 0.0)))
+    c.cur_tol_x, c.cur_tol_y = float(cm.get("lin_vel_x_toler", 0.0)), float(cm.get("lin_vel_y_toler", 0.0))
+    c.cur_tol_yaw = float(cm.get("ang_vel_yaw_toler", 0.0))
     rw = cfg["rewards"]
     terms = reward_terms(cfg)
     c.n_rew = len(terms)

@@ -20,6 +20,11 @@ struct B200T1Handle {
     long long* ctr_dev;   // [0] rng step, [1] common_step_counter, [2..3] any-reset flags (parity)
     double* stats_dev;    // [1 + n_rew + 1] episode sums, then count as double
     const uint32_t* inject;  // parity-test hook (b200_t1_inject_rng); null in production
+    // command curriculum (cfg.curriculum): caller-owned grid, per-step success counts and running sums (library-owned)
+    float* cur_prob;
+    int32_t* cur_count;
+    float* cur_cdf;
+    int cur_cells;
 };
 
 namespace b200 {
@@ -41,6 +46,8 @@ inline EnvView make_view(const B200T1Handle* h) {
     v.env_base = h->env_base;
     v.seed = h->seed;
     v.inject = h->inject;
+    v.cur_count = h->cur_count;
+    v.cur_cdf = h->cur_cdf;
     return v;
 }
 // defined in physics_kernels.cu

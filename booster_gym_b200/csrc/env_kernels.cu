@@ -44,6 +44,8 @@ __device__ __forceinline__ void store_obs_rows(float* sbuf, const float* obs_l, 
     }
 }
 
+// PHASE 0: the whole post-physics step.  PHASE 1 / 2: the two halves around the command-curriculum grid update (t1_env.cuh).
+template <int PHASE>
 __global__ void __launch_bounds__(POST_BLOCK)
 k_post(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c, TerrainView terr,
        const long long* __restrict__ ctr, int noise_on, float* __restrict__ obs, float* __restrict__ priv,
@@ -55,10 +57,12 @@ k_post(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant_
     const long long step = ctr[0], common_step = ctr[1];
     float obs_l[B200_NOBS], priv_l[B200_NPRIV];
     if (e < v.n) {
-        const StepOut o = env_post_physics(v, e, m, c, terr, common_step, (uint64_t)step, noise_on, obs_l, priv_l, rew_terms);
+        const StepOut o = env_post_physics<B200T1ModelF, PHASE>(v, e, m, c, terr, common_step, (uint64_t)step, noise_on, obs_l, priv_l, rew_terms);
+        if (PHASE != 2) {
         rew[e] = o.rew;
         done[e] = (uint8_t)o.done;
-        if (o.done) {
+        }
+        if (PHASE != 2 && o.done) {
             flags[step & 1] = 1;  // benign race: every writer stores 1
             // device episode statistics (utils/recorder.py:36-62): flush this episode's sums
             float* f = v.f;
@@ -73,7 +77,14 @@ k_post(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant_
             IS(I_episode_steps) = 0;
         }
     }
-    store_obs_rows(sbuf, obs_l, priv_l, e0, v.n, obs, priv);
+    if (PHASE != 1) store_obs_rows(sbuf, obs_l, priv_l, e0, v.n, obs, priv);
+}
+
+// envs/t1.py:404-413 for the whole grid + the running sums the draws of :416 use (one block, one thread per cell)
+__global__ void k_curriculum_apply(float* __restrict__ prob, int32_t* __restrict__ count, float* __restrict__ cdf, int cells, float rate) {
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) curriculum_apply_cell(prob, count, i, rate);
+    __syncthreads();
+    if (threadIdx.x == 0) curriculum_scan(prob, cdf, cells);
 }
 
 // extras["time_outs"] is rebound only on steps where at least one env resets (envs/t1.py:317 vs :556, SURVEY 8a note 1)
@@ -84,6 +95,7 @@ __global__ void k_finalize_timeouts(const int32_t* __restrict__ is, int n, const
     if (flags[ctr[0] & 1]) time_out[e] = (uint8_t)is[(size_t)I_time_out_buf * n + e];
 }
 
+template <int PHASE>   // 0 = all; 1 = the resets, 2 = commands + observations (around the command-curriculum grid update)
 __global__ void __launch_bounds__(POST_BLOCK)
 k_reset_all(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c, TerrainView terr,
             const long long* __restrict__ ctr, float* __restrict__ obs, float* __restrict__ priv) {
@@ -94,14 +106,16 @@ k_reset_all(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_cons
     float obs_l[B200_NOBS], priv_l[B200_NPRIV];
     if (e < v.n) {
         // T1.reset(): _reset_idx(all) ; _resample_commands ; _compute_observations   (envs/t1.py:294-299)
-        env_reset_one(v, e, c, terr, step);
+        if (PHASE != 2) env_reset_one(v, e, c, terr, step);
         float* f = v.f;
         int32_t* is = v.is;
         const int n = v.n;
-        if (IS(I_episode_length_buf) == IS(I_cmd_resample_time)) env_resample_command(v, e, c, step);
-        env_observations(v, e, c, terr, step, 1, obs_l, priv_l);
+        if (PHASE != 1) {
+            if (IS(I_episode_length_buf) == IS(I_cmd_resample_time)) env_resample_command(v, e, c, step);
+            env_observations(v, e, c, terr, step, 1, obs_l, priv_l);
+        }
     }
-    store_obs_rows(sbuf, obs_l, priv_l, e0, v.n, obs, priv);
+    if (PHASE != 1) store_obs_rows(sbuf, obs_l, priv_l, e0, v.n, obs, priv);
 }
 
 __global__ void k_init_params(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c) {
@@ -151,7 +165,8 @@ int b200_t1_create(const B200T1ModelF* model, const B200T1Config* cfg, const int
         return set_error(B200_ERR_ARG, "trimesh terrain needs a heightfield");
     if (cfg->n_rew < 0 || cfg->n_rew > B200_MAX_REW) return set_error(B200_ERR_ARG, "bad reward count");
     if (cfg->decimation <= 0 || cfg->resample_hi <= cfg->resample_lo) return set_error(B200_ERR_ARG, "bad control/command config");
-    if (cfg->curriculum) return set_error(B200_ERR_UNSUPPORTED, "command curriculum is not built yet (SURVEY 8 f4)");
+    if (cfg->curriculum && (cfg->cur_lin_levels < 0 || cfg->cur_ang_levels < 0 || (2 * cfg->cur_lin_levels + 1) * (2 * cfg->cur_ang_levels + 1) > 4096))
+        return set_error(B200_ERR_ARG, "bad command-curriculum grid");
     CUDA_TRY(cudaSetDevice(device));
     B200T1Handle* h = new (std::nothrow) B200T1Handle();
     if (!h) return set_error(B200_ERR_ARG, "out of host memory");
@@ -174,6 +189,12 @@ int b200_t1_create(const B200T1ModelF* model, const B200T1Config* cfg, const int
     CUDA_TRY(cudaMemset(h->ctr_dev, 0, 4 * sizeof(long long)));
     CUDA_TRY(cudaMalloc(&h->stats_dev, (B200_MAX_REW + 4) * sizeof(double)));
     CUDA_TRY(cudaMemset(h->stats_dev, 0, (B200_MAX_REW + 4) * sizeof(double)));
+    if (cfg->curriculum) {
+        h->cur_cells = (2 * cfg->cur_lin_levels + 1) * (2 * cfg->cur_ang_levels + 1);
+        CUDA_TRY(cudaMalloc(&h->cur_count, h->cur_cells * sizeof(int32_t)));
+        CUDA_TRY(cudaMemset(h->cur_count, 0, h->cur_cells * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&h->cur_cdf, h->cur_cells * sizeof(float)));
+    }
     *out = h;
     return B200_OK;
 }
@@ -184,6 +205,8 @@ int b200_t1_destroy(B200T1Handle* h) {
     if (h->hf_dev) cudaFree(h->hf_dev);
     if (h->ctr_dev) cudaFree(h->ctr_dev);
     if (h->stats_dev) cudaFree(h->stats_dev);
+    if (h->cur_count) cudaFree(h->cur_count);
+    if (h->cur_cdf) cudaFree(h->cur_cdf);
     delete h;
     return B200_OK;
 }
@@ -192,6 +215,14 @@ int b200_t1_bind_state(B200T1Handle* h, float* fstate, int32_t* istate) {
     if (!h || !fstate || !istate) return set_error(B200_ERR_ARG, "b200_t1_bind_state: null pointer");
     h->fstate = fstate;
     h->istate = istate;
+    return B200_OK;
+}
+int b200_t1_bind_curriculum(B200T1Handle* h, float* prob, int rows, int cols) {
+    if (!h || !prob) return set_error(B200_ERR_ARG, "b200_t1_bind_curriculum: null pointer");
+    if (!h->cfg.curriculum) return set_error(B200_ERR_STATE, "b200_t1_bind_curriculum: the command curriculum is disabled in this config");
+    if (rows != 2 * h->cfg.cur_lin_levels + 1 || cols != 2 * h->cfg.cur_ang_levels + 1)
+        return set_error(B200_ERR_ARG, "b200_t1_bind_curriculum: grid shape must be [2 lin_vel_levels + 1, 2 ang_vel_levels + 1]");
+    h->cur_prob = prob;
     return B200_OK;
 }
 int b200_t1_inject_rng(B200T1Handle* h, const uint32_t* table) {
@@ -204,7 +235,13 @@ int b200_t1_num_envs(const B200T1Handle* h) { return h ? h->num_envs : B200_ERR_
 
 #define NEED_STATE(h)                                                                  \
     if (!(h)) return set_error(B200_ERR_ARG, "null handle");                           \
-    if (!(h)->fstate || !(h)->istate) return set_error(B200_ERR_STATE, "state not bound")
+    if (!(h)->fstate || !(h)->istate) return set_error(B200_ERR_STATE, "state not bound"); \
+    if ((h)->cfg.curriculum && !(h)->cur_prob) return set_error(B200_ERR_STATE, "command curriculum enabled but no grid bound (b200_t1_bind_curriculum)")
+
+static void launch_curriculum_apply(B200T1Handle* h, cudaStream_t st) {
+    k_curriculum_apply<<<1, 512, 0, st>>>(h->cur_prob, h->cur_count, h->cur_cdf, h->cur_cells, h->cfg.cur_update_rate);
+    g_launches += 1;
+}
 
 int b200_t1_init_params(B200T1Handle* h, int env_index_base, int total_envs, void* stream) {
     NEED_STATE(h);
@@ -221,8 +258,15 @@ int b200_t1_reset(B200T1Handle* h, float* obs, float* priv, void* stream) {
     if (!obs || !priv) return set_error(B200_ERR_ARG, "b200_t1_reset: null output");
     cudaStream_t st = (cudaStream_t)stream;
     k_advance<<<1, 1, 0, st>>>(h->ctr_dev, -1, 0);
-    k_reset_all<<<(h->num_envs + POST_BLOCK - 1) / POST_BLOCK, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg,
-                                                                                    make_terrain(h), h->ctr_dev, obs, priv);
+    const int grid = (h->num_envs + POST_BLOCK - 1) / POST_BLOCK;
+    if (h->cfg.curriculum) {
+        k_reset_all<1><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, obs, priv);
+        launch_curriculum_apply(h, st);
+        k_reset_all<2><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, obs, priv);
+        g_launches += 1;
+    } else {
+        k_reset_all<0><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, obs, priv);
+    }
     g_launches += 2;
     return launch_status("k_reset_all");
 }
@@ -236,9 +280,18 @@ int b200_t1_physics(B200T1Handle* h, const float* actions, int n_substeps, int a
 
 static int launch_post(B200T1Handle* h, float* obs, float* priv, float* rew, uint8_t* done, uint8_t* time_out,
                        float* rew_terms, int noise_on, cudaStream_t st) {
-    k_post<<<(h->num_envs + POST_BLOCK - 1) / POST_BLOCK, POST_BLOCK, 0, st>>>(
-        make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done, rew_terms,
-        h->ctr_dev + 2, h->stats_dev);
+    const int grid = (h->num_envs + POST_BLOCK - 1) / POST_BLOCK;
+    if (h->cfg.curriculum) {
+        k_post<1><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done,
+                                               rew_terms, h->ctr_dev + 2, h->stats_dev);
+        launch_curriculum_apply(h, st);
+        k_post<2><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done,
+                                               rew_terms, h->ctr_dev + 2, h->stats_dev);
+        g_launches += 1;
+    } else {
+        k_post<0><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done,
+                                               rew_terms, h->ctr_dev + 2, h->stats_dev);
+    }
     k_finalize_timeouts<<<(h->num_envs + 255) / 256, 256, 0, st>>>(h->istate, h->num_envs, h->ctr_dev, h->ctr_dev + 2, time_out);
     g_launches += 2;
     return launch_status("k_post");

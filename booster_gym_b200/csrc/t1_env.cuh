@@ -27,6 +27,10 @@ struct EnvView {
     // kernel, the CPU oracle and the reference (with torch.randn_like & co. patched) run on identical samples.
     // Layout: uint32 [B200_RNG_SLOTS][12][n]: per slot 4 raw words, 4 uniforms (float bits), 4 normals (float bits).
     const uint32_t* inject;
+    // command curriculum (null when off): per-cell success counts of this step (k_curriculum_apply turns them into the grid
+    // update) and the running sums of the grid the resampling envs draw from
+    int32_t* cur_count;
+    const float* cur_cdf;
 };
 
 // slot of a step-time draw in the injection table; -1 for the one-off construction draws (never injected)
@@ -379,12 +383,54 @@ B200_HD float reward_term(int id, const RewardSnap& s, const B200T1Config& c, fl
     return 0.0f;
 }
 
+// envs/t1.py:391-413 for ONE resetting env: a successful episode (long enough, command tracked) raises its grid cell and the
+// 4 neighbours by update_rate.  The adds are recorded as integer COUNTS per cell; k_curriculum_apply performs them as the
+// reference does (count sequential fp32 adds of the rate, then clamp to 1) - order-free and bit-exact.
+B200_HD void env_update_curriculum(const EnvView& v, int e, const B200T1Config& c) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
+    bool success = (float)IS(I_episode_length_buf) > c.cur_success_len;
+    success = success && (fabsf(FS(F_filtered_lin_vel + 0) - FS(F_commands + 0)) < c.cur_tol_x);
+    success = success && (fabsf(FS(F_filtered_lin_vel + 1) - FS(F_commands + 1)) < c.cur_tol_y);
+    success = success && (fabsf(FS(F_filtered_ang_vel + 2) - FS(F_commands + 2)) < c.cur_tol_yaw);
+    if (!success || v.cur_count == nullptr) return;
+    const int rows = 2 * c.cur_lin_levels + 1, cols = 2 * c.cur_ang_levels + 1;
+    const int x = IS(I_env_curriculum_level + 0) + c.cur_lin_levels, y = IS(I_env_curriculum_level + 1) + c.cur_ang_levels;
+    if (x < 0 || x >= rows || y < 0 || y >= cols) return;
+#if defined(__CUDA_ARCH__)
+#define B200_CUR_INC(ix) atomicAdd(v.cur_count + (ix), 1)
+#else
+#define B200_CUR_INC(ix) (v.cur_count[(ix)] += 1)
+#endif
+    B200_CUR_INC(x * cols + y);
+    if (x > 0) B200_CUR_INC((x - 1) * cols + y);
+    if (x < rows - 1) B200_CUR_INC((x + 1) * cols + y);
+    if (y > 0) B200_CUR_INC(x * cols + y - 1);
+    if (y < cols - 1) B200_CUR_INC(x * cols + y + 1);
+#undef B200_CUR_INC
+}
+
+// the grid update of one step (:404-413) and the running sums for the draws of :416 - ONE thread per cell, thread 0 scans
+template <typename IntT>
+B200_HD void curriculum_apply_cell(float* prob, IntT* count, int i, float rate) {
+    float p = prob[i];
+    for (int k = (int)count[i]; k > 0; --k) p = p + rate;
+    prob[i] = fminf(p, 1.0f);
+    count[i] = 0;
+}
+B200_HD void curriculum_scan(const float* prob, float* cdf, int cells) {
+    float run = 0.0f;
+    for (int i = 0; i < cells; ++i) { run = run + prob[i]; cdf[i] = run; }
+}
+
 // envs/t1.py:301-341 for ONE env (always resets; the caller decides).  `step` = RNG counter of this call.
 B200_HD void env_reset_one(const EnvView& v, int e, const B200T1Config& c, const TerrainView& terr, uint64_t step) {
     float* f = v.f;
     int32_t* is = v.is;
     const int n = v.n;
     const uint32_t ge = (uint32_t)(v.env_base + e);
+    if (c.curriculum) env_update_curriculum(v, e, c);   // :305, before the episode's state is overwritten
     // _reset_dofs :319-325.  Reference quirk (SURVEY 8a note 12): the noise has the shape of default_dof_pos, [1,12],
     // so every env that resets in the same call receives the SAME 12 joint offsets -> the draw is keyed by the step
     // only (env id B200_RNG_SHARED_ENV), not by the env.
@@ -436,7 +482,7 @@ B200_HD void env_reset_one(const EnvView& v, int e, const B200T1Config& c, const
     IS(I_delay_steps) = (int32_t)(d.w[0] % (uint32_t)c.decimation);
 }
 
-// envs/t1.py:362-389 (non-curriculum branch) for one env whose episode_length == cmd_resample_time
+// envs/t1.py:362-389 (+ :415-435 when the curriculum is on) for one env whose episode_length == cmd_resample_time
 B200_HD void env_resample_command(const EnvView& v, int e, const B200T1Config& c, uint64_t step) {
     float* f = v.f;
     int32_t* is = v.is;
@@ -445,9 +491,31 @@ B200_HD void env_resample_command(const EnvView& v, int e, const B200T1Config& c
     const Draw d0 = env_draw(v, e, ge, step, RP_COMMAND, 0);
     const Draw d1 = env_draw(v, e, ge, step, RP_COMMAND, 1);
     // torch_rand_float(lo, hi) = (hi - lo) * rand + lo
-    float cx = (c.lin_vel_x[1] - c.lin_vel_x[0]) * d0.r.u[0] + c.lin_vel_x[0];
-    float cy = (c.lin_vel_y[1] - c.lin_vel_y[0]) * d0.r.u[1] + c.lin_vel_y[0];
-    float cz = (c.ang_vel_yaw[1] - c.ang_vel_yaw[0]) * d0.r.u[2] + c.ang_vel_yaw[0];
+    float cx, cy, cz;
+    if (c.curriculum && v.cur_cdf != nullptr) {
+        // _resample_curriculum_commands :415-435.  torch.multinomial(prob.flatten(), ., replacement=True) is restated as the inverse
+        // CDF of the same distribution on this env's uniform (no torch sampler on the device): first cell whose running fp32 sum
+        // exceeds u * total.  The grid was updated and scanned by k_curriculum_apply after this step's resets (:305 before :488).
+        const int cols = 2 * c.cur_ang_levels + 1, cells = (2 * c.cur_lin_levels + 1) * cols;
+        const float target = d1.r.u[2] * v.cur_cdf[cells - 1];
+        int lo = 0, hi = cells - 1;             // smallest i with cdf[i] > target, clamped to the last cell
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (v.cur_cdf[mid] > target) hi = mid; else lo = mid + 1;
+        }
+        // reference quirk (SURVEY 8a note 13): the flat index of the [lin, ang] grid is decoded as (idx % cols, idx // cols)
+        const int lin = lo % cols - c.cur_lin_levels, ang = lo / cols - c.cur_ang_levels;
+        IS(I_env_curriculum_level + 0) = lin;
+        IS(I_env_curriculum_level + 1) = ang;
+        const float r0 = (0.5f - -0.5f) * d0.r.u[0] + -0.5f, r1 = (1.0f - -1.0f) * d0.r.u[1] + -1.0f, r2 = (0.5f - -0.5f) * d0.r.u[2] + -0.5f;
+        cx = ((float)lin + r0) * c.cur_res_x;
+        cy = ((float)(lin < 0 ? -lin : lin) * r1) * c.cur_res_y;
+        cz = ((float)ang + r2) * c.cur_res_ang;
+    } else {
+        cx = (c.lin_vel_x[1] - c.lin_vel_x[0]) * d0.r.u[0] + c.lin_vel_x[0];
+        cy = (c.lin_vel_y[1] - c.lin_vel_y[0]) * d0.r.u[1] + c.lin_vel_y[0];
+        cz = (c.ang_vel_yaw[1] - c.ang_vel_yaw[0]) * d0.r.u[2] + c.ang_vel_yaw[0];
+    }
     float gf = (c.gait_frequency[1] - c.gait_frequency[0]) * d0.r.u[3] + c.gait_frequency[0];
     // reference: an exact still_proportion of the resampled envs via randperm (:381); here an independent Bernoulli
     // draw per env (no cross-env dependency on the device) - DESIGN.md "deviations"
@@ -547,7 +615,10 @@ struct StepOut {
 
 // envs/t1.py:460-497 for one env.  common_step = common_step_counter after the increment (:477); step = RNG counter.
 // stats (nullable): double[1 + n_rew + 1] sums + int64 count at stats_count, accumulated with atomics on the device.
-template <typename Model>
+// PHASE 0 = the whole step.  With the command curriculum the resampling envs draw from a grid that ALL of this step's resets
+// have updated first (:305 before :488), a dependency across envs: PHASE 1 stops after the resets (:460-486), the grid is
+// updated (k_curriculum_apply), PHASE 2 finishes the step (:487-495).  Nothing but the env's state crosses the cut.
+template <typename Model, int PHASE = 0>
 B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr,
                                  int64_t common_step, uint64_t step, int noise_on, float* obs, float* priv,
                                  float* rew_terms /* [n_rew][n] or null */) {
@@ -555,6 +626,9 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     int32_t* is = v.is;
     const int n = v.n;
     const uint32_t ge = (uint32_t)(v.env_base + e);
+    StepOut o;
+    o.rew = 0.0f; o.done = 0; o.time_out = 0;
+    if (PHASE != 2) {
     // :463-473
     float q[4] = {FS(F_root_states + 3), FS(F_root_states + 4), FS(F_root_states + 5), FS(F_root_states + 6)};
     {
@@ -635,6 +709,11 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     IS(I_episode_steps) += 1;
     // :485-488
     if (reset) env_reset_one(v, e, c, terr, step);
+    o.rew = rew;
+    o.done = reset ? 1 : 0;
+    o.time_out = time_out ? 1 : 0;
+    if (PHASE == 1) return o;
+    }
     env_teleport(v, e, m, c, terr);
     if (IS(I_episode_length_buf) == IS(I_cmd_resample_time)) env_resample_command(v, e, c, step);
     // :490
@@ -644,10 +723,6 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     for (int j = 0; j < 12; ++j) { FS(F_last_actions + j) = FS(F_actions + j); FS(F_last_dof_vel + j) = FS(F_dof_vel + j); }
 #pragma unroll
     for (int j = 0; j < 6; ++j) { FS(F_last_root_vel + j) = FS(F_root_states + 7 + j); FS(F_last_feet_pos + j) = FS(F_feet_pos + j); }
-    StepOut o;
-    o.rew = rew;
-    o.done = reset ? 1 : 0;
-    o.time_out = time_out ? 1 : 0;
     return o;
 }
 

@@ -51,7 +51,8 @@
     X(reset_buf, 1)                                                                                              \
     X(time_out_buf, 1)                                                                                           \
     X(episode_steps, 1)     /* utils/recorder.py:37-43 */                                                         \
-    X(nan_resets, 1)
+    X(nan_resets, 1)                                                                                             \
+    X(env_curriculum_level, 2) /* (lin, ang) level of the current command (envs/t1.py:262) */
 
 namespace b200 {
 

@@ -74,6 +74,14 @@ class T1(BaseTask):
         _lib.check(self._lib.b200_t1_bind_state(self._h, self._fstate.data_ptr(), self._istate.data_ptr()), "bind_state")
         self._ffields = _lib.field_table(0)
         self._ifields = _lib.field_table(1)
+        # command-curriculum grid (envs/t1.py:255-262): a device tensor the kernels update in place; the Runner reads / assigns
+        # `env.curriculum_prob` for checkpoints (utils/runner.py:91,211) - the setter copies INTO this buffer
+        cm = cfg["commands"]
+        self._curriculum_prob = torch.zeros(1 + 2 * cm["lin_vel_levels"], 1 + 2 * cm["ang_vel_levels"], dtype=torch.float, device=dev)
+        self._curriculum_prob[cm["lin_vel_levels"], cm["ang_vel_levels"]] = 1.0
+        if cm.get("curriculum"):
+            _lib.check(self._lib.b200_t1_bind_curriculum(self._h, self._curriculum_prob.data_ptr(), self._curriculum_prob.shape[0],
+                                                         self._curriculum_prob.shape[1]), "bind_curriculum")
 
         self._get_env_origins()
         _lib.check(self._lib.b200_t1_init_params(self._h, self._env_index_base, self._total_envs, self._stream()), "init_params")
@@ -140,14 +148,32 @@ class T1(BaseTask):
         self.gravity_vec = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat((n, 1))
         self.default_dof_pos = torch.tensor([list(self._c_cfg.default_dof_pos)], dtype=torch.float, device=dev)
 
-        cm = cfg["commands"]
-        self.curriculum_prob = torch.zeros(1 + 2 * cm["lin_vel_levels"], 1 + 2 * cm["ang_vel_levels"], dtype=torch.float, device=dev)
-        self.curriculum_prob[cm["lin_vel_levels"], cm["ang_vel_levels"]] = 1.0
-        self.env_curriculum_level = torch.zeros(n, 2, dtype=torch.long, device=dev)
-        self.mean_lin_vel_level = 0.0
-        self.mean_ang_vel_level = 0.0
-        self.max_lin_vel_level = 0.0
-        self.max_ang_vel_level = 0.0
+        self.env_curriculum_level = self._iview("env_curriculum_level")   # [N, 2] (lin, ang) level of the current command
+
+    # ---- command curriculum surface (envs/t1.py:255-262, 419-422; read by utils/runner.py:91,198-201,211) -------------------
+    @property
+    def curriculum_prob(self):
+        return self._curriculum_prob
+
+    @curriculum_prob.setter
+    def curriculum_prob(self, value):
+        self._curriculum_prob.copy_(torch.as_tensor(value).to(device=self._curriculum_prob.device, dtype=torch.float).reshape(self._curriculum_prob.shape))
+
+    @property
+    def mean_lin_vel_level(self):
+        return torch.mean(torch.abs(self.env_curriculum_level[:, 0]).float())
+
+    @property
+    def mean_ang_vel_level(self):
+        return torch.mean(torch.abs(self.env_curriculum_level[:, 1]).float())
+
+    @property
+    def max_lin_vel_level(self):
+        return torch.max(torch.abs(self.env_curriculum_level[:, 0]))
+
+    @property
+    def max_ang_vel_level(self):
+        return torch.max(torch.abs(self.env_curriculum_level[:, 1]))
 
     def _prepare_reward_function(self):
         terms = config.reward_terms(self.cfg)

@@ -216,8 +216,18 @@ class Runner:
         obs, infos = self.env.reset()
         privileged_obs = infos["privileged_obs"]
         SC = _abi.SC
+        cur_multi = self.world_size > 1 and bool(self.cfg["commands"].get("curriculum"))
         for it in range(self.cfg["basic"]["max_iterations"]):
+            if cur_multi:
+                cur_before = self.env.curriculum_prob.clone()
             obs, privileged_obs = self.rollout(obs, privileged_obs)
+            if cur_multi:
+                # every rank raised its own copy of the command-curriculum grid from its own envs' successes; merge once per
+                # iteration: sum of the ranks' increments on top of the common starting grid, clamped like envs/t1.py:413
+                # (SURVEY 8e "other cross-rank state"; a single-process run clamps after every step instead - same fixed point)
+                delta = self.env.curriculum_prob - cur_before
+                torch.distributed.all_reduce(delta)
+                self.env.curriculum_prob = torch.clamp(cur_before + delta, max=1.0)
             self.learner.scalars[SC["SUM_VALUE_LOSS"]:SC["EPOCHS"] + 1].zero_()
             self.update(obs, privileged_obs)
             sc = self.learner.scalars.cpu()  # the one host sync of the iteration

@@ -103,7 +103,12 @@ typedef struct B200T1Config {
     float lin_vel_x[2], lin_vel_y[2], ang_vel_yaw[2], gait_frequency[2];
     float still_proportion;
     int32_t resample_lo, resample_hi; /* int(s/dt) */
-    int32_t curriculum;
+    int32_t curriculum;               /* envs/T1.yaml:124: command curriculum (envs/t1.py:391-435) */
+    int32_t cur_lin_levels, cur_ang_levels;      /* grid = [2 lin + 1][2 ang + 1] */
+    float cur_update_rate;
+    float cur_res_x, cur_res_y, cur_res_ang;     /* lin_vel_x_resolution, lin_vel_y_resolution, ang_vel_resolution */
+    float cur_success_len;                       /* ceil(episode_length_s / dt) * (1 - episode_length_toler) */
+    float cur_tol_x, cur_tol_y, cur_tol_yaw;
     /* rewards (envs/T1.yaml:251-291) */
     int32_t n_rew;                    /* number of non-zero scales, YAML order */
     int32_t rew_id[B200_MAX_REW];     /* B200_REW_* per active term */
@@ -179,6 +184,10 @@ int b200_rng_fill(const B200T1Handle* h, uint64_t step, int purpose, int sub, in
  * as float bits); while set, reset()/step() READ their random draws from it instead of generating them, so kernel,
  * CPU oracle and the reference (torch.randn_like & co. patched) see identical samples. NULL restores Philox.
  * Slots: 0-2 reset dof noise, 3-4 reset root, 5 delay, 6-7 command, 8-9 kick, 10-11 push, 12-20 observation noise. */
+/* Command curriculum (`commands.curriculum: true`): `prob` is the caller-owned device grid float[(2 lin + 1) * (2 ang + 1)]
+ * (env.curriculum_prob, row-major [lin, ang]); resets of successful episodes raise it, command resampling draws from it.
+ * Must be bound before the first reset/step when the curriculum is enabled. */
+int b200_t1_bind_curriculum(B200T1Handle* h, float* prob, int rows, int cols);
 int b200_t1_inject_rng(B200T1Handle* h, const uint32_t* table);
 int b200_t1_rng_slots(void);
 

@@ -82,6 +82,34 @@ int hc_env_post(const B200T1ModelF* m, const B200T1Config* c, const int16_t* hf,
         for (int e = 0; e < n; ++e) time_out_extras[e] = (uint8_t)istate[(size_t)I_time_out_buf * n + e];
     return any;
 }
+// the command-curriculum step (cfg.curriculum): what k_post<1>, k_curriculum_apply, k_post<2> do, serially
+int hc_env_post_curriculum(const B200T1ModelF* m, const B200T1Config* c, float* fstate, int32_t* istate, int n, const uint32_t* inject,
+                           long long common_step, unsigned long long step, int noise_on, float* prob, float* obs, float* priv,
+                           float* rew, uint8_t* done, uint8_t* time_out_extras, float* rew_terms) {
+    const int cells = (2 * c->cur_lin_levels + 1) * (2 * c->cur_ang_levels + 1);
+    int32_t* count = new int32_t[cells]();
+    float* cdf = new float[cells]();
+    EnvView v{fstate, istate, n, 0, 42ull, inject, count, cdf};
+    const TerrainView tv = make_tv(c, nullptr, 0, 0);
+    int any = 0;
+    for (int e = 0; e < n; ++e) {
+        const StepOut o = env_post_physics<B200T1ModelF, 1>(v, e, *m, *c, tv, common_step, step, noise_on, obs + (size_t)e * B200_NOBS,
+                                                            priv + (size_t)e * B200_NPRIV, rew_terms);
+        rew[e] = o.rew;
+        done[e] = (uint8_t)o.done;
+        any |= o.done;
+    }
+    for (int i = 0; i < cells; ++i) curriculum_apply_cell(prob, count, i, c->cur_update_rate);
+    curriculum_scan(prob, cdf, cells);
+    for (int e = 0; e < n; ++e)
+        env_post_physics<B200T1ModelF, 2>(v, e, *m, *c, tv, common_step, step, noise_on, obs + (size_t)e * B200_NOBS,
+                                          priv + (size_t)e * B200_NPRIV, rew_terms);
+    if (any)
+        for (int e = 0; e < n; ++e) time_out_extras[e] = (uint8_t)istate[(size_t)I_time_out_buf * n + e];
+    delete[] count;
+    delete[] cdf;
+    return any;
+}
 int hc_env_reset_all(const B200T1ModelF* m, const B200T1Config* c, const int16_t* hf, int rows, int cols, float* fstate,
                      int32_t* istate, int n, const uint32_t* inject, unsigned long long step, float* obs, float* priv) {
     EnvView v{fstate, istate, n, 0, 42ull, inject};

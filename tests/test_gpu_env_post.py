@@ -129,3 +129,93 @@ def test_post_physics_kernel_matches_oracle_full_size(terrain, common_step):
     got, terms = gpu_step(cfg, st, table, common_step, hf)
     compare(got, terms, ref, out["terms"])
     assert out["reset_buf"].sum() > 100 and out["time_out_buf"].sum() > 100
+
+
+def _curriculum_cfg():
+    cfg = load_cfg("plane")
+    cfg["commands"]["curriculum"] = True
+    return cfg
+
+
+def test_command_curriculum_kernels_match_reference_fixture():
+    """SURVEY 8 f4 (envs/t1.py:391-435): k_post<1> -> k_curriculum_apply -> k_post<2> through the public T1 API against the golden
+    the reference produced with `curriculum: true`: grid bit-exact, levels exact, commands bit-exact, everything else as usual"""
+    z = load("env_step_curriculum.npz")
+    cfg = _curriculum_cfg()
+    st = step_inputs(z)
+    n = st["root_states"].shape[0]
+    env = make_env(cfg, n)
+    load_state(env, st)
+    env.curriculum_prob = torch.from_numpy(z["in_curriculum_prob"])          # the checkpoint-loading path (utils/runner.py:91)
+    env.inject_rng(torch.from_numpy(z["table"].view(np.int32)).cuda())
+    env.common_step_counter = int(z["common_step"]) - 1
+    obs, rew, done, extras = env.post_physics(noise=True)
+    torch.cuda.synchronize()
+    got = read_state(env)
+    assert np.array_equal(env.curriculum_prob.cpu().numpy().view(np.uint32), z["out_curriculum_prob"].view(np.uint32))
+    assert np.array_equal(got["env_curriculum_level"].astype(np.int64), z["out_env_curriculum_level"])
+    assert np.array_equal(got["commands"].view(np.uint32), z["out_commands"].view(np.uint32))
+    assert float(env.mean_lin_vel_level) == pytest.approx(float(z["out_mean_lin_vel_level"]))
+    assert float(env.mean_ang_vel_level) == pytest.approx(float(z["out_mean_ang_vel_level"]))
+    assert int(env.max_lin_vel_level) == int(z["out_max_lin_vel_level"]) and int(env.max_ang_vel_level) == int(z["out_max_ang_vel_level"])
+    got.update(obs=obs.cpu().numpy(), priv=extras["privileged_obs"].cpu().numpy(), rew=rew.cpu().numpy(),
+               reset_buf=done.cpu().numpy(), extras_time_outs=extras["time_outs"].cpu().numpy())
+    terms = {k: v.cpu().numpy() for k, v in extras["rew_terms"].items()}
+    ref = {k: z["out_" + k] for k in OUT_EXACT + OUT_FLOAT}
+    ref_terms = {f[len("out_term_"):]: z[f] for f in z.files if f.startswith("out_term_")}
+    compare(got, terms, ref, ref_terms)
+    env.close()
+
+
+def test_command_curriculum_full_size_and_closed_loop():
+    """N = 4096: kernel vs the pinned oracle on a synthetic state with a partly filled grid (identical injected draws), then 300 real
+    steps of the public API with the curriculum on: the grid only grows, stays in [0, 1], levels stay inside the grid"""
+    from oracle.env_oracle import EnvOracle
+    from oracle.ref_harness import make_table
+    from oracle.synth import synthetic_state
+
+    n = 4096
+    cfg = _curriculum_cfg()
+    L, A = cfg["commands"]["lin_vel_levels"], cfg["commands"]["ang_vel_levels"]
+    st = synthetic_state(n, 77, False)
+    g = np.random.default_rng(9)
+    st["actions"] = g.uniform(-1, 1, (n, 12)).astype(np.float32)
+    st["torques"] = g.normal(0, 8, (n, 12)).astype(np.float32)
+    st["root_states"][:, 7:13] *= 0.2
+    to = np.arange(1, n, 9)                           # the envs whose episode times out this step: make them track their command
+    st["filtered_lin_vel"][to, 0:2] = st["commands"][to, 0:2] / np.float32(0.9)
+    st["filtered_ang_vel"][to, 2] = st["commands"][to, 2] / np.float32(0.9)
+    prob = np.zeros((2 * L + 1, 2 * A + 1), np.float32)
+    prob[L - 4: L + 5, A - 4: A + 5] = g.uniform(0, 1, (9, 9)).astype(np.float32)
+    st["curriculum_prob"] = prob
+    st["env_curriculum_level"] = np.stack([g.integers(-L, L + 1, n), g.integers(-A, A + 1, n)], axis=1).astype(np.int64)
+    table = make_table(n, 6)
+    o = EnvOracle(cfg, st, None, model_json())
+    out = o.step_post(table, 500)
+    env = make_env(cfg, n)
+    load_state(env, st)
+    env.curriculum_prob = torch.from_numpy(prob)
+    env.inject_rng(torch.from_numpy(table.view(np.int32)).cuda())
+    env.common_step_counter = 499
+    obs, rew, done, extras = env.post_physics(noise=True)
+    torch.cuda.synchronize()
+    got = read_state(env)
+    assert (o.s["curriculum_prob"] != prob).sum() > 50
+    assert np.array_equal(env.curriculum_prob.cpu().numpy().view(np.uint32), o.s["curriculum_prob"].view(np.uint32))
+    assert np.array_equal(got["env_curriculum_level"].astype(np.int64), o.s["env_curriculum_level"])
+    assert np.array_equal(got["commands"].view(np.uint32), o.s["commands"].view(np.uint32))
+    assert close(obs.cpu().numpy(), out["obs"]) and close(rew.cpu().numpy(), out["rew"])
+    env.close()
+    # closed loop
+    env = make_env(cfg, 1024)
+    obs, _ = env.reset()
+    before = env.curriculum_prob.clone()
+    act = torch.zeros(1024, 12, device="cuda")
+    for _ in range(300):
+        obs, rew, done, extras = env.step(act)
+    torch.cuda.synchronize()
+    p = env.curriculum_prob
+    assert torch.isfinite(obs).all() and p.min() >= 0 and p.max() <= 1.0 and (p >= before).all()
+    lev = env.env_curriculum_level
+    assert lev[:, 0].abs().max() <= L and lev[:, 1].abs().max() <= A
+    env.close()

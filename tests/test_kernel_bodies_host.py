@@ -55,6 +55,38 @@ def test_post_physics_body_matches_reference(name, terrain):
         assert close(terms[j], z["out_term_" + nm]), nm
 
 
+def test_command_curriculum_body_matches_reference():
+    """the kernel bodies of the command curriculum (success counts, grid update + clamp, inverse-CDF level draw with the
+    reference's transposed decoding, level -> command) against the golden produced by the reference with `curriculum: true`"""
+    from golden_util import OUT_EXACT, OUT_FLOAT
+
+    z = load("env_step_curriculum.npz")
+    cfg = load_cfg("plane")
+    cfg["commands"]["curriculum"] = True
+    m, c = _cfg_structs(cfg)
+    assert c.curriculum == 1 and c.cur_lin_levels == 10 and c.cur_success_len == 1350.0
+    st = step_inputs(z)
+    n = st["root_states"].shape[0]
+    f, i, ff, fi = pack_state(st, n)
+    prob = np.ascontiguousarray(z["in_curriculum_prob"].copy())
+    table = np.ascontiguousarray(z["table"])
+    obs = np.zeros((n, 47), np.float32); priv = np.zeros((n, 14), np.float32); rew = np.zeros(n, np.float32)
+    done = np.zeros(n, np.uint8); tout = np.zeros(n, np.uint8); terms = np.zeros((c.n_rew, n), np.float32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().hc_env_post_curriculum(C.byref(m), C.byref(c), P(f), P(i), n, P(table), C.c_longlong(int(z["common_step"])), C.c_ulonglong(1), 1,
+                                 P(prob), P(obs), P(priv), P(rew), P(done), P(tout), P(terms))
+    got = unpack(f, i, ff, fi)
+    assert np.array_equal(prob.view(np.uint32), z["out_curriculum_prob"].view(np.uint32))          # grid: bit-exact
+    assert np.array_equal(got["env_curriculum_level"].astype(np.int64), z["out_env_curriculum_level"])
+    assert np.array_equal(got["commands"].view(np.uint32), z["out_commands"].view(np.uint32))       # level -> command: bit-exact
+    assert np.array_equal(done.astype(bool), z["out_reset_buf"])
+    got.update(obs=obs, priv=priv, rew=rew, reset_buf=done, time_out_buf=got["time_out_buf"], extras_time_outs=tout)
+    for k in OUT_EXACT:
+        assert np.array_equal(np.asarray(got[k]).astype(np.int64).reshape(z["out_" + k].shape), z["out_" + k].astype(np.int64)), k
+    for k in OUT_FLOAT:
+        assert close(np.asarray(got[k]).reshape(z["out_" + k].shape), z["out_" + k]), k
+
+
 def test_reset_body_matches_reference():
     z = load("env_reset_trimesh.npz")
     cfg = load_cfg("trimesh")
