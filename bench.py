@@ -40,7 +40,7 @@ def parse():
                     help="1 = BASELINE.json configs[1] (flat terrain, 4096 envs/GPU; the bench line); 2 = configs[2]/[3] (rough heightfield "
                          "terrain + kicks/pushes + domain randomisation, 8192 envs/GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graphs", type=int, default=0, help="replay the rollout from a CUDA graph")
+    ap.add_argument("--graphs", type=int, default=1, help="replay the rollout from a CUDA graph (Runner.train's default); 0 = eager launches")
     args = ap.parse_args()
     if args.num_envs is None:
         args.num_envs = 4096 if args.config == 1 else 8192

@@ -43,11 +43,8 @@ struct GemmArgs {
 #define G_TILE_FLOATS (G_BM * G_LDS_R)  // 4608 >= 32 * 136 = 4352
 #define G_SMEM_BYTES (4 * G_TILE_FLOATS * (int)sizeof(float))
 
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// round-to-nearest (ties away) to tf32 on the bit pattern: 2 ALU ops; cvt.rna.tf32.f32 compiles to ~6 on sm_100 (finite inputs only)
+__device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = f2tf32(x);
     lo = f2tf32(x - __uint_as_float(hi));

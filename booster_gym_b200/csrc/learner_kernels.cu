@@ -410,11 +410,16 @@ __global__ void k_bump(unsigned long long* ctr) { *ctr += 1ull; }
 // ---- K4: fused rollout policy (utils/runner.py:109-111; utils/model.py:18-32) -----------------------------------------
 // One launch per env step: act = actor(obs) + exp(logstd) * eps for PF_ROWS observations per CTA.  All four layers run
 // inside the CTA with the activations resident in shared memory (47 -> 256 -> 128 -> 128 -> 12); the weights stream
-// from L2 in [N][32] k-tiles.  Hidden layers: mma.sync m16n8k8 3xTF32 with a fresh accumulator per k-step (round-to-
-// nearest adds, same arithmetic as gemm3x.cuh); head + sampling: one warp per row, fp32 FMAs + in-kernel Philox.
+// from L2 in 16-deep k-tiles, transposed on the fly to [k][N].
+// Hidden layers on the FP32 FMA pipe: at 4096 rows the layers are far too small for tcgen05 tiles, and the legacy mma.sync
+// TF32 path (the first version: 3xTF32, 3072 HMMA per 16 rows) measured 47 us at 4096 envs and 86 us at 8192 - bound by the
+// legacy MMA issue rate, ~34 TFLOP/s executed - where plain FFMA needs a third of the instructions' time and no operand split
+// (and is exactly the reference's fp32 arithmetic class).  Thread tile: 4 rows x 8 (N = 256) or 4 (N = 128) columns; a warp
+// shares its 4 rows (broadcast LDS.128 of A) and reads W as conflict-free LDS.128.  Head + sampling: one warp per row,
+// fp32 FMAs + in-kernel Philox.
 #define PF_ROWS 32
+#define PF_KT 16      // k-tile depth
 #define PF_THREADS 256
-#define PF_WT_LD 36   // k-tile row stride (floats): 36 % 32 = 4 -> conflict-free fragment reads
 struct PolicyFusedArgs {
     const float* obs;      // [n, 47]
     const float *W0, *b0, *W1, *b1, *W2, *b2, *W3, *b3, *logstd;
@@ -428,59 +433,59 @@ struct PolicyFusedArgs {
 
 template <int K, int KP, int N, int LDA, int LDO>
 __device__ __forceinline__ void pf_layer(const float* __restrict__ W, const float* __restrict__ bias, const float* As, float* Os,
-                                         float* Ws /* [2][N][PF_WT_LD] */) {
+                                         float* Ws /* [2][PF_KT][N] */) {
     // As: [32][LDA] fp32 (K valid columns, zero padded to KP); Os: [32][LDO]; W: [N][K] row-major in global memory
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gq = lane >> 2, tq = lane & 3;
-    constexpr int NW = N / 8;        // columns per warp
-    constexpr int NT = NW / 8;       // n8 tiles per warp
-    constexpr int KT = KP / 32;      // k-tiles
-    float acc[2][NT][4];
+    constexpr int G = N / 128;       // column groups of 4 per thread: columns g * 128 + 4 * lane + (0..3)
+    constexpr int KT = KP / PF_KT;   // k-tiles
+    static_assert(PF_ROWS == 4 * (PF_THREADS / 32) && (N == 128 || N == 256) && KP % PF_KT == 0, "thread tiling");
+    float acc[4][4 * G];
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.0f;
+        for (int c = 0; c < 4 * G; ++c) acc[r][c] = 0.0f;
     auto load_tile = [&](int kt, float* dst) {
-        // [N][32] floats of W starting at column kt*32 (guarded against K), coalesced along k
-        for (int idx = tid; idx < N * 32; idx += PF_THREADS) {
-            const int nrow = idx >> 5, kk = idx & 31;
-            const int kcol = kt * 32 + kk;
-            dst[nrow * PF_WT_LD + kk] = (kcol < K) ? __ldg(W + (size_t)nrow * K + kcol) : 0.0f;
+        // W[n][kt*16 + k8*8 .. +7] -> dst[k][n]: consecutive lanes take consecutive n (conflict-free stores); every lane reads one
+        // full 32-byte sector of its row when rows are 16-byte aligned
+        for (int idx = tid; idx < N * (PF_KT / 8); idx += PF_THREADS) {
+            const int nrow = idx % N, k8 = (idx / N) * 8;
+            const int kcol = kt * PF_KT + k8;
+            float w[8];
+            if (K % 4 == 0) {
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(W + (size_t)nrow * K + kcol));
+                const float4 hi = __ldg(reinterpret_cast<const float4*>(W + (size_t)nrow * K + kcol + 4));
+                w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = (kcol + i < K) ? __ldg(W + (size_t)nrow * K + kcol + i) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[(k8 + i) * N + nrow] = w[i];
         }
     };
     load_tile(0, Ws);
     __syncthreads();
     for (int kt = 0; kt < KT; ++kt) {
-        const float* Wt = Ws + (kt & 1) * N * PF_WT_LD;
-        if (kt + 1 < KT) load_tile(kt + 1, Ws + ((kt + 1) & 1) * N * PF_WT_LD);
+        const float* Wt = Ws + (kt & 1) * PF_KT * N;
+        if (kt + 1 < KT) load_tile(kt + 1, Ws + ((kt + 1) & 1) * PF_KT * N);
 #pragma unroll
-        for (int kb = 0; kb < 32; kb += 8) {
-            uint32_t ah[2][4], al[2][4];
+        for (int kk = 0; kk < PF_KT; kk += 4) {
+            float4 a4[4];
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi) {
-                const int rb = mi * 16;
-                const int kc = kt * 32 + kb;
-                split_tf32(As[(rb + gq) * LDA + kc + tq], ah[mi][0], al[mi][0]);
-                split_tf32(As[(rb + gq + 8) * LDA + kc + tq], ah[mi][1], al[mi][1]);
-                split_tf32(As[(rb + gq) * LDA + kc + tq + 4], ah[mi][2], al[mi][2]);
-                split_tf32(As[(rb + gq + 8) * LDA + kc + tq + 4], ah[mi][3], al[mi][3]);
-            }
+            for (int r = 0; r < 4; ++r) a4[r] = *reinterpret_cast<const float4*>(As + (4 * warp + r) * LDA + kt * PF_KT + kk);
 #pragma unroll
-            for (int ni = 0; ni < NT; ++ni) {
-                const int cb = warp * NW + ni * 8;
-                uint32_t bh[2], bl[2];
-                split_tf32(Wt[(cb + gq) * PF_WT_LD + kb + tq], bh[0], bl[0]);
-                split_tf32(Wt[(cb + gq) * PF_WT_LD + kb + tq + 4], bh[1], bl[1]);
+            for (int i = 0; i < 4; ++i) {
 #pragma unroll
-                for (int mi = 0; mi < 2; ++mi) {
-                    float t[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma_tf32(t, al[mi], bh);
-                    mma_tf32(t, ah[mi], bl);
-                    mma_tf32(t, ah[mi], bh);
+                for (int g = 0; g < G; ++g) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(Wt + (kk + i) * N + g * 128 + 4 * lane);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[mi][ni][q] += t[q];
+                    for (int r = 0; r < 4; ++r) {
+                        const float av = (i == 0) ? a4[r].x : (i == 1) ? a4[r].y : (i == 2) ? a4[r].z : a4[r].w;
+                        acc[r][4 * g + 0] = fmaf(av, w4.x, acc[r][4 * g + 0]);
+                        acc[r][4 * g + 1] = fmaf(av, w4.y, acc[r][4 * g + 1]);
+                        acc[r][4 * g + 2] = fmaf(av, w4.z, acc[r][4 * g + 2]);
+                        acc[r][4 * g + 3] = fmaf(av, w4.w, acc[r][4 * g + 3]);
+                    }
                 }
             }
         }
@@ -488,36 +493,35 @@ __device__ __forceinline__ void pf_layer(const float* __restrict__ W, const floa
     }
     // bias + ELU -> next activation buffer
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int g = 0; g < G; ++g) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + g * 128 + 4 * lane));
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni) {
-            const int c = warp * NW + ni * 8 + 2 * tq;
-            const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int r = mi * 16 + gq + 8 * half;
-                float v0 = acc[mi][ni][2 * half] + b0, v1 = acc[mi][ni][2 * half + 1] + b1;
-                v0 = (v0 > 0.f) ? v0 : expm1f(v0);
-                v1 = (v1 > 0.f) ? v1 : expm1f(v1);
-                Os[r * LDO + c] = v0;
-                Os[r * LDO + c + 1] = v1;
-            }
+        for (int r = 0; r < 4; ++r) {
+            float4 v;
+            v.x = acc[r][4 * g + 0] + b4.x; v.y = acc[r][4 * g + 1] + b4.y; v.z = acc[r][4 * g + 2] + b4.z; v.w = acc[r][4 * g + 3] + b4.w;
+            v.x = (v.x > 0.f) ? v.x : expm1f(v.x);
+            v.y = (v.y > 0.f) ? v.y : expm1f(v.y);
+            v.z = (v.z > 0.f) ? v.z : expm1f(v.z);
+            v.w = (v.w > 0.f) ? v.w : expm1f(v.w);
+            *reinterpret_cast<float4*>(Os + (4 * warp + r) * LDO + g * 128 + 4 * lane) = v;
         }
+    }
     __syncthreads();
 }
 
 #define PF_LD0 68    // 64 + 4
 #define PF_LD1 260   // 256 + 4
 #define PF_LD2 132   // 128 + 4
-#define PF_SMEM_FLOATS (PF_ROWS * (PF_LD0 + PF_LD1 + PF_LD2 + PF_LD2) + 2 * 256 * PF_WT_LD + 12 * 128)
+// two activation buffers, reused: P holds H1 then H3, Q holds X0 then H2
+#define PF_SMEM_FLOATS (PF_ROWS * (PF_LD1 + PF_LD2) + 2 * PF_KT * 256 + 12 * 128)
 __global__ void __launch_bounds__(PF_THREADS) k_policy_fused(const PolicyFusedArgs a) {
     extern __shared__ __align__(16) float pf_smem[];
     float* X0 = pf_smem;
-    float* H1 = X0 + PF_ROWS * PF_LD0;
-    float* H2 = H1 + PF_ROWS * PF_LD1;
-    float* H3 = H2 + PF_ROWS * PF_LD2;
-    float* Ws = H3 + PF_ROWS * PF_LD2;
-    float* W3s = Ws + 2 * 256 * PF_WT_LD;
+    float* H2 = X0;                        // Q: X0 (ld 68) is dead once layer 1 has run
+    float* H1 = X0 + PF_ROWS * PF_LD2;     // P
+    float* H3 = H1;                        // P: H1 is dead once layer 2 has run
+    float* Ws = H1 + PF_ROWS * PF_LD1;
+    float* W3s = Ws + 2 * PF_KT * 256;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.x * PF_ROWS;
     for (int idx = tid; idx < PF_ROWS * 64; idx += PF_THREADS) {

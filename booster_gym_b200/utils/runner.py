@@ -195,6 +195,24 @@ class Runner:
             buf.update_data("time_outs", n, infos["time_outs"])
         return obs, privileged_obs
 
+    def rollout_graphed(self, obs, privileged_obs):
+        """the same rollout replayed from a CUDA graph: 24 x (6 buffer writes + policy + physics + post-physics) are ~220 launches whose
+        host-side issue cost (Python + ctypes + torch dispatch) exceeds their GPU time at 4096 envs; RNG / step counters live on the
+        device, so a replay draws fresh noise.  The first call runs eagerly (a normal rollout) and then captures."""
+        if getattr(self, "_rollout_graph", None) is None:
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                out = self.rollout(obs, privileged_obs)          # eager: this IS iteration 0's rollout
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self._rollout_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._rollout_graph):          # recorded, not executed
+                self._rollout_out = self.rollout(out[0], out[1])
+            return out
+        self._rollout_graph.replay()
+        return self._rollout_out
+
     def update(self, obs, privileged_obs):
         """utils/runner.py:123-185: old distribution, then mini_epochs x [values, GAE, losses, backward, clip, Adam, KL]"""
         buf, lrn = self.buffer, self.learner
@@ -217,10 +235,11 @@ class Runner:
         privileged_obs = infos["privileged_obs"]
         SC = _abi.SC
         cur_multi = self.world_size > 1 and bool(self.cfg["commands"].get("curriculum"))
+        use_graph = os.environ.get("B200_ROLLOUT_GRAPH", "1") != "0"
         for it in range(self.cfg["basic"]["max_iterations"]):
             if cur_multi:
                 cur_before = self.env.curriculum_prob.clone()
-            obs, privileged_obs = self.rollout(obs, privileged_obs)
+            obs, privileged_obs = (self.rollout_graphed if use_graph else self.rollout)(obs, privileged_obs)
             if cur_multi:
                 # every rank raised its own copy of the command-curriculum grid from its own envs' successes; merge once per
                 # iteration: sum of the ranks' increments on top of the common starting grid, clamped like envs/t1.py:413
