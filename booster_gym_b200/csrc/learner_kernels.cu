@@ -141,9 +141,24 @@ __device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
 }
 
 
-// W [rows, cols] fp32 -> split copies: K-major [rows, cols_pad] (zero padded) and, if WTh != null, transposed [cols, rows]
-__global__ void k_weight_prep(const float* __restrict__ W, int rows, int cols, int cols_pad, float* __restrict__ Wh,
-                              float* __restrict__ Wl, float* __restrict__ WTh, float* __restrict__ WTl) {
+// W [rows, cols] fp32 -> split copies: K-major [rows, cols_pad] (zero padded) and, if WTh != null, transposed [cols, rows];
+// all six hidden-layer matrices in ONE launch (blockIdx.y = matrix)
+struct WeightPrepJob {
+    const float* W;
+    float *Wh, *Wl, *WTh, *WTl;
+    int rows, cols, cols_pad;
+};
+struct WeightPrepJobs {
+    WeightPrepJob j[6];
+};
+__global__ void k_weight_prep(const WeightPrepJobs jobs) {
+    const WeightPrepJob& q = jobs.j[blockIdx.y];
+    const float* __restrict__ W = q.W;
+    float* __restrict__ Wh = q.Wh;
+    float* __restrict__ Wl = q.Wl;
+    float* __restrict__ WTh = q.WTh;
+    float* __restrict__ WTl = q.WTl;
+    const int rows = q.rows, cols = q.cols, cols_pad = q.cols_pad;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * cols_pad) return;
     const int r = idx / cols_pad, c = idx - r * cols_pad;
@@ -613,20 +628,34 @@ __global__ void __launch_bounds__(128) k_gae(float* __restrict__ rewards, const 
     double s = 0.0, s2 = 0.0;
     if (e < N) {
         float next_v = last_values[e], last_adv = 0.0f;
-        for (int t = T - 1; t >= 0; --t) {
-            const size_t i = (size_t)t * N + e;
-            const float v = values[i];
-            const bool to = time_outs[i] != 0;
-            float r = rewards[i];
-            if (to) { r = v; rewards[i] = v; }
-            const float nnt = (dones[i] != 0 || to) ? 0.0f : 1.0f;
-            const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nnt), next_v)), v);
-            last_adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last_adv));
-            adv[i] = last_adv;
-            ret[i] = __fadd_rn(v, last_adv);
-            s += (double)last_adv;
-            s2 += (double)last_adv * (double)last_adv;
-            next_v = v;
+        // the recurrence is sequential in t, its loads are not: fetch 8 time steps at once, then run them
+        for (int t1 = T; t1 > 0; t1 -= 8) {
+            float vv[8], rr[8];
+            uint8_t dd[8], oo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t1 - 1 - k;
+                const size_t i = (size_t)(t >= 0 ? t : 0) * N + e;
+                vv[k] = values[i]; rr[k] = rewards[i]; dd[k] = dones[i]; oo[k] = time_outs[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t1 - 1 - k;
+                if (t < 0) break;
+                const size_t i = (size_t)t * N + e;
+                const float v = vv[k];
+                const bool to = oo[k] != 0;
+                float r = rr[k];
+                if (to) { r = v; rewards[i] = v; }
+                const float nnt = (dd[k] != 0 || to) ? 0.0f : 1.0f;
+                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nnt), next_v)), v);
+                last_adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last_adv));
+                adv[i] = last_adv;
+                ret[i] = __fadd_rn(v, last_adv);
+                s += (double)last_adv;
+                s2 += (double)last_adv * (double)last_adv;
+                next_v = v;
+            }
         }
     }
     if (stats) {
@@ -1158,12 +1187,15 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
         {P_CW0, 256, 61, 64, w.Wc0h, w.Wc0l, 0, 0, false},        {P_CW1, 256, 256, 256, w.Wc1h, w.Wc1l, w.Wc1Th, w.Wc1Tl, true},
         {P_CW2, 128, 256, 256, w.Wc2h, w.Wc2l, w.Wc2Th, w.Wc2Tl, true}, {P_AW0, 256, 47, 64, w.Wa0h, w.Wa0l, 0, 0, false},
         {P_AW1, 128, 256, 256, w.Wa1h, w.Wa1l, w.Wa1Th, w.Wa1Tl, true}, {P_AW2, 128, 128, 128, w.Wa2h, w.Wa2l, w.Wa2Th, w.Wa2Tl, true}};
-    for (const Job& j : jobs) {
-        const int total = j.rows * j.pad;
-        k_weight_prep<<<(total + 255) / 256, 256, 0, st>>>(p->P(j.pi), j.rows, j.cols, j.pad, ws + j.h, ws + j.l,
-                                                           j.tr ? ws + j.th : nullptr, j.tr ? ws + j.tl : nullptr);
+    WeightPrepJobs wj;
+    int max_total = 0;
+    for (int i = 0; i < 6; ++i) {
+        const Job& j = jobs[i];
+        wj.j[i] = WeightPrepJob{p->P(j.pi), ws + j.h, ws + j.l, j.tr ? ws + j.th : nullptr, j.tr ? ws + j.tl : nullptr, j.rows, j.cols, j.pad};
+        max_total = j.rows * j.pad > max_total ? j.rows * j.pad : max_total;
     }
-    g_launches += 6;
+    k_weight_prep<<<dim3((max_total + 255) / 256, 6), 256, 0, st>>>(wj);
+    g_launches += 1;
     return launch_status("k_weight_prep");
 }
 // full-batch forward passes over the M = T*N stored samples (activations kept in fp32 for the backward pass)
