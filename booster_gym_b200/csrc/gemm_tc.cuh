@@ -526,47 +526,19 @@ k_tc_rowmajor(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CU
                 const bool row_ok = row < g.M;          // per lane; invalid rows compute on row 0 and contribute / store nothing
                 const size_t base = (size_t)(row_ok ? row : 0) * g.ldo + col0;
                 float v[32];
-                if (EPI == EPI_FWD) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                for (int j = 0; j < 32; j += 4) {   // (EPI_FWD; the dgrad epilogue is the pipelined loop above)
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float x = __uint_as_float(r[j + t]) + bb[t];
-                            v[j + t] = (NACC > 1) ? ((x > 0.0f) ? x : expm1f(x)) : elu_fast(x);  // the accurate (multi-accumulator) variant keeps expm1f
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float h8[8];
-                        ldg_v8(g.aux + base + j, h8);
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) v[j + t] = __uint_as_float(r[j + t]) * ((h8[t] > 0.0f) ? 1.0f : (h8[t] + 1.0f));
+                    for (int t = 0; t < 4; ++t) {
+                        const float x = __uint_as_float(r[j + t]) + bb[t];
+                        v[j + t] = (NACC > 1) ? ((x > 0.0f) ? x : expm1f(x)) : elu_fast(x);  // the accurate (two-accumulator) variant keeps expm1f
                     }
                 }
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) stg_v8(g.out + base + j, v + j);
-                }
-                if (EPI == EPI_DGRAD && g.colsum) {
-                    if (!row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-                    }
-                    // column sums over this warp's 32 rows: butterfly reduce-scatter (31 shuffle+add), lane j ends with column j
-#pragma unroll
-                    for (int half = 16; half >= 1; half >>= 1) {
-                        const bool upper = (lane & half) != 0;
-#pragma unroll
-                        for (int j = 0; j < half; ++j) {
-                            const float send = upper ? v[j] : v[j + half];
-                            const float keep = upper ? v[j + half] : v[j];
-                            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-                        }
-                    }
-                    atomicAdd(g.colsum + col0 + lane, v[0]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");

@@ -3,9 +3,11 @@
 // the full-batch epoch body with all five loss terms and their hand-derived backward (utils/runner.py:146-161), and
 // clip_grad_norm_ + Adam + KL-adaptive learning rate (utils/runner.py:162-180) - all device-resident, no host sync.
 //
-// Dense contractions go through k_gemm3x (gemm3x.cuh): tensor-core TF32 MMAs with an error-compensated 3-term split so
-// results stay within fp32 rounding of the reference's SGEMM (parity bar 1e-5 relative).  Activations are kept in a
-// caller-provided workspace, [M, width] row-major, post-ELU (ELU' = h > 0 ? 1 : h + 1 needs no pre-activation copy).
+// Dense contractions of the update go through gemm_tc.cuh (tcgen05.mma kind::tf32 with TMEM accumulators and TMA, error-
+// compensated 3-term TF32 split so results stay within fp32 rounding of the reference's SGEMM; parity bar 1e-5 relative);
+// the rollout policy runs on the FP32 FMA pipe (k_policy_fused); only b200_critic_value still uses the mma.sync path of
+// gemm3x.cuh.  Activations live in a caller-provided workspace as plain fp32, [M, width] row-major, post-ELU
+// (ELU' = h > 0 ? 1 : h + 1 needs no pre-activation copy).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -55,7 +57,7 @@ struct Workspace {
     size_t WP[6];                                       // partial weight-gradient tiles of the six k_tc_wgrad launches of an epoch
     size_t Wc0h, Wc0l, Wc1h, Wc1l, Wc2h, Wc2l, Wa0h, Wa0l, Wa1h, Wa1l, Wa2h, Wa2l;   // split weights, K padded to 64 for layer 0
     size_t Wc1Th, Wc1Tl, Wc2Th, Wc2Tl, Wa1Th, Wa1Tl, Wa2Th, Wa2Tl;                  // transposed split weights for dgrad
-    size_t LXa, LXc, L1, L2, L3, LV, LMU;               // rollout-sized (N rows) fp32 buffers of the mma.sync path
+    size_t LXc, L1, L2, L3, LV;                          // N-row fp32 buffers of b200_critic_value (mma.sync path, gemm3x.cuh)
     size_t total;
 };
 static Workspace make_workspace(int T, int N) {
@@ -75,8 +77,8 @@ static Workspace make_workspace(int T, int N) {
     w.Wa1h = take(128 * 256); w.Wa1l = take(128 * 256); w.Wa2h = take(128 * 128); w.Wa2l = take(128 * 128);
     w.Wc1Th = take(256 * 256); w.Wc1Tl = take(256 * 256); w.Wc2Th = take(256 * 128); w.Wc2Tl = take(256 * 128);
     w.Wa1Th = take(256 * 128); w.Wa1Tl = take(256 * 128); w.Wa2Th = take(128 * 128); w.Wa2Tl = take(128 * 128);
-    w.LXa = take(n * 48); w.LXc = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
-    w.LV = take(n); w.LMU = take(n * 12);
+    w.LXc = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
+    w.LV = take(n);
     w.total = o;
     return w;
 }
@@ -172,16 +174,6 @@ __global__ void k_weight_prep(const WeightPrepJobs jobs) {
     }
 }
 
-// fp32 -> (hi, lo)
-__global__ void k_split(const float* __restrict__ x, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float h, l;
-    split_tf32f(x[i], h, l);
-    hi[i] = h;
-    lo[i] = l;
-}
-
 // critic head: V[m] = b + sum_k H[m,k] w[k], one warp per row (H rows are 128 floats = one float4 per lane)
 __global__ void k_value_head(const float* __restrict__ H, const float* __restrict__ w, const float* __restrict__ b, int n,
                              float* __restrict__ V) {
@@ -244,30 +236,6 @@ __global__ void __launch_bounds__(HB_THREADS) k_value_head_bwd(const float* __re
             for (int v = 0; v < HB_THREADS / 32; ++v) sb += (double)redb[v];
             atomicAdd(db, (float)sb);
         }
-    }
-}
-
-// bias gradient: db[c] += sum over rows of (dYh + dYl)[r,c]   (C <= 256; 256 threads, rows split over blockDim/Cp row-lanes)
-#define CS_ROWS 256
-__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, const float* __restrict__ dYl, int n, int C, int ld,
-                                                float* __restrict__ db) {
-    __shared__ double red[256];
-    int Cp = 1;
-    while (Cp < C) Cp <<= 1;           // 16, 128 or 256
-    const int lanes = 256 / Cp;
-    const int c = threadIdx.x % Cp, rl = threadIdx.x / Cp;
-    const int r0 = blockIdx.x * CS_ROWS, r1 = min(n, r0 + CS_ROWS);
-    double acc = 0.0;
-    if (c < C) {
-        if (dYl) for (int r = r0 + rl; r < r1; r += lanes) acc += (double)dY[(size_t)r * ld + c] + (double)dYl[(size_t)r * ld + c];
-        else for (int r = r0 + rl; r < r1; r += lanes) acc += (double)dY[(size_t)r * ld + c];
-    }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    if (rl == 0 && c < C) {
-        double s = 0.0;
-        for (int l = 0; l < lanes; ++l) s += red[l * Cp + c];
-        atomicAdd(db + c, (float)s);
     }
 }
 
@@ -386,37 +354,6 @@ __global__ void __launch_bounds__(HB_THREADS, 2) k_actor_head_bwd(const float* _
         double sb = 0.0;
         for (int v = 0; v < HB_THREADS / 32; ++v) sb += (double)redb[v][threadIdx.x];
         atomicAdd(db + threadIdx.x, (float)sb);
-    }
-}
-
-// rollout sampling (utils/runner.py:110-111): act = mu + exp(logstd) * eps
-__global__ void k_sample(const float* __restrict__ mu, const float* __restrict__ logstd, const float* __restrict__ eps_in,
-                         int n, uint64_t seed, uint64_t step, const unsigned long long* __restrict__ ctr, int env_base,
-                         int deterministic, float* __restrict__ act, float* __restrict__ mu_out) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    if (ctr) step = (uint64_t)(*ctr);
-    float eps[12];
-    if (deterministic) {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) eps[j] = 0.0f;
-    } else if (eps_in) {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) eps[j] = eps_in[(size_t)e * 12 + j];
-    } else {
-#pragma unroll
-        for (int sub = 0; sub < 3; ++sub) {
-            const Rand4 r = rand4(rng_words(seed, (uint32_t)(env_base + e), step, RP_POLICY, sub));
-#pragma unroll
-            for (int l = 0; l < 4; ++l) eps[4 * sub + l] = r.n[l];
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        const float m = mu[(size_t)e * 12 + j];
-        const float a = deterministic ? m : __fadd_rn(m, __fmul_rn(expf(logstd[j]), eps[j]));
-        act[(size_t)e * 12 + j] = a;
-        if (mu_out) mu_out[(size_t)e * 12 + j] = m;
     }
 }
 
@@ -956,7 +893,7 @@ __global__ void k_post_apply(float* __restrict__ scalars, const double* __restri
 }
 
 // =====================================================================================================================
-// measurement hooks: launch counter (bench.py "gpu_launches") and CUDA-event timing of every k_gemm3x launch on the
+// measurement hooks: launch counter (bench.py "gpu_launches") and CUDA-event timing of every GEMM launch on the
 // launching stream (bench.py "roofline": algorithmic FLOPs / measured duration of the dominant kernel)
 // =====================================================================================================================
 namespace b200 {
@@ -990,7 +927,7 @@ static void prof_end(cudaStream_t st) {
 }
 
 // =====================================================================================================================
-// dense layers on k_gemm3x
+// dense layers on k_gemm3x (b200_critic_value only)
 // =====================================================================================================================
 #define CU_TRY(expr)                                                   \
     do {                                                               \
@@ -1013,41 +950,6 @@ static cudaError_t linear_fwd(const float* X, int ldx, int k_pad, const float* W
     g_launches += 1;
     return e;
 }
-// dX[n, k] = (dY[n, n_out] W[n_out, k]) * ELU'(H[n, k])
-static cudaError_t linear_dgrad(const float* dY, int ldy, int n_out, const float* W, int k, const float* H, int ldh,
-                                float* dX, int ldx, int n, cudaStream_t st) {
-    GemmArgs g{};
-    g.A = dY; g.B = W; g.C = dX; g.bias = nullptr; g.aux = H;
-    g.I = n; g.Cn = k; g.R = n_out;
-    g.lda = ldy; g.ldb = k; g.ldc = ldx; g.ldaux = ldh;
-    g.cn_store = k; g.r_chunk = 0; g.r_valid_b = 0;
-    prof_begin(st, 2.0 * n * (double)n_out * k);
-    const cudaError_t e = launch_gemm3x<false, true, EPI_ELU_GRAD>(g, 1, st);
-    prof_end(st);
-    g_launches += 1;
-    return e;
-}
-// dW[n_out, k_valid] += dY[n, n_out]^T X[n, k_pad]   (split over n, atomic accumulate; dW must be zeroed by the caller)
-#define WGRAD_CHUNK 1024
-static cudaError_t linear_wgrad(const float* dY, int ldy, int n_out, const float* X, int ldx, int k_pad, int k_valid,
-                                float* dW, int n, cudaStream_t st) {
-    GemmArgs g{};
-    g.A = dY; g.B = X; g.C = dW; g.bias = nullptr; g.aux = nullptr;
-    g.I = n_out; g.Cn = k_pad; g.R = n;
-    g.lda = ldy; g.ldb = ldx; g.ldc = k_valid; g.ldaux = 0;
-    g.cn_store = k_valid; g.r_chunk = WGRAD_CHUNK; g.r_valid_b = 0;
-    prof_begin(st, 2.0 * n * (double)n_out * k_valid);
-    const cudaError_t e = launch_gemm3x<true, true, EPI_ATOMIC>(g, (n + WGRAD_CHUNK - 1) / WGRAD_CHUNK, st);
-    prof_end(st);
-    g_launches += 1;
-    return e;
-}
-static cudaError_t bias_grad(const float* dY, const float* dYl, int ld, int C, int n, float* db, cudaStream_t st) {
-    k_colsum<<<(n + CS_ROWS - 1) / CS_ROWS, 256, 0, st>>>(dY, dYl, n, C, ld, db);
-    g_launches += 1;
-    return cudaPeekAtLastError();
-}
-
 // ---- reduction of the k_tc_wgrad partial tiles: dW[row, col] += sum over parts, all six weight matrices in one launch ----
 struct WgradJob {
     const float* P;   // [tiles_y * tiles_z][parts][128][bn]
@@ -1224,16 +1126,6 @@ static int critic_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     return launch_status("k_value_head");
 }
 
-// actor 47 -> 256 -> 128 -> 128 -> 12 (utils/model.py:18-26)
-static int actor_forward(const B200Ppo* p, const float* X, int ldx, int k_pad, int n, float* H1, float* H2, float* H3,
-                         float* MU, cudaStream_t st) {
-    CU_TRY(linear_fwd(X, ldx, k_pad, p->P(P_AW0), 47, p->P(P_AB0), H1, 256, n, 256, true, st));
-    CU_TRY(linear_fwd(H1, 256, 256, p->P(P_AW1), 256, p->P(P_AB1), H2, 128, n, 128, true, st));
-    CU_TRY(linear_fwd(H2, 128, 128, p->P(P_AW2), 128, p->P(P_AB2), H3, 128, n, 128, true, st));
-    k_actor_head<<<(n * 32 + 255) / 256 < 1184 ? (n * 32 + 255) / 256 : 1184, 256, 0, st>>>(H3, p->P(P_AW3), p->P(P_AB3), n, MU);
-    g_launches += 1;
-    return launch_status("k_actor_head");
-}
 // critic 61 -> 256 -> 256 -> 128 -> 1 (utils/model.py:9-17); Xc is the packed [n,64] cat(obs, priv)
 static int critic_forward(const B200Ppo* p, const float* Xc, int n, float* H1, float* H2, float* H3, float* V,
                           cudaStream_t st) {
