@@ -30,7 +30,11 @@ def _model_fields(real):
         ("jnt_lower", real * NU), ("jnt_upper", real * NU), ("dof_inertia", real * NU),
         ("foot_corner", real * 3 * 4), ("gravity", real), ("dt", real), ("contact_k", real), ("contact_c", real),
         ("stiction_vel", real), ("limit_k", real), ("limit_c", real),
-        ("axis", C.c_int32 * NB), ("enable_contact", C.c_int32), ("enable_limits", C.c_int32), ("pad0", C.c_int32),
+        ("trunk_box_pos", real * 3), ("trunk_box_half", real * 3), ("trunk_box_radius", real), ("cyl_pos", real * 3 * 2), ("cyl_radius", real * 2),
+        ("cyl_half", real * 2), ("body_mu", real), ("self_k", real), ("self_c", real), ("foot_cap", real * 3 * 2),
+        ("foot_cap_radius", real),
+        ("axis", C.c_int32 * NB), ("enable_contact", C.c_int32), ("enable_limits", C.c_int32),
+        ("enable_body_contact", C.c_int32), ("enable_self_contact", C.c_int32), ("pad0", C.c_int32),
     ]
 
 

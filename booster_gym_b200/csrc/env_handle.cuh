@@ -17,6 +17,7 @@ struct B200T1Handle {
     int32_t* istate;
     int16_t* hf_dev;
     int hf_rows, hf_cols;
+    float hf_max;         // highest heightfield sample [m] (0 for the plane)
     long long* ctr_dev;   // [0] rng step, [1] common_step_counter, [2..3] any-reset flags (parity)
     double* stats_dev;    // [1 + n_rew + 1] episode sums, then count as double
     const uint32_t* inject;  // parity-test hook (b200_t1_inject_rng); null in production
@@ -36,6 +37,7 @@ inline TerrainView make_terrain(const B200T1Handle* h) {
     t.border_pixels = h->cfg.border_pixels;
     t.horizontal_scale = h->cfg.horizontal_scale;
     t.vertical_scale = h->cfg.vertical_scale;
+    t.max_height = (h->cfg.terrain_type == 0) ? 0.0f : h->hf_max;
     return t;
 }
 inline EnvView make_view(const B200T1Handle* h) {

@@ -184,6 +184,9 @@ int b200_t1_create(const B200T1ModelF* model, const B200T1Config* cfg, const int
         const size_t bytes = (size_t)hf_rows * hf_cols * sizeof(int16_t);
         CUDA_TRY(cudaMalloc(&h->hf_dev, bytes));
         CUDA_TRY(cudaMemcpy(h->hf_dev, hf_host, bytes, cudaMemcpyHostToDevice));
+        int16_t top = hf_host[0];
+        for (size_t i = 1; i < (size_t)hf_rows * hf_cols; ++i) top = hf_host[i] > top ? hf_host[i] : top;
+        h->hf_max = (float)((double)top * cfg->vertical_scale) + 1e-5f;  // bound of the bilinear interpolant (terrain.cuh)
     }
     CUDA_TRY(cudaMalloc(&h->ctr_dev, 4 * sizeof(long long)));
     CUDA_TRY(cudaMemset(h->ctr_dev, 0, 4 * sizeof(long long)));

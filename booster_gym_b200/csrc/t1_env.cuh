@@ -135,6 +135,7 @@ B200_HD float raw_rand(const B200Rand& r, float u, float nrm) { return (r.dist =
 // unclipped) or raw torques if !apply_pd.  Lanes whose env index is out of range compute on a clamped index and store
 // nothing (they must still take part in the shuffles).
 #if defined(__CUDACC__)
+#define B200_SHAPE_MARGIN 0.03f
 template <typename T> __device__ __forceinline__ T pair_sum(T x) { return x + __shfl_xor_sync(0xffffffffu, x, 1); }
 
 template <typename Model>
@@ -195,7 +196,17 @@ __device__ __forceinline__ void env_physics_pair(const EnvView& v, int e, bool v
         tsum[k] = 0.0f;
     }
     LegWork<float> W;
+    W.foot_fn = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { W.trunk_f[r] = 0.0f; W.body_f2[r] = 0.0f; }
     float qb[6], ql[6];
+    // per-thread slices of shared memory for the contact matrices of the rarely touching shapes (t1_leg_phase1)
+    __shared__ float kx_scratch[B200_KX_SIZE * PHYS_BLOCK];
+    float* Kx = kx_scratch + threadIdx.x;
+    // The first tick of a call always evaluates the shapes (the state may have been written from outside); afterwards a
+    // shape can come within reach only by crossing the margin: 3 cm = 15 m/s x one tick, and an env whose squared root
+    // velocity exceeds terminate_vel (50) is reset (envs/t1.py:554).
+    bool near_ground = m.enable_body_contact != 0;
     for (int i = 0; i < n_substeps; ++i) {
         float tau[6];
 #pragma unroll
@@ -211,14 +222,33 @@ __device__ __forceinline__ void env_physics_pair(const EnvView& v, int e, bool v
                 tau[k] = target[k];
             }
         }
-        t1_leg_phase1<float>(m, par, s, side, tau, push_f, push_t, terr, W);
+        // trunk box / leg cylinders: evaluated out of line, and only while one of them is within a margin of the
+        // ground (W.clearance of the previous tick; t1_dynamics.cuh "rarely touching shapes")
+        int shape_mask = 0;
+        if (near_ground) {
+            const LegState<float> tmp = s;
+            shape_mask = shapes_prepass<PHYS_BLOCK, float>(m, tmp, side, terr, Kx);
+        }
+        t1_leg_phase1<float, PHYS_BLOCK>(m, par, s, side, tau, push_f, push_t, terr, W, Kx, shape_mask);
+        near_ground = W.clearance < B200_SHAPE_MARGIN;
 #pragma unroll
         for (int q = 0; q < 21; ++q) W.Mbb[q] = pair_sum(W.Mbb[q]);
 #pragma unroll
         for (int q = 0; q < 6; ++q) W.rb[q] = pair_sum(W.rb[q]);
         t1_leg_phase2<float>(m, s, W, qb, ql, true);
     }
+    // net contact force per body after the last substep (gym.refresh_net_contact_force_tensor, envs/t1.py:462) reduced to what
+    // the env reads: |F| > 1 N (envs/t1.py:553,628).  The trunk's force is the sum of the two lanes' shares.
+    int cmask = 0;
+    {
+        const float tf[3] = {pair_sum(W.trunk_f[0]), pair_sum(W.trunk_f[1]), pair_sum(W.trunk_f[2])};
+        if (side == 0 && tf[0] * tf[0] + tf[1] * tf[1] + tf[2] * tf[2] > 1.0f) cmask |= 1;
+        if (W.body_f2[0] > 1.0f) cmask |= 1 << (1 + 6 * side + 2);
+        if (W.body_f2[1] > 1.0f) cmask |= 1 << (1 + 6 * side + 3);
+        if (W.body_f2[2] > 1.0f) cmask |= 1 << (1 + 6 * side + 5);
+    }
     if (!valid) return;
+    IS(I_contact_mask + side) = cmask;
     // write back (refresh_* tensors of envs/t1.py:454,460-462): the left-leg lane stores the base
     if (side == 0) {
 #pragma unroll
@@ -297,6 +327,7 @@ struct RewardSnap {
     int contact[2];
     float gait_process, gait_frequency;
     int ep_len;
+    int contact_mask;
 };
 B200_HD void reward_snapshot(const EnvView& v, int e, RewardSnap& s) {
     const float* f = v.f;
@@ -323,6 +354,7 @@ B200_HD void reward_snapshot(const EnvView& v, int e, RewardSnap& s) {
     s.gait_process = FS(F_gait_process);
     s.gait_frequency = FS(F_gait_frequency);
     s.ep_len = IS(I_episode_length_buf);
+    s.contact_mask = IS(I_contact_mask) | IS(I_contact_mask + 1);
 }
 
 // reward term k of envs/t1.py:606-730 (unscaled); `h_base` = terrain height under the base
@@ -346,7 +378,11 @@ B200_HD float reward_term(int id, const RewardSnap& s, const B200T1Config& c, fl
         case B200_REW_DOF_POS_LIMITS: { float a = 0; for (int j = 0; j < 12; ++j) a += ((s.dof_pos[j] < c.dof_pos_soft_lower[j]) || (s.dof_pos[j] > c.dof_pos_soft_upper[j])) ? 1.0f : 0.0f; return a; }
         case B200_REW_DOF_VEL_LIMITS: { float a = 0; for (int j = 0; j < 12; ++j) a += fminf(fmaxf(fabsf(s.dof_vel[j]) - c.dof_vel_limits[j] * c.soft_dof_vel_limit, 0.0f), 1.0f); return a; }
         case B200_REW_TORQUE_LIMITS: { float a = 0; for (int j = 0; j < 12; ++j) a += fmaxf(fabsf(s.torques[j]) - c.torque_limits[j] * c.soft_torque_limit, 0.0f); return a; }
-        case B200_REW_COLLISION: return 0.0f;  // only the feet carry contact points in this build; feet are not penalised bodies
+        case B200_REW_COLLISION: {  // :627-629: number of penalised bodies whose net contact force exceeds 1 N
+            int cnt = 0;
+            for (int mk = s.contact_mask & c.penalized_body_mask; mk; mk &= mk - 1) ++cnt;
+            return (float)cnt;
+        }
         case B200_REW_FEET_SLIP: {
             float a = 0;
             for (int k = 0; k < 2; ++k) {
@@ -686,7 +722,8 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
 #pragma unroll
     for (int r = 0; r < 6; ++r) { const float t = FS(F_root_states + 7 + r); vsq += t * t; }
     bool finite = (vsq == vsq) && (fabsf(vsq) <= 3.0e38f) && (FS(F_root_states + 2) == FS(F_root_states + 2));
-    bool reset = (vsq > c.terminate_vel) || (FS(F_root_states + 2) - h_base < c.terminate_height);
+    const int contact_mask = IS(I_contact_mask) | IS(I_contact_mask + 1);  // bit b: |contact_forces[b]| > 1 (:553)
+    bool reset = ((contact_mask & c.termination_body_mask) != 0) || (vsq > c.terminate_vel) || (FS(F_root_states + 2) - h_base < c.terminate_height);
     if (!finite) { reset = true; IS(I_nan_resets) += 1; }  // a diverged env is reset, not propagated
     bool time_out = ep_len > c.max_episode_length;
     reset = reset || time_out;

@@ -52,7 +52,8 @@
     X(time_out_buf, 1)                                                                                           \
     X(episode_steps, 1)     /* utils/recorder.py:37-43 */                                                         \
     X(nan_resets, 1)                                                                                             \
-    X(env_curriculum_level, 2) /* (lin, ang) level of the current command (envs/t1.py:262) */
+    X(env_curriculum_level, 2) /* (lin, ang) level of the current command (envs/t1.py:262) */                    \
+    X(contact_mask, 2)      /* per leg lane: bit b = |net contact force on body b| > 1 N after the last substep (envs/t1.py:553,628) */
 
 namespace b200 {
 

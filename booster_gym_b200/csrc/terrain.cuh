@@ -28,6 +28,7 @@ struct TerrainView {
     int rows, cols, border_pixels;
     float horizontal_scale;
     double vertical_scale;
+    float max_height = 3.0e38f;  // upper bound of every lookup (culls the rarely touching collision shapes); default: never cull
 
     B200_HD float operator()(float px, float py) const {
         if (hf == nullptr) return 0.0f;

@@ -54,7 +54,10 @@ class T1(BaseTask):
 
         self._c_cfg = config.t1_config(cfg)
         sp = config.sim_params(cfg)
-        self._c_model = robot.model_f(foot_corner=config.feet_edge_pos(cfg), dt=sp["dt"], gravity=sp["gravity"])
+        # asset.self_collisions is Isaac Gym's collision FILTER: 0 = leg-leg contacts enabled, 1 = disabled (envs/T1.yaml:69)
+        self._c_model = robot.model_f(foot_corner=config.feet_edge_pos(cfg), dt=sp["dt"], gravity=sp["gravity"],
+                                      terrain_friction=float(cfg["terrain"]["static_friction"]),
+                                      self_contact=int(cfg["asset"].get("self_collisions", 0)) == 0)
         hf = self.terrain.height_field_raw
         handle = C.c_void_p()
         if hf is not None:

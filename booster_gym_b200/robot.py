@@ -25,7 +25,14 @@ def load_json(path=_ASSET):
         return json.load(f)
 
 
-def fill_model(struct, js=None, foot_corner=None, enable_contact=True, enable_limits=True, dt=0.002, gravity=9.81):
+# leg-leg contacts act between two links of a few kg, not on the whole robot: springs formed for this mass
+SELF_CONTACT_MASS = 2.0
+# Isaac Gym's default shape friction (the reference only randomises the foot shapes, envs/t1.py:162-167)
+DEFAULT_SHAPE_FRICTION = 1.0
+
+
+def fill_model(struct, js=None, foot_corner=None, enable_contact=True, enable_limits=True, dt=0.002, gravity=9.81,
+               body_contact=True, self_contact=True, terrain_friction=1.0):
     js = js or load_json()
     for b in range(_abi.NB):
         for r in range(3):
@@ -54,7 +61,33 @@ def fill_model(struct, js=None, foot_corner=None, enable_contact=True, enable_li
     struct.stiction_vel = STICTION_VEL
     struct.limit_k = SOLREF_K
     struct.limit_c = SOLREF_B
+    # collision primitives other than the soles: trunk box, hip-yaw and shank cylinders (same both sides)
+    g = js["geoms"]
+    for r in range(3):
+        struct.trunk_box_pos[r] = g["Trunk"][0]["pos"][r]
+        struct.trunk_box_half[r] = g["Trunk"][0]["size"][r]
+    struct.trunk_box_radius = sum(v * v for v in g["Trunk"][0]["size"]) ** 0.5
+    for i, name in enumerate(("Hip_Yaw_Left", "Shank_Left")):
+        assert g[name][0]["type"] == "cylinder" and g[name] == g[name.replace("Left", "Right")]
+        for r in range(3):
+            struct.cyl_pos[i][r] = g[name][0]["pos"][r]
+        struct.cyl_radius[i] = g[name][0]["size"][0]
+        struct.cyl_half[i] = g[name][0]["size"][1]
+    struct.body_mu = 0.5 * (DEFAULT_SHAPE_FRICTION + terrain_friction)  # PhysX combines by averaging
+    struct.self_k = SOLREF_K * SELF_CONTACT_MASS
+    struct.self_c = SOLREF_B * SELF_CONTACT_MASS
+    # the foot box (half 0.1115 x 0.05 x 0.015) as a capsule along its long axis for leg-leg contact
+    fb = g["left_foot_link"][0]
+    rad = fb["size"][1]
+    for i, sgn in enumerate((1.0, -1.0)):
+        struct.foot_cap[i][0] = fb["pos"][0] + sgn * (fb["size"][0] - rad)
+        struct.foot_cap[i][1] = fb["pos"][1]
+        struct.foot_cap[i][2] = fb["pos"][2]
+    struct.foot_cap_radius = rad
     struct.enable_contact = 1 if enable_contact else 0
+    # B200_BODY_CONTACT / B200_SELF_CONTACT = 0: measurement switches (cost of the f3 shapes), not configuration
+    struct.enable_body_contact = 1 if (enable_contact and body_contact and os.environ.get("B200_BODY_CONTACT", "1") != "0") else 0
+    struct.enable_self_contact = 1 if (enable_contact and self_contact and os.environ.get("B200_SELF_CONTACT", "1") != "0") else 0
     struct.enable_limits = 1 if enable_limits else 0
     struct.pad0 = 0
     return struct

@@ -53,9 +53,22 @@ extern "C" {
     REAL contact_c;              /* normal damper per corner [N s/m] = solref B * contact_mass */           \
     REAL stiction_vel;           /* regularisation velocity of the Coulomb law [m/s] */                      \
     REAL limit_k, limit_c;       /* joint-limit spring/damper per unit effective inertia [1/s^2, 1/s] */     \
+    /* collision primitives other than the soles (resources/T1/T1_locomotion.xml:42,66,71,99,104) */ \
+    REAL trunk_box_pos[3];       /* box centre in the trunk frame */                                         \
+    REAL trunk_box_half[3];                                                                                  \
+    REAL trunk_box_radius;       /* |half|: bounding sphere used to cull the box against the highest terrain sample */ \
+    REAL cyl_pos[2][3];          /* cylinder centre in its body frame: [0] Hip_Yaw (leg link 2), [1] Shank (3) */ \
+    REAL cyl_radius[2];          /* the cylinder axis is the body z axis */                                  \
+    REAL cyl_half[2];                                                                                        \
+    REAL body_mu;                /* combined Coulomb coefficient of those shapes against the ground */       \
+    REAL self_k, self_c;         /* leg-leg penalty spring / damper [N/m, N s/m] */                          \
+    REAL foot_cap[2][3];         /* capsule of the foot box for leg-leg contact: segment end points, foot frame */ \
+    REAL foot_cap_radius;                                                                                    \
     int32_t axis[B200_NB];       /* hinge axis 0/1/2, -1 for the free joint */                              \
     int32_t enable_contact;      /* 0 = contact-free dynamics (BASELINE config 5 i) */                      \
     int32_t enable_limits;                                                                                   \
+    int32_t enable_body_contact; /* 1: trunk box / hip-yaw / shank cylinders against the ground */           \
+    int32_t enable_self_contact; /* 1: leg-leg capsule contacts (asset.self_collisions: 0 = enabled) */      \
     int32_t pad0;
 
 typedef struct B200T1ModelF { B200_MODEL_FIELDS(float) } B200T1ModelF;

@@ -133,6 +133,21 @@ class EnvOracle:
         self.s.setdefault("feet_yaw", np.zeros((self.n, 2), f32))
         self.s.setdefault("feet_contact", np.zeros((self.n, 2), bool))
         self.extras_time_outs = np.zeros(self.n, bool)
+        names = js["body_names"]   # envs/t1.py:86-92: substring match, in the order of the YAML lists
+        self.penalized = [names.index(b) for key in cfg["rewards"]["penalize_contacts_on"] for b in names if key in b]
+        self.terminating = [names.index(b) for key in cfg["rewards"]["terminate_contacts_on"] for b in names if key in b]
+
+    def contact_flags(self):
+        """[n, 13] bool: norm(contact_forces[:, b]) > 1.  Input either as the raw force tensor (fixtures made by the reference) or
+        as the kernel's per-lane bit masks (state rows `contact_mask`)."""
+        s = self.s
+        if "contact_forces" in s:
+            cf = np.asarray(s["contact_forces"], f32).reshape(self.n, 13, 3)
+            return np.sqrt(np.sum(cf * cf, axis=2, dtype=f32)) > f32(1.0)
+        if "contact_mask" in s:
+            mk = np.bitwise_or.reduce(np.asarray(s["contact_mask"]).reshape(self.n, -1).astype(np.int64), axis=1)
+            return ((mk[:, None] >> np.arange(13)[None, :]) & 1).astype(bool)
+        return np.zeros((self.n, 13), bool)
 
     def init_derived(self):
         """envs/t1.py:240-244: base-frame vectors from the state the env is constructed with"""
@@ -333,8 +348,8 @@ class EnvOracle:
             return np.exp(-sq(s["commands"][:, 2] - s["filtered_ang_vel"][:, 2]) / f32(rw["tracking_sigma"]))
         if name == "base_height":
             return sq(rs[:, 2] - self.h(rs[:, 0:3]) - f32(rw["base_height_target"]))
-        if name == "collision":
-            return np.zeros(n, f32)  # contact_forces of the penalised bodies: none carry contacts in this build
+        if name == "collision":  # envs/t1.py:627-629 on the per-body flags |contact_forces[b]| > 1
+            return np.sum(self.contact_flags()[:, self.penalized], axis=1).astype(f32)
         if name == "lin_vel_z":
             return sq(s["filtered_lin_vel"][:, 2])
         if name == "ang_vel_xy":
@@ -432,7 +447,8 @@ class EnvOracle:
         # _check_termination
         rw = cfg["rewards"]
         vsq = self._rowsum(np.square(rs[:, 7:13]))
-        reset = vsq > f32(rw["terminate_vel"])
+        reset = np.any(self.contact_flags()[:, self.terminating], axis=1)   # :553
+        reset |= vsq > f32(rw["terminate_vel"])
         reset |= rs[:, 2] - self.h(rs[:, 0:3]) < f32(rw["terminate_height"])
         time_out = s["episode_length_buf"] > np.ceil(rw["episode_length_s"] / self.dt)
         reset |= time_out

@@ -110,6 +110,17 @@ def tick(model, env, tau=None, push_f=(0, 0, 0), push_t=(0, 0, 0), terrain=None,
     return st, np.array(qacc), np.array(fn)
 
 
+def tick_f(model, env, tau=None, push_f=(0, 0, 0), push_t=(0, 0, 0), terrain=None, integrate=True):
+    """like tick(), also returning the net contact force per body [13, 3] (gym.refresh_net_contact_force_tensor rows)"""
+    terrain = terrain or make_terrain()
+    qacc = (C.c_double * 18)()
+    fn = (C.c_double * 2)()
+    bf = (C.c_double * 39)()
+    st = lib().t1o_tick_f(C.byref(model), C.byref(env), _d(tau if tau is not None else [0.0] * 12), _d(push_f), _d(push_t),
+                          C.byref(terrain), qacc, fn, bf, 1 if integrate else 0)
+    return st, np.array(qacc), np.array(fn), np.array(bf).reshape(13, 3)
+
+
 def mass_matrix(model, env):
     M = np.zeros((18, 18))
     lib().t1o_mass_matrix(C.byref(model), C.byref(env), M.ctypes.data_as(C.c_void_p))

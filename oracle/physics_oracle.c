@@ -206,10 +206,38 @@ void t1o_mass_matrix(const B200T1ModelD* m, const T1OEnv* e, double* M_out /*NV*
     memcpy(M_out, M, sizeof M);
 }
 
+/* One penalty contact point against the ground (normal +z), the force law of DESIGN.md "contact": adds dt J^T D J to M,
+ * J^T F to rhs and F to the body's net contact force.  p = world position of the point on body b. */
+static double ground_point(const B200T1ModelD* m, const Kin* k, int b, const double* p, const T1OTerrain* terr, const double* qvel,
+                           double kn, double cn, double mu, double M[NV][NV], double* rhs, double* body_f /*NB*3*/) {
+    const double dt = m->dt, dn = cn + dt * kn;
+    double Jv[3][NV], Jw[3][NV], vc[3] = {0, 0, 0};
+    /* the kernel evaluates the ground at fp32(pos + rel); mirror the rounding of the lookup argument */
+    double ground = t1o_terrain_height(terr, (float)p[0], (float)p[1]);
+    double depth = ground - p[2];
+    if (depth <= 0) return 0;
+    jacobian(k, b, p, Jv, Jw);
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < NV; ++i) vc[r] += Jv[r][i] * qvel[i];
+    double fn0 = kn * depth - cn * vc[2];
+    if (fn0 <= 0) return 0;
+    double vt = sqrt(vc[0] * vc[0] + vc[1] * vc[1]);
+    double dtan = mu * fn0 / fmax(vt, m->stiction_vel);
+    double D[3] = {dtan, dtan, dn};
+    double Fe[3] = {-dtan * vc[0], -dtan * vc[1], kn * depth - dn * vc[2]};
+    for (int i = 0; i < NV; ++i) {
+        for (int r = 0; r < 3; ++r) rhs[i] += Jv[r][i] * Fe[r];
+        for (int j = 0; j < NV; ++j)
+            for (int r = 0; r < 3; ++r) M[i][j] += dt * D[r] * Jv[r][i] * Jv[r][j];
+    }
+    for (int r = 0; r < 3; ++r) body_f[3 * b + r] += Fe[r];
+    return fn0;
+}
+
 /* One tick. tau[12], push_f/push_t in the trunk's LOCAL frame at the trunk CoM. Returns 0, or -1 if M_hat is not SPD.
  * qacc_out[18] (nullable); foot_fn_out[2] (nullable). */
-int t1o_tick(const B200T1ModelD* m, T1OEnv* e, const double* tau, const double* push_f, const double* push_t,
-             const T1OTerrain* terr, double* qacc_out, double* foot_fn_out, int integrate) {
+int t1o_tick_f(const B200T1ModelD* m, T1OEnv* e, const double* tau, const double* push_f, const double* push_t,
+               const T1OTerrain* terr, double* qacc_out, double* foot_fn_out, double* body_f_out /*13*3, nullable*/, int integrate) {
     Kin k;
     kinematics(m, e, &k);
     const double dt = m->dt;
@@ -258,35 +286,45 @@ int t1o_tick(const B200T1ModelD* m, T1OEnv* e, const double* tau, const double* 
     }
     /* foot contact: linearly-implicit normal spring-damper + lagged regularised Coulomb friction */
     double foot_fn[2] = {0, 0};
+    double body_f[NB * 3];
+    memset(body_f, 0, sizeof body_f);
     if (m->enable_contact) {
         for (int s = 0; s < 2; ++s) {
             int b = 6 + 6 * s;
-            double kn = m->contact_k * e->kscale[s], cn = m->contact_c * e->cscale[s], dn = cn + dt * kn;
+            double kn = m->contact_k * e->kscale[s], cn = m->contact_c * e->cscale[s];
             for (int c = 0; c < 4; ++c) {
-                double rp[3], p[3], Jv[3][NV], Jw[3][NV], vc[3] = {0, 0, 0};
+                double rp[3], p[3];
                 matvec(k.R[b], m->foot_corner[c], rp);
-                /* the kernel evaluates the ground at fp32(pos + rel); mirror the rounding of the lookup argument */
                 for (int r = 0; r < 3; ++r) p[r] = k.x[b][r] + rp[r];
-                double ground = t1o_terrain_height(terr, (float)p[0], (float)p[1]);
-                double depth = ground - p[2];
-                if (depth <= 0) continue;
-                jacobian(&k, b, p, Jv, Jw);
-                for (int r = 0; r < 3; ++r)
-                    for (int i = 0; i < NV; ++i) vc[r] += Jv[r][i] * qvel[i];
-                double fn0 = kn * depth - cn * vc[2];
-                if (fn0 <= 0) continue;
-                foot_fn[s] += fn0;
-                double vt = sqrt(vc[0] * vc[0] + vc[1] * vc[1]);
-                double dtan = e->mu[s] * fn0 / fmax(vt, m->stiction_vel);
-                double D[3] = {dtan, dtan, dn};
-                double Fe[3] = {-dtan * vc[0], -dtan * vc[1], kn * depth - dn * vc[2]};
-                for (int i = 0; i < NV; ++i) {
-                    for (int r = 0; r < 3; ++r) rhs[i] += Jv[r][i] * Fe[r];
-                    for (int j = 0; j < NV; ++j)
-                        for (int r = 0; r < 3; ++r) M[i][j] += dt * D[r] * Jv[r][i] * Jv[r][j];
-                }
+                foot_fn[s] += ground_point(m, &k, b, p, terr, qvel, kn, cn, e->mu[s], M, rhs, body_f);
             }
         }
+    }
+    /* the other collision primitives against the ground: trunk box corners, lowest rim point of each end
+     * cap of the hip-yaw and shank cylinders (resources/T1/T1_locomotion.xml:42,66,71,99,104) */
+    if (m->enable_body_contact) {
+        for (int c = 0; c < 8; ++c) {
+            double l[3], rp[3], p[3];
+            for (int r = 0; r < 3; ++r) l[r] = m->trunk_box_pos[r] + (((c >> r) & 1) ? -1.0 : 1.0) * m->trunk_box_half[r];
+            matvec(k.R[0], l, rp);
+            for (int r = 0; r < 3; ++r) p[r] = k.x[0][r] + rp[r];
+            ground_point(m, &k, 0, p, terr, qvel, m->contact_k, m->contact_c, m->body_mu, M, rhs, body_f);
+        }
+        for (int s = 0; s < 2; ++s)
+            for (int ci = 0; ci < 2; ++ci) {
+                int b = 1 + 6 * s + 2 + ci;
+                double cw[3], a[3] = {k.R[b][2], k.R[b][5], k.R[b][8]}, down[3];
+                matvec(k.R[b], m->cyl_pos[ci], cw);
+                /* unit vector in the cap plane pointing most steeply down: -(z - (z.a) a) / |.| ; none if the cylinder stands upright */
+                double n2 = 1.0 - a[2] * a[2], inv = (n2 > 1e-12) ? 1.0 / sqrt(n2) : 0.0;
+                down[0] = a[2] * a[0] * inv; down[1] = a[2] * a[1] * inv; down[2] = -n2 * inv;
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    double p[3];
+                    for (int r = 0; r < 3; ++r)
+                        p[r] = k.x[b][r] + cw[r] + (e2 ? -1.0 : 1.0) * m->cyl_half[ci] * a[r] + m->cyl_radius[ci] * down[r];
+                    ground_point(m, &k, b, p, terr, qvel, m->contact_k, m->contact_c, m->body_mu, M, rhs, body_f);
+                }
+            }
     }
     if (m->enable_limits) {
         for (int j = 0; j < 12; ++j) {
@@ -303,6 +341,7 @@ int t1o_tick(const B200T1ModelD* m, T1OEnv* e, const double* tau, const double* 
     if (cholesky_solve(M, rhs) != 0) return -1;
     if (qacc_out) memcpy(qacc_out, rhs, sizeof rhs);
     if (foot_fn_out) { foot_fn_out[0] = foot_fn[0]; foot_fn_out[1] = foot_fn[1]; }
+    if (body_f_out) memcpy(body_f_out, body_f, sizeof body_f);
     if (!integrate) return 0;
     /* mj_Euler: velocities first, positions with the NEW velocities, exact quaternion exponential */
     for (int r = 0; r < 3; ++r) {
@@ -323,6 +362,11 @@ int t1o_tick(const B200T1ModelD* m, T1OEnv* e, const double* tau, const double* 
         for (int i = 0; i < 4; ++i) e->quat[i] = nq[i] / n2;
     }
     return 0;
+}
+
+int t1o_tick(const B200T1ModelD* m, T1OEnv* e, const double* tau, const double* push_f, const double* push_t,
+             const T1OTerrain* terr, double* qacc_out, double* foot_fn_out, int integrate) {
+    return t1o_tick_f(m, e, tau, push_f, push_t, terr, qacc_out, foot_fn_out, 0, integrate);
 }
 
 /* feet world pose (position, quaternion xyzw by the same Shepperd branches as the kernel is NOT required: tests

@@ -233,7 +233,9 @@ def build_reference_env(mods, cfg, state, hf=None):
     body_states[:, [6, 12], 3:7] = T(state["feet_quat"]).reshape(n, 2, 4)
     dof_state = torch.stack([T(state["dof_pos"]), T(state["dof_vel"])], dim=-1).reshape(n * 12, 2).contiguous()
     tensors = dict(root_states=T(state["root_states"]).clone(), dof_state=dof_state,
-                   contact_forces=torch.zeros(n * 13, 3), body_states=body_states.reshape(n * 13, 13))
+                   contact_forces=(T(state["contact_forces"]).reshape(n * 13, 3).clone() if "contact_forces" in state
+                                   else torch.zeros(n * 13, 3)),
+                   body_states=body_states.reshape(n * 13, 13))
     e = t1_mod.T1.__new__(t1_mod.T1)
     e.cfg, e.device, e.gym, e.sim = cfg, "cpu", NullGym(tensors), None
     e.viewer, e.camera, e.headless, e.up_axis_idx, e.enable_viewer_sync = None, None, True, 2, True
@@ -259,7 +261,10 @@ def build_reference_env(mods, cfg, state, hf=None):
     for key in cfg["rewards"]["penalize_contacts_on"]:
         pen.extend([s for s in names if key in s])
     e.penalized_contact_indices = torch.tensor([names.index(s) for s in pen], dtype=torch.long)
-    e.termination_contact_indices = torch.zeros(0, dtype=torch.long)
+    term = []   # envs/t1.py:90-92
+    for key in cfg["rewards"]["terminate_contacts_on"]:
+        term.extend([s for s in names if key in s])
+    e.termination_contact_indices = torch.tensor([names.index(s) for s in term], dtype=torch.long)
     e.base_indice = 0
     e.feet_indices = torch.tensor([6, 12], dtype=torch.long)
     st = cfg["init_state"]

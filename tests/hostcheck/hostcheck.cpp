@@ -16,7 +16,7 @@ template <typename T> struct FlatEnv {  // mirrors oracle T1OEnv field order, in
 template <typename T, typename Model>
 static int tick_impl(const Model* m, FlatEnv<T>* e, const T* tau, const T* push_f, const T* push_t, const int16_t* hf,
                      int rows, int cols, int border_pixels, float hscale, double vscale, T* qacc, T* foot_fn,
-                     int integrate) {
+                     int integrate, T* contact_out /*9, nullable: |F|^2 of hip-yaw, shank, foot per leg, then the trunk force*/) {
     DynState<T> s;
     DynParams<T> p;
     memcpy(s.pos, e->pos, sizeof(T) * 3); memcpy(s.quat, e->quat, sizeof(T) * 4);
@@ -33,6 +33,11 @@ static int tick_impl(const Model* m, FlatEnv<T>* e, const T* tau, const T* push_
     memcpy(e->q, s.q, sizeof(T) * 12); memcpy(e->qd, s.qd, sizeof(T) * 12);
     if (qacc) memcpy(qacc, aux.qacc, sizeof(T) * B200_NV);
     if (foot_fn) { foot_fn[0] = aux.foot_fn[0]; foot_fn[1] = aux.foot_fn[1]; }
+    if (contact_out) {
+        for (int sd = 0; sd < 2; ++sd)
+            for (int i = 0; i < 3; ++i) contact_out[3 * sd + i] = aux.body_f2[sd][i];
+        for (int i = 0; i < 3; ++i) contact_out[6 + i] = aux.trunk_f[i];
+    }
     return 0;
 }
 
@@ -40,12 +45,17 @@ extern "C" {
 int hc_tick_d(const B200T1ModelD* m, void* env, const double* tau, const double* push_f, const double* push_t,
               const int16_t* hf, int rows, int cols, int border_pixels, float hscale, double vscale, double* qacc,
               double* foot_fn, int integrate) {
-    return tick_impl<double>(m, (FlatEnv<double>*)env, tau, push_f, push_t, hf, rows, cols, border_pixels, hscale, vscale, qacc, foot_fn, integrate);
+    return tick_impl<double>(m, (FlatEnv<double>*)env, tau, push_f, push_t, hf, rows, cols, border_pixels, hscale, vscale, qacc, foot_fn, integrate, nullptr);
+}
+int hc_tick_d_contacts(const B200T1ModelD* m, void* env, const double* tau, const double* push_f, const double* push_t,
+                       const int16_t* hf, int rows, int cols, int border_pixels, float hscale, double vscale, double* qacc,
+                       double* foot_fn, int integrate, double* contact_out) {
+    return tick_impl<double>(m, (FlatEnv<double>*)env, tau, push_f, push_t, hf, rows, cols, border_pixels, hscale, vscale, qacc, foot_fn, integrate, contact_out);
 }
 int hc_tick_f(const B200T1ModelF* m, void* env, const float* tau, const float* push_f, const float* push_t,
               const int16_t* hf, int rows, int cols, int border_pixels, float hscale, double vscale, float* qacc,
               float* foot_fn, int integrate) {
-    return tick_impl<float>(m, (FlatEnv<float>*)env, tau, push_f, push_t, hf, rows, cols, border_pixels, hscale, vscale, qacc, foot_fn, integrate);
+    return tick_impl<float>(m, (FlatEnv<float>*)env, tau, push_f, push_t, hf, rows, cols, border_pixels, hscale, vscale, qacc, foot_fn, integrate, nullptr);
 }
 float hc_terrain_height(const int16_t* hf, int rows, int cols, int border_pixels, float hscale, double vscale, float x, float y) {
     TerrainView tv{hf, rows, cols, border_pixels, hscale, vscale};

@@ -147,6 +147,44 @@ def test_decimated_loop_against_fp64_oracle(t1_cfg):
     assert np.abs(env.last_dof_targets.cpu().double().numpy() - lt).max() < 1e-6
 
 
+def test_body_contacts_against_fp64_oracle(t1_cfg):
+    """trunk box / hip-yaw / shank cylinders against the ground on tumbling low robots.  One tick: qacc within
+    2e-3 * max(1, |qacc|_inf) of the FP64 oracle (the foot-contact tolerance), and the per-body contact flags the env reads
+    (|net contact force| > 1 N: collision reward envs/t1.py:627-629, termination :553) equal to the oracle's."""
+    from oracle import physics as op
+
+    n = 128
+    env = make_env(t1_cfg, n)
+    g = randomize_state(env, 23, True)
+    rs = env.root_states.clone()
+    rs[:, 2] = (0.05 + 0.45 * torch.rand(n, generator=g)).cuda()
+    q = torch.randn(n, 4, generator=g)
+    rs[:, 3:7] = (q / q.norm(dim=1, keepdim=True)).cuda()
+    env.root_states.copy_(rs)
+    tau = torch.randn(n, 12, generator=g) * 10.0
+    md, oenvs = oracle_envs(env, range(n))
+    qacc = torch.zeros(18, n, device="cuda")
+    env.physics(tau.cuda(), 1, apply_pd=False, qacc_out=qacc)
+    torch.cuda.synchronize()
+    qa = qacc.cpu().double().numpy()
+    mask = env._iview("contact_mask").cpu().numpy()
+    mask = mask[:, 0] | mask[:, 1]
+    worst = 0.0
+    hits = np.zeros(13, int)
+    for e in range(n):
+        st, ref, fn, bf = op.tick_f(md, oenvs[e], tau[e].double().numpy(), integrate=False)
+        assert st == 0
+        worst = max(worst, np.abs(qa[:, e] - ref).max() / max(1.0, np.abs(ref).max()))
+        fnorm = np.linalg.norm(bf, axis=1)
+        hits += fnorm > 1
+        for b in range(13):
+            if abs(fnorm[b] - 1.0) > 0.05:   # away from the threshold the fp32 kernel and the fp64 oracle must agree
+                assert bool((mask[e] >> b) & 1) == bool(fnorm[b] > 1.0), (e, b, fnorm[b])
+    print("worst relative qacc error", worst, "contacts per body", hits)
+    assert worst < 2e-3
+    assert hits[0] > 10 and min(hits[3], hits[4], hits[9], hits[10]) > 5
+
+
 def test_free_fall_and_momentum(t1_cfg):
     """physical invariants (SURVEY 8c ii): zero-torque free fall has base qacc (0,0,-g); feet FK matches the oracle"""
     from oracle import physics as op

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import OUT_EXACT, OUT_FLOAT, STATE_KEYS, close, load, load_cfg, model_json, step_inputs
+from golden_util import OUT_EXACT, OUT_FLOAT, STATE_KEYS, close, fixture_cfg, load, load_cfg, model_json, step_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -70,10 +70,11 @@ def compare(got, terms, ref, ref_terms):
 
 
 @pytest.mark.parametrize("name,terrain", [("env_step_plane.npz", "plane"), ("env_step_trimesh.npz", "trimesh"),
-                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_trimesh_noreset.npz", "trimesh")])
+                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_trimesh_noreset.npz", "trimesh"),
+                                          ("env_step_contacts.npz", "plane")])
 def test_post_physics_kernel_matches_reference_fixture(name, terrain):
     z = load(name)
-    cfg = load_cfg(terrain)
+    cfg = fixture_cfg(name, terrain)
     hf = z["hf"] if "hf" in z.files else None
     got, terms = gpu_step(cfg, step_inputs(z), z["table"], z["common_step"], hf)
     ref = {k: z["out_" + k] for k in OUT_EXACT + OUT_FLOAT}

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from golden_util import OUT_EXACT, OUT_FLOAT, STATE_KEYS, close, load, load_cfg, step_inputs
+from golden_util import OUT_EXACT, OUT_FLOAT, STATE_KEYS, close, fixture_cfg, load, load_cfg, step_inputs
 from hostcheck_util import lib, pack_state, unpack
 
 
@@ -19,8 +19,8 @@ def _cfg_structs(cfg):
     return m, c
 
 
-def run_host_step(z, terrain):
-    cfg = load_cfg(terrain)
+def run_host_step(z, terrain, name=None):
+    cfg = fixture_cfg(name, terrain)
     m, c = _cfg_structs(cfg)
     st = step_inputs(z)
     n = st["root_states"].shape[0]
@@ -39,12 +39,13 @@ def run_host_step(z, terrain):
 
 
 @pytest.mark.parametrize("name,terrain", [("env_step_plane.npz", "plane"), ("env_step_trimesh.npz", "trimesh"),
-                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_trimesh_noreset.npz", "trimesh")])
+                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_trimesh_noreset.npz", "trimesh"),
+                                          ("env_step_contacts.npz", "plane")])
 def test_post_physics_body_matches_reference(name, terrain):
     from booster_gym_b200 import config
 
     z = load(name)
-    cfg, got, terms = run_host_step(z, terrain)
+    cfg, got, terms = run_host_step(z, terrain, name)
     for k in OUT_EXACT:   # masks, counters, indices: bit-exact
         assert np.array_equal(np.asarray(got[k]).astype(np.int64).reshape(z["out_" + k].shape), z["out_" + k].astype(np.int64)), k
     for k in OUT_FLOAT:   # fp32: 1e-5 relative (north_star)
@@ -180,3 +181,56 @@ def test_physics_oracle_invariants():
     c0 = L0; c1 = L1
     assert np.allclose(c0, c1, rtol=5e-3, atol=0.2)             # angular momentum about the origin, same O(dt) argument
     assert abs(E1 - E0) < 0.05 * abs(E0)                      # semi-implicit Euler energy drift over 0.4 s
+
+
+def test_body_contacts_match_fp64_oracle():
+    """trunk box corners and the hip-yaw / shank cylinders against the ground.  The kernel recursion (composite
+    contact matrices folded into the CRBA sweep, double) vs the dense-Jacobian oracle on tumbling low robots: qacc to 1e-10,
+    the net contact force per body (what contact_forces / the collision reward read) to 1e-8."""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    md = robot.model_d()
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    hits = np.zeros(13, int)
+    for it in range(120):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        e = op.make_env(md, pos=(rng.normal(), rng.normal(), rng.uniform(0.05, 0.5)), quat=q, vlin=rng.normal(size=3), wb=rng.normal(size=3) * 2,
+                        q=rng.uniform(-0.8, 0.8, 12), qd=rng.normal(size=12) * 3)
+        tau = rng.normal(size=12) * 10
+        st, qa_o, fn_o, bf = op.tick_f(md, op.Env.from_buffer_copy(e), tau, integrate=False)
+        assert st == 0
+        e2 = op.Env.from_buffer_copy(e)
+        qacc = (C.c_double * 18)(); fn = (C.c_double * 2)(); co = (C.c_double * 9)()
+        lib().hc_tick_d_contacts(C.byref(md), C.byref(e2), op._d(tau), op._d([0] * 3), op._d([0] * 3), None, 0, 0, 50, C.c_float(0.1),
+                                 C.c_double(0.005), qacc, fn, 0, co)
+        worst = max(worst, np.max(np.abs(qa_o - np.array(qacc))) / max(1.0, np.max(np.abs(qa_o))))
+        f2 = (bf ** 2).sum(axis=1)
+        hits += f2 > 1
+        co = np.array(co)
+        assert np.allclose(co[:6], f2[[3, 4, 6, 9, 10, 12]], rtol=1e-8, atol=1e-8)
+        assert np.allclose(co[6:], bf[0], rtol=1e-8, atol=1e-8)
+        assert not f2[[1, 2, 5, 7, 8, 11]].any()          # links without collision geometry
+    assert worst < 1e-10
+    assert hits[0] > 10 and min(hits[3], hits[4], hits[9], hits[10]) > 5   # every new shape was exercised
+
+
+def test_fallen_robot_rests_on_its_body():
+    """a robot dropped face-down / on its back / on its side comes to rest ON the trunk box and the leg cylinders (before f3 it sank
+    until the soles caught it): the supporting forces add up to its weight and non-foot bodies carry most of it"""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    md = robot.model_d()
+    q0 = np.array([-0.2, 0, 0, 0.4, -0.25, 0] * 2)
+    h = np.sin(np.pi / 4)
+    for quat in [(0, h, 0, h), (0, -h, 0, h), (h, 0, 0, h)]:
+        e = op.make_env(md, pos=(0, 0, 0.4), quat=quat, q=q0)
+        for _ in range(1000):
+            tau = 50 * (q0 - np.array(e.q[:])) - 1.0 * np.array(e.qd[:])
+            st, _, _, bf = op.tick_f(md, e, tau)
+            assert st == 0
+        assert np.linalg.norm(e.vlin[:]) < 5e-3 and e.pos[2] > 0.0
+        assert abs(bf[:, 2].sum() - 31.6144 * 9.81) < 0.02 * 31.6144 * 9.81
+        assert np.linalg.norm(bf[[0, 3, 4, 9, 10]], axis=1).sum() > 200.0

@@ -4,16 +4,17 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import OUT_EXACT, OUT_FLOAT, close, load, load_cfg, model_json, step_inputs
+from golden_util import OUT_EXACT, OUT_FLOAT, close, fixture_cfg, load, load_cfg, model_json, step_inputs
 
 
 @pytest.mark.parametrize("name,terrain", [("env_step_plane.npz", "plane"), ("env_step_trimesh.npz", "trimesh"),
-                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_trimesh_noreset.npz", "trimesh")])
+                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_trimesh_noreset.npz", "trimesh"),
+                                          ("env_step_contacts.npz", "plane")])
 def test_env_oracle_step_matches_reference(name, terrain):
     from oracle.env_oracle import EnvOracle
 
     z = load(name)
-    cfg = load_cfg(terrain)
+    cfg = fixture_cfg(name, terrain)
     hf = z["hf"] if "hf" in z.files else None
     o = EnvOracle(cfg, step_inputs(z), hf, model_json())
     out = o.step_post(z["table"], int(z["common_step"]))

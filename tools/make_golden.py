@@ -176,6 +176,34 @@ def gen_env(mods):
             np.savez_compressed(os.path.join(OUT, "terrain_lookup.npz"), hf=hf, xy=xy, heights=h)
 
 
+def gen_contacts(mods):
+    """net contact forces on non-foot bodies -> `collision` reward (envs/t1.py:627-629) and contact termination
+    (:553, with terminate_contacts_on set).  contact_forces is an INPUT of the reference step (gym tensor, physics = identity)."""
+    cfg = load_cfg("plane")
+    cfg["rewards"]["terminate_contacts_on"] = ["Trunk", "Shank"]
+    n = 96
+    state = synthetic_state(n, 11, False)
+    state["root_states"][:, 2] = 0.7            # nobody terminates by height: resets below come from contacts / velocity / length
+    gg = np.random.default_rng(21)
+    cf = np.zeros((n, 13, 3), np.float32)
+    hit = gg.uniform(size=(n, 13)) < 0.25
+    mag = np.where(gg.uniform(size=(n, 13)) < 0.5, gg.uniform(0.2, 0.999, (n, 13)), gg.uniform(1.001, 300.0, (n, 13)))
+    d = gg.normal(size=(n, 13, 3))
+    d /= np.linalg.norm(d, axis=2, keepdims=True)
+    cf[hit] = (d * mag[:, :, None])[hit].astype(np.float32)
+    cf[:, [1, 2, 5, 7, 8, 11]] = 0.0             # links without collision geometry never carry contact forces
+    state["contact_forces"] = cf
+    actions = np.random.default_rng(5).uniform(-1.4, 1.4, (n, 12)).astype(np.float32)
+    table, cap, out, log = run_reference_step(mods, cfg, state, None, 499, actions, 83)
+    save = {"in_" + k: v for k, v in state.items()}
+    save.update({"out_" + k: v for k, v in out.items()})
+    save.update(actions_raw=actions, table=table, common_step=np.int64(500), post_loop_torques=cap["torques"],
+                post_loop_last_dof_targets=cap["last_dof_targets"], post_loop_actions=cap["actions"])
+    np.savez_compressed(os.path.join(OUT, "env_step_contacts.npz"), **save)
+    print("contacts step: resets", int(out["reset_buf"].sum()), "collision term min", float(out["term_collision"].min()),
+          "envs with collisions", int((out["term_collision"] != 0).sum()))
+
+
 def gen_learner(mods):
     import torch.nn.functional as F
 
@@ -277,7 +305,11 @@ if __name__ == "__main__":
     if ref is None:
         raise SystemExit("reference tree not found")
     mods = H.import_reference()
+    if "--contacts-only" in sys.argv:
+        gen_contacts(mods)
+        raise SystemExit(0)
     gen_env(mods)
+    gen_contacts(mods)
     gen_learner(mods)
     gen_actor(ref)
     print("fixtures written to", OUT)
