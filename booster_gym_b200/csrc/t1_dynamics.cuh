@@ -42,6 +42,15 @@ B200_HD void b_sincos(float x, float& s, float& c) {
 B200_HD void b_sincos(double x, double& s, double& c) { s = sin(x); c = cos(x); }
 B200_HD float b_sqrt(float x) { return sqrtf(x); }
 B200_HD double b_sqrt(double x) { return sqrt(x); }
+// division in the rarely executed shape code: approximate on the device (2 ulp), exact on the host
+B200_HD float b_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+B200_HD double b_div(double a, double b) { return a / b; }
 B200_HD float b_abs(float x) { return fabsf(x); }
 B200_HD double b_abs(double x) { return fabs(x); }
 B200_HD float b_max(float a, float b) { return fmaxf(a, b); }
@@ -190,93 +199,242 @@ B200_HD bool contact_ground_point(const T* p, T depth, const T* w, const T* v, T
     return true;
 }
 
-// ---- the rarely touching shapes: trunk box, hip-yaw and shank cylinders -------------------------------------
-// They are evaluated by shapes_prepass() (below, after LegState), OUT OF LINE and BEFORE the tick's forward pass, i.e. at a
-// point where few values are live: k_physics is one warp per CTA at 255 registers, and shape code placed inside the forward
-// pass cost 10 % of the tick even when it never ran.  Results travel through a per-thread scratch (shared memory on the
-// device, stride KS = block size; a plain array with KS = 1 on the host), slot j = 0 trunk share, 1 hip-yaw, 2 shank:
+// ---- the rarely touching shapes: trunk box, hip-yaw and shank cylinders, leg-leg capsules -----------------------
+// k_physics is one warp per CTA at 255 registers and streams its code from L2: shape code placed inline in the tick cost
+// 10 % even when it never ran.  So the tick only PUBLISHES the few frames the shapes need into a per-thread scratch (shared
+// memory on the device, stride KS = block size; a plain array with KS = 1 on the host), applies exact conservative culls
+// (lowest point of a shape above the highest terrain sample; the two legs on their own sides of the trunk's sagittal
+// plane), and when a cull fails calls shapes_eval() OUT OF LINE, which reads the scratch (its own and the partner leg
+// lane's) and leaves one slot per body:  slot j = 0 trunk share, 1 hip-yaw link, 2 shank, 3 foot (leg-leg contacts only; the
+// sole corners stay in the tick):
 //   Kx[(27 j + i) KS], i < 21: implicit contact matrix (6x6 lower-tri, [ang; lin]);  i = 21..23: wrench moment about the
 //   reference point;  i = 24..26: net contact force.
+// Published geometry, at B200_KX_GEOM + :  0..5 shank capsule axis ends (+z, -z; relative to the trunk origin, world axes),
+// 6..11 shank spatial velocity (w, v) about the trunk origin, 12..17 foot capsule axis ends, 18..23 foot spatial velocity,
+// 24..26 hip-yaw cylinder centre, 27..29 its axis, 30..35 hip-yaw link spatial velocity, 36 `inward` (publish_shank);
+// 37..45 trunk rotation, 46..48 trunk position, 49..54 trunk spatial velocity (written only ahead of a trunk evaluation).
 #define B200_KX_SLOT 27
-#define B200_KX_SIZE (3 * B200_KX_SLOT)
+#define B200_KX_GEOM (4 * B200_KX_SLOT)
+#define B200_KX_SIZE (B200_KX_GEOM + 55)
+#if defined(__CUDA_ARCH__)
+#define B200_SYNCWARP() __syncwarp()
+#else
+#define B200_SYNCWARP()
+#endif
 
-template <typename T> struct ShapeFrame {
-    T R[3][3];   // frame of the body that carries the shape
-    T x[3];      // its origin relative to the reference point (the trunk origin)
-    T pos[3];    // world position of the reference point
-    T w[3], v[3];  // spatial velocity of the body about the reference point
+// accumulators of one scratch slot while shapes_eval runs (K itself accumulates in the scratch)
+template <typename T> struct ShapeAcc {
+    T Wn[3], Wf[3];
+    bool init, active;
 };
-
-template <int KS, typename T> B200_HD void shape_slot_clear(T* K) {
+template <int KS, typename T> B200_HD void shape_slot_begin(ShapeAcc<T>& acc, T* K) {
+    if (acc.init) return;
+    acc.init = true;
 #pragma unroll
-    for (int i = 0; i < B200_KX_SLOT; ++i) K[i * KS] = 0;
-}
-template <int KS, typename T> B200_HD void shape_slot_wrench(T* K, const T* Wn, const T* Wf) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) { K[(21 + r) * KS] = Wn[r]; K[(24 + r) * KS] = Wf[r]; }
+    for (int i = 0; i < 21; ++i) K[i * KS] = 0;
 }
 
-// One collision cylinder (axis = body z; resources/T1/T1_locomotion.xml:66,71,99,104) against the ground: the lowest rim
-// point of each end cap is a contact point (the deepest points of a cylinder over a flat patch unless it stands on a cap).
+// One collision cylinder (centre c relative to the reference point, unit axis a; resources/T1/T1_locomotion.xml:66,71,99,104)
+// against the ground: the lowest rim point of each end cap is a contact point (the deepest points of a cylinder over a
+// flat patch unless it stands on a cap).
 template <int KS, typename T, typename Model, typename Terr>
-B200_HD bool cylinder_ground(const Model& m, int ci, const ShapeFrame<T>& g, const Terr& terr, T* K) {
-    const T* cp = m.cyl_pos[ci];
+B200_HD void cylinder_ground(const Model& m, int ci, const T* c, const T* a, const T* pos, const T* w, const T* v, const Terr& terr,
+                             T* K, ShapeAcc<T>& acc) {
     const T rad = m.cyl_radius[ci], half = m.cyl_half[ci];
-    T c[3], a[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        c[r] = g.x[r] + g.R[r][0] * cp[0] + g.R[r][1] * cp[1] + g.R[r][2] * cp[2];
-        a[r] = g.R[r][2];
-    }
-    // cull: lowest point of the cylinder = centre_z - half |a_z| - rad sqrt(1 - a_z^2)
     const T n2 = b_max(T(1) - a[2] * a[2], T(0));
-    const T sn = b_sqrt(n2);
-    if (g.pos[2] + c[2] - (half * b_abs(a[2]) + rad * sn) > (T)terr.max_height) return false;
-    shape_slot_clear<KS>(K);
-    T Wn[3] = {0, 0, 0}, Wf[3] = {0, 0, 0};
+    shape_slot_begin<KS>(acc, K);
     // lowest rim point of a cap = cap centre - rad * d / |d| with d = z - (z.a) a  (|d|^2 = 1 - a_z^2)
-    const T sc = (n2 > T(1e-12)) ? rad / sn : T(0);
+    const T sc = (n2 > T(1e-12)) ? rad / b_sqrt(n2) : T(0);
     const T off[3] = {sc * a[2] * a[0], sc * a[2] * a[1], -sc * n2};
     const T kn = m.contact_k, cn = m.contact_c, dn = cn + m.dt * kn;
-    bool active = false;
     T fsum = 0;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         const T hs = e ? -half : half;
         const T p[3] = {c[0] + hs * a[0] + off[0], c[1] + hs * a[1] + off[1], c[2] + hs * a[2] + off[2]};
-        const T ground = (T)terr((float)(g.pos[0] + p[0]), (float)(g.pos[1] + p[1]));
-        const T depth = ground - (g.pos[2] + p[2]);
-        if (depth > 0 && contact_ground_point<KS>(p, depth, g.w, g.v, kn, cn, dn, m.body_mu, m.dt, m.stiction_vel, K, Wn, Wf, fsum)) active = true;
+        const T ground = (T)terr((float)(pos[0] + p[0]), (float)(pos[1] + p[1]));
+        const T depth = ground - (pos[2] + p[2]);
+        if (depth > 0 && contact_ground_point<KS>(p, depth, w, v, kn, cn, dn, m.body_mu, m.dt, m.stiction_vel, K, acc.Wn, acc.Wf, fsum))
+            acc.active = true;
     }
-    if (active) shape_slot_wrench<KS>(K, Wn, Wf);
-    return active;
 }
 
 // The trunk box (resources/T1/T1_locomotion.xml:42): the 4 corners on the side of this leg lane (side 0: +y, 1: -y).
 template <int KS, typename T, typename Model, typename Terr>
-B200_HD bool trunk_ground(const Model& m, int side, const ShapeFrame<T>& g, const Terr& terr, T* K) {
+B200_HD void trunk_ground(const Model& m, int side, const T R0[3][3], const T* pos, const T* w, const T* v, const Terr& terr, T* K,
+                          ShapeAcc<T>& acc) {
     const T* bp = m.trunk_box_pos;
     const T* bh = m.trunk_box_half;
     const T ly = bp[1] + (side == 0 ? bh[1] : -bh[1]);
-    const T low = g.pos[2] + g.R[2][0] * bp[0] + g.R[2][1] * ly + g.R[2][2] * bp[2] - (b_abs(g.R[2][0]) * bh[0] + b_abs(g.R[2][2]) * bh[2]);
-    if (low > (T)terr.max_height) return false;
-    shape_slot_clear<KS>(K);
-    T Wn[3] = {0, 0, 0}, Wf[3] = {0, 0, 0};
+    shape_slot_begin<KS>(acc, K);
     const T kn = m.contact_k, cn = m.contact_c, dn = cn + m.dt * kn;
-    bool active = false;
     T fsum = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const T lx = bp[0] + ((c & 1) ? -bh[0] : bh[0]), lz = bp[2] + ((c & 2) ? -bh[2] : bh[2]);
         T p[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) p[r] = g.R[r][0] * lx + g.R[r][1] * ly + g.R[r][2] * lz;
-        const T ground = (T)terr((float)(g.pos[0] + p[0]), (float)(g.pos[1] + p[1]));
-        const T depth = ground - (g.pos[2] + p[2]);
-        if (depth > 0 && contact_ground_point<KS>(p, depth, g.w, g.v, kn, cn, dn, m.body_mu, m.dt, m.stiction_vel, K, Wn, Wf, fsum)) active = true;
+        for (int r = 0; r < 3; ++r) p[r] = R0[r][0] * lx + R0[r][1] * ly + R0[r][2] * lz;
+        const T ground = (T)terr((float)(pos[0] + p[0]), (float)(pos[1] + p[1]));
+        const T depth = ground - (pos[2] + p[2]);
+        if (depth > 0 && contact_ground_point<KS>(p, depth, w, v, kn, cn, dn, m.body_mu, m.dt, m.stiction_vel, K, acc.Wn, acc.Wf, fsum))
+            acc.active = true;
     }
-    if (active) shape_slot_wrench<KS>(K, Wn, Wf);
-    return active;
+}
+
+// ---- leg-leg contacts (asset.self_collisions: 0 = enabled, envs/T1.yaml:69) -------------------------------------------------
+// The shank cylinder and the foot box of each leg are treated as capsules (segment + radius).  Every (left, right) pair of
+// capsules closer than the sum of the radii pushes the two bodies apart along the line between the closest axis points with
+// a linearly-implicit spring-damper on the RELATIVE normal velocity; each leg lane is implicit in its own velocity only (the
+// partner's velocity enters explicitly), so the legs stay uncoupled in the mass matrix and the forces are equal and opposite.
+// closest points of two segments P1 + s d1, P2 + t d2 (s, t in [0, 1]); both segments have positive length
+template <typename T> B200_HD T clamp01(T x) { return x < 0 ? T(0) : (x > 1 ? T(1) : x); }
+template <typename T> B200_HD void segment_closest(const T* P1, const T* d1, const T* P2, const T* d2, T& s, T& t) {
+    // branch-free (selects only): the tick evaluates two of these on every step and lets the scheduler interleave them
+    const T r[3] = {P1[0] - P2[0], P1[1] - P2[1], P1[2] - P2[2]};
+    const T a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), c = dot3(d1, r), b = dot3(d1, d2);
+    const T denom = a * e - b * b;
+    const T ia = b_div(T(1), a), ie = b_div(T(1), e);
+    const T s0 = (denom > T(1e-12) * a * e) ? clamp01(b_div(b * f - c * e, denom)) : T(0);
+    const T t0 = (b * s0 + f) * ie;
+    const T s_lo = clamp01(-c * ia), s_hi = clamp01((b - c) * ia);
+    s = (t0 < 0) ? s_lo : ((t0 > 1) ? s_hi : s0);
+    t = clamp01(t0);
+}
+
+// Bounding spheres of MY capsule i and the partner's capsule j (0 shank, 1 foot) from the published geometry (G mine, Gp the
+// partner's: axis ends at 12 i + 0..5): false = too far apart to touch.
+template <int KS, typename T, typename Model>
+B200_HD bool capsule_spheres_touch(const Model& m, int i, int j, const T* G, const T* Gp) {
+    T cc[3], la = 0, lb = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const T a0 = G[(12 * i + r) * KS], a1 = G[(12 * i + 3 + r) * KS], b0 = Gp[(12 * j + r) * KS], b1 = Gp[(12 * j + 3 + r) * KS];
+        cc[r] = T(0.5) * ((a0 + a1) - (b0 + b1));
+        la += (a1 - a0) * (a1 - a0);
+        lb += (b1 - b0) * (b1 - b0);
+    }
+    const T reach = T(0.5) * (b_sqrt(la) + b_sqrt(lb)) + ((i == 0) ? m.cyl_radius[1] : m.foot_cap_radius) + ((j == 0) ? m.cyl_radius[1] : m.foot_cap_radius);
+    return !(dot3(cc, cc) > reach * reach);
+}
+
+// One (mine i, partner j) capsule pair: true if they press on each other; then pm = my axis point relative to the reference
+// point, n = unit normal from the partner's axis point to mine, fmag = the explicit force along n on my body [N].  The link
+// spatial velocities are at 12 i + 6..11 of the published geometry.
+template <int KS, typename T, typename Model>
+B200_HD bool capsule_pair(const Model& m, int side, int i, int j, const T* G, const T* Gp, T* pm, T* n, T& fmag) {
+    const T rsum = ((i == 0) ? m.cyl_radius[1] : m.foot_cap_radius) + ((j == 0) ? m.cyl_radius[1] : m.foot_cap_radius);
+    const T ks = m.self_k, cs = m.self_c, dn = cs + m.dt * ks;
+    T pa[3], dm[3], pb[3], dother[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        pa[r] = G[(12 * i + r) * KS];
+        dm[r] = G[(12 * i + 3 + r) * KS] - pa[r];
+        pb[r] = Gp[(12 * j + r) * KS];
+        dother[r] = Gp[(12 * j + 3 + r) * KS] - pb[r];
+    }
+    // always evaluate (left segment, right segment) so that both lanes of an env pick the same closest points
+    T sl, sr;
+    if (side == 0) segment_closest(pa, dm, pb, dother, sl, sr);
+    else segment_closest(pb, dother, pa, dm, sl, sr);
+    const T um = (side == 0) ? sl : sr, uo = (side == 0) ? sr : sl;
+    T po[3], d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        pm[r] = pa[r] + um * dm[r];
+        po[r] = pb[r] + uo * dother[r];
+        d[r] = pm[r] - po[r];
+    }
+    const T d2 = dot3(d, d);
+    const bool touching = (d2 < rsum * rsum) && (d2 > T(1e-12));
+    const T dist = b_sqrt(b_max(d2, T(1e-12)));
+    const T depth = rsum - dist;
+    const T inv = b_div(T(1), dist);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) n[r] = d[r] * inv;
+    // relative velocity of the two axis points (rigid-body velocity v + w x p of each link)
+    T wm[3], wo[3], t1[3], t2[3], vr[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { wm[r] = G[(12 * i + 6 + r) * KS]; wo[r] = Gp[(12 * j + 6 + r) * KS]; }
+    cross3(wm, pm, t1);
+    cross3(wo, po, t2);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) vr[r] = (G[(12 * i + 9 + r) * KS] + t1[r]) - (Gp[(12 * j + 9 + r) * KS] + t2[r]);
+    const T vn = dot3(vr, n);
+    fmag = ks * depth - dn * vn;
+    return touching && (ks * depth - cs * vn > 0);
+}
+// fold an active pair into (K, Wn, Wf):  K += dt dn r r^T with r = [pm x n ; n]  (normal velocity of my axis point = r . [w; v])
+template <int KS, typename T, typename Model>
+B200_HD void capsule_pair_apply(const Model& m, const T* pm, const T* n, T fmag, T* K, T* Wn, T* Wf) {
+    const T Fe[3] = {fmag * n[0], fmag * n[1], fmag * n[2]};
+    T pxF[3], pxn[3];
+    cross3(pm, Fe, pxF);
+    cross3(pm, n, pxn);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { Wn[r] += pxF[r]; Wf[r] += Fe[r]; }
+    const T rr[6] = {pxn[0], pxn[1], pxn[2], n[0], n[1], n[2]};
+    const T D = m.dt * (m.self_c + m.dt * m.self_k);
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) K[(a * (a + 1) / 2 + b) * KS] += D * rr[a] * rr[b];
+}
+
+// What the tick calls when a cull fails.  `what`: bit 0 trunk box, 1 hip-yaw cylinder, 2 shank cylinder (all against the
+// ground).  Kx = this lane's scratch, Kp = the partner leg lane's (same env).  Returns a mask: bit j =
+// slot j holds an active contact.
+template <int KS, typename T, typename Model, typename Terr>
+B200_COLD int shapes_eval(const Model& m, int side, int what, const Terr terr, T* Kx, const T* Kp) {
+    ShapeAcc<T> acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        acc[j].init = false; acc[j].active = false;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { acc[j].Wn[r] = 0; acc[j].Wf[r] = 0; }
+    }
+    const T* G = Kx + B200_KX_GEOM * KS;
+    T pos[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) pos[r] = G[(46 + r) * KS];
+    if (what & 1) {
+        T R0[3][3], w[3], v[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R0[r][c] = G[(37 + 3 * r + c) * KS];
+            w[r] = G[(49 + r) * KS]; v[r] = G[(52 + r) * KS];
+        }
+        trunk_ground<KS>(m, side, R0, pos, w, v, terr, Kx, acc[0]);
+    }
+    if (what & 2) {
+        T c[3], a[3], w[3], v[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { c[r] = G[(24 + r) * KS]; a[r] = G[(27 + r) * KS]; w[r] = G[(30 + r) * KS]; v[r] = G[(33 + r) * KS]; }
+        cylinder_ground<KS>(m, 0, c, a, pos, w, v, terr, Kx + B200_KX_SLOT * KS, acc[1]);
+    }
+    if (what & 4) {
+        T c[3], a[3], w[3], v[3];
+        const T ih = T(0.5) / m.cyl_half[1];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const T p0 = G[r * KS], p1 = G[(3 + r) * KS];
+            c[r] = T(0.5) * (p0 + p1); a[r] = (p0 - p1) * ih;
+            w[r] = G[(6 + r) * KS]; v[r] = G[(9 + r) * KS];
+        }
+        cylinder_ground<KS>(m, 1, c, a, pos, w, v, terr, Kx + B200_KX_SLOT * 2 * KS, acc[2]);
+    }
+    int mask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (acc[j].active) {
+            mask |= 1 << j;
+            T* K = Kx + B200_KX_SLOT * j * KS;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { K[(21 + r) * KS] = acc[j].Wn[r]; K[(24 + r) * KS] = acc[j].Wf[r]; }
+        }
+    }
+    return mask;
 }
 
 // ---- leg-parallel formulation ------------------------------------------------------------------------------------
@@ -308,17 +466,72 @@ template <typename T> struct LegWork {
     T foot_fn;     // explicit normal-force estimate of this foot [N]
     T body_f2[3];  // |contact force|^2 on this leg's hip-yaw link, shank and foot (net_contact_force rows, envs/t1.py:553,628)
     T trunk_f[3];  // this lane's share of the contact force on the trunk (the pair adds the two shares)
-    T clearance;   // lowest point of this lane's rarely touching shapes above the highest terrain sample [m]
     T foot_pos[3]; // foot link origin, world
     T Rf[3][3];    // foot rotation
 };
 B200_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// Kinematics of the trunk and of this leg's links 0..3 (positions, frames, velocities - the same recurrences as the forward
-// pass of t1_leg_phase1) and the contacts of the shapes they carry.  Returns a mask: bit j = slot j holds an active contact.
-// `s` is taken BY VALUE-COPY on the device side of the call (the caller copies its registers into a temporary).
-template <int KS, typename T, typename Model, typename Terr>
-B200_COLD int shapes_prepass(const Model& m, const LegState<T>& s, int side, const Terr terr, T* Kx) {
+// ---- what the forward pass publishes for the shapes (also used by the host wrapper to pre-fill the partner leg) ----------------
+// Each returns the quantity its cull needs.  R, x, w, v: frame / origin (relative to the trunk origin) / spatial velocity of
+// the link; R0 = trunk frame.
+// hip-yaw (ci = 0) or shank (ci = 1) cylinder: height of its lowest point above the trunk origin's height
+template <typename T, typename Model> B200_HD T cylinder_low(const Model& m, int ci, const T R[3][3], const T* x) {
+    const T* cp = m.cyl_pos[ci];
+    const T cz = x[2] + R[2][0] * cp[0] + R[2][1] * cp[1] + R[2][2] * cp[2];
+    const T az = R[2][2];
+    return cz - (m.cyl_half[ci] * b_abs(az) + m.cyl_radius[ci] * b_sqrt(b_max(T(1) - az * az, T(0))));
+}
+template <int KS, typename T, typename Model>
+B200_HD void publish_hipyaw(const Model& m, const T R[3][3], const T* x, const T* w, const T* v, T* G) {
+    const T* cp = m.cyl_pos[0];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        G[(24 + r) * KS] = x[r] + R[r][0] * cp[0] + R[r][1] * cp[1] + R[r][2] * cp[2];
+        G[(27 + r) * KS] = R[r][2];
+        G[(30 + r) * KS] = w[r];
+        G[(33 + r) * KS] = v[r];
+    }
+}
+// shank capsule: returns `inward` = how far it stays on its own side of the trunk's sagittal plane; the legs can touch only
+// if inward(left leg) + inward(right leg) <= 0
+template <int KS, typename T, typename Model>
+B200_HD T publish_shank(const Model& m, const T R[3][3], const T* x, const T* w, const T* v, const T R0[3][3], int side, T* G) {
+    const T* cp = m.cyl_pos[1];
+    const T h = m.cyl_half[1];
+    T yc = 0, ya = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const T c = x[r] + R[r][0] * cp[0] + R[r][1] * cp[1] + R[r][2] * cp[2];
+        G[r * KS] = c + h * R[r][2];
+        G[(3 + r) * KS] = c - h * R[r][2];
+        G[(6 + r) * KS] = w[r];
+        G[(9 + r) * KS] = v[r];
+        yc += c * R0[r][1];
+        ya += R[r][2] * R0[r][1];
+    }
+    return (side == 0 ? yc : -yc) - h * b_abs(ya) - m.cyl_radius[1];
+}
+template <int KS, typename T, typename Model>
+B200_HD T publish_foot(const Model& m, const T R[3][3], const T* x, const T* w, const T* v, const T R0[3][3], int side, T* G) {
+    T y0 = 0, y1 = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const T p0 = x[r] + R[r][0] * m.foot_cap[0][0] + R[r][1] * m.foot_cap[0][1] + R[r][2] * m.foot_cap[0][2];
+        const T p1 = x[r] + R[r][0] * m.foot_cap[1][0] + R[r][1] * m.foot_cap[1][1] + R[r][2] * m.foot_cap[1][2];
+        G[(12 + r) * KS] = p0;
+        G[(15 + r) * KS] = p1;
+        G[(18 + r) * KS] = w[r];
+        G[(21 + r) * KS] = v[r];
+        y0 += p0 * R0[r][1];
+        y1 += p1 * R0[r][1];
+    }
+    if (side != 0) { y0 = -y0; y1 = -y1; }
+    return (y0 < y1 ? y0 : y1) - m.foot_cap_radius;
+}
+
+// Host wrapper only: publish a leg's geometry from its state (the device publishes from inside the forward pass; the host
+// runs the two legs one after the other, so the partner's geometry must exist before the first leg's tick).
+template <typename T, typename Model> B200_HD void leg_geom_publish(const Model& m, const LegState<T>& s, int side, T* G) {
     T quat[4];
     {
         const T n = b_sqrt(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
@@ -326,49 +539,46 @@ B200_COLD int shapes_prepass(const Model& m, const LegState<T>& s, int side, con
 #pragma unroll
         for (int i = 0; i < 4; ++i) quat[i] = s.quat[i] * inv;
     }
-    ShapeFrame<T> g;
-    quat_to_mat(quat, g.R);
-    T R0[3][3];
+    T R0[3][3], R[3][3], xp[3] = {0, 0, 0}, w[3], v[3];
+    quat_to_mat(quat, R0);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) R0[r][c] = g.R[r][c];
-        g.x[r] = 0; g.pos[r] = s.pos[r];
-        g.w[r] = R0[r][0] * s.wb[0] + R0[r][1] * s.wb[1] + R0[r][2] * s.wb[2];
-        g.v[r] = s.vlin[r];
+        for (int c = 0; c < 3; ++c) R[r][c] = R0[r][c];
+        w[r] = R0[r][0] * s.wb[0] + R0[r][1] * s.wb[1] + R0[r][2] * s.wb[2];
+        v[r] = s.vlin[r];
     }
-    int mask = 0;
-    if (trunk_ground<KS>(m, side, g, terr, Kx)) mask |= 1;
+    T inward = T(1e30);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 6; ++k) {
         const int b = 1 + 6 * side + k;
-        const int axis = (k == 0 || k == 3) ? 1 : (k == 2 ? 2 : 0);  // y x z y
+        const int axis = (k == 0 || k == 3 || k == 4) ? 1 : (k == 2 ? 2 : 0);
         const T* off = m.body_pos[b];
         T x[3], a[3], sl[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            x[r] = g.x[r] + g.R[r][0] * off[0] + g.R[r][1] * off[1] + g.R[r][2] * off[2];
-            a[r] = g.R[r][axis];
+            x[r] = xp[r] + R[r][0] * off[0] + R[r][1] * off[1] + R[r][2] * off[2];
+            a[r] = R[r][axis];
         }
-        rotate_about_axis(g.R, axis, s.q[k]);
+        rotate_about_axis(R, axis, s.q[k]);
         cross3(x, a, sl);
         const T qd = s.qd[k];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            g.w[r] += qd * a[r];
-            g.v[r] += qd * sl[r];
-            g.x[r] = x[r];
+        for (int r = 0; r < 3; ++r) { w[r] += qd * a[r]; v[r] += qd * sl[r]; xp[r] = x[r]; }
+        if (k == 2) publish_hipyaw<1>(m, R, x, w, v, G);
+        if (k == 3) inward = publish_shank<1>(m, R, x, w, v, R0, side, G);
+        if (k == 5) {
+            const T lo = publish_foot<1>(m, R, x, w, v, R0, side, G);
+            inward = lo < inward ? lo : inward;
         }
-        if (k >= 2 && cylinder_ground<KS>(m, k - 2, g, terr, Kx + B200_KX_SLOT * (k - 1) * KS)) mask |= 1 << (k - 1);
     }
-    return mask;
+    G[36] = inward;
 }
 
-// Kx: the shape scratch described above (B200_KX_SIZE entries, stride KS); shape_mask: what shapes_prepass() returned for this
-// lane (0 when it was skipped because the previous tick left every shape clear of the ground by a margin, W.clearance).
+// Kx: the shape scratch described above (B200_KX_SIZE entries, stride KS) of this leg lane; Kp: the partner leg lane's.
 template <typename T, int KS = 1, typename Model, typename Terr>
 B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>& s, int side, const T* tau /*6*/, const T* push_f,
-                           const T* push_t, const Terr& terr, LegWork<T>& W, T* Kx, int shape_mask) {
+                           const T* push_t, const Terr& terr, LegWork<T>& W, T* Kx, const T* Kp) {
     const T dt = m.dt;
     {
         const T n = b_sqrt(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
@@ -427,24 +637,18 @@ B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>&
 #pragma unroll
     for (int r = 0; r < 3; ++r) W.trunk_f[r] = 0;
     W.body_f2[0] = 0; W.body_f2[1] = 0; W.body_f2[2] = 0;
-    T clearance = T(1e30);   // lowest point of the trunk box / hip-yaw / shank cylinders above the highest terrain sample
+    // culls of the rarely touching shapes (evaluated after the forward pass): bit 0 trunk box, 1 hip-yaw cylinder, 2 shank
+    // cylinder reach down to the highest terrain sample, bit 3 the legs are not separated by the trunk's sagittal plane
+    int shape_what = 0;
+    T inward = T(1e30);
+    T* G = Kx + B200_KX_GEOM * KS;
     if (m.enable_body_contact) {
         // lowest of the 4 box corners on this lane's side: centre_z - |R0[2][0]| hx - |R0[2][2]| hz with the y offset signed
         const T* bp = m.trunk_box_pos;
         const T* bh = m.trunk_box_half;
         const T ly = bp[1] + (side == 0 ? bh[1] : -bh[1]);
         const T low = s.pos[2] + R0[2][0] * bp[0] + R0[2][1] * ly + R0[2][2] * bp[2] - (b_abs(R0[2][0]) * bh[0] + b_abs(R0[2][2]) * bh[2]);
-        clearance = low - (T)terr.max_height;
-        if (shape_mask & 1) {
-            act_trunk = true;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                f0n[r] -= Kx[(21 + r) * KS];
-                const T f = Kx[(24 + r) * KS];
-                f0f[r] -= f;
-                W.trunk_f[r] = f;
-            }
-        }
+        if (!(low > (T)terr.max_height)) shape_what |= 1;
     }
 
     // --- leg: forward pass (kinematics, inertias, bias wrenches) ------------------------------------------------------
@@ -501,30 +705,106 @@ B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>&
             xp[r] = x[r]; wp[r] = w[r]; vp[r] = v[r]; alp[r] = al[r]; avp[r] = av[r];
         }
         // hip-yaw (k = 2) and shank (k = 3) collision cylinders against the ground (resources/T1/T1_locomotion.xml:66,71)
-        if ((k == 2 || k == 3) && m.enable_body_contact) {
-            // lowest point of the cylinder (axis a = R[:,2]): centre_z - half |a_z| - rad sqrt(1 - a_z^2)
-            const T* cp = m.cyl_pos[k - 2];
-            const T cz = x[2] + R[2][0] * cp[0] + R[2][1] * cp[1] + R[2][2] * cp[2];
-            const T az = R[2][2];
-            const T low = s.pos[2] + cz - (m.cyl_half[k - 2] * b_abs(az) + m.cyl_radius[k - 2] * b_sqrt(b_max(T(1) - az * az, T(0))));
-            const T cl = low - (T)terr.max_height;
-            clearance = cl < clearance ? cl : clearance;
-            if (shape_mask & (1 << (k - 1))) {
-                act_cyl[k - 2] = true;
-                const T* K = Kx + B200_KX_SLOT * (k - 1) * KS;
+        // publish what the rarely touching shapes need (shape scratch) and evaluate their culls
+        if (k == 2 && m.enable_body_contact) {
+            publish_hipyaw<KS>(m, R, x, w, v, G);
+            if (!(s.pos[2] + cylinder_low(m, 0, R, x) > (T)terr.max_height)) shape_what |= 2;
+        }
+        if (k == 3 && (m.enable_body_contact | m.enable_self_contact)) {
+            inward = publish_shank<KS>(m, R, x, w, v, R0, side, G);
+            if (m.enable_body_contact && !(s.pos[2] + cylinder_low(m, 1, R, x) > (T)terr.max_height)) shape_what |= 4;
+        }
+        if (k == 5 && m.enable_self_contact) {
+            const T lo = publish_foot<KS>(m, R, x, w, v, R0, side, G);
+            inward = lo < inward ? lo : inward;
+        }
+    }
+    // --- rarely touching shapes: out-of-line evaluation when a cull failed, then fold the slots in ----------------------------
+    int shape_mask = 0;
+    bool legs_close = false;   // the two legs are NOT separated by the trunk's sagittal plane: only then can capsules touch
+    if (m.enable_body_contact | m.enable_self_contact) {
+        if (m.enable_self_contact) {
+            G[36 * KS] = inward;
+            B200_SYNCWARP();   // the partner lane's geometry (published above) and its `inward` are visible from here on
+            legs_close = !(inward + Kp[(B200_KX_GEOM + 36) * KS] > 0);
+        }
+        if (shape_what) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) G[(37 + 3 * r + c) * KS] = R0[r][c];
+                G[(46 + r) * KS] = s.pos[r];
+                G[(49 + r) * KS] = w0[r];
+                G[(52 + r) * KS] = v0[r];
+            }
+            shape_mask = shapes_eval<KS>(m, side, shape_what, terr, Kx, Kp);
+        }
+    }
+    if (shape_mask & 1) {
+        act_trunk = true;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            f0n[r] -= Kx[(21 + r) * KS];
+            const T f = Kx[(24 + r) * KS];
+            f0f[r] -= f;
+            W.trunk_f[r] = f;
+        }
+    }
+#pragma unroll
+    for (int k = 2; k <= 3; ++k) {
+        if (shape_mask & (1 << (k - 1))) {
+            act_cyl[k - 2] = true;
+            const T* K = Kx + B200_KX_SLOT * (k - 1) * KS;
+            T f2 = 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                fn[k][r] -= K[(21 + r) * KS];
+                const T f = K[(24 + r) * KS];
+                ff[k][r] -= f;
+                f2 += f * f;
+            }
+            W.body_f2[k - 2] = f2;
+        }
+    }
+    // --- leg-leg contacts of the shank capsule ------------------------------------------------------------------------------
+    // The same-type pairs (shank - shank, foot - foot) are evaluated on EVERY tick, branch-free and back to back: the kernel's
+    // time is its slowest warp's, some warp of a 4096-env rollout always holds a pair of touching legs, and a rarely taken
+    // block is fetched cold from L2 every time it runs (measured per 10-tick launch, standing / falling robots: behind the
+    // sagittal-plane cull 119 / 211 us, always-on 135 / 148 us; without leg-leg contacts 116 / 124 us).
+    // The cross pair (shank - partner's foot) needs crossed legs: behind the sagittal-plane and bounding-sphere culls.
+    bool foot_hit = false;
+    T foot_pm[3], foot_n[3], foot_fmag = 0;
+    if (m.enable_self_contact) {
+        const T* Gp = Kp + B200_KX_GEOM * KS;
+        T pm[3], n[3], fmag;
+        // both same-type pairs back to back (independent chains); the foot's result is consumed in the foot section
+        bool hit = capsule_pair<KS>(m, side, 0, 0, G, Gp, pm, n, fmag);
+        foot_hit = capsule_pair<KS>(m, side, 1, 1, G, Gp, foot_pm, foot_n, foot_fmag);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j == 1) hit = legs_close && capsule_spheres_touch<KS>(m, 0, 1, G, Gp) && capsule_pair<KS>(m, side, 0, 1, G, Gp, pm, n, fmag);
+            if (hit) {
+                T* K = Kx + B200_KX_SLOT * 2 * KS;
+                T Wn[3] = {0, 0, 0}, Wf[3] = {0, 0, 0};
+                if (!act_cyl[1]) {
+#pragma unroll
+                    for (int i = 0; i < B200_KX_SLOT; ++i) K[i * KS] = 0;
+                    act_cyl[1] = true;
+                }
+                capsule_pair_apply<KS>(m, pm, n, fmag, K, Wn, Wf);
                 T f2 = 0;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    fn[k][r] -= K[(21 + r) * KS];
-                    const T f = K[(24 + r) * KS];
-                    ff[k][r] -= f;
+                    fn[3][r] -= Wn[r];
+                    ff[3][r] -= Wf[r];
+                    const T f = K[(24 + r) * KS] + Wf[r];   // net contact force on the shank so far (slot entry 24..26)
+                    K[(24 + r) * KS] = f;
                     f2 += f * f;
                 }
-                W.body_f2[k - 2] = f2;
+                W.body_f2[1] = f2;
             }
         }
     }
-    W.clearance = clearance;
     // --- foot contact: 4 sole corners against the heightfield --------------------------------------------------------
     T Kc[21];  // implicit contact matrix of this foot (6x6 symmetric, lower-tri, order [ang; lin]), already * dt
 #pragma unroll
@@ -551,6 +831,18 @@ B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>&
             const T depth = ground - (s.pos[2] + p[2]);
             if (depth > 0 && contact_ground_point<1>(p, depth, wp, vp, kn, cn, dn, par.mu, dt, m.stiction_vel, Kc, Wn, Wf, W.foot_fn))
                 foot_active = true;
+        }
+        if (m.enable_self_contact) {   // foot - foot capsule pair on every tick, foot - partner's shank behind the culls (see above)
+            const T* Gp = Kp + B200_KX_GEOM * KS;
+            T pm[3], n[3], fmag;
+            if (foot_hit) {
+                capsule_pair_apply<1>(m, foot_pm, foot_n, foot_fmag, Kc, Wn, Wf);
+                foot_active = true;
+            }
+            if (legs_close && capsule_spheres_touch<KS>(m, 1, 0, G, Gp) && capsule_pair<KS>(m, side, 1, 0, G, Gp, pm, n, fmag)) {
+                capsule_pair_apply<1>(m, pm, n, fmag, Kc, Wn, Wf);
+                foot_active = true;
+            }
         }
         W.body_f2[2] = Wf[0] * Wf[0] + Wf[1] * Wf[1] + Wf[2] * Wf[2];
         if (foot_active) {
@@ -842,12 +1134,13 @@ B200_HD void t1_tick(const Model& m, const DynParams<T>& par, DynState<T>& s, co
     LegState<T> ls[2];
     LegParams<T> lp[2];
     LegWork<T> W[2];
-    T Kx[B200_KX_SIZE];
+    T Kx[2][B200_KX_SIZE];
     for (int side = 0; side < 2; ++side) {
         leg_split(s, par, side, ls[side], lp[side]);
-        const int mask = m.enable_body_contact ? shapes_prepass<1, T>(m, ls[side], side, terr, Kx) : 0;
-        t1_leg_phase1<T>(m, lp[side], ls[side], side, tau + 6 * side, push_f, push_t, terr, W[side], Kx, mask);
+        leg_geom_publish(m, ls[side], side, Kx[side] + B200_KX_GEOM);   // the device publishes from inside the forward pass
     }
+    for (int side = 0; side < 2; ++side)
+        t1_leg_phase1<T>(m, lp[side], ls[side], side, tau + 6 * side, push_f, push_t, terr, W[side], Kx[side], Kx[1 - side]);
     for (int i = 0; i < 21; ++i) { const T t = W[0].Mbb[i] + W[1].Mbb[i]; W[0].Mbb[i] = t; W[1].Mbb[i] = t; }
     for (int i = 0; i < 6; ++i) { const T t = W[0].rb[i] + W[1].rb[i]; W[0].rb[i] = t; W[1].rb[i] = t; }
     for (int side = 0; side < 2; ++side) {

@@ -135,7 +135,6 @@ B200_HD float raw_rand(const B200Rand& r, float u, float nrm) { return (r.dist =
 // unclipped) or raw torques if !apply_pd.  Lanes whose env index is out of range compute on a clamped index and store
 // nothing (they must still take part in the shuffles).
 #if defined(__CUDACC__)
-#define B200_SHAPE_MARGIN 0.03f
 template <typename T> __device__ __forceinline__ T pair_sum(T x) { return x + __shfl_xor_sync(0xffffffffu, x, 1); }
 
 template <typename Model>
@@ -200,13 +199,10 @@ __device__ __forceinline__ void env_physics_pair(const EnvView& v, int e, bool v
 #pragma unroll
     for (int r = 0; r < 3; ++r) { W.trunk_f[r] = 0.0f; W.body_f2[r] = 0.0f; }
     float qb[6], ql[6];
-    // per-thread slices of shared memory for the contact matrices of the rarely touching shapes (t1_leg_phase1)
+    // per-thread slices of shared memory: geometry and contact matrices of the rarely touching shapes (t1_dynamics.cuh)
     __shared__ float kx_scratch[B200_KX_SIZE * PHYS_BLOCK];
     float* Kx = kx_scratch + threadIdx.x;
-    // The first tick of a call always evaluates the shapes (the state may have been written from outside); afterwards a
-    // shape can come within reach only by crossing the margin: 3 cm = 15 m/s x one tick, and an env whose squared root
-    // velocity exceeds terminate_vel (50) is reset (envs/t1.py:554).
-    bool near_ground = m.enable_body_contact != 0;
+    const float* Kp = kx_scratch + (threadIdx.x ^ 1);   // the partner leg lane's slice (leg-leg contacts)
     for (int i = 0; i < n_substeps; ++i) {
         float tau[6];
 #pragma unroll
@@ -222,15 +218,7 @@ __device__ __forceinline__ void env_physics_pair(const EnvView& v, int e, bool v
                 tau[k] = target[k];
             }
         }
-        // trunk box / leg cylinders: evaluated out of line, and only while one of them is within a margin of the
-        // ground (W.clearance of the previous tick; t1_dynamics.cuh "rarely touching shapes")
-        int shape_mask = 0;
-        if (near_ground) {
-            const LegState<float> tmp = s;
-            shape_mask = shapes_prepass<PHYS_BLOCK, float>(m, tmp, side, terr, Kx);
-        }
-        t1_leg_phase1<float, PHYS_BLOCK>(m, par, s, side, tau, push_f, push_t, terr, W, Kx, shape_mask);
-        near_ground = W.clearance < B200_SHAPE_MARGIN;
+        t1_leg_phase1<float, PHYS_BLOCK>(m, par, s, side, tau, push_f, push_t, terr, W, Kx, Kp);
 #pragma unroll
         for (int q = 0; q < 21; ++q) W.Mbb[q] = pair_sum(W.Mbb[q]);
 #pragma unroll

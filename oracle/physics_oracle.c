@@ -326,6 +326,67 @@ int t1o_tick_f(const B200T1ModelD* m, T1OEnv* e, const double* tau, const double
                 }
             }
     }
+    /* leg-leg contacts (asset.self_collisions: 0 = enabled, envs/T1.yaml:69): shank cylinders and foot boxes as capsules.
+     * Every (left, right) pair closer than the sum of the radii is pushed apart along the line between the closest axis points:
+     * spring on the overlap, damper on the relative normal velocity; linearly implicit per body (block-diagonal: the
+     * partner's velocity change is not anticipated - DESIGN.md "contact"). */
+    if (m->enable_self_contact) {
+        double P[2][2][2][3]; /* [leg][capsule 0 shank / 1 foot][end][xyz], world */
+        for (int sd = 0; sd < 2; ++sd) {
+            int bs = 1 + 6 * sd + 3, bf = 1 + 6 * sd + 5;
+            for (int e2 = 0; e2 < 2; ++e2) {
+                double l[3] = {m->cyl_pos[1][0], m->cyl_pos[1][1], m->cyl_pos[1][2] + (e2 ? -1.0 : 1.0) * m->cyl_half[1]}, rp[3];
+                matvec(k.R[bs], l, rp);
+                for (int r = 0; r < 3; ++r) P[sd][0][e2][r] = k.x[bs][r] + rp[r];
+                matvec(k.R[bf], m->foot_cap[e2], rp);
+                for (int r = 0; r < 3; ++r) P[sd][1][e2][r] = k.x[bf][r] + rp[r];
+            }
+        }
+        const double ks = m->self_k, cs = m->self_c, dns = cs + dt * ks;
+        for (int i = 0; i < 2; ++i)       /* capsule of the left leg */
+            for (int j = 0; j < 2; ++j) { /* capsule of the right leg */
+                int bl = 1 + (i ? 5 : 3), br = 7 + (j ? 5 : 3);
+                double d1[3], d2[3], rr[3];
+                for (int r = 0; r < 3; ++r) {
+                    d1[r] = P[0][i][1][r] - P[0][i][0][r];
+                    d2[r] = P[1][j][1][r] - P[1][j][0][r];
+                    rr[r] = P[0][i][0][r] - P[1][j][0][r];
+                }
+                double a = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], ee = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
+                double f = d2[0] * rr[0] + d2[1] * rr[1] + d2[2] * rr[2], c = d1[0] * rr[0] + d1[1] * rr[1] + d1[2] * rr[2];
+                double b = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2], den = a * ee - b * b, sp, tp;
+                sp = (den > 1e-12 * a * ee) ? fmin(1.0, fmax(0.0, (b * f - c * ee) / den)) : 0.0;
+                tp = (b * sp + f) / ee;
+                if (tp < 0) { tp = 0; sp = fmin(1.0, fmax(0.0, -c / a)); }
+                else if (tp > 1) { tp = 1; sp = fmin(1.0, fmax(0.0, (b - c) / a)); }
+                double pl[3], pr[3], dd[3];
+                for (int r = 0; r < 3; ++r) {
+                    pl[r] = P[0][i][0][r] + sp * d1[r];
+                    pr[r] = P[1][j][0][r] + tp * d2[r];
+                    dd[r] = pl[r] - pr[r];
+                }
+                double dist = sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+                double rsum = (i ? m->foot_cap_radius : m->cyl_radius[1]) + (j ? m->foot_cap_radius : m->cyl_radius[1]);
+                double depth = rsum - dist;
+                if (depth <= 0 || dist <= 1e-6) continue;
+                double n[3] = {dd[0] / dist, dd[1] / dist, dd[2] / dist}; /* from the right capsule towards the left one */
+                double JvL[3][NV], JwL[3][NV], JvR[3][NV], JwR[3][NV], gl[NV], gr[NV], vn = 0;
+                jacobian(&k, bl, pl, JvL, JwL);
+                jacobian(&k, br, pr, JvR, JwR);
+                for (int q = 0; q < NV; ++q) {
+                    gl[q] = n[0] * JvL[0][q] + n[1] * JvL[1][q] + n[2] * JvL[2][q];
+                    gr[q] = n[0] * JvR[0][q] + n[1] * JvR[1][q] + n[2] * JvR[2][q];
+                    vn += (gl[q] - gr[q]) * qvel[q];
+                }
+                if (ks * depth - cs * vn <= 0) continue;
+                double fmag = ks * depth - dns * vn;
+                for (int q = 0; q < NV; ++q) {
+                    rhs[q] += (gl[q] - gr[q]) * fmag;
+                    for (int q2 = 0; q2 < NV; ++q2) M[q][q2] += dt * dns * (gl[q] * gl[q2] + gr[q] * gr[q2]);
+                }
+                for (int r = 0; r < 3; ++r) { body_f[3 * bl + r] += fmag * n[r]; body_f[3 * br + r] -= fmag * n[r]; }
+            }
+    }
     if (m->enable_limits) {
         for (int j = 0; j < 12; ++j) {
             double viol = 0;

@@ -185,6 +185,46 @@ def test_body_contacts_against_fp64_oracle(t1_cfg):
     assert hits[0] > 10 and min(hits[3], hits[4], hits[9], hits[10]) > 5
 
 
+def test_leg_leg_contacts_against_fp64_oracle(t1_cfg):
+    """leg-leg capsule contacts (asset.self_collisions: 0) with the two leg lanes of an env exchanging their capsule
+    axes by shuffle: one tick on legs rolled into each other, qacc within 2e-3 * max(1, |qacc|_inf) of the FP64 oracle and
+    the shank / foot contact flags equal to the oracle's; 10 more ticks keep every env finite."""
+    from oracle import physics as op
+
+    n = 96
+    env = make_env(t1_cfg, n)
+    g = randomize_state(env, 31, True)
+    q = env.default_dof_pos.cpu().repeat(n, 1) + (torch.rand(n, 12, generator=g) - 0.5) * 0.6
+    q[:, 1] = -0.35 * torch.rand(n, generator=g)
+    q[:, 7] = 0.35 * torch.rand(n, generator=g)
+    q[:, 2] = torch.rand(n, generator=g) - 0.5
+    q[:, 8] = torch.rand(n, generator=g) - 0.5
+    env.dof_pos.copy_(q.cuda())
+    tau = torch.randn(n, 12, generator=g) * 10.0
+    md, oenvs = oracle_envs(env, range(n))
+    qacc = torch.zeros(18, n, device="cuda")
+    env.physics(tau.cuda(), 1, apply_pd=False, qacc_out=qacc)
+    torch.cuda.synchronize()
+    qa = qacc.cpu().double().numpy()
+    mask = env._iview("contact_mask").cpu().numpy()
+    mask = mask[:, 0] | mask[:, 1]
+    worst, n_self = 0.0, 0
+    for e in range(n):
+        st, ref, fn, bf = op.tick_f(md, oenvs[e], tau[e].double().numpy(), integrate=False)
+        assert st == 0
+        worst = max(worst, np.abs(qa[:, e] - ref).max() / max(1.0, np.abs(ref).max()))
+        fnorm = np.linalg.norm(bf, axis=1)
+        n_self += int(fnorm[[4, 6, 10, 12]].max() > 1.0)
+        for b in (4, 6, 10, 12):
+            if abs(fnorm[b] - 1.0) > 0.05:
+                assert bool((mask[e] >> b) & 1) == bool(fnorm[b] > 1.0), (e, b, fnorm[b])
+    print("worst relative qacc error", worst, "envs with leg-leg contact", n_self)
+    assert worst < 2e-3 and n_self > 20
+    env.physics(tau.cuda(), 10, apply_pd=False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(env.root_states).all() and torch.isfinite(env.dof_pos).all()
+
+
 def test_free_fall_and_momentum(t1_cfg):
     """physical invariants (SURVEY 8c ii): zero-torque free fall has base qacc (0,0,-g); feet FK matches the oracle"""
     from oracle import physics as op

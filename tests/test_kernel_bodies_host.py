@@ -231,6 +231,67 @@ def test_fallen_robot_rests_on_its_body():
             tau = 50 * (q0 - np.array(e.q[:])) - 1.0 * np.array(e.qd[:])
             st, _, _, bf = op.tick_f(md, e, tau)
             assert st == 0
-        assert np.linalg.norm(e.vlin[:]) < 5e-3 and e.pos[2] > 0.0
+        assert np.linalg.norm(e.vlin[:]) < 2e-2 and e.pos[2] > 0.0   # (on its side it keeps rolling slowly)
         assert abs(bf[:, 2].sum() - 31.6144 * 9.81) < 0.02 * 31.6144 * 9.81
         assert np.linalg.norm(bf[[0, 3, 4, 9, 10]], axis=1).sum() > 200.0
+
+
+def test_leg_leg_contacts_match_fp64_oracle():
+    """leg-leg contacts (shank / foot capsules, asset.self_collisions: 0).  Kernel recursion (double; capsule pairs
+    evaluated per leg lane, implicit in the lane's own velocity) vs the dense-Jacobian oracle on legs rolled into each other:
+    qacc to 1e-10, per-body net contact forces to 1e-8, and the pair forces are equal and opposite."""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    md = robot.model_d()
+    md_off = robot.model_d(self_contact=False)
+    rng = np.random.default_rng(5)
+    q0 = np.array([-0.2, 0, 0, 0.4, -0.25, 0] * 2)
+    worst, n_self = 0.0, 0
+    for it in range(150):
+        airborne = it % 3 != 0
+        q = q0 + rng.uniform(-0.3, 0.3, 12)
+        q[1] = -rng.uniform(0.0, 0.35); q[7] = rng.uniform(0.0, 0.35)      # hip rolls inward
+        q[2] = rng.uniform(-0.5, 0.5); q[8] = rng.uniform(-0.5, 0.5)
+        e = op.make_env(md, pos=(0, 0, 1.5 if airborne else 0.62), vlin=rng.normal(size=3), wb=rng.normal(size=3), q=q, qd=rng.normal(size=12) * 3)
+        tau = rng.normal(size=12) * 10
+        st, qa_o, _, bf = op.tick_f(md, op.Env.from_buffer_copy(e), tau, integrate=False)
+        _, _, _, bf_off = op.tick_f(md_off, op.Env.from_buffer_copy(e), tau, integrate=False)
+        assert st == 0
+        hit = np.abs(bf - bf_off).max() > 1e-9
+        n_self += int(hit)
+        e2 = op.Env.from_buffer_copy(e)
+        qacc = (C.c_double * 18)(); fn = (C.c_double * 2)(); co = (C.c_double * 9)()
+        lib().hc_tick_d_contacts(C.byref(md), C.byref(e2), op._d(tau), op._d([0] * 3), op._d([0] * 3), None, 0, 0, 50, C.c_float(0.1),
+                                 C.c_double(0.005), qacc, fn, 0, co)
+        worst = max(worst, np.max(np.abs(qa_o - np.array(qacc))) / max(1.0, np.max(np.abs(qa_o))))
+        f2 = (bf ** 2).sum(axis=1)
+        assert np.allclose(np.array(co)[:6], f2[[3, 4, 6, 9, 10, 12]], rtol=1e-8, atol=1e-8)
+        if hit and airborne:
+            assert np.abs(bf.sum(axis=0)).max() < 1e-9    # internal forces only
+    assert worst < 1e-10 and n_self > 40
+
+
+def test_legs_do_not_pass_through_each_other():
+    """both hip rolls driven inwards on a floating robot: without leg-leg contacts the feet end up inside each other (centre
+    distance ~0); with them the foot capsules (radius 5 cm each) keep their axes about 10 cm apart"""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    q0 = np.array([-0.2, 0, 0, 0.4, -0.25, 0] * 2)
+    tgt = q0.copy(); tgt[1] = -0.3; tgt[7] = 0.3
+    kd = np.array([3, 3, 3, 3, 0.3, 0.3] * 2)
+    res = {}
+    for sc in (True, False):
+        md = robot.model_d(self_contact=sc, gravity=0.0)
+        e = op.make_env(md, pos=(0, 0, 2.0), q=q0)
+        mind = 1e9
+        for _ in range(1000):
+            tau = np.clip(50 * (tgt - np.array(e.q[:])) - kd * np.array(e.qd[:]), -30, 30)
+            st, _, _, bf = op.tick_f(md, e, tau)
+            assert st == 0
+            p, _ = op.feet(md, e)
+            mind = min(mind, np.linalg.norm(p[0] - p[1]))
+        res[sc] = (mind, np.linalg.norm(bf, axis=1))
+    assert res[False][0] < 0.03 and res[True][0] > 0.075
+    assert res[True][1][[6, 12]].min() > 10.0 and res[False][1].max() == 0.0
