@@ -5,7 +5,9 @@
 
 #include "../../include/b200_t1.h"
 
+#ifndef PHYS_BLOCK
 #define PHYS_BLOCK 32
+#endif
 
 namespace b200 {
 int set_error(int code, const char* msg);

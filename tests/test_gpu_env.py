@@ -147,17 +147,22 @@ def test_decimated_loop_against_fp64_oracle(t1_cfg):
     assert np.abs(env.last_dof_targets.cpu().double().numpy() - lt).max() < 1e-6
 
 
-def test_body_contacts_against_fp64_oracle(t1_cfg):
+@pytest.mark.parametrize("terrain", ["plane", "trimesh"])
+def test_body_contacts_against_fp64_oracle(t1_cfg, terrain):
     """trunk box / hip-yaw / shank cylinders against the ground on tumbling low robots.  One tick: qacc within
     2e-3 * max(1, |qacc|_inf) of the FP64 oracle (the foot-contact tolerance), and the per-body contact flags the env reads
     (|net contact force| > 1 N: collision reward envs/t1.py:627-629, termination :553) equal to the oracle's."""
     from oracle import physics as op
 
     n = 128
-    env = make_env(t1_cfg, n)
+    env = make_env(t1_cfg, n, terrain=terrain)
     g = randomize_state(env, 23, True)
     rs = env.root_states.clone()
-    rs[:, 2] = (0.05 + 0.45 * torch.rand(n, generator=g)).cuda()
+    if terrain == "trimesh":   # spread over the rough tiles; heights relative to the local ground (culls use a pooled local bound)
+        rs[:, 0] = (5.0 + 70.0 * torch.rand(n, generator=g)).cuda()
+        rs[:, 1] = (1.0 + 8.0 * torch.rand(n, generator=g)).cuda()
+    ground = env.terrain.terrain_heights(rs[:, 0:3].contiguous()) if terrain == "trimesh" else 0.0
+    rs[:, 2] = (0.05 + 0.45 * torch.rand(n, generator=g)).cuda() + ground
     q = torch.randn(n, 4, generator=g)
     rs[:, 3:7] = (q / q.norm(dim=1, keepdim=True)).cuda()
     env.root_states.copy_(rs)
@@ -171,8 +176,9 @@ def test_body_contacts_against_fp64_oracle(t1_cfg):
     mask = mask[:, 0] | mask[:, 1]
     worst = 0.0
     hits = np.zeros(13, int)
+    oterr = op.make_terrain(env.terrain.height_field_raw) if terrain == "trimesh" else None
     for e in range(n):
-        st, ref, fn, bf = op.tick_f(md, oenvs[e], tau[e].double().numpy(), integrate=False)
+        st, ref, fn, bf = op.tick_f(md, oenvs[e], tau[e].double().numpy(), terrain=oterr, integrate=False)
         assert st == 0
         worst = max(worst, np.abs(qa[:, e] - ref).max() / max(1.0, np.abs(ref).max()))
         fnorm = np.linalg.norm(bf, axis=1)
