@@ -1,7 +1,8 @@
 """Live (CUDA-event) timing of the rollout components through the public API: policy, physics x10, post-physics, full step.
 Note: timed in a Python loop, so each figure is max(GPU time, host issue cost) - see DESIGN.md (K4)."""
 import copy, os, sys, numpy as np, torch, yaml
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tools/ -> repo root; sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tools/ -> repo root
+sys.path.insert(0, ROOT)
 from booster_gym_b200.envs import T1
 from booster_gym_b200.learner import Learner
 from oracle import learner as L
