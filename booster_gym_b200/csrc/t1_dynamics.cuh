@@ -202,11 +202,11 @@ B200_HD bool contact_ground_point(const T* p, T depth, const T* w, const T* v, T
 // ---- the rarely touching shapes: trunk box, hip-yaw and shank cylinders, leg-leg capsules -----------------------
 // k_physics is one warp per CTA at 255 registers and streams its code from L2: shape code placed inline in the tick cost
 // 10 % even when it never ran.  So the tick only PUBLISHES the few frames the shapes need into a per-thread scratch (shared
-// memory on the device, stride KS = block size; a plain array with KS = 1 on the host), applies exact conservative culls
+// memory on the device, stride KS = block size; a plain array with KS = 1 on the host) and applies exact conservative culls
 // (lowest point of a shape above the highest terrain sample; the two legs on their own sides of the trunk's sagittal
-// plane), and when a cull fails calls shapes_eval() OUT OF LINE, which reads the scratch (its own and the partner leg
-// lane's) and leaves one slot per body:  slot j = 0 trunk share, 1 hip-yaw link, 2 shank, 3 foot (leg-leg contacts only; the
-// sole corners stay in the tick):
+// plane).  When a ground cull fails it calls shapes_eval() OUT OF LINE, which reads the scratch and leaves one slot per body
+// (slot j = 0 trunk share, 1 hip-yaw link, 2 shank); the leg-leg capsule pairs read the partner leg lane's scratch inline
+// (t1_leg_phase1); the shank's contributions of both kinds meet in slot 2, the foot's stay in registers:
 //   Kx[(27 j + i) KS], i < 21: implicit contact matrix (6x6 lower-tri, [ang; lin]);  i = 21..23: wrench moment about the
 //   reference point;  i = 24..26: net contact force.
 // Published geometry, at B200_KX_GEOM + :  0..5 shank capsule axis ends (+z, -z; relative to the trunk origin, world axes),
@@ -214,7 +214,7 @@ B200_HD bool contact_ground_point(const T* p, T depth, const T* w, const T* v, T
 // 24..26 hip-yaw cylinder centre, 27..29 its axis, 30..35 hip-yaw link spatial velocity, 36 `inward` (publish_shank);
 // 37..45 trunk rotation, 46..48 trunk position, 49..54 trunk spatial velocity (written only ahead of a trunk evaluation).
 #define B200_KX_SLOT 27
-#define B200_KX_GEOM (4 * B200_KX_SLOT)
+#define B200_KX_GEOM (3 * B200_KX_SLOT)
 #define B200_KX_SIZE (B200_KX_GEOM + 55)
 #if defined(__CUDA_ARCH__)
 #define B200_SYNCWARP() __syncwarp()
@@ -386,9 +386,9 @@ B200_HD void capsule_pair_apply(const Model& m, const T* pm, const T* n, T fmag,
 // slot j holds an active contact.
 template <int KS, typename T, typename Model, typename Terr>
 B200_COLD int shapes_eval(const Model& m, int side, int what, const Terr terr, T* Kx, const T* Kp) {
-    ShapeAcc<T> acc[4];
+    ShapeAcc<T> acc[3];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 3; ++j) {
         acc[j].init = false; acc[j].active = false;
 #pragma unroll
         for (int r = 0; r < 3; ++r) { acc[j].Wn[r] = 0; acc[j].Wf[r] = 0; }
@@ -426,7 +426,7 @@ B200_COLD int shapes_eval(const Model& m, int side, int what, const Terr terr, T
     }
     int mask = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 3; ++j) {
         if (acc[j].active) {
             mask |= 1 << j;
             T* K = Kx + B200_KX_SLOT * j * KS;
