@@ -192,17 +192,22 @@ class T1(BaseTask):
                    "b200_t1_reset")
         return self.obs_buf, self.extras
 
-    def step(self, actions, _device_counter=False):
+    def step(self, actions, _device_counter=False, _out=None):
+        """`_out` (not in the reference surface): (obs, privileged_obs, rew, done_u8) tensors the step writes INSTEAD of the env's own
+        obs_buf / privileged_obs_buf / rew_buf / reset_buf - the Runner passes the rows of its rollout storage, which removes four
+        copy kernels per step.  The returned tensors are then those; the env's own buffers keep their previous content."""
         a = actions
         if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.obs_buf.device:
             a = a.to(device=self.obs_buf.device, dtype=torch.float32).contiguous()
         self.common_step_counter += 1
-        _lib.check(self._lib.b200_t1_step(self._h, a.data_ptr(), self.obs_buf.data_ptr(), self.privileged_obs_buf.data_ptr(),
-                                          self.rew_buf.data_ptr(), self._done_u8.data_ptr(), self._time_outs_u8.data_ptr(),
-                                          self._rew_terms.data_ptr(), -1 if _device_counter else self.common_step_counter,
-                                          self._stream()), "b200_t1_step")
+        obs, priv, rew, done = (self.obs_buf, self.privileged_obs_buf, self.rew_buf, self._done_u8) if _out is None else _out
+        _lib.check(self._lib.b200_t1_step(self._h, a.data_ptr(), obs.data_ptr(), priv.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                          self._time_outs_u8.data_ptr(), self._rew_terms.data_ptr(),
+                                          -1 if _device_counter else self.common_step_counter, self._stream()), "b200_t1_step")
         self.render()
-        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+        if _out is None:
+            return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+        return obs, rew, done.view(torch.bool), {"rew_terms": self.extras["rew_terms"], "privileged_obs": priv, "time_outs": self.extras["time_outs"]}
 
     # ---- extras (not in the reference surface) ---------------------------------------------------------------------
     def physics(self, actions_or_torques, n_substeps, apply_pd=True, qacc_out=None):

@@ -181,17 +181,23 @@ class Runner:
 
     # ---- the loop ----------------------------------------------------------------------------------------------------
     def rollout(self, obs, privileged_obs):
-        """utils/runner.py:106-121: horizon_length x [store obs, act, env.step, store transition]"""
+        """utils/runner.py:106-121: horizon_length x [store obs, act, env.step, store transition].  The transition is stored by the
+        producing kernels themselves: the policy samples into the `actions` row, the env step writes reward / done into their rows
+        and the NEXT observation into row n + 1 (`T1.step(_out=...)`); only row 0 of the observations and the time-outs (whose tensor
+        is rebound only on steps with a reset, SURVEY 8a note 1) are copied.  The last step writes the env's own buffers, which
+        are what this returns - as the reference's loop does."""
         buf, env, lrn = self.buffer, self.env, self.learner
-        for n in range(self.cfg["runner"]["horizon_length"]):
-            buf.update_data("obses", n, obs)
-            buf.update_data("privileged_obses", n, privileged_obs)
+        horizon = self.cfg["runner"]["horizon_length"]
+        buf.update_data("obses", 0, obs)
+        buf.update_data("privileged_obses", 0, privileged_obs)
+        for n in range(horizon):
             act = buf["actions"][n]
             lrn.act(obs, act)                      # mu = actor(obs); act = mu + sigma * eps, written into the buffer row
-            obs, rew, done, infos = env.step(act, _device_counter=True)
+            last = n == horizon - 1
+            out = (env.obs_buf if last else buf["obses"][n + 1], env.privileged_obs_buf if last else buf["privileged_obses"][n + 1],
+                   buf["rewards"][n], buf.row("dones", n))
+            obs, rew, done, infos = env.step(act, _device_counter=True, _out=out)
             privileged_obs = infos["privileged_obs"]
-            buf.update_data("rewards", n, rew)
-            buf.update_data("dones", n, done)
             buf.update_data("time_outs", n, infos["time_outs"])
         return obs, privileged_obs
 

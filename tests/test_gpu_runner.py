@@ -61,3 +61,37 @@ def test_graph_replay_equals_eager_rollout(tmp_path):
             os.chdir(cwd)
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_rollout_storage_matches_the_reference_loop(tmp_path):
+    """Runner.rollout lets the kernels write the transition straight into the rollout storage (T1.step(_out=...)); the buffers must
+    equal those of the reference's own loop shape (utils/runner.py:106-121: copy obs, act, step into the env's buffers, copy the rest)."""
+    outs = []
+    for direct in (True, False):
+        runner, cwd = _runner(tmp_path)
+        try:
+            env, buf, lrn = runner.env, runner.buffer, runner.learner
+            obs, infos = env.reset()
+            priv = infos["privileged_obs"]
+            for _ in range(2):
+                if direct:
+                    obs, priv = runner.rollout(obs, priv)
+                else:
+                    for n in range(runner.cfg["runner"]["horizon_length"]):
+                        buf.update_data("obses", n, obs)
+                        buf.update_data("privileged_obses", n, priv)
+                        act = buf["actions"][n]
+                        lrn.act(obs, act)
+                        obs, rew, done, infos = env.step(act, _device_counter=True)
+                        priv = infos["privileged_obs"]
+                        buf.update_data("rewards", n, rew)
+                        buf.update_data("dones", n, done)
+                        buf.update_data("time_outs", n, infos["time_outs"])
+            torch.cuda.synchronize()
+            outs.append({k: buf[k].clone() for k in ("actions", "obses", "privileged_obses", "rewards", "dones", "time_outs")}
+                        | {"last_obs": obs.clone(), "last_priv": priv.clone()})
+        finally:
+            os.chdir(cwd)
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert outs[0]["dones"].any() and outs[0]["rewards"].abs().sum() > 0
