@@ -7,7 +7,9 @@
 // fp32 numbers small on an 80 m terrain), composite-rigid-body mass matrix, recursive Newton-Euler bias, sparse
 // L^T D L factorisation in leaf-to-root order (left/right leg blocks never couple), semi-implicit Euler with an
 // exact quaternion exponential.  Contact is NOT MuJoCo's convex solver: 8 sole corners against the heightfield with
-// a linearly-implicit spring-damper normal force and a lagged, regularised Coulomb friction (DESIGN.md "contact").
+// a linearly-implicit spring-damper normal force and a lagged, regularised Coulomb friction (DESIGN.md "contact"); the
+// same law for the trunk box corners and the hip-yaw / shank cylinder rims, and a frictionless variant between the two
+// legs' shank / foot capsules ("the rarely touching shapes" below).
 //
 // The code is a template over the scalar type and is __host__ __device__: the CUDA kernels instantiate it with
 // float; tests/ build it for the host (float and double) to check the algebra against oracle/ without a GPU.

@@ -23,7 +23,7 @@ extern "C" {
 #define B200_NV 18   /* 6 free-joint + 12 hinge DoF */
 #define B200_NQ 19
 #define B200_NU 12
-#define B200_NCON 8  /* sole-corner contact points, 4 per foot (envs/T1.yaml:79-82) */
+#define B200_NCON 8  /* sole-corner contact points, 4 per foot (envs/T1.yaml:79-82); the other collision shapes: model fields below */
 #define B200_NOBS 47
 #define B200_NPRIV 14
 #define B200_MAX_REW 26
