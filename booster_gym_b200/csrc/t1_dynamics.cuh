@@ -36,7 +36,20 @@ template <> struct ModelOf<double> { typedef B200T1ModelD type; };
 
 B200_HD void b_sincos(float x, float& s, float& c) {
 #if defined(__CUDA_ARCH__)
-    sincosf(x, &s, &c);
+    // The tick is instruction-fetch bound and calls this 7 times: CUDA's sincosf inlines ~150 instructions each (Payne-Hanek slow
+    // path included); joint angles are a few radians, so a 3-constant Cody-Waite reduction to [-pi/4, pi/4] (exact products
+    // for |k| < 2^13) + the cephes minimax polynomials do it in ~25 with |error| < 1e-7 (measured on 2e7 samples in [-8, 8]).
+    const float k = rintf(x * 0.636619772367581343f);
+    float r = fmaf(-k, 1.5703125f, x);
+    r = fmaf(-k, 4.837512969970703125e-4f, r);
+    r = fmaf(-k, 7.54978995489188216e-8f, r);
+    const float z = r * r;
+    const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, r, r);
+    const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z, fmaf(-0.5f, z, 1.0f));
+    const int q = (int)k;
+    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
 #else
     s = sinf(x); c = cosf(x);
 #endif
@@ -53,6 +66,14 @@ B200_HD float b_div(float a, float b) {
 #endif
 }
 B200_HD double b_div(double a, double b) { return a / b; }
+B200_HD float b_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+B200_HD double b_rsqrt(double x) { return 1.0 / sqrt(x); }
 B200_HD float b_abs(float x) { return fabsf(x); }
 B200_HD double b_abs(double x) { return fabs(x); }
 B200_HD float b_max(float a, float b) { return fmaxf(a, b); }
@@ -173,8 +194,8 @@ B200_HD bool contact_ground_point(const T* p, T depth, const T* w, const T* v, T
     const T fn0 = kn * depth - cn * vc[2];
     if (!(fn0 > 0)) return false;
     fn_sum += fn0;
-    const T vt = b_sqrt(vc[0] * vc[0] + vc[1] * vc[1]);
-    const T dtan = mu * fn0 / b_max(vt, vstick);
+    const T vt2 = vc[0] * vc[0] + vc[1] * vc[1];
+    const T dtan = mu * fn0 * ((vt2 > vstick * vstick) ? b_rsqrt(vt2) : b_div(T(1), vstick));   // mu fn0 / max(|v_t|, vstick)
     const T Fe[3] = {-dtan * vc[0], -dtan * vc[1], kn * depth - dn * vc[2]};
     T pxF[3];
     cross3(p, Fe, pxF);
@@ -349,9 +370,9 @@ B200_HD bool capsule_pair(const Model& m, int side, int i, int j, const T* G, co
     }
     const T d2 = dot3(d, d);
     const bool touching = (d2 < rsum * rsum) && (d2 > T(1e-12));
-    const T dist = b_sqrt(b_max(d2, T(1e-12)));
+    const T inv = b_rsqrt(b_max(d2, T(1e-12)));
+    const T dist = d2 * inv;
     const T depth = rsum - dist;
-    const T inv = b_div(T(1), dist);
 #pragma unroll
     for (int r = 0; r < 3; ++r) n[r] = d[r] * inv;
     // relative velocity of the two axis points (rigid-body velocity v + w x p of each link)
@@ -463,7 +484,7 @@ template <typename T> struct LegWork {
     T Mbb[21];     // base-base block, lower-tri, order v(3), w_body(3): partial after phase 1, total after the exchange
     T rb[6];       // base right-hand side: partial / total
     T Mlb[6][6];   // leg row k x base column j  (L factors after phase 1)
-    T Mll[21];     // leg-leg lower-tri (D on the diagonal, L below, after phase 1)
+    T Mll[21];     // leg-leg lower-tri (D^-1 on the diagonal, L below, after phase 1)
     T xl[6];       // leg right-hand side after the leg's part of the forward substitution
     T foot_fn;     // explicit normal-force estimate of this foot [N]
     T body_f2[3];  // |contact force|^2 on this leg's hip-yaw link, shank and foot (net_contact_force rows, envs/t1.py:553,628)
@@ -480,8 +501,8 @@ B200_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 template <typename T, typename Model> B200_HD T cylinder_low(const Model& m, int ci, const T R[3][3], const T* x) {
     const T* cp = m.cyl_pos[ci];
     const T cz = x[2] + R[2][0] * cp[0] + R[2][1] * cp[1] + R[2][2] * cp[2];
-    const T az = R[2][2];
-    return cz - (m.cyl_half[ci] * b_abs(az) + m.cyl_radius[ci] * b_sqrt(b_max(T(1) - az * az, T(0))));
+    // exact: cz - half |a_z| - rad sqrt(1 - a_z^2); the cull drops the square root (conservative by at most one radius)
+    return cz - (m.cyl_half[ci] * b_abs(R[2][2]) + m.cyl_radius[ci]);
 }
 template <int KS, typename T, typename Model>
 B200_HD void publish_hipyaw(const Model& m, const T R[3][3], const T* x, const T* w, const T* v, T* G) {
@@ -583,8 +604,7 @@ B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>&
                            const T* push_t, const Terr& terr, LegWork<T>& W, T* Kx, const T* Kp) {
     const T dt = m.dt;
     {
-        const T n = b_sqrt(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
-        const T inv = T(1) / n;
+        const T inv = b_rsqrt(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) s.quat[i] *= inv;
     }
@@ -980,7 +1000,7 @@ B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>&
     // --- L^T D L elimination of the leg DoFs, leaf to root (MuJoCo mj_factorM order: no fill-in) ------------------------
 #pragma unroll
     for (int k = 5; k >= 0; --k) {
-        const T inv = T(1) / W.Mll[tri(k, k)];
+        const T inv = b_div(T(1), W.Mll[tri(k, k)]);   // kept ON the diagonal below: phase 2 multiplies instead of dividing again
         // rows i = leg DoFs below k
 #pragma unroll
         for (int i = 0; i < k; ++i) {
@@ -1001,6 +1021,7 @@ B200_HD void t1_leg_phase1(const Model& m, const LegParams<T>& par, LegState<T>&
         for (int i = 0; i < k; ++i) W.Mll[tri(k, i)] *= inv;
 #pragma unroll
         for (int j = 0; j < 6; ++j) W.Mlb[k][j] *= inv;
+        W.Mll[tri(k, k)] = inv;
     }
     // forward substitution, leg part: x_j -= L_ij x_i for i = leg DoFs (descending)
 #pragma unroll
@@ -1021,7 +1042,7 @@ B200_HD void t1_leg_phase2(const Model& m, LegState<T>& s, LegWork<T>& W, T* qac
     // factor the 6x6 base block
 #pragma unroll
     for (int k = 5; k >= 0; --k) {
-        const T inv = T(1) / B[tri(k, k)];
+        const T inv = b_div(T(1), B[tri(k, k)]);
 #pragma unroll
         for (int i = 0; i < k; ++i) {
             const T l = B[tri(k, i)] * inv;
@@ -1030,20 +1051,21 @@ B200_HD void t1_leg_phase2(const Model& m, LegState<T>& s, LegWork<T>& W, T* qac
         }
 #pragma unroll
         for (int i = 0; i < k; ++i) B[tri(k, i)] *= inv;
+        B[tri(k, k)] = inv;   // D^-1 on the diagonal
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i)
 #pragma unroll
         for (int j = 0; j < i; ++j) x[j] -= B[tri(i, j)] * x[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) x[i] /= B[tri(i, i)];
+    for (int i = 0; i < 6; ++i) x[i] *= B[tri(i, i)];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j < i; ++j) x[i] -= B[tri(i, j)] * x[j];
     // leg: scale by D, then x_i -= sum_j L_ij x_j over base and lower leg DoFs
 #pragma unroll
-    for (int i = 0; i < 6; ++i) W.xl[i] /= W.Mll[tri(i, i)];
+    for (int i = 0; i < 6; ++i) W.xl[i] *= W.Mll[tri(i, i)];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
@@ -1079,7 +1101,7 @@ B200_HD void t1_leg_phase2(const Model& m, LegState<T>& s, LegWork<T>& W, T* qac
         nq[1] = qw * dy - qx * dz + qy * dw + qz * dx;
         nq[2] = qw * dz + qx * dy - qy * dx + qz * dw;
         nq[3] = qw * dw - qx * dx - qy * dy - qz * dz;
-        const T inv = T(1) / b_sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+        const T inv = b_rsqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) s.quat[i] = nq[i] * inv;
     }
