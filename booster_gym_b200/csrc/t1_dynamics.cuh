@@ -60,7 +60,10 @@ B200_HD double b_sqrt(double x) { return sqrt(x); }
 // division in the rarely executed shape code: approximate on the device (2 ulp), exact on the host
 B200_HD float b_div(float a, float b) {
 #if defined(__CUDA_ARCH__)
-    return __fdividef(a, b);
+    // one MUFU.RCP + one FMUL (__fdividef adds a 4-instruction rescue for |b| > 2^126, which no divisor here reaches)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return a * r;
 #else
     return a / b;
 #endif
@@ -68,7 +71,9 @@ B200_HD float b_div(float a, float b) {
 B200_HD double b_div(double a, double b) { return a / b; }
 B200_HD float b_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    float r;   // one MUFU.RSQ (rsqrtf adds denormal scaling; every argument here is a sum of squares far above 1e-38)
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -96,19 +101,20 @@ template <typename T> B200_HD void quat_to_mat(const T* q, T R[3][3]) {
 
 // rotation matrix -> quaternion xyzw (w >= 0 branch-stable Shepperd form)
 template <typename T> B200_HD void mat_to_quat(const T R[3][3], T* q) {
+    // the branch's largest component is sqrt(x) / 2, the others (sums of off-diagonal pairs) / (2 sqrt(x)): one rsqrt, no division
     T tr = R[0][0] + R[1][1] + R[2][2];
     if (tr > 0) {
-        T s = b_sqrt(tr + 1) * 2;
-        q[3] = s / 4; q[0] = (R[2][1] - R[1][2]) / s; q[1] = (R[0][2] - R[2][0]) / s; q[2] = (R[1][0] - R[0][1]) / s;
+        const T x = tr + 1, rs = b_rsqrt(x), h = T(0.5) * rs;
+        q[3] = T(0.5) * x * rs; q[0] = (R[2][1] - R[1][2]) * h; q[1] = (R[0][2] - R[2][0]) * h; q[2] = (R[1][0] - R[0][1]) * h;
     } else if (R[0][0] > R[1][1] && R[0][0] > R[2][2]) {
-        T s = b_sqrt(1 + R[0][0] - R[1][1] - R[2][2]) * 2;
-        q[3] = (R[2][1] - R[1][2]) / s; q[0] = s / 4; q[1] = (R[0][1] + R[1][0]) / s; q[2] = (R[0][2] + R[2][0]) / s;
+        const T x = 1 + R[0][0] - R[1][1] - R[2][2], rs = b_rsqrt(x), h = T(0.5) * rs;
+        q[3] = (R[2][1] - R[1][2]) * h; q[0] = T(0.5) * x * rs; q[1] = (R[0][1] + R[1][0]) * h; q[2] = (R[0][2] + R[2][0]) * h;
     } else if (R[1][1] > R[2][2]) {
-        T s = b_sqrt(1 + R[1][1] - R[0][0] - R[2][2]) * 2;
-        q[3] = (R[0][2] - R[2][0]) / s; q[0] = (R[0][1] + R[1][0]) / s; q[1] = s / 4; q[2] = (R[1][2] + R[2][1]) / s;
+        const T x = 1 + R[1][1] - R[0][0] - R[2][2], rs = b_rsqrt(x), h = T(0.5) * rs;
+        q[3] = (R[0][2] - R[2][0]) * h; q[0] = (R[0][1] + R[1][0]) * h; q[1] = T(0.5) * x * rs; q[2] = (R[1][2] + R[2][1]) * h;
     } else {
-        T s = b_sqrt(1 + R[2][2] - R[0][0] - R[1][1]) * 2;
-        q[3] = (R[1][0] - R[0][1]) / s; q[0] = (R[0][2] + R[2][0]) / s; q[1] = (R[1][2] + R[2][1]) / s; q[2] = s / 4;
+        const T x = 1 + R[2][2] - R[0][0] - R[1][1], rs = b_rsqrt(x), h = T(0.5) * rs;
+        q[3] = (R[1][0] - R[0][1]) * h; q[0] = (R[0][2] + R[2][0]) * h; q[1] = (R[1][2] + R[2][1]) * h; q[2] = T(0.5) * x * rs;
     }
 }
 
@@ -311,7 +317,14 @@ B200_HD void trunk_ground(const Model& m, int side, const T R0[3][3], const T* p
 // a linearly-implicit spring-damper on the RELATIVE normal velocity; each leg lane is implicit in its own velocity only (the
 // partner's velocity enters explicitly), so the legs stay uncoupled in the mass matrix and the forces are equal and opposite.
 // closest points of two segments P1 + s d1, P2 + t d2 (s, t in [0, 1]); both segments have positive length
-template <typename T> B200_HD T clamp01(T x) { return x < 0 ? T(0) : (x > 1 ? T(1) : x); }
+B200_HD float clamp01(float x) {
+#if defined(__CUDA_ARCH__)
+    return __saturatef(x);
+#else
+    return x < 0 ? 0.0f : (x > 1 ? 1.0f : x);
+#endif
+}
+B200_HD double clamp01(double x) { return x < 0 ? 0.0 : (x > 1 ? 1.0 : x); }
 template <typename T> B200_HD void segment_closest(const T* P1, const T* d1, const T* P2, const T* d2, T& s, T& t) {
     // branch-free (selects only): the tick evaluates two of these on every step and lets the scheduler interleave them
     const T r[3] = {P1[0] - P2[0], P1[1] - P2[1], P1[2] - P2[2]};
@@ -1090,10 +1103,11 @@ B200_HD void t1_leg_phase2(const Model& m, LegState<T>& s, LegWork<T>& W, T* qac
     }
     {
         // quat <- quat (x) exp(dt * wb / 2)   (body-frame angular velocity: right multiplication)
-        const T wn = b_sqrt(s.wb[0] * s.wb[0] + s.wb[1] * s.wb[1] + s.wb[2] * s.wb[2]);
+        const T wn2 = s.wb[0] * s.wb[0] + s.wb[1] * s.wb[1] + s.wb[2] * s.wb[2];
+        const T iw = b_rsqrt(b_max(wn2, T(1e-30))), wn = wn2 * iw;
         T sh, ch, k;
         b_sincos(T(0.5) * dt * wn, sh, ch);
-        k = (wn > T(1e-9)) ? sh / wn : T(0.5) * dt;
+        k = (wn > T(1e-9)) ? sh * iw : T(0.5) * dt;
         const T dx = k * s.wb[0], dy = k * s.wb[1], dz = k * s.wb[2], dw = ch;
         const T qx = s.quat[0], qy = s.quat[1], qz = s.quat[2], qw = s.quat[3];
         T nq[4];
