@@ -34,11 +34,11 @@ template <typename T> struct ModelOf;
 template <> struct ModelOf<float> { typedef B200T1ModelF type; };
 template <> struct ModelOf<double> { typedef B200T1ModelD type; };
 
-B200_HD void b_sincos(float x, float& s, float& c) {
-#if defined(__CUDA_ARCH__)
-    // The tick is instruction-fetch bound and calls this 7 times: CUDA's sincosf inlines ~150 instructions each (Payne-Hanek slow
-    // path included); joint angles are a few radians, so a 3-constant Cody-Waite reduction to [-pi/4, pi/4] (exact products
-    // for |k| < 2^13) + the cephes minimax polynomials do it in ~25 with |error| < 1e-7 (measured on 2e7 samples in [-8, 8]).
+// sin / cos for BOUNDED arguments (joint angles, half rotation angles: a few radians).  The tick is instruction-fetch bound and
+// needs 7 of these: CUDA's sincosf inlines ~150 instructions each (Payne-Hanek slow path included); a 3-constant Cody-Waite
+// reduction to [-pi/4, pi/4] (exact products for |k| < 2^13) + the cephes minimax polynomials take ~25, |error| < 1e-7 for
+// |x| <= 8 (tests/test_kernel_bodies_host.py::test_bounded_sincos).
+B200_HD void sincos_bounded(float x, float& s, float& c) {
     const float k = rintf(x * 0.636619772367581343f);
     float r = fmaf(-k, 1.5703125f, x);
     r = fmaf(-k, 4.837512969970703125e-4f, r);
@@ -50,6 +50,10 @@ B200_HD void b_sincos(float x, float& s, float& c) {
     const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
     s = (q & 2) ? -ss : ss;
     c = ((q + 1) & 2) ? -cc : cc;
+}
+B200_HD void b_sincos(float x, float& s, float& c) {
+#if defined(__CUDA_ARCH__)
+    sincos_bounded(x, s, c);
 #else
     s = sinf(x); c = cosf(x);
 #endif

@@ -132,6 +132,9 @@ int hc_env_reset_all(const B200T1ModelF* m, const B200T1Config* c, const int16_t
     }
     return 0;
 }
+void hc_sincos_bounded(const float* x, int n, float* s, float* c) {   // the device path of b_sincos(float), t1_dynamics.cuh
+    for (int i = 0; i < n; ++i) sincos_bounded(x[i], s[i], c[i]);
+}
 void hc_philox(unsigned long long seed, unsigned int env, unsigned long long step, int purpose, int sub, unsigned int* words,
                float* uni, float* nrm) {
     const Philox4 p = rng_words(seed, env, step, purpose, sub);

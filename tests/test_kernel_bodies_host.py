@@ -295,3 +295,15 @@ def test_legs_do_not_pass_through_each_other():
         res[sc] = (mind, np.linalg.norm(bf, axis=1))
     assert res[False][0] < 0.03 and res[True][0] > 0.075
     assert res[True][1][[6, 12]].min() > 10.0 and res[False][1].max() == 0.0
+
+
+def test_bounded_sincos():
+    """the 25-instruction sin / cos the physics tick uses on the device for joint angles (t1_dynamics.cuh sincos_bounded): absolute error
+    below 1e-7 over [-8, 8] rad (joint limits are within +-3), including tiny arguments and multiples of pi / 4"""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-8, 8, 2_000_000), rng.uniform(-1e-3, 1e-3, 100_000), np.arange(-10, 11) * (np.pi / 4), [0.0]]).astype(np.float32)
+    s = np.zeros_like(x); c = np.zeros_like(x)
+    lib().hc_sincos_bounded(x.ctypes.data_as(C.c_void_p), C.c_int(len(x)), s.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p))
+    xd = x.astype(np.float64)
+    assert np.abs(s - np.sin(xd)).max() < 1e-7 and np.abs(c - np.cos(xd)).max() < 1e-7
+    assert s[-1] == 0.0 and c[-1] == 1.0
