@@ -24,7 +24,8 @@ extern "C" int t1p_env_physics(const B200T1ModelD* m, PortEnv* envs, int nenv, c
                                double action_scale, const double* kp, const double* kd, const double* fric,
                                const double* torque_limit, const int* delay, double* last_targets, int decimation,
                                double* torques_mean) {
-    const TerrainView terr{nullptr, 0, 0, 0, 0.1f, 0.005};
+    TerrainView terr{nullptr, 0, 0, 0, 0.1f, 0.005};
+    terr.max_height = 0.0f;   // the plane: lets the shape culls of the tick work as they do on the device (a fair CPU baseline)
 #pragma omp parallel for schedule(static)
     for (int n = 0; n < nenv; ++n) {
         DynState<double> s;
