@@ -307,3 +307,49 @@ def test_bounded_sincos():
     xd = x.astype(np.float64)
     assert np.abs(s - np.sin(xd)).max() < 1e-7 and np.abs(c - np.cos(xd)).max() < 1e-7
     assert s[-1] == 0.0 and c[-1] == 1.0
+
+
+def test_fp32_tick_stays_finite_under_flailing_legs():
+    """the fp32 kernel body (host build) with every contact kind switched on, driven for 1.5 s by PD targets that keep swinging the
+    legs through each other and into the ground: no NaN / Inf, joint speeds and the base height stay physical (the stiff
+    leg-leg and body contacts are linearly implicit; this is the long-horizon stability check the one-tick parity tests cannot give)"""
+    from booster_gym_b200 import robot
+    from oracle import physics as op
+
+    mf = robot.model_f()
+    rng = np.random.default_rng(11)
+    q0 = np.array([-0.2, 0, 0, 0.4, -0.25, 0] * 2)
+    kp = np.array([200, 200, 200, 200, 50, 50] * 2, np.float64)
+    kd = np.array([5, 5, 5, 5, 1, 1] * 2, np.float64)
+    lim = np.array([45, 30, 30, 60, 24, 15] * 2, np.float64)
+
+    class EnvF(C.Structure):
+        _fields_ = [("pos", C.c_float * 3), ("quat", C.c_float * 4), ("vlin", C.c_float * 3), ("wb", C.c_float * 3), ("q", C.c_float * 12),
+                    ("qd", C.c_float * 12), ("mass", C.c_float * 13), ("com", C.c_float * 3 * 13), ("mu", C.c_float * 2),
+                    ("kscale", C.c_float * 2), ("cscale", C.c_float * 2)]
+
+    f32 = lambda a: (C.c_float * len(a))(*[float(v) for v in a])  # noqa: E731
+    worst_qd = 0.0
+    for trial in range(4):
+        e = EnvF()
+        e.pos[:] = [0, 0, 0.70]; e.quat[:] = [0, 0, 0, 1]
+        e.q[:] = list(q0)
+        for b in range(13):
+            e.mass[b] = mf.mass[b]
+            for r in range(3):
+                e.com[b][r] = mf.ipos[b][r]
+        e.mu[:] = [1.0, 1.0]; e.kscale[:] = [1.0, 1.0]; e.cscale[:] = [1.0, 1.0]
+        tgt = q0.copy()
+        for i in range(750):
+            if i % 75 == 0:   # new targets every 0.15 s: hip rolls / yaws swing inwards and outwards, knees fold
+                tgt = q0 + rng.uniform(-0.6, 0.6, 12)
+                tgt[1] = rng.uniform(-0.5, 0.3); tgt[7] = rng.uniform(-0.3, 0.5)
+            q = np.array(e.q[:]); qd = np.array(e.qd[:])
+            tau = np.clip(kp * (tgt - q) - kd * qd, -lim, lim)
+            qacc = (C.c_float * 18)(); fn = (C.c_float * 2)()
+            lib().hc_tick_f(C.byref(mf), C.byref(e), f32(tau), f32([0] * 3), f32([0] * 3), None, 0, 0, 50, C.c_float(0.1), C.c_double(0.005), qacc, fn, 1)
+            st = np.array(list(e.pos) + list(e.quat) + list(e.vlin) + list(e.wb) + list(e.q) + list(e.qd))
+            assert np.isfinite(st).all(), (trial, i)
+            worst_qd = max(worst_qd, np.abs(np.array(e.qd[:])).max())
+        assert -0.05 < e.pos[2] < 1.2
+    assert worst_qd < 100.0
