@@ -5,6 +5,9 @@
 
 Fixtures (small .npz files, committed; the GPU box has no reference tree):
   env_step_{plane,trimesh}.npz  reference T1.step() with physics = identity on a seeded synthetic state, RNG injected
+  env_step_curriculum.npz       reference T1.step() with `commands.curriculum: true`
+  env_step_contacts.npz         reference T1.step() with non-zero contact_forces and `terminate_contacts_on: [Trunk, Shank]`
+                                (collision reward, contact termination; `--contacts-only` regenerates just this one)
   env_reset_trimesh.npz         reference T1.reset()
   terrain_lookup.npz            reference Terrain.terrain_heights on a seeded heightfield
   learner_small.npz             reference ActorCritic + discount_values + surrogate_loss + the loop body of
