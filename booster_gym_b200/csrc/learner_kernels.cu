@@ -12,12 +12,13 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <new>
 
 #include "common.cuh"
-#include "gemm3x.cuh"
 #include "gemm_tc.cuh"
+#include "mlp_chain.cuh"
 #include "rng.cuh"
 
 using namespace b200;
@@ -50,14 +51,16 @@ enum { DS_ADV_SUM = B200_DS_ADV_SUM, DS_ADV_SUMSQ = B200_DS_ADV_SUMSQ, DS_ADV_CO
 #define WP_MAX_CTAS 160   // >= CTAs of one k_tc_wgrad launch (one wave: <= SM count)
 struct Workspace {
     size_t Xa, Xc;                                      // packed inputs [M,64] (obs, zero padded), [M+N,64] (obs, priv, zero padded)
+    size_t Xah, Xal, Xch, Xcl;                          // the same, pre-split into tf32 hi / lo (A operand of the fused chain's first layer)
     size_t C1, C2, C3;                                  // critic post-ELU activations [M+N,256],[M+N,256],[M+N,128]
     size_t A1, A2, A3;                                  // actor post-ELU activations [M,256],[M,128],[M,128]
     size_t V, MU, ADV, RET, DV, DMU;
-    size_t G1, G2;                                      // gradient ping-pong [M,256]
+    size_t GC3, GC2, GC1, GA3, GA2, GA1;                // dL/dz of the hidden layers: critic [M,128],[M,256],[M,256]; actor [M,128],[M,128],[M,256]
+    size_t G1, G2;                                      // layer-by-layer path: gradient ping-pong [M,256] (aliases GC1, GC2)
     size_t WP[6];                                       // partial weight-gradient tiles of the six k_tc_wgrad launches of an epoch
     size_t Wc0h, Wc0l, Wc1h, Wc1l, Wc2h, Wc2l, Wa0h, Wa0l, Wa1h, Wa1l, Wa2h, Wa2l;   // split weights, K padded to 64 for layer 0
     size_t Wc1Th, Wc1Tl, Wc2Th, Wc2Tl, Wa1Th, Wa1Tl, Wa2Th, Wa2Tl;                  // transposed split weights for dgrad
-    size_t LXc, L1, L2, L3, LV;                          // N-row fp32 buffers of b200_critic_value (mma.sync path, gemm3x.cuh)
+    size_t LXc, LXh, LXl, L1, L2, L3, LV;                // N-row fp32 buffers of b200_critic_value
     size_t total;
 };
 static Workspace make_workspace(int T, int N) {
@@ -67,17 +70,20 @@ static Workspace make_workspace(int T, int N) {
     auto take = [&](size_t cnt) { size_t r = o; o += (cnt + 255) & ~(size_t)255; return r; };  // 1 KiB aligned (TMA needs 16 B)
     const size_t Mc = M + n;  // the critic also evaluates the N post-rollout observations (last_values, utils/runner.py:133) in the same pass
     w.Xa = take(M * 64); w.Xc = take(Mc * 64);
+    w.Xah = take(M * 64); w.Xal = take(M * 64); w.Xch = take(Mc * 64); w.Xcl = take(Mc * 64);
     w.C1 = take(Mc * 256); w.C2 = take(Mc * 256); w.C3 = take(Mc * 128);
     w.A1 = take(M * 256); w.A2 = take(M * 128); w.A3 = take(M * 128);
     w.V = take(Mc); w.MU = take(M * 12); w.ADV = take(M); w.RET = take(M); w.DV = take(M); w.DMU = take(M * 12);
-    w.G1 = take(M * 256); w.G2 = take(M * 256);
+    w.GC3 = take(M * 128); w.GC2 = take(M * 256); w.GC1 = take(M * 256);
+    w.GA3 = take(M * 128); w.GA2 = take(M * 128); w.GA1 = take(M * 256);
+    w.G1 = w.GC1; w.G2 = w.GC2;
     for (int j = 0; j < 6; ++j) w.WP[j] = take((size_t)WP_MAX_CTAS * 128 * 256);
     w.Wc0h = take(256 * 64); w.Wc0l = take(256 * 64); w.Wc1h = take(256 * 256); w.Wc1l = take(256 * 256);
     w.Wc2h = take(128 * 256); w.Wc2l = take(128 * 256); w.Wa0h = take(256 * 64); w.Wa0l = take(256 * 64);
     w.Wa1h = take(128 * 256); w.Wa1l = take(128 * 256); w.Wa2h = take(128 * 128); w.Wa2l = take(128 * 128);
     w.Wc1Th = take(256 * 256); w.Wc1Tl = take(256 * 256); w.Wc2Th = take(256 * 128); w.Wc2Tl = take(256 * 128);
     w.Wa1Th = take(256 * 128); w.Wa1Tl = take(256 * 128); w.Wa2Th = take(128 * 128); w.Wa2Tl = take(128 * 128);
-    w.LXc = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
+    w.LXc = take(n * 64); w.LXh = take(n * 64); w.LXl = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
     w.LV = take(n);
     w.total = o;
     return w;
@@ -114,6 +120,7 @@ struct B200Ppo {
     Workspace w;
     tc::MapCache* maps;           // TMA tensor maps of the (fixed) workspace buffers, built lazily on first use
     int num_sms;
+    bool chain_fwd_configured = false, chain_bwd_configured = false;   // per-handle (= per-device) dynamic shared memory opt-in
     float* P(int i) const { return params + kParams[i].offset; }
     float* G(int i) const { return grads + kParams[i].offset; }
 };
@@ -122,9 +129,17 @@ struct B200Ppo {
 // small kernels
 // =====================================================================================================================
 
-// obs [n,47] (+ priv [n,14]) -> zero-padded GEMM operands Xa [n,48], Xc [n,64] (either output may be null)
-__global__ void k_pack_inputs(const float* __restrict__ obs, const float* __restrict__ priv, int n, float* __restrict__ Xa,
-                              float* __restrict__ Xc) {
+__device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
+    hi = tc::tf32_rna(x);
+    lo = tc::tf32_rna(x - hi);
+}
+
+// obs [n,47] (+ priv [n,14]) -> zero-padded GEMM operands Xa [n,64] (obs), Xc [n,64] (obs, priv) as plain fp32 (operand of the
+// weight-gradient GEMMs) and pre-split into tf32 hi / lo (A operand of the fused chain's first layer).  Any output may be null.
+struct PackOut {
+    float *Xa, *Xah, *Xal, *Xc, *Xch, *Xcl;
+};
+__global__ void k_pack_inputs(const float* __restrict__ obs, const float* __restrict__ priv, int n, const PackOut o) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)n * 64;
     if (idx >= total) return;
@@ -133,15 +148,14 @@ __global__ void k_pack_inputs(const float* __restrict__ obs, const float* __rest
     float v = 0.0f;
     if (c < 47) v = obs[r * 47 + c];
     else if (c < 61 && priv) v = priv[r * 14 + (c - 47)];
-    if (Xc) Xc[idx] = v;
-    if (Xa) Xa[idx] = (c < 47) ? v : 0.0f;
+    float hi, lo;
+    split_tf32f(v, hi, lo);
+    if (o.Xc) o.Xc[idx] = v;
+    if (o.Xch) { o.Xch[idx] = hi; o.Xcl[idx] = lo; }
+    const bool a = c < 47;
+    if (o.Xa) o.Xa[idx] = a ? v : 0.0f;
+    if (o.Xah) { o.Xah[idx] = a ? hi : 0.0f; o.Xal[idx] = a ? lo : 0.0f; }
 }
-
-__device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
-    hi = tc::tf32_rna(x);
-    lo = tc::tf32_rna(x - hi);
-}
-
 
 // W [rows, cols] fp32 -> split copies: K-major [rows, cols_pad] (zero padded) and, if WTh != null, transposed [cols, rows];
 // all six hidden-layer matrices in ONE launch (blockIdx.y = matrix)
@@ -899,18 +913,20 @@ __global__ void k_post_apply(float* __restrict__ scalars, const double* __restri
 namespace b200 {
 long long g_launches = 0;
 }
-enum { PK_MMA_SYNC = 0, PK_TC_ROW = 1, PK_TC_WGRAD = 2, PK_COUNT = 3 };  // kernel families timed by b200_profile_gemm
+enum { PK_MMA_SYNC = 0, PK_TC_ROW = 1, PK_TC_WGRAD = 2, PK_CHAIN_FWD = 3, PK_CHAIN_BWD = 4, PK_COUNT = 5 };  // kernel families timed by b200_profile_gemm
 struct GemmProfile {
     bool on = false;
     int used = 0;
     static const int kMax = 8192;
     cudaEvent_t* ev = nullptr;  // 2 * kMax
     unsigned char* kind = nullptr;
-    double flops[PK_COUNT] = {0.0, 0.0, 0.0};
-    double bytes[PK_COUNT] = {0.0, 0.0, 0.0};   // algorithmic HBM bytes (operands read once + results written once)
+    double flops[PK_COUNT] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double bytes[PK_COUNT] = {0.0, 0.0, 0.0, 0.0, 0.0};   // HBM bytes of the launch's traffic model (operands read once + results written once)
 } g_prof;
 
 static bool g_tc_pair = getenv("B200_TC_PAIR") ? atoi(getenv("B200_TC_PAIR")) != 0 : false;   // cta_group::2 GEMMs (b200_tc_set_pair)
+static bool g_chain_exact_actor = getenv("B200_CHAIN_EXACT_ELU") ? atoi(getenv("B200_CHAIN_EXACT_ELU")) != 0 : false;   // expm1f in the actor chain
+static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
 static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
 static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC, double bytes = 0.0) {
@@ -926,30 +942,12 @@ static void prof_end(cudaStream_t st) {
     g_prof.used += 1;
 }
 
-// =====================================================================================================================
-// dense layers on k_gemm3x (b200_critic_value only)
-// =====================================================================================================================
 #define CU_TRY(expr)                                                   \
     do {                                                               \
         cudaError_t _e = (expr);                                       \
         if (_e != cudaSuccess) return set_cuda_error(_e, #expr);       \
     } while (0)
 
-// Y[n, n_out] = act(X[n, k_pad] W[n_out, k_valid]^T + b)
-static cudaError_t linear_fwd(const float* X, int ldx, int k_pad, const float* W, int k_valid, const float* b, float* Y,
-                              int ldy, int n, int n_out, bool elu, cudaStream_t st, float* Yh = nullptr, float* Yl = nullptr) {
-    GemmArgs g{};
-    g.C_hi = Yh; g.C_lo = Yl;
-    g.A = X; g.B = W; g.C = Y; g.bias = b; g.aux = nullptr;
-    g.I = n; g.Cn = n_out; g.R = k_pad;
-    g.lda = ldx; g.ldb = k_valid; g.ldc = ldy; g.ldaux = 0;
-    g.cn_store = n_out; g.r_chunk = 0; g.r_valid_b = k_valid;
-    prof_begin(st, 2.0 * n * (double)n_out * k_valid);
-    const cudaError_t e = elu ? launch_gemm3x<false, false, EPI_BIAS_ELU>(g, 1, st) : launch_gemm3x<false, false, EPI_BIAS>(g, 1, st);
-    prof_end(st);
-    g_launches += 1;
-    return e;
-}
 // ---- reduction of the k_tc_wgrad partial tiles: dW[row, col] += sum over parts, all six weight matrices in one launch ----
 struct WgradJob {
     const float* P;   // [tiles_y * tiles_z][parts][128][bn]
@@ -1103,10 +1101,119 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
 // full-batch forward passes over the M = T*N stored samples (activations kept in fp32 for the backward pass)
 // The ACTOR forward uses the 4-accumulator variant with the exact expm1f: log-prob sensitivity to mu is 1/sigma ~ 7.4 per
 // unit (sigma = e^-2), so mu wants short accumulation chains (TMEM adds truncate) - see gemm_tc.cuh.
-static int actor_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
+// ---- fused layer chains (mlp_chain.cuh): the three hidden layers of a net in one persistent kernel per direction --------------
+struct ChainNetPtrs {          // one net's operands of a forward launch
+    const float *Xh, *Xl;      // [rows, 64] pre-split input
+    const float *W1h, *W1l, *W2h, *W2l, *W3h, *W3l, *b1, *b2, *b3;
+    float *H1, *H2, *H3;
+    int rows, n2, exact, k_valid;
+};
+static int chain_fill_fwd(const B200Ppo* p, chain::FwdNet& N, const ChainNetPtrs& c) {
+    N.rows = c.rows; N.n2 = c.n2; N.exact = c.exact; N.pad_ = 0;
+    if (c.rows <= 0) { N.rows = 0; return B200_OK; }
+    TC_MAP(mXh, c.Xh, c.rows, 64, 64, tc::BM, true);
+    TC_MAP(mXl, c.Xl, c.rows, 64, 64, tc::BM, true);
+    TC_MAP(mW1h, c.W1h, 256, 64, 64, 256, true);
+    TC_MAP(mW1l, c.W1l, 256, 64, 64, 256, true);
+    TC_MAP(mW2h, c.W2h, c.n2, 256, 256, c.n2, true);
+    TC_MAP(mW2l, c.W2l, c.n2, 256, 256, c.n2, true);
+    TC_MAP(mW3h, c.W3h, 128, c.n2, c.n2, 128, true);
+    TC_MAP(mW3l, c.W3l, 128, c.n2, c.n2, 128, true);
+    N.mXh = *mXh; N.mXl = *mXl; N.mW1h = *mW1h; N.mW1l = *mW1l; N.mW2h = *mW2h; N.mW2l = *mW2l; N.mW3h = *mW3h; N.mW3l = *mW3l;
+    N.b1 = c.b1; N.b2 = c.b2; N.b3 = c.b3; N.H1 = c.H1; N.H2 = c.H2; N.H3 = c.H3;
+    return B200_OK;
+}
+static ChainNetPtrs critic_ptrs(const B200Ppo* p, int rows) {
+    float* ws = p->ws; const Workspace& w = p->w;
+    return ChainNetPtrs{ws + w.Xch, ws + w.Xcl, ws + w.Wc0h, ws + w.Wc0l, ws + w.Wc1h, ws + w.Wc1l, ws + w.Wc2h, ws + w.Wc2l,
+                        p->P(P_CB0), p->P(P_CB1), p->P(P_CB2), ws + w.C1, ws + w.C2, ws + w.C3, rows, 256, 0, 61};
+}
+static ChainNetPtrs actor_ptrs(const B200Ppo* p, int rows) {
+    float* ws = p->ws; const Workspace& w = p->w;
+    return ChainNetPtrs{ws + w.Xah, ws + w.Xal, ws + w.Wa0h, ws + w.Wa0l, ws + w.Wa1h, ws + w.Wa1l, ws + w.Wa2h, ws + w.Wa2l,
+                        p->P(P_AB0), p->P(P_AB1), p->P(P_AB2), ws + w.A1, ws + w.A2, ws + w.A3, rows, 128, g_chain_exact_actor ? 1 : 0, 47};
+}
+static int chain_forward(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs& c1, cudaStream_t st) {
+    chain::FwdParams P;
+    memset(&P, 0, sizeof(P));
+    int rc;
+    if ((rc = chain_fill_fwd(p, P.net[0], c0)) != B200_OK) return rc;
+    if ((rc = chain_fill_fwd(p, P.net[1], c1)) != B200_OK) return rc;
+    const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
+    if (tiles <= 0) return B200_OK;
+    if (!p->chain_fwd_configured) {
+        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::F_SMEM));
+        p->chain_fwd_configured = true;
+    }
+    double fl = 0.0, by = 0.0;
+    const ChainNetPtrs* cs[2] = {&c0, &c1};
+    for (int i = 0; i < 2; ++i) {
+        const double r = cs[i]->rows > 0 ? cs[i]->rows : 0;
+        fl += 2.0 * r * ((double)cs[i]->k_valid * 256 + 256.0 * cs[i]->n2 + (double)cs[i]->n2 * 128);
+        by += 4.0 * r * (2 * 64 + 256 + cs[i]->n2 + 128);   // X hi + lo read; h1, h2, h3 written
+    }
+    prof_begin(st, fl, PK_CHAIN_FWD, by);
+    chain::k_mlp_fwd<<<tiles < p->num_sms ? tiles : p->num_sms, chain::F_THREADS, chain::F_SMEM, st>>>(P);
+    prof_end(st);
+    g_launches += 1;
+    return launch_status("k_mlp_fwd");
+}
+// both nets' hidden-layer input gradients + bias gradients: dz3 (from the head kernels) -> dz2, dz1
+static int chain_backward(B200Ppo* p, int M, bool critic, bool actor, cudaStream_t st) {
+    float* ws = p->ws; const Workspace& w = p->w;
+    chain::BwdParams P;
+    memset(&P, 0, sizeof(P));
+    double fl = 0.0, by = 0.0;
+    for (int i = 0; i < 2; ++i) {
+        chain::BwdNet& N = P.net[i];
+        N.n2 = i == 0 ? 256 : 128;
+        N.rows = (i == 0 ? critic : actor) ? M : 0;
+        if (N.rows <= 0) continue;
+        const float* Z3 = ws + (i == 0 ? w.GC3 : w.GA3);
+        const float* H2 = ws + (i == 0 ? w.C2 : w.A2);
+        const float* H1 = ws + (i == 0 ? w.C1 : w.A1);
+        const float* W3Th = ws + (i == 0 ? w.Wc2Th : w.Wa2Th);
+        const float* W3Tl = ws + (i == 0 ? w.Wc2Tl : w.Wa2Tl);
+        const float* W2Th = ws + (i == 0 ? w.Wc1Th : w.Wa1Th);
+        const float* W2Tl = ws + (i == 0 ? w.Wc1Tl : w.Wa1Tl);
+        TC_MAP(mZ3, Z3, M, 128, 128, tc::BM, true);
+        TC_MAP(mH2, H2, M, N.n2, N.n2, tc::BM, true);
+        TC_MAP(mH1, H1, M, 256, 256, tc::BM, true);
+        TC_MAP(mW3Th, W3Th, N.n2, 128, 128, N.n2, true);
+        TC_MAP(mW3Tl, W3Tl, N.n2, 128, 128, N.n2, true);
+        TC_MAP(mW2Th, W2Th, 256, N.n2, N.n2, 256, true);
+        TC_MAP(mW2Tl, W2Tl, 256, N.n2, N.n2, 256, true);
+        N.mZ3 = *mZ3; N.mH2 = *mH2; N.mH1 = *mH1; N.mW3Th = *mW3Th; N.mW3Tl = *mW3Tl; N.mW2Th = *mW2Th; N.mW2Tl = *mW2Tl;
+        N.DZ2 = ws + (i == 0 ? w.GC2 : w.GA2);
+        N.DZ1 = ws + (i == 0 ? w.GC1 : w.GA1);
+        N.db2 = p->G(i == 0 ? P_CB1 : P_AB1);
+        N.db1 = p->G(i == 0 ? P_CB0 : P_AB0);
+        fl += 2.0 * M * (128.0 * N.n2 + (double)N.n2 * 256);
+        by += 4.0 * M * (128.0 + 2.0 * N.n2 + 2.0 * 256);   // dz3, h2, h1 read; dz2, dz1 written
+    }
+    const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
+    if (tiles <= 0) return B200_OK;
+    if (!p->chain_bwd_configured) {
+        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::B_SMEM));
+        p->chain_bwd_configured = true;
+    }
+    prof_begin(st, fl, PK_CHAIN_BWD, by);
+    chain::k_mlp_bwd<<<tiles < p->num_sms ? tiles : p->num_sms, chain::B_THREADS, chain::B_SMEM, st>>>(P);
+    prof_end(st);
+    g_launches += 1;
+    return launch_status("k_mlp_bwd");
+}
+
+static int actor_forward_tc(B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
     int rc;
+    if (g_chain) {
+        if ((rc = chain_forward(p, critic_ptrs(p, 0), actor_ptrs(p, M), st))) return rc;
+        k_actor_head<<<1184, 256, 0, st>>>(ws + w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + w.MU);
+        g_launches += 1;
+        return launch_status("k_actor_head");
+    }
     if ((rc = tc_fwd(p, ws + w.Xa, 47, 64, ws + w.Wa0h, ws + w.Wa0l, 64, p->P(P_AB0), ws + w.A1, M, 256, st, true))) return rc;
     if ((rc = tc_fwd(p, ws + w.A1, 256, 256, ws + w.Wa1h, ws + w.Wa1l, 256, p->P(P_AB1), ws + w.A2, M, 128, st, true))) return rc;
     if ((rc = tc_fwd(p, ws + w.A2, 128, 128, ws + w.Wa2h, ws + w.Wa2l, 128, p->P(P_AB2), ws + w.A3, M, 128, st, true))) return rc;
@@ -1114,25 +1221,20 @@ static int actor_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
     g_launches += 1;
     return launch_status("k_actor_head");
 }
-static int critic_forward_tc(const B200Ppo* p, int M, cudaStream_t st) {
+static int critic_forward_tc(B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
     int rc;
+    if (g_chain) {
+        if ((rc = chain_forward(p, critic_ptrs(p, M), actor_ptrs(p, 0), st))) return rc;
+        k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
+        g_launches += 1;
+        return launch_status("k_value_head");
+    }
     if ((rc = tc_fwd(p, ws + w.Xc, 61, 64, ws + w.Wc0h, ws + w.Wc0l, 64, p->P(P_CB0), ws + w.C1, M, 256, st))) return rc;
     if ((rc = tc_fwd(p, ws + w.C1, 256, 256, ws + w.Wc1h, ws + w.Wc1l, 256, p->P(P_CB1), ws + w.C2, M, 256, st))) return rc;
     if ((rc = tc_fwd(p, ws + w.C2, 256, 256, ws + w.Wc2h, ws + w.Wc2l, 256, p->P(P_CB2), ws + w.C3, M, 128, st))) return rc;
     k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
-    g_launches += 1;
-    return launch_status("k_value_head");
-}
-
-// critic 61 -> 256 -> 256 -> 128 -> 1 (utils/model.py:9-17); Xc is the packed [n,64] cat(obs, priv)
-static int critic_forward(const B200Ppo* p, const float* Xc, int n, float* H1, float* H2, float* H3, float* V,
-                          cudaStream_t st) {
-    CU_TRY(linear_fwd(Xc, 64, 64, p->P(P_CW0), 61, p->P(P_CB0), H1, 256, n, 256, true, st));
-    CU_TRY(linear_fwd(H1, 256, 256, p->P(P_CW1), 256, p->P(P_CB1), H2, 256, n, 256, true, st));
-    CU_TRY(linear_fwd(H2, 256, 256, p->P(P_CW2), 256, p->P(P_CB2), H3, 128, n, 128, true, st));
-    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(H3, p->P(P_CW3), p->P(P_CB3), n, V);
     g_launches += 1;
     return launch_status("k_value_head");
 }
@@ -1228,9 +1330,17 @@ int b200_critic_value(B200Ppo* p, const float* obs, const float* priv, int n, fl
     if (!obs || !priv || !values || n <= 0 || n > p->cfg.num_envs) return set_error(B200_ERR_ARG, "b200_critic_value: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
-    k_pack_inputs<<<(int)(((size_t)n * 64 + 255) / 256), 256, 0, st>>>(obs, priv, n, nullptr, ws + p->w.LXc);
+    const Workspace& w = p->w;
+    k_pack_inputs<<<(int)(((size_t)n * 64 + 255) / 256), 256, 0, st>>>(obs, priv, n, PackOut{nullptr, nullptr, nullptr, nullptr, ws + w.LXh, ws + w.LXl});
     g_launches += 1;
-    return critic_forward(p, ws + p->w.LXc, n, ws + p->w.L1, ws + p->w.L2, ws + p->w.L3, values, st);
+    int rc = weight_prep(p, st);   // the parameters may have changed since the last epoch
+    if (rc != B200_OK) return rc;
+    ChainNetPtrs c = critic_ptrs(p, n);
+    c.Xh = ws + w.LXh; c.Xl = ws + w.LXl; c.H1 = ws + w.L1; c.H2 = ws + w.L2; c.H3 = ws + w.L3;
+    if ((rc = chain_forward(p, c, actor_ptrs(p, 0), st)) != B200_OK) return rc;
+    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(ws + w.L3, p->P(P_CW3), p->P(P_CB3), n, values);
+    g_launches += 1;
+    return launch_status("k_value_head");
 }
 
 int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const float* actions, float* old_mu,
@@ -1240,7 +1350,8 @@ int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const 
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     const int M = p->cfg.horizon * p->cfg.num_envs;
-    k_pack_inputs<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(obses, privs, M, ws + p->w.Xa, ws + p->w.Xc);
+    k_pack_inputs<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(
+        obses, privs, M, PackOut{ws + p->w.Xa, ws + p->w.Xah, ws + p->w.Xal, ws + p->w.Xc, ws + p->w.Xch, ws + p->w.Xcl});
     int rc = weight_prep(p, st);
     if (rc != B200_OK) return rc;
     if ((rc = actor_forward_tc(p, M, st)) != B200_OK) return rc;
@@ -1272,7 +1383,11 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     int rc = weight_prep(p, st);  // the parameters changed in the previous epoch's b200_ppo_apply
     if (rc != B200_OK) return rc;
     // last_values = critic(post-rollout obs): appended as rows [M, M+N) of the critic batch, evaluated in the same GEMMs
-    k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(last_obs, last_priv, N, nullptr, ws + p->w.Xc + (size_t)M * 64);
+    {
+        const size_t o = (size_t)M * 64;
+        k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(
+            last_obs, last_priv, N, PackOut{nullptr, nullptr, nullptr, ws + p->w.Xc + o, ws + p->w.Xch + o, ws + p->w.Xcl + o});
+    }
     if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
     k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
@@ -1308,6 +1423,23 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     k_finalize_logstd<<<1, 32, 0, st>>>(p->dstats, p->cfg.entropy_coef, p->G(P_LOGSTD));
     g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
+    if (g_chain) {
+        // head backward kernels produce dz3 of both nets (+ the head's own gradients and layer 3's bias gradient), ONE fused chain
+        // launch produces dz2, dz1 and the remaining bias gradients, then the six weight-gradient GEMMs
+        float *GA3 = ws + w.GA3, *GA2 = ws + w.GA2, *GA1 = ws + w.GA1, *GC3 = ws + w.GC3, *GC2 = ws + w.GC2, *GC1 = ws + w.GC1;
+        k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, GA3, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2));
+        k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, GC3, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2));
+        g_launches += 2;
+        if ((rc = launch_status("k_head_bwd")) != B200_OK) return rc;
+        if ((rc = chain_backward(p, M, true, true, st))) return rc;
+        if ((rc = tc_wgrad(p, jobs, 0, GA3, 128, ws + w.A2, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
+        if ((rc = tc_wgrad(p, jobs, 1, GA2, 128, ws + w.A1, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
+        if ((rc = tc_wgrad(p, jobs, 2, GA1, 256, ws + w.Xa, 64, 64, 47, p->G(P_AW0), M, st))) return rc;
+        if ((rc = tc_wgrad(p, jobs, 3, GC3, 128, ws + w.C2, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
+        if ((rc = tc_wgrad(p, jobs, 4, GC2, 256, ws + w.C1, 256, 256, 256, p->G(P_CW1), M, st))) return rc;
+        if ((rc = tc_wgrad(p, jobs, 5, GC1, 256, ws + w.Xc, 64, 64, 61, p->G(P_CW0), M, st))) return rc;
+        return wgrad_reduce(jobs, st);
+    }
     // ---- actor backward: the 12-wide head as a fused FMA kernel, the hidden layers on tcgen05
     k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, G1, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2));
     g_launches += 1;
@@ -1379,6 +1511,10 @@ int b200_tc_set_pair(int enable) {
     g_tc_pair = enable != 0;
     return B200_OK;
 }
+int b200_tc_set_chain(int enable) {
+    g_chain = enable != 0;
+    return B200_OK;
+}
 
 #ifdef B200_TC_TIMELINE
 /* debug builds only (tools/tc_timeline.py): per-CTA timelines of the tcgen05 GEMM launches since the last reset, in launch order */
@@ -1387,6 +1523,15 @@ int b200_tc_timeline_read(unsigned long long* out /* [TL_SLOTS][160][12] */) {
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpyFromSymbol(out, tc::g_tl, sizeof(unsigned long long) * TL_SLOTS * 160 * 12));
     return g_tl_slot;
+}
+#endif
+
+#ifdef B200_CHAIN_TL
+/* debug builds only (tools/chain_timeline.py): per-CTA blocked-cycle counters of the last k_mlp_fwd / k_mlp_bwd launch */
+int b200_chain_timeline_read(long long* out /* [2][160][16] */) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out, chain::g_chain_tl, sizeof(long long) * 2 * 160 * 16));
+    return B200_OK;
 }
 #endif
 
@@ -1440,6 +1585,18 @@ float* b200_ppo_buffer(B200Ppo* p, int which) {
         case 4: return p->ws + p->w.V + (size_t)p->cfg.horizon * p->cfg.num_envs;
         case 5: return p->ws + p->w.DV;
         case 6: return p->ws + p->w.DMU;
+        case 7: return p->ws + p->w.C1;
+        case 8: return p->ws + p->w.C2;
+        case 9: return p->ws + p->w.C3;
+        case 10: return p->ws + p->w.A1;
+        case 11: return p->ws + p->w.A2;
+        case 12: return p->ws + p->w.A3;
+        case 13: return p->ws + p->w.GC2;
+        case 14: return p->ws + p->w.GC1;
+        case 15: return p->ws + p->w.GA2;
+        case 16: return p->ws + p->w.GA1;
+        case 17: return p->ws + p->w.GC3;
+        case 18: return p->ws + p->w.GA3;
     }
     return nullptr;
 }

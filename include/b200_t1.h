@@ -312,6 +312,10 @@ int b200_profile_gemm_bytes(int kind, double* total_bytes);
  * (clusters of 2, tcgen05 cta_group::2, 256-row tiles, each CTA stages half of the weight tile).  Same results; the pair
  * variant halves the per-CTA L2 -> shared-memory weight traffic but measured ~4 % slower on this shape. */
 int b200_tc_set_pair(int enable);
+/* hidden layers of the PPO epoch: 1 (default) = fused layer chains (mlp_chain.cuh: one persistent tcgen05 kernel per direction,
+ * activations handed from layer to layer in TMEM), 0 = one GEMM launch per layer (k_tc_rowmajor).  Same results within the
+ * stated tolerances; replaces the autograd graph of utils/runner.py:132-133,148,163. */
+int b200_tc_set_chain(int enable);
 
 #ifdef __cplusplus
 }
