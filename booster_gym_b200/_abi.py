@@ -65,6 +65,7 @@ class T1Config(C.Structure):
         ("dof_damping", Rand), ("dof_friction", Rand), ("friction", Rand), ("compliance", Rand),
         ("restitution", Rand), ("base_com", Rand), ("base_mass", Rand), ("other_com", Rand), ("other_mass", Rand),
         ("kick_interval", C.c_int32), ("push_interval", C.c_int32), ("push_duration", C.c_int32),
+        ("push_all_substeps", C.c_int32),
         ("lin_vel_x", C.c_float * 2), ("lin_vel_y", C.c_float * 2), ("ang_vel_yaw", C.c_float * 2),
         ("gait_frequency", C.c_float * 2), ("still_proportion", C.c_float),
         ("resample_lo", C.c_int32), ("resample_hi", C.c_int32), ("curriculum", C.c_int32),

@@ -114,6 +114,7 @@ def t1_config(cfg):
     c.kick_interval = int(np.ceil(rz["kick_interval_s"] / dt))
     c.push_interval = int(np.ceil(rz["push_interval_s"] / dt))
     c.push_duration = int(np.ceil(rz["push_duration_s"] / dt))
+    c.push_all_substeps = 1 if rz.get("push_all_substeps") else 0
     cm = cfg["commands"]
     for key in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "gait_frequency"):
         getattr(c, key)[0] = float(cm[key][0])

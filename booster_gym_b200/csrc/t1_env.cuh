@@ -226,6 +226,12 @@ __device__ __forceinline__ void env_physics_pair(const EnvView& v, int e, bool v
 #pragma unroll
         for (int q = 0; q < 6; ++q) W.rb[q] = pair_sum(W.rb[q]);
         t1_leg_phase2<float>(m, s, W, qb, ql, true);
+        // Isaac Gym applies the tensors of apply_rigid_body_force_tensors (registered once per step(), envs/t1.py:522-527) to the
+        // next simulate() only: the push acts on the first substep
+        if (i == 0 && !c.push_all_substeps) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { push_f[r] = 0.0f; push_t[r] = 0.0f; }
+        }
     }
     // net contact force per body after the last substep (gym.refresh_net_contact_force_tensor, envs/t1.py:462) reduced to what
     // the env reads: |F| > 1 N (envs/t1.py:553,628).  The trunk's force is the sum of the two lanes' shares.
@@ -827,7 +833,8 @@ B200_HD void env_init_params(const EnvView& v, int e, const Model& m, const B200
     for (int k = 0; k < 2; ++k) { FS(F_feet_roll + k) = 0.0f; FS(F_feet_yaw + k) = 0.0f; FS(F_feet_force + k) = 0.0f; IS(I_feet_contact + k) = 0; }
     for (int k = 0; k < 27; ++k) FS(F_episode_sums + k) = 0.0f;
     IS(I_episode_length_buf) = 0; IS(I_cmd_resample_time) = 0; IS(I_delay_steps) = 0;
-    IS(I_reset_buf) = 1; IS(I_time_out_buf) = 0; IS(I_episode_steps) = 0; IS(I_nan_resets) = 0;
+    IS(I_reset_buf) = 1; IS(I_time_out_buf) = 0; IS(I_nan_resets) = 0;
+    IS(I_episode_steps) = -1;   // the reference Recorder's step counter is 0 (not 1) after the first step() (utils/recorder.py:37-40)
 }
 
 }  // namespace b200

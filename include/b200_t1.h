@@ -112,6 +112,9 @@ typedef struct B200T1Config {
         push_torque, dof_stiffness, dof_damping, dof_friction, friction, compliance, restitution, base_com,
         base_mass, other_com, other_mass;
     int32_t kick_interval, push_interval, push_duration; /* in env steps: ceil(s / dt) */
+    int32_t push_all_substeps; /* 0 (default, the reference): the push registered by gym.apply_rigid_body_force_tensors once per
+                                * step() (envs/t1.py:522-527) acts on the NEXT simulate() only, i.e. on the first of the
+                                * `decimation` substeps; 1: on every substep (extension key randomization.push_all_substeps) */
     /* commands (envs/T1.yaml:112-134) */
     float lin_vel_x[2], lin_vel_y[2], ang_vel_yaw[2], gait_frequency[2];
     float still_proportion;

@@ -468,12 +468,17 @@ void t1o_energy_momentum(const B200T1ModelD* m, const T1OEnv* e, double* energy,
 
 /* ---- the decimated PD loop of one env.step (envs/t1.py:439-456) for `nenv` independent envs ---------------------
  * actions [nenv][12] (already clipped), kp/kd/fric [nenv][12], delay [nenv]; last_targets in/out [nenv][12];
- * torques_mean out [nenv][12]. mjcf_mode != 0: play_mujoco.py:751-755 (no delay, no joint friction). */
+ * torques_mean out [nenv][12]. mjcf_mode & 1: play_mujoco.py:751-755 (no delay, no joint friction).  The push acts on the
+ * first substep only (Isaac Gym applies the force tensors of envs/t1.py:522-527 to the next simulate() call); mjcf_mode & 2: on
+ * every substep. */
 int t1o_env_physics(const B200T1ModelD* m, T1OEnv* envs, int nenv, const double* actions, const double* default_q,
                     double action_scale, const double* kp, const double* kd, const double* fric,
                     const double* torque_limit, const int* delay, double* last_targets, const double* push_f,
                     const double* push_t, const T1OTerrain* terr, int decimation, double* torques_mean, int mjcf_mode) {
     int bad = 0;
+    const int push_all = (mjcf_mode & 2) != 0;
+    const double zero3[3] = {0.0, 0.0, 0.0};
+    mjcf_mode &= 1;
 #pragma omp parallel for schedule(static) reduction(+ : bad)
     for (int n = 0; n < nenv; ++n) {
         double tgt[12], tau[12], acc[12];
@@ -491,7 +496,8 @@ int t1o_env_physics(const B200T1ModelD* m, T1OEnv* envs, int nenv, const double*
                 tau[j] = t;
                 acc[j] += t;
             }
-            if (t1o_tick(m, &envs[n], tau, push_f + 3 * n, push_t + 3 * n, terr, 0, 0, 1) != 0) bad += 1;
+            const int pushed = push_all || i == 0;
+            if (t1o_tick(m, &envs[n], tau, pushed ? push_f + 3 * n : zero3, pushed ? push_t + 3 * n : zero3, terr, 0, 0, 1) != 0) bad += 1;
         }
         for (int j = 0; j < 12; ++j) torques_mean[12 * n + j] = acc[j] / decimation;
     }

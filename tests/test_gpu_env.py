@@ -127,7 +127,10 @@ def test_decimated_loop_against_fp64_oracle(t1_cfg):
     a = act.clamp(-1, 1).double().numpy().copy()
     q0 = env.default_dof_pos.cpu().double().numpy().ravel().copy()
     lim = env.torque_limits.cpu().double().numpy().copy()
-    pf = np.zeros((n, 3)); pt = np.zeros((n, 3)); tm = np.zeros((n, 12))
+    # a constant push on the trunk (envs/t1.py:506-527): kernel and oracle apply it on the FIRST substep only
+    pf = np.random.RandomState(0).normal(0.0, 10.0, (n, 3)); pt = np.random.RandomState(1).normal(0.0, 2.0, (n, 3)); tm = np.zeros((n, 12))
+    env.pushing_forces.copy_(torch.from_numpy(pf).float().cuda())
+    env.pushing_torques.copy_(torch.from_numpy(pt).float().cuda())
     terr = op.make_terrain()
     lib = op.lib()
     P = lambda x: x.ctypes.data_as(C.c_void_p)
@@ -145,6 +148,46 @@ def test_decimated_loop_against_fp64_oracle(t1_cfg):
         assert np.abs(np.abs(pos[e, 3:7] @ np.array(arr[e].quat[:])) - 1.0) < 1e-6
         assert np.abs(tq[e] - tm[e]).max() < 1e-3 * max(1.0, np.abs(tm[e]).max())
     assert np.abs(env.last_dof_targets.cpu().double().numpy() - lt).max() < 1e-6
+
+
+@pytest.mark.parametrize("all_substeps", [0, 1])
+def test_push_impulse_of_one_env_step(t1_cfg, all_substeps):
+    """ADVICE r1 / SURVEY 8a note 7: apply_rigid_body_force_tensors is called once per step() (envs/t1.py:522-527) and Isaac Gym
+    applies it to the next simulate() only, so a constant push F (trunk frame) changes the robot's linear momentum by R F dt_sim
+    per env step (1 of the 10 substeps), not by 10x that; `randomization.push_all_substeps: true` is the other reading.  Measured
+    as the momentum difference between pushed and unpushed copies of the same airborne states (FP64 oracle momentum of the
+    GPU state)."""
+    from oracle import physics as op
+
+    n = 16
+    cfg_over = {"randomization__push_all_substeps": bool(all_substeps)}
+    dp = []
+    F = np.random.RandomState(3).normal(0.0, 10.0, (n, 3))
+    Rs = None
+    for pushed in (0, 1):
+        env = make_env(t1_cfg, n, **cfg_over)
+        randomize_state(env, 7, True)
+        env.last_dof_targets.copy_(env.dof_pos)
+        if pushed:
+            env.pushing_forces.copy_(torch.from_numpy(F).float().cuda())
+        if Rs is None:
+            quat = env.root_states[:, 3:7].cpu().double().numpy()
+            Rs = []
+            for x, y, z, w in quat / np.linalg.norm(quat, axis=1, keepdims=True):
+                Rs.append(np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                                    [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                                    [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]]))
+        env.physics(torch.zeros(n, 12, device="cuda"), 10, apply_pd=True)
+        torch.cuda.synchronize()
+        md, oenvs = oracle_envs(env, range(n))
+        dp.append(np.array([op.energy_momentum(md, oe)[1] for oe in oenvs]))
+    dt_sim = 0.002
+    for e in range(n):
+        want = Rs[e] @ F[e] * dt_sim * (10 if all_substeps else 1)
+        got = dp[1][e] - dp[0][e]
+        # the body rotates during the step and the two copies' internal motion differs after the first substep (the discrete
+        # momentum of the articulated system is conserved to O(dt^2) only): 5 % + 3e-4 kg m/s - a factor 10 is what is at stake
+        assert np.abs(got - want).max() <= 0.05 * np.abs(want).max() + 3e-4, (e, got, want)
 
 
 @pytest.mark.parametrize("terrain", ["plane", "trimesh"])
