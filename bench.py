@@ -10,7 +10,8 @@ Prints ONE JSON line (rank 0).  `value` = env-steps/s of the whole job over the 
 resident in HBM; `e2e` = the same loop driven through the public Runner API with the step's synthetic state batch
 uploaded from pinned host memory and the iteration's scalars read back, inside the timed region.  Extra keys give the
 rollout-only rate (the north_star's "env-steps/s incl. policy") and the PPO update time.
-`--impl reference` times the CPU port of the same iteration (oracle/cpu_baseline.py) on the host cores.
+`--impl reference` times the CPU port of the same iteration (oracle/cpu_baseline.py) on the host cores: whole iterations at a
+bounded number of environments, measured as they run.
 """
 import argparse
 import json
@@ -57,37 +58,43 @@ def workload(args):
 def config_dict(args, world):
     return {"workload": workload(args), "num_envs_per_gpu": args.num_envs, "total_envs": args.num_envs * world, "horizon": 24,
             "mini_epochs": 20, "terrain": "plane" if args.config == 1 else "trimesh", "parallelism": f"env-sharded dp{world}",
-            "l2": "working set (the learner streams ~1.9 GB of fp32 activations per epoch through a >400 MB workspace per GPU) is larger than "
+            "l2": "working set (the learner streams ~1.5 GB of fp32 activations per epoch through a >1 GB workspace per GPU) is larger than "
                   "the 126 MB L2; no flush needed",
             "rollout_cuda_graph": bool(args.graphs)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+REF_ENVS = 1024   # environments of the CPU arms' bounded sample (a whole iteration at a quarter of configs[1]'s 4096 envs)
+
+
 def reference_arm(args):
-    """CPU port of the iteration on the host cores; rank 0 only"""
+    """The path's CPU implementation on the host cores (oracle/cpu_baseline.py: the port - neither reference physics engine exists
+    on the box); rank 0 only.  Each step is one WHOLE iteration (24-step rollout incl. policy, physics, post-physics pass +
+    old-dist + 20 epochs) at REF_ENVS environments, timed as it runs: ms_per_step x steps is wall time spent inside this process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cpu_baseline
 
-    vals, parts = [], None
-    for _ in range(max(1, args.warmup if args.warmup < 1 else 0)):
-        pass
-    t_all = time.perf_counter()
-    for k in range(max(1, args.steps)):
-        r = cpu_baseline.iteration_sample(num_envs=args.num_envs, phys_envs=256, phys_steps=2, ppo_epochs=1)
-        vals.append(r)
-        if time.perf_counter() - t_all > 150:
-            break
-    sec = sum(v["seconds_per_iteration"] for v in vals) / len(vals)
-    value = args.num_envs * 24 / sec
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
+    it = cpu_baseline.CpuIteration(num_envs=REF_ENVS)
+    for _ in range(args.warmup):
+        it.iteration()
+    secs, parts = [], None
+    for _ in range(max(1, args.steps)):
+        s_, parts = it.iteration()
+        secs.append(s_)
+    sec = sum(secs) / len(secs)
+    value = REF_ENVS * 24 / sec
+    cfg = config_dict(args, 1)
+    cfg["reference_sample_envs"] = REF_ENVS
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs), "warmup": args.warmup,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "impl": "reference", "config": config_dict(args, 1),
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": vals[0]["cores"], "kind": "port", "sample": vals[0]["sample"]},
+           "data": "synthetic", "impl": "reference", "config": cfg,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": it.cores, "kind": "port", "sample": it.sample_text()},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "one CPU process on rank 0 regardless of --gpus; each step is a bounded sample extrapolated to a full iteration",
-           "parts": vals[0]["parts"]}
+           "note": "one CPU process on rank 0 regardless of --gpus; every step is a whole iteration at the sample's env count, "
+                   "measured, not extrapolated (CPU cost is linear in the number of environments)",
+           "parts_s": parts}
     print(json.dumps(out), flush=True)
 
 
@@ -229,62 +236,99 @@ def b200_arm(args):
     ms_e2e = timed(e2e_iteration, args.steps) / args.steps
     e2e_value = world * N * T / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel family: CUDA events around every GEMM launch (recorded inside the library on
-    # the launching stream), one extra iteration; the family with the largest summed duration is reported
+    # ---- roofline of the dominant kernel family: CUDA events around every launch of the MLP GEMM kernels (recorded inside the
+    # library on the launching stream) during one extra iteration.  SURVEY 8(d) assigns K6 (the MLP contractions) to the TENSOR
+    # roof, so that is `bound`; the HBM side is reported beside it.  Algorithmic figures per sample per epoch from SURVEY 8(d):
+    # 1 005 312 FLOP (fwd 353 536 + bwd 651 776) and 304 B if activations stayed on chip; `traffic_model` is what this
+    # implementation's launches are DESIGNED to move (every operand once, every result once), `traffic` what ncu measured.
     lib.b200_profile_gemm(1)
     iteration()
+    torch.cuda.synchronize(dev)
+    names = {1: ("k_tc_rowmajor", "tcgen05 3xTF32 GEMM, one launch per layer (B200_CHAIN=0 path)"),
+             2: ("k_tc_wgrad", "tcgen05/TMEM/TMA 3xTF32, MN-major operands, in-smem split: the six MLP weight gradients"),
+             3: ("k_mlp_fwd", "fused forward layer chain: 3 hidden layers per launch, activations handed over in TMEM (TS-form tcgen05.mma)"),
+             4: ("k_mlp_bwd", "fused backward layer chain: dz3 -> dz2 -> dz1 + bias gradients per launch")}
     fams = {}
-    names = {0: "k_gemm3x (mma.sync 3xTF32: b200_critic_value only)",
-             1: "k_tc_rowmajor (tcgen05/TMEM/TMA 3xTF32 with in-smem operand split: MLP forward + dgrad, fused bias/ELU/ELU' epilogue)",
-             2: "k_tc_wgrad (tcgen05/TMEM/TMA 3xTF32, MN-major operands, in-smem split: MLP weight gradients)"}
-    fam_bytes = {}
-    for kind in (0, 1, 2):
+    for kind in names:
         ms_g, fl_g, n_g, by_g = C.c_double(), C.c_double(), C.c_int(), C.c_double()
         lib.b200_profile_gemm_read(kind, C.byref(ms_g), C.byref(fl_g), C.byref(n_g))
         lib.b200_profile_gemm_bytes(kind, C.byref(by_g))
-        fams[kind] = (ms_g.value, fl_g.value, n_g.value)
-        fam_bytes[kind] = by_g.value
+        if n_g.value:
+            fams[kind] = {"ms": ms_g.value, "flop": fl_g.value, "launches": n_g.value, "bytes_model": by_g.value}
     lib.b200_profile_gemm(0)
-    top = max(fams, key=lambda k: fams[k][0])
-    ms_top, fl_top, n_top = fams[top]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    achieved = fl_top / (ms_top * 1e-3) / 1e12 if ms_top > 0 else 0.0
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of that family, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(str(top))
+    peak_hbm = peaks.get("hbm_gbs", 6500.0)
+    ncu_traffic = {}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this round
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         pass
-    # the family is bounded by whichever roofline it sits closer to: HBM (fp32 activations in / out, 4 B per element) or the
-    # tensor pipe (measured dense BF16 peak; the 3xTF32 split executes 3x the algorithmic FLOPs at half the BF16 rate)
-    peak_hbm = peaks.get("hbm_gbs", 6500.0)
-    gbs = fam_bytes[top] / (ms_top * 1e-3) / 1e9 if ms_top > 0 else 0.0
-    hbm_bound = gbs / peak_hbm >= achieved / peak_tf
-    roofline = {"kernel": names[top], "bound": "hbm" if hbm_bound else "tensor", "achieved": gbs if hbm_bound else achieved,
-                "peak": peak_hbm if hbm_bound else peak_tf, "unit": "GB/s" if hbm_bound else "TFLOP/s",
-                "frac": gbs / peak_hbm if hbm_bound else achieved / peak_tf, "traffic": traffic,
-                "tensor": {"achieved_tflops": achieved, "peak_tflops": peak_tf, "frac": achieved / peak_tf},
-                "hbm": {"achieved_gbs": gbs, "peak_gbs": peak_hbm, "frac": gbs / peak_hbm, "algorithmic_bytes_per_step": fam_bytes[top]},
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained (measured)" if peaks else "fallback 6.5 TB/s, 1.4 PFLOP/s",
-                "launches_per_step": n_top, "algorithmic_tflop_per_step": fl_top / 1e12, "avg_launch_ms": ms_top / max(1, n_top),
-                "share_of_step": ms_top / ms_step,
-                "families": {names[k].split(" ")[0]: {"ms_per_step": fams[k][0], "algorithmic_tflop": fams[k][1] / 1e12, "launches": fams[k][2],
-                                                      "tflops": (fams[k][1] / (fams[k][0] * 1e-3) / 1e12 if fams[k][0] > 0 else 0.0),
-                                                      "gbs": (fam_bytes[k] / (fams[k][0] * 1e-3) / 1e9 if fams[k][0] > 0 else 0.0)} for k in fams},
-                "note": "algorithmic FLOPs = 2*rows*out*k once per product (the 3-term TF32 split executes 3x that on the tensor pipe); "
-                        "peak is the measured dense BF16 figure (TF32 is nominally half of it)"}
+    top = max(fams, key=lambda k: fams[k]["ms"])
+    M = T * N
+    fam_out = {}
+    for k, f in fams.items():
+        tfl = f["flop"] / (f["ms"] * 1e-3) / 1e12
+        fam_out[names[k][0]] = {"ms_per_step": f["ms"], "launches": f["launches"], "algorithmic_tflop": f["flop"] / 1e12, "tflops": tfl,
+                                "frac_of_bf16_sustained": tfl / peak_tf, "frac_of_3xtf32_ceiling": tfl / (peak_tf / 6.0),
+                                "traffic_model_gbs": f["bytes_model"] / (f["ms"] * 1e-3) / 1e9,
+                                "traffic_model_bytes_per_launch": f["bytes_model"] / f["launches"],
+                                "ncu_dram_bytes_per_launch": ncu_traffic.get(names[k][0])}
+    ft = fams[top]
+    achieved = ft["flop"] / (ft["ms"] * 1e-3) / 1e12
+    all_ms = sum(f["ms"] for f in fams.values())
+    all_fl = sum(f["flop"] for f in fams.values())
+    roofline = {"kernel": f"{names[top][0]} ({names[top][1]})", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": ncu_traffic.get(names[top][0]),
+                "frac_of_3xtf32_ceiling": achieved / (peak_tf / 6.0),
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / hbm_gbs (measured on this pool)" if peaks
+                                else "fallback 1.4 PFLOP/s, 6.5 TB/s (B200_PROFILING.md)"),
+                "launches_per_step": ft["launches"], "algorithmic_flop_per_launch": ft["flop"] / ft["launches"],
+                "avg_launch_ms": ft["ms"] / ft["launches"], "share_of_step": ft["ms"] / ms_step,
+                "hbm": {"algorithmic_bytes_per_sample_epoch": 304, "algorithmic_bytes_per_step": 304.0 * M * E,
+                        "traffic_model_bytes_per_step": sum(f["bytes_model"] for f in fams.values()),
+                        "traffic_model_gbs_all_mlp_kernels": sum(f["bytes_model"] for f in fams.values()) / (all_ms * 1e-3) / 1e9,
+                        "peak_gbs": peak_hbm},
+                "all_mlp_kernels": {"ms_per_step": all_ms, "algorithmic_tflop_per_step": all_fl / 1e12, "tflops": all_fl / (all_ms * 1e-3) / 1e12,
+                                    "frac_of_bf16_sustained": all_fl / (all_ms * 1e-3) / 1e12 / peak_tf,
+                                    "share_of_step": all_ms / ms_step},
+                "families": fam_out,
+                "note": "algorithmic FLOPs = 2*rows*out*k once per product; the fp32-accurate 3-term TF32 split EXECUTES 3x that at the TF32 "
+                        "rate (half of BF16), so 1/6 of the BF16 peak is the ceiling of this arithmetic class (frac_of_3xtf32_ceiling)"}
+
+    # ---- k_physics against the MEASURED FP32 FMA peak (FP32-pipe roofline, measured on the box)
+    fma = C.c_double()
+    lib.b200_fma_peak(C.byref(fma), stream.cuda_stream)
+    FLOP_TICK = 13218.0   # tools/count_flops.py (instrumented exact count, standing robot; frozen in BASELINE.md section 5)
+    act0 = torch.zeros(N, 12, device=dev)
+    for _ in range(3):
+        env.physics(act0, 10, apply_pd=True)
+    torch.cuda.synchronize(dev)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record(stream)
+    for _ in range(20):
+        env.physics(act0, 10, apply_pd=True)
+    pe1.record(stream)
+    torch.cuda.synchronize(dev)
+    phys_ms = pe0.elapsed_time(pe1) / 20
+    phys_tf = FLOP_TICK * 10 * N / (phys_ms * 1e-3) / 1e12
+    roofline["k_physics"] = {"bound": "fp32", "avg_launch_ms": phys_ms, "flop_per_env_tick": FLOP_TICK, "achieved_tflops": phys_tf,
+                             "peak_tflops_measured_fma": fma.value, "frac": phys_tf / fma.value if fma.value > 0 else None,
+                             "note": "one launch = 10 ticks of every env; latency-bound at this env count (2 lanes per env, 1 warp per CTA)"}
+    exchange = "none" if world == 1 else ("peer" if lrn.peers_bound else "nccl")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import cpu_baseline
 
-            r = cpu_baseline.iteration_sample(num_envs=N, phys_envs=256, phys_steps=2, ppo_epochs=1)
-            cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            r = cpu_baseline.iteration_sample(num_envs=REF_ENVS, iterations=1, warmup=1)
+            cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                   "seconds_per_iteration_at_sample_size": r["seconds_per_iteration"], "parts_s": r["parts"]}
         except Exception as ex:  # the baseline is informational; never lose the GPU number because of it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
@@ -295,7 +339,7 @@ def b200_arm(args):
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "rollout_env_steps_per_s": world * N * T / (ms_roll * 1e-3), "rollout_ms": ms_roll, "ppo_update_ms": ms_upd,
-               "ppo_iteration_ms": ms_step}
+               "ppo_iteration_ms": ms_step, "exchange": exchange, "mlp_path": "chain" if os.environ.get("B200_CHAIN", "1") != "0" else "layers"}
         print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

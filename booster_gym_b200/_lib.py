@@ -61,6 +61,7 @@ PROTOTYPES = {
     "b200_profile_gemm_read": (_i, [_i, C.POINTER(_d), C.POINTER(_d), _ip]),
     "b200_profile_gemm_bytes": (_i, [_i, C.POINTER(_d)]),
     "b200_tc_set_pair": (_i, [_i]),
+    "b200_fma_peak": (_i, [C.POINTER(_d), _vp]),
     "b200_tc_set_chain": (_i, [_i]),
 }
 

@@ -30,7 +30,10 @@ class Learner:
         self.scalars = torch.zeros(_abi.SC["COUNT"], dtype=torch.float32, device=dev)
         self.dstats = torch.zeros(_abi.DS["COUNT"], dtype=torch.float64, device=dev)
         ws_bytes = self._lib.b200_ppo_workspace_bytes(self.horizon, self.num_envs)
-        self.workspace = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        # the library needs a 1 KiB-aligned workspace (TMA / 128-byte swizzle); the caching allocator only promises 512 B
+        self._workspace_raw = torch.empty(ws_bytes // 4 + 256, dtype=torch.float32, device=dev)
+        off = (-self._workspace_raw.data_ptr() % 1024) // 4
+        self.workspace = self._workspace_raw[off:off + ws_bytes // 4]
         M = self.horizon * self.num_envs
         self.old_mu = torch.empty(M, 12, dtype=torch.float32, device=dev)
         self.old_logp = torch.empty(M, dtype=torch.float32, device=dev)
@@ -50,8 +53,8 @@ class Learner:
     def bind_peers(self, group=None):
         """Multi-GPU: exchange advantage moments / gradients / loss sums over NVLink peer memory inside the library's own kernels
         (b200_ppo_bind_peers) instead of three NCCL all-reduces per epoch.  Needs torch.distributed (NCCL) initialised and a
-        symmetric-memory allocation peer-mapped across the node's ranks.  Returns False (and leaves the NCCL protocol of
-        Runner.update in charge) if symmetric memory is unavailable."""
+        symmetric-memory allocation peer-mapped across the node's ranks.  Raises if the buffers cannot be bound (no silent NCCL
+        fall-back: B200_PEER_EXCHANGE=0 selects that protocol explicitly); returns False only for single-process runs."""
         import torch.distributed as dist
 
         if self.world_size <= 1 or not dist.is_initialized():
@@ -73,11 +76,11 @@ class Learner:
             _lib.check(self._lib.b200_ppo_bind_peers(self._h, arr, int(hdl.rank), len(ptrs)), "b200_ppo_bind_peers")
             self._peer_buf, self._peer_hdl = buf, hdl
             self.peers_bound = True
-        except Exception as ex:  # noqa: BLE001 - any failure keeps the (slower) NCCL protocol
-            import warnings
-
-            warnings.warn(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL all-reduce")
-            self.peers_bound = False
+        except Exception as ex:  # noqa: BLE001
+            # A silent fall-back would make a scaling run unable to say which data plane it measured: failing to bind is an
+            # error.  The NCCL protocol of Runner.update is selected explicitly with B200_PEER_EXCHANGE=0.
+            raise _lib.B200Error(f"peer-memory gradient exchange could not be bound ({type(ex).__name__}: {ex}); "
+                                 f"set B200_PEER_EXCHANGE=0 to run the NCCL all-reduce protocol instead") from ex
         # all ranks must agree, otherwise the lockstep protocol deadlocks
         flag = torch.tensor([1 if self.peers_bound else 0], device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)

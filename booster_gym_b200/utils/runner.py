@@ -99,7 +99,7 @@ class Runner:
         if self.world_size > 1:
             torch.distributed.broadcast(self.learner.params, src=0)
             if os.environ.get("B200_PEER_EXCHANGE", "1") != "0":
-                self.learner.bind_peers()   # NVLink peer-memory exchange inside the learner kernels (falls back to NCCL)
+                self.learner.bind_peers()   # NVLink peer-memory exchange inside the learner kernels (raises if it cannot be bound)
         self.optimizer = FlatAdam(self.model, self.learner)
         self._load()
 
@@ -235,7 +235,9 @@ class Runner:
                 torch.distributed.all_reduce(lrn.dstats[4:10])
             lrn.apply()
 
-    def train(self):
+    def train(self, on_iteration=None):
+        """utils/runner.py:99-215.  `on_iteration(it, episode_means, episode_count, scalars)` (not in the reference surface) is
+        called once per iteration with what the Recorder is fed - tools/learning_curve.py and the learning test use it."""
         self.recorder = Recorder(self.cfg) if self.rank == 0 else None
         obs, infos = self.env.reset()
         privileged_obs = infos["privileged_obs"]
@@ -261,6 +263,8 @@ class Runner:
             kl_mean = sc[SC["KL"]].item()
             ep_means, ep_count = self.env.episode_stats()
             self.env.common_step_counter = self.env.counters()[1]
+            if on_iteration is not None:
+                on_iteration(it, ep_means, ep_count, sc)
             if self.recorder is not None:
                 self.recorder.record_episode_summary(ep_means, ep_count, it)
                 self.recorder.record_statistics(

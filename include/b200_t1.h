@@ -315,6 +315,9 @@ int b200_profile_gemm_bytes(int kind, double* total_bytes);
  * (clusters of 2, tcgen05 cta_group::2, 256-row tiles, each CTA stages half of the weight tile).  Same results; the pair
  * variant halves the per-CTA L2 -> shared-memory weight traffic but measured ~4 % slower on this shape. */
 int b200_tc_set_pair(int enable);
+/* measured FP32 FMA throughput of the current device in TFLOP/s (FMA = 2 FLOP): 8 independent chains per thread, 8 CTAs of 256
+ * threads per SM, best of 5 launches timed with CUDA events on `stream`.  Roofline denominator of k_physics. */
+int b200_fma_peak(double* tflops, void* stream);
 /* hidden layers of the PPO epoch: 1 (default) = fused layer chains (mlp_chain.cuh: one persistent tcgen05 kernel per direction,
  * activations handed from layer to layer in TMEM), 0 = one GEMM launch per layer (k_tc_rowmajor).  Same results within the
  * stated tolerances; replaces the autograd graph of utils/runner.py:132-133,148,163. */
