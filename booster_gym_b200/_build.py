@@ -36,7 +36,7 @@ def _nvcc():
 
 
 def _deps():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "b200_t1.h")]
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [os.path.join(ROOT, "include", "b200_t1.h")]
 
 
 def _stale(target, sources):
@@ -46,11 +46,51 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash():
+    """content hash of everything the library is built from (+ the flags): file times do not survive a repo snapshot, contents do"""
+    import hashlib
+
+    h = hashlib.sha256()
+    for path in sorted(_deps()):
+        if os.path.isfile(path):
+            h.update(os.path.basename(path).encode())
+            h.update(open(path, "rb").read())
+    h.update(" ".join(ARCH + COMMON).encode())
+    return h.hexdigest()
+
+
+def up_to_date():
+    """True if libb200t1.so exists and was built from exactly the sources in the tree"""
+    try:
+        return os.path.exists(LIB) and open(STAMP).read().strip() == source_hash()
+    except OSError:
+        return False
+
+
+def build_locked(verbose=False):
+    """build() under an inter-process file lock (torchrun ranks of a fresh checkout all arrive here at once); the library is
+    linked into a temporary file and renamed into place, so nobody can dlopen a half-written file"""
+    import fcntl
+
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    with open(os.path.join(ROOT, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if up_to_date():
+                return LIB
+            return build(force=False, verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 def build(force=False, verbose=False, ptxas_info=False):
     """Compile every CUDA translation unit for sm_100a and link libb200t1.so. Returns the library path."""
     units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u))]
     deps = _deps()
-    if not force and not _stale(LIB, deps):
+    if not force and not _stale(LIB, deps) and up_to_date():
         return LIB
     nv = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -72,10 +112,15 @@ def build(force=False, verbose=False, ptxas_info=False):
             sys.stdout.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {u}")
-    cmd = [nv] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nv] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", tmp] + objs
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
+    with open(STAMP + ".tmp", "w") as f:
+        f.write(source_hash())
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 

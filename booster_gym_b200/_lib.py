@@ -80,10 +80,15 @@ def load(build_if_missing=True):
     if _LIB is not None:
         return _LIB
     path = _build.LIB
-    if not os.path.exists(path):
+    if not _build.up_to_date():
+        # missing, or built from other sources than the tree holds (a stale library would be loaded silently otherwise): rebuild
+        # under a file lock - concurrent ranks wait for the first one.  Without nvcc a stale library is an error, never a fallback.
         if not build_if_missing:
-            raise B200Error(f"{path} is missing (no CPU fallback exists; run `python -m booster_gym_b200._build`)")
-        _build.build()
+            raise B200Error(f"{path} is missing or stale (no CPU fallback exists; run `python -m booster_gym_b200._build`)")
+        try:
+            _build.build_locked()
+        except RuntimeError as e:
+            raise B200Error(f"{path} is missing or stale and cannot be rebuilt here: {e}") from e
     lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         try:

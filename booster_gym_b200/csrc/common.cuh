@@ -12,6 +12,17 @@
 namespace b200 {
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember which devices a kernel has been configured on
+// (a process may create learners / envs on several devices)
+template <typename K> inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, unsigned long long& device_mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((device_mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) device_mask |= 1ull << dev;
+    return e;
+}
 inline int launch_status(const char* what) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { cudaGetLastError(); return set_cuda_error(e, what); }

@@ -27,6 +27,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 #include <map>
 #include <tuple>
 
@@ -784,11 +786,10 @@ inline cudaError_t launch_rowmajor(const CUtensorMap* A, const CUtensorMap* Bh, 
                                    cudaStream_t st) {
     using S = RowSmem<BN, NA, NB, PAIR>;
     static_assert(S::TOTAL <= 232448, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(k_tc_rowmajor<BN, NA, NB, EPI, NACC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    static unsigned long long configured = 0;   // per-device bit mask
+    {
+        const cudaError_t e = ensure_dynamic_smem(k_tc_rowmajor<BN, NA, NB, EPI, NACC, PAIR>, S::TOTAL, configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int tm = PAIR ? 2 * BM : BM;
     const int tiles = ((g.M + tm - 1) / tm) * ((g.Nout + BN - 1) / BN);
@@ -817,11 +818,10 @@ inline cudaError_t launch_rowmajor(const CUtensorMap* A, const CUtensorMap* Bh, 
 template <int BN, int STAGES, int WBK>
 inline cudaError_t launch_wgrad(const CUtensorMap* Y, const CUtensorMap* X, const WgradArgs& g, int kin_padded, cudaStream_t st) {
     constexpr int SMEM = STAGES * (2 * BM * WBK * 4 + 2 * BN * WBK * 4) + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad<BN, STAGES, WBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    static unsigned long long configured = 0;   // per-device bit mask
+    {
+        const cudaError_t e = ensure_dynamic_smem(k_tc_wgrad<BN, STAGES, WBK>, SMEM, configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     dim3 grid((g.M + g.chunk - 1) / g.chunk, (g.Nout + BM - 1) / BM, (kin_padded + BN - 1) / BN);
     k_tc_wgrad<BN, STAGES, WBK><<<grid, WG_THREADS, SMEM, st>>>(*Y, *X, g);

@@ -1306,12 +1306,9 @@ int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* 
     NEED_PPO(p);
     if (!obs || !actions || n <= 0) return set_error(B200_ERR_ARG, "b200_policy_act: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    static bool configured = false;
+    static unsigned long long configured = 0;   // per-device bit mask
     constexpr int SMEM = PF_SMEM_FLOATS * (int)sizeof(float);
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_policy_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = true;
-    }
+    CUDA_TRY(ensure_dynamic_smem(k_policy_fused, SMEM, configured));
     const bool auto_step = (step == B200_STEP_AUTO);
     PolicyFusedArgs a{};
     a.obs = obs;

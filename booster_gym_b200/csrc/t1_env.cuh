@@ -788,28 +788,33 @@ B200_HD void env_init_params(const EnvView& v, int e, const Model& m, const B200
         }
     }
     for (int b = 0; b < B200_NB; ++b) {
+        // CoM and mass may be configured with DIFFERENT distribution kinds: a uniform and a normal of one Philox block share words
+        // (rng.cuh: u[i] and n[i] both read word i), so the mass draws from its own block
         const Rand4 r = rand4(rng_words(v.seed, ge, 0, RP_INIT_BODY, b));
+        const Rand4 rmass = rand4(rng_words(v.seed, ge, 0, RP_INIT_BODY, 16 + b));
         const B200Rand& rc = (b == 0) ? c.base_com : c.other_com;
         const B200Rand& rm = (b == 0) ? c.base_mass : c.other_mass;
 #pragma unroll
         for (int k = 0; k < 3; ++k) FS(F_body_com + 3 * b + k) = apply_rand((float)m.ipos[b][k], rc, r.u[k], r.n[k]);
-        FS(F_body_mass + b) = apply_rand((float)m.mass[b], rm, r.u[3], r.n[3]);
+        FS(F_body_mass + b) = apply_rand((float)m.mass[b], rm, rmass.u[0], rmass.n[0]);
         if (b == 0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) FS(F_base_mass_scaled + k) = rc.enabled ? raw_rand(rc, r.u[k], r.n[k]) : 0.0f;
-            FS(F_base_mass_scaled + 3) = rm.enabled ? raw_rand(rm, r.u[3], r.n[3]) : 0.0f;
+            FS(F_base_mass_scaled + 3) = rm.enabled ? raw_rand(rm, rmass.u[0], rmass.n[0]) : 0.0f;
         }
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const Rand4 r = rand4(rng_words(v.seed, ge, 0, RP_INIT_FOOT, k));
+        const Rand4 r = rand4(rng_words(v.seed, ge, 0, RP_INIT_FOOT, k));        // friction
+        const Rand4 r2 = rand4(rng_words(v.seed, ge, 0, RP_INIT_FOOT, 2 + k));   // compliance   (own blocks: the three keys may be
+        const Rand4 r3 = rand4(rng_words(v.seed, ge, 0, RP_INIT_FOOT, 4 + k));   // restitution   configured with different kinds)
         // PhysX material of the foot shapes (envs/t1.py:162-167): friction is combined with the ground by averaging
         // (PhysX default combine mode); compliance / restitution scale this build's contact spring / damper.
         const float mu_foot = c.friction.enabled ? apply_rand(0.0f, c.friction, r.u[0], r.n[0]) : c.terrain_friction;
         FS(F_foot_friction + k) = 0.5f * (mu_foot + c.terrain_friction);
-        const float comp = c.compliance.enabled ? apply_rand(0.0f, c.compliance, r.u[1], r.n[1]) : 1.0f;
+        const float comp = c.compliance.enabled ? apply_rand(0.0f, c.compliance, r2.u[0], r2.n[0]) : 1.0f;
         FS(F_foot_kscale + k) = 1.0f / fmaxf(comp, 0.1f);
-        const float rest = c.restitution.enabled ? apply_rand(0.0f, c.restitution, r.u[2], r.n[2]) : 0.0f;
+        const float rest = c.restitution.enabled ? apply_rand(0.0f, c.restitution, r3.u[0], r3.n[0]) : 0.0f;
         FS(F_foot_cscale + k) = 1.0f - 0.5f * fminf(fmaxf(rest, 0.0f), 1.0f);
     }
     // _init_buffers :193-272 (the values a freshly created sim reports: identity pose at the env origin, at rest)
