@@ -121,6 +121,7 @@ struct B200Ppo {
     tc::MapCache* maps;           // TMA tensor maps of the (fixed) workspace buffers, built lazily on first use
     int num_sms;
     bool chain_fwd_configured = false, chain_bwd_configured = false;   // per-handle (= per-device) dynamic shared memory opt-in
+    bool actor_fwd_done = false;   // epoch_a ran the actor forward together with the critic's (one fused-chain launch)
     float* P(int i) const { return params + kParams[i].offset; }
     float* G(int i) const { return grads + kParams[i].offset; }
 };
@@ -926,6 +927,7 @@ struct GemmProfile {
 
 static bool g_tc_pair = getenv("B200_TC_PAIR") ? atoi(getenv("B200_TC_PAIR")) != 0 : false;   // cta_group::2 GEMMs (b200_tc_set_pair)
 static bool g_chain_exact_actor = getenv("B200_CHAIN_EXACT_ELU") ? atoi(getenv("B200_CHAIN_EXACT_ELU")) != 0 : false;   // expm1f in the actor chain
+static bool g_chain_pair = getenv("B200_CHAIN_PAIR") ? atoi(getenv("B200_CHAIN_PAIR")) != 0 : false;   // chains on CTA pairs (cta_group::2)
 static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
 static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
@@ -1113,12 +1115,13 @@ static int chain_fill_fwd(const B200Ppo* p, chain::FwdNet& N, const ChainNetPtrs
     if (c.rows <= 0) { N.rows = 0; return B200_OK; }
     TC_MAP(mXh, c.Xh, c.rows, 64, 64, tc::BM, true);
     TC_MAP(mXl, c.Xl, c.rows, 64, 64, tc::BM, true);
-    TC_MAP(mW1h, c.W1h, 256, 64, 64, 256, true);
-    TC_MAP(mW1l, c.W1l, 256, 64, 64, 256, true);
-    TC_MAP(mW2h, c.W2h, c.n2, 256, 256, c.n2, true);
-    TC_MAP(mW2l, c.W2l, c.n2, 256, 256, c.n2, true);
-    TC_MAP(mW3h, c.W3h, 128, c.n2, c.n2, 128, true);
-    TC_MAP(mW3l, c.W3l, 128, c.n2, c.n2, 128, true);
+    const int pd = g_chain_pair ? 2 : 1;   // CTA pairs: each CTA stages half of the rows of a weight k-block
+    TC_MAP(mW1h, c.W1h, 256, 64, 64, 256 / pd, true);
+    TC_MAP(mW1l, c.W1l, 256, 64, 64, 256 / pd, true);
+    TC_MAP(mW2h, c.W2h, c.n2, 256, 256, c.n2 / pd, true);
+    TC_MAP(mW2l, c.W2l, c.n2, 256, 256, c.n2 / pd, true);
+    TC_MAP(mW3h, c.W3h, 128, c.n2, c.n2, 128 / pd, true);
+    TC_MAP(mW3l, c.W3l, 128, c.n2, c.n2, 128 / pd, true);
     N.mXh = *mXh; N.mXl = *mXl; N.mW1h = *mW1h; N.mW1l = *mW1l; N.mW2h = *mW2h; N.mW2l = *mW2l; N.mW3h = *mW3h; N.mW3l = *mW3l;
     N.b1 = c.b1; N.b2 = c.b2; N.b3 = c.b3; N.H1 = c.H1; N.H2 = c.H2; N.H3 = c.H3;
     return B200_OK;
@@ -1133,6 +1136,32 @@ static ChainNetPtrs actor_ptrs(const B200Ppo* p, int rows) {
     return ChainNetPtrs{ws + w.Xah, ws + w.Xal, ws + w.Wa0h, ws + w.Wa0l, ws + w.Wa1h, ws + w.Wa1l, ws + w.Wa2h, ws + w.Wa2l,
                         p->P(P_AB0), p->P(P_AB1), p->P(P_AB2), ws + w.A1, ws + w.A2, ws + w.A3, rows, 128, g_chain_exact_actor ? 1 : 0, 47};
 }
+// one persistent CTA per SM, or (pair) one cluster of two CTAs per TPC
+template <typename Params>
+static cudaError_t chain_launch(void (*kernel)(const Params), const Params& P, int rows0, int rows1, int threads, int smem, bool pair,
+                                int num_sms, cudaStream_t st) {
+    const int tm = pair ? 2 * tc::BM : tc::BM;
+    const int tiles = (rows0 + tm - 1) / tm + (rows1 + tm - 1) / tm;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    if (pair) {
+        const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+        cfg.gridDim = dim3(2 * pairs);
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
+    }
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    return cudaLaunchKernelEx(&cfg, kernel, P);
+}
+
 static int chain_forward(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs& c1, cudaStream_t st) {
     chain::FwdParams P;
     memset(&P, 0, sizeof(P));
@@ -1142,7 +1171,8 @@ static int chain_forward(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs&
     const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
     if (tiles <= 0) return B200_OK;
     if (!p->chain_fwd_configured) {
-        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::F_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::F_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::F_SMEM));
         p->chain_fwd_configured = true;
     }
     double fl = 0.0, by = 0.0;
@@ -1153,9 +1183,11 @@ static int chain_forward(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs&
         by += 4.0 * r * (2 * 64 + 256 + cs[i]->n2 + 128);   // X hi + lo read; h1, h2, h3 written
     }
     prof_begin(st, fl, PK_CHAIN_FWD, by);
-    chain::k_mlp_fwd<<<tiles < p->num_sms ? tiles : p->num_sms, chain::F_THREADS, chain::F_SMEM, st>>>(P);
+    const cudaError_t le = g_chain_pair ? chain_launch(chain::k_mlp_fwd<1>, P, P.net[0].rows, P.net[1].rows, chain::F_THREADS, chain::F_SMEM, true, p->num_sms, st)
+                                        : chain_launch(chain::k_mlp_fwd<0>, P, P.net[0].rows, P.net[1].rows, chain::F_THREADS, chain::F_SMEM, false, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
+    if (le != cudaSuccess) return set_cuda_error(le, "k_mlp_fwd");
     return launch_status("k_mlp_fwd");
 }
 // both nets' hidden-layer input gradients + bias gradients: dz3 (from the head kernels) -> dz2, dz1
@@ -1179,10 +1211,10 @@ static int chain_backward(B200Ppo* p, int M, bool critic, bool actor, cudaStream
         TC_MAP(mZ3, Z3, M, 128, 128, tc::BM, true);
         TC_MAP(mH2, H2, M, N.n2, N.n2, tc::BM, true);
         TC_MAP(mH1, H1, M, 256, 256, tc::BM, true);
-        TC_MAP(mW3Th, W3Th, N.n2, 128, 128, N.n2, true);
-        TC_MAP(mW3Tl, W3Tl, N.n2, 128, 128, N.n2, true);
-        TC_MAP(mW2Th, W2Th, 256, N.n2, N.n2, 256, true);
-        TC_MAP(mW2Tl, W2Tl, 256, N.n2, N.n2, 256, true);
+        TC_MAP(mW3Th, W3Th, N.n2, 128, 128, g_chain_pair ? N.n2 / 2 : N.n2, true);
+        TC_MAP(mW3Tl, W3Tl, N.n2, 128, 128, g_chain_pair ? N.n2 / 2 : N.n2, true);
+        TC_MAP(mW2Th, W2Th, 256, N.n2, N.n2, g_chain_pair ? 64 : 256, true);   // pairs: 64 rows of each 128-column output half per CTA
+        TC_MAP(mW2Tl, W2Tl, 256, N.n2, N.n2, g_chain_pair ? 64 : 256, true);
         N.mZ3 = *mZ3; N.mH2 = *mH2; N.mH1 = *mH1; N.mW3Th = *mW3Th; N.mW3Tl = *mW3Tl; N.mW2Th = *mW2Th; N.mW2Tl = *mW2Tl;
         N.DZ2 = ws + (i == 0 ? w.GC2 : w.GA2);
         N.DZ1 = ws + (i == 0 ? w.GC1 : w.GA1);
@@ -1194,13 +1226,16 @@ static int chain_backward(B200Ppo* p, int M, bool critic, bool actor, cudaStream
     const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
     if (tiles <= 0) return B200_OK;
     if (!p->chain_bwd_configured) {
-        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::B_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::B_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(chain::k_mlp_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::B_SMEM));
         p->chain_bwd_configured = true;
     }
     prof_begin(st, fl, PK_CHAIN_BWD, by);
-    chain::k_mlp_bwd<<<tiles < p->num_sms ? tiles : p->num_sms, chain::B_THREADS, chain::B_SMEM, st>>>(P);
+    const cudaError_t le = g_chain_pair ? chain_launch(chain::k_mlp_bwd<1>, P, P.net[0].rows, P.net[1].rows, chain::B_THREADS, chain::B_SMEM, true, p->num_sms, st)
+                                        : chain_launch(chain::k_mlp_bwd<0>, P, P.net[0].rows, P.net[1].rows, chain::B_THREADS, chain::B_SMEM, false, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
+    if (le != cudaSuccess) return set_cuda_error(le, "k_mlp_bwd");
     return launch_status("k_mlp_bwd");
 }
 
@@ -1385,7 +1420,15 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
         k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(
             last_obs, last_priv, N, PackOut{nullptr, nullptr, nullptr, ws + p->w.Xc + o, ws + p->w.Xch + o, ws + p->w.Xcl + o});
     }
-    if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
+    if (g_chain) {
+        // both nets in ONE persistent launch: 800 critic + 768 actor tiles balance over the SMs better than two launches of ~5.3
+        // waves each; the actor's mu is not needed before epoch_b's loss
+        if ((rc = chain_forward(p, critic_ptrs(p, M + N), actor_ptrs(p, M), st)) != B200_OK) return rc;
+        k_value_head<<<(int)(((size_t)(M + N) * 32 + 255) / 256), 256, 0, st>>>(ws + p->w.C3, p->P(P_CW3), p->P(P_CB3), M + N, ws + p->w.V);
+        k_actor_head<<<1184, 256, 0, st>>>(ws + p->w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + p->w.MU);
+        g_launches += 2;
+        p->actor_fwd_done = true;
+    } else if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
     k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
     g_launches += 3;  // memset, k_pack_inputs, k_gae
@@ -1407,8 +1450,9 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     float *MU = ws + w.MU, *DV = ws + w.DV, *DMU = ws + w.DMU;
     float *G1 = ws + w.G1, *G2 = ws + w.G2;
     WgradJobs jobs{};
-    int rc = actor_forward_tc(p, M, st);
-    if (rc != B200_OK) return rc;
+    int rc = B200_OK;
+    if (!p->actor_fwd_done && (rc = actor_forward_tc(p, M, st)) != B200_OK) return rc;
+    p->actor_fwd_done = false;
     CUDA_TRY(cudaMemsetAsync(p->grads, 0, NPARAMS_PADDED * sizeof(float), st));
     if (p->peers) {   // global advantage normalisation (utils/runner.py:145 over all ranks' samples)
         k_xchg_reduce_stats<<<1, 32, 0, st>>>(p->px, p->dstats, (int)(p->seq_stat & 1u), p->seq_stat);
@@ -1510,6 +1554,7 @@ int b200_tc_set_pair(int enable) {
 }
 int b200_tc_set_chain(int enable) {
     g_chain = enable != 0;
+    g_chain_pair = enable == 2;
     return B200_OK;
 }
 

@@ -77,10 +77,66 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// PAIR = 1 (cta_group::2): a cluster of two CTAs (the two SMs of a TPC) works on 256 rows.  Each CTA keeps ITS 128 rows' accumulators
+// / A operands in its own TMEM and lo ring and stages HALF of every weight k-block; the leader CTA issues the MMAs (M = 256), the
+// tensor cores exchange the weight halves.  Per-CTA shared-memory traffic of the weight operand - the measured limiter of the
+// single-CTA kernel (3 MMAs per k-step each re-read the whole tile: ~125-150 B/clk needed of 128 B/clk) - halves.
+template <int PAIR> __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma_tf32_pair(d, da, db, idesc, acc); else umma_tf32(d, da, db, idesc, acc);
+}
+template <int PAIR> __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma_tf32_ts_pair(d, a, db, idesc, acc); else umma_tf32_ts(d, a, db, idesc, acc);
+}
+template <int PAIR> __device__ __forceinline__ void commit(uint64_t* bar) {   // PAIR: arrives on `bar` in BOTH CTAs
+    if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+}
+// wait on a barrier of the leader CTA that also collects arrivals / TMA bytes of the peer CTA
+template <int PAIR> __device__ __forceinline__ void wait_collect(uint64_t* b, uint32_t parity, int code) {
+    if (!PAIR) { mbar_wait_wd(b, parity, code); return; }
+    uint32_t done;
+    const uint32_t a = smem_u32(b);
+    const long long t0 = clock64();
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) {
+            atomicExch(&g_chain_error, (unsigned)code);
+            printf("mlp_chain watchdog: block %d thread %d cluster barrier code %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, code, parity);
+            __trap();
+        }
+    } while (!done);
+}
+// producer side of such a barrier: the leader announces the bytes of BOTH CTAs, the peer only arrives
+template <int PAIR> __device__ __forceinline__ void expect_collect(uint64_t* bar, uint32_t bytes_per_cta, uint32_t rank) {
+    if (!PAIR) { mbar_expect_tx(bar, bytes_per_cta); return; }
+    if (rank == 0) mbar_expect_tx(bar, 2 * bytes_per_cta); else mbar_arrive_leader(bar);
+}
+template <int PAIR> __device__ __forceinline__ void tma_collect(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1) {
+    if (PAIR) tma_load_2d_pair(map, bar, dst, c0, c1); else tma_load_2d(map, bar, dst, c0, c1);
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {   // results are valid after tmem_wait_ld()
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ... and the compiler must not read the registers of an outstanding tcgen05.ld before the wait: tie them to it
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t* r, uint32_t* q) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]) :: "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -92,9 +148,10 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // more (expensive) net-0 tile get one less net-1 tile.  Every warp role walks the same sequence.
 struct TileSeq {
     int nt0, nt1, G, cta, net, idx;
-    __device__ TileSeq(int rows0, int rows1) {
-        nt0 = (rows0 + BM - 1) / BM; nt1 = (rows1 + BM - 1) / BM;
-        G = (int)gridDim.x; cta = (int)blockIdx.x; net = 0; idx = cta;
+    __device__ TileSeq(int rows0, int rows1, int pair = 0) {   // pair: 256-row tiles, one worker per cluster of two CTAs
+        const int tm = pair ? 2 * BM : BM;
+        nt0 = (rows0 + tm - 1) / tm; nt1 = (rows1 + tm - 1) / tm;
+        G = (int)gridDim.x >> pair; cta = (int)blockIdx.x >> pair; net = 0; idx = cta;
     }
     __device__ bool next(int& n, int& tile) {
         while (net < 2) {
@@ -121,12 +178,12 @@ __device__ __forceinline__ void publish_slice(const float* v, uint32_t taddr, ui
     sts_v4(rbase + ((((uint32_t)(2 * g)) ^ sw) << 4), make_float4(lo[0], lo[1], lo[2], lo[3]));
     sts_v4(rbase + ((((uint32_t)(2 * g + 1)) ^ sw) << 4), make_float4(lo[4], lo[5], lo[6], lo[7]));
 }
-__device__ __forceinline__ void publish_done(uint64_t* bar, int lane) {
+__device__ __forceinline__ void publish_done(uint64_t* bar, int lane, bool to_leader = false) {
     tmem_wait_st();
     fence_async_smem();                                   // generic-proxy lo writes -> visible to the tensor core's reads
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+    if (lane == 0) { if (to_leader) mbar_arrive_leader(bar); else mbar_arrive(bar); }
 }
 
 // =====================================================================================================================
@@ -151,48 +208,58 @@ static constexpr int F_X_HI = 0, F_X_LO = 2 * KB_BYTES, F_B = 4 * KB_BYTES, F_LO
                      F_BAR = F_LO + F_LO_STAGES * KB_BYTES, F_SMEM = F_BAR + 256 + 1024;
 static_assert(F_SMEM <= 232448, "shared memory budget");
 
-// ELU in 5 instructions: x > 0 ? x : ex2.approx(x log2 e) - 1.  ABSOLUTE error <= ~3e-7 (2 ulp of ex2.approx around 1 plus the
-// rounding of the scaled argument) - a few fp32 ulps of the O(1) activations, unlike expm1f it is not small RELATIVE to tiny
-// outputs, which no consumer needs: h only enters dot products and ELU' = h + 1.  exact = 1 keeps expm1f (~30 instructions).
-__device__ __forceinline__ float elu_sel(float x, int exact) {
-    if (exact) return (x > 0.0f) ? x : expm1f(x);
+// ELU in 5 straight-line instructions: x > 0 ? x : ex2.approx(x log2 e) - 1.  ABSOLUTE error <= ~3e-7 (2 ulp of ex2.approx around 1
+// plus the rounding of the scaled argument) - a few fp32 ulps of the O(1) activations; unlike expm1f it is not small RELATIVE to tiny
+// outputs, which no consumer needs: h only enters dot products and ELU' = h + 1.  No branches: a run-time "exact" switch put every
+// element into its own basic block (BSSY / BSYNC) and serialised the eight MUFU latencies of a slice (measured: the epilogue's
+// tcgen05.ld + bias + ELU part was 55 % of the kernel).
+__device__ __forceinline__ float elu_sel(float x, int) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
     return (x > 0.0f) ? x : (e - 1.0f);
 }
 
+template <int PAIR>
 __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* x_full = (uint64_t*)(smem + F_BAR);
+    uint64_t* x_full = (uint64_t*)(smem + F_BAR);   // (PAIR: the leader's copy collects both CTAs' tiles)
     uint64_t* x_empty = x_full + 1;
-    uint64_t* b_full = x_empty + 1;          // [NUNITS]
+    uint64_t* b_full = x_empty + 1;          // [NUNITS]   (PAIR: leader's copy collects both CTAs' halves)
     uint64_t* b_empty = b_full + NUNITS;     // [NUNITS]
-    uint64_t* lo_full = b_empty + NUNITS;    // [F_LO_STAGES]
+    uint64_t* lo_full = b_empty + NUNITS;    // [F_LO_STAGES]   (PAIR: leader's copy collects both CTAs' epilogue warps)
     uint64_t* lo_empty = lo_full + F_LO_STAGES;
     uint64_t* accf = lo_empty + F_LO_STAGES; // [3] layer l's accumulator complete
     uint32_t* tmem_slot = (uint32_t*)(accf + 3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    constexpr int TM = PAIR ? 2 * BM : BM;       // rows of a work tile
 
     if (warp == 0 && lane == 0) {
-        mbar_init(x_full, 1); mbar_init(x_empty, 1);
-        for (int s = 0; s < NUNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < F_LO_STAGES; ++s) { mbar_init(&lo_full[s], EPI_W); mbar_init(&lo_empty[s], 1); }
+        mbar_init(x_full, PAIR ? 2 : 1); mbar_init(x_empty, 1);
+        for (int s = 0; s < NUNITS; ++s) { mbar_init(&b_full[s], PAIR ? 2 : 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < F_LO_STAGES; ++s) { mbar_init(&lo_full[s], EPI_W * (PAIR ? 2 : 1)); mbar_init(&lo_empty[s], 1); }
         for (int s = 0; s < 3; ++s) mbar_init(&accf[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===== TMA producer: the tile's pre-split input, then the weight k-blocks of the three layers in consumption order =====
+        // (PAIR: every CTA loads its own 128 rows of X and its HALF of the rows of each weight k-block: hi at +0, lo at +16 KB of a unit)
         if (lane == 0) {
             uint32_t u = 0, t = 0;
             auto wide = [&](const CUtensorMap* mh, const CUtensorMap* ml, int kb) {   // [256 x 32] hi and lo: one unit each
@@ -203,91 +270,95 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
                     tma_load_2d(half ? ml : mh, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb * BK, 0);
                 }
             };
-            auto narrow = [&](const CUtensorMap* mh, const CUtensorMap* ml, int kb) { // [128 x 32] hi + lo in one unit
+            auto narrow = [&](const CUtensorMap* mh, const CUtensorMap* ml, int kb, int nrows) { // hi + lo of [nrows x 32] in one unit
                 const uint32_t s = u % NUNITS, ph = (u / NUNITS) & 1;
                 mbar_wait_wd(&b_empty[s], ph ^ 1, 110 + (int)s);
-                mbar_expect_tx(&b_full[s], UNIT_BYTES);
-                tma_load_2d(mh, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb * BK, 0);
-                tma_load_2d(ml, &b_full[s], sbase + F_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, 0);
+                const int mine = PAIR ? nrows / 2 : nrows;
+                expect_collect<PAIR>(&b_full[s], (uint32_t)(2 * mine * BK * 4), rank);
+                tma_collect<PAIR>(mh, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb * BK, (int)rank * mine);
+                tma_collect<PAIR>(ml, &b_full[s], sbase + F_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, (int)rank * mine);
                 ++u;
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, PAIR);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const FwdNet& N = P.net[ni];
-                const int m0 = tile * BM;
+                const int m0 = tile * TM + (int)rank * BM;
                 mbar_wait_wd(x_empty, (t & 1) ^ 1, 120);
-                mbar_expect_tx(x_full, 4 * KB_BYTES);
-                tma_load_2d(&N.mXh, x_full, sbase + F_X_HI, 0, m0);
-                tma_load_2d(&N.mXh, x_full, sbase + F_X_HI + KB_BYTES, BK, m0);
-                tma_load_2d(&N.mXl, x_full, sbase + F_X_LO, 0, m0);
-                tma_load_2d(&N.mXl, x_full, sbase + F_X_LO + KB_BYTES, BK, m0);
-                for (int kb = 0; kb < 2; ++kb) wide(&N.mW1h, &N.mW1l, kb);
-                for (int kb = 0; kb < 8; ++kb) { if (N.n2 == 256) wide(&N.mW2h, &N.mW2l, kb); else narrow(&N.mW2h, &N.mW2l, kb); }
-                for (int kb = 0; kb < N.n2 / BK; ++kb) narrow(&N.mW3h, &N.mW3l, kb);
+                expect_collect<PAIR>(x_full, 4 * KB_BYTES, rank);
+                tma_collect<PAIR>(&N.mXh, x_full, sbase + F_X_HI, 0, m0);
+                tma_collect<PAIR>(&N.mXh, x_full, sbase + F_X_HI + KB_BYTES, BK, m0);
+                tma_collect<PAIR>(&N.mXl, x_full, sbase + F_X_LO, 0, m0);
+                tma_collect<PAIR>(&N.mXl, x_full, sbase + F_X_LO + KB_BYTES, BK, m0);
+                for (int kb = 0; kb < 2; ++kb) { if (PAIR) narrow(&N.mW1h, &N.mW1l, kb, 256); else wide(&N.mW1h, &N.mW1l, kb); }
+                for (int kb = 0; kb < 8; ++kb) { if (!PAIR && N.n2 == 256) wide(&N.mW2h, &N.mW2l, kb); else narrow(&N.mW2h, &N.mW2l, kb, N.n2); }
+                for (int kb = 0; kb < N.n2 / BK; ++kb) narrow(&N.mW3h, &N.mW3l, kb, 128);
                 ++t;
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (PAIR: the leader CTA issues for both) =====
+        if (lane == 0 && rank == 0) {
             uint32_t u = 0, t = 0, li = 0;
             CTL_DECL;
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            // weight k-block of an N-row layer: waits for its unit(s), returns the operand addresses and the barriers to release
+            auto weights = [&](int nn, uint32_t& b_hi, uint32_t& b_lo, uint64_t*& e0, uint64_t*& e1, int code) {
+                e1 = nullptr;
+                if (!PAIR && nn == 256) {
+                    const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1, sb = (u + 1) % NUNITS, pb = ((u + 1) / NUNITS) & 1;
+                    u += 2;
+                    CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, code));
+                    CTL_WAIT(2, mbar_wait_wd(&b_full[sb], pb, code + 1));
+                    b_hi = sbase + F_B + sa * UNIT_BYTES; b_lo = sbase + F_B + sb * UNIT_BYTES;
+                    e0 = &b_empty[sa]; e1 = &b_empty[sb];
+                } else {
+                    const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1;
+                    u += 1;
+                    CTL_WAIT(2, wait_collect<PAIR>(&b_full[sa], pa, code + 2));
+                    b_hi = sbase + F_B + sa * UNIT_BYTES; b_lo = b_hi + UNIT_BYTES / 2;
+                    e0 = &b_empty[sa];
+                }
+            };
+            TileSeq seq(P.net[0].rows, P.net[1].rows, PAIR);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const int n2 = P.net[ni].n2;
                 const uint32_t par = t & 1;
                 const uint32_t c1 = tmem_base + par * 256, c2 = tmem_base + (1 - par) * 256, c3 = c1;
                 // ---- layer 1 (A = X from shared memory)
-                CTL_WAIT(0, mbar_wait_wd(x_full, par, 200));
+                CTL_WAIT(0, wait_collect<PAIR>(x_full, par, 200));
                 if (t > 0) CTL_WAIT(1, mbar_wait_wd(&accf[2], (t - 1) & 1, 201));   // layer 3 of the previous tile has finished READING h2 from c1's half
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < 2; ++kb) {
-                    const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1, sb = (u + 1) % NUNITS, pb = ((u + 1) / NUNITS) & 1;
-                    u += 2;
-                    CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, 210));
-                    CTL_WAIT(2, mbar_wait_wd(&b_full[sb], pb, 211));
+                    uint32_t b_hi, b_lo;
+                    uint64_t *e0, *e1;
+                    weights(256, b_hi, b_lo, e0, e1, 210);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_hi = sbase + F_X_HI + kb * KB_BYTES, a_lo = sbase + F_X_LO + kb * KB_BYTES;
-                    const uint32_t b_hi = sbase + F_B + sa * UNIT_BYTES, b_lo = sbase + F_B + sb * UNIT_BYTES;
-                    constexpr uint32_t id = idesc_tf32_m(BM, 256);
+                    constexpr uint32_t id = idesc_tf32_m(TM, 256);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t off = k * 32;
-                        umma_tf32(c1, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
-                        umma_tf32(c1, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), id, 1u);
-                        umma_tf32(c1, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), id, 1u);
+                        mma_ss<PAIR>(c1, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
+                        mma_ss<PAIR>(c1, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), id, 1u);
+                        mma_ss<PAIR>(c1, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), id, 1u);
                     }
-                    umma_commit(&b_empty[sa]);
-                    umma_commit(&b_empty[sb]);
+                    commit<PAIR>(e0);
+                    if (e1) commit<PAIR>(e1);
                 }
-                umma_commit(x_empty);
-                umma_commit(&accf[0]);
+                commit<PAIR>(x_empty);
+                commit<PAIR>(&accf[0]);
                 // ---- layers 2 and 3 (A hi from TMEM in place, A lo from the ring)
                 for (int layer = 0; layer < 2; ++layer) {
                     const int nk = layer == 0 ? 8 : n2 / BK, nn = layer == 0 ? n2 : 128;
                     const uint32_t ca = layer == 0 ? c1 : c2, cd = layer == 0 ? c2 : c3;
-                    const uint32_t id = idesc_tf32_m(BM, nn);
+                    const uint32_t id = idesc_tf32_m(TM, nn);
                     for (int kb = 0; kb < nk; ++kb, ++li) {
                         uint32_t b_hi, b_lo;
-                        uint64_t *e0, *e1 = nullptr;
-                        if (nn == 256) {
-                            const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1, sb = (u + 1) % NUNITS, pb = ((u + 1) / NUNITS) & 1;
-                            u += 2;
-                            CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, 220));
-                            CTL_WAIT(2, mbar_wait_wd(&b_full[sb], pb, 221));
-                            b_hi = sbase + F_B + sa * UNIT_BYTES; b_lo = sbase + F_B + sb * UNIT_BYTES;
-                            e0 = &b_empty[sa]; e1 = &b_empty[sb];
-                        } else {
-                            const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1;
-                            u += 1;
-                            CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, 222));
-                            b_hi = sbase + F_B + sa * UNIT_BYTES; b_lo = b_hi + UNIT_BYTES / 2;
-                            e0 = &b_empty[sa];
-                        }
+                        uint64_t *e0, *e1;
+                        weights(nn, b_hi, b_lo, e0, e1, 220);
                         const uint32_t ls = li % F_LO_STAGES, lph = (li / F_LO_STAGES) & 1;
-                        CTL_WAIT(3 + layer, mbar_wait_wd(&lo_full[ls], lph, 230 + layer));   // the epilogue has published this k-block (hi in TMEM, lo in the ring)
+                        CTL_WAIT(3 + layer, wait_collect<PAIR>(&lo_full[ls], lph, 230 + layer));   // the epilogue(s) have published this k-block (hi in TMEM, lo in the ring)
                         asm volatile("tcgen05.fence::after_thread_sync;");
                         const uint32_t a_lo = sbase + F_LO + ls * KB_BYTES;
                         // 128-wide outputs leave 128 free columns next to the accumulator: the dominant a_hi * b_hi products get their own
@@ -297,15 +368,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t off = k * 32, a_t = ca + kb * BK + k * 8;
-                            umma_tf32(cs, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
-                            umma_tf32_ts(cs, a_t, desc_kmajor(b_lo + off), id, 1u);
-                            umma_tf32_ts(cd, a_t, desc_kmajor(b_hi + off), id, (nn == 128 && (kb | k) == 0) ? 0u : 1u);
+                            mma_ss<PAIR>(cs, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
+                            mma_ts<PAIR>(cs, a_t, desc_kmajor(b_lo + off), id, 1u);
+                            mma_ts<PAIR>(cd, a_t, desc_kmajor(b_hi + off), id, (nn == 128 && (kb | k) == 0) ? 0u : 1u);
                         }
-                        umma_commit(&lo_empty[ls]);
-                        umma_commit(e0);
-                        if (e1) umma_commit(e1);
+                        commit<PAIR>(&lo_empty[ls]);
+                        commit<PAIR>(e0);
+                        if (e1) commit<PAIR>(e1);
                     }
-                    umma_commit(&accf[1 + layer]);
+                    commit<PAIR>(&accf[1 + layer]);
                 }
                 ++t;
             }
@@ -315,17 +386,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
         // ===== epilogue warps: TMEM lane quarter q (rows), 8-column slice g of every 32-column k-block =====
         const int q = warp & 3, g = (warp - F_EPI0) >> 2;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const int rit = q * 32 + lane;                 // row in tile
+        const int rit = q * 32 + lane;                 // row in this CTA's 128-row tile
         uint32_t t = 0, li = 0;
         CTL_DECL;
-        TileSeq seq(P.net[0].rows, P.net[1].rows);
+        TileSeq seq(P.net[0].rows, P.net[1].rows, PAIR);
         int ni, tile;
         while (seq.next(ni, tile)) {
             const FwdNet& N = P.net[ni];
             const int n2 = N.n2, exact = N.exact;
             const uint32_t par = t & 1;
             const uint32_t c1 = tmem_base + par * 256 + lane_off, c2 = tmem_base + (1 - par) * 256 + lane_off, c3 = c1;
-            const int row = tile * BM + rit;
+            const int row = tile * TM + (int)rank * BM + rit;
             const bool row_ok = row < N.rows;
             const size_t rsafe = (size_t)(row_ok ? row : 0);
 #pragma unroll 1
@@ -336,41 +407,54 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
                 float* out = (layer == 0 ? N.H1 : (layer == 1 ? N.H2 : N.H3)) + rsafe * width;
                 CTL_WAIT(layer, mbar_wait_wd(&accf[layer], par, 300 + layer));
                 asm volatile("tcgen05.fence::after_thread_sync;");
+                // software pipeline over the k-blocks: the accumulator slice and the bias of k-block kb + 1 are requested before kb is
+                // processed (tcgen05.ld is asynchronous until tcgen05.wait::ld), so their latency hides behind the ELU / publish of kb
+                const bool two_acc = layer > 0 && width == 128;   // big + small accumulator (see the MMA issuer)
+                const int nkb = width / BK;
+                uint32_t rn[8], rn2[8];
+                float4 bn0, bn1;
+                tmem_ld8_nowait(cacc + g * 8, rn);
+                if (two_acc) tmem_ld8_nowait(cacc + 128 + g * 8, rn2);
+                bn0 = __ldg(reinterpret_cast<const float4*>(bias + g * 8)); bn1 = __ldg(reinterpret_cast<const float4*>(bias + g * 8 + 4));
 #pragma unroll 1
-                for (int kb = 0; kb < width / BK; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb) {
                     const int col = kb * BK + g * 8;
                     uint32_t r[8];
-                    tmem_ld8(cacc + col, r);
-                    if (layer > 0 && width == 128) {   // big + small accumulator (see the MMA issuer)
-                        uint32_t r2[8];
-                        tmem_ld8(cacc + 128 + col, r2);
+                    if (two_acc) tmem_wait_ld16(rn, rn2); else tmem_wait_ld8(rn);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                    for (int j = 0; j < 8; ++j) r[j] = two_acc ? __float_as_uint(__uint_as_float(rn[j]) + __uint_as_float(rn2[j])) : rn[j];
+                    const float4 b0 = bn0, b1 = bn1;
+                    if (kb + 1 < nkb) {
+                        tmem_ld8_nowait(cacc + col + BK, rn);
+                        if (two_acc) tmem_ld8_nowait(cacc + 128 + col + BK, rn2);
+                        bn0 = __ldg(reinterpret_cast<const float4*>(bias + col + BK)); bn1 = __ldg(reinterpret_cast<const float4*>(bias + col + BK + 4));
                     }
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
                     float v[8];
                     v[0] = elu_sel(__uint_as_float(r[0]) + b0.x, exact); v[1] = elu_sel(__uint_as_float(r[1]) + b0.y, exact);
                     v[2] = elu_sel(__uint_as_float(r[2]) + b0.z, exact); v[3] = elu_sel(__uint_as_float(r[3]) + b0.w, exact);
                     v[4] = elu_sel(__uint_as_float(r[4]) + b1.x, exact); v[5] = elu_sel(__uint_as_float(r[5]) + b1.y, exact);
                     v[6] = elu_sel(__uint_as_float(r[6]) + b1.z, exact); v[7] = elu_sel(__uint_as_float(r[7]) + b1.w, exact);
-                    if (row_ok) stg_v8(out + col, v);
+                    CTL_WAIT(4, if (row_ok) stg_v8(out + col, v));
                     if (layer < 2) {
                         const uint32_t ls = li % F_LO_STAGES, lph = (li / F_LO_STAGES) & 1;
                         CTL_WAIT(3, mbar_wait_wd(&lo_empty[ls], lph ^ 1, 310 + layer));   // the MMAs that read this ring stage have completed
-                        publish_slice(v, cacc + col, sbase + F_LO + ls * KB_BYTES, rit, g);
-                        publish_done(&lo_full[ls], lane);
+                        CTL_WAIT(5, publish_slice(v, cacc + col, sbase + F_LO + ls * KB_BYTES, rit, g));
+                        CTL_WAIT(6, publish_done(&lo_full[ls], lane, PAIR && rank != 0));
                         ++li;
                     }
                 }
             }
             ++t;
         }
-        if (threadIdx.x == 32 * F_EPI0) CTL_FLUSH(0, 8, 4);
+        if (threadIdx.x == 32 * F_EPI0) CTL_FLUSH(0, 8, 7);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == 1) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
 }
 
 // =====================================================================================================================
@@ -410,39 +494,50 @@ __device__ __forceinline__ void colsum8(float* v, int lane, float* dst) {
     if (lane < 8) atomicAdd(dst + lane, tot);   // lane l holds column l (bit i of l picked the upper half at step 2^i)
 }
 
+template <int PAIR>
 __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant__ BwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* b_full = (uint64_t*)(smem + B_BAR);
+    uint64_t* b_full = (uint64_t*)(smem + B_BAR);   // (PAIR: leader's copy collects both CTAs' halves)
     uint64_t* b_empty = b_full + NUNITS;
-    uint64_t* lo_full = b_empty + NUNITS;
+    uint64_t* lo_full = b_empty + NUNITS;           // (PAIR: leader's copy collects both CTAs' epilogue warps)
     uint64_t* lo_empty = lo_full + B_LO_STAGES;
-    uint64_t* aux_full = lo_empty + B_LO_STAGES;
+    uint64_t* aux_full = lo_empty + B_LO_STAGES;    // (always local: each CTA's epilogue reads its own rows)
     uint64_t* aux_empty = aux_full + B_AUX_STAGES;
     uint64_t* accf = aux_empty + B_AUX_STAGES;   // [2]: dh2 complete, dh1 complete
     uint32_t* tmem_slot = (uint32_t*)(accf + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    constexpr int TM = PAIR ? 2 * BM : BM;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < NUNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < B_LO_STAGES; ++s) { mbar_init(&lo_full[s], EPI_W); mbar_init(&lo_empty[s], 1); }
+        for (int s = 0; s < NUNITS; ++s) { mbar_init(&b_full[s], PAIR ? 2 : 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < B_LO_STAGES; ++s) { mbar_init(&lo_full[s], EPI_W * (PAIR ? 2 : 1)); mbar_init(&lo_empty[s], 1); }
         for (int s = 0; s < B_AUX_STAGES; ++s) { mbar_init(&aux_full[s], 1); mbar_init(&aux_empty[s], EPI_W); }
         mbar_init(&accf[0], 1); mbar_init(&accf[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t CZ = 0, CA = 128, CD_LO = 384, CD_HI = 0;   // TMEM columns: dz3, dh2/dz2, dh1 columns [0,128) / [128,256)
 
     if (warp == 0) {
         // ===== TMA producer: weight k-blocks (W3^T then W2^T per tile) =====
+        // single CTA: [256 x 32] tiles take two units (hi, lo), [128 x 32] one (hi at +0, lo at +16 KB).
+        // PAIR: every k-block is one unit holding this CTA's HALF of the rows: hi at +0, lo at +16 KB; for W2^T (whose 256 output columns
+        //       are produced as two 128-column MMAs) the half is this CTA's 64 rows of each output half: [h0 rows | h1 rows].
         if (lane == 0) {
             uint32_t u = 0;
             auto wide = [&](const CUtensorMap* mh, const CUtensorMap* ml, int kb) {
@@ -453,24 +548,36 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
                     tma_load_2d(half ? ml : mh, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb * BK, 0);
                 }
             };
-            auto narrow = [&](const CUtensorMap* mh, const CUtensorMap* ml, int kb) {
+            auto narrow = [&](const CUtensorMap* mh, const CUtensorMap* ml, int kb, int nrows) {
                 const uint32_t s = u % NUNITS, ph = (u / NUNITS) & 1;
                 mbar_wait_wd(&b_empty[s], ph ^ 1, 510 + (int)s);
-                mbar_expect_tx(&b_full[s], UNIT_BYTES);
-                tma_load_2d(mh, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb * BK, 0);
-                tma_load_2d(ml, &b_full[s], sbase + B_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, 0);
+                const int mine = PAIR ? nrows / 2 : nrows;
+                expect_collect<PAIR>(&b_full[s], (uint32_t)(2 * mine * BK * 4), rank);
+                tma_collect<PAIR>(mh, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb * BK, (int)rank * mine);
+                tma_collect<PAIR>(ml, &b_full[s], sbase + B_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, (int)rank * mine);
                 ++u;
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            auto halves = [&](const CUtensorMap* mh, const CUtensorMap* ml, int kb) {   // PAIR only: 64-row boxes
+                const uint32_t s = u % NUNITS, ph = (u / NUNITS) & 1;
+                mbar_wait_wd(&b_empty[s], ph ^ 1, 515 + (int)s);
+                expect_collect<PAIR>(&b_full[s], (uint32_t)UNIT_BYTES, rank);
+                const uint32_t base = sbase + B_B + s * UNIT_BYTES;
+                for (int h = 0; h < 2; ++h) {
+                    tma_collect<PAIR>(mh, &b_full[s], base + h * (UNIT_BYTES / 4), kb * BK, h * 128 + (int)rank * 64);
+                    tma_collect<PAIR>(ml, &b_full[s], base + UNIT_BYTES / 2 + h * (UNIT_BYTES / 4), kb * BK, h * 128 + (int)rank * 64);
+                }
+                ++u;
+            };
+            TileSeq seq(P.net[0].rows, P.net[1].rows, PAIR);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const BwdNet& N = P.net[ni];
-                for (int kb = 0; kb < 4; ++kb) { if (N.n2 == 256) wide(&N.mW3Th, &N.mW3Tl, kb); else narrow(&N.mW3Th, &N.mW3Tl, kb); }
-                for (int kb = 0; kb < N.n2 / BK; ++kb) wide(&N.mW2Th, &N.mW2Tl, kb);
+                for (int kb = 0; kb < 4; ++kb) { if (!PAIR && N.n2 == 256) wide(&N.mW3Th, &N.mW3Tl, kb); else narrow(&N.mW3Th, &N.mW3Tl, kb, N.n2); }
+                for (int kb = 0; kb < N.n2 / BK; ++kb) { if (PAIR) halves(&N.mW2Th, &N.mW2Tl, kb); else wide(&N.mW2Th, &N.mW2Tl, kb); }
             }
         }
     } else if (warp == 2) {
-        // ===== TMA producer: aux tiles in the epilogue's consumption order =====
+        // ===== TMA producer: aux tiles (this CTA's 128 rows) in the epilogue's consumption order =====
         if (lane == 0) {
             uint32_t ai = 0;
             auto aux = [&](const CUtensorMap* m, int kb, int m0) {
@@ -480,26 +587,27 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
                 tma_load_2d(m, &aux_full[s], sbase + B_AUX + s * KB_BYTES, kb * BK, m0);
                 ++ai;
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, PAIR);
             int cn, ct, nn = 0, nt = 0;
             bool have = seq.next(cn, ct);
-            if (have) for (int kb = 0; kb < 4; ++kb) aux(&P.net[cn].mZ3, kb, ct * BM);
+            if (have) for (int kb = 0; kb < 4; ++kb) aux(&P.net[cn].mZ3, kb, ct * TM + (int)rank * BM);
             while (have) {
                 const bool hn = seq.next(nn, nt);
                 const BwdNet& N = P.net[cn];
-                for (int kb = 0; kb < N.n2 / BK; ++kb) aux(&N.mH2, kb, ct * BM);
-                for (int kb = 4; kb < 8; ++kb) aux(&N.mH1, kb, ct * BM);
-                if (hn) for (int kb = 0; kb < 4; ++kb) aux(&P.net[nn].mZ3, kb, nt * BM);
-                for (int kb = 0; kb < 4; ++kb) aux(&N.mH1, kb, ct * BM);
+                const int m0 = ct * TM + (int)rank * BM;
+                for (int kb = 0; kb < N.n2 / BK; ++kb) aux(&N.mH2, kb, m0);
+                for (int kb = 4; kb < 8; ++kb) aux(&N.mH1, kb, m0);
+                if (hn) for (int kb = 0; kb < 4; ++kb) aux(&P.net[nn].mZ3, kb, nt * TM + (int)rank * BM);
+                for (int kb = 0; kb < 4; ++kb) aux(&N.mH1, kb, m0);
                 have = hn; cn = nn; ct = nt;
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (PAIR: the leader CTA issues for both) =====
+        if (lane == 0 && rank == 0) {
             uint32_t u = 0, li = 0;
             CTL_DECL;
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, PAIR);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const int n2 = P.net[ni].n2;
@@ -507,7 +615,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
                 for (int kb = 0; kb < 4; ++kb, ++li) {
                     uint32_t b_hi, b_lo;
                     uint64_t *e0, *e1 = nullptr;
-                    if (n2 == 256) {
+                    if (!PAIR && n2 == 256) {
                         const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1, sb = (u + 1) % NUNITS, pb = ((u + 1) / NUNITS) & 1;
                         u += 2;
                         CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, 600));
@@ -517,55 +625,66 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
                     } else {
                         const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1;
                         u += 1;
-                        CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, 602));
+                        CTL_WAIT(2, wait_collect<PAIR>(&b_full[sa], pa, 602));
                         b_hi = sbase + B_B + sa * UNIT_BYTES; b_lo = b_hi + UNIT_BYTES / 2;
                         e0 = &b_empty[sa];
                     }
                     const uint32_t ls = li % B_LO_STAGES, lph = (li / B_LO_STAGES) & 1;
-                    CTL_WAIT(3, mbar_wait_wd(&lo_full[ls], lph, 610));
+                    CTL_WAIT(3, wait_collect<PAIR>(&lo_full[ls], lph, 610));
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_lo = sbase + B_LO + ls * KB_BYTES;
-                    const uint32_t id = idesc_tf32_m(BM, n2);
+                    const uint32_t id = idesc_tf32_m(TM, n2);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t off = k * 32, a_t = tmem_base + CZ + kb * BK + k * 8;
-                        umma_tf32(tmem_base + CA, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
-                        umma_tf32_ts(tmem_base + CA, a_t, desc_kmajor(b_lo + off), id, 1u);
-                        umma_tf32_ts(tmem_base + CA, a_t, desc_kmajor(b_hi + off), id, 1u);
+                        mma_ss<PAIR>(tmem_base + CA, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
+                        mma_ts<PAIR>(tmem_base + CA, a_t, desc_kmajor(b_lo + off), id, 1u);
+                        mma_ts<PAIR>(tmem_base + CA, a_t, desc_kmajor(b_hi + off), id, 1u);
                     }
-                    umma_commit(&lo_empty[ls]);
-                    umma_commit(e0);
-                    if (e1) umma_commit(e1);
+                    commit<PAIR>(&lo_empty[ls]);
+                    commit<PAIR>(e0);
+                    if (e1) commit<PAIR>(e1);
                 }
-                umma_commit(&accf[0]);
+                commit<PAIR>(&accf[0]);
                 // ---- dh1 [128, 256] = dz2 [128, n2] W2: n2 / 32 k-blocks, the output as two 128-column halves
                 for (int kb = 0; kb < n2 / BK; ++kb, ++li) {
-                    const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1, sb = (u + 1) % NUNITS, pb = ((u + 1) / NUNITS) & 1;
-                    u += 2;
-                    CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, 620));
-                    CTL_WAIT(2, mbar_wait_wd(&b_full[sb], pb, 621));
-                    const uint32_t b_hi = sbase + B_B + sa * UNIT_BYTES, b_lo = sbase + B_B + sb * UNIT_BYTES;
+                    uint32_t b_hi, b_lo, hstep;
+                    uint64_t *e0, *e1 = nullptr;
+                    if (PAIR) {
+                        const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1;
+                        u += 1;
+                        CTL_WAIT(2, wait_collect<PAIR>(&b_full[sa], pa, 620));
+                        b_hi = sbase + B_B + sa * UNIT_BYTES; b_lo = b_hi + UNIT_BYTES / 2; hstep = UNIT_BYTES / 4;   // 64 rows per output half
+                        e0 = &b_empty[sa];
+                    } else {
+                        const uint32_t sa = u % NUNITS, pa = (u / NUNITS) & 1, sb = (u + 1) % NUNITS, pb = ((u + 1) / NUNITS) & 1;
+                        u += 2;
+                        CTL_WAIT(2, mbar_wait_wd(&b_full[sa], pa, 620));
+                        CTL_WAIT(2, mbar_wait_wd(&b_full[sb], pb, 621));
+                        b_hi = sbase + B_B + sa * UNIT_BYTES; b_lo = sbase + B_B + sb * UNIT_BYTES; hstep = UNIT_BYTES / 2;   // rows 128..255 of the tile
+                        e0 = &b_empty[sa]; e1 = &b_empty[sb];
+                    }
                     const uint32_t ls = li % B_LO_STAGES, lph = (li / B_LO_STAGES) & 1;
-                    CTL_WAIT(4, mbar_wait_wd(&lo_full[ls], lph, 630));
+                    CTL_WAIT(4, wait_collect<PAIR>(&lo_full[ls], lph, 630));
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_lo = sbase + B_LO + ls * KB_BYTES;
-                    constexpr uint32_t id = idesc_tf32_m(BM, 128);
+                    constexpr uint32_t id = idesc_tf32_m(TM, 128);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t off = k * 32, a_t = tmem_base + CA + kb * BK + k * 8;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const uint32_t cd = tmem_base + (h ? CD_HI : CD_LO), boff = off + h * (UNIT_BYTES / 2);   // rows 128..255 of the weight tile
-                            umma_tf32(cd, desc_kmajor(a_lo + off), desc_kmajor(b_hi + boff), id, (kb | k) ? 1u : 0u);
-                            umma_tf32_ts(cd, a_t, desc_kmajor(b_lo + boff), id, 1u);
-                            umma_tf32_ts(cd, a_t, desc_kmajor(b_hi + boff), id, 1u);
+                            const uint32_t cd = tmem_base + (h ? CD_HI : CD_LO), boff = off + h * hstep;
+                            mma_ss<PAIR>(cd, desc_kmajor(a_lo + off), desc_kmajor(b_hi + boff), id, (kb | k) ? 1u : 0u);
+                            mma_ts<PAIR>(cd, a_t, desc_kmajor(b_lo + boff), id, 1u);
+                            mma_ts<PAIR>(cd, a_t, desc_kmajor(b_hi + boff), id, 1u);
                         }
                     }
-                    umma_commit(&lo_empty[ls]);
-                    umma_commit(&b_empty[sa]);
-                    umma_commit(&b_empty[sb]);
+                    commit<PAIR>(&lo_empty[ls]);
+                    commit<PAIR>(e0);
+                    if (e1) commit<PAIR>(e1);
                 }
-                umma_commit(&accf[1]);
+                commit<PAIR>(&accf[1]);
             }
             CTL_FLUSH(1, 0, 5);
         }
@@ -575,6 +694,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int rit = q * 32 + lane;
         const uint32_t sw = (uint32_t)(rit & 7);
+        const bool to_leader = PAIR && rank != 0;
         uint32_t t = 0, li = 0, ai = 0;
         CTL_DECL;
         // this thread's 8 floats of the aux k-block in ring stage s (128-byte swizzled rows).  The stage is handed back to the TMA
@@ -597,7 +717,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
             const uint32_t ls = li % B_LO_STAGES, lph = (li / B_LO_STAGES) & 1;
             CTL_WAIT(3, mbar_wait_wd(&lo_empty[ls], lph ^ 1, 710));
             publish_slice(v, tmem_base + lane_off + tcol, sbase + B_LO + ls * KB_BYTES, rit, g);
-            publish_done(&lo_full[ls], lane);
+            publish_done(&lo_full[ls], lane, to_leader);
             ++li;
         };
         auto stage_dz3 = [&]() {   // dz3 of a tile: aux tiles -> A operand (no arithmetic)
@@ -626,7 +746,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
             colsum8(v, lane, db + col);
             aux_release(as);
         };
-        TileSeq seq(P.net[0].rows, P.net[1].rows);
+        TileSeq seq(P.net[0].rows, P.net[1].rows, PAIR);
         int cn, ct, nn = 0, nt = 0;
         bool have = seq.next(cn, ct);
         if (have) stage_dz3();
@@ -634,7 +754,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
             const bool hn = seq.next(nn, nt);
             const BwdNet& N = P.net[cn];
             const int n2 = N.n2;
-            const int row = ct * BM + rit;
+            const int row = ct * TM + (int)rank * BM + rit;
             const bool row_ok = row < N.rows;
             const size_t rsafe = (size_t)(row_ok ? row : 0);
             const uint32_t par = t & 1;
@@ -657,9 +777,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
         if (threadIdx.x == 32 * B_EPI0) CTL_FLUSH(1, 8, 4);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == 1) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
 }
 
 }  // namespace chain

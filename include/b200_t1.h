@@ -319,7 +319,8 @@ int b200_tc_set_pair(int enable);
  * threads per SM, best of 5 launches timed with CUDA events on `stream`.  Roofline denominator of k_physics. */
 int b200_fma_peak(double* tflops, void* stream);
 /* hidden layers of the PPO epoch: 1 (default) = fused layer chains (mlp_chain.cuh: one persistent tcgen05 kernel per direction,
- * activations handed from layer to layer in TMEM), 0 = one GEMM launch per layer (k_tc_rowmajor).  Same results within the
+ * activations handed from layer to layer in TMEM), 2 = the same chains on CTA pairs (clusters of 2, tcgen05 cta_group::2, 256-row
+ * tiles, each CTA stages half of every weight k-block), 0 = one GEMM launch per layer (k_tc_rowmajor).  Same results within the
  * stated tolerances; replaces the autograd graph of utils/runner.py:132-133,148,163. */
 int b200_tc_set_chain(int enable);
 

@@ -21,6 +21,7 @@ def rel(a, b):
 
 def main():
     T, N = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4, 1000)
+    modes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]   # 0 layers, 1 chain, 2 chain on CTA pairs
     cfg = yaml.safe_load(open(os.path.join(ROOT, "envs", "T1.yaml")))
     cfg = copy.deepcopy(cfg)
     cfg["runner"]["horizon_length"] = T
@@ -41,7 +42,7 @@ def main():
               13: (M, 256), 14: (M, 256), 5: (M,), 6: (M, 12)}
     names = {0: "V", 3: "mu", 7: "C1", 8: "C2", 9: "C3", 10: "A1", 11: "A2", 12: "A3", 13: "dz2 critic", 14: "dz1 critic", 5: "dV", 6: "dmu"}
     snaps = {}
-    for chain in (0, 1):
+    for chain in modes:
         lib.b200_tc_set_chain(chain)
         lrn.old_dist(dev["obses"], dev["privileged_obses"], dev["actions"])
         rew = dev["rewards"].clone()
@@ -50,12 +51,14 @@ def main():
         torch.cuda.synchronize()
         snaps[chain] = ({k: lrn.buffer(k, s) for k, s in shapes.items()}, {k: v.clone() for k, v in lrn.views(lrn.grads).items()})
         print(f"chain={chain}: epoch ran", flush=True)
-    for k in shapes:
-        print(f"  {names[k]:12s} chain vs layers: {rel(snaps[1][0][k], snaps[0][0][k]):.3e}")
-    for k in snaps[0][1]:
-        print(f"  grad {k:18s} chain vs layers: {rel(snaps[1][1][k], snaps[0][1][k]):.3e}")
+    base = modes[0]
+    for m in modes[1:]:
+        for k in shapes:
+            print(f"  {names[k]:12s} mode {m} vs mode {base}: {rel(snaps[m][0][k], snaps[base][0][k]):.3e}")
+        for k in snaps[base][1]:
+            print(f"  grad {k:18s} mode {m} vs mode {base}: {rel(snaps[m][1][k], snaps[base][1][k]):.3e}")
     # the chain's input gradients against torch fp64 on the chain's own inputs; where are the bad rows?
-    lib.b200_tc_set_chain(1)
+    lib.b200_tc_set_chain(modes[-1])
     rew = dev["rewards"].clone()
     lrn.epoch_a(rew, d8, t8, lo, lp)
     lrn.epoch_b(dev["actions"])
@@ -82,9 +85,9 @@ def main():
     sd64 = {k: v.double() for k, v in sd.items()}
     mu64 = L.actor_mean(sd64, buf["obses"].double()).reshape(M, 12)
     v64 = L.critic_value(sd64, buf["obses"].double(), buf["privileged_obses"].double()).reshape(M)
-    for chain in (0, 1):
+    for chain in modes:
         print(f"  chain={chain}: mu vs fp64 {rel(snaps[chain][0][3].cpu().double(), mu64):.3e}   V vs fp64 {rel(snaps[chain][0][0].cpu().double(), v64):.3e}")
-    for chain in (0, 1):
+    for chain in modes:
         lib.b200_tc_set_chain(chain)
         for _ in range(2):
             lrn.epoch_a(rew, d8, t8, lo, lp)

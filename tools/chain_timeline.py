@@ -40,5 +40,9 @@ for k, name in ((0, "k_mlp_fwd (last launch = actor)"), (1, "k_mlp_bwd (critic +
     m = a.mean(0)
     print(f"  MMA thread: total {m[5]:9.0f} clk | wait x_full {m[0]:8.0f}  accf-safety {m[1]:8.0f}  weights {m[2]:8.0f}  lo_full(L2/dgrad3) {m[3]:8.0f}  lo_full(L3/dgrad2) {m[4]:8.0f}"
           f"  -> issuing/other {m[5] - m[:5].sum():8.0f}")
-    print(f"  epilogue  : total {m[12]:9.0f} clk | wait accf0 {m[8]:8.0f}  accf1 {m[9]:8.0f}  accf2|aux {m[10]:8.0f}  lo_empty {m[11]:8.0f}  -> working {m[12] - m[8:12].sum():8.0f}")
+    if k == 0:
+        print(f"  epilogue  : total {m[15]:9.0f} clk | wait accf0 {m[8]:8.0f}  accf1 {m[9]:8.0f}  accf2 {m[10]:8.0f}  lo_empty {m[11]:8.0f} | st.global {m[12]:8.0f}  "
+              f"publish_slice (split, tcgen05.st, st.shared) {m[13]:8.0f}  publish_done (wait::st, fences, arrive) {m[14]:8.0f}  -> tcgen05.ld + bias + ELU {m[15] - m[8:15].sum():8.0f}")
+    else:
+        print(f"  epilogue  : total {m[12]:9.0f} clk | wait accf0 {m[8]:8.0f}  accf1 {m[9]:8.0f}  aux {m[10]:8.0f}  lo_empty {m[11]:8.0f}  -> working {m[12] - m[8:12].sum():8.0f}")
     print(f"  total max {a[:, 5].max():.0f} min {a[:, 5].min():.0f}")
