@@ -221,6 +221,11 @@ __device__ __forceinline__ float elu_sel(float x, int) {
 
 template <int PAIR>
 __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant__ FwdParams P) {
+    // PAIR: every weight k-block is ONE unit per CTA (its half), so three units are as deep as four were; the 32 KB saved double the
+    // lo ring: the leader's MMA needs BOTH CTAs' epilogues per k-block, and two stages exposed that hand-shake's latency
+    constexpr int NUNITS = PAIR ? 3 : 4, F_LO_STAGES = PAIR ? 4 : 2;
+    constexpr int F_LO = F_B + NUNITS * UNIT_BYTES, F_BAR = F_LO + F_LO_STAGES * KB_BYTES;
+    static_assert(F_BAR + 256 + 1024 <= F_SMEM, "shared memory layout");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* x_full = (uint64_t*)(smem + F_BAR);   // (PAIR: the leader's copy collects both CTAs' tiles)
@@ -364,13 +369,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
                         // 128-wide outputs leave 128 free columns next to the accumulator: the dominant a_hi * b_hi products get their own
                         // accumulator (TMEM accumulation truncates: 1/3 of the adds on the large accumulator = 1/3 of the bias), the
                         // two small cross terms share the second one; the epilogue adds them (round to nearest)
-                        const uint32_t cs = nn == 128 ? cd + 128 : cd;
+                        const uint32_t cs = (nn == 128 && !P.net[ni].exact) ? cd + 128 : cd;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t off = k * 32, a_t = ca + kb * BK + k * 8;
                             mma_ss<PAIR>(cs, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
                             mma_ts<PAIR>(cs, a_t, desc_kmajor(b_lo + off), id, 1u);
-                            mma_ts<PAIR>(cd, a_t, desc_kmajor(b_hi + off), id, (nn == 128 && (kb | k) == 0) ? 0u : 1u);
+                            mma_ts<PAIR>(cd, a_t, desc_kmajor(b_hi + off), id, (cs != cd && (kb | k) == 0) ? 0u : 1u);
                         }
                         commit<PAIR>(&lo_empty[ls]);
                         commit<PAIR>(e0);
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 // software pipeline over the k-blocks: the accumulator slice and the bias of k-block kb + 1 are requested before kb is
                 // processed (tcgen05.ld is asynchronous until tcgen05.wait::ld), so their latency hides behind the ELU / publish of kb
-                const bool two_acc = layer > 0 && width == 128;   // big + small accumulator (see the MMA issuer)
+                const bool two_acc = layer > 0 && width == 128 && !exact;   // big + small accumulator (see the MMA issuer)
                 const int nkb = width / BK;
                 uint32_t rn[8], rn2[8];
                 float4 bn0, bn1;
@@ -434,7 +439,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
                     v[2] = elu_sel(__uint_as_float(r[2]) + b0.z, exact); v[3] = elu_sel(__uint_as_float(r[3]) + b0.w, exact);
                     v[4] = elu_sel(__uint_as_float(r[4]) + b1.x, exact); v[5] = elu_sel(__uint_as_float(r[5]) + b1.y, exact);
                     v[6] = elu_sel(__uint_as_float(r[6]) + b1.z, exact); v[7] = elu_sel(__uint_as_float(r[7]) + b1.w, exact);
-                    CTL_WAIT(4, if (row_ok) stg_v8(out + col, v));
                     if (layer < 2) {
                         const uint32_t ls = li % F_LO_STAGES, lph = (li / F_LO_STAGES) & 1;
                         CTL_WAIT(3, mbar_wait_wd(&lo_empty[ls], lph ^ 1, 310 + layer));   // the MMAs that read this ring stage have completed
@@ -442,6 +446,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
                         CTL_WAIT(6, publish_done(&lo_full[ls], lane, PAIR && rank != 0));
                         ++li;
                     }
+                    // the HBM copy goes out AFTER the hand-over: the fence in publish_done (MEMBAR.ALL.CTA) waits for every earlier
+                    // memory operation of the thread, and a global store in front of it put an L2 round trip on the critical path of
+                    // every k-block
+                    CTL_WAIT(4, if (row_ok) stg_v8(out + col, v));
                 }
             }
             ++t;
@@ -496,6 +504,9 @@ __device__ __forceinline__ void colsum8(float* v, int lane, float* dst) {
 
 template <int PAIR>
 __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant__ BwdParams P) {
+    constexpr int NUNITS = PAIR ? 3 : 4, B_LO_STAGES = PAIR ? 4 : 3, B_AUX_STAGES = PAIR ? 4 : 3;   // (see k_mlp_fwd)
+    constexpr int B_LO = NUNITS * UNIT_BYTES, B_AUX = B_LO + B_LO_STAGES * KB_BYTES, B_BAR = B_AUX + B_AUX_STAGES * KB_BYTES;
+    static_assert(B_BAR + 256 + 1024 <= B_SMEM, "shared memory layout");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* b_full = (uint64_t*)(smem + B_BAR);   // (PAIR: leader's copy collects both CTAs' halves)
@@ -737,8 +748,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd(const __grid_constant_
             tmem_ld8(tmem_base + lane_off + tcol, r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) * ((h[j] > 0.0f) ? 1.0f : (h[j] + 1.0f));
-            if (row_ok) stg_v8(out_row + col, v);
             if (handoff) publish(v, tcol);
+            if (row_ok) stg_v8(out_row + col, v);   // after the hand-over (see k_mlp_fwd): keeps the L2 round trip off the fence
             if (!row_ok) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = 0.0f;
