@@ -107,7 +107,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -201,13 +201,20 @@ def b200_arm(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return ms.item()
 
+    # nvidia-smi needs a few hundred ms to start reporting (longer on an 8-GPU box) and the default timed region lasts ~0.1 s:
+    # the sampler runs from before the warm-up to after the timed region, and the same iteration keeps the GPU under the same load
+    # (untimed) until it has seen it for at least a second
+    clocks = ClockSampler(local)
+    t_load = time.perf_counter()
     for _ in range(max(3, args.warmup)):
         iteration()
     # ---- main measurement: states resident in HBM --------------------------------------------------------------
-    clocks = ClockSampler(local)
     l0 = lib.b200_launch_count()
     ms_total = timed(iteration, args.steps)
     launches = lib.b200_launch_count() - l0 + (graph_launches * args.steps if graph is not None else 0)
+    while time.perf_counter() - t_load < 1.2:
+        iteration()
+    torch.cuda.synchronize(dev)
     clock_info = clocks.stop()
     ms_step = ms_total / args.steps
     value = world * N * T / (ms_step * 1e-3)

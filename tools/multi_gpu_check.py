@@ -86,14 +86,26 @@ def main():
         bufd = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in buf.items()}
         omu, osig, olp = L.old_dist(sdd, bufd["obses"], bufd["actions"])
         adam, lr = L.new_adam(sdd), LR
+        outs, lrs = [], []
         for _ in range(3):
+            lrs.append(lr)
             o = L.epoch(sdd, adam, bufd, last_obs.double(), last_priv.double(), omu, osig, olp, lr)
             lr = o["lr"]
-        werr = 0.0
+            outs.append(o)
+        # Adam's update lr * m_hat / (sqrt(v_hat) + eps) is ~ lr * sign(g): an element whose gradient is small against the stated
+        # gradient tolerance (2e-4 of the tensor max, tests/test_gpu_learner.py) may legitimately move differently.  Same element-wise
+        # bound as the single-GPU test: sum over the steps of lr * min(2, 2 * 2e-4 * max|g| / |g_ij|), on top of 1e-5 relative.
+        werr, wviol = 0.0, 0.0
         for name, ref64 in sdd.items():
             ours = b.views()[name].cpu().double().reshape(ref64.shape)
-            werr = max(werr, (ours - ref64).abs().max().item())
-        assert werr <= 0.3 * LR * 3, werr   # Adam's sign-like steps: within 30 % of the distance moved (see tests/test_gpu_learner.py)
+            err = (ours - ref64).abs()
+            bound = torch.zeros_like(err)
+            for o_, lr_ in zip(outs, lrs):
+                g = o_["grads"][name].double().reshape(err.shape).abs()
+                bound += lr_ * torch.clamp(2.0 * 2e-4 * g.max() / g.clamp_min(1e-30), max=2.0)
+            werr = max(werr, err.max().item())
+            wviol = max(wviol, (err - bound - 1e-5 * ref64.abs().max()).max().item())
+        assert wviol <= 0.0, (wviol, werr)
         assert abs(sc_b[_abi.SC["LR"]].item() - lr) <= 1e-6 * lr
         assert abs(sc_b[_abi.SC["KL"]].item() - o["kl"]) <= 1e-4 * max(abs(o["kl"]), 1e-3) + 1e-7, (sc_b[_abi.SC["KL"]].item(), o["kl"])
         print(f"MULTI-GPU OK world={world}: peer vs NCCL {worst:.2e}, vs fp64 full batch {werr:.2e} (lr {lr:.3e})")
