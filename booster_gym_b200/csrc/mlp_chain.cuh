@@ -334,22 +334,37 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd(const __grid_constant_
                 CTL_WAIT(0, wait_collect<PAIR>(x_full, par, 200));
                 if (t > 0) CTL_WAIT(1, mbar_wait_wd(&accf[2], (t - 1) & 1, 201));   // layer 3 of the previous tile has finished READING h2 from c1's half
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                for (int kb = 0; kb < 2; ++kb) {
-                    uint32_t b_hi, b_lo;
-                    uint64_t *e0, *e1;
-                    weights(256, b_hi, b_lo, e0, e1, 210);
+                {
+                    // K = 64 is two k-blocks, both resident (X tile and all four weight units): issue the 16 small cross-term MMAs of
+                    // BOTH k-blocks first and the 8 dominant a_hi * b_hi MMAs last.  TMEM accumulation truncates on every add, by up to
+                    // an ulp of the accumulator: the small terms now land while the accumulator is ~2^-11 of its final size, which
+                    // leaves 8 instead of 24 full-size truncations on this layer (the 128-wide layers get the same effect from their
+                    // second accumulator).
+                    uint32_t b_hi[2], b_lo[2];
+                    uint64_t *e0[2], *e1[2];
+                    for (int kb = 0; kb < 2; ++kb) weights(256, b_hi[kb], b_lo[kb], e0[kb], e1[kb], 210);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t a_hi = sbase + F_X_HI + kb * KB_BYTES, a_lo = sbase + F_X_LO + kb * KB_BYTES;
                     constexpr uint32_t id = idesc_tf32_m(TM, 256);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t off = k * 32;
-                        mma_ss<PAIR>(c1, desc_kmajor(a_lo + off), desc_kmajor(b_hi + off), id, (kb | k) ? 1u : 0u);
-                        mma_ss<PAIR>(c1, desc_kmajor(a_hi + off), desc_kmajor(b_lo + off), id, 1u);
-                        mma_ss<PAIR>(c1, desc_kmajor(a_hi + off), desc_kmajor(b_hi + off), id, 1u);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint32_t a_hi = sbase + F_X_HI + kb * KB_BYTES, a_lo = sbase + F_X_LO + kb * KB_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t off = k * 32;
+                            mma_ss<PAIR>(c1, desc_kmajor(a_lo + off), desc_kmajor(b_hi[kb] + off), id, (kb | k) ? 1u : 0u);
+                            mma_ss<PAIR>(c1, desc_kmajor(a_hi + off), desc_kmajor(b_lo[kb] + off), id, 1u);
+                        }
                     }
-                    commit<PAIR>(e0);
-                    if (e1) commit<PAIR>(e1);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint32_t a_hi = sbase + F_X_HI + kb * KB_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mma_ss<PAIR>(c1, desc_kmajor(a_hi + k * 32), desc_kmajor(b_hi[kb] + k * 32), id, 1u);
+                    }
+                    for (int kb = 0; kb < 2; ++kb) {
+                        commit<PAIR>(e0[kb]);
+                        if (e1[kb]) commit<PAIR>(e1[kb]);
+                    }
                 }
                 commit<PAIR>(x_empty);
                 commit<PAIR>(&accf[0]);
