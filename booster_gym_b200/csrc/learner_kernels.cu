@@ -189,17 +189,27 @@ __global__ void k_weight_prep(const WeightPrepJobs jobs) {
     }
 }
 
-// critic head: V[m] = b + sum_k H[m,k] w[k], one warp per row (H rows are 128 floats = one float4 per lane)
-__global__ void k_value_head(const float* __restrict__ H, const float* __restrict__ w, const float* __restrict__ b, int n,
-                             float* __restrict__ V) {
-    const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const float4 h = reinterpret_cast<const float4*>(H + (size_t)warp * 128)[lane];
-    const float4 ww = reinterpret_cast<const float4*>(w)[lane];
-    float s = h.x * ww.x + h.y * ww.y + h.z * ww.z + h.w * ww.w;
+// critic head: V[m] = b + sum_k H[m,k] w[k].  Four lanes per row, eight rows per warp: every load instruction reads eight 64-byte row
+// segments (whole sectors), each lane forms the partial dot product of its 32 elements and two shuffles finish it - 6 instead of
+// ~20 warp instructions per row of the one-warp-per-row version.
+__global__ void __launch_bounds__(256) k_value_head(const float* __restrict__ H, const float* __restrict__ w, const float* __restrict__ b, int n,
+                                                    float* __restrict__ V) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, row = gt >> 2, sub = gt & 3;
+    const bool ok = row < n;
+    const float4* hp = reinterpret_cast<const float4*>(H + (size_t)(ok ? row : 0) * 128) + sub;
+    const float4* wp = reinterpret_cast<const float4*>(w) + sub;
+    float4 h[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) V[warp] = s + b[0];
+    for (int c = 0; c < 8; ++c) h[c] = ok ? __ldg(hp + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 ww = __ldg(wp + 4 * c);
+        s = fmaf(h[c].x, ww.x, s); s = fmaf(h[c].y, ww.y, s); s = fmaf(h[c].z, ww.z, s); s = fmaf(h[c].w, ww.w, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (ok && sub == 0) V[row] = s + b[0];
 }
 
 // backward of the critic head: dH[m,k] = dV[m] w[k] ELU'(H[m,k]); dw[k] += sum_m dV[m] H[m,k]; db += sum_m dV[m];
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(HB_THREADS) k_value_head_bwd(const float* __re
     const int r0 = blockIdx.x * HB_ROWS + warp * (HB_ROWS / 8), r1 = min(n, r0 + HB_ROWS / 8);
     float4 aw = make_float4(0.f, 0.f, 0.f, 0.f), ap = aw;
     float ab = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = r0; r < r1; ++r) {
         const float g = __ldg(dV + r);
         const float4 h = reinterpret_cast<const float4*>(H + (size_t)r * 128)[lane];
@@ -271,34 +281,53 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&p)[16], int lane)
     }
     return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 16);   // lane l (mod 16) now holds output index with bits (l&8 ? 8:0)|(l&4 ? 4:0)|...
 }
+// (the forward kernel below keeps W in shared memory and gives each row to FOUR lanes - 32 of its 128 hidden units each - so a row
+// costs 2 x 12 shuffles instead of the 32 of a 16-value butterfly per warp-row, and every LDS.128 of W feeds two rows)
 __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf, const float* __restrict__ W,
                                                     const float* __restrict__ b, int n, float* __restrict__ MU) {
-    const int lane = threadIdx.x & 31;
-    float4 w[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) w[j] = reinterpret_cast<const float4*>(W + j * 128)[lane];
-    // after the reduce-scatter lane l holds column j(l): step `half` keeps the upper half of the remaining index range on lanes
-    // with that bit set, so j = (l & 8) | (l & 4) | (l & 2) | (l & 1) = l & 15
-    const int jmine = lane & 15;
-    const float bj = (jmine < 12) ? b[jmine] : 0.0f;
+    __shared__ float4 sw[12][32];
+    for (int i = threadIdx.x; i < 12 * 32; i += 256) sw[i >> 5][i & 31] = reinterpret_cast<const float4*>(W)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane & 3, rl = lane >> 2;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    // two rows per iteration (both loads in flight); the second row's 12 outputs ride in the upper half-warp's butterfly slots
-    for (int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; row < n; row += 2 * warps) {
-        const bool two = row + 1 < n;
-        const float4 h0 = reinterpret_cast<const float4*>(Hf + (size_t)row * 128)[lane];
-        const float4 h1 = two ? reinterpret_cast<const float4*>(Hf + (size_t)(row + 1) * 128)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float p[16], q[16];
+    float bj[3];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            p[j] = h0.x * w[j].x + h0.y * w[j].y + h0.z * w[j].z + h0.w * w[j].w;
-            q[j] = h1.x * w[j].x + h1.y * w[j].y + h1.z * w[j].z + h1.w * w[j].w;
+    for (int t = 0; t < 3; ++t) bj[t] = b[3 * sub + t];
+    // a warp takes 16 rows per iteration: rows base + rl and base + 8 + rl
+    for (int base = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 16; base < n; base += 16 * warps) {
+        const int r0 = base + rl, r1 = base + 8 + rl;
+        const bool ok0 = r0 < n, ok1 = r1 < n;
+        const float4* p0 = reinterpret_cast<const float4*>(Hf + (size_t)(ok0 ? r0 : 0) * 128) + sub;
+        const float4* p1 = reinterpret_cast<const float4*>(Hf + (size_t)(ok1 ? r1 : 0) * 128) + sub;
+        float4 h0[8], h1[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { h0[c] = __ldg(p0 + 4 * c); h1[c] = __ldg(p1 + 4 * c); }
+        float a0[12], a1[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const float4 w4 = sw[j][4 * c + sub];
+                a0[j] = fmaf(h0[c].x, w4.x, a0[j]); a0[j] = fmaf(h0[c].y, w4.y, a0[j]); a0[j] = fmaf(h0[c].z, w4.z, a0[j]); a0[j] = fmaf(h0[c].w, w4.w, a0[j]);
+                a1[j] = fmaf(h1[c].x, w4.x, a1[j]); a1[j] = fmaf(h1[c].y, w4.y, a1[j]); a1[j] = fmaf(h1[c].z, w4.z, a1[j]); a1[j] = fmaf(h1[c].w, w4.w, a1[j]);
+            }
         }
 #pragma unroll
-        for (int j = 12; j < 16; ++j) p[j] = q[j] = 0.0f;
-        const float o0 = warp_reduce_scatter16(p, lane) + bj;
-        const float o1 = warp_reduce_scatter16(q, lane) + bj;
-        if (lane < 12) MU[(size_t)row * 12 + lane] = o0;
-        else if (lane >= 16 && lane < 28 && two) MU[(size_t)(row + 1) * 12 + (lane - 16)] = o1;
+        for (int j = 0; j < 12; ++j) {
+            a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], 1); a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], 2);
+            a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], 1); a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], 2);
+        }
+        // all four lanes of a row hold the 12 sums: lane `sub` stores outputs 3 sub .. 3 sub + 2
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) { if (j == 3 * sub + t) { v0 = a0[j]; v1 = a1[j]; } }
+            if (ok0) MU[(size_t)r0 * 12 + 3 * sub + t] = v0 + bj[t];
+            if (ok1) MU[(size_t)r1 * 12 + 3 * sub + t] = v1 + bj[t];
+        }
     }
 }
 
@@ -1262,14 +1291,14 @@ static int critic_forward_tc(B200Ppo* p, int M, cudaStream_t st) {
     int rc;
     if (g_chain) {
         if ((rc = chain_forward(p, critic_ptrs(p, M), actor_ptrs(p, 0), st))) return rc;
-        k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
+        k_value_head<<<(int)(((size_t)M * 4 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
         g_launches += 1;
         return launch_status("k_value_head");
     }
     if ((rc = tc_fwd(p, ws + w.Xc, 61, 64, ws + w.Wc0h, ws + w.Wc0l, 64, p->P(P_CB0), ws + w.C1, M, 256, st))) return rc;
     if ((rc = tc_fwd(p, ws + w.C1, 256, 256, ws + w.Wc1h, ws + w.Wc1l, 256, p->P(P_CB1), ws + w.C2, M, 256, st))) return rc;
     if ((rc = tc_fwd(p, ws + w.C2, 256, 256, ws + w.Wc2h, ws + w.Wc2l, 256, p->P(P_CB2), ws + w.C3, M, 128, st))) return rc;
-    k_value_head<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
+    k_value_head<<<(int)(((size_t)M * 4 + 255) / 256), 256, 0, st>>>(ws + w.C3, p->P(P_CW3), p->P(P_CB3), M, ws + w.V);
     g_launches += 1;
     return launch_status("k_value_head");
 }
@@ -1370,7 +1399,7 @@ int b200_critic_value(B200Ppo* p, const float* obs, const float* priv, int n, fl
     ChainNetPtrs c = critic_ptrs(p, n);
     c.Xh = ws + w.LXh; c.Xl = ws + w.LXl; c.H1 = ws + w.L1; c.H2 = ws + w.L2; c.H3 = ws + w.L3;
     if ((rc = chain_forward(p, c, actor_ptrs(p, 0), st)) != B200_OK) return rc;
-    k_value_head<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(ws + w.L3, p->P(P_CW3), p->P(P_CB3), n, values);
+    k_value_head<<<(int)(((size_t)n * 4 + 255) / 256), 256, 0, st>>>(ws + w.L3, p->P(P_CW3), p->P(P_CB3), n, values);
     g_launches += 1;
     return launch_status("k_value_head");
 }
@@ -1397,7 +1426,7 @@ int b200_gae(float* rewards, const uint8_t* dones, const uint8_t* time_outs, con
              void* stream) {
     if (!rewards || !dones || !time_outs || !values || !last_values || !advantages || !returns || horizon <= 0 || num_envs <= 0)
         return set_error(B200_ERR_ARG, "b200_gae: bad argument");
-    k_gae<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, dones, time_outs, values, last_values,
+    k_gae<<<(num_envs + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rewards, dones, time_outs, values, last_values,
                                                                       (float)gamma, (float)(gamma * lam), horizon,
                                                                       num_envs, advantages, returns, stats);
     g_launches += 1;
@@ -1424,12 +1453,12 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
         // both nets in ONE persistent launch: 800 critic + 768 actor tiles balance over the SMs better than two launches of ~5.3
         // waves each; the actor's mu is not needed before epoch_b's loss
         if ((rc = chain_forward(p, critic_ptrs(p, M + N), actor_ptrs(p, M), st)) != B200_OK) return rc;
-        k_value_head<<<(int)(((size_t)(M + N) * 32 + 255) / 256), 256, 0, st>>>(ws + p->w.C3, p->P(P_CW3), p->P(P_CB3), M + N, ws + p->w.V);
+        k_value_head<<<(int)(((size_t)(M + N) * 4 + 255) / 256), 256, 0, st>>>(ws + p->w.C3, p->P(P_CW3), p->P(P_CB3), M + N, ws + p->w.V);
         k_actor_head<<<1184, 256, 0, st>>>(ws + p->w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + p->w.MU);
         g_launches += 2;
         p->actor_fwd_done = true;
     } else if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
-    k_gae<<<(N + 127) / 128, 128, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
+    k_gae<<<(N + 31) / 32, 32, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
     g_launches += 3;  // memset, k_pack_inputs, k_gae
     if (p->peers) {   // this rank's advantage moments -> peers (summed in epoch_b, behind the actor forward)
