@@ -955,7 +955,7 @@ struct GemmProfile {
 } g_prof;
 
 static bool g_tc_pair = getenv("B200_TC_PAIR") ? atoi(getenv("B200_TC_PAIR")) != 0 : false;   // cta_group::2 GEMMs (b200_tc_set_pair)
-static bool g_chain_exact_actor = getenv("B200_CHAIN_EXACT_ELU") ? atoi(getenv("B200_CHAIN_EXACT_ELU")) != 0 : false;   // debug: 1 = single accumulator for the 128-wide layers
+static int g_chain_exact_actor = getenv("B200_CHAIN_DEBUG") ? atoi(getenv("B200_CHAIN_DEBUG")) : 0;   // debug: 1 = single accumulator for the 128-wide layers
 static bool g_chain_pair = getenv("B200_CHAIN_PAIR") ? atoi(getenv("B200_CHAIN_PAIR")) != 0 : false;   // chains on CTA pairs (cta_group::2)
 static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
@@ -1158,12 +1158,12 @@ static int chain_fill_fwd(const B200Ppo* p, chain::FwdNet& N, const ChainNetPtrs
 static ChainNetPtrs critic_ptrs(const B200Ppo* p, int rows) {
     float* ws = p->ws; const Workspace& w = p->w;
     return ChainNetPtrs{ws + w.Xch, ws + w.Xcl, ws + w.Wc0h, ws + w.Wc0l, ws + w.Wc1h, ws + w.Wc1l, ws + w.Wc2h, ws + w.Wc2l,
-                        p->P(P_CB0), p->P(P_CB1), p->P(P_CB2), ws + w.C1, ws + w.C2, ws + w.C3, rows, 256, g_chain_exact_actor ? 1 : 0, 61};
+                        p->P(P_CB0), p->P(P_CB1), p->P(P_CB2), ws + w.C1, ws + w.C2, ws + w.C3, rows, 256, g_chain_exact_actor, 61};
 }
 static ChainNetPtrs actor_ptrs(const B200Ppo* p, int rows) {
     float* ws = p->ws; const Workspace& w = p->w;
     return ChainNetPtrs{ws + w.Xah, ws + w.Xal, ws + w.Wa0h, ws + w.Wa0l, ws + w.Wa1h, ws + w.Wa1l, ws + w.Wa2h, ws + w.Wa2l,
-                        p->P(P_AB0), p->P(P_AB1), p->P(P_AB2), ws + w.A1, ws + w.A2, ws + w.A3, rows, 128, g_chain_exact_actor ? 1 : 0, 47};
+                        p->P(P_AB0), p->P(P_AB1), p->P(P_AB2), ws + w.A1, ws + w.A2, ws + w.A3, rows, 128, g_chain_exact_actor, 47};
 }
 // one persistent CTA per SM, or (pair) one cluster of two CTAs per TPC
 template <typename Params>
