@@ -63,6 +63,7 @@ PROTOTYPES = {
     "b200_tc_set_pair": (_i, [_i]),
     "b200_fma_peak": (_i, [C.POINTER(_d), _vp]),
     "b200_tc_set_chain": (_i, [_i]),
+    "b200_tc_set_h2": (_i, [_i]),
 }
 
 

@@ -753,7 +753,8 @@ struct MapCache {
     }
     // MN-major operand tiles of k_tc_wgrad: the fp32 matrix [rows, cols] (cols a multiple of 32, leading dimension ld) viewed as
     // (32 floats, rows, cols / 32); box = (32, box_rows, box_chunks) with the BASE32B swizzle
-    const CUtensorMap* get3(const float* base, int rows, int cols, int ld, int box_rows, int box_chunks) {
+    // swz128 = true: plain SWIZZLE_128B (16-bit MN-major operands: the h2 words of h2.cuh viewed as fp16 pairs)
+    const CUtensorMap* get3(const float* base, int rows, int cols, int ld, int box_rows, int box_chunks, bool swz128 = false) {
         if (!enc) {
             void* fn = nullptr;
             cudaDriverEntryPointQueryResult q;
@@ -763,7 +764,7 @@ struct MapCache {
             }
             enc = (EncodeTiledFn)fn;
         }
-        auto key = std::make_tuple((const void*)base, rows, cols, ld, box_rows, 1000 + box_chunks);
+        auto key = std::make_tuple((const void*)base, rows, cols, ld, box_rows, (swz128 ? 2000 : 1000) + box_chunks);
         auto it = maps.find(key);
         if (it != maps.end()) return &it->second;
         CUtensorMap m;
@@ -772,7 +773,8 @@ struct MapCache {
         cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
         cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               swz128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             error = "cuTensorMapEncodeTiled (3-D) failed";
             return nullptr;

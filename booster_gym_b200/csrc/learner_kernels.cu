@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "mlp_chain.cuh"
+#include "h2.cuh"
 #include "rng.cuh"
 
 using namespace b200;
@@ -61,6 +62,12 @@ struct Workspace {
     size_t Wc0h, Wc0l, Wc1h, Wc1l, Wc2h, Wc2l, Wa0h, Wa0l, Wa1h, Wa1l, Wa2h, Wa2l;   // split weights, K padded to 64 for layer 0
     size_t Wc1Th, Wc1Tl, Wc2Th, Wc2Tl, Wa1Th, Wa1Tl, Wa2Th, Wa2Tl;                  // transposed split weights for dgrad
     size_t LXc, LXh, LXl, L1, L2, L3, LV;                // N-row fp32 buffers of b200_critic_value
+    // ---- h2 operand format (h2.cuh): two fp16 halves per 32-bit word, power-of-two scales
+    size_t SC;                                          // h2::SC_COUNT floats: gradient scales of this epoch (k_finalize_loss)
+    size_t ZR;                                          // zeroed by weight_prep: uint32 amax[64] (|dV|, |dmu| of k_loss), float colabs[4][256]
+    size_t PXa, PXc, PA1, PA2, PC1, PC2;                // h2 words of the inputs / activations (operands of the weight-gradient kernel)
+    size_t PGA3, PGA2, PGA1, PGC3, PGC2, PGC1;          // h2 words of dL/dz
+    size_t WP2;                                         // partial tiles of k_wgrad_h2 [CTA][128][128]
     size_t total;
 };
 static Workspace make_workspace(int T, int N) {
@@ -85,6 +92,10 @@ static Workspace make_workspace(int T, int N) {
     w.Wa1Th = take(256 * 128); w.Wa1Tl = take(256 * 128); w.Wa2Th = take(128 * 128); w.Wa2Tl = take(128 * 128);
     w.LXc = take(n * 64); w.LXh = take(n * 64); w.LXl = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
     w.LV = take(n);
+    w.SC = take(h2::SC_COUNT); w.ZR = take(64 + 4 * 256);
+    w.PXa = take(M * 64); w.PXc = take(M * 64); w.PA1 = take(M * 256); w.PA2 = take(M * 128); w.PC1 = take(M * 256); w.PC2 = take(M * 256);
+    w.PGA3 = take(M * 128); w.PGA2 = take(M * 128); w.PGA1 = take(M * 256); w.PGC3 = take(M * 128); w.PGC2 = take(M * 256); w.PGC1 = take(M * 256);
+    w.WP2 = take((size_t)WP_MAX_CTAS * 128 * 128);
     w.total = o;
     return w;
 }
@@ -164,6 +175,7 @@ struct WeightPrepJob {
     const float* W;
     float *Wh, *Wl, *WTh, *WTl;
     int rows, cols, cols_pad;
+    float* colabs;    // nullable: colabs[c] += |W[r, c]| (bound of the input-gradient magnitudes, k_finalize_loss)
 };
 struct WeightPrepJobs {
     WeightPrepJob j[6];
@@ -183,6 +195,7 @@ __global__ void k_weight_prep(const WeightPrepJobs jobs) {
     split_tf32f(c < cols ? W[(size_t)r * cols + c] : 0.0f, hi, lo);
     Wh[idx] = hi;
     Wl[idx] = lo;
+    if (q.colabs && c < cols) atomicAdd(q.colabs + c, fabsf(W[(size_t)r * cols + c]));
     if (WTh && c < cols) {
         WTh[(size_t)c * rows + r] = hi;
         WTl[(size_t)c * rows + r] = lo;
@@ -673,8 +686,9 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
                                                      const float* __restrict__ old_logp, const float* __restrict__ logstd,
                                                      const float* __restrict__ scalars, double* __restrict__ dstats, int M,
                                                      float e_clip, float bound_coef, float* __restrict__ dV,
-                                                     float* __restrict__ dMU) {
+                                                     float* __restrict__ dMU, unsigned int* __restrict__ amax) {
     const int m = blockIdx.x * LOSS_BLOCK + threadIdx.x;
+    float mx_v = 0.0f, mx_mu = 0.0f;   // largest |dV|, |dmu| of this thread (h2 gradient scale, k_finalize_loss)
     const double cnt = dstats[DS_ADV_COUNT];
     const double mean_d = dstats[DS_ADV_SUM] / cnt;
     const double var_d = fmax((dstats[DS_ADV_SUMSQ] - dstats[DS_ADV_SUM] * mean_d) / (cnt - 1.0), 0.0);
@@ -698,6 +712,7 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
         const float dv = __fsub_rn(v, rt);
         red[0] = dv * dv;
         dV[m] = 2.0f * dv * invM;
+        mx_v = fabsf(2.0f * dv * invM);
         // surrogate
         const float A = __fdiv_rn(__fsub_rn(adv[m], a_mean), __fadd_rn(a_std, 1.0e-8f));
         const float lp = normal_logp12(a, u, sg, ls);
@@ -725,7 +740,9 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
             ent += 0.5f + LOG_SQRT_2PI + ls[j];
             const float dm = u[j] - old_mu[(size_t)m * 12 + j];
             kl += logf(sg[j] / sg_old[j]) + 0.5f * (sg_old[j] * sg_old[j] + dm * dm) / var - 0.5f;
-            dMU[(size_t)m * 12 + j] = dlp * d / var + bscale * (up + dn);
+            const float dmu_j = dlp * d / var + bscale * (up + dn);
+            dMU[(size_t)m * 12 + j] = dmu_j;
+            mx_mu = fmaxf(mx_mu, fabsf(dmu_j));
             red[6 + j] = dlp * (d * d / var - 1.0f);
         }
         red[2] = bsum;
@@ -744,6 +761,16 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0) sh[warp][i] = x;
+    }
+    if (amax) {
+        // non-negative floats order like their bit patterns; NaN / Inf are left out (the scale falls back to 1)
+        unsigned bv = isfinite(mx_v) ? __float_as_uint(mx_v) : 0u, bm = isfinite(mx_mu) ? __float_as_uint(mx_mu) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bv = max(bv, __shfl_xor_sync(0xffffffffu, bv, o));
+            bm = max(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        }
+        if (lane == 0) { if (bv) atomicMax(amax + 0, bv); if (bm) atomicMax(amax + 1, bm); }
     }
     __syncthreads();
     if (threadIdx.x < LOSS_NRED) {
@@ -857,9 +884,49 @@ __global__ void k_xchg_reduce_stats(const PeerX x, double* __restrict__ dstats, 
 }
 
 // logstd gradient = reduced surrogate part + entropy_coef * d mean(entropy) / d logstd_j (= entropy_coef)
-__global__ void k_finalize_logstd(const double* __restrict__ dstats, float entropy_coef, float* __restrict__ g_logstd) {
-    const int j = threadIdx.x;
-    if (j < 12) g_logstd[j] = (float)dstats[DS_DLOGSTD + j] + entropy_coef;
+// + the h2 gradient scales of this epoch (h2.cuh): a power of two per net such that a RIGOROUS bound of every dL/dz magnitude of
+// the net maps below 2^15 (fp16 max 65504):  |dz3| <= max|dhead| * max_k sum_j |W_head[j,k]|,  |dz2| <= |dz3|_max * max_k sum_n |W3[n,k]|
+// (ELU' <= 1),  |dz1| likewise with W2.  max|dV|, max|dmu| come from k_loss, the column abs-sums from k_weight_prep.
+__global__ void __launch_bounds__(256) k_finalize_loss(const double* __restrict__ dstats, float entropy_coef, float* __restrict__ g_logstd,
+                                                       const float* __restrict__ Wa3, const float* __restrict__ wc3,
+                                                       const unsigned int* __restrict__ amax, const float* __restrict__ cab,
+                                                       float* __restrict__ sc) {
+    const int t = threadIdx.x;
+    if (t < 12) g_logstd[t] = (float)dstats[DS_DLOGSTD + t] + entropy_coef;
+    if (!sc) return;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // actor head, critic head, Wc3, Wc2, Wa3, Wa2 (column abs-sums)
+    if (t < 128) {
+        float s = 0.0f;
+        for (int j = 0; j < 12; ++j) s += fabsf(Wa3[j * 128 + t]);
+        v[0] = s;
+        v[1] = fabsf(wc3[t]);
+        v[4] = cab[2 * 256 + t];
+    }
+    v[2] = cab[0 * 256 + t];
+    v[3] = cab[1 * 256 + t];
+    v[5] = cab[3 * 256 + t];
+    __shared__ float red[8][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
+        if ((t & 31) == 0) red[t >> 5][i] = v[i];
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int i = 0; i < 6; ++i)
+            for (int w = 1; w < 8; ++w) v[i] = fmaxf(v[i], red[w][i]);
+        const float bound_c = __uint_as_float(amax[0]) * v[1] * fmaxf(1.0f, fmaxf(v[2], v[2] * v[3]));
+        const float bound_a = __uint_as_float(amax[1]) * v[0] * fmaxf(1.0f, fmaxf(v[4], v[4] * v[5]));
+        const float b[2] = {bound_c, bound_a};
+        for (int i = 0; i < 2; ++i) {
+            int e = 0;
+            if (b[i] > 0.0f && isfinite(b[i])) e = 14 - ilogbf(b[i]);   // bound * 2^e < 2^15
+            e = max(-100, min(100, e));
+            sc[2 * i] = ldexpf(1.0f, e);
+            sc[2 * i + 1] = ldexpf(1.0f, -e);
+        }
+    }
 }
 
 // clip_grad_norm_ part 1 (utils/runner.py:164): sum of squares of the (world-averaged) flat gradient
@@ -958,6 +1025,7 @@ static bool g_tc_pair = getenv("B200_TC_PAIR") ? atoi(getenv("B200_TC_PAIR")) !=
 static int g_chain_exact_actor = getenv("B200_CHAIN_DEBUG") ? atoi(getenv("B200_CHAIN_DEBUG")) : 0;   // debug: 1 = single accumulator for the 128-wide layers
 static bool g_chain_pair = getenv("B200_CHAIN_PAIR") ? atoi(getenv("B200_CHAIN_PAIR")) != 0 : false;   // chains on CTA pairs (cta_group::2)
 static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
+static bool g_h2_wgrad = getenv("B200_H2_WGRAD") ? atoi(getenv("B200_H2_WGRAD")) != 0 : false;   // weight gradients on the h2 format (h2.cuh)
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
 static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
 static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC, double bytes = 0.0) {
@@ -1120,9 +1188,13 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
         {P_AW1, 128, 256, 256, w.Wa1h, w.Wa1l, w.Wa1Th, w.Wa1Tl, true}, {P_AW2, 128, 128, 128, w.Wa2h, w.Wa2l, w.Wa2Th, w.Wa2Tl, true}};
     WeightPrepJobs wj;
     int max_total = 0;
+    // column abs-sums of the four matrices an input gradient passes through: [0] critic.4, [1] critic.2, [2] actor.4, [3] actor.2
+    static const int cab_slot[6] = {-1, 1, 0, -1, 3, 2};
+    CU_TRY(cudaMemsetAsync(ws + w.ZR, 0, (64 + 4 * 256) * sizeof(float), st));
     for (int i = 0; i < 6; ++i) {
         const Job& j = jobs[i];
-        wj.j[i] = WeightPrepJob{p->P(j.pi), ws + j.h, ws + j.l, j.tr ? ws + j.th : nullptr, j.tr ? ws + j.tl : nullptr, j.rows, j.cols, j.pad};
+        wj.j[i] = WeightPrepJob{p->P(j.pi), ws + j.h, ws + j.l, j.tr ? ws + j.th : nullptr, j.tr ? ws + j.tl : nullptr, j.rows, j.cols, j.pad,
+                                cab_slot[i] >= 0 ? ws + w.ZR + 64 + cab_slot[i] * 256 : nullptr};
         max_total = j.rows * j.pad > max_total ? j.rows * j.pad : max_total;
     }
     k_weight_prep<<<dim3((max_total + 255) / 256, 6), 256, 0, st>>>(wj);
@@ -1266,6 +1338,77 @@ static int chain_backward(B200Ppo* p, int M, bool critic, bool actor, cudaStream
     g_launches += 1;
     if (le != cudaSuccess) return set_cuda_error(le, "k_mlp_bwd");
     return launch_status("k_mlp_bwd");
+}
+
+// ---- weight gradients on the h2 operand format (h2.cuh): all six hidden-layer matrices in one launch + one reduction ----------
+struct WgH2Operand { const float* dY; const float* X; int n_out, k_cols, k_valid; int pi; bool actor; float sx; };
+static int h2_pack(const float* src, float* dst, size_t n, float scale, const float* scale_ptr, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    h2::k_h2_pack<<<blocks, 256, 0, st>>>(src, reinterpret_cast<uint32_t*>(dst), n4, scale, scale_ptr);
+    g_launches += 1;
+    return launch_status("k_h2_pack");
+}
+static int wgrad_h2(B200Ppo* p, const WgH2Operand* ops, int M, cudaStream_t st) {
+    h2::WgParams P;
+    h2::WgRedJobs R;
+    memset(&P, 0, sizeof(P));
+    memset(&R, 0, sizeof(R));
+    // tiles (n-major, then k) and their cost per row: a 64-column tile issues half-width MMAs and loads 3/4 of the bytes
+    double cost[h2::WG_MAX_TILES];
+    int nt = 0, total = 0;
+    double flops = 0.0, bytes = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        const WgH2Operand& o = ops[j];
+        const int kch = o.k_cols >= 128 ? 4 : 2;
+        const CUtensorMap* mY = p->maps->get3(o.dY, M, o.n_out, o.n_out, h2::WG2_ROWS, 4, true);
+        const CUtensorMap* mX = p->maps->get3(o.X, M, o.k_cols, o.k_cols, h2::WG2_ROWS, kch, true);
+        if (!mY || !mX) return set_error(B200_ERR_CUDA, p->maps->error ? p->maps->error : "tensor map creation failed");
+        P.mY[j] = *mY; P.mX[j] = *mX; P.kchunks[j] = kch;
+        const int tn = o.n_out / 128, tk = (o.k_cols + 127) / 128;
+        h2::WgRedJob& r = R.job[j];
+        r.D = p->G(o.pi); r.isg = p->ws + p->w.SC + (o.actor ? h2::SC_ISG_A : h2::SC_ISG_C); r.inv_sx = 1.0f / o.sx;
+        r.n_out = o.n_out; r.k_valid = o.k_valid; r.ldd = o.k_valid; r.tile0 = nt; r.tiles_k = tk; r.first = total;
+        total += o.n_out * o.k_valid;
+        for (int a = 0; a < tn; ++a)
+            for (int b = 0; b < tk; ++b, ++nt) {
+                if (nt >= h2::WG_MAX_TILES) return set_error(B200_ERR_ARG, "wgrad_h2: too many tiles");
+                P.tile[nt].job = j; P.tile[nt].n0 = a * 128; P.tile[nt].k0 = b * 128;
+                cost[nt] = kch == 4 ? 1.0 : 0.6;
+            }
+        flops += 2.0 * M * (double)o.n_out * o.k_valid;
+        bytes += 4.0 * M * ((double)o.n_out + o.k_cols);
+    }
+    // one wave: the smallest per-CTA budget B with sum ceil(M cost / B) <= CTAs
+    const int ctas = p->num_sms < WP_MAX_CTAS ? p->num_sms : WP_MAX_CTAS;
+    double lo = 1.0, hi = (double)M * 2.0;
+    for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        long long need = 0;
+        for (int t = 0; t < nt; ++t) need += (long long)ceil(M * cost[t] / mid);
+        if (need <= ctas) hi = mid; else lo = mid;
+    }
+    int first = 0;
+    for (int t = 0; t < nt; ++t) {
+        int parts = (int)ceil(M * cost[t] / hi);
+        if (parts < 1) parts = 1;
+        int chunk = ((M + parts - 1) / parts + 31) / 32 * 32;
+        parts = (M + chunk - 1) / chunk;
+        P.tile[t].first = first; P.tile[t].parts = parts; P.tile[t].chunk = chunk;
+        first += parts;
+    }
+    if (first > WP_MAX_CTAS) return set_error(B200_ERR_ARG, "wgrad_h2: work split exceeds the partial-tile buffer");
+    P.ntiles = nt; P.M = M; P.P = p->ws + p->w.WP2;
+    memcpy(R.tile, P.tile, sizeof(P.tile));
+    R.P = P.P; R.count = 6; R.total = total;
+    static unsigned long long configured = 0;
+    CU_TRY(ensure_dynamic_smem(h2::k_wgrad_h2, h2::WG2_SMEM, configured));
+    prof_begin(st, flops, PK_TC_WGRAD, bytes);
+    h2::k_wgrad_h2<<<first, h2::WG2_THREADS, h2::WG2_SMEM, st>>>(P);
+    prof_end(st);
+    h2::k_wgrad_h2_reduce<<<(total + 255) / 256, 256, 0, st>>>(R);
+    g_launches += 2;
+    return launch_status("k_wgrad_h2");
 }
 
 static int actor_forward_tc(B200Ppo* p, int M, cudaStream_t st) {
@@ -1489,8 +1632,9 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     }
     k_loss<<<(M + LOSS_BLOCK - 1) / LOSS_BLOCK, LOSS_BLOCK, 0, st>>>(ws + w.V, ws + w.RET, ws + w.ADV, MU, actions, old_mu, old_logp,
                                                                     p->P(P_LOGSTD), p->scalars, p->dstats, M, p->cfg.e_clip,
-                                                                    p->cfg.bound_coef, DV, DMU);
-    k_finalize_logstd<<<1, 32, 0, st>>>(p->dstats, p->cfg.entropy_coef, p->G(P_LOGSTD));
+                                                                    p->cfg.bound_coef, DV, DMU, reinterpret_cast<unsigned int*>(ws + w.ZR));
+    k_finalize_loss<<<1, 256, 0, st>>>(p->dstats, p->cfg.entropy_coef, p->G(P_LOGSTD), p->P(P_AW3), p->P(P_CW3),
+                                       reinterpret_cast<const unsigned int*>(ws + w.ZR), ws + w.ZR + 64, ws + w.SC);
     g_launches += 3;  // memset, k_loss, k_finalize_logstd
     if ((rc = launch_status("k_loss")) != B200_OK) return rc;
     if (g_chain) {
@@ -1502,6 +1646,27 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
         g_launches += 2;
         if ((rc = launch_status("k_head_bwd")) != B200_OK) return rc;
         if ((rc = chain_backward(p, M, true, true, st))) return rc;
+        if (g_h2_wgrad) {
+            // bring-up path: the TF32 chains' fp32 tensors packed into h2 words by an extra pass (the h2 chains write the words themselves)
+            const float* sga = ws + w.SC + h2::SC_SG_A;
+            const float* sgc = ws + w.SC + h2::SC_SG_C;
+            struct PK { const float* src; size_t dst; size_t n; float s; const float* sp; };
+            const size_t m = (size_t)M;
+            const PK pk[12] = {{ws + w.Xa, w.PXa, m * 64, h2::S_X, nullptr},   {ws + w.Xc, w.PXc, m * 64, h2::S_X, nullptr},
+                               {ws + w.A1, w.PA1, m * 256, h2::S_ACT, nullptr}, {ws + w.A2, w.PA2, m * 128, h2::S_ACT, nullptr},
+                               {ws + w.C1, w.PC1, m * 256, h2::S_ACT, nullptr}, {ws + w.C2, w.PC2, m * 256, h2::S_ACT, nullptr},
+                               {GA3, w.PGA3, m * 128, 1.0f, sga}, {GA2, w.PGA2, m * 128, 1.0f, sga}, {GA1, w.PGA1, m * 256, 1.0f, sga},
+                               {GC3, w.PGC3, m * 128, 1.0f, sgc}, {GC2, w.PGC2, m * 256, 1.0f, sgc}, {GC1, w.PGC1, m * 256, 1.0f, sgc}};
+            for (int i = 0; i < 12; ++i)
+                if ((rc = h2_pack(pk[i].src, ws + pk[i].dst, pk[i].n, pk[i].s, pk[i].sp, st))) return rc;
+            const WgH2Operand ops[6] = {{ws + w.PGA3, ws + w.PA2, 128, 128, 128, P_AW2, true, h2::S_ACT},
+                                        {ws + w.PGA2, ws + w.PA1, 128, 256, 256, P_AW1, true, h2::S_ACT},
+                                        {ws + w.PGA1, ws + w.PXa, 256, 64, 47, P_AW0, true, h2::S_X},
+                                        {ws + w.PGC3, ws + w.PC2, 128, 256, 256, P_CW2, false, h2::S_ACT},
+                                        {ws + w.PGC2, ws + w.PC1, 256, 256, 256, P_CW1, false, h2::S_ACT},
+                                        {ws + w.PGC1, ws + w.PXc, 256, 64, 61, P_CW0, false, h2::S_X}};
+            return wgrad_h2(p, ops, M, st);
+        }
         if ((rc = tc_wgrad(p, jobs, 0, GA3, 128, ws + w.A2, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
         if ((rc = tc_wgrad(p, jobs, 1, GA2, 128, ws + w.A1, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
         if ((rc = tc_wgrad(p, jobs, 2, GA1, 256, ws + w.Xa, 64, 64, 47, p->G(P_AW0), M, st))) return rc;
@@ -1579,6 +1744,10 @@ int b200_ppo_bind_peers(B200Ppo* p, const unsigned long long* buffer_ptrs, int r
 }
 int b200_tc_set_pair(int enable) {
     g_tc_pair = enable != 0;
+    return B200_OK;
+}
+int b200_tc_set_h2(int mode) {
+    g_h2_wgrad = (mode & 1) != 0;
     return B200_OK;
 }
 int b200_tc_set_chain(int enable) {

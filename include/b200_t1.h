@@ -323,6 +323,10 @@ int b200_fma_peak(double* tflops, void* stream);
  * tiles, each CTA stages half of every weight k-block), 0 = one GEMM launch per layer (k_tc_rowmajor).  Same results within the
  * stated tolerances; replaces the autograd graph of utils/runner.py:132-133,148,163. */
 int b200_tc_set_chain(int enable);
+/* operand format of the hidden-layer GEMMs (h2.cuh): bit 0 = weight gradients, bit 1 = forward / input-gradient chains on "h2 words"
+ * (two fp16 halves per 32-bit word, power-of-two scales, tcgen05.mma kind::f16: twice the kind::tf32 rate, fp32-class products);
+ * 0 = the 3xTF32 kernels.  Same results within the stated tolerances. */
+int b200_tc_set_h2(int mode);
 
 #ifdef __cplusplus
 }
