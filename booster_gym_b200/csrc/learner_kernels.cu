@@ -20,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "mlp_chain.cuh"
 #include "h2.cuh"
+#include "mlp_chain_h2.cuh"
 #include "rng.cuh"
 
 using namespace b200;
@@ -150,6 +151,7 @@ __device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
 // weight-gradient GEMMs) and pre-split into tf32 hi / lo (A operand of the fused chain's first layer).  Any output may be null.
 struct PackOut {
     float *Xa, *Xah, *Xal, *Xc, *Xch, *Xcl;
+    int h2;   // 1: Xah / Xch receive h2 words (h2.cuh) instead of tf32 hi halves, Xal / Xcl are not written
 };
 __global__ void k_pack_inputs(const float* __restrict__ obs, const float* __restrict__ priv, int n, const PackOut o) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,11 +162,17 @@ __global__ void k_pack_inputs(const float* __restrict__ obs, const float* __rest
     float v = 0.0f;
     if (c < 47) v = obs[r * 47 + c];
     else if (c < 61 && priv) v = priv[r * 14 + (c - 47)];
+    const bool a = c < 47;
+    if (o.h2) {
+        const float wv = __uint_as_float(h2::pack_clamped(v * h2::S_X));
+        if (o.Xch) o.Xch[idx] = wv;
+        if (o.Xah) o.Xah[idx] = a ? wv : 0.0f;
+        return;
+    }
     float hi, lo;
     split_tf32f(v, hi, lo);
     if (o.Xc) o.Xc[idx] = v;
     if (o.Xch) { o.Xch[idx] = hi; o.Xcl[idx] = lo; }
-    const bool a = c < 47;
     if (o.Xa) o.Xa[idx] = a ? v : 0.0f;
     if (o.Xah) { o.Xah[idx] = a ? hi : 0.0f; o.Xal[idx] = a ? lo : 0.0f; }
 }
@@ -179,6 +187,7 @@ struct WeightPrepJob {
 };
 struct WeightPrepJobs {
     WeightPrepJob j[6];
+    int h2;   // 1: Wh / WTh receive the h2 words of S_W * w (B'), Wl / WTl the same words with their halves swapped (B'')
 };
 __global__ void k_weight_prep(const WeightPrepJobs jobs) {
     const WeightPrepJob& q = jobs.j[blockIdx.y];
@@ -192,7 +201,13 @@ __global__ void k_weight_prep(const WeightPrepJobs jobs) {
     if (idx >= rows * cols_pad) return;
     const int r = idx / cols_pad, c = idx - r * cols_pad;
     float hi, lo;
-    split_tf32f(c < cols ? W[(size_t)r * cols + c] : 0.0f, hi, lo);
+    if (jobs.h2) {
+        const uint32_t wa = h2::pack_clamped((c < cols ? W[(size_t)r * cols + c] : 0.0f) * h2::S_W);
+        hi = __uint_as_float(wa);
+        lo = __uint_as_float(h2::swap_halves(wa));
+    } else {
+        split_tf32f(c < cols ? W[(size_t)r * cols + c] : 0.0f, hi, lo);
+    }
     Wh[idx] = hi;
     Wl[idx] = lo;
     if (q.colabs && c < cols) atomicAdd(q.colabs + c, fabsf(W[(size_t)r * cols + c]));
@@ -233,7 +248,9 @@ __global__ void __launch_bounds__(256) k_value_head(const float* __restrict__ H,
 #define HB_THREADS 256
 __global__ void __launch_bounds__(HB_THREADS) k_value_head_bwd(const float* __restrict__ H, const float* __restrict__ w,
                                                                const float* __restrict__ dV, int n, float* __restrict__ dH,
-                                                               float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev) {
+                                                               float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev,
+                                                               const float* __restrict__ sg) {
+    const float gs = sg ? sg[0] : 0.0f;   // != 0: dH is written as h2 words of gs * dH (h2.cuh)
     __shared__ float4 red[2][HB_THREADS / 32][32];
     __shared__ float redb[HB_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,7 +267,13 @@ __global__ void __launch_bounds__(HB_THREADS) k_value_head_bwd(const float* __re
         d.y = g * w4.y * ((h.y > 0.0f) ? 1.0f : (h.y + 1.0f));
         d.z = g * w4.z * ((h.z > 0.0f) ? 1.0f : (h.z + 1.0f));
         d.w = g * w4.w * ((h.w > 0.0f) ? 1.0f : (h.w + 1.0f));
-        reinterpret_cast<float4*>(dH + (size_t)r * 128)[lane] = d;
+        if (gs != 0.0f) {
+            uint4 wd;
+            wd.x = h2::pack(d.x * gs); wd.y = h2::pack(d.y * gs); wd.z = h2::pack(d.z * gs); wd.w = h2::pack(d.w * gs);
+            reinterpret_cast<uint4*>(dH + (size_t)r * 128)[lane] = wd;
+        } else {
+            reinterpret_cast<float4*>(dH + (size_t)r * 128)[lane] = d;
+        }
         aw.x = fmaf(g, h.x, aw.x); aw.y = fmaf(g, h.y, aw.y); aw.z = fmaf(g, h.z, aw.z); aw.w = fmaf(g, h.w, aw.w);
         ap.x += d.x; ap.y += d.y; ap.z += d.z; ap.w += d.w;
         ab += g;
@@ -349,7 +372,9 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ Hf
 // units per lane (coalesced 512-byte rows), W and the 12 x 4 dW partials in registers; block-level combine in shared memory.
 __global__ void __launch_bounds__(HB_THREADS, 2) k_actor_head_bwd(const float* __restrict__ Hf, const float* __restrict__ W,
                                                                const float* __restrict__ dMU, int n, float* __restrict__ dH,
-                                                               float* __restrict__ dW, float* __restrict__ db, float* __restrict__ db_prev) {
+                                                               float* __restrict__ dW, float* __restrict__ db, float* __restrict__ db_prev,
+                                                               const float* __restrict__ sg) {
+    const float gs = sg ? sg[0] : 0.0f;   // != 0: dH is written as h2 words of gs * dH (h2.cuh)
     __shared__ float4 red[HB_THREADS / 32][7][32];    // per-warp partials of 7 of the 13 outputs rows (12 dW rows + the dH column sums) at a time
     __shared__ float redb[HB_THREADS / 32][12];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -381,7 +406,13 @@ __global__ void __launch_bounds__(HB_THREADS, 2) k_actor_head_bwd(const float* _
         dh.y = g.y * ((h.y > 0.0f) ? 1.0f : (h.y + 1.0f));
         dh.z = g.z * ((h.z > 0.0f) ? 1.0f : (h.z + 1.0f));
         dh.w = g.w * ((h.w > 0.0f) ? 1.0f : (h.w + 1.0f));
-        reinterpret_cast<float4*>(dH + (size_t)r * 128)[lane] = dh;
+        if (gs != 0.0f) {
+            uint4 wd;
+            wd.x = h2::pack(dh.x * gs); wd.y = h2::pack(dh.y * gs); wd.z = h2::pack(dh.z * gs); wd.w = h2::pack(dh.w * gs);
+            reinterpret_cast<uint4*>(dH + (size_t)r * 128)[lane] = wd;
+        } else {
+            reinterpret_cast<float4*>(dH + (size_t)r * 128)[lane] = dh;
+        }
         ap.x += dh.x; ap.y += dh.y; ap.z += dh.z; ap.w += dh.w;
         float mine = 0.0f;
 #pragma unroll
@@ -1026,6 +1057,7 @@ static int g_chain_exact_actor = getenv("B200_CHAIN_DEBUG") ? atoi(getenv("B200_
 static bool g_chain_pair = getenv("B200_CHAIN_PAIR") ? atoi(getenv("B200_CHAIN_PAIR")) != 0 : false;   // chains on CTA pairs (cta_group::2)
 static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
 static bool g_h2_wgrad = getenv("B200_H2_WGRAD") ? atoi(getenv("B200_H2_WGRAD")) != 0 : false;   // weight gradients on the h2 format (h2.cuh)
+static bool g_h2_chain = getenv("B200_H2_CHAIN") ? atoi(getenv("B200_H2_CHAIN")) != 0 : false;   // forward / input-gradient chains on the h2 format (mlp_chain_h2.cuh)
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
 static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
 static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC, double bytes = 0.0) {
@@ -1197,6 +1229,7 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
                                 cab_slot[i] >= 0 ? ws + w.ZR + 64 + cab_slot[i] * 256 : nullptr};
         max_total = j.rows * j.pad > max_total ? j.rows * j.pad : max_total;
     }
+    wj.h2 = g_h2_chain ? 1 : 0;
     k_weight_prep<<<dim3((max_total + 255) / 256, 6), 256, 0, st>>>(wj);
     g_launches += 1;
     return launch_status("k_weight_prep");
@@ -1263,7 +1296,42 @@ static cudaError_t chain_launch(void (*kernel)(const Params), const Params& P, i
     return cudaLaunchKernelEx(&cfg, kernel, P);
 }
 
+// the same launch on the h2 operand format (mlp_chain_h2.cuh): Xh = input words, W*h / W*l = B' / B'' words, H1 / H2 receive words
+static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs& c1, cudaStream_t st) {
+    chain2::FwdParams P;
+    memset(&P, 0, sizeof(P));
+    const ChainNetPtrs* cs[2] = {&c0, &c1};
+    double fl = 0.0, by = 0.0;
+    for (int i = 0; i < 2; ++i) {
+        const ChainNetPtrs& c = *cs[i];
+        chain2::FwdNet& N = P.net[i];
+        N.rows = c.rows > 0 ? c.rows : 0; N.n2 = c.n2; N.single_acc = c.exact & 1; N.pad_ = 0;
+        if (c.rows <= 0) continue;
+        TC_MAP(mX, c.Xh, c.rows, 64, 64, tc::BM, true);
+        TC_MAP(mW1a, c.W1h, 256, 64, 64, 256, true);
+        TC_MAP(mW1b, c.W1l, 256, 64, 64, 256, true);
+        TC_MAP(mW2a, c.W2h, c.n2, 256, 256, c.n2, true);
+        TC_MAP(mW2b, c.W2l, c.n2, 256, 256, c.n2, true);
+        TC_MAP(mW3a, c.W3h, 128, c.n2, c.n2, 128, true);
+        TC_MAP(mW3b, c.W3l, 128, c.n2, c.n2, 128, true);
+        N.mX = *mX; N.mW1a = *mW1a; N.mW1b = *mW1b; N.mW2a = *mW2a; N.mW2b = *mW2b; N.mW3a = *mW3a; N.mW3b = *mW3b;
+        N.b1 = c.b1; N.b2 = c.b2; N.b3 = c.b3;
+        N.H1 = reinterpret_cast<uint32_t*>(c.H1); N.H2 = reinterpret_cast<uint32_t*>(c.H2); N.H3 = c.H3;
+        fl += 2.0 * c.rows * ((double)c.k_valid * 256 + 256.0 * c.n2 + (double)c.n2 * 128);
+        by += 4.0 * c.rows * (64 + 256 + c.n2 + 128);   // X words read; h1, h2 words and h3 written
+    }
+    const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
+    if (tiles <= 0) return B200_OK;
+    static unsigned long long configured = 0;
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2, chain2::F_SMEM, configured));
+    prof_begin(st, fl, PK_CHAIN_FWD, by);
+    chain2::k_mlp_fwd_h2<<<tiles < p->num_sms ? tiles : p->num_sms, chain2::F_THREADS, chain2::F_SMEM, st>>>(P);
+    prof_end(st);
+    g_launches += 1;
+    return launch_status("k_mlp_fwd_h2");
+}
 static int chain_forward(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs& c1, cudaStream_t st) {
+    if (g_h2_chain) return chain_forward_h2(p, c0, c1, st);
     chain::FwdParams P;
     memset(&P, 0, sizeof(P));
     int rc;
@@ -1292,7 +1360,44 @@ static int chain_forward(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs&
     return launch_status("k_mlp_fwd");
 }
 // both nets' hidden-layer input gradients + bias gradients: dz3 (from the head kernels) -> dz2, dz1
+static int chain_backward_h2(B200Ppo* p, int M, bool critic, bool actor, cudaStream_t st) {
+    float* ws = p->ws; const Workspace& w = p->w;
+    chain2::BwdParams P;
+    memset(&P, 0, sizeof(P));
+    double fl = 0.0, by = 0.0;
+    for (int i = 0; i < 2; ++i) {
+        chain2::BwdNet& N = P.net[i];
+        N.n2 = i == 0 ? 256 : 128;
+        N.rows = (i == 0 ? critic : actor) ? M : 0;
+        if (N.rows <= 0) continue;
+        TC_MAP(mZ3, ws + (i == 0 ? w.GC3 : w.GA3), M, 128, 128, tc::BM, true);
+        TC_MAP(mH2, ws + (i == 0 ? w.C2 : w.A2), M, N.n2, N.n2, tc::BM, true);
+        TC_MAP(mH1, ws + (i == 0 ? w.C1 : w.A1), M, 256, 256, tc::BM, true);
+        TC_MAP(mW3Ta, ws + (i == 0 ? w.Wc2Th : w.Wa2Th), N.n2, 128, 128, N.n2, true);
+        TC_MAP(mW3Tb, ws + (i == 0 ? w.Wc2Tl : w.Wa2Tl), N.n2, 128, 128, N.n2, true);
+        TC_MAP(mW2Ta, ws + (i == 0 ? w.Wc1Th : w.Wa1Th), 256, N.n2, N.n2, 256, true);
+        TC_MAP(mW2Tb, ws + (i == 0 ? w.Wc1Tl : w.Wa1Tl), 256, N.n2, N.n2, 256, true);
+        N.mZ3 = *mZ3; N.mH2 = *mH2; N.mH1 = *mH1; N.mW3Ta = *mW3Ta; N.mW3Tb = *mW3Tb; N.mW2Ta = *mW2Ta; N.mW2Tb = *mW2Tb;
+        N.DZ2 = reinterpret_cast<uint32_t*>(ws + (i == 0 ? w.GC2 : w.GA2));
+        N.DZ1 = reinterpret_cast<uint32_t*>(ws + (i == 0 ? w.GC1 : w.GA1));
+        N.db2 = p->G(i == 0 ? P_CB1 : P_AB1);
+        N.db1 = p->G(i == 0 ? P_CB0 : P_AB0);
+        N.isg = ws + w.SC + (i == 0 ? h2::SC_ISG_C : h2::SC_ISG_A);
+        fl += 2.0 * M * (128.0 * N.n2 + (double)N.n2 * 256);
+        by += 4.0 * M * (128.0 + 2.0 * N.n2 + 2.0 * 256);   // dz3, h2, h1 read; dz2, dz1 written
+    }
+    const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
+    if (tiles <= 0) return B200_OK;
+    static unsigned long long configured = 0;
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2, chain2::B_SMEM, configured));
+    prof_begin(st, fl, PK_CHAIN_BWD, by);
+    chain2::k_mlp_bwd_h2<<<tiles < p->num_sms ? tiles : p->num_sms, chain2::B_THREADS, chain2::B_SMEM, st>>>(P);
+    prof_end(st);
+    g_launches += 1;
+    return launch_status("k_mlp_bwd_h2");
+}
 static int chain_backward(B200Ppo* p, int M, bool critic, bool actor, cudaStream_t st) {
+    if (g_h2_chain) return chain_backward_h2(p, M, critic, actor, st);
     float* ws = p->ws; const Workspace& w = p->w;
     chain::BwdParams P;
     memset(&P, 0, sizeof(P));
@@ -1535,7 +1640,7 @@ int b200_critic_value(B200Ppo* p, const float* obs, const float* priv, int n, fl
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     const Workspace& w = p->w;
-    k_pack_inputs<<<(int)(((size_t)n * 64 + 255) / 256), 256, 0, st>>>(obs, priv, n, PackOut{nullptr, nullptr, nullptr, nullptr, ws + w.LXh, ws + w.LXl});
+    k_pack_inputs<<<(int)(((size_t)n * 64 + 255) / 256), 256, 0, st>>>(obs, priv, n, PackOut{nullptr, nullptr, nullptr, nullptr, ws + w.LXh, ws + w.LXl, g_h2_chain ? 1 : 0});
     g_launches += 1;
     int rc = weight_prep(p, st);   // the parameters may have changed since the last epoch
     if (rc != B200_OK) return rc;
@@ -1555,7 +1660,7 @@ int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const 
     float* ws = p->ws;
     const int M = p->cfg.horizon * p->cfg.num_envs;
     k_pack_inputs<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(
-        obses, privs, M, PackOut{ws + p->w.Xa, ws + p->w.Xah, ws + p->w.Xal, ws + p->w.Xc, ws + p->w.Xch, ws + p->w.Xcl});
+        obses, privs, M, PackOut{ws + p->w.Xa, ws + p->w.Xah, ws + p->w.Xal, ws + p->w.Xc, ws + p->w.Xch, ws + p->w.Xcl, g_h2_chain ? 1 : 0});
     int rc = weight_prep(p, st);
     if (rc != B200_OK) return rc;
     if ((rc = actor_forward_tc(p, M, st)) != B200_OK) return rc;
@@ -1590,7 +1695,7 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     {
         const size_t o = (size_t)M * 64;
         k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(
-            last_obs, last_priv, N, PackOut{nullptr, nullptr, nullptr, ws + p->w.Xc + o, ws + p->w.Xch + o, ws + p->w.Xcl + o});
+            last_obs, last_priv, N, PackOut{nullptr, nullptr, nullptr, ws + p->w.Xc + o, ws + p->w.Xch + o, ws + p->w.Xcl + o, g_h2_chain ? 1 : 0});
     }
     if (g_chain) {
         // both nets in ONE persistent launch: 800 critic + 768 actor tiles balance over the SMs better than two launches of ~5.3
@@ -1641,11 +1746,20 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
         // head backward kernels produce dz3 of both nets (+ the head's own gradients and layer 3's bias gradient), ONE fused chain
         // launch produces dz2, dz1 and the remaining bias gradients, then the six weight-gradient GEMMs
         float *GA3 = ws + w.GA3, *GA2 = ws + w.GA2, *GA1 = ws + w.GA1, *GC3 = ws + w.GC3, *GC2 = ws + w.GC2, *GC1 = ws + w.GC1;
-        k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, GA3, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2));
-        k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, GC3, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2));
+        k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, GA3, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2),
+                                                                             g_h2_chain ? ws + w.SC + h2::SC_SG_A : nullptr);
+        k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, GC3, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2),
+                                                                             g_h2_chain ? ws + w.SC + h2::SC_SG_C : nullptr);
         g_launches += 2;
         if ((rc = launch_status("k_head_bwd")) != B200_OK) return rc;
         if ((rc = chain_backward(p, M, true, true, st))) return rc;
+        if (g_h2_chain) {
+            // the chains wrote every operand as h2 words: the weight-gradient kernel takes them as they are
+            const WgH2Operand ops[6] = {{GA3, ws + w.A2, 128, 128, 128, P_AW2, true, h2::S_ACT},  {GA2, ws + w.A1, 128, 256, 256, P_AW1, true, h2::S_ACT},
+                                        {GA1, ws + w.Xah, 256, 64, 47, P_AW0, true, h2::S_X},      {GC3, ws + w.C2, 128, 256, 256, P_CW2, false, h2::S_ACT},
+                                        {GC2, ws + w.C1, 256, 256, 256, P_CW1, false, h2::S_ACT},  {GC1, ws + w.Xch, 256, 64, 61, P_CW0, false, h2::S_X}};
+            return wgrad_h2(p, ops, M, st);
+        }
         if (g_h2_wgrad) {
             // bring-up path: the TF32 chains' fp32 tensors packed into h2 words by an extra pass (the h2 chains write the words themselves)
             const float* sga = ws + w.SC + h2::SC_SG_A;
@@ -1676,7 +1790,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
         return wgrad_reduce(jobs, st);
     }
     // ---- actor backward: the 12-wide head as a fused FMA kernel, the hidden layers on tcgen05
-    k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, G1, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2));
+    k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, G1, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2), nullptr);
     g_launches += 1;
     if ((rc = launch_status("k_actor_head_bwd")) != B200_OK) return rc;
     // (each bias gradient = column sum of the layer's output gradient, accumulated by the kernel that produces it)
@@ -1686,7 +1800,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     if ((rc = tc_dgrad(p, G2, 128, ws + w.Wa1Th, ws + w.Wa1Tl, 256, ws + w.A1, G1, p->G(P_AB0), M, st))) return rc;
     if ((rc = tc_wgrad(p, jobs, 2, G1, 256, ws + w.Xa, 64, 64, 47, p->G(P_AW0), M, st))) return rc;
     // ---- critic backward
-    k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2));
+    k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, G1, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2), nullptr);
     g_launches += 1;
     if ((rc = launch_status("k_value_head_bwd")) != B200_OK) return rc;
     if ((rc = tc_wgrad(p, jobs, 3, G1, 128, ws + w.C2, 256, 256, 256, p->G(P_CW2), M, st))) return rc;
@@ -1748,11 +1862,14 @@ int b200_tc_set_pair(int enable) {
 }
 int b200_tc_set_h2(int mode) {
     g_h2_wgrad = (mode & 1) != 0;
+    g_h2_chain = (mode & 2) != 0;
+    if (g_h2_chain) g_chain = true;
     return B200_OK;
 }
 int b200_tc_set_chain(int enable) {
     g_chain = enable != 0;
     g_chain_pair = enable == 2;
+    if (enable != 1) g_h2_chain = false;   // the h2 chains exist as single-CTA fused chains only
     return B200_OK;
 }
 

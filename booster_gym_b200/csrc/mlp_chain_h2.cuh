@@ -1,0 +1,588 @@
+// mlp_chain_h2.cuh - the fused layer chains of mlp_chain.cuh on the h2 operand format (h2.cuh): tcgen05.mma kind::f16.
+//
+//   forward   X[128,64] -> h1 = ELU(X W1^T + b1) -> h2 = ELU(h1 W2^T + b2) -> h3 = ELU(h2 W3^T + b3)
+//   backward  dz3[128,128] -> dz2 = (dz3 W3) * ELU'(h2) -> dz1 = (dz2 W2) * ELU'(h1)        (+ bias gradients = column sums)
+//
+// Every operand element is ONE 32-bit word {fp16 hi, fp16 lo} (scaled by a power of two).  A row of words is a K-major fp16 row
+// whose K index alternates hi, lo, so with the weights staged twice - B' = words, B'' = words with the halves swapped -
+//        D_main  += A' B'^T   = sum_k  a_hi b_hi + a_lo b_lo
+//        D_small += A' B''^T  = sum_k  a_hi b_lo + a_lo b_hi
+// is the full fp32-class product in TWO MMAs per k-step at twice the TF32 rate (the 3xTF32 chain needed three at the TF32 rate).
+// The hand-over between layers is one tcgen05.st: the epilogue thread that owns (row, column c) of layer l's accumulator writes
+// the packed word of its activation back to column c - the TMEM cell a kind::f16 TS-form MMA reads as the K pair (2c, 2c+1) of its
+// A operand.  No lo operand, no shared-memory ring, no proxy fence: what is left of a hand-over is tcgen05.ld -> bias, ELU, pack ->
+// tcgen05.st -> tcgen05.wait::st -> mbarrier arrive.
+// TMEM maps are those of mlp_chain.cuh.  The activations go to HBM as the same words (4 B per element, what fp32 took): the
+// backward chain reads them back as such, and the weight-gradient kernel takes them as MN-major operands without any conversion.
+#pragma once
+#include "h2.cuh"
+#include "mlp_chain.cuh"
+
+namespace b200 {
+namespace chain2 {
+using namespace tc;
+using chain::TileSeq;
+using chain::tmem_ld8;
+using chain::tmem_ld8_nowait;
+using chain::tmem_st8;
+using chain::tmem_wait_ld16;
+using chain::tmem_wait_ld8;
+using chain::tmem_wait_st;
+using h2::mbar_wait_wd;
+using h2::umma_f16;
+using h2::umma_f16_ts;
+
+static constexpr int UNIT_BYTES = 32768;          // one weight-ring unit: [256 x 32] words (B' OR B'') or [128 x 32] B' + B''
+static constexpr int KB_BYTES = BM * BK * 4;      // one [128 x 32] word k-block tile
+static constexpr int HAND = 8;                    // hand-over barriers (>= k-blocks of a layer: the epilogue cannot run further ahead)
+static constexpr int EPI_W = 16;
+
+__host__ __device__ constexpr uint32_t idesc_f16_k(int n) {   // K-major operands, D = f32, A = B = f16, M = 128
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ELU in 5 straight-line instructions (see mlp_chain.cuh: absolute error <= ~3e-7)
+__device__ __forceinline__ float elu_fast5(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return (x > 0.0f) ? x : (e - 1.0f);
+}
+
+// the hand-over: this warp's 32 rows x 8 columns of the next layer's A operand are in TMEM
+__device__ __forceinline__ void handover(uint64_t* bar, int lane) {
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+struct alignas(64) FwdNet {
+    CUtensorMap mX;                       // input words [rows, 64], box 32 x 128
+    CUtensorMap mW1a, mW1b;               // [256, 64]   box 32 x 256     (a = B', b = B'': halves swapped)
+    CUtensorMap mW2a, mW2b;               // [n2, 256]   box 32 x n2
+    CUtensorMap mW3a, mW3b;               // [128, n2]   box 32 x 128
+    const float *b1, *b2, *b3;
+    uint32_t *H1, *H2;                    // post-ELU activations as h2 words [rows, 256], [rows, n2]
+    float* H3;                            // [rows, 128] fp32 (the head kernels' operand)
+    int rows, n2, single_acc, pad_;       // single_acc: debug - one accumulator for the 128-wide layers
+};
+struct alignas(64) FwdParams { FwdNet net[2]; };
+
+static constexpr int F_UNITS = 6;
+static constexpr int F_EPI0 = 2;                           // first epilogue warp
+static constexpr int F_THREADS = 32 * (F_EPI0 + EPI_W);    // TMA, MMA, 16 epilogue warps
+static constexpr int F_X = 0, F_B = 2 * KB_BYTES, F_BAR = F_B + F_UNITS * UNIT_BYTES, F_SMEM = F_BAR + 256 + 1024;
+static_assert(F_SMEM <= 232448, "shared memory budget");
+
+__global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* x_full = (uint64_t*)(smem + F_BAR);
+    uint64_t* x_empty = x_full + 1;
+    uint64_t* b_full = x_empty + 1;          // [F_UNITS]
+    uint64_t* b_empty = b_full + F_UNITS;    // [F_UNITS]
+    uint64_t* a_full = b_empty + F_UNITS;    // [HAND] a k-block of the next layer's A operand is in TMEM
+    uint64_t* accf = a_full + HAND;          // [3] layer l's accumulator complete
+    uint32_t* tmem_slot = (uint32_t*)(accf + 3);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(x_full, 1); mbar_init(x_empty, 1);
+        for (int s = 0; s < F_UNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < HAND; ++s) mbar_init(&a_full[s], EPI_W);
+        for (int s = 0; s < 3; ++s) mbar_init(&accf[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: the tile's input words, then the weight k-blocks of the three layers in consumption order =====
+        if (lane == 0) {
+            uint32_t u = 0, t = 0;
+            auto wide = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kb) {   // [256 x 32] B' and B'': one unit each
+                for (int half = 0; half < 2; ++half, ++u) {
+                    const uint32_t s = u % F_UNITS, ph = (u / F_UNITS) & 1;
+                    mbar_wait_wd(&b_empty[s], ph ^ 1, 100 + (int)s);
+                    mbar_expect_tx(&b_full[s], UNIT_BYTES);
+                    tma_load_2d(half ? mb : ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb * BK, 0);
+                }
+            };
+            auto narrow = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kb) {   // B' + B'' of [128 x 32] in one unit
+                const uint32_t s = u % F_UNITS, ph = (u / F_UNITS) & 1;
+                mbar_wait_wd(&b_empty[s], ph ^ 1, 110 + (int)s);
+                mbar_expect_tx(&b_full[s], UNIT_BYTES);
+                tma_load_2d(ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb * BK, 0);
+                tma_load_2d(mb, &b_full[s], sbase + F_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, 0);
+                ++u;
+            };
+            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            int ni, tile;
+            while (seq.next(ni, tile)) {
+                const FwdNet& N = P.net[ni];
+                const int m0 = tile * BM;
+                mbar_wait_wd(x_empty, (t & 1) ^ 1, 120);
+                mbar_expect_tx(x_full, 2 * KB_BYTES);
+                tma_load_2d(&N.mX, x_full, sbase + F_X, 0, m0);
+                tma_load_2d(&N.mX, x_full, sbase + F_X + KB_BYTES, BK, m0);
+                for (int kb = 0; kb < 2; ++kb) wide(&N.mW1a, &N.mW1b, kb);
+                for (int kb = 0; kb < 8; ++kb) { if (N.n2 == 256) wide(&N.mW2a, &N.mW2b, kb); else narrow(&N.mW2a, &N.mW2b, kb); }
+                for (int kb = 0; kb < N.n2 / BK; ++kb) narrow(&N.mW3a, &N.mW3b, kb);
+                ++t;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t u = 0, t = 0, li = 0;
+            // weight k-block of an N-row layer: waits for its unit(s), returns the operand addresses and the barriers to release
+            auto weights = [&](int nn, uint32_t& b_a, uint32_t& b_b, uint64_t*& e0, uint64_t*& e1, int code) {
+                e1 = nullptr;
+                if (nn == 256) {
+                    const uint32_t sa = u % F_UNITS, pa = (u / F_UNITS) & 1, sb = (u + 1) % F_UNITS, pb = ((u + 1) / F_UNITS) & 1;
+                    u += 2;
+                    mbar_wait_wd(&b_full[sa], pa, code);
+                    mbar_wait_wd(&b_full[sb], pb, code + 1);
+                    b_a = sbase + F_B + sa * UNIT_BYTES; b_b = sbase + F_B + sb * UNIT_BYTES;
+                    e0 = &b_empty[sa]; e1 = &b_empty[sb];
+                } else {
+                    const uint32_t sa = u % F_UNITS, pa = (u / F_UNITS) & 1;
+                    u += 1;
+                    mbar_wait_wd(&b_full[sa], pa, code + 2);
+                    b_a = sbase + F_B + sa * UNIT_BYTES; b_b = b_a + UNIT_BYTES / 2;
+                    e0 = &b_empty[sa];
+                }
+            };
+            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            int ni, tile;
+            while (seq.next(ni, tile)) {
+                const int n2 = P.net[ni].n2;
+                const uint32_t par = t & 1;
+                const uint32_t c1 = tmem_base + par * 256, c2 = tmem_base + (1 - par) * 256, c3 = c1;
+                // ---- layer 1 (A = X words from shared memory)
+                mbar_wait_wd(x_full, par, 200);
+                if (t > 0) mbar_wait_wd(&accf[2], (t - 1) & 1, 201);   // layer 3 of the previous tile has finished READING h2 from c1's half
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                {
+                    // K = 64 is two k-blocks, both resident: the 8 small cross-term MMAs of BOTH k-blocks first and the 8 dominant ones last
+                    // (TMEM accumulation truncates by up to an ulp of the accumulator on every add: the small terms land while it is small)
+                    uint32_t b_a[2], b_b[2];
+                    uint64_t *e0[2], *e1[2];
+                    for (int kb = 0; kb < 2; ++kb) weights(256, b_a[kb], b_b[kb], e0[kb], e1[kb], 210);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    constexpr uint32_t id = idesc_f16_k(256);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint32_t a = sbase + F_X + kb * KB_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(c1, desc_kmajor(a + k * 32), desc_kmajor(b_b[kb] + k * 32), id, (kb | k) ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint32_t a = sbase + F_X + kb * KB_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(c1, desc_kmajor(a + k * 32), desc_kmajor(b_a[kb] + k * 32), id, 1u);
+                    }
+                    for (int kb = 0; kb < 2; ++kb) {
+                        umma_commit(e0[kb]);
+                        if (e1[kb]) umma_commit(e1[kb]);
+                    }
+                }
+                umma_commit(x_empty);
+                umma_commit(&accf[0]);
+                // ---- layers 2 and 3 (A words from TMEM in place)
+                for (int layer = 0; layer < 2; ++layer) {
+                    const int nk = layer == 0 ? 8 : n2 / BK, nn = layer == 0 ? n2 : 128;
+                    const uint32_t ca = layer == 0 ? c1 : c2, cd = layer == 0 ? c2 : c3;
+                    const uint32_t id = idesc_f16_k(nn);
+                    // 128-wide outputs leave 128 free columns next to the accumulator: the cross terms get their own accumulator there
+                    // and the epilogue adds the two with a round-to-nearest FADD
+                    const uint32_t cs = (nn == 128 && !P.net[ni].single_acc) ? cd + 128 : cd;
+                    for (int kb = 0; kb < nk; ++kb, ++li) {
+                        uint32_t b_a, b_b;
+                        uint64_t *e0, *e1;
+                        weights(nn, b_a, b_b, e0, e1, 220);
+                        mbar_wait_wd(&a_full[li % HAND], (li / HAND) & 1, 230 + layer);   // the epilogue has written this k-block's words to TMEM
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t off = k * 32, a_t = ca + kb * BK + k * 8;
+                            umma_f16_ts(cs, a_t, desc_kmajor(b_b + off), id, (kb | k) ? 1u : 0u);
+                            umma_f16_ts(cd, a_t, desc_kmajor(b_a + off), id, (cs != cd && (kb | k) == 0) ? 0u : 1u);
+                        }
+                        umma_commit(e0);
+                        if (e1) umma_commit(e1);
+                    }
+                    umma_commit(&accf[1 + layer]);
+                }
+                ++t;
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter q (rows), 8-column slice g of every 32-column k-block =====
+        const int q = warp & 3, g = (warp - F_EPI0) >> 2;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int rit = q * 32 + lane;                 // row in this CTA's 128-row tile
+        uint32_t t = 0, li = 0;
+        TileSeq seq(P.net[0].rows, P.net[1].rows);
+        int ni, tile;
+        while (seq.next(ni, tile)) {
+            const FwdNet& N = P.net[ni];
+            const int n2 = N.n2;
+            const uint32_t par = t & 1;
+            const uint32_t c1 = tmem_base + par * 256 + lane_off, c2 = tmem_base + (1 - par) * 256 + lane_off, c3 = c1;
+            const int row = tile * BM + rit;
+            const bool row_ok = row < N.rows;
+            const size_t rsafe = (size_t)(row_ok ? row : 0);
+#pragma unroll 1
+            for (int layer = 0; layer < 3; ++layer) {
+                const int width = layer == 0 ? 256 : (layer == 1 ? n2 : 128);
+                const uint32_t cacc = layer == 0 ? c1 : (layer == 1 ? c2 : c3);
+                const float* bias = layer == 0 ? N.b1 : (layer == 1 ? N.b2 : N.b3);
+                const float inv = layer == 0 ? 1.0f / (h2::S_X * h2::S_W) : 1.0f / (h2::S_ACT * h2::S_W);
+                mbar_wait_wd(&accf[layer], par, 300 + layer);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                // software pipeline over the k-blocks: the accumulator slice and the bias of k-block kb + 1 are requested before kb is processed
+                const bool two_acc = layer > 0 && width == 128 && !N.single_acc;
+                const int nkb = width / BK;
+                uint32_t rn[8], rn2[8];
+                float4 bn0, bn1;
+                tmem_ld8_nowait(cacc + g * 8, rn);
+                if (two_acc) tmem_ld8_nowait(cacc + 128 + g * 8, rn2);
+                bn0 = __ldg(reinterpret_cast<const float4*>(bias + g * 8)); bn1 = __ldg(reinterpret_cast<const float4*>(bias + g * 8 + 4));
+#pragma unroll 1
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int col = kb * BK + g * 8;
+                    float a[8];
+                    if (two_acc) tmem_wait_ld16(rn, rn2); else tmem_wait_ld8(rn);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = two_acc ? __uint_as_float(rn[j]) + __uint_as_float(rn2[j]) : __uint_as_float(rn[j]);
+                    const float bb[8] = {bn0.x, bn0.y, bn0.z, bn0.w, bn1.x, bn1.y, bn1.z, bn1.w};
+                    if (kb + 1 < nkb) {
+                        tmem_ld8_nowait(cacc + col + BK, rn);
+                        if (two_acc) tmem_ld8_nowait(cacc + 128 + col + BK, rn2);
+                        bn0 = __ldg(reinterpret_cast<const float4*>(bias + col + BK)); bn1 = __ldg(reinterpret_cast<const float4*>(bias + col + BK + 4));
+                    }
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = elu_fast5(fmaf(a[j], inv, bb[j]));
+                    if (layer < 2) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[j] = h2::pack(fminf(v[j] * h2::S_ACT, h2::H2_MAX));
+                        tmem_st8(cacc + col, w);
+                        handover(&a_full[li % HAND], lane);
+                        ++li;
+                        // the HBM copy goes out AFTER the hand-over
+                        if (row_ok) stg_v8(reinterpret_cast<float*>((layer == 0 ? N.H1 : N.H2) + rsafe * width + col), reinterpret_cast<const float*>(w));
+                    } else {
+                        if (row_ok) stg_v8(N.H3 + rsafe * 128 + col, v);
+                    }
+                }
+            }
+            ++t;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// =====================================================================================================================
+// backward (input gradients of the hidden layers + bias gradients)
+// =====================================================================================================================
+struct alignas(64) BwdNet {
+    CUtensorMap mZ3, mH2, mH1;            // words: dz3 [rows,128], h2 [rows,n2], h1 [rows,256]; box 32 x 128 (the epilogue's "aux" tiles)
+    CUtensorMap mW3Ta, mW3Tb;             // W3^T [n2, 128]   box 32 x n2
+    CUtensorMap mW2Ta, mW2Tb;             // W2^T [256, n2]   box 32 x 256
+    uint32_t *DZ2, *DZ1;                  // words [rows, n2], [rows, 256] (scaled by the net's gradient scale)
+    float *db2, *db1;                     // bias gradients of layers 2 and 1 (+= column sums of dz2 / dz1)
+    const float* isg;                     // device: 1 / gradient scale of this net
+    int rows, n2;
+};
+struct alignas(64) BwdParams { BwdNet net[2]; };
+
+static constexpr int B_UNITS = 5, B_AUX_STAGES = 4;
+static constexpr int B_EPI0 = 3;                           // warp 0 weight TMA, 1 MMA, 2 aux TMA
+static constexpr int B_THREADS = 32 * (B_EPI0 + EPI_W);
+static constexpr int B_B = 0, B_AUX = B_UNITS * UNIT_BYTES, B_BAR = B_AUX + B_AUX_STAGES * KB_BYTES, B_SMEM = B_BAR + 256 + 1024;
+static_assert(B_SMEM <= 232448, "shared memory budget");
+
+// column sums of this warp's 32 rows x 8 columns -> atomics on dst[0..7], scaled
+__device__ __forceinline__ void colsum8s(float* v, int lane, float* dst, float scale) {
+#pragma unroll
+    for (int half = 4; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = upper ? v[j] : v[j + half];
+            const float keep = upper ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 8);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+    if (lane < 8) atomicAdd(dst + lane, tot * scale);   // lane l holds column l (bit i of l picked the upper half at step 2^i)
+}
+
+__global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_constant__ BwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* b_full = (uint64_t*)(smem + B_BAR);
+    uint64_t* b_empty = b_full + B_UNITS;
+    uint64_t* a_full = b_empty + B_UNITS;           // [HAND]
+    uint64_t* aux_full = a_full + HAND;
+    uint64_t* aux_empty = aux_full + B_AUX_STAGES;
+    uint64_t* accf = aux_empty + B_AUX_STAGES;   // [2]: dh2 complete, dh1 complete
+    uint32_t* tmem_slot = (uint32_t*)(accf + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < B_UNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < HAND; ++s) mbar_init(&a_full[s], EPI_W);
+        for (int s = 0; s < B_AUX_STAGES; ++s) { mbar_init(&aux_full[s], 1); mbar_init(&aux_empty[s], EPI_W); }
+        mbar_init(&accf[0], 1); mbar_init(&accf[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t CZ = 0, CA = 128, CD_LO = 384, CD_HI = 0;   // TMEM columns: dz3, dh2/dz2, dh1 columns [0,128) / [128,256)
+
+    if (warp == 0) {
+        // ===== TMA producer: weight k-blocks (W3^T then W2^T per tile) =====
+        if (lane == 0) {
+            uint32_t u = 0;
+            auto wide = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kb) {
+                for (int half = 0; half < 2; ++half, ++u) {
+                    const uint32_t s = u % B_UNITS, ph = (u / B_UNITS) & 1;
+                    mbar_wait_wd(&b_empty[s], ph ^ 1, 500 + (int)s);
+                    mbar_expect_tx(&b_full[s], UNIT_BYTES);
+                    tma_load_2d(half ? mb : ma, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb * BK, 0);
+                }
+            };
+            auto narrow = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kb) {
+                const uint32_t s = u % B_UNITS, ph = (u / B_UNITS) & 1;
+                mbar_wait_wd(&b_empty[s], ph ^ 1, 510 + (int)s);
+                mbar_expect_tx(&b_full[s], UNIT_BYTES);
+                tma_load_2d(ma, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb * BK, 0);
+                tma_load_2d(mb, &b_full[s], sbase + B_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, 0);
+                ++u;
+            };
+            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            int ni, tile;
+            while (seq.next(ni, tile)) {
+                const BwdNet& N = P.net[ni];
+                for (int kb = 0; kb < 4; ++kb) { if (N.n2 == 256) wide(&N.mW3Ta, &N.mW3Tb, kb); else narrow(&N.mW3Ta, &N.mW3Tb, kb); }
+                for (int kb = 0; kb < N.n2 / BK; ++kb) wide(&N.mW2Ta, &N.mW2Tb, kb);
+            }
+        }
+    } else if (warp == 2) {
+        // ===== TMA producer: aux tiles (this CTA's 128 rows) in the epilogue's consumption order =====
+        if (lane == 0) {
+            uint32_t ai = 0;
+            auto aux = [&](const CUtensorMap* m, int kb, int m0) {
+                const uint32_t s = ai % B_AUX_STAGES, ph = (ai / B_AUX_STAGES) & 1;
+                mbar_wait_wd(&aux_empty[s], ph ^ 1, 520 + (int)s);
+                mbar_expect_tx(&aux_full[s], KB_BYTES);
+                tma_load_2d(m, &aux_full[s], sbase + B_AUX + s * KB_BYTES, kb * BK, m0);
+                ++ai;
+            };
+            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            int cn, ct, nn = 0, nt = 0;
+            bool have = seq.next(cn, ct);
+            if (have) for (int kb = 0; kb < 4; ++kb) aux(&P.net[cn].mZ3, kb, ct * BM);
+            while (have) {
+                const bool hn = seq.next(nn, nt);
+                const BwdNet& N = P.net[cn];
+                const int m0 = ct * BM;
+                for (int kb = 0; kb < N.n2 / BK; ++kb) aux(&N.mH2, kb, m0);
+                for (int kb = 4; kb < 8; ++kb) aux(&N.mH1, kb, m0);
+                if (hn) for (int kb = 0; kb < 4; ++kb) aux(&P.net[nn].mZ3, kb, nt * BM);
+                for (int kb = 0; kb < 4; ++kb) aux(&N.mH1, kb, m0);
+                have = hn; cn = nn; ct = nt;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t u = 0, li = 0;
+            auto weights = [&](bool two_units, uint32_t& b_a, uint32_t& b_b, uint64_t*& e0, uint64_t*& e1, int code) {
+                e1 = nullptr;
+                if (two_units) {
+                    const uint32_t sa = u % B_UNITS, pa = (u / B_UNITS) & 1, sb = (u + 1) % B_UNITS, pb = ((u + 1) / B_UNITS) & 1;
+                    u += 2;
+                    mbar_wait_wd(&b_full[sa], pa, code);
+                    mbar_wait_wd(&b_full[sb], pb, code + 1);
+                    b_a = sbase + B_B + sa * UNIT_BYTES; b_b = sbase + B_B + sb * UNIT_BYTES;
+                    e0 = &b_empty[sa]; e1 = &b_empty[sb];
+                } else {
+                    const uint32_t sa = u % B_UNITS, pa = (u / B_UNITS) & 1;
+                    u += 1;
+                    mbar_wait_wd(&b_full[sa], pa, code + 2);
+                    b_a = sbase + B_B + sa * UNIT_BYTES; b_b = b_a + UNIT_BYTES / 2;
+                    e0 = &b_empty[sa];
+                }
+            };
+            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            int ni, tile;
+            while (seq.next(ni, tile)) {
+                const int n2 = P.net[ni].n2;
+                // ---- dh2 [128, n2] = dz3 [128,128] W3: 4 k-blocks
+                for (int kb = 0; kb < 4; ++kb, ++li) {
+                    uint32_t b_a, b_b;
+                    uint64_t *e0, *e1;
+                    weights(n2 == 256, b_a, b_b, e0, e1, 600);
+                    mbar_wait_wd(&a_full[li % HAND], (li / HAND) & 1, 610);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t id = idesc_f16_k(n2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t off = k * 32, a_t = tmem_base + CZ + kb * BK + k * 8;
+                        umma_f16_ts(tmem_base + CA, a_t, desc_kmajor(b_b + off), id, (kb | k) ? 1u : 0u);
+                        umma_f16_ts(tmem_base + CA, a_t, desc_kmajor(b_a + off), id, 1u);
+                    }
+                    umma_commit(e0);
+                    if (e1) umma_commit(e1);
+                }
+                umma_commit(&accf[0]);
+                // ---- dh1 [128, 256] = dz2 [128, n2] W2: n2 / 32 k-blocks, the output as two 128-column halves
+                for (int kb = 0; kb < n2 / BK; ++kb, ++li) {
+                    uint32_t b_a, b_b;
+                    uint64_t *e0, *e1;
+                    weights(true, b_a, b_b, e0, e1, 620);
+                    mbar_wait_wd(&a_full[li % HAND], (li / HAND) & 1, 630);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    constexpr uint32_t id = idesc_f16_k(128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t off = k * 32, a_t = tmem_base + CA + kb * BK + k * 8;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t cd = tmem_base + (h ? CD_HI : CD_LO), boff = off + h * (UNIT_BYTES / 2);   // rows 128..255 of the tile
+                            umma_f16_ts(cd, a_t, desc_kmajor(b_b + boff), id, (kb | k) ? 1u : 0u);
+                            umma_f16_ts(cd, a_t, desc_kmajor(b_a + boff), id, 1u);
+                        }
+                    }
+                    umma_commit(e0);
+                    if (e1) umma_commit(e1);
+                }
+                umma_commit(&accf[1]);
+            }
+        }
+    } else if (warp >= B_EPI0) {
+        // ===== epilogue warps =====
+        const int q = warp & 3, g = (warp - B_EPI0) >> 2;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int rit = q * 32 + lane;
+        const uint32_t sw = (uint32_t)(rit & 7);
+        uint32_t t = 0, li = 0, ai = 0;
+        // this thread's 8 words of the aux k-block in ring stage s (128-byte swizzled rows).  The stage is handed back to the TMA
+        // producer by aux_release() only AFTER instructions that consume the loaded registers have issued (see mlp_chain.cuh).
+        auto aux_read = [&](uint32_t* h) -> uint32_t {
+            const uint32_t s = ai % B_AUX_STAGES, ph = (ai / B_AUX_STAGES) & 1;
+            mbar_wait_wd(&aux_full[s], ph, 700);
+            const uint32_t rbase = sbase + B_AUX + s * KB_BYTES + (uint32_t)rit * 128u;
+            const float4 x0 = lds_v4(rbase + ((((uint32_t)(2 * g)) ^ sw) << 4)), x1 = lds_v4(rbase + ((((uint32_t)(2 * g + 1)) ^ sw) << 4));
+            h[0] = __float_as_uint(x0.x); h[1] = __float_as_uint(x0.y); h[2] = __float_as_uint(x0.z); h[3] = __float_as_uint(x0.w);
+            h[4] = __float_as_uint(x1.x); h[5] = __float_as_uint(x1.y); h[6] = __float_as_uint(x1.z); h[7] = __float_as_uint(x1.w);
+            ++ai;
+            return s;
+        };
+        auto aux_release = [&](uint32_t s) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aux_empty[s]);
+        };
+        auto stage_dz3 = [&]() {   // dz3 of a tile: aux tiles -> A operand, the words as they are
+#pragma unroll 1
+            for (int kb = 0; kb < 4; ++kb) {
+                uint32_t w[8];
+                const uint32_t as = aux_read(w);
+                tmem_st8(tmem_base + lane_off + CZ + kb * BK + g * 8, w);
+                handover(&a_full[li % HAND], lane);
+                ++li;
+                aux_release(as);
+            }
+        };
+        // one k-block of an ELU'-masked gradient: v = acc * ELU'(h); store; column sums; optionally hand over to the next GEMM
+        auto grad_block = [&](uint32_t tcol, uint32_t* out_row, int col, float* db, float isg, bool row_ok, bool handoff) {
+            uint32_t hw[8];
+            const uint32_t as = aux_read(hw);
+            uint32_t r[8];
+            tmem_ld8(tmem_base + lane_off + tcol, r);
+            float v[8];
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float h = h2::unpack(hw[j]);   // = S_ACT * activation
+                v[j] = __uint_as_float(r[j]) * (1.0f / h2::S_W) * ((h > 0.0f) ? 1.0f : fmaf(h, 1.0f / h2::S_ACT, 1.0f));
+                w[j] = h2::pack(v[j]);
+            }
+            if (handoff) {
+                tmem_st8(tmem_base + lane_off + tcol, w);
+                handover(&a_full[li % HAND], lane);
+                ++li;
+            }
+            if (row_ok) stg_v8(reinterpret_cast<float*>(out_row + col), reinterpret_cast<const float*>(w));
+            if (!row_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+            }
+            colsum8s(v, lane, db + col, isg);
+            aux_release(as);
+        };
+        TileSeq seq(P.net[0].rows, P.net[1].rows);
+        int cn, ct, nn = 0, nt = 0;
+        bool have = seq.next(cn, ct);
+        if (have) stage_dz3();
+        while (have) {
+            const bool hn = seq.next(nn, nt);
+            const BwdNet& N = P.net[cn];
+            const int n2 = N.n2;
+            const int row = ct * BM + rit;
+            const bool row_ok = row < N.rows;
+            const size_t rsafe = (size_t)(row_ok ? row : 0);
+            const uint32_t par = t & 1;
+            const float isg = __ldg(N.isg);
+            // dz2
+            mbar_wait_wd(&accf[0], par, 720);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll 1
+            for (int kb = 0; kb < n2 / BK; ++kb) grad_block(CA + kb * BK + g * 8, N.DZ2 + rsafe * n2, kb * BK + g * 8, N.db2, isg, row_ok, true);
+            // dz1: high half of the columns first (it shares TMEM columns with the next tile's dz3)
+            mbar_wait_wd(&accf[1], par, 721);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll 1
+            for (int kb = 4; kb < 8; ++kb) grad_block(CD_HI + (kb - 4) * BK + g * 8, N.DZ1 + rsafe * 256, kb * BK + g * 8, N.db1, isg, row_ok, false);
+            if (hn) stage_dz3();
+#pragma unroll 1
+            for (int kb = 0; kb < 4; ++kb) grad_block(CD_LO + kb * BK + g * 8, N.DZ1 + rsafe * 256, kb * BK + g * 8, N.db1, isg, row_ok, false);
+            have = hn; cn = nn; ct = nt;
+            ++t;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+}  // namespace chain2
+}  // namespace b200
