@@ -90,18 +90,6 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* b, uint32_t parity, int c
     } while (!done);
 }
 
-// ---- fp32 -> h2 words (inputs once per iteration; also the bring-up path of every other operand) ---------------------------------
-__global__ void __launch_bounds__(256) k_h2_pack(const float* __restrict__ src, uint32_t* __restrict__ dst, size_t n4, float scale,
-                                                 const float* __restrict__ scale_ptr) {
-    const float s = scale_ptr ? scale * scale_ptr[0] : scale;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(src)[i];
-        uint4 o;
-        o.x = pack_clamped(v.x * s); o.y = pack_clamped(v.y * s); o.z = pack_clamped(v.z * s); o.w = pack_clamped(v.w * s);
-        reinterpret_cast<uint4*>(dst)[i] = o;
-    }
-}
-
 // =====================================================================================================================
 // weight gradients: D[n, k] = sum over rows m of dY[m, n] X[m, k]   for ALL SIX hidden-layer matrices of an epoch in ONE launch
 // =====================================================================================================================

@@ -66,9 +66,8 @@ struct Workspace {
     // ---- h2 operand format (h2.cuh): two fp16 halves per 32-bit word, power-of-two scales
     size_t SC;                                          // h2::SC_COUNT floats: gradient scales of this epoch (k_finalize_loss)
     size_t ZR;                                          // zeroed by weight_prep: uint32 amax[64] (|dV|, |dmu| of k_loss), float colabs[4][256]
-    size_t PXa, PXc, PA1, PA2, PC1, PC2;                // h2 words of the inputs / activations (operands of the weight-gradient kernel)
-    size_t PGA3, PGA2, PGA1, PGC3, PGC2, PGC1;          // h2 words of dL/dz
     size_t WP2;                                         // partial tiles of k_wgrad_h2 [CTA][128][128]
+    size_t BS;                                          // S_ACT * bias of the layers whose output is handed on as h2 words: critic 1, 2, actor 1, 2 (4 x 256)
     size_t total;
 };
 static Workspace make_workspace(int T, int N) {
@@ -94,9 +93,8 @@ static Workspace make_workspace(int T, int N) {
     w.LXc = take(n * 64); w.LXh = take(n * 64); w.LXl = take(n * 64); w.L1 = take(n * 256); w.L2 = take(n * 256); w.L3 = take(n * 128);
     w.LV = take(n);
     w.SC = take(h2::SC_COUNT); w.ZR = take(64 + 4 * 256);
-    w.PXa = take(M * 64); w.PXc = take(M * 64); w.PA1 = take(M * 256); w.PA2 = take(M * 128); w.PC1 = take(M * 256); w.PC2 = take(M * 256);
-    w.PGA3 = take(M * 128); w.PGA2 = take(M * 128); w.PGA1 = take(M * 256); w.PGC3 = take(M * 128); w.PGC2 = take(M * 256); w.PGC1 = take(M * 256);
     w.WP2 = take((size_t)WP_MAX_CTAS * 128 * 128);
+    w.BS = take(4 * 256);
     w.total = o;
     return w;
 }
@@ -187,9 +185,17 @@ struct WeightPrepJob {
 };
 struct WeightPrepJobs {
     WeightPrepJob j[6];
+    const float* bias[4];   // h2: blockIdx.y == 6 writes bias_scaled[i][c] = S_ACT * bias[i][c]
+    float* bias_scaled;     // [4][256]
+    int bias_n[4];
     int h2;   // 1: Wh / WTh receive the h2 words of S_W * w (B'), Wl / WTl the same words with their halves swapped (B'')
 };
 __global__ void k_weight_prep(const WeightPrepJobs jobs) {
+    if (blockIdx.y == 6) {
+        const int idx = blockIdx.x * blockDim.x + threadIdx.x, i = idx >> 8, c = idx & 255;
+        if (i < 4 && c < jobs.bias_n[i]) jobs.bias_scaled[i * 256 + c] = h2::S_ACT * jobs.bias[i][c];
+        return;
+    }
     const WeightPrepJob& q = jobs.j[blockIdx.y];
     const float* __restrict__ W = q.W;
     float* __restrict__ Wh = q.Wh;
@@ -1056,8 +1062,10 @@ static bool g_tc_pair = getenv("B200_TC_PAIR") ? atoi(getenv("B200_TC_PAIR")) !=
 static int g_chain_exact_actor = getenv("B200_CHAIN_DEBUG") ? atoi(getenv("B200_CHAIN_DEBUG")) : 0;   // debug: 1 = single accumulator for the 128-wide layers
 static bool g_chain_pair = getenv("B200_CHAIN_PAIR") ? atoi(getenv("B200_CHAIN_PAIR")) != 0 : false;   // chains on CTA pairs (cta_group::2)
 static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
-static bool g_h2_wgrad = getenv("B200_H2_WGRAD") ? atoi(getenv("B200_H2_WGRAD")) != 0 : false;   // weight gradients on the h2 format (h2.cuh)
-static bool g_h2_chain = getenv("B200_H2_CHAIN") ? atoi(getenv("B200_H2_CHAIN")) != 0 : false;   // forward / input-gradient chains on the h2 format (mlp_chain_h2.cuh)
+static bool g_h2_chain = getenv("B200_H2") ? atoi(getenv("B200_H2")) != 0 : true;   // hidden-layer GEMMs on the h2 operand format (h2.cuh, mlp_chain_h2.cuh); 0 = 3xTF32 kernels
+// epilogue warp groups of the h2 chains (1 or 2; measured best: forward 2, backward 1)
+static int g_h2_groups_fwd = getenv("B200_H2_GROUPS_FWD") ? atoi(getenv("B200_H2_GROUPS_FWD")) : 2;
+static int g_h2_groups_bwd = getenv("B200_H2_GROUPS_BWD") ? atoi(getenv("B200_H2_GROUPS_BWD")) : 1;
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
 static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
 static void prof_begin(cudaStream_t st, double flops, int kind = PK_MMA_SYNC, double bytes = 0.0) {
@@ -1230,7 +1238,10 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
         max_total = j.rows * j.pad > max_total ? j.rows * j.pad : max_total;
     }
     wj.h2 = g_h2_chain ? 1 : 0;
-    k_weight_prep<<<dim3((max_total + 255) / 256, 6), 256, 0, st>>>(wj);
+    wj.bias[0] = p->P(P_CB0); wj.bias[1] = p->P(P_CB1); wj.bias[2] = p->P(P_AB0); wj.bias[3] = p->P(P_AB1);
+    wj.bias_n[0] = 256; wj.bias_n[1] = 256; wj.bias_n[2] = 256; wj.bias_n[3] = 128;
+    wj.bias_scaled = ws + w.BS;
+    k_weight_prep<<<dim3((max_total + 255) / 256, g_h2_chain ? 7 : 6), 256, 0, st>>>(wj);
     g_launches += 1;
     return launch_status("k_weight_prep");
 }
@@ -1305,7 +1316,7 @@ static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPt
     for (int i = 0; i < 2; ++i) {
         const ChainNetPtrs& c = *cs[i];
         chain2::FwdNet& N = P.net[i];
-        N.rows = c.rows > 0 ? c.rows : 0; N.n2 = c.n2; N.single_acc = c.exact & 1; N.pad_ = 0;
+        N.rows = c.rows > 0 ? c.rows : 0; N.n2 = c.n2; N.pad0_ = 0; N.pad_ = 0;
         if (c.rows <= 0) continue;
         TC_MAP(mX, c.Xh, c.rows, 64, 64, tc::BM, true);
         TC_MAP(mW1a, c.W1h, 256, 64, 64, 256, true);
@@ -1314,18 +1325,24 @@ static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPt
         TC_MAP(mW2b, c.W2l, c.n2, 256, 256, c.n2, true);
         TC_MAP(mW3a, c.W3h, 128, c.n2, c.n2, 128, true);
         TC_MAP(mW3b, c.W3l, 128, c.n2, c.n2, 128, true);
+        TC_MAP(mH1, c.H1, c.rows, 256, 256, tc::BM, true);
+        TC_MAP(mH2, c.H2, c.rows, c.n2, c.n2, tc::BM, true);
+        TC_MAP(mH3, c.H3, c.rows, 128, 128, tc::BM, true);
         N.mX = *mX; N.mW1a = *mW1a; N.mW1b = *mW1b; N.mW2a = *mW2a; N.mW2b = *mW2b; N.mW3a = *mW3a; N.mW3b = *mW3b;
-        N.b1 = c.b1; N.b2 = c.b2; N.b3 = c.b3;
-        N.H1 = reinterpret_cast<uint32_t*>(c.H1); N.H2 = reinterpret_cast<uint32_t*>(c.H2); N.H3 = c.H3;
+        N.mH1 = *mH1; N.mH2 = *mH2; N.mH3 = *mH3;
+        N.b1s = p->ws + p->w.BS + (i == 0 ? 0 : 512); N.b2s = N.b1s + 256; N.b3 = c.b3;   // (net 0 = critic, net 1 = actor)
         fl += 2.0 * c.rows * ((double)c.k_valid * 256 + 256.0 * c.n2 + (double)c.n2 * 128);
         by += 4.0 * c.rows * (64 + 256 + c.n2 + 128);   // X words read; h1, h2 words and h3 written
     }
     const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
     if (tiles <= 0) return B200_OK;
-    static unsigned long long configured = 0;
-    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2, chain2::F_SMEM, configured));
+    static unsigned long long configured[2] = {0, 0};
+    const int grid = tiles < p->num_sms ? tiles : p->num_sms;
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<1>, chain2::F_SMEM, configured[0]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<2>, chain2::F_SMEM, configured[1]));
     prof_begin(st, fl, PK_CHAIN_FWD, by);
-    chain2::k_mlp_fwd_h2<<<tiles < p->num_sms ? tiles : p->num_sms, chain2::F_THREADS, chain2::F_SMEM, st>>>(P);
+    if (g_h2_groups_fwd == 1) chain2::k_mlp_fwd_h2<1><<<grid, chain2::F_THREADS, chain2::F_SMEM, st>>>(P);
+    else chain2::k_mlp_fwd_h2<2><<<grid, chain2::F_THREADS, chain2::F_SMEM, st>>>(P);
     prof_end(st);
     g_launches += 1;
     return launch_status("k_mlp_fwd_h2");
@@ -1377,9 +1394,10 @@ static int chain_backward_h2(B200Ppo* p, int M, bool critic, bool actor, cudaStr
         TC_MAP(mW3Tb, ws + (i == 0 ? w.Wc2Tl : w.Wa2Tl), N.n2, 128, 128, N.n2, true);
         TC_MAP(mW2Ta, ws + (i == 0 ? w.Wc1Th : w.Wa1Th), 256, N.n2, N.n2, 256, true);
         TC_MAP(mW2Tb, ws + (i == 0 ? w.Wc1Tl : w.Wa1Tl), 256, N.n2, N.n2, 256, true);
+        TC_MAP(mDZ2, ws + (i == 0 ? w.GC2 : w.GA2), M, N.n2, N.n2, tc::BM, true);
+        TC_MAP(mDZ1, ws + (i == 0 ? w.GC1 : w.GA1), M, 256, 256, tc::BM, true);
         N.mZ3 = *mZ3; N.mH2 = *mH2; N.mH1 = *mH1; N.mW3Ta = *mW3Ta; N.mW3Tb = *mW3Tb; N.mW2Ta = *mW2Ta; N.mW2Tb = *mW2Tb;
-        N.DZ2 = reinterpret_cast<uint32_t*>(ws + (i == 0 ? w.GC2 : w.GA2));
-        N.DZ1 = reinterpret_cast<uint32_t*>(ws + (i == 0 ? w.GC1 : w.GA1));
+        N.mDZ2 = *mDZ2; N.mDZ1 = *mDZ1;
         N.db2 = p->G(i == 0 ? P_CB1 : P_AB1);
         N.db1 = p->G(i == 0 ? P_CB0 : P_AB0);
         N.isg = ws + w.SC + (i == 0 ? h2::SC_ISG_C : h2::SC_ISG_A);
@@ -1388,10 +1406,13 @@ static int chain_backward_h2(B200Ppo* p, int M, bool critic, bool actor, cudaStr
     }
     const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
     if (tiles <= 0) return B200_OK;
-    static unsigned long long configured = 0;
-    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2, chain2::B_SMEM, configured));
+    static unsigned long long configured[2] = {0, 0};
+    const int grid = tiles < p->num_sms ? tiles : p->num_sms;
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<1>, chain2::B_SMEM, configured[0]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<2>, chain2::B_SMEM, configured[1]));
     prof_begin(st, fl, PK_CHAIN_BWD, by);
-    chain2::k_mlp_bwd_h2<<<tiles < p->num_sms ? tiles : p->num_sms, chain2::B_THREADS, chain2::B_SMEM, st>>>(P);
+    if (g_h2_groups_bwd == 1) chain2::k_mlp_bwd_h2<1><<<grid, chain2::B_THREADS, chain2::B_SMEM, st>>>(P);
+    else chain2::k_mlp_bwd_h2<2><<<grid, chain2::B_THREADS, chain2::B_SMEM, st>>>(P);
     prof_end(st);
     g_launches += 1;
     return launch_status("k_mlp_bwd_h2");
@@ -1447,19 +1468,12 @@ static int chain_backward(B200Ppo* p, int M, bool critic, bool actor, cudaStream
 
 // ---- weight gradients on the h2 operand format (h2.cuh): all six hidden-layer matrices in one launch + one reduction ----------
 struct WgH2Operand { const float* dY; const float* X; int n_out, k_cols, k_valid; int pi; bool actor; float sx; };
-static int h2_pack(const float* src, float* dst, size_t n, float scale, const float* scale_ptr, cudaStream_t st) {
-    const size_t n4 = n / 4;
-    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-    h2::k_h2_pack<<<blocks, 256, 0, st>>>(src, reinterpret_cast<uint32_t*>(dst), n4, scale, scale_ptr);
-    g_launches += 1;
-    return launch_status("k_h2_pack");
-}
 static int wgrad_h2(B200Ppo* p, const WgH2Operand* ops, int M, cudaStream_t st) {
     h2::WgParams P;
     h2::WgRedJobs R;
     memset(&P, 0, sizeof(P));
     memset(&R, 0, sizeof(R));
-    // tiles (n-major, then k) and their cost per row: a 64-column tile issues half-width MMAs and loads 3/4 of the bytes
+    // tiles (n-major, then k) and their cost per row
     double cost[h2::WG_MAX_TILES];
     int nt = 0, total = 0;
     double flops = 0.0, bytes = 0.0;
@@ -1479,7 +1493,7 @@ static int wgrad_h2(B200Ppo* p, const WgH2Operand* ops, int M, cudaStream_t st) 
             for (int b = 0; b < tk; ++b, ++nt) {
                 if (nt >= h2::WG_MAX_TILES) return set_error(B200_ERR_ARG, "wgrad_h2: too many tiles");
                 P.tile[nt].job = j; P.tile[nt].n0 = a * 128; P.tile[nt].k0 = b * 128;
-                cost[nt] = kch == 4 ? 1.0 : 0.6;
+                cost[nt] = 1.0;   // an MMA costs the same ~216 clk whether N is 256 or 128 (tools/micro/mma_rate.cu)
             }
         flops += 2.0 * M * (double)o.n_out * o.k_valid;
         bytes += 4.0 * M * ((double)o.n_out + o.k_cols);
@@ -1760,27 +1774,6 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
                                         {GC2, ws + w.C1, 256, 256, 256, P_CW1, false, h2::S_ACT},  {GC1, ws + w.Xch, 256, 64, 61, P_CW0, false, h2::S_X}};
             return wgrad_h2(p, ops, M, st);
         }
-        if (g_h2_wgrad) {
-            // bring-up path: the TF32 chains' fp32 tensors packed into h2 words by an extra pass (the h2 chains write the words themselves)
-            const float* sga = ws + w.SC + h2::SC_SG_A;
-            const float* sgc = ws + w.SC + h2::SC_SG_C;
-            struct PK { const float* src; size_t dst; size_t n; float s; const float* sp; };
-            const size_t m = (size_t)M;
-            const PK pk[12] = {{ws + w.Xa, w.PXa, m * 64, h2::S_X, nullptr},   {ws + w.Xc, w.PXc, m * 64, h2::S_X, nullptr},
-                               {ws + w.A1, w.PA1, m * 256, h2::S_ACT, nullptr}, {ws + w.A2, w.PA2, m * 128, h2::S_ACT, nullptr},
-                               {ws + w.C1, w.PC1, m * 256, h2::S_ACT, nullptr}, {ws + w.C2, w.PC2, m * 256, h2::S_ACT, nullptr},
-                               {GA3, w.PGA3, m * 128, 1.0f, sga}, {GA2, w.PGA2, m * 128, 1.0f, sga}, {GA1, w.PGA1, m * 256, 1.0f, sga},
-                               {GC3, w.PGC3, m * 128, 1.0f, sgc}, {GC2, w.PGC2, m * 256, 1.0f, sgc}, {GC1, w.PGC1, m * 256, 1.0f, sgc}};
-            for (int i = 0; i < 12; ++i)
-                if ((rc = h2_pack(pk[i].src, ws + pk[i].dst, pk[i].n, pk[i].s, pk[i].sp, st))) return rc;
-            const WgH2Operand ops[6] = {{ws + w.PGA3, ws + w.PA2, 128, 128, 128, P_AW2, true, h2::S_ACT},
-                                        {ws + w.PGA2, ws + w.PA1, 128, 256, 256, P_AW1, true, h2::S_ACT},
-                                        {ws + w.PGA1, ws + w.PXa, 256, 64, 47, P_AW0, true, h2::S_X},
-                                        {ws + w.PGC3, ws + w.PC2, 128, 256, 256, P_CW2, false, h2::S_ACT},
-                                        {ws + w.PGC2, ws + w.PC1, 256, 256, 256, P_CW1, false, h2::S_ACT},
-                                        {ws + w.PGC1, ws + w.PXc, 256, 64, 61, P_CW0, false, h2::S_X}};
-            return wgrad_h2(p, ops, M, st);
-        }
         if ((rc = tc_wgrad(p, jobs, 0, GA3, 128, ws + w.A2, 128, 128, 128, p->G(P_AW2), M, st))) return rc;
         if ((rc = tc_wgrad(p, jobs, 1, GA2, 128, ws + w.A1, 256, 256, 256, p->G(P_AW1), M, st))) return rc;
         if ((rc = tc_wgrad(p, jobs, 2, GA1, 256, ws + w.Xa, 64, 64, 47, p->G(P_AW0), M, st))) return rc;
@@ -1861,15 +1854,16 @@ int b200_tc_set_pair(int enable) {
     return B200_OK;
 }
 int b200_tc_set_h2(int mode) {
-    g_h2_wgrad = (mode & 1) != 0;
-    g_h2_chain = (mode & 2) != 0;
-    if (g_h2_chain) g_chain = true;
+    g_h2_chain = (mode & 1) != 0;
+    if (g_h2_chain) { g_chain = true; g_chain_pair = false; }
+    if (mode & 0x30) g_h2_groups_fwd = ((mode >> 4) & 3) >= 2 ? 2 : 1;   // bits 4-5 / 6-7: epilogue warp groups (1 or 2) of the forward /
+    if (mode & 0xC0) g_h2_groups_bwd = ((mode >> 6) & 3) >= 2 ? 2 : 1;   // backward chain
     return B200_OK;
 }
 int b200_tc_set_chain(int enable) {
     g_chain = enable != 0;
     g_chain_pair = enable == 2;
-    if (enable != 1) g_h2_chain = false;   // the h2 chains exist as single-CTA fused chains only
+    if (enable != 1) g_h2_chain = false;   // the h2 kernels exist as single-CTA fused chains only (re-enable with b200_tc_set_h2(1))
     return B200_OK;
 }
 

@@ -323,9 +323,10 @@ int b200_fma_peak(double* tflops, void* stream);
  * tiles, each CTA stages half of every weight k-block), 0 = one GEMM launch per layer (k_tc_rowmajor).  Same results within the
  * stated tolerances; replaces the autograd graph of utils/runner.py:132-133,148,163. */
 int b200_tc_set_chain(int enable);
-/* operand format of the hidden-layer GEMMs (h2.cuh): bit 0 = weight gradients, bit 1 = forward / input-gradient chains on "h2 words"
- * (two fp16 halves per 32-bit word, power-of-two scales, tcgen05.mma kind::f16: twice the kind::tf32 rate, fp32-class products);
- * 0 = the 3xTF32 kernels.  Same results within the stated tolerances. */
+/* operand format of the hidden-layer GEMMs of the PPO epoch: bit 0 = 1 (default) "h2 words" (h2.cuh: two fp16 halves per 32-bit word,
+ * power-of-two scales, tcgen05.mma kind::f16 - two MMAs per k-step at twice the kind::tf32 rate, fp32-class products; forward and
+ * input-gradient chains in mlp_chain_h2.cuh, all six weight gradients in one k_wgrad_h2 launch), 0 = the 3xTF32 kernels.  Bits 4-5 /
+ * 6-7: epilogue warp groups (1 or 2) of the forward / backward chain (tuning).  Same results within the stated tolerances. */
 int b200_tc_set_h2(int mode);
 
 #ifdef __cplusplus

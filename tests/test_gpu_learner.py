@@ -149,16 +149,26 @@ def test_gae_bit_exact(T, N):
     assert abs(s[0].item() - adv_ref.double().sum().item()) <= 1e-9 * max(1.0, adv_ref.double().abs().sum().item())
 
 
-@pytest.mark.parametrize("T,N,pair", [(24, 4096, 0), (3, 200, 0), (6, 1000, 1)])
-def test_epoch_against_oracle(t1_cfg, T, N, pair):
-    """pair = 1 runs the critic forward / dgrad GEMMs on CTA pairs (tcgen05 cta_group::2) - same tolerances"""
+@pytest.mark.parametrize("T,N,mode", [(24, 4096, "h2"), (3, 200, "h2"), (6, 1000, "h2"), (24, 4096, "tf32"), (6, 1000, "tf32-pair"),
+                                      (5, 300, "layers")])
+def test_epoch_against_oracle(t1_cfg, T, N, mode):
+    """h2: the default kernels (two-fp16-halves operand format, tcgen05 kind::f16: mlp_chain_h2.cuh, k_wgrad_h2); tf32: the 3xTF32
+    fused chains + k_tc_wgrad; tf32-pair: the same chains on CTA pairs (cta_group::2); layers: one 3xTF32 GEMM launch per layer.
+    Same tolerances for all."""
     from booster_gym_b200 import _lib
 
-    _lib.load().b200_tc_set_pair(pair)
+    lib = _lib.load()
     try:
+        if mode == "h2":
+            lib.b200_tc_set_chain(1)
+            lib.b200_tc_set_h2(1)
+        else:
+            lib.b200_tc_set_h2(0)
+            lib.b200_tc_set_chain({"tf32": 1, "tf32-pair": 2, "layers": 0}[mode])
         _epoch_against_oracle(t1_cfg, T, N)
     finally:
-        _lib.load().b200_tc_set_pair(0)
+        lib.b200_tc_set_chain(1)
+        lib.b200_tc_set_h2(1)
 
 
 def _epoch_against_oracle(t1_cfg, T, N):

@@ -22,6 +22,8 @@ cfg["runner"]["horizon_length"] = T
 lib = _lib.load()
 lib.b200_chain_timeline_read.restype = C.c_int
 lib.b200_chain_timeline_read.argtypes = [C.c_void_p]
+if len(sys.argv) > 3:
+    lib.b200_tc_set_h2(int(sys.argv[3]))   # e.g. 35 = h2 chains, two epilogue warp groups
 lrn = Learner(cfg, N, "cuda:0", learning_rate=1e-4, seed=1)
 lrn.load_state_dict(L.init_params(0))
 buf, lo, lp = L.synthetic_rollout(T, N, seed=3, done_rate=0.02, timeout_rate=0.03)

@@ -1,5 +1,6 @@
 """h2 operand format (h2.cuh) against the 3xTF32 kernels and the fp64 oracle on the same inputs: parameter gradients of one epoch,
-and the time of one epoch each way.  Usage: python tools/h2_check.py [T N] [modes, e.g. 0,1,3]"""
+and the time of one epoch each way.  Usage: python tools/h2_check.py [T N] [b200_tc_set_h2 modes, e.g. 0,1,17 (17 = h2, one forward
+epilogue warp group)]"""
 import copy
 import ctypes as C
 import os
