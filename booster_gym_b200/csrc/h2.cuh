@@ -187,13 +187,13 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) k_wgrad_h2(const __grid_consta
                 mbar_wait_wd(&full[s], ph, 920 + (int)s);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t a = sbase + s * WG2_STAGE, b = a + WG2_A;
+                const uint64_t da0 = desc_mn16(a, WG2_BOX), db0 = desc_mn16(b, WG2_BOX);
 #pragma unroll
                 for (int k = 0; k < WG2_ROWS / 16; ++k) {
-                    const uint32_t off = k * 2048;   // 16 rows (samples) = two 8-row swizzle groups
-                    const uint64_t db = desc_mn16(b + off, WG2_BOX);
+                    const uint64_t koff = (uint64_t)(k * 2048 >> 4);   // 16 rows (samples) = two 8-row swizzle groups; start-address field counts 16 bytes
                     const uint32_t acc = (first && k == 0) ? 0u : 1u;
-                    umma_f16(tmem_base, desc_mn16(a + off, WG2_BOX), db, idesc, acc);
-                    umma_f16(tmem_base + 256, desc_mn16(a + 2 * WG2_BOX + off, WG2_BOX), db, idesc, acc);
+                    umma_f16(tmem_base, da0 + koff, db0 + koff, idesc, acc);
+                    umma_f16(tmem_base + 256, da0 + (2 * WG2_BOX >> 4) + koff, db0 + koff, idesc, acc);
                 }
                 umma_commit(&empty[s]);
             }

@@ -1063,8 +1063,11 @@ static int g_chain_exact_actor = getenv("B200_CHAIN_DEBUG") ? atoi(getenv("B200_
 static bool g_chain_pair = getenv("B200_CHAIN_PAIR") ? atoi(getenv("B200_CHAIN_PAIR")) != 0 : false;   // chains on CTA pairs (cta_group::2)
 static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
 static bool g_h2_chain = getenv("B200_H2") ? atoi(getenv("B200_H2")) != 0 : true;   // hidden-layer GEMMs on the h2 operand format (h2.cuh, mlp_chain_h2.cuh); 0 = 3xTF32 kernels
-// epilogue warp groups of the h2 chains (1 or 2; measured best: forward 2, backward 1)
-static int g_h2_groups_fwd = getenv("B200_H2_GROUPS_FWD") ? atoi(getenv("B200_H2_GROUPS_FWD")) : 2;
+// epilogue warp groups of the h2 chains (1 or 2; measured equal within noise)
+// h2 chains: weight multicast in clusters of two CTAs (halves the L2 -> SM weight stream; measured: no gain, the kernels are bound by the per-k-block
+// epilogue latency, not by the fill - off by default)
+static bool g_h2_mc = getenv("B200_H2_MC") ? atoi(getenv("B200_H2_MC")) != 0 : false;
+static int g_h2_groups_fwd = getenv("B200_H2_GROUPS_FWD") ? atoi(getenv("B200_H2_GROUPS_FWD")) : 1;
 static int g_h2_groups_bwd = getenv("B200_H2_GROUPS_BWD") ? atoi(getenv("B200_H2_GROUPS_BWD")) : 1;
 static int g_tl_slot = 0;   // timeline slot of the next tcgen05 launch (debug builds)
 static int tl_next() { const int s = g_tl_slot; g_tl_slot = (g_tl_slot + 1) % 40; return s; }
@@ -1307,6 +1310,12 @@ static cudaError_t chain_launch(void (*kernel)(const Params), const Params& P, i
     return cudaLaunchKernelEx(&cfg, kernel, P);
 }
 
+// h2 chains: one persistent CTA per SM; `pair`: clusters of two CTAs that share the weight stream (256-row work tiles)
+template <typename Params>
+static cudaError_t h2_chain_launch(void (*kernel)(const Params), const Params& P, int rows0, int rows1, int threads, int smem, bool pair,
+                                   int num_sms, cudaStream_t st) {
+    return chain_launch(kernel, P, rows0, rows1, threads, smem, pair, num_sms, st);
+}
 // the same launch on the h2 operand format (mlp_chain_h2.cuh): Xh = input words, W*h / W*l = B' / B'' words, H1 / H2 receive words
 static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs& c1, cudaStream_t st) {
     chain2::FwdParams P;
@@ -1318,13 +1327,14 @@ static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPt
         chain2::FwdNet& N = P.net[i];
         N.rows = c.rows > 0 ? c.rows : 0; N.n2 = c.n2; N.pad0_ = 0; N.pad_ = 0;
         if (c.rows <= 0) continue;
+        const int pd = g_h2_mc ? 2 : 1;   // weight multicast in CTA pairs: each CTA loads half of the rows of a weight k-block
         TC_MAP(mX, c.Xh, c.rows, 64, 64, tc::BM, true);
-        TC_MAP(mW1a, c.W1h, 256, 64, 64, 256, true);
-        TC_MAP(mW1b, c.W1l, 256, 64, 64, 256, true);
-        TC_MAP(mW2a, c.W2h, c.n2, 256, 256, c.n2, true);
-        TC_MAP(mW2b, c.W2l, c.n2, 256, 256, c.n2, true);
-        TC_MAP(mW3a, c.W3h, 128, c.n2, c.n2, 128, true);
-        TC_MAP(mW3b, c.W3l, 128, c.n2, c.n2, 128, true);
+        TC_MAP(mW1a, c.W1h, 256, 64, 64, 256 / pd, true);
+        TC_MAP(mW1b, c.W1l, 256, 64, 64, 256 / pd, true);
+        TC_MAP(mW2a, c.W2h, c.n2, 256, 256, (c.n2 == 256 ? 256 : 128) / pd, true);
+        TC_MAP(mW2b, c.W2l, c.n2, 256, 256, (c.n2 == 256 ? 256 : 128) / pd, true);
+        TC_MAP(mW3a, c.W3h, 128, c.n2, c.n2, 128 / pd, true);
+        TC_MAP(mW3b, c.W3l, 128, c.n2, c.n2, 128 / pd, true);
         TC_MAP(mH1, c.H1, c.rows, 256, 256, tc::BM, true);
         TC_MAP(mH2, c.H2, c.rows, c.n2, c.n2, tc::BM, true);
         TC_MAP(mH3, c.H3, c.rows, 128, 128, tc::BM, true);
@@ -1336,15 +1346,18 @@ static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPt
     }
     const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
     if (tiles <= 0) return B200_OK;
-    static unsigned long long configured[2] = {0, 0};
-    const int grid = tiles < p->num_sms ? tiles : p->num_sms;
-    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<1>, chain2::F_SMEM, configured[0]));
-    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<2>, chain2::F_SMEM, configured[1]));
+    static unsigned long long configured[4] = {0, 0, 0, 0};
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<1, 0>, chain2::F_SMEM, configured[0]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<2, 0>, chain2::F_SMEM, configured[1]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<1, 1>, chain2::F_SMEM, configured[2]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<2, 1>, chain2::F_SMEM, configured[3]));
     prof_begin(st, fl, PK_CHAIN_FWD, by);
-    if (g_h2_groups_fwd == 1) chain2::k_mlp_fwd_h2<1><<<grid, chain2::F_THREADS, chain2::F_SMEM, st>>>(P);
-    else chain2::k_mlp_fwd_h2<2><<<grid, chain2::F_THREADS, chain2::F_SMEM, st>>>(P);
+    const bool g2 = g_h2_groups_fwd != 1;
+    const cudaError_t le = g_h2_mc ? h2_chain_launch(g2 ? chain2::k_mlp_fwd_h2<2, 1> : chain2::k_mlp_fwd_h2<1, 1>, P, P.net[0].rows, P.net[1].rows, chain2::F_THREADS, chain2::F_SMEM, true, p->num_sms, st)
+                                   : h2_chain_launch(g2 ? chain2::k_mlp_fwd_h2<2, 0> : chain2::k_mlp_fwd_h2<1, 0>, P, P.net[0].rows, P.net[1].rows, chain2::F_THREADS, chain2::F_SMEM, false, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
+    if (le != cudaSuccess) return set_cuda_error(le, "k_mlp_fwd_h2");
     return launch_status("k_mlp_fwd_h2");
 }
 static int chain_forward(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs& c1, cudaStream_t st) {
@@ -1390,10 +1403,11 @@ static int chain_backward_h2(B200Ppo* p, int M, bool critic, bool actor, cudaStr
         TC_MAP(mZ3, ws + (i == 0 ? w.GC3 : w.GA3), M, 128, 128, tc::BM, true);
         TC_MAP(mH2, ws + (i == 0 ? w.C2 : w.A2), M, N.n2, N.n2, tc::BM, true);
         TC_MAP(mH1, ws + (i == 0 ? w.C1 : w.A1), M, 256, 256, tc::BM, true);
-        TC_MAP(mW3Ta, ws + (i == 0 ? w.Wc2Th : w.Wa2Th), N.n2, 128, 128, N.n2, true);
-        TC_MAP(mW3Tb, ws + (i == 0 ? w.Wc2Tl : w.Wa2Tl), N.n2, 128, 128, N.n2, true);
-        TC_MAP(mW2Ta, ws + (i == 0 ? w.Wc1Th : w.Wa1Th), 256, N.n2, N.n2, 256, true);
-        TC_MAP(mW2Tb, ws + (i == 0 ? w.Wc1Tl : w.Wa1Tl), 256, N.n2, N.n2, 256, true);
+        const int pd = g_h2_mc ? 2 : 1;
+        TC_MAP(mW3Ta, ws + (i == 0 ? w.Wc2Th : w.Wa2Th), N.n2, 128, 128, (N.n2 == 256 ? 256 : 128) / pd, true);
+        TC_MAP(mW3Tb, ws + (i == 0 ? w.Wc2Tl : w.Wa2Tl), N.n2, 128, 128, (N.n2 == 256 ? 256 : 128) / pd, true);
+        TC_MAP(mW2Ta, ws + (i == 0 ? w.Wc1Th : w.Wa1Th), 256, N.n2, N.n2, 256 / pd, true);
+        TC_MAP(mW2Tb, ws + (i == 0 ? w.Wc1Tl : w.Wa1Tl), 256, N.n2, N.n2, 256 / pd, true);
         TC_MAP(mDZ2, ws + (i == 0 ? w.GC2 : w.GA2), M, N.n2, N.n2, tc::BM, true);
         TC_MAP(mDZ1, ws + (i == 0 ? w.GC1 : w.GA1), M, 256, 256, tc::BM, true);
         N.mZ3 = *mZ3; N.mH2 = *mH2; N.mH1 = *mH1; N.mW3Ta = *mW3Ta; N.mW3Tb = *mW3Tb; N.mW2Ta = *mW2Ta; N.mW2Tb = *mW2Tb;
@@ -1406,15 +1420,18 @@ static int chain_backward_h2(B200Ppo* p, int M, bool critic, bool actor, cudaStr
     }
     const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
     if (tiles <= 0) return B200_OK;
-    static unsigned long long configured[2] = {0, 0};
-    const int grid = tiles < p->num_sms ? tiles : p->num_sms;
-    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<1>, chain2::B_SMEM, configured[0]));
-    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<2>, chain2::B_SMEM, configured[1]));
+    static unsigned long long configured[4] = {0, 0, 0, 0};
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<1, 0>, chain2::B_SMEM, configured[0]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<2, 0>, chain2::B_SMEM, configured[1]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<1, 1>, chain2::B_SMEM, configured[2]));
+    CU_TRY(ensure_dynamic_smem(chain2::k_mlp_bwd_h2<2, 1>, chain2::B_SMEM, configured[3]));
     prof_begin(st, fl, PK_CHAIN_BWD, by);
-    if (g_h2_groups_bwd == 1) chain2::k_mlp_bwd_h2<1><<<grid, chain2::B_THREADS, chain2::B_SMEM, st>>>(P);
-    else chain2::k_mlp_bwd_h2<2><<<grid, chain2::B_THREADS, chain2::B_SMEM, st>>>(P);
+    const bool g2 = g_h2_groups_bwd != 1;
+    const cudaError_t le = g_h2_mc ? h2_chain_launch(g2 ? chain2::k_mlp_bwd_h2<2, 1> : chain2::k_mlp_bwd_h2<1, 1>, P, P.net[0].rows, P.net[1].rows, chain2::B_THREADS, chain2::B_SMEM, true, p->num_sms, st)
+                                   : h2_chain_launch(g2 ? chain2::k_mlp_bwd_h2<2, 0> : chain2::k_mlp_bwd_h2<1, 0>, P, P.net[0].rows, P.net[1].rows, chain2::B_THREADS, chain2::B_SMEM, false, p->num_sms, st);
     prof_end(st);
     g_launches += 1;
+    if (le != cudaSuccess) return set_cuda_error(le, "k_mlp_bwd_h2");
     return launch_status("k_mlp_bwd_h2");
 }
 static int chain_backward(B200Ppo* p, int M, bool critic, bool actor, cudaStream_t st) {
@@ -1858,6 +1875,7 @@ int b200_tc_set_h2(int mode) {
     if (g_h2_chain) { g_chain = true; g_chain_pair = false; }
     if (mode & 0x30) g_h2_groups_fwd = ((mode >> 4) & 3) >= 2 ? 2 : 1;   // bits 4-5 / 6-7: epilogue warp groups (1 or 2) of the forward /
     if (mode & 0xC0) g_h2_groups_bwd = ((mode >> 6) & 3) >= 2 ? 2 : 1;   // backward chain
+    if (mode & 0x300) g_h2_mc = ((mode >> 8) & 3) >= 2;                  // bits 8-9: 1 = every CTA streams its own weights, 2 = multicast in CTA pairs
     return B200_OK;
 }
 int b200_tc_set_chain(int enable) {

@@ -63,7 +63,32 @@ __device__ __forceinline__ void handover(uint64_t* bar, int lane) {
 // 128-byte lines per warp instruction - measured 68 % busy LSU data pipe, with the bias loads queueing behind the stores.  Instead
 // the 16 warps write their 32-byte row pieces into a [128 x 32]-word staging tile in shared memory (128-byte swizzle, conflict-free
 // 16-byte stores) and one thread of a dedicated warp sends the 16 KB tile out as ONE bulk tensor store (rows beyond the tensor are clipped).
-static constexpr int O_STAGES = 2;
+#ifndef H2_O_STAGES
+#define H2_O_STAGES 2
+#endif
+static constexpr int O_STAGES = H2_O_STAGES;
+// MC = 1: clusters of two CTAs share the WEIGHT stream.  Every CTA re-reads all weights of a net for each of its row tiles (0.9 MB
+// per critic tile): measured, with MMAs, arithmetic and stores switched off the forward kernel still took 107 of its 190 us - the
+// L2 -> SM fill (~42 B/clk/SM).  The two CTAs of a cluster walk the same tile sequence on neighbouring row tiles; each loads HALF of
+// every weight k-block and multicasts it into both shared memories (cp.async.bulk.tensor ... .multicast::cluster), a ring stage is
+// free once BOTH tensor cores have read it (tcgen05.commit ... .multicast::cluster on the stage's `empty` barrier).  Everything else
+// (input / aux tiles, TMEM, epilogue, stores) stays private to the CTA; the MMAs stay cta_group::1.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the cluster
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int MC> __device__ __forceinline__ void release_unit(uint64_t* bar) {
+    if (MC) umma_commit_mc(bar); else umma_commit(bar);
+}
+// one weight-ring unit: [rows x 32] words of map `m` at k-block kb -> dst; MC: this CTA loads its half of the rows for both CTAs
+template <int MC> __device__ __forceinline__ void load_rows(const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb, int rows, uint32_t rank) {
+    if (MC) tma_load_2d_mc(m, bar, dst + rank * (uint32_t)(rows / 2) * 128u, kb * BK, (int)rank * (rows / 2));
+    else tma_load_2d(m, bar, dst, kb * BK, 0);
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -96,7 +121,7 @@ struct alignas(64) FwdNet {
 };
 struct alignas(64) FwdParams { FwdNet net[2]; };
 
-static constexpr int F_UNITS = 5;
+static constexpr int F_UNITS = O_STAGES == 2 ? 5 : 4;
 static constexpr int F_EPI0 = 3;                           // first epilogue warp
 static constexpr int F_THREADS = 32 * (F_EPI0 + EPI_W);    // TMA loads, MMA, TMA stores, 16 epilogue warps
 static constexpr int F_X = 0, F_B = 2 * KB_BYTES, F_OUT = F_B + F_UNITS * UNIT_BYTES, F_BAR = F_OUT + O_STAGES * KB_BYTES,
@@ -106,7 +131,7 @@ static_assert(F_SMEM <= 232448, "shared memory budget");
 // G = epilogue warp groups: group j owns the k-blocks kb = j (mod G) of every layer and walks a k-block's 32 columns in G chunks of
 // 8 per thread, so G hand-overs are in flight at once and one group's fixed latencies (tcgen05.ld, tcgen05.wait::st, the mbarrier
 // round trip to the MMA thread) hide behind the other groups' arithmetic.  G = 1: all 16 warps on the same k-block.
-template <int G>
+template <int G, int MC>
 __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -120,13 +145,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
     uint64_t* o_full = drained + 1;          // [O_STAGES] an output staging tile is complete
     uint64_t* o_empty = o_full + O_STAGES;   // [O_STAGES] ... and has been read by its bulk store
     uint32_t* tmem_slot = (uint32_t*)(o_empty + O_STAGES);
-    static_assert(G == 1 || G == O_STAGES, "one staging tile per epilogue warp group");
+    static_assert(O_STAGES % G == 0, "staging tiles rotate over the epilogue warp groups");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    constexpr int TM = MC ? 2 * BM : BM;      // rows of a work tile (MC: one 128-row half per CTA)
 
     if (warp == 0 && lane == 0) {
         mbar_init(x_full, 1); mbar_init(x_empty, 1);
-        for (int s = 0; s < F_UNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < F_UNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MC ? 2 : 1); }
         for (int s = 0; s < HAND; ++s) mbar_init(&a_full[s], EPI_W / G);
         for (int s = 0; s < 3; ++s) mbar_init(&accf[s], 1);
         mbar_init(drained, EPI_W);
@@ -138,7 +165,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -146,7 +173,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
         // ===== TMA stores: every staged [128 x 32] output tile -> h1 / h2 (words) / h3 (fp32) =====
         if (lane == 0) {
             uint32_t oi = 0;
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const FwdNet& N = P.net[ni];
@@ -156,7 +183,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                     for (int kb = 0; kb < nkb; ++kb, ++oi) {
                         const uint32_t s = oi % O_STAGES, ph = (oi / O_STAGES) & 1;
                         mbar_wait_wd(&o_full[s], ph, 400 + (int)s);
-                        tma_store_2d(map, sbase + F_OUT + s * KB_BYTES, kb * BK, tile * BM);
+                        tma_store_2d(map, sbase + F_OUT + s * KB_BYTES, kb * BK, tile * TM + (int)rank * BM);
                         // all but the newest store have finished READING their staging tile: hand the previous one back
                         asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(O_STAGES - 1) : "memory");
                         if (oi >= O_STAGES - 1) mbar_arrive(&o_empty[(oi - (O_STAGES - 1)) % O_STAGES]);
@@ -174,22 +201,22 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                     const uint32_t s = u % F_UNITS, ph = (u / F_UNITS) & 1;
                     mbar_wait_wd(&b_empty[s], ph ^ 1, 100 + (int)s);
                     mbar_expect_tx(&b_full[s], UNIT_BYTES);
-                    tma_load_2d(half ? mb : ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb * BK, 0);
+                    load_rows<MC>(half ? mb : ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb, 256, rank);
                 }
             };
             auto narrow = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kb) {   // B' + B'' of [128 x 32] in one unit
                 const uint32_t s = u % F_UNITS, ph = (u / F_UNITS) & 1;
                 mbar_wait_wd(&b_empty[s], ph ^ 1, 110 + (int)s);
                 mbar_expect_tx(&b_full[s], UNIT_BYTES);
-                tma_load_2d(ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb * BK, 0);
-                tma_load_2d(mb, &b_full[s], sbase + F_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, 0);
+                load_rows<MC>(ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb, 128, rank);
+                load_rows<MC>(mb, &b_full[s], sbase + F_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb, 128, rank);
                 ++u;
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const FwdNet& N = P.net[ni];
-                const int m0 = tile * BM;
+                const int m0 = tile * TM + (int)rank * BM;
                 mbar_wait_wd(x_empty, (t & 1) ^ 1, 120);
                 mbar_expect_tx(x_full, 2 * KB_BYTES);
                 tma_load_2d(&N.mX, x_full, sbase + F_X, 0, m0);
@@ -223,7 +250,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                     e0 = &b_empty[sa];
                 }
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const int n2 = P.net[ni].n2;
@@ -241,21 +268,24 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                     for (int kb = 0; kb < 2; ++kb) weights(256, b_a[kb], b_b[kb], e0[kb], e1[kb], 210);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     constexpr uint32_t id = idesc_f16_k(256);
+                    // (descriptors: one per operand tile, + 2 per 32-byte k-step in the start-address field - the issuing thread's own
+                    // instructions between two tcgen05.mma are on the critical path of the tensor pipe)
+                    uint64_t da[2], dba[2], dbb[2];
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) { da[kb] = desc_kmajor(sbase + F_X + kb * KB_BYTES); dba[kb] = desc_kmajor(b_a[kb]); dbb[kb] = desc_kmajor(b_b[kb]); }
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
-                        const uint32_t a = sbase + F_X + kb * KB_BYTES;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16(c1, desc_kmajor(a + k * 32), desc_kmajor(b_b[kb] + k * 32), id, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma_f16(c1, da[kb] + 2 * k, dbb[kb] + 2 * k, id, (kb | k) ? 1u : 0u);
                     }
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
-                        const uint32_t a = sbase + F_X + kb * KB_BYTES;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16(c1, desc_kmajor(a + k * 32), desc_kmajor(b_a[kb] + k * 32), id, 1u);
+                        for (int k = 0; k < 4; ++k) umma_f16(c1, da[kb] + 2 * k, dba[kb] + 2 * k, id, 1u);
                     }
                     for (int kb = 0; kb < 2; ++kb) {
-                        umma_commit(e0[kb]);
-                        if (e1[kb]) umma_commit(e1[kb]);
+                        release_unit<MC>(e0[kb]);
+                        if (e1[kb]) release_unit<MC>(e1[kb]);
                     }
                 }
                 umma_commit(x_empty);
@@ -278,18 +308,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                         weights(nn, b_a, b_b, e0, e1, 220);
                         CTL_WAIT(3 + layer, mbar_wait_wd(&a_full[li % HAND], (li / HAND) & 1, 230 + layer));   // the epilogue has written this k-block's words to TMEM
                         asm volatile("tcgen05.fence::after_thread_sync;");
+                        const uint64_t dba = desc_kmajor(b_a), dbb = desc_kmajor(b_b);
+                        const uint32_t a_t = ca + kb * BK;
+                        if (nn == 128) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t off = k * 32, a_t = ca + kb * BK + k * 8;
-                            if (nn == 128) {
-                                umma_f16_ts(cd, a_t, desc_kmajor(b_a + off), id, (kb | k) ? 1u : 0u);
-                            } else {
-                                umma_f16_ts(cd, a_t, desc_kmajor(b_b + off), id, (kb | k) ? 1u : 0u);
-                                umma_f16_ts(cd, a_t, desc_kmajor(b_a + off), id, 1u);
+                            for (int k = 0; k < 4; ++k) umma_f16_ts(cd, a_t + k * 8, dba + 2 * k, id, (kb | k) ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_f16_ts(cd, a_t + k * 8, dbb + 2 * k, id, (kb | k) ? 1u : 0u);
+                                umma_f16_ts(cd, a_t + k * 8, dba + 2 * k, id, 1u);
                             }
                         }
-                        umma_commit(e0);
-                        if (e1) umma_commit(e1);
+                        release_unit<MC>(e0);
+                        if (e1) release_unit<MC>(e1);
                     }
                     umma_commit(&accf[1 + layer]);
                 }
@@ -304,7 +336,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
         const int rit = q * 32 + lane;                 // row in this CTA's 128-row tile
         uint32_t t = 0, li_base = 0, oi_base = 0;
         CTL_DECL;
-        TileSeq seq(P.net[0].rows, P.net[1].rows);
+        TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
         int ni, tile;
         while (seq.next(ni, tile)) {
             const FwdNet& N = P.net[ni];
@@ -382,7 +414,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
         if (threadIdx.x == 32 * F_EPI0) CTL_FLUSH(0, 8, 7);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();   // (MC: the peer's multicasts / commits into this CTA have all landed)
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
@@ -401,7 +433,11 @@ struct alignas(64) BwdNet {
 };
 struct alignas(64) BwdParams { BwdNet net[2]; };
 
-static constexpr int B_UNITS = 4, B_AUX_STAGES = 4;
+#ifndef H2_B_UNITS
+#define H2_B_UNITS 4
+#define H2_B_AUX 4
+#endif
+static constexpr int B_UNITS = H2_B_UNITS, B_AUX_STAGES = H2_B_AUX;
 static constexpr int B_EPI0 = 4;                           // warp 0 weight TMA, 1 MMA, 2 aux TMA, 3 TMA stores
 static constexpr int B_THREADS = 32 * (B_EPI0 + EPI_W);
 static constexpr int B_B = 0, B_AUX = B_UNITS * UNIT_BYTES, B_OUT = B_AUX + B_AUX_STAGES * KB_BYTES, B_BAR = B_OUT + O_STAGES * KB_BYTES,
@@ -425,7 +461,7 @@ __device__ __forceinline__ void colsum8s(float* v, int lane, float* dst, float s
     if (lane < 8) atomicAdd(dst + lane, tot * scale);   // lane l holds column l (bit i of l picked the upper half at step 2^i)
 }
 
-template <int G>   // epilogue warp groups (see k_mlp_fwd_h2)
+template <int G, int MC>   // epilogue warp groups, weight multicast in CTA pairs (see k_mlp_fwd_h2)
 __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_constant__ BwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -439,12 +475,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
     uint64_t* o_full = drained + 1;              // [O_STAGES] output staging tiles (see k_mlp_fwd_h2)
     uint64_t* o_empty = o_full + O_STAGES;
     uint32_t* tmem_slot = (uint32_t*)(o_empty + O_STAGES);
-    static_assert(G == 1 || G == O_STAGES, "one staging tile per epilogue warp group");
+    static_assert(O_STAGES % G == 0, "staging tiles rotate over the epilogue warp groups");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    constexpr int TM = MC ? 2 * BM : BM;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < B_UNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < B_UNITS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MC ? 2 : 1); }
         for (int s = 0; s < HAND; ++s) mbar_init(&a_full[s], EPI_W / G);
         for (int s = 0; s < B_AUX_STAGES; ++s) { mbar_init(&aux_full[s], 1); mbar_init(&aux_empty[s], EPI_W / G); }
         mbar_init(&accf[0], 1); mbar_init(&accf[1], 1);
@@ -457,7 +495,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
     // TMEM columns: dz3 words [0,128); dh2 / dz2 [256, 512) (n2 = 128: main products [256,384) | cross terms [384,512)); dh1 [0,256) - its first
@@ -468,7 +506,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
         // ===== TMA stores: the staged [128 x 32] tiles of dz2, then dz1, per row tile =====
         if (lane == 0) {
             uint32_t oi = 0;
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const BwdNet& N = P.net[ni];
@@ -478,7 +516,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
                     for (int kb = 0; kb < nkb; ++kb, ++oi) {
                         const uint32_t s = oi % O_STAGES, ph = (oi / O_STAGES) & 1;
                         mbar_wait_wd(&o_full[s], ph, 800 + (int)s);
-                        tma_store_2d(map, sbase + B_OUT + s * KB_BYTES, kb * BK, tile * BM);
+                        tma_store_2d(map, sbase + B_OUT + s * KB_BYTES, kb * BK, tile * TM + (int)rank * BM);
                         asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(O_STAGES - 1) : "memory");
                         if (oi >= O_STAGES - 1) mbar_arrive(&o_empty[(oi - (O_STAGES - 1)) % O_STAGES]);
                     }
@@ -495,18 +533,18 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
                     const uint32_t s = u % B_UNITS, ph = (u / B_UNITS) & 1;
                     mbar_wait_wd(&b_empty[s], ph ^ 1, 500 + (int)s);
                     mbar_expect_tx(&b_full[s], UNIT_BYTES);
-                    tma_load_2d(half ? mb : ma, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb * BK, 0);
+                    load_rows<MC>(half ? mb : ma, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb, 256, rank);
                 }
             };
             auto narrow = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kb) {
                 const uint32_t s = u % B_UNITS, ph = (u / B_UNITS) & 1;
                 mbar_wait_wd(&b_empty[s], ph ^ 1, 510 + (int)s);
                 mbar_expect_tx(&b_full[s], UNIT_BYTES);
-                tma_load_2d(ma, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb * BK, 0);
-                tma_load_2d(mb, &b_full[s], sbase + B_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb * BK, 0);
+                load_rows<MC>(ma, &b_full[s], sbase + B_B + s * UNIT_BYTES, kb, 128, rank);
+                load_rows<MC>(mb, &b_full[s], sbase + B_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb, 128, rank);
                 ++u;
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const BwdNet& N = P.net[ni];
@@ -525,17 +563,17 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
                 tma_load_2d(m, &aux_full[s], sbase + B_AUX + s * KB_BYTES, kb * BK, m0);
                 ++ai;
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
             int cn, ct, nn = 0, nt = 0;
             bool have = seq.next(cn, ct);
-            if (have) for (int kb = 0; kb < 4; ++kb) aux(&P.net[cn].mZ3, kb, ct * BM);
+            if (have) for (int kb = 0; kb < 4; ++kb) aux(&P.net[cn].mZ3, kb, ct * TM + (int)rank * BM);
             while (have) {
                 const bool hn = seq.next(nn, nt);
                 const BwdNet& N = P.net[cn];
-                const int m0 = ct * BM;
+                const int m0 = ct * TM + (int)rank * BM;
                 for (int kb = 0; kb < N.n2 / BK; ++kb) aux(&N.mH2, kb, m0);
                 for (int kb = 0; kb < 4; ++kb) aux(&N.mH1, kb, m0);
-                if (hn) for (int kb = 0; kb < 4; ++kb) aux(&P.net[nn].mZ3, kb, nt * BM);
+                if (hn) for (int kb = 0; kb < 4; ++kb) aux(&P.net[nn].mZ3, kb, nt * TM + (int)rank * BM);
                 for (int kb = 4; kb < 8; ++kb) aux(&N.mH1, kb, m0);
                 have = hn; cn = nn; ct = nt;
             }
@@ -562,7 +600,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
                     e0 = &b_empty[sa];
                 }
             };
-            TileSeq seq(P.net[0].rows, P.net[1].rows);
+            TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
             int ni, tile;
             while (seq.next(ni, tile)) {
                 const int n2 = P.net[ni].n2;
@@ -574,18 +612,20 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
                     CTL_WAIT(3, mbar_wait_wd(&a_full[li % HAND], (li / HAND) & 1, 610));
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     constexpr uint32_t id = idesc_f16_k(256);   // (every MMA is N = 256: see k_mlp_fwd_h2)
+                    const uint64_t dba = desc_kmajor(b_a), dbb = desc_kmajor(b_b);
+                    const uint32_t a_t = tmem_base + CZ + kb * BK, cd = tmem_base + CA;
+                    if (n2 == 128) {   // stacked [B'; B''] unit: main | cross
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t off = k * 32, a_t = tmem_base + CZ + kb * BK + k * 8;
-                        if (n2 == 128) {   // stacked [B'; B''] unit: main | cross
-                            umma_f16_ts(tmem_base + CA, a_t, desc_kmajor(b_a + off), id, (kb | k) ? 1u : 0u);
-                        } else {
-                            umma_f16_ts(tmem_base + CA, a_t, desc_kmajor(b_b + off), id, (kb | k) ? 1u : 0u);
-                            umma_f16_ts(tmem_base + CA, a_t, desc_kmajor(b_a + off), id, 1u);
+                        for (int k = 0; k < 4; ++k) umma_f16_ts(cd, a_t + k * 8, dba + 2 * k, id, (kb | k) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16_ts(cd, a_t + k * 8, dbb + 2 * k, id, (kb | k) ? 1u : 0u);
+                            umma_f16_ts(cd, a_t + k * 8, dba + 2 * k, id, 1u);
                         }
                     }
-                    umma_commit(e0);
-                    if (e1) umma_commit(e1);
+                    release_unit<MC>(e0);
+                    if (e1) release_unit<MC>(e1);
                 }
                 umma_commit(&accf[0]);
                 // ---- dh1 [128, 256] = dz2 [128, n2] W2: n2 / 32 k-blocks
@@ -597,14 +637,15 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
                     CTL_WAIT(4, mbar_wait_wd(&a_full[li % HAND], (li / HAND) & 1, 630));
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     constexpr uint32_t id = idesc_f16_k(256);
+                    const uint64_t dba = desc_kmajor(b_a), dbb = desc_kmajor(b_b);
+                    const uint32_t a_t = tmem_base + CA + kb * BK, cd = tmem_base + CD;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint32_t off = k * 32, a_t = tmem_base + CA + kb * BK + k * 8;
-                        umma_f16_ts(tmem_base + CD, a_t, desc_kmajor(b_b + off), id, (kb | k) ? 1u : 0u);
-                        umma_f16_ts(tmem_base + CD, a_t, desc_kmajor(b_a + off), id, 1u);
+                        umma_f16_ts(cd, a_t + k * 8, dbb + 2 * k, id, (kb | k) ? 1u : 0u);
+                        umma_f16_ts(cd, a_t + k * 8, dba + 2 * k, id, 1u);
                     }
-                    umma_commit(e0);
-                    if (e1) umma_commit(e1);
+                    release_unit<MC>(e0);
+                    if (e1) release_unit<MC>(e1);
                 }
                 umma_commit(&accf[1]);
                 ++t;
@@ -697,7 +738,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
             oi_base += (uint32_t)nkb;
             if (handoff) li_base += (uint32_t)nkb;
         };
-        TileSeq seq(P.net[0].rows, P.net[1].rows);
+        TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
         int cn, ct, nn = 0, nt = 0;
         bool have = seq.next(cn, ct);
         if (have) stage_dz3();
@@ -705,7 +746,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
             const bool hn = seq.next(nn, nt);
             const BwdNet& N = P.net[cn];
             const int n2 = N.n2;
-            const bool row_ok = ct * BM + rit < N.rows;
+            const bool row_ok = ct * TM + (int)rank * BM + rit < N.rows;
             const uint32_t par = t & 1;
             const float isg = __ldg(N.isg);
             // dz2
@@ -727,7 +768,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
         if (threadIdx.x == 32 * B_EPI0) CTL_FLUSH(1, 8, 4);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
