@@ -58,7 +58,7 @@ def workload(args):
 def config_dict(args, world):
     return {"workload": workload(args), "num_envs_per_gpu": args.num_envs, "total_envs": args.num_envs * world, "horizon": 24,
             "mini_epochs": 20, "terrain": "plane" if args.config == 1 else "trimesh", "parallelism": f"env-sharded dp{world}",
-            "l2": "working set (the learner streams ~1.5 GB of fp32 activations per epoch through a >1 GB workspace per GPU) is larger than "
+            "l2": "working set (the learner streams ~2.2 GB of activations and gradients per epoch through a >1 GB workspace per GPU) is larger than "
                   "the 126 MB L2; no flush needed",
             "rollout_cuda_graph": bool(args.graphs)}
 
@@ -251,10 +251,18 @@ def b200_arm(args):
     lib.b200_profile_gemm(1)
     iteration()
     torch.cuda.synchronize(dev)
-    names = {1: ("k_tc_rowmajor", "tcgen05 3xTF32 GEMM, one launch per layer (B200_CHAIN=0 path)"),
-             2: ("k_tc_wgrad", "tcgen05/TMEM/TMA 3xTF32, MN-major operands, in-smem split: the six MLP weight gradients"),
-             3: ("k_mlp_fwd", "fused forward layer chain: 3 hidden layers per launch, activations handed over in TMEM (TS-form tcgen05.mma)"),
-             4: ("k_mlp_bwd", "fused backward layer chain: dz3 -> dz2 -> dz1 + bias gradients per launch")}
+    h2 = os.environ.get("B200_H2", "1") != "0" and os.environ.get("B200_CHAIN", "1") == "1"
+    if h2:   # default: the h2 operand format (two fp16 halves per word, tcgen05.mma kind::f16; h2.cuh, mlp_chain_h2.cuh)
+        names = {2: ("k_wgrad_h2", "all six MLP weight gradients in ONE launch: tcgen05 kind::f16 on MN-major h2 words straight from TMA, register flush every 64 MMAs"),
+                 3: ("k_mlp_fwd_h2", "fused forward layer chain on h2 words: 3 hidden layers of both nets per launch, hand-over = one packed word per TMEM column (TS-form tcgen05.mma kind::f16)"),
+                 4: ("k_mlp_bwd_h2", "fused backward layer chain on h2 words: dz3 -> dz2 -> dz1 + bias gradients of both nets per launch")}
+        split_exec, split_name = 4.0, "h2 split (2 MMAs of twice the K per product = 4x the algorithmic FLOPs at the BF16 / FP16 rate)"
+    else:
+        names = {1: ("k_tc_rowmajor", "tcgen05 3xTF32 GEMM, one launch per layer (B200_CHAIN=0 path)"),
+                 2: ("k_tc_wgrad", "tcgen05/TMEM/TMA 3xTF32, MN-major operands, in-smem split: the six MLP weight gradients"),
+                 3: ("k_mlp_fwd", "fused forward layer chain: 3 hidden layers per launch, activations handed over in TMEM (TS-form tcgen05.mma)"),
+                 4: ("k_mlp_bwd", "fused backward layer chain: dz3 -> dz2 -> dz1 + bias gradients per launch")}
+        split_exec, split_name = 6.0, "3xTF32 split (3 MMAs per product at the TF32 rate = 6x the algorithmic FLOPs at the BF16 rate)"
     fams = {}
     for kind in names:
         ms_g, fl_g, n_g, by_g = C.c_double(), C.c_double(), C.c_int(), C.c_double()
@@ -281,8 +289,9 @@ def b200_arm(args):
     for k, f in fams.items():
         tfl = f["flop"] / (f["ms"] * 1e-3) / 1e12
         fam_out[names[k][0]] = {"ms_per_step": f["ms"], "launches": f["launches"], "algorithmic_tflop": f["flop"] / 1e12, "tflops": tfl,
-                                "frac_of_bf16_sustained": tfl / peak_tf, "frac_of_3xtf32_ceiling": tfl / (peak_tf / 6.0),
+                                "frac_of_bf16_sustained": tfl / peak_tf, "frac_of_split_ceiling": tfl / (peak_tf / split_exec),
                                 "traffic_model_gbs": f["bytes_model"] / (f["ms"] * 1e-3) / 1e9,
+                                "traffic_model_frac_of_hbm_peak": f["bytes_model"] / (f["ms"] * 1e-3) / 1e9 / peak_hbm,
                                 "traffic_model_bytes_per_launch": f["bytes_model"] / f["launches"],
                                 "ncu_dram_bytes_per_launch": ncu_traffic.get(names[k][0])}
     ft = fams[top]
@@ -291,7 +300,7 @@ def b200_arm(args):
     all_fl = sum(f["flop"] for f in fams.values())
     roofline = {"kernel": f"{names[top][0]} ({names[top][1]})", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": ncu_traffic.get(names[top][0]),
-                "frac_of_3xtf32_ceiling": achieved / (peak_tf / 6.0),
+                "frac_of_split_ceiling": achieved / (peak_tf / split_exec), "split_ceiling_tflops": peak_tf / split_exec,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / hbm_gbs (measured on this pool)" if peaks
                                 else "fallback 1.4 PFLOP/s, 6.5 TB/s (B200_PROFILING.md)"),
                 "launches_per_step": ft["launches"], "algorithmic_flop_per_launch": ft["flop"] / ft["launches"],
@@ -304,8 +313,8 @@ def b200_arm(args):
                                     "frac_of_bf16_sustained": all_fl / (all_ms * 1e-3) / 1e12 / peak_tf,
                                     "share_of_step": all_ms / ms_step},
                 "families": fam_out,
-                "note": "algorithmic FLOPs = 2*rows*out*k once per product; the fp32-accurate 3-term TF32 split EXECUTES 3x that at the TF32 "
-                        "rate (half of BF16), so 1/6 of the BF16 peak is the ceiling of this arithmetic class (frac_of_3xtf32_ceiling)"}
+                "note": "algorithmic FLOPs = 2*rows*out*k once per product; the fp32-accurate " + split_name + " bounds this arithmetic class at "
+                        "1/%d of the measured BF16 peak (frac_of_split_ceiling); `traffic` = dram bytes per launch of this round's ncu capture" % int(split_exec)}
 
     # ---- k_physics against the MEASURED FP32 FMA peak (FP32-pipe roofline, measured on the box)
     fma = C.c_double()
@@ -346,7 +355,8 @@ def b200_arm(args):
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "rollout_env_steps_per_s": world * N * T / (ms_roll * 1e-3), "rollout_ms": ms_roll, "ppo_update_ms": ms_upd,
-               "ppo_iteration_ms": ms_step, "exchange": exchange, "mlp_path": "chain" if os.environ.get("B200_CHAIN", "1") != "0" else "layers"}
+               "ppo_iteration_ms": ms_step, "exchange": exchange,
+               "mlp_path": "h2" if h2 else ("chain-tf32" if os.environ.get("B200_CHAIN", "1") != "0" else "layers-tf32")}
         print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
