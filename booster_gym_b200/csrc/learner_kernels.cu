@@ -21,6 +21,7 @@
 #include "mlp_chain.cuh"
 #include "h2.cuh"
 #include "mlp_chain_h2.cuh"
+#include "heads.cuh"
 #include "rng.cuh"
 
 using namespace b200;
@@ -1777,10 +1778,20 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
         // head backward kernels produce dz3 of both nets (+ the head's own gradients and layer 3's bias gradient), ONE fused chain
         // launch produces dz2, dz1 and the remaining bias gradients, then the six weight-gradient GEMMs
         float *GA3 = ws + w.GA3, *GA2 = ws + w.GA2, *GA1 = ws + w.GA1, *GC3 = ws + w.GC3, *GC2 = ws + w.GC2, *GC1 = ws + w.GC1;
-        k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, GA3, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2),
-                                                                             g_h2_chain ? ws + w.SC + h2::SC_SG_A : nullptr);
-        k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, GC3, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2),
-                                                                             g_h2_chain ? ws + w.SC + h2::SC_SG_C : nullptr);
+        if (g_h2_chain) {
+            // streaming head backward (heads.cuh): bulk-copy fed, dz3 written as h2 words
+            static unsigned long long cfg_a = 0, cfg_c = 0;
+            CU_TRY(ensure_dynamic_smem(heads::k_head_bwd_pipe<12>, heads::HeadSmem<12>::TOTAL, cfg_a));
+            CU_TRY(ensure_dynamic_smem(heads::k_head_bwd_pipe<1>, heads::HeadSmem<1>::TOTAL, cfg_c));
+            const int tiles = (M + heads::HB2_ROWS - 1) / heads::HB2_ROWS, grid = tiles < 2 * p->num_sms ? tiles : 2 * p->num_sms;
+            heads::k_head_bwd_pipe<12><<<grid, heads::HB2_THREADS, heads::HeadSmem<12>::TOTAL, st>>>(
+                ws + w.A3, p->P(P_AW3), DMU, M, reinterpret_cast<uint32_t*>(GA3), p->G(P_AW3), p->G(P_AB3), p->G(P_AB2), ws + w.SC + h2::SC_SG_A);
+            heads::k_head_bwd_pipe<1><<<grid, heads::HB2_THREADS, heads::HeadSmem<1>::TOTAL, st>>>(
+                ws + w.C3, p->P(P_CW3), DV, M, reinterpret_cast<uint32_t*>(GC3), p->G(P_CW3), p->G(P_CB3), p->G(P_CB2), ws + w.SC + h2::SC_SG_C);
+        } else {
+            k_actor_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.A3, p->P(P_AW3), DMU, M, GA3, p->G(P_AW3), p->G(P_AB3), p->G(P_AB2), nullptr);
+            k_value_head_bwd<<<(M + HB_ROWS - 1) / HB_ROWS, HB_THREADS, 0, st>>>(ws + w.C3, p->P(P_CW3), DV, M, GC3, p->G(P_CW3), p->G(P_CB3), p->G(P_CB2), nullptr);
+        }
         g_launches += 2;
         if ((rc = launch_status("k_head_bwd")) != B200_OK) return rc;
         if ((rc = chain_backward(p, M, true, true, st))) return rc;
