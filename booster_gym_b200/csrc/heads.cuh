@@ -144,5 +144,83 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k_head_bwd_pipe(const float* _
     }
 }
 
+// forward of the heads with the same feed: OUT[m, j] = b[j] + sum_k H[m,k] W[j,k]  (V for J = 1, mu for J = 12).  One warp per row, a
+// float4 of hidden units per lane, the J partial dot products combined by a 16-value butterfly reduce-scatter (lane l ends up with output l).
+template <int J>
+__global__ void __launch_bounds__(HB2_THREADS, 2) k_head_fwd_pipe(const float* __restrict__ H, const float* __restrict__ W, const float* __restrict__ b,
+                                                                  int n, float* __restrict__ OUT) {
+    constexpr int STAGE = HB2_ROWS * 512, W_OFF = HB2_STAGES * STAGE, BAR_OFF = W_OFF + J * 512;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = (uint64_t*)(smem + BAR_OFF);
+    uint64_t* empty = full + HB2_STAGES;
+    float4* sw = (float4*)(smem + W_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const int tiles = (n + HB2_ROWS - 1) / HB2_ROWS;
+    for (int i = threadIdx.x; i < J * 32; i += HB2_THREADS) sw[i] = reinterpret_cast<const float4*>(W)[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HB2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], HB2_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == HB2_WARPS) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const uint32_t s = it % HB2_STAGES, ph = (it / HB2_STAGES) & 1;
+                h2::mbar_wait_wd(&empty[s], ph ^ 1, 960);
+                const int r0 = t * HB2_ROWS, rows = min(HB2_ROWS, n - r0);
+                mbar_expect_tx(&full[s], (uint32_t)rows * 512u);
+                bulk_load(sbase + s * STAGE, H + (size_t)r0 * 128, (uint32_t)rows * 512u, &full[s]);
+            }
+        }
+        return;
+    }
+    const float bj = lane < J ? b[lane] : 0.0f;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % HB2_STAGES, ph = (it / HB2_STAGES) & 1;
+        h2::mbar_wait_wd(&full[s], ph, 961);
+        const int r0 = t * HB2_ROWS, rows = min(HB2_ROWS, n - r0);
+        const float4* hs = reinterpret_cast<const float4*>(smem + s * STAGE);
+#pragma unroll 2
+        for (int r = warp; r < rows; r += HB2_WARPS) {
+            const float4 h = hs[r * 32 + lane];
+            if (J == 1) {
+                const float4 w4 = sw[lane];
+                float p = fmaf(h.x, w4.x, fmaf(h.y, w4.y, fmaf(h.z, w4.z, h.w * w4.w)));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+                if (lane == 0) OUT[r0 + r] = p + bj;
+            } else {
+                float p[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < J) {
+                        const float4 w4 = sw[j * 32 + lane];
+                        p[j] = fmaf(h.x, w4.x, fmaf(h.y, w4.y, fmaf(h.z, w4.z, h.w * w4.w)));
+                    } else {
+                        p[j] = 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int half = 8; half >= 1; half >>= 1) {
+                    const bool upper = (lane & half) != 0;
+#pragma unroll
+                    for (int j = 0; j < half; ++j) {
+                        const float send = upper ? p[j] : p[j + half];
+                        const float keep = upper ? p[j + half] : p[j];
+                        p[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+                    }
+                }
+                const float tot = p[0] + __shfl_xor_sync(0xffffffffu, p[0], 16);   // lane l (mod 16) holds output l
+                if (lane < J) OUT[(size_t)(r0 + r) * J + lane] = tot + bj;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+}
+
 }  // namespace heads
 }  // namespace b200

@@ -651,6 +651,7 @@ __global__ void k_old_logp(const float* __restrict__ mu, const float* __restrict
 //   rewards[time_outs] = values[time_outs] (in place); done = done | time_out;
 //   delta = r + gamma*nnt*V[t+1] - V[t];  A[t] = delta + gamma*lam*nnt*A[t+1];  returns = V + A
 // and accumulates sum / sum of squares / count of the raw advantages (double) for the normalisation of :145.
+#define GAE_CHUNK 24
 __global__ void __launch_bounds__(128) k_gae(float* __restrict__ rewards, const uint8_t* __restrict__ dones,
                                              const uint8_t* __restrict__ time_outs, const float* __restrict__ values,
                                              const float* __restrict__ last_values, float gamma, float gamma_lam, int T,
@@ -660,18 +661,18 @@ __global__ void __launch_bounds__(128) k_gae(float* __restrict__ rewards, const 
     double s = 0.0, s2 = 0.0;
     if (e < N) {
         float next_v = last_values[e], last_adv = 0.0f;
-        // the recurrence is sequential in t, its loads are not: fetch 8 time steps at once, then run them
-        for (int t1 = T; t1 > 0; t1 -= 8) {
-            float vv[8], rr[8];
-            uint8_t dd[8], oo[8];
+        // the recurrence is sequential in t, its loads are not: fetch 24 time steps (the shipped horizon) at once, then run them
+        for (int t1 = T; t1 > 0; t1 -= GAE_CHUNK) {
+            float vv[GAE_CHUNK], rr[GAE_CHUNK];
+            uint8_t dd[GAE_CHUNK], oo[GAE_CHUNK];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < GAE_CHUNK; ++k) {
                 const int t = t1 - 1 - k;
                 const size_t i = (size_t)(t >= 0 ? t : 0) * N + e;
                 vv[k] = values[i]; rr[k] = rewards[i]; dd[k] = dones[i]; oo[k] = time_outs[i];
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < GAE_CHUNK; ++k) {
                 const int t = t1 - 1 - k;
                 if (t < 0) break;
                 const size_t i = (size_t)t * N + e;
@@ -1548,6 +1549,18 @@ static int wgrad_h2(B200Ppo* p, const WgH2Operand* ops, int M, cudaStream_t st) 
     return launch_status("k_wgrad_h2");
 }
 
+// forward heads on the bulk-copy-fed streaming kernels (heads.cuh)
+template <int J>
+static int head_forward(const B200Ppo* p, const float* H, const float* W, const float* b, int n, float* out, cudaStream_t st) {
+    constexpr int SMEM = heads::HB2_STAGES * heads::HB2_ROWS * 512 + J * 512 + 64;
+    static unsigned long long configured = 0;
+    CU_TRY(ensure_dynamic_smem(heads::k_head_fwd_pipe<J>, SMEM, configured));
+    const int tiles = (n + heads::HB2_ROWS - 1) / heads::HB2_ROWS, grid = tiles < 2 * p->num_sms ? tiles : 2 * p->num_sms;
+    heads::k_head_fwd_pipe<J><<<grid, heads::HB2_THREADS, SMEM, st>>>(H, W, b, n, out);
+    g_launches += 1;
+    return launch_status("k_head_fwd_pipe");
+}
+
 static int actor_forward_tc(B200Ppo* p, int M, cudaStream_t st) {
     float* ws = p->ws;
     const Workspace& w = p->w;
@@ -1733,9 +1746,8 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
         // both nets in ONE persistent launch: 800 critic + 768 actor tiles balance over the SMs better than two launches of ~5.3
         // waves each; the actor's mu is not needed before epoch_b's loss
         if ((rc = chain_forward(p, critic_ptrs(p, M + N), actor_ptrs(p, M), st)) != B200_OK) return rc;
-        k_value_head<<<(int)(((size_t)(M + N) * 4 + 255) / 256), 256, 0, st>>>(ws + p->w.C3, p->P(P_CW3), p->P(P_CB3), M + N, ws + p->w.V);
-        k_actor_head<<<1184, 256, 0, st>>>(ws + p->w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + p->w.MU);
-        g_launches += 2;
+        if ((rc = head_forward<1>(p, ws + p->w.C3, p->P(P_CW3), p->P(P_CB3), M + N, ws + p->w.V, st)) != B200_OK) return rc;
+        if ((rc = head_forward<12>(p, ws + p->w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + p->w.MU, st)) != B200_OK) return rc;
         p->actor_fwd_done = true;
     } else if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
     k_gae<<<(N + 31) / 32, 32, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,

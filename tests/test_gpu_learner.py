@@ -224,7 +224,11 @@ def _epoch_against_oracle(t1_cfg, T, N):
             # not average out in the sums the way the reference's fp32 rounding does.  Measured on B200: <= 1.2e-4 of the
             # tensor max (actor biases, epoch 0) with mu itself at 7e-7 of scale; the fp32 reference is 1.8e-5 from
             # fp64 on the same tensors one epoch later.  Stated tolerance: 2e-4 relative (+ 3x the reference's own error).
-            judge("grad " + name, g[name].cpu().reshape(o64["grads"][name].shape), o32["grads"][name], o64["grads"][name], rel=2e-4)
+            # Round 2: the CRITIC's gradients meet the north_star's 1e-5 (measured 2e-6 .. 6e-6 of the tensor max in every mode); the
+            # actor's stay at the stated 2e-4 (measured <= 1.6e-4: DESIGN section 4 derives why a truncating accumulator cannot do better
+            # on a quantity that is a 150x-cancelling sum of mu's error / sigma).
+            judge("grad " + name, g[name].cpu().reshape(o64["grads"][name].shape), o32["grads"][name], o64["grads"][name],
+                  rel=1e-5 if name.startswith("critic.") else 2e-4)
         lrn.apply()
         sc = lrn.scalars.cpu()
         from booster_gym_b200 import _abi
@@ -232,7 +236,10 @@ def _epoch_against_oracle(t1_cfg, T, N):
         for key, nm in (("VALUE_LOSS", "value_loss"), ("ACTOR_LOSS", "actor_loss"), ("BOUND_LOSS", "bound_loss"),
                         ("ENTROPY", "entropy"), ("KL", "kl")):
             ours, f32, f64 = sc[_abi.SC[key]].item(), o32[nm], o64[nm]
-            assert abs(ours - f64) <= 1e-5 * max(abs(f64), 1e-3) + 3 * abs(f32 - f64) + 1e-9, (ep, nm, ours, f32, f64)
+            # actor_loss at epoch 0 is -mean(A_normalised * 1): O(1) terms that cancel to ~1e-17 in fp64, so its scale is the
+            # magnitude of its terms (mean |A_normalised| ~ 0.8), not of the sum
+            floor = 0.1 if nm == "actor_loss" else 1e-3
+            assert abs(ours - f64) <= 1e-5 * max(abs(f64), floor) + 3 * abs(f32 - f64) + 1e-9, (ep, nm, ours, f32, f64)
         assert abs(sc[_abi.SC["GRAD_NORM"]].item() - o64["grad_norm"]) <= 1e-4 * o64["grad_norm"], (sc[_abi.SC["GRAD_NORM"]].item(), o64["grad_norm"])
         assert abs(sc[_abi.SC["LR"]].item() - o64["lr"]) <= 1e-6 * o64["lr"], (sc[_abi.SC["LR"]].item(), o64["lr"])
         p = lrn.views()
