@@ -60,7 +60,8 @@ def config_dict(args, world):
             "mini_epochs": 20, "terrain": "plane" if args.config == 1 else "trimesh", "parallelism": f"env-sharded dp{world}",
             "l2": "working set (the learner streams ~2.2 GB of activations and gradients per epoch through a >1 GB workspace per GPU) is larger than "
                   "the 126 MB L2; no flush needed",
-            "rollout_cuda_graph": bool(args.graphs)}
+            "rollout_cuda_graph": bool(args.graphs),
+            "update_cuda_graph": bool(args.graphs) and world == 1 and os.environ.get("B200_UPDATE_GRAPH", "1") != "0"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -176,12 +177,30 @@ def b200_arm(args):
             runner.rollout(obs, priv)
         graph_launches = lib.b200_launch_count() - lc0   # kernels of this library inside one replay (the host counter only sees the capture)
 
+    # the update as a second graph (single process: with peers bound the exchange kernels take host-side sequence numbers, and the
+    # NCCL protocol interleaves collectives - both stay eager); lr / Adam step / KL rule are device-resident, so a replay IS the next update
+    upd_graph, upd_launches = None, 0
+    if args.graphs and world == 1 and os.environ.get("B200_UPDATE_GRAPH", "1") != "0":
+        runner.update(obs, priv)
+        torch.cuda.synchronize(dev)
+        upd_graph = torch.cuda.CUDAGraph()
+        lc0 = lib.b200_launch_count()
+        with torch.cuda.graph(upd_graph):
+            runner.update(obs, priv)
+        upd_launches = lib.b200_launch_count() - lc0
+
+    def update():
+        if upd_graph is not None:
+            upd_graph.replay()
+        else:
+            runner.update(obs, priv)
+
     def iteration():
         if graph is not None:
             graph.replay()
         else:
             runner.rollout(obs, priv)
-        runner.update(obs, priv)
+        update()
 
     def barrier():
         if world > 1:
@@ -211,7 +230,7 @@ def b200_arm(args):
     # ---- main measurement: states resident in HBM --------------------------------------------------------------
     l0 = lib.b200_launch_count()
     ms_total = timed(iteration, args.steps)
-    launches = lib.b200_launch_count() - l0 + (graph_launches * args.steps if graph is not None else 0)
+    launches = lib.b200_launch_count() - l0 + (graph_launches * args.steps if graph is not None else 0) + upd_launches * args.steps
     while time.perf_counter() - t_load < 1.2:
         iteration()
     torch.cuda.synchronize(dev)
@@ -221,7 +240,7 @@ def b200_arm(args):
 
     # ---- phase split (rollout only / update only), informational ----------------------------------------------------
     ms_roll = timed(lambda: (graph.replay() if graph is not None else runner.rollout(obs, priv)), max(2, args.steps)) / max(2, args.steps)
-    ms_upd = timed(lambda: runner.update(obs, priv), max(2, args.steps)) / max(2, args.steps)
+    ms_upd = timed(update, max(2, args.steps)) / max(2, args.steps)
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------
     f_host = env._fstate.cpu().pin_memory()
@@ -249,7 +268,11 @@ def b200_arm(args):
     # 1 005 312 FLOP (fwd 353 536 + bwd 651 776) and 304 B if activations stayed on chip; `traffic_model` is what this
     # implementation's launches are DESIGNED to move (every operand once, every result once), `traffic` what ncu measured.
     lib.b200_profile_gemm(1)
-    iteration()
+    if graph is not None:
+        graph.replay()
+    else:
+        runner.rollout(obs, priv)
+    runner.update(obs, priv)     # eager: the events are recorded by the library around its launches
     torch.cuda.synchronize(dev)
     h2 = os.environ.get("B200_H2", "1") != "0" and os.environ.get("B200_CHAIN", "1") == "1"
     if h2:   # default: the h2 operand format (two fp16 halves per word, tcgen05.mma kind::f16; h2.cuh, mlp_chain_h2.cuh)

@@ -67,6 +67,11 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k_head_bwd_pipe(const float* _
         }
     } else {
         const float gs = sg[0];
+        // this lane's 4 columns of every head row stay in REGISTERS: re-reading them from shared memory for every row (J LDS.128 per
+        // row and warp) made the J = 12 kernels shared-memory-bandwidth bound (52 clk of the LSU pipe per row: 18 us of 37 measured)
+        float4 wr[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) wr[j] = sw[j * 32 + lane];
         uint32_t it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
             const uint32_t s = it % HB2_STAGES, ph = (it / HB2_STAGES) & 1;
@@ -77,16 +82,14 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k_head_bwd_pipe(const float* _
 #pragma unroll 1
             for (int r = warp; r < rows; r += HB2_WARPS) {
                 const float4 h = hs[r * 32 + lane];
-                float d[J];
-#pragma unroll
-                for (int j = 0; j < J; ++j) d[j] = ds[r * J + j];
                 float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const float4 wj = sw[j * 32 + lane];
-                    g.x = fmaf(d[j], wj.x, g.x); g.y = fmaf(d[j], wj.y, g.y); g.z = fmaf(d[j], wj.z, g.z); g.w = fmaf(d[j], wj.w, g.w);
-                    acc[j].x = fmaf(d[j], h.x, acc[j].x); acc[j].y = fmaf(d[j], h.y, acc[j].y);
-                    acc[j].z = fmaf(d[j], h.z, acc[j].z); acc[j].w = fmaf(d[j], h.w, acc[j].w);
+                    const float4 wj = wr[j];
+                    const float dj = ds[r * J + j];   // (broadcast load, consumed at once: 2 x J float4 of weights / sums live in registers)
+                    g.x = fmaf(dj, wj.x, g.x); g.y = fmaf(dj, wj.y, g.y); g.z = fmaf(dj, wj.z, g.z); g.w = fmaf(dj, wj.w, g.w);
+                    acc[j].x = fmaf(dj, h.x, acc[j].x); acc[j].y = fmaf(dj, h.y, acc[j].y);
+                    acc[j].z = fmaf(dj, h.z, acc[j].z); acc[j].w = fmaf(dj, h.w, acc[j].w);
                 }
                 float4 dh;
                 dh.x = g.x * ((h.x > 0.0f) ? 1.0f : (h.x + 1.0f));
@@ -97,10 +100,7 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k_head_bwd_pipe(const float* _
                 wd.x = h2::pack(dh.x * gs); wd.y = h2::pack(dh.y * gs); wd.z = h2::pack(dh.z * gs); wd.w = h2::pack(dh.w * gs);
                 reinterpret_cast<uint4*>(DZ + (size_t)(r0 + r) * 128)[lane] = wd;
                 ap.x += dh.x; ap.y += dh.y; ap.z += dh.z; ap.w += dh.w;
-                float mine = 0.0f;
-#pragma unroll
-                for (int j = 0; j < J; ++j) mine = (lane == j) ? d[j] : mine;
-                ab += mine;
+                if (lane < J) ab += ds[r * J + lane];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -177,6 +177,9 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k_head_fwd_pipe(const float* _
         return;
     }
     const float bj = lane < J ? b[lane] : 0.0f;
+    float4 wr[J];   // this lane's 4 columns of every head row, in registers (see k_head_bwd_pipe)
+#pragma unroll
+    for (int j = 0; j < J; ++j) wr[j] = sw[j * 32 + lane];
     uint32_t it = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
         const uint32_t s = it % HB2_STAGES, ph = (it / HB2_STAGES) & 1;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k_head_fwd_pipe(const float* _
         for (int r = warp; r < rows; r += HB2_WARPS) {
             const float4 h = hs[r * 32 + lane];
             if (J == 1) {
-                const float4 w4 = sw[lane];
+                const float4 w4 = wr[0];
                 float p = fmaf(h.x, w4.x, fmaf(h.y, w4.y, fmaf(h.z, w4.z, h.w * w4.w)));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k_head_fwd_pipe(const float* _
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (j < J) {
-                        const float4 w4 = sw[j * 32 + lane];
+                        const float4 w4 = wr[j < J ? j : 0];
                         p[j] = fmaf(h.x, w4.x, fmaf(h.y, w4.y, fmaf(h.z, w4.z, h.w * w4.w)));
                     } else {
                         p[j] = 0.0f;

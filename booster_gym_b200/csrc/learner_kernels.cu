@@ -611,6 +611,41 @@ __global__ void __launch_bounds__(PF_THREADS) k_policy_fused(const PolicyFusedAr
     }
 }
 
+// Tensor-core act path (b200_policy_act for >= g_policy_tc_min_rows rows): the actor's hidden layers run on the fused forward chain
+// (k_mlp_fwd_h2), this is the head + sampling stage of k_policy_fused over the chain's h3 rows - same dot-product order, same Philox
+// keys (seed, global env, step, lane / 4), so both paths draw the same noise.  One warp per row, the head weights in registers.
+__global__ void __launch_bounds__(256) k_act_head(const float* __restrict__ H3, const PolicyFusedArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 w[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(a.W3 + j * 128) + lane);
+    const float bj = lane < 12 ? a.b3[lane] : 0.0f;
+    const float sg = lane < 12 ? expf(a.logstd[lane]) : 0.0f;
+    const uint64_t step = a.ctr ? (uint64_t)(*a.ctr) : a.step;
+    for (int row = blockIdx.x * 8 + warp; row < a.n; row += gridDim.x * 8) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(H3 + (size_t)row * 128) + lane);
+        float out = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            float s = h.x * w[j].x + h.y * w[j].y + h.z * w[j].z + h.w * w[j].w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == j) out = s + bj;
+        }
+        if (lane < 12) {
+            float act = out;
+            if (!a.deterministic) {
+                float eps;
+                if (a.eps_in) eps = a.eps_in[(size_t)row * 12 + lane];
+                else eps = rand4(rng_words(a.seed, (uint32_t)(a.env_base + row), step, RP_POLICY, lane >> 2)).n[lane & 3];
+                act = __fadd_rn(out, __fmul_rn(sg, eps));
+            }
+            a.actions[(size_t)row * 12 + lane] = act;
+            if (a.mu_out) a.mu_out[(size_t)row * 12 + lane] = out;
+        }
+    }
+}
+
 #define LOG_SQRT_2PI 0.91893853320467274178f
 
 // Normal(mu, exp(logstd)).log_prob(a).sum(-1)  (torch.distributions.Normal.log_prob, summed left to right)
@@ -1064,6 +1099,9 @@ static bool g_tc_pair = getenv("B200_TC_PAIR") ? atoi(getenv("B200_TC_PAIR")) !=
 static int g_chain_exact_actor = getenv("B200_CHAIN_DEBUG") ? atoi(getenv("B200_CHAIN_DEBUG")) : 0;   // debug: 1 = single accumulator for the 128-wide layers
 static bool g_chain_pair = getenv("B200_CHAIN_PAIR") ? atoi(getenv("B200_CHAIN_PAIR")) != 0 : false;   // chains on CTA pairs (cta_group::2)
 static bool g_chain = getenv("B200_CHAIN") ? atoi(getenv("B200_CHAIN")) != 0 : true;           // fused layer chains (mlp_chain.cuh); 0 = layer-by-layer GEMMs
+// b200_policy_act: rows from which the actor's hidden layers run on the tensor-core forward chain instead of the FP32-FMA kernel
+// (128-row tcgen05 tiles: 4096 rows are 32 CTAs of one tile each; the FMA kernel needs ~46 us at 4096 rows and doubles at 8192)
+static int g_policy_tc_min_rows = getenv("B200_POLICY_TC_MIN_ROWS") ? atoi(getenv("B200_POLICY_TC_MIN_ROWS")) : 2048;
 static bool g_h2_chain = getenv("B200_H2") ? atoi(getenv("B200_H2")) != 0 : true;   // hidden-layer GEMMs on the h2 operand format (h2.cuh, mlp_chain_h2.cuh); 0 = 3xTF32 kernels
 // epilogue warp groups of the h2 chains (1 or 2; measured equal within noise)
 // h2 chains: weight multicast in clusters of two CTAs (halves the L2 -> SM weight stream; measured: no gain, the kernels are bound by the per-k-block
@@ -1667,12 +1705,32 @@ int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* 
     constexpr int SMEM = PF_SMEM_FLOATS * (int)sizeof(float);
     CUDA_TRY(ensure_dynamic_smem(k_policy_fused, SMEM, configured));
     const bool auto_step = (step == B200_STEP_AUTO);
+    const bool reuse = (deterministic & B200_ACT_REUSE_WEIGHTS) != 0;
     PolicyFusedArgs a{};
     a.obs = obs;
     a.W0 = p->P(P_AW0); a.b0 = p->P(P_AB0); a.W1 = p->P(P_AW1); a.b1 = p->P(P_AB1); a.W2 = p->P(P_AW2); a.b2 = p->P(P_AB2);
     a.W3 = p->P(P_AW3); a.b3 = p->P(P_AB3); a.logstd = p->P(P_LOGSTD);
     a.eps_in = eps_in; a.ctr = auto_step ? p->act_ctr : nullptr; a.actions = actions; a.mu_out = mu_out;
-    a.seed = seed; a.step = step; a.n = n; a.env_base = p->cfg.env_base; a.deterministic = deterministic;
+    a.seed = seed; a.step = step; a.n = n; a.env_base = p->cfg.env_base; a.deterministic = deterministic & 1;
+    if (g_h2_chain && n >= g_policy_tc_min_rows && n <= p->cfg.num_envs) {
+        // tensor-core path: obs -> h2 words, hidden layers on the fused forward chain (the N-row buffers of b200_critic_value), head + sampling
+        float* ws = p->ws;
+        const Workspace& w = p->w;
+        k_pack_inputs<<<(int)(((size_t)n * 64 + 255) / 256), 256, 0, st>>>(obs, nullptr, n, PackOut{nullptr, ws + w.LXh, nullptr, nullptr, nullptr, nullptr, 1});
+        g_launches += 1;
+        int rc;
+        // the weight operands (B' / B'' words, pre-scaled biases) are rebuilt unless the caller vouches that the parameters have not
+        // changed since its previous call (Runner.rollout: every step but the first) - a per-call argument, so a captured graph replays it
+        if (!reuse && (rc = weight_prep(p, st)) != B200_OK) return rc;
+        ChainNetPtrs c = actor_ptrs(p, n);
+        c.Xh = ws + w.LXh; c.Xl = ws + w.LXl; c.H1 = ws + w.L1; c.H2 = ws + w.L2; c.H3 = ws + w.L3;
+        if ((rc = chain_forward(p, critic_ptrs(p, 0), c, st)) != B200_OK) return rc;
+        const int blocks = (n + 7) / 8;
+        k_act_head<<<blocks < 4 * p->num_sms ? blocks : 4 * p->num_sms, 256, 0, st>>>(ws + w.L3, a);
+        if (auto_step) k_bump<<<1, 1, 0, st>>>(p->act_ctr);
+        g_launches += auto_step ? 2 : 1;
+        return launch_status("k_act_head");
+    }
     k_policy_fused<<<(n + PF_ROWS - 1) / PF_ROWS, PF_THREADS, SMEM, st>>>(a);
     if (auto_step) k_bump<<<1, 1, 0, st>>>(p->act_ctr);
     g_launches += auto_step ? 2 : 1;
@@ -1899,6 +1957,10 @@ int b200_tc_set_h2(int mode) {
     if (mode & 0x30) g_h2_groups_fwd = ((mode >> 4) & 3) >= 2 ? 2 : 1;   // bits 4-5 / 6-7: epilogue warp groups (1 or 2) of the forward /
     if (mode & 0xC0) g_h2_groups_bwd = ((mode >> 6) & 3) >= 2 ? 2 : 1;   // backward chain
     if (mode & 0x300) g_h2_mc = ((mode >> 8) & 3) >= 2;                  // bits 8-9: 1 = every CTA streams its own weights, 2 = multicast in CTA pairs
+    if (mode & 0xC00) {   // bits 10-11: b200_policy_act 1 = always FP32-FMA, 2 = always the tensor-core chain, 3 = by row count (default)
+        const int m = (mode >> 10) & 3;
+        g_policy_tc_min_rows = m == 1 ? 0x7fffffff : (m == 2 ? 1 : (getenv("B200_POLICY_TC_MIN_ROWS") ? atoi(getenv("B200_POLICY_TC_MIN_ROWS")) : 2048));
+    }
     return B200_OK;
 }
 int b200_tc_set_chain(int enable) {

@@ -113,13 +113,16 @@ class Learner:
         self.scalars[_abi.SC["LR"]] = float(lr)
 
     # ---- kernels -------------------------------------------------------------------------------------------------------
-    def act(self, obs, actions_out, mu_out=None, eps=None, deterministic=False, step=None):
+    def act(self, obs, actions_out, mu_out=None, eps=None, deterministic=False, step=None, reuse_weights=False):
+        """reuse_weights: the caller vouches that the parameters have not changed since its previous act() call (B200_ACT_REUSE_WEIGHTS:
+        the tensor-core path of >= 2048 rows then skips rebuilding its weight operands); the default rebuilds them on every call."""
         if step is None:
             step = 0xFFFFFFFFFFFFFFFF  # B200_STEP_AUTO: device-side counter, so captured graphs draw fresh noise on replay
+        flags = (1 if deterministic else 0) | (2 if reuse_weights else 0)
         _lib.check(self._lib.b200_policy_act(self._h, obs.data_ptr(), obs.shape[0], actions_out.data_ptr(),
                                              mu_out.data_ptr() if mu_out is not None else None,
                                              eps.data_ptr() if eps is not None else None, self.seed, int(step),
-                                             1 if deterministic else 0, self._stream()), "b200_policy_act")
+                                             flags, self._stream()), "b200_policy_act")
         return actions_out
 
     def value(self, obs, priv, out=None):

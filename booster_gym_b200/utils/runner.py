@@ -192,7 +192,9 @@ class Runner:
         buf.update_data("privileged_obses", 0, privileged_obs)
         for n in range(horizon):
             act = buf["actions"][n]
-            lrn.act(obs, act)                      # mu = actor(obs); act = mu + sigma * eps, written into the buffer row
+            # mu = actor(obs); act = mu + sigma * eps, written into the buffer row (the parameters only change in update(): every
+            # step but the first may reuse the weight operands of the tensor-core act path)
+            lrn.act(obs, act, reuse_weights=n > 0)
             last = n == horizon - 1
             out = (env.obs_buf if last else buf["obses"][n + 1], env.privileged_obs_buf if last else buf["privileged_obses"][n + 1],
                    buf["rewards"][n], buf.row("dones", n))
@@ -235,6 +237,28 @@ class Runner:
                 torch.distributed.all_reduce(lrn.dstats[4:10])
             lrn.apply()
 
+    def update_graphed(self, obs, privileged_obs):
+        """the same update replayed from a CUDA graph (single process only): 20 epochs x ~17 launches with ~1-3 us of dependent-launch
+        latency each.  lr, Adam step and the KL rule live on the device, every pointer is a fixed buffer, so a replay IS the next
+        update.  With peers bound the exchange kernels carry host-side sequence numbers as arguments, and the NCCL protocol interleaves
+        collectives: both stay eager.  The first call runs eagerly on a side stream (warm-up), the second captures."""
+        if self.world_size > 1 or os.environ.get("B200_UPDATE_GRAPH", "1") == "0":
+            return self.update(obs, privileged_obs)
+        key = (obs.data_ptr(), privileged_obs.data_ptr())
+        g = getattr(self, "_update_graph", None)
+        if g is not None and self._update_graph_key == key:
+            g.replay()
+            return
+        if getattr(self, "_update_warm", None) != key:
+            self._update_warm = key                 # first sight of these buffers: a plain update (also the capture warm-up)
+            return self.update(obs, privileged_obs)
+        torch.cuda.synchronize(self.device)
+        self._update_graph = torch.cuda.CUDAGraph()
+        self._update_graph_key = key
+        with torch.cuda.graph(self._update_graph):  # recorded, not executed
+            self.update(obs, privileged_obs)
+        self._update_graph.replay()
+
     def train(self, on_iteration=None):
         """utils/runner.py:99-215.  `on_iteration(it, episode_means, episode_count, scalars)` (not in the reference surface) is
         called once per iteration with what the Recorder is fed - tools/learning_curve.py and the learning test use it."""
@@ -256,7 +280,7 @@ class Runner:
                 torch.distributed.all_reduce(delta)
                 self.env.curriculum_prob = torch.clamp(cur_before + delta, max=1.0)
             self.learner.scalars[SC["SUM_VALUE_LOSS"]:SC["EPOCHS"] + 1].zero_()
-            self.update(obs, privileged_obs)
+            (self.update_graphed if use_graph else self.update)(obs, privileged_obs)
             sc = self.learner.scalars.cpu()  # the one host sync of the iteration
             epochs = max(1.0, sc[SC["EPOCHS"]].item())
             self.learning_rate = sc[SC["LR"]].item()

@@ -261,6 +261,10 @@ enum { /* rows of the device `dstats` array (sums; cleared by b200_ppo_epoch_a) 
  * eps drawn in-kernel (Philox, keyed by seed/env/step) unless eps_in != NULL. deterministic != 0 -> act = mu (play).
  * step = B200_STEP_AUTO: the RNG step is a device-side counter incremented by every such call (CUDA-graph replayable). */
 #define B200_STEP_AUTO 0xFFFFFFFFFFFFFFFFull
+/* `deterministic` is a flag word: bit 0 = act = mu; bit 1 (B200_ACT_REUSE_WEIGHTS) = the parameters have not changed since this
+ * caller's previous b200_policy_act call, so the tensor-core path (>= 2048 rows: hidden layers on the fused tcgen05 forward chain)
+ * may reuse the weight operands it prepared then.  Without the bit every call rebuilds them (always correct). */
+#define B200_ACT_REUSE_WEIGHTS 2
 int b200_policy_act(B200Ppo* p, const float* obs, int n, float* actions, float* mu_out /*nullable*/,
                     const float* eps_in /*nullable*/, uint64_t seed, uint64_t step, int deterministic, void* stream);
 /* replaces est_value (utils/model.py:34-36) */

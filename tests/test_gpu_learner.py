@@ -72,6 +72,47 @@ def test_actor_critic_forward(t1_cfg, n):
     judge("value", v.cpu(), L.critic_value(sd, obs, priv), L.critic_value(sd64, obs.double(), priv.double()), atol=1e-6)
 
 
+def test_tensor_core_act_path_against_the_fma_kernel(t1_cfg):
+    """b200_policy_act for >= 2048 rows runs the hidden layers on the fused tcgen05 forward chain (k_pack_inputs -> k_mlp_fwd_h2 ->
+    k_act_head); below, k_policy_fused (FP32 FMA).  Both against the fp64 oracle at 1e-5, the same Philox noise on both paths, a ragged
+    last tile (2500 = 19 x 128 + 68 rows), and the B200_ACT_REUSE_WEIGHTS contract."""
+    from booster_gym_b200 import _lib
+
+    lib = _lib.load()
+    n = 2500
+    cfg, lrn, sd, L = _mk(t1_cfg, 2, 4096)
+    obs = torch.randn(n, 47, generator=torch.Generator().manual_seed(11))
+    sd64 = {k: v.double() for k, v in sd.items()}
+    ref32, ref64 = L.actor_mean(sd, obs), L.actor_mean(sd64, obs.double())
+    out = {}
+    try:
+        for name, mode in (("fma", 1 | (1 << 10)), ("tc", 1 | (2 << 10))):
+            lib.b200_tc_set_h2(mode)
+            act = torch.empty(n, 12, device="cuda")
+            mu = torch.empty(n, 12, device="cuda")
+            lrn.act(obs.cuda(), act, mu_out=mu, step=7)
+            judge("mu " + name, mu.cpu(), ref32, ref64, atol=1e-6)
+            out[name] = (act.cpu(), mu.cpu())
+        sigma = torch.exp(sd["logstd"]).reshape(1, 12)
+        eps_fma = (out["fma"][0] - out["fma"][1]) / sigma
+        eps_tc = (out["tc"][0] - out["tc"][1]) / sigma
+        assert (eps_fma - eps_tc).abs().max().item() <= 1e-4          # same draws (act - mu cancels to ~1e-7 / sigma)
+        assert 0.9 < eps_tc.std().item() < 1.1 and abs(eps_tc.mean().item()) < 0.05
+        # reuse: same parameters -> same answer without rebuilding the operands
+        mu2 = torch.empty(n, 12, device="cuda")
+        act2 = torch.empty(n, 12, device="cuda")
+        lrn.act(obs.cuda(), act2, mu_out=mu2, step=7, reuse_weights=True)
+        assert torch.equal(mu2.cpu(), out["tc"][1]) and torch.equal(act2.cpu(), out["tc"][0])
+        # changed parameters: a call without the flag sees them
+        sd_b = {k: v.clone() for k, v in sd.items()}
+        sd_b["actor.2.weight"] *= 0.5
+        lrn.load_state_dict(sd_b)
+        lrn.act(obs.cuda(), act2, mu_out=mu2, deterministic=True)
+        judge("mu after a parameter change", mu2.cpu(), L.actor_mean(sd_b, obs), L.actor_mean({k: v.double() for k, v in sd_b.items()}, obs.double()), atol=1e-6)
+    finally:
+        lib.b200_tc_set_h2(1 | (3 << 10))   # back to the default: by row count
+
+
 def test_shipped_policy_known_answer():
     """MLP known-answer from the reference's shipped actor deploy/models/T1.pt: actor(zeros) golden vector."""
     import os

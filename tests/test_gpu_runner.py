@@ -95,3 +95,42 @@ def test_rollout_storage_matches_the_reference_loop(tmp_path):
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
     assert outs[0]["dones"].any() and outs[0]["rewards"].abs().sum() > 0
+
+
+def test_graph_replay_equals_eager_update(tmp_path):
+    """Runner.update_graphed: the 20-epoch update replayed from a CUDA graph against the same update launched kernel by kernel, from the
+    same parameters / Adam state / lr / rollout storage.  (The head and bias gradients are float atomics, so two runs agree to rounding,
+    not to the bit: the difference is held to 1e-3 of the parameter change of the update.)"""
+    runner, cwd = _runner(tmp_path)
+    try:
+        lrn = runner.learner
+        obs, infos = runner.env.reset()
+        priv = infos["privileged_obs"]
+        for _ in range(2):                      # first sight of the buffers: eager; second: capture + replay
+            obs, priv = runner.rollout_graphed(obs, priv)
+            runner.update_graphed(obs, priv)
+        assert getattr(runner, "_update_graph", None) is not None
+        obs, priv = runner.rollout_graphed(obs, priv)
+        torch.cuda.synchronize()
+        snap = [t.clone() for t in (lrn.params, lrn.adam_m, lrn.adam_v, lrn.scalars, lrn.dstats, runner.buffer["rewards"])]
+
+        def restore():
+            for t, s in zip((lrn.params, lrn.adam_m, lrn.adam_v, lrn.scalars, lrn.dstats, runner.buffer["rewards"]), snap):
+                t.copy_(s)
+
+        runner.update_graphed(obs, priv)        # a replay
+        torch.cuda.synchronize()
+        a, sa = lrn.params.clone(), lrn.scalars.clone()
+        restore()
+        runner.update(obs, priv)                # eager
+        torch.cuda.synchronize()
+        b, sb = lrn.params.clone(), lrn.scalars.clone()
+        moved = (b - snap[0]).abs().max().item()
+        assert moved > 0 and torch.isfinite(a).all()
+        assert (a - b).abs().max().item() <= 1e-3 * moved, ((a - b).abs().max().item(), moved)
+        from booster_gym_b200 import _abi
+
+        assert sa[_abi.SC["ADAM_STEP"]].item() == sb[_abi.SC["ADAM_STEP"]].item() == snap[3][_abi.SC["ADAM_STEP"]].item() + runner.cfg["runner"]["mini_epochs"]
+        assert abs(sa[_abi.SC["LR"]].item() - sb[_abi.SC["LR"]].item()) <= 1e-6 * sb[_abi.SC["LR"]].item()
+    finally:
+        os.chdir(cwd)
