@@ -61,7 +61,8 @@ def config_dict(args, world):
             "l2": "working set (the learner streams ~2.2 GB of activations and gradients per epoch through a >1 GB workspace per GPU) is larger than "
                   "the 126 MB L2; no flush needed",
             "rollout_cuda_graph": bool(args.graphs),
-            "update_cuda_graph": bool(args.graphs) and world == 1 and os.environ.get("B200_UPDATE_GRAPH", "1") != "0"}
+            "update_cuda_graph": bool(args.graphs) and os.environ.get("B200_UPDATE_GRAPH", "1") != "0"
+                                 and (world == 1 or os.environ.get("B200_PEER_EXCHANGE", "1") != "0")}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -177,10 +178,10 @@ def b200_arm(args):
             runner.rollout(obs, priv)
         graph_launches = lib.b200_launch_count() - lc0   # kernels of this library inside one replay (the host counter only sees the capture)
 
-    # the update as a second graph (single process: with peers bound the exchange kernels take host-side sequence numbers, and the
-    # NCCL protocol interleaves collectives - both stay eager); lr / Adam step / KL rule are device-resident, so a replay IS the next update
+    # the update as a second graph (not with the NCCL protocol, whose collectives are issued from Python between the kernels); lr / Adam
+    # step / KL rule / peer-exchange sequence numbers are device-resident, so a replay IS the next update
     upd_graph, upd_launches = None, 0
-    if args.graphs and world == 1 and os.environ.get("B200_UPDATE_GRAPH", "1") != "0":
+    if args.graphs and (world == 1 or lrn.peers_bound) and os.environ.get("B200_UPDATE_GRAPH", "1") != "0":
         runner.update(obs, priv)
         torch.cuda.synchronize(dev)
         upd_graph = torch.cuda.CUDAGraph()

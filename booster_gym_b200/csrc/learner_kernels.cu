@@ -120,8 +120,7 @@ struct PeerX {
 struct B200Ppo {
     PeerX px;
     int peers;                    // 1 once b200_ppo_bind_peers succeeded
-    unsigned int seq_grad, seq_stat;
-    unsigned int* xch_counter;    // device: block counter of the post kernels
+    unsigned int* xch_counter;    // device [4]: block counter of the post kernels, gradient / moment exchange sequence numbers
     B200PpoConfig cfg;
     int device;
     float *params, *grads, *adam_m, *adam_v, *scalars;
@@ -890,8 +889,12 @@ __device__ __forceinline__ void xch_wait(const PeerX& x, int channel, unsigned s
 }
 
 // gradients + loss sums -> my slot; the last block to finish raises the flags
+// The sequence numbers live in device memory (counter[1] = gradient exchanges, counter[2] = moment exchanges done so far), not in kernel
+// arguments: a CUDA graph of the update replays with the arguments it was captured with, and the protocol must keep counting.
 __global__ void __launch_bounds__(256) k_xchg_post_grads(const PeerX x, const float* __restrict__ grads, const double* __restrict__ dstats,
-                                                         int parity, unsigned seq, unsigned* __restrict__ counter) {
+                                                         unsigned* __restrict__ counter) {
+    const unsigned seq = counter[1] + 1u;     // (written only by the last block, after every block has read it: see below)
+    const int parity = (int)(seq & 1u);
     float* slot = xch_slot(x, x.rank, parity);
     const float4* g4 = reinterpret_cast<const float4*>(grads);
     float4* s4 = reinterpret_cast<float4*>(slot);
@@ -900,17 +903,20 @@ __global__ void __launch_bounds__(256) k_xchg_post_grads(const PeerX x, const fl
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(counter, 1u);
+        const unsigned done = atomicAdd(counter, 1u);   // (every block read counter[1] before its arrival here)
         if (done == gridDim.x - 1) {
-            *counter = 0u;
+            counter[0] = 0u;
+            counter[1] = seq;
             __threadfence_system();
             xch_raise(x, 0, seq);
         }
     }
 }
 // all-reduce (sum) of the gradient and the loss sums over the peers' slots, fused with the gradient norm of clip_grad_norm_
-__global__ void __launch_bounds__(256) k_xchg_reduce_grads(const PeerX x, float* __restrict__ grads, double* __restrict__ dstats, int parity,
-                                                           unsigned seq, float inv_world) {
+__global__ void __launch_bounds__(256) k_xchg_reduce_grads(const PeerX x, float* __restrict__ grads, double* __restrict__ dstats,
+                                                           const unsigned* __restrict__ counter, float inv_world) {
+    const unsigned seq = counter[1];          // the post kernel before this launch (same stream) has finished
+    const int parity = (int)(seq & 1u);
     xch_wait(x, 0, seq);
     float4* g4 = reinterpret_cast<float4*>(grads);
     float s = 0.0f;
@@ -941,14 +947,18 @@ __global__ void __launch_bounds__(256) k_xchg_reduce_grads(const PeerX x, float*
     }
 }
 // advantage moments (sum, sum of squares, count) of this rank -> my slot, flags raised
-__global__ void k_xchg_post_stats(const PeerX x, const double* __restrict__ dstats, int parity, unsigned seq) {
+__global__ void k_xchg_post_stats(const PeerX x, const double* __restrict__ dstats, unsigned* __restrict__ counter) {
+    const unsigned seq = counter[2] + 1u;
+    const int parity = (int)(seq & 1u);
     double* d = reinterpret_cast<double*>(xch_slot(x, x.rank, parity) + NPARAMS_PADDED + 16);
     if (threadIdx.x < 4) d[threadIdx.x] = dstats[threadIdx.x];
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) xch_raise(x, 1, seq);
+    if (threadIdx.x == 0) { counter[2] = seq; xch_raise(x, 1, seq); }   // (single block: every thread read counter[2] before the barrier)
 }
-__global__ void k_xchg_reduce_stats(const PeerX x, double* __restrict__ dstats, int parity, unsigned seq) {
+__global__ void k_xchg_reduce_stats(const PeerX x, double* __restrict__ dstats, const unsigned* __restrict__ counter) {
+    const unsigned seq = counter[2];
+    const int parity = (int)(seq & 1u);
     xch_wait(x, 1, seq);
     if (threadIdx.x < 4) {
         double t = 0.0;
@@ -1676,12 +1686,11 @@ int b200_ppo_create(const B200PpoConfig* cfg, float* params, float* grads, float
     p->num_sms = 148;
     cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
     p->peers = 0;
-    p->seq_grad = p->seq_stat = 0;
     p->xch_counter = nullptr;
     cudaError_t ce = cudaMalloc(&p->act_ctr, sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(p->act_ctr, 0, sizeof(unsigned long long));
-    if (ce == cudaSuccess) ce = cudaMalloc(&p->xch_counter, sizeof(unsigned int));
-    if (ce == cudaSuccess) ce = cudaMemset(p->xch_counter, 0, sizeof(unsigned int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->xch_counter, 4 * sizeof(unsigned int));
+    if (ce == cudaSuccess) ce = cudaMemset(p->xch_counter, 0, 4 * sizeof(unsigned int));
     if (ce != cudaSuccess) { delete p; return set_cuda_error(ce, "b200_ppo_create: counter allocation"); }
     *out = p;
     return B200_OK;
@@ -1812,8 +1821,7 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
     g_launches += 3;  // memset, k_pack_inputs, k_gae
     if (p->peers) {   // this rank's advantage moments -> peers (summed in epoch_b, behind the actor forward)
-        p->seq_stat += 1;
-        k_xchg_post_stats<<<1, 32, 0, st>>>(p->px, p->dstats, (int)(p->seq_stat & 1u), p->seq_stat);
+        k_xchg_post_stats<<<1, 32, 0, st>>>(p->px, p->dstats, p->xch_counter);
         g_launches += 1;
     }
     return launch_status("k_gae");
@@ -1834,7 +1842,7 @@ int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, cons
     p->actor_fwd_done = false;
     CUDA_TRY(cudaMemsetAsync(p->grads, 0, NPARAMS_PADDED * sizeof(float), st));
     if (p->peers) {   // global advantage normalisation (utils/runner.py:145 over all ranks' samples)
-        k_xchg_reduce_stats<<<1, 32, 0, st>>>(p->px, p->dstats, (int)(p->seq_stat & 1u), p->seq_stat);
+        k_xchg_reduce_stats<<<1, 32, 0, st>>>(p->px, p->dstats, p->xch_counter);
         g_launches += 1;
     }
     k_loss<<<(M + LOSS_BLOCK - 1) / LOSS_BLOCK, LOSS_BLOCK, 0, st>>>(ws + w.V, ws + w.RET, ws + w.ADV, MU, actions, old_mu, old_logp,
@@ -1914,10 +1922,8 @@ int b200_ppo_apply(B200Ppo* p, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const float inv_world = 1.0f / (float)p->cfg.world_size;
     if (p->peers) {   // sum-all-reduce of the gradient + loss sums over NVLink peer memory, fused with the gradient norm
-        p->seq_grad += 1;
-        const int parity = (int)(p->seq_grad & 1u);
-        k_xchg_post_grads<<<64, 256, 0, st>>>(p->px, p->grads, p->dstats, parity, p->seq_grad, p->xch_counter);
-        k_xchg_reduce_grads<<<96, 256, 0, st>>>(p->px, p->grads, p->dstats, parity, p->seq_grad, inv_world);
+        k_xchg_post_grads<<<64, 256, 0, st>>>(p->px, p->grads, p->dstats, p->xch_counter);
+        k_xchg_reduce_grads<<<96, 256, 0, st>>>(p->px, p->grads, p->dstats, p->xch_counter, inv_world);
         g_launches += 1;
     } else {
         k_grad_sumsq<<<148, 256, 0, st>>>(p->grads, NPARAMS_PADDED, inv_world, p->dstats);
@@ -1944,7 +1950,7 @@ int b200_ppo_bind_peers(B200Ppo* p, const unsigned long long* buffer_ptrs, int r
     p->px.rank = rank;
     p->px.world = world;
     p->peers = 1;
-    p->seq_grad = p->seq_stat = 0;
+    CUDA_TRY(cudaMemset(p->xch_counter, 0, 4 * sizeof(unsigned int)));   // the flags of a fresh peer buffer are zero: sequence numbers restart
     return B200_OK;
 }
 int b200_tc_set_pair(int enable) {

@@ -238,11 +238,11 @@ class Runner:
             lrn.apply()
 
     def update_graphed(self, obs, privileged_obs):
-        """the same update replayed from a CUDA graph (single process only): 20 epochs x ~17 launches with ~1-3 us of dependent-launch
-        latency each.  lr, Adam step and the KL rule live on the device, every pointer is a fixed buffer, so a replay IS the next
-        update.  With peers bound the exchange kernels carry host-side sequence numbers as arguments, and the NCCL protocol interleaves
-        collectives: both stay eager.  The first call runs eagerly on a side stream (warm-up), the second captures."""
-        if self.world_size > 1 or os.environ.get("B200_UPDATE_GRAPH", "1") == "0":
+        """the same update replayed from a CUDA graph: 20 epochs x ~17 launches with ~1-3 us of dependent-launch latency each.  lr,
+        Adam step, the KL rule and (multi-GPU, peer-memory exchange) the exchange sequence numbers live on the device, every pointer
+        is a fixed buffer, so a replay IS the next update.  Only the NCCL protocol (B200_PEER_EXCHANGE=0), which interleaves
+        collectives issued from Python, stays eager.  The first call runs eagerly (warm-up), the second captures."""
+        if (self.world_size > 1 and not self.learner.peers_bound) or os.environ.get("B200_UPDATE_GRAPH", "1") == "0":
             return self.update(obs, privileged_obs)
         key = (obs.data_ptr(), privileged_obs.data_ptr())
         g = getattr(self, "_update_graph", None)
