@@ -705,23 +705,30 @@ __global__ void __launch_bounds__(128) k_gae(float* __restrict__ rewards, const 
                 const size_t i = (size_t)(t >= 0 ? t : 0) * N + e;
                 vv[k] = values[i]; rr[k] = rewards[i]; dd[k] = dones[i]; oo[k] = time_outs[i];
             }
+            // straight-line recurrence (no early exit: the steps of a short last chunk are predicated off), so that all 4 x 24 loads
+            // above are issued before the first use - with a `break` per step the compiler sank them next to their uses: 24
+            // dependent memory round trips, measured 15 us for 2 MB
 #pragma unroll
             for (int k = 0; k < GAE_CHUNK; ++k) {
                 const int t = t1 - 1 - k;
-                if (t < 0) break;
-                const size_t i = (size_t)t * N + e;
+                const bool live = t >= 0;
+                const size_t i = (size_t)(live ? t : 0) * N + e;
                 const float v = vv[k];
                 const bool to = oo[k] != 0;
                 float r = rr[k];
-                if (to) { r = v; rewards[i] = v; }
+                if (to) r = v;
+                if (live && to) rewards[i] = v;
                 const float nnt = (dd[k] != 0 || to) ? 0.0f : 1.0f;
                 const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nnt), next_v)), v);
-                last_adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last_adv));
-                adv[i] = last_adv;
-                ret[i] = __fadd_rn(v, last_adv);
-                s += (double)last_adv;
-                s2 += (double)last_adv * (double)last_adv;
-                next_v = v;
+                const float a_new = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last_adv));
+                if (live) {
+                    last_adv = a_new;
+                    adv[i] = a_new;
+                    ret[i] = __fadd_rn(v, a_new);
+                    s += (double)a_new;
+                    s2 += (double)a_new * (double)a_new;
+                    next_v = v;
+                }
             }
         }
     }
@@ -770,13 +777,24 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
     float red[LOSS_NRED];
 #pragma unroll
     for (int i = 0; i < LOSS_NRED; ++i) red[i] = 0.0f;
+    // per-action constants of the two distributions: the same for every sample, so 12 threads of the block evaluate them once (the
+    // exp / log pairs were ~40 % of this kernel's instructions when every thread computed them for itself); same expressions, same bits
+    __shared__ float c_sg[12], c_ls[12], c_sgo[12], c_klc[12];
+    if (threadIdx.x < 12) {
+        const float sgj = expf(logstd[threadIdx.x]), sgo = expf(scalars[B200_SC_OLD_LOGSTD + threadIdx.x]);
+        c_sg[threadIdx.x] = sgj;
+        c_ls[threadIdx.x] = logf(sgj);
+        c_sgo[threadIdx.x] = sgo;
+        c_klc[threadIdx.x] = logf(sgj / sgo);
+    }
+    __syncthreads();
     if (m < M) {
         float sg[12], ls[12], sg_old[12], a[12], u[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
-            sg[j] = expf(logstd[j]);
-            ls[j] = logf(sg[j]);
-            sg_old[j] = expf(scalars[B200_SC_OLD_LOGSTD + j]);
+            sg[j] = c_sg[j];
+            ls[j] = c_ls[j];
+            sg_old[j] = c_sgo[j];
             a[j] = actions[(size_t)m * 12 + j];
             u[j] = mu[(size_t)m * 12 + j];
         }
@@ -812,7 +830,7 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
             bsum += up * up + dn * dn;
             ent += 0.5f + LOG_SQRT_2PI + ls[j];
             const float dm = u[j] - old_mu[(size_t)m * 12 + j];
-            kl += logf(sg[j] / sg_old[j]) + 0.5f * (sg_old[j] * sg_old[j] + dm * dm) / var - 0.5f;
+            kl += c_klc[j] + 0.5f * (sg_old[j] * sg_old[j] + dm * dm) / var - 0.5f;
             const float dmu_j = dlp * d / var + bscale * (up + dn);
             dMU[(size_t)m * 12 + j] = dmu_j;
             mx_mu = fmaxf(mx_mu, fabsf(dmu_j));
