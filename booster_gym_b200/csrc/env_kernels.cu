@@ -5,6 +5,7 @@
 // what makes the masks (feet_contact, reset, dof_pos_limits counts) bit-exact.  These passes are HBM-bound.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -78,6 +79,75 @@ k_post(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant_
         }
     }
     if (PHASE != 1) store_obs_rows(sbuf, obs_l, priv_l, e0, v.n, obs, priv);
+}
+
+// The whole post-physics step with one env on TWO warps (the default without the command curriculum).  k_post<0> runs ~12 000
+// dependent instructions per env on one warp per SM: it is bound by instruction latency and fetch (ncu: 8.5 stall cycles per issue,
+// nothing to overlap them with), not by memory.  The reward terms (R) and the reset + teleport + command resampling + observations
+// (T) of an env are independent once part A (derived state, feet, termination) is done and the reward snapshot sits in registers
+// (t1_env.cuh), so warp 0 runs A, snapshot, R and warp 1 runs [reset], T of the same 32 envs at the same time.  Every quantity is
+// still computed by exactly one thread with the same instructions: results are bit-identical to k_post<0> (tests/test_gpu_env_post.py).
+#define PAIR_ENVS 32
+__global__ void __launch_bounds__(2 * PAIR_ENVS)
+k_post_pair(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_constant__ B200T1Config c, TerrainView terr,
+            const long long* __restrict__ ctr, int noise_on, float* __restrict__ obs, float* __restrict__ priv,
+            float* __restrict__ rew, uint8_t* __restrict__ done, float* __restrict__ rew_terms, long long* flags, double* stats) {
+    __shared__ float sbuf[PAIR_ENVS * POST_ROW];
+    __shared__ int s_reset[PAIR_ENVS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e0 = blockIdx.x * PAIR_ENVS;
+    const int e = e0 + lane;
+    const long long step = ctr[0], common_step = ctr[1];
+    const bool live = e < v.n;
+    PostA a;
+    a.h_base = 0.0f; a.finite = true; a.reset = false; a.time_out = false;
+    RewardSnap snap;
+    if (warp == 0 && live) {
+        a = env_post_a(v, e, m, c, terr, common_step, (uint64_t)step);
+        reward_snapshot(v, e, snap);
+        s_reset[lane] = a.reset ? 1 : 0;
+    }
+    __syncthreads();   // part A's state (global) and the reset flags are visible to warp 1
+    if (warp == 0) {
+        if (live) {
+            const float r = env_post_rewards(v, e, c, snap, a.h_base, a.finite, rew_terms);
+            rew[e] = r;
+            done[e] = (uint8_t)(a.reset ? 1 : 0);
+            if (a.reset) {
+                flags[step & 1] = 1;  // benign race: every writer stores 1
+                // device episode statistics (utils/recorder.py:36-62): flush this episode's sums
+                float* f = v.f;
+                int32_t* is = v.is;
+                const int n = v.n;
+                for (int k = 0; k < 1 + c.n_rew; ++k) {
+                    atomicAdd(&stats[k], (double)FS(F_episode_sums + k));
+                    FS(F_episode_sums + k) = 0.0f;
+                }
+                atomicAdd(&stats[1 + c.n_rew], (double)IS(I_episode_steps));
+                atomicAdd(&stats[2 + c.n_rew], 1.0);
+                IS(I_episode_steps) = 0;
+            }
+        }
+    } else if (live) {
+        float obs_l[B200_NOBS], priv_l[B200_NPRIV];
+        if (s_reset[lane]) env_reset_one(v, e, c, terr, (uint64_t)step);
+        env_post_tail(v, e, m, c, terr, (uint64_t)step, noise_on, obs_l, priv_l);
+#pragma unroll
+        for (int i = 0; i < B200_NOBS; ++i) sbuf[lane * POST_ROW + i] = obs_l[i];
+#pragma unroll
+        for (int i = 0; i < B200_NPRIV; ++i) sbuf[lane * POST_ROW + B200_NOBS + i] = priv_l[i];
+    }
+    __syncthreads();
+    // coalesced write-out of the [N,47] / [N,14] row-major API tensors
+    const int cnt = min(PAIR_ENVS, v.n - e0), t = threadIdx.x;
+    for (int idx = t; idx < cnt * B200_NOBS; idx += 2 * PAIR_ENVS) {
+        const int el = idx / B200_NOBS, i = idx - el * B200_NOBS;
+        obs[(size_t)e0 * B200_NOBS + idx] = sbuf[el * POST_ROW + i];
+    }
+    for (int idx = t; idx < cnt * B200_NPRIV; idx += 2 * PAIR_ENVS) {
+        const int el = idx / B200_NPRIV, i = idx - el * B200_NPRIV;
+        priv[(size_t)e0 * B200_NPRIV + idx] = sbuf[el * POST_ROW + B200_NOBS + i];
+    }
 }
 
 // envs/t1.py:404-413 for the whole grid + the running sums the draws of :416 use (one block, one thread per cell)
@@ -281,6 +351,7 @@ int b200_t1_physics(B200T1Handle* h, const float* actions, int n_substeps, int a
     return launch_physics(h, actions, n_substeps, apply_pd, qacc_out, -1, 0, st);
 }
 
+static bool g_post_pair = getenv("B200_POST_PAIR") ? atoi(getenv("B200_POST_PAIR")) != 0 : true;   // 0: k_post<0> (one warp per 32 envs)
 static int launch_post(B200T1Handle* h, float* obs, float* priv, float* rew, uint8_t* done, uint8_t* time_out,
                        float* rew_terms, int noise_on, cudaStream_t st) {
     const int grid = (h->num_envs + POST_BLOCK - 1) / POST_BLOCK;
@@ -291,6 +362,9 @@ static int launch_post(B200T1Handle* h, float* obs, float* priv, float* rew, uin
         k_post<2><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done,
                                                rew_terms, h->ctr_dev + 2, h->stats_dev);
         g_launches += 1;
+    } else if (g_post_pair) {
+        k_post_pair<<<(h->num_envs + PAIR_ENVS - 1) / PAIR_ENVS, 2 * PAIR_ENVS, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on,
+                                                                                         obs, priv, rew, done, rew_terms, h->ctr_dev + 2, h->stats_dev);
     } else {
         k_post<0><<<grid, POST_BLOCK, 0, st>>>(make_view(h), h->model, h->cfg, make_terrain(h), h->ctr_dev, noise_on, obs, priv, rew, done,
                                                rew_terms, h->ctr_dev + 2, h->stats_dev);

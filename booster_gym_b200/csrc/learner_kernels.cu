@@ -789,14 +789,26 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
     }
     __syncthreads();
     if (m < M) {
-        float sg[12], ls[12], sg_old[12], a[12], u[12];
+        float sg[12], ls[12], sg_old[12], a[12], u[12], uo[12];
+        {
+            // the three 48-byte rows of this sample as 3 x 3 float4 loads issued together (the old_mu reads used to sit inside the loop
+            // below, one dependent memory round trip per action behind the division calls)
+            const float4* a4 = reinterpret_cast<const float4*>(actions + (size_t)m * 12);
+            const float4* u4 = reinterpret_cast<const float4*>(mu + (size_t)m * 12);
+            const float4* o4 = reinterpret_cast<const float4*>(old_mu + (size_t)m * 12);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float4 x = a4[q], y = u4[q], z = o4[q];
+                a[4 * q] = x.x; a[4 * q + 1] = x.y; a[4 * q + 2] = x.z; a[4 * q + 3] = x.w;
+                u[4 * q] = y.x; u[4 * q + 1] = y.y; u[4 * q + 2] = y.z; u[4 * q + 3] = y.w;
+                uo[4 * q] = z.x; uo[4 * q + 1] = z.y; uo[4 * q + 2] = z.z; uo[4 * q + 3] = z.w;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
             sg[j] = c_sg[j];
             ls[j] = c_ls[j];
             sg_old[j] = c_sgo[j];
-            a[j] = actions[(size_t)m * 12 + j];
-            u[j] = mu[(size_t)m * 12 + j];
         }
         // value loss
         const float v = V[m], rt = ret[m];
@@ -820,7 +832,7 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
         else dr = -0.5f * A;
         const float dlp = dr * ratio * invM;
         // bound loss, entropy, kl, gradients
-        float bsum = 0.0f, ent = 0.0f, kl = 0.0f;
+        float bsum = 0.0f, ent = 0.0f, kl = 0.0f, dmu[12];
         const float bscale = bound_coef * 2.0f / ((float)M * 12.0f);
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
@@ -829,13 +841,16 @@ __global__ void __launch_bounds__(LOSS_BLOCK) k_loss(const float* __restrict__ V
             const float up = fmaxf(u[j] - 1.0f, 0.0f), dn = fminf(u[j] + 1.0f, 0.0f);
             bsum += up * up + dn * dn;
             ent += 0.5f + LOG_SQRT_2PI + ls[j];
-            const float dm = u[j] - old_mu[(size_t)m * 12 + j];
+            const float dm = u[j] - uo[j];
             kl += c_klc[j] + 0.5f * (sg_old[j] * sg_old[j] + dm * dm) / var - 0.5f;
             const float dmu_j = dlp * d / var + bscale * (up + dn);
-            dMU[(size_t)m * 12 + j] = dmu_j;
+            dmu[j] = dmu_j;
             mx_mu = fmaxf(mx_mu, fabsf(dmu_j));
             red[6 + j] = dlp * (d * d / var - 1.0f);
         }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            reinterpret_cast<float4*>(dMU + (size_t)m * 12)[q] = make_float4(dmu[4 * q], dmu[4 * q + 1], dmu[4 * q + 2], dmu[4 * q + 3]);
         red[2] = bsum;
         red[3] = ent;
         red[4] = kl;
@@ -1848,6 +1863,8 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
 int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, const float* old_logp, void* stream) {
     NEED_PPO(p);
     if (!actions || !old_mu || !old_logp) return set_error(B200_ERR_ARG, "b200_ppo_epoch_b: null pointer");
+    if ((reinterpret_cast<uintptr_t>(actions) & 15) || (reinterpret_cast<uintptr_t>(old_mu) & 15))
+        return set_error(B200_ERR_ARG, "b200_ppo_epoch_b: actions / old_mu must be 16-byte aligned (rows of 12 floats are read as float4)");
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     const Workspace& w = p->w;

@@ -651,17 +651,21 @@ struct StepOut {
 // PHASE 0 = the whole step.  With the command curriculum the resampling envs draw from a grid that ALL of this step's resets
 // have updated first (:305 before :488), a dependency across envs: PHASE 1 stops after the resets (:460-486), the grid is
 // updated (k_curriculum_apply), PHASE 2 finishes the step (:487-495).  Nothing but the env's state crosses the cut.
-template <typename Model, int PHASE = 0>
-B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr,
-                                 int64_t common_step, uint64_t step, int noise_on, float* obs, float* priv,
-                                 float* rew_terms /* [n_rew][n] or null */) {
+// The step in four parts, so that the device kernel can run independent parts of ONE env on different warps (k_post_pair,
+// env_kernels.cu): A = derived state, feet, counters, kicks / pushes, termination (:463-478,499-527,551-558); the reward snapshot;
+// R = the reward terms and episode sums (:560-572); [reset :485-486]; T = teleport, command resampling, observations, last_* (:487-495).
+// R reads only the snapshot (registers) and the episode sums, which neither the reset nor T touches.
+struct PostA {
+    float h_base;
+    bool finite, reset, time_out;
+};
+template <typename Model>
+B200_HD PostA env_post_a(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr, int64_t common_step,
+                         uint64_t step) {
     float* f = v.f;
     int32_t* is = v.is;
     const int n = v.n;
     const uint32_t ge = (uint32_t)(v.env_base + e);
-    StepOut o;
-    o.rew = 0.0f; o.done = 0; o.time_out = 0;
-    if (PHASE != 2) {
     // :463-473
     float q[4] = {FS(F_root_states + 3), FS(F_root_states + 4), FS(F_root_states + 5), FS(F_root_states + 6)};
     {
@@ -714,23 +718,32 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
         }
     }
     // _check_termination :551-558
-    const float h_base = terr(FS(F_root_states + 0), FS(F_root_states + 1));
+    PostA a;
+    a.h_base = terr(FS(F_root_states + 0), FS(F_root_states + 1));
     float vsq = 0.0f;
 #pragma unroll
     for (int r = 0; r < 6; ++r) { const float t = FS(F_root_states + 7 + r); vsq += t * t; }
-    bool finite = (vsq == vsq) && (fabsf(vsq) <= 3.0e38f) && (FS(F_root_states + 2) == FS(F_root_states + 2));
+    a.finite = (vsq == vsq) && (fabsf(vsq) <= 3.0e38f) && (FS(F_root_states + 2) == FS(F_root_states + 2));
     const int contact_mask = IS(I_contact_mask) | IS(I_contact_mask + 1);  // bit b: |contact_forces[b]| > 1 (:553)
-    bool reset = ((contact_mask & c.termination_body_mask) != 0) || (vsq > c.terminate_vel) || (FS(F_root_states + 2) - h_base < c.terminate_height);
-    if (!finite) { reset = true; IS(I_nan_resets) += 1; }  // a diverged env is reset, not propagated
+    bool reset = ((contact_mask & c.termination_body_mask) != 0) || (vsq > c.terminate_vel) || (FS(F_root_states + 2) - a.h_base < c.terminate_height);
+    if (!a.finite) { reset = true; IS(I_nan_resets) += 1; }  // a diverged env is reset, not propagated
     bool time_out = ep_len > c.max_episode_length;
     reset = reset || time_out;
     time_out = time_out || (ep_len == IS(I_cmd_resample_time));
     IS(I_reset_buf) = reset ? 1 : 0;
     IS(I_time_out_buf) = time_out ? 1 : 0;
-    // _compute_reward :560-572
+    a.reset = reset;
+    a.time_out = time_out;
+    return a;
+}
+
+// _compute_reward :560-572 from the snapshot; returns the step's reward
+B200_HD float env_post_rewards(const EnvView& v, int e, const B200T1Config& c, const RewardSnap& snap, float h_base, bool finite,
+                               float* rew_terms /* [n_rew][n] or null */) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
     float rew = 0.0f;
-    RewardSnap snap;
-    reward_snapshot(v, e, snap);
     // the per-term episode sums are read 4 terms ahead: a load inside the rolled loop stalled every iteration for a full memory
     // round trip (17 % of k_post's stall samples sat on the one FADD that consumed it)
     const int nr = c.n_rew;
@@ -748,13 +761,16 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     if (c.only_positive_rewards) rew = fmaxf(rew, 0.0f);
     FS(F_episode_sums + 0) += rew;
     IS(I_episode_steps) += 1;
-    // :485-488
-    if (reset) env_reset_one(v, e, c, terr, step);
-    o.rew = rew;
-    o.done = reset ? 1 : 0;
-    o.time_out = time_out ? 1 : 0;
-    if (PHASE == 1) return o;
-    }
+    return rew;
+}
+
+// :487-495: teleport, command resampling, observations, last_* bookkeeping
+template <typename Model>
+B200_HD void env_post_tail(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr, uint64_t step,
+                           int noise_on, float* obs, float* priv) {
+    float* f = v.f;
+    int32_t* is = v.is;
+    const int n = v.n;
     env_teleport(v, e, m, c, terr);
     if (IS(I_episode_length_buf) == IS(I_cmd_resample_time)) env_resample_command(v, e, c, step);
     // :490
@@ -764,6 +780,27 @@ B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const 
     for (int j = 0; j < 12; ++j) { FS(F_last_actions + j) = FS(F_actions + j); FS(F_last_dof_vel + j) = FS(F_dof_vel + j); }
 #pragma unroll
     for (int j = 0; j < 6; ++j) { FS(F_last_root_vel + j) = FS(F_root_states + 7 + j); FS(F_last_feet_pos + j) = FS(F_feet_pos + j); }
+}
+
+template <typename Model, int PHASE = 0>
+B200_HD StepOut env_post_physics(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr,
+                                 int64_t common_step, uint64_t step, int noise_on, float* obs, float* priv,
+                                 float* rew_terms /* [n_rew][n] or null */) {
+    StepOut o;
+    o.rew = 0.0f; o.done = 0; o.time_out = 0;
+    if (PHASE != 2) {
+        const PostA a = env_post_a(v, e, m, c, terr, common_step, step);
+        RewardSnap snap;
+        reward_snapshot(v, e, snap);
+        const float rew = env_post_rewards(v, e, c, snap, a.h_base, a.finite, rew_terms);
+        // :485-488
+        if (a.reset) env_reset_one(v, e, c, terr, step);
+        o.rew = rew;
+        o.done = a.reset ? 1 : 0;
+        o.time_out = a.time_out ? 1 : 0;
+        if (PHASE == 1) return o;
+    }
+    env_post_tail(v, e, m, c, terr, step, noise_on, obs, priv);
     return o;
 }
 
