@@ -103,11 +103,14 @@ k_post_pair(EnvView v, const __grid_constant__ B200T1ModelF m, const __grid_cons
     a.h_base = 0.0f; a.finite = true; a.reset = false; a.time_out = false;
     RewardSnap snap;
     if (warp == 0 && live) {
-        a = env_post_a(v, e, m, c, terr, common_step, (uint64_t)step);
-        reward_snapshot(v, e, snap);
+        a = env_post_a<B200T1ModelF, 1>(v, e, m, c, terr, common_step, (uint64_t)step);   // (left foot; the right one on warp 1)
         s_reset[lane] = a.reset ? 1 : 0;
+    } else if (live) {
+        env_refresh_feet<B200T1ModelF, 2>(v, e, m, terr);   // reads the physics step's foot pose only: independent of part A
     }
-    __syncthreads();   // part A's state (global) and the reset flags are visible to warp 1
+    __syncthreads();   // part A's state (global) and the reset flags are visible to both warps
+    if (warp == 0 && live) reward_snapshot(v, e, snap);
+    __syncthreads();   // ... and the snapshot is taken before warp 1 starts overwriting what it reads
     if (warp == 0) {
         if (live) {
             const float r = env_post_rewards(v, e, c, snap, a.h_base, a.finite, rew_terms);

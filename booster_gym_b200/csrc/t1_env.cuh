@@ -283,13 +283,15 @@ __device__ __forceinline__ void env_physics_pair(const EnvView& v, int e, bool v
 #endif  // __CUDACC__
 
 // ---- envs/t1.py:529-549 ------------------------------------------------------------------------------------------
-template <typename Model>
+// FEET: bit k set = refresh foot k (the two feet are independent: k_post_pair refreshes one per warp)
+template <typename Model, int FEET = 3>
 B200_HD void env_refresh_feet(const EnvView& v, int e, const Model& m, const TerrainView& terr) {
     float* f = v.f;
     int32_t* is = v.is;
     const int n = v.n;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
+        if (!((FEET >> k) & 1)) continue;
         float q[4], p[3];
 #pragma unroll
         for (int r = 0; r < 4; ++r) q[r] = FS(F_feet_quat + 4 * k + r);
@@ -659,7 +661,7 @@ struct PostA {
     float h_base;
     bool finite, reset, time_out;
 };
-template <typename Model>
+template <typename Model, int FEET = 3>
 B200_HD PostA env_post_a(const EnvView& v, int e, const Model& m, const B200T1Config& c, const TerrainView& terr, int64_t common_step,
                          uint64_t step) {
     float* f = v.f;
@@ -686,7 +688,7 @@ B200_HD PostA env_post_a(const EnvView& v, int e, const Model& m, const B200T1Co
             FS(F_filtered_ang_vel + r) = ba[r] * w + FS(F_filtered_ang_vel + r) * w1;
         }
     }
-    env_refresh_feet(v, e, m, terr);  // :474
+    env_refresh_feet<Model, FEET>(v, e, m, terr);  // :474
     // :476-478
     const int ep_len = IS(I_episode_length_buf) + 1;
     IS(I_episode_length_buf) = ep_len;
