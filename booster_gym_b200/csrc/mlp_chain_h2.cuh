@@ -89,6 +89,11 @@ template <int MC> __device__ __forceinline__ void load_rows(const CUtensorMap* m
     if (MC) tma_load_2d_mc(m, bar, dst + rank * (uint32_t)(rows / 2) * 128u, kb * BK, (int)rank * (rows / 2));
     else tma_load_2d(m, bar, dst, kb * BK, 0);
 }
+#ifdef H2_HALF_W   // measurement build (results are garbage): only the B' half of every weight k-block is fetched - what a CTA pair's MMA would stream per SM
+#define H2_SKIP_BPP 1
+#else
+#define H2_SKIP_BPP 0
+#endif
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                 for (int half = 0; half < 2; ++half, ++u) {
                     const uint32_t s = u % F_UNITS, ph = (u / F_UNITS) & 1;
                     mbar_wait_wd(&b_empty[s], ph ^ 1, 100 + (int)s);
+                    if (H2_SKIP_BPP && half) { mbar_expect_tx(&b_full[s], 0); continue; }
                     mbar_expect_tx(&b_full[s], UNIT_BYTES);
                     load_rows<MC>(half ? mb : ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb, 256, rank);
                 }
@@ -207,9 +213,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
             auto narrow = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kb) {   // B' + B'' of [128 x 32] in one unit
                 const uint32_t s = u % F_UNITS, ph = (u / F_UNITS) & 1;
                 mbar_wait_wd(&b_empty[s], ph ^ 1, 110 + (int)s);
-                mbar_expect_tx(&b_full[s], UNIT_BYTES);
+                mbar_expect_tx(&b_full[s], H2_SKIP_BPP ? UNIT_BYTES / 2 : UNIT_BYTES);
                 load_rows<MC>(ma, &b_full[s], sbase + F_B + s * UNIT_BYTES, kb, 128, rank);
-                load_rows<MC>(mb, &b_full[s], sbase + F_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb, 128, rank);
+                if (!H2_SKIP_BPP) load_rows<MC>(mb, &b_full[s], sbase + F_B + s * UNIT_BYTES + UNIT_BYTES / 2, kb, 128, rank);
                 ++u;
             };
             TileSeq seq(P.net[0].rows, P.net[1].rows, MC);
