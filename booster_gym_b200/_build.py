@@ -98,7 +98,12 @@ def build(force=False, verbose=False, ptxas_info=False):
     procs = []
     for u in units:
         src = os.path.join(CSRC, u)
-        obj = os.path.join(OBJ_DIR, u.replace(".cu", ".o"))
+        # (the flags are part of the object's name: an object built with other flags, e.g. a -D measurement switch passed through
+        # B200_NVCC_EXTRA, is never linked into a library whose stamp claims the current flags)
+        import hashlib
+
+        tag = hashlib.sha256(" ".join(ARCH + COMMON + UNITS[u]).encode()).hexdigest()[:10]
+        obj = os.path.join(OBJ_DIR, u.replace(".cu", "." + tag + ".o"))
         objs.append(obj)
         if not force and not _stale(obj, deps):
             continue

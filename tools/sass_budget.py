@@ -2,7 +2,7 @@
 """Instruction budget of one kernel by SOURCE LINE: static SASS count (nvdisasm -g line table of the -lineinfo build) and,
 optionally, the warp-stall samples of an `ncu --set full --import-source on` capture of the SAME build mapped onto the lines.
 
-    python tools/sass_budget.py build/obj/physics_kernels.o _Z9k_physics [gpurun_out/prof_physics.ncu-rep] [--top 40]
+    python tools/sass_budget.py build/obj/physics_kernels.<flags hash>.o _Z9k_physics [gpurun_out/prof_physics.ncu-rep] [--top 40]
 
 This is how the instruction diet of k_physics / k_post was driven: both kernels are instruction-fetch
 bound, so their time follows the executed instruction stream; the table shows where the stream goes (inlined helpers are
