@@ -33,6 +33,7 @@ PROTOTYPES = {
     "b200_t1_physics": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b200_t1_post_physics": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "b200_t1_episode_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), _vp]),
+    "b200_t1_episode_stats_async": (_i, [_vp, _vp, _vp]),
     "b200_terrain_heights": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b200_rng_fill": (_i, [_vp, _u64, _i, _i, _i, _vp, _vp]),
     "b200_t1_bind_curriculum": (_i, [_vp, _vp, _i, _i]),

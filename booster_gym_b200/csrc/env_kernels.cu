@@ -410,6 +410,15 @@ int b200_t1_episode_stats(B200T1Handle* h, double* sums_host, int64_t* count_hos
     return B200_OK;
 }
 
+int b200_t1_episode_stats_async(B200T1Handle* h, double* out_pinned, void* stream) {
+    if (!h || !out_pinned) return set_error(B200_ERR_ARG, "b200_t1_episode_stats_async: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = h->cfg.n_rew + 3;
+    CUDA_TRY(cudaMemcpyAsync(out_pinned, h->stats_dev, k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemsetAsync(h->stats_dev, 0, k * sizeof(double), st));
+    return B200_OK;
+}
+
 int b200_terrain_heights(const B200T1Handle* h, const float* xy, int stride, int count, float* out, void* stream) {
     if (!h || !xy || !out || stride < 2 || count < 0) return set_error(B200_ERR_ARG, "b200_terrain_heights: bad argument");
     if (count == 0) return B200_OK;

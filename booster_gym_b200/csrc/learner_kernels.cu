@@ -1303,8 +1303,13 @@ static int wgrad_reduce(const WgradJobs& jobs, cudaStream_t st) {
     g_launches += 1;
     return launch_status("k_wgrad_reduce");
 }
-// split copies of the six hidden-layer weight matrices (they change every epoch)
-static int weight_prep(const B200Ppo* p, cudaStream_t st) {
+// one small launch instead of two memset nodes (back-to-back memsets cost ~5 us of idle time each inside a graph)
+__global__ void k_zero2(float* __restrict__ a, int na, double* __restrict__ b, int nb) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na; i += gridDim.x * blockDim.x) a[i] = 0.0f;
+    if (b) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) b[i] = 0.0;
+}
+// split copies of the six hidden-layer weight matrices (they change every epoch); `also_zero` (nullable): the epoch's dstats
+static int weight_prep(const B200Ppo* p, cudaStream_t st, double* also_zero = nullptr) {
     float* ws = p->ws;
     const Workspace& w = p->w;
     struct Job { int pi, rows, cols, pad; size_t h, l, th, tl; bool tr; };
@@ -1316,7 +1321,8 @@ static int weight_prep(const B200Ppo* p, cudaStream_t st) {
     int max_total = 0;
     // column abs-sums of the four matrices an input gradient passes through: [0] critic.4, [1] critic.2, [2] actor.4, [3] actor.2
     static const int cab_slot[6] = {-1, 1, 0, -1, 3, 2};
-    CU_TRY(cudaMemsetAsync(ws + w.ZR, 0, (64 + 4 * 256) * sizeof(float), st));
+    k_zero2<<<2, 256, 0, st>>>(ws + w.ZR, 64 + 4 * 256, also_zero, DS_COUNT);
+    g_launches += 1;
     for (int i = 0; i < 6; ++i) {
         const Job& j = jobs[i];
         wj.j[i] = WeightPrepJob{p->P(j.pi), ws + j.h, ws + j.l, j.tr ? ws + j.th : nullptr, j.tr ? ws + j.tl : nullptr, j.rows, j.cols, j.pad,
@@ -1833,8 +1839,7 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     const int T = p->cfg.horizon, N = p->cfg.num_envs, M = T * N;
-    CUDA_TRY(cudaMemsetAsync(p->dstats, 0, DS_COUNT * sizeof(double), st));
-    int rc = weight_prep(p, st);  // the parameters changed in the previous epoch's b200_ppo_apply
+    int rc = weight_prep(p, st, p->dstats);  // the parameters changed in the previous epoch's b200_ppo_apply; also clears dstats
     if (rc != B200_OK) return rc;
     // last_values = critic(post-rollout obs): appended as rows [M, M+N) of the critic batch, evaluated in the same GEMMs
     {

@@ -237,6 +237,21 @@ class T1(BaseTask):
             out[name] = sums[1 + i] / k
         return out, cnt.value
 
+    def episode_stats_async(self, out_pinned):
+        """stream-ordered read-and-clear of the same accumulators into a pinned float64 tensor of n_rew + 3 elements, no
+        synchronisation (decode with `decode_episode_stats` once an event recorded after this call has completed)"""
+        assert out_pinned.is_pinned() and out_pinned.dtype == torch.float64 and out_pinned.numel() >= len(self.reward_names) + 3
+        _lib.check(self._lib.b200_t1_episode_stats_async(self._h, out_pinned.data_ptr(), self._stream()), "episode_stats_async")
+
+    def decode_episode_stats(self, host):
+        n = len(self.reward_names)
+        cnt = int(host[n + 2].item() + 0.5)
+        k = max(1, cnt)
+        out = {"reward": host[0].item() / k, "steps": host[n + 1].item() / k}
+        for i, name in enumerate(self.reward_names):
+            out[name] = host[1 + i].item() / k
+        return out, cnt
+
     def inject_rng(self, table):
         """parity-test hook: int32/uint32 tensor [slots, 12, N] on the device (or None to restore the Philox draws)"""
         self._inject = table

@@ -261,14 +261,57 @@ class Runner:
 
     def train(self, on_iteration=None):
         """utils/runner.py:99-215.  `on_iteration(it, episode_means, episode_count, scalars)` (not in the reference surface) is
-        called once per iteration with what the Recorder is fed - tools/learning_curve.py and the learning test use it."""
+        called once per iteration with what the Recorder is fed - tools/learning_curve.py and the learning test use it.
+
+        Nothing on the device waits for the host (lr, KL rule, Adam step, RNG / step counters are device-resident), so the loop is
+        pipelined: the scalars / episode statistics / curriculum levels of iteration i are copied to pinned host memory in stream
+        order, the graphs of iteration i + 1 are launched, and only then the host waits for iteration i's copies and logs them
+        (TensorBoard, callbacks) while the GPU is busy.  A checkpoint needs the parameters OF its iteration and drains the pipeline."""
         self.recorder = Recorder(self.cfg) if self.rank == 0 else None
         obs, infos = self.env.reset()
         privileged_obs = infos["privileged_obs"]
         SC = _abi.SC
         cur_multi = self.world_size > 1 and bool(self.cfg["commands"].get("curriculum"))
         use_graph = os.environ.get("B200_ROLLOUT_GRAPH", "1") != "0"
-        for it in range(self.cfg["basic"]["max_iterations"]):
+        pipelined = os.environ.get("B200_TRAIN_PIPELINE", "1") != "0"
+        horizon = self.cfg["runner"]["horizon_length"]
+        n_stats = len(self.env.reward_names) + 3
+        slots = [{"scalars": torch.empty(SC["COUNT"], dtype=torch.float32).pin_memory(), "stats": torch.zeros(n_stats, dtype=torch.float64).pin_memory(),
+                  "levels": torch.zeros(4, dtype=torch.float32).pin_memory(), "event": torch.cuda.Event(), "it": -1} for _ in range(2)]
+        max_it = self.cfg["basic"]["max_iterations"]
+
+        def publish(slot):
+            """host side of one finished iteration: wait for its copies, then callbacks / Recorder"""
+            slot["event"].synchronize()
+            it, sc = slot["it"], slot["scalars"]
+            epochs = max(1.0, sc[SC["EPOCHS"]].item())
+            self.learning_rate = sc[SC["LR"]].item()
+            ep_means, ep_count = self.env.decode_episode_stats(slot["stats"])
+            if on_iteration is not None:
+                on_iteration(it, ep_means, ep_count, sc)
+            if self.recorder is not None:
+                lv = slot["levels"]
+                self.recorder.record_episode_summary(ep_means, ep_count, it)
+                self.recorder.record_statistics(
+                    {
+                        "value_loss": sc[SC["SUM_VALUE_LOSS"]].item() / epochs,
+                        "actor_loss": sc[SC["SUM_ACTOR_LOSS"]].item() / epochs,
+                        "bound_loss": sc[SC["SUM_BOUND_LOSS"]].item() / epochs,
+                        "entropy": sc[SC["SUM_ENTROPY"]].item() / epochs,
+                        "kl_mean": sc[SC["KL"]].item(),
+                        "lr": self.learning_rate,
+                        "curriculum/mean_lin_vel_level": lv[0].item(),
+                        "curriculum/mean_ang_vel_level": lv[1].item(),
+                        "curriculum/max_lin_vel_level": lv[2].item(),
+                        "curriculum/max_ang_vel_level": lv[3].item(),
+                    },
+                    it,
+                )
+                print("epoch: {}/{}".format(it + 1, max_it))
+
+        pending = None
+        step_base = self.env.common_step_counter
+        for it in range(max_it):
             if cur_multi:
                 cur_before = self.env.curriculum_prob.clone()
             obs, privileged_obs = (self.rollout_graphed if use_graph else self.rollout)(obs, privileged_obs)
@@ -281,38 +324,29 @@ class Runner:
                 self.env.curriculum_prob = torch.clamp(cur_before + delta, max=1.0)
             self.learner.scalars[SC["SUM_VALUE_LOSS"]:SC["EPOCHS"] + 1].zero_()
             (self.update_graphed if use_graph else self.update)(obs, privileged_obs)
-            sc = self.learner.scalars.cpu()  # the one host sync of the iteration
-            epochs = max(1.0, sc[SC["EPOCHS"]].item())
-            self.learning_rate = sc[SC["LR"]].item()
-            kl_mean = sc[SC["KL"]].item()
-            ep_means, ep_count = self.env.episode_stats()
-            self.env.common_step_counter = self.env.counters()[1]
-            if on_iteration is not None:
-                on_iteration(it, ep_means, ep_count, sc)
-            if self.recorder is not None:
-                self.recorder.record_episode_summary(ep_means, ep_count, it)
-                self.recorder.record_statistics(
-                    {
-                        "value_loss": sc[SC["SUM_VALUE_LOSS"]].item() / epochs,
-                        "actor_loss": sc[SC["SUM_ACTOR_LOSS"]].item() / epochs,
-                        "bound_loss": sc[SC["SUM_BOUND_LOSS"]].item() / epochs,
-                        "entropy": sc[SC["SUM_ENTROPY"]].item() / epochs,
-                        "kl_mean": kl_mean,
-                        "lr": self.learning_rate,
-                        "curriculum/mean_lin_vel_level": self.env.mean_lin_vel_level,
-                        "curriculum/mean_ang_vel_level": self.env.mean_ang_vel_level,
-                        "curriculum/max_lin_vel_level": self.env.max_lin_vel_level,
-                        "curriculum/max_ang_vel_level": self.env.max_ang_vel_level,
-                    },
-                    it,
+            # ---- this iteration's results -> pinned host memory, in stream order (the next iteration overwrites the device copies)
+            slot = slots[it & 1]
+            slot["it"] = it
+            slot["scalars"].copy_(self.learner.scalars, non_blocking=True)
+            self.env.episode_stats_async(slot["stats"])
+            lvl = torch.abs(self.env.env_curriculum_level).float()
+            slot["levels"].copy_(torch.cat([lvl.mean(0), lvl.max(0).values]), non_blocking=True)
+            slot["event"].record(torch.cuda.current_stream(self.device))
+            self.env.common_step_counter = step_base + (it + 1) * horizon   # (the device counter advances once per env step: no read-back)
+            # ---- the previous iteration is logged while this one runs
+            if pending is not None:
+                publish(pending)
+            pending = slot
+            save_now = self.recorder is not None and (it + 1) % self.cfg["runner"]["save_interval"] == 0
+            if not pipelined or save_now or it == max_it - 1:
+                publish(pending)
+                pending = None
+            if save_now:
+                self.recorder.save(
+                    {"model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(),
+                     "curriculum": self.env.curriculum_prob},
+                    it + 1,
                 )
-                if (it + 1) % self.cfg["runner"]["save_interval"] == 0:
-                    self.recorder.save(
-                        {"model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(),
-                         "curriculum": self.env.curriculum_prob},
-                        it + 1,
-                    )
-                print("epoch: {}/{}".format(it + 1, self.cfg["basic"]["max_iterations"]))
 
     def play(self, max_steps=None):
         obs, infos = self.env.reset()

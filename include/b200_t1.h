@@ -187,6 +187,10 @@ int b200_t1_post_physics(B200T1Handle* h, float* obs, float* priv, float* rew, u
  * {sum of finished-episode reward, per-term sums..., sum of steps}, count = finished episodes; read-and-clear.
  * This call synchronises the stream. */
 int b200_t1_episode_stats(B200T1Handle* h, double* sums_host, int64_t* count_host, void* stream);
+/* the same read-and-clear WITHOUT the synchronisation: out_pinned (page-locked host memory, n_rew + 3 doubles) receives
+ * {reward sum, per-term sums..., step sum, episode count} in stream order; the caller waits on an event of its own before reading
+ * (Runner.train logs iteration i while the graphs of iteration i + 1 run). */
+int b200_t1_episode_stats_async(B200T1Handle* h, double* out_pinned, void* stream);
 
 /* replaces Terrain.terrain_heights (utils/terrain.py:101-121) on the device heightfield; xy rows of `stride` floats */
 int b200_terrain_heights(const B200T1Handle* h, const float* xy, int stride, int count, float* out, void* stream);

@@ -36,6 +36,7 @@ def test_train_runs_three_iterations_and_writes_a_checkpoint(tmp_path):
         assert torch.isfinite(runner.learner.params).all() and not torch.equal(p0, runner.learner.params)
         assert runner.learner.scalars[_abi.SC["ADAM_STEP"]].item() == 3 * runner.cfg["runner"]["mini_epochs"]
         assert getattr(runner, "_rollout_graph", None) is not None           # iterations 1.. were graph replays
+        assert runner.env.common_step_counter == runner.env.counters()[1] == 3 * runner.cfg["runner"]["horizon_length"]   # host mirror of the device counter
         ckpts = [os.path.join(d, f) for d, _, fs in os.walk(tmp_path) for f in fs if f.endswith(".pth")]
         assert len(ckpts) == 1
         ck = torch.load(ckpts[0], map_location="cpu", weights_only=True)
@@ -134,3 +135,31 @@ def test_graph_replay_equals_eager_update(tmp_path):
         assert abs(sa[_abi.SC["LR"]].item() - sb[_abi.SC["LR"]].item()) <= 1e-6 * sb[_abi.SC["LR"]].item()
     finally:
         os.chdir(cwd)
+
+
+def test_pipelined_logging_reports_every_iteration_in_order(tmp_path):
+    """Runner.train logs iteration i while the graphs of iteration i + 1 run (pinned-memory snapshots + events): the callback must
+    still see every iteration once, in order, with that iteration's scalars (Adam step = 20 (it + 1)), and the same numbers as the
+    unpipelined loop (B200_TRAIN_PIPELINE=0) up to the float-atomic noise of the gradients."""
+    from booster_gym_b200 import _abi
+
+    seen = {}
+    for mode in ("1", "0"):
+        os.environ["B200_TRAIN_PIPELINE"] = mode
+        try:
+            runner, cwd = _runner(tmp_path, basic={"max_iterations": 5})
+            rows = []
+            try:
+                runner.train(on_iteration=lambda it, means, count, sc: rows.append(
+                    (it, int(sc[_abi.SC["ADAM_STEP"]].item()), float(sc[_abi.SC["LR"]].item()), count, means["steps"])))
+            finally:
+                os.chdir(cwd)
+        finally:
+            os.environ.pop("B200_TRAIN_PIPELINE", None)
+        assert [r[0] for r in rows] == list(range(5))
+        assert [r[1] for r in rows] == [runner.cfg["runner"]["mini_epochs"] * (i + 1) for i in range(5)]
+        seen[mode] = rows
+    for a, b in zip(seen["1"], seen["0"]):
+        assert a[3] == b[3] and abs(a[4] - b[4]) <= 1e-9 * max(1.0, abs(b[4]))       # iteration 0's episodes are identical (same rollout)
+        break
+    assert sum(r[3] for r in seen["1"]) > 0

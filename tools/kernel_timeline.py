@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--terrain", type=str, default="plane")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--out", type=str, default=None)
+    ap.add_argument("--gaps", action="store_true", help="list the largest idle gaps between consecutive kernels")
     ap.add_argument("--eager-update", action="store_true", help="launch the update kernel by kernel instead of replaying its CUDA graph")
     a = ap.parse_args()
     import torch
@@ -66,6 +67,26 @@ def main():
         c = agg.setdefault(name, [0, 0.0])
         c[0] += 1
         c[1] += dur
+    if a.gaps:
+        # idle time between consecutive kernels on the device, by (previous kernel -> next kernel)
+        evs = []
+        for ev in prof.events():
+            dur = getattr(ev, "device_time", 0) or getattr(ev, "cuda_time", 0)
+            if dur and hasattr(ev, "time_range"):
+                evs.append((ev.time_range.start, ev.time_range.end, re.sub(r"\(.*", "", ev.name).replace("void ", "")))
+        evs.sort()
+        gaps = collections.OrderedDict()
+        end_prev, name_prev = None, None
+        for st, en, nm in evs:
+            if end_prev is not None and st > end_prev:
+                g = gaps.setdefault((name_prev[:36], nm[:36]), [0, 0.0])
+                g[0] += 1
+                g[1] += st - end_prev
+            if end_prev is None or en > end_prev:
+                end_prev, name_prev = en, nm
+        print(f"idle gaps per iteration: {sum(v[1] for v in gaps.values()) / a.iters / 1e3:.3f} ms")
+        for (p_, n_), (cnt, us) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:14]:
+            print(f"   {p_:36s} -> {n_:36s} {cnt / a.iters:6.1f} per it  {us / cnt:8.2f} us avg  {us / a.iters:9.1f} us/it")
     tot = sum(v[1] for v in agg.values())
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
     print(f"iteration (CUDA events, no profiler): {ms_plain:.3f} ms; sum of kernel durations under CUPTI: {tot / a.iters / 1e3:.3f} ms per iteration")
