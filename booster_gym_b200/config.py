@@ -157,7 +157,11 @@ def t1_config(cfg):
         c.dof_pos_soft_lower[j] = float(soft_lo[j])
         c.dof_pos_soft_upper[j] = float(soft_hi[j])
         c.dof_vel_limits[j] = js["urdf_velocity"][j]
-        c.torque_limits[j] = js["urdf_effort"][j]
+        # envs/t1.py clips to the URDF effort limits Isaac Gym reports; play_mujoco.py:753-755 (BASELINE configs[0]) clips to the MJCF
+        # actuator ctrlrange, which differs for hip roll (45 vs 30 N m) and knee (65 vs 60) - SURVEY 8a note 10.  asset.effort_limits: "mjcf"
+        # selects the latter (tests/test_gpu_closed_loop.py); the shipped YAML has no such key = the training path's URDF limits.
+        c.torque_limits[j] = (float(js["ctrlrange"][j][1]) if str(cfg.get("asset", {}).get("effort_limits", "urdf")).lower() == "mjcf"
+                              else js["urdf_effort"][j])
     pen = 0
     for name in rw["penalize_contacts_on"]:
         for b, bn in enumerate(body_names):

@@ -124,7 +124,10 @@ struct alignas(64) FwdNet {
     const float *b1s, *b2s, *b3;          // biases of layers 1 and 2 pre-scaled by S_ACT (k_weight_prep), layer 3 as it is
     int rows, n2, pad0_, pad_;
 };
-struct alignas(64) FwdParams { FwdNet net[2]; };
+// gain[l]: factor on layer l's accumulator (1 by default).  TMEM accumulation truncates toward zero on every add, so an accumulator
+// built from n adds sits up to n ulp BELOW its exact magnitude (mean ~n/2 ulp): a gain of 1 + n_eff 2^-25 is the midpoint estimate of
+// what was truncated - a measurement knob (B200_H2_GAIN, tools/h2_check.py), not the default.
+struct alignas(64) FwdParams { FwdNet net[2]; float gain[4]; };
 
 static constexpr int F_UNITS = O_STAGES == 2 ? 5 : 4;
 static constexpr int F_EPI0 = 3;                           // first epilogue warp
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                 const int width = layer == 0 ? 256 : (layer == 1 ? n2 : 128);
                 const uint32_t cacc = layer == 0 ? c1 : (layer == 1 ? c2 : c3);
                 const float* bias = layer == 0 ? N.b1s : (layer == 1 ? N.b2s : N.b3);
-                const float inv = layer == 0 ? 1.0f / (h2::S_X * h2::S_W) : 1.0f / (h2::S_ACT * h2::S_W);
+                const float inv = (layer == 0 ? 1.0f / (h2::S_X * h2::S_W) : 1.0f / (h2::S_ACT * h2::S_W)) * P.gain[layer];
                 CTL_WAIT(layer, mbar_wait_wd(&accf[layer], par, 300 + layer));
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 // software pipeline over the 8-column items, two register sets (unrolled by two, no copies): the accumulator slice and the

@@ -46,13 +46,13 @@ class T1(BaseTask):
         dev = self.device
         self.dof_pos_limits = torch.tensor(np.stack([js["urdf_lower"], js["urdf_upper"]], axis=1), dtype=torch.float, device=dev)
         self.dof_vel_limits = torch.tensor(js["urdf_velocity"], dtype=torch.float, device=dev)
-        self.torque_limits = torch.tensor(js["urdf_effort"], dtype=torch.float, device=dev)
         self.base_indice = self.body_names.index(cfg["asset"]["base_name"])
         self.feet_indices = torch.tensor([self.body_names.index(n) for n in cfg["asset"]["foot_names"]], dtype=torch.long, device=dev)
         if self.feet_indices.tolist() != js["feet_bodies"]:
             raise ValueError("asset.foot_names must name the two foot links of the T1 model")
 
         self._c_cfg = config.t1_config(cfg)
+        self.torque_limits = torch.tensor(list(self._c_cfg.torque_limits), dtype=torch.float, device=dev)   # URDF efforts, or the MJCF ctrlrange (asset.effort_limits)
         sp = config.sim_params(cfg)
         # asset.self_collisions is Isaac Gym's collision FILTER: 0 = leg-leg contacts enabled, 1 = disabled (envs/T1.yaml:69)
         self._c_model = robot.model_f(foot_corner=config.feet_edge_pos(cfg), dt=sp["dt"], gravity=sp["gravity"],

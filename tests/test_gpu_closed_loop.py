@@ -25,6 +25,7 @@ def test_closed_loop_rollout_tracks_fp64_oracle(t1_cfg):
     n = 8
     cfg["env"]["num_envs"] = n
     cfg["terrain"]["type"] = "plane"
+    cfg.setdefault("asset", {})["effort_limits"] = "mjcf"   # play_mujoco.py clips to the MJCF ctrlrange (SURVEY 8a note 10), not the URDF efforts
     cfg["noise"] = {}
     for k in list(cfg["randomization"].keys()):
         if isinstance(cfg["randomization"][k], dict):
@@ -48,6 +49,7 @@ def test_closed_loop_rollout_tracks_fp64_oracle(t1_cfg):
     kp = np.tile(np.array(list(env._c_cfg.kp_nominal), dtype=np.float64), (n, 1))
     kd = np.tile(np.array(list(env._c_cfg.kd_nominal), dtype=np.float64), (n, 1))
     fr = np.zeros((n, 12)); lim = env.torque_limits.cpu().double().numpy(); delay = np.zeros(n, np.int32)
+    assert lim.ravel()[1] == 45.0 and lim.ravel()[3] == 65.0      # hip roll / knee: ctrlrange, not the URDF's 30 / 60
     lt = env.last_dof_targets.cpu().double().numpy().copy()
     pf = np.zeros((n, 3)); pt = np.zeros((n, 3)); tm = np.zeros((n, 12)); terr = op.make_terrain()
     P = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
