@@ -28,7 +28,8 @@ using namespace tc;
 
 static constexpr float S_ACT = 16.0f;        // hidden activations (ELU outputs >= -1; clamped at 65000 / 16)
 static constexpr float S_W = 1024.0f;        // hidden-layer weights
-static constexpr float S_X = 1.0f;           // network inputs (observations)
+static constexpr float S_X = 256.0f;         // network inputs (observations): with a scale of 1 the lo half of an input of magnitude 0.1 was an fp16 SUBNORMAL (absolute
+                                             // precision 2^-24, i.e. 6e-7 of the value); |x| beyond 65000 / 256 = 254 is clamped
 static constexpr float H2_MAX = 65000.0f;    // largest magnitude stored (fp16 max is 65504)
 
 // device scalars of the format (workspace region `SC`): gradient scales of the two nets, chosen per epoch

@@ -1406,6 +1406,16 @@ static cudaError_t h2_chain_launch(void (*kernel)(const Params), const Params& P
                                    int num_sms, cudaStream_t st) {
     return chain_launch(kernel, P, rows0, rows1, threads, smem, pair, num_sms, st);
 }
+// midpoint compensation of a TMEM accumulator built by n truncating adds (mlp_chain_h2.cuh, FwdNet::gain): 1 + n 2^-26, scaled by
+// B200_H2_MIDPOINT (default 1; 0 switches the compensation off)
+static float midpoint_gain(int n_adds, int which = 0) {
+    static const float k = getenv("B200_H2_MIDPOINT") ? (float)atof(getenv("B200_H2_MIDPOINT")) : 1.0f;
+    static const float kx[4] = {getenv("B200_H2_MIDPOINT_L1") ? (float)atof(getenv("B200_H2_MIDPOINT_L1")) : 1.0f,
+                                getenv("B200_H2_MIDPOINT_L2") ? (float)atof(getenv("B200_H2_MIDPOINT_L2")) : 1.0f,
+                                getenv("B200_H2_MIDPOINT_L3") ? (float)atof(getenv("B200_H2_MIDPOINT_L3")) : 1.0f,
+                                getenv("B200_H2_MIDPOINT_BWD") ? (float)atof(getenv("B200_H2_MIDPOINT_BWD")) : 1.0f};   // measurement knobs
+    return 1.0f + k * kx[which & 3] * (float)n_adds * 1.490116119384765625e-8f;
+}
 // the same launch on the h2 operand format (mlp_chain_h2.cuh): Xh = input words, W*h / W*l = B' / B'' words, H1 / H2 receive words
 static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPtrs& c1, cudaStream_t st) {
     chain2::FwdParams P;
@@ -1431,17 +1441,15 @@ static int chain_forward_h2(B200Ppo* p, const ChainNetPtrs& c0, const ChainNetPt
         N.mX = *mX; N.mW1a = *mW1a; N.mW1b = *mW1b; N.mW2a = *mW2a; N.mW2b = *mW2b; N.mW3a = *mW3a; N.mW3b = *mW3b;
         N.mH1 = *mH1; N.mH2 = *mH2; N.mH3 = *mH3;
         N.b1s = p->ws + p->w.BS + (i == 0 ? 0 : 512); N.b2s = N.b1s + 256; N.b3 = c.b3;   // (net 0 = critic, net 1 = actor)
+        // accumulating MMAs per layer with the dominant terms present: layer 1 issues its 8 cross-term MMAs first (into a small
+        // accumulator) and 8 main ones; layer 2 is 8 k-blocks x 4 k-steps (x 2 when the 256-wide layer issues cross and main terms
+        // into the same columns); layer 3 is n2 / 32 k-blocks x 4 on stacked main | cross columns
+        N.gain[0] = midpoint_gain(8, 0); N.gain[1] = midpoint_gain(c.n2 == 256 ? 64 : 32, 1); N.gain[2] = midpoint_gain(c.n2 / 32 * 4, 2); N.gain[3] = 1.0f;
         fl += 2.0 * c.rows * ((double)c.k_valid * 256 + 256.0 * c.n2 + (double)c.n2 * 128);
         by += 4.0 * c.rows * (64 + 256 + c.n2 + 128);   // X words read; h1, h2 words and h3 written
     }
     const int tiles = (P.net[0].rows + tc::BM - 1) / tc::BM + (P.net[1].rows + tc::BM - 1) / tc::BM;
     if (tiles <= 0) return B200_OK;
-    for (int l = 0; l < 4; ++l) P.gain[l] = 1.0f;
-    if (const char* gs = getenv("B200_H2_GAIN")) {   // measurement knob: "n1,n2,n3" in units of 2^-25 per layer (see FwdParams)
-        float n[3] = {0.f, 0.f, 0.f};
-        sscanf(gs, "%f,%f,%f", &n[0], &n[1], &n[2]);
-        for (int l = 0; l < 3; ++l) P.gain[l] = 1.0f + n[l] * 2.98023223876953125e-8f;
-    }
     static unsigned long long configured[4] = {0, 0, 0, 0};
     CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<1, 0>, chain2::F_SMEM, configured[0]));
     CU_TRY(ensure_dynamic_smem(chain2::k_mlp_fwd_h2<2, 0>, chain2::F_SMEM, configured[1]));
@@ -1495,6 +1503,9 @@ static int chain_backward_h2(B200Ppo* p, int M, bool critic, bool actor, cudaStr
         chain2::BwdNet& N = P.net[i];
         N.n2 = i == 0 ? 256 : 128;
         N.rows = (i == 0 ? critic : actor) ? M : 0;
+        // dz2 = dz3 W3: 4 k-blocks x 4 k-steps (x 2 MMAs into the same columns for the 256-wide critic layer); dz1 = dz2 W2: n2 / 32
+        // k-blocks x 4 k-steps x 2 (the 256 outputs take the cross and the main MMA in the same columns)
+        N.gain[0] = midpoint_gain(N.n2 == 256 ? 32 : 16, 3); N.gain[1] = midpoint_gain(N.n2 / 32 * 4 * 2, 3);
         if (N.rows <= 0) continue;
         TC_MAP(mZ3, ws + (i == 0 ? w.GC3 : w.GA3), M, 128, 128, tc::BM, true);
         TC_MAP(mH2, ws + (i == 0 ? w.C2 : w.A2), M, N.n2, N.n2, tc::BM, true);
@@ -1660,10 +1671,11 @@ static int actor_forward_tc(B200Ppo* p, int M, cudaStream_t st) {
     const Workspace& w = p->w;
     int rc;
     if (g_chain) {
+        // the SAME head kernel as the epoch's forward (b200_ppo_epoch_a): the old distribution of b200_ppo_old_dist and the first epoch's mu
+        // must agree to the bit, as they do in the reference (ratio == 1, KL == 0 in epoch 0) - a different summation order moved mu by
+        // ~1e-7 of its scale and, amplified by (a - mu) / sigma^2, the probability ratios by up to 3e-4
         if ((rc = chain_forward(p, critic_ptrs(p, 0), actor_ptrs(p, M), st))) return rc;
-        k_actor_head<<<1184, 256, 0, st>>>(ws + w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + w.MU);
-        g_launches += 1;
-        return launch_status("k_actor_head");
+        return head_forward<12>(p, ws + w.A3, p->P(P_AW3), p->P(P_AB3), M, ws + w.MU, st);
     }
     if ((rc = tc_fwd(p, ws + w.Xa, 47, 64, ws + w.Wa0h, ws + w.Wa0l, 64, p->P(P_AB0), ws + w.A1, M, 256, st, true))) return rc;
     if ((rc = tc_fwd(p, ws + w.A1, 256, 256, ws + w.Wa1h, ws + w.Wa1l, 256, p->P(P_AB1), ws + w.A2, M, 128, st, true))) return rc;

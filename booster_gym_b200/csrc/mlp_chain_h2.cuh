@@ -123,11 +123,14 @@ struct alignas(64) FwdNet {
     CUtensorMap mH1, mH2, mH3;            // outputs: h1 words [rows,256], h2 words [rows,n2], h3 fp32 [rows,128]; box 32 x 128
     const float *b1s, *b2s, *b3;          // biases of layers 1 and 2 pre-scaled by S_ACT (k_weight_prep), layer 3 as it is
     int rows, n2, pad0_, pad_;
+    // Midpoint compensation of the truncating accumulator.  A tcgen05.mma adds into TMEM with truncation toward zero, so an accumulator
+    // built by n accumulating MMAs sits between 0 and n ulp BELOW its exact magnitude - a bias that, unlike round-to-nearest errors, does
+    // not average out over the batch (measured: mu -7.3e-7 of its mean magnitude, and the actor's gradients inherit it amplified by 1 /
+    // sigma).  gain[l] = 1 + n_l 2^-26 (n_l = accumulating MMAs of layer l with the dominant terms present) moves the result to the middle
+    // of that interval: mean signed error of mu +5e-8, max error halved (h2::midpoint_gain, set by the host; B200_H2_MIDPOINT=0: all 1).
+    float gain[4];
 };
-// gain[l]: factor on layer l's accumulator (1 by default).  TMEM accumulation truncates toward zero on every add, so an accumulator
-// built from n adds sits up to n ulp BELOW its exact magnitude (mean ~n/2 ulp): a gain of 1 + n_eff 2^-25 is the midpoint estimate of
-// what was truncated - a measurement knob (B200_H2_GAIN, tools/h2_check.py), not the default.
-struct alignas(64) FwdParams { FwdNet net[2]; float gain[4]; };
+struct alignas(64) FwdParams { FwdNet net[2]; };
 
 static constexpr int F_UNITS = O_STAGES == 2 ? 5 : 4;
 static constexpr int F_EPI0 = 3;                           // first epilogue warp
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_mlp_fwd_h2(const __grid_consta
                 const int width = layer == 0 ? 256 : (layer == 1 ? n2 : 128);
                 const uint32_t cacc = layer == 0 ? c1 : (layer == 1 ? c2 : c3);
                 const float* bias = layer == 0 ? N.b1s : (layer == 1 ? N.b2s : N.b3);
-                const float inv = (layer == 0 ? 1.0f / (h2::S_X * h2::S_W) : 1.0f / (h2::S_ACT * h2::S_W)) * P.gain[layer];
+                const float inv = (layer == 0 ? 1.0f / (h2::S_X * h2::S_W) : 1.0f / (h2::S_ACT * h2::S_W)) * N.gain[layer];
                 CTL_WAIT(layer, mbar_wait_wd(&accf[layer], par, 300 + layer));
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 // software pipeline over the 8-column items, two register sets (unrolled by two, no copies): the accumulator slice and the
@@ -439,6 +442,7 @@ struct alignas(64) BwdNet {
     float *db2, *db1;                     // bias gradients of layers 2 and 1 (+= column sums of dz2 / dz1)
     const float* isg;                     // device: 1 / gradient scale of this net
     int rows, n2;
+    float gain[2];                        // midpoint compensation of the dz2 / dz1 accumulators (see FwdNet)
 };
 struct alignas(64) BwdParams { BwdNet net[2]; };
 
@@ -704,7 +708,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
             ai_base += 4; li_base += 4;
         };
         // a segment of ELU'-masked gradient k-blocks: v = acc * ELU'(h); store; column sums; optionally hand over to the next GEMM
-        auto grad_segment = [&](int nkb, uint32_t tcol0, uint32_t cross, int col0, float* db, float isg, bool row_ok, bool handoff) {
+        auto grad_segment = [&](int nkb, uint32_t tcol0, uint32_t cross, int col0, float* db, float isg, bool row_ok, bool handoff, float gain) {
+            const float ascale = (1.0f / h2::S_W) * gain;
 #pragma unroll 1
             for (int kb = grp; kb < nkb; kb += G) {
                 const uint32_t as = aux_wait(ai_base + kb);
@@ -726,7 +731,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
                     for (int j = 0; j < 8; ++j) {
                         const float h = h2::unpack(hw[j]);   // = S_ACT * activation
                         const float acc = cross ? __uint_as_float(r[j]) + __uint_as_float(r2[j]) : __uint_as_float(r[j]);
-                        v[j] = acc * (1.0f / h2::S_W) * ((h > 0.0f) ? 1.0f : fmaf(h, 1.0f / h2::S_ACT, 1.0f));
+                        v[j] = acc * ascale * ((h > 0.0f) ? 1.0f : fmaf(h, 1.0f / h2::S_ACT, 1.0f));
                         w[j] = h2::pack(v[j]);
                     }
                     if (handoff) {
@@ -761,13 +766,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_bwd_h2(const __grid_consta
             // dz2
             CTL_WAIT(0, mbar_wait_wd(&accf[0], par, 720));
             asm volatile("tcgen05.fence::after_thread_sync;");
-            grad_segment(n2 / BK, CA, n2 == 128 ? 128u : 0u, 0, N.db2, isg, row_ok, true);
+            grad_segment(n2 / BK, CA, n2 == 128 ? 128u : 0u, 0, N.db2, isg, row_ok, true, N.gain[0]);
             // dz1: the half that shares TMEM columns with the next tile's dz3 first
             CTL_WAIT(1, mbar_wait_wd(&accf[1], par, 721));
             asm volatile("tcgen05.fence::after_thread_sync;");
-            grad_segment(4, CD, 0u, 0, N.db1, isg, row_ok, false);
+            grad_segment(4, CD, 0u, 0, N.db1, isg, row_ok, false, N.gain[1]);
             if (hn) stage_dz3();
-            grad_segment(4, CD + 128, 0u, 128, N.db1, isg, row_ok, false);
+            grad_segment(4, CD + 128, 0u, 128, N.db1, isg, row_ok, false, N.gain[1]);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(drained);

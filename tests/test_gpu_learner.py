@@ -206,13 +206,13 @@ def test_epoch_against_oracle(t1_cfg, T, N, mode):
         else:
             lib.b200_tc_set_h2(0)
             lib.b200_tc_set_chain({"tf32": 1, "tf32-pair": 2, "layers": 0}[mode])
-        _epoch_against_oracle(t1_cfg, T, N)
+        _epoch_against_oracle(t1_cfg, T, N, actor_rel=8e-5 if mode == "h2" else 2e-4)
     finally:
         lib.b200_tc_set_chain(1)
         lib.b200_tc_set_h2(1)
 
 
-def _epoch_against_oracle(t1_cfg, T, N):
+def _epoch_against_oracle(t1_cfg, T, N, actor_rel=2e-4):
     LR = 1e-4  # one Adam step of 1e-4 moves the policy by KL ~ 0.1: ratios leave the clip range without making epoch 1 chaotic
     cfg, lrn, sd, L = _mk(t1_cfg, T, N, lr=LR)
     buf, last_obs, last_priv = L.synthetic_rollout(T, N, seed=3, done_rate=0.02, timeout_rate=0.03)
@@ -258,18 +258,18 @@ def _epoch_against_oracle(t1_cfg, T, N):
         judge("mu", lrn.buffer(3, (T, N, 12)).cpu(), o32["mu"], o64["mu"])
         g = lrn.views(lrn.grads)
         for name in o64["grads"]:
-            # gradients are 98k-term sums with heavy cancellation (|sum| ~ sum|terms| / 150 for the actor biases), and the
-            # actor's gradient inherits mu's error amplified by 1/sigma (d = a - mu enters as d / sigma^2, sigma = e^-2).
-            # The tcgen05 path's errors are NOT random rounding: the 3xTF32 operand split is a fixed 2^-23-relative
-            # perturbation of the weights and TMEM accumulation truncates, so they are smooth in the observation and do
-            # not average out in the sums the way the reference's fp32 rounding does.  Measured on B200: <= 1.2e-4 of the
-            # tensor max (actor biases, epoch 0) with mu itself at 7e-7 of scale; the fp32 reference is 1.8e-5 from
-            # fp64 on the same tensors one epoch later.  Stated tolerance: 2e-4 relative (+ 3x the reference's own error).
-            # Round 2: the CRITIC's gradients meet the north_star's 1e-5 (measured 2e-6 .. 6e-6 of the tensor max in every mode); the
-            # actor's stay at the stated 2e-4 (measured <= 1.6e-4: DESIGN section 4 derives why a truncating accumulator cannot do better
-            # on a quantity that is a 150x-cancelling sum of mu's error / sigma).
+            # Parameter gradients.  CRITIC: the north_star's 1e-5 of the tensor max (measured 2e-6 .. 6e-6 in every mode).  ACTOR: its
+            # gradients are 98k-term sums with ~150x cancellation that inherit mu's error amplified by 1 / sigma (d = a - mu enters as
+            # d / sigma^2, sigma = e^-2, and this test scales the head x8), and TMEM accumulation truncates toward zero - a bias that
+            # does not average out over the batch the way the fp32 reference's round-to-nearest errors do.  Default kernels (h2, with
+            # the midpoint compensation of the truncating accumulators, mlp_chain_h2.cuh): measured against fp64 at (24, 4096), epoch 0:
+            # actor biases 3.6e-5 .. 5.9e-5, actor weights 2.0e-5 .. 3.5e-5 of the tensor max (without the compensation 9e-5 / 5.5e-5; the
+            # fp32 reference itself is up to 2e-5 away on these tensors) -> stated tolerance 8e-5 (B200_TEST_ACTOR_REL=1e-5
+            # B200_TEST_REPORT=1 prints every ratio).  Epoch 1 starts from parameters that already differ by the first Adam step's bound
+            # (below), so its comparison is no longer one of kernel accuracy alone: 1.5e-4.  The 3xTF32 fallback kernels have no
+            # compensation: 2e-4 (measured <= 1.6e-4).
             judge("grad " + name, g[name].cpu().reshape(o64["grads"][name].shape), o32["grads"][name], o64["grads"][name],
-                  rel=1e-5 if name.startswith("critic.") else 2e-4)
+                  rel=1e-5 if name.startswith("critic.") else float(os.environ.get("B200_TEST_ACTOR_REL", actor_rel if ep == 0 else max(actor_rel, 1.5e-4))))
         lrn.apply()
         sc = lrn.scalars.cpu()
         from booster_gym_b200 import _abi
@@ -288,9 +288,9 @@ def _epoch_against_oracle(t1_cfg, T, N):
             # after Adam every parameter moved by at most ~lr; compare the parameters themselves
             pass
     # parameters after two epochs.  Adam's update lr * m_hat / (sqrt(v_hat) + eps) is ~ lr * sign(g): its sensitivity to a
-    # gradient error dg is lr * O(dg / |g|) per element, so elements with a small gradient amplify the (stated, 2e-4 of the
+    # gradient error dg is lr * O(dg / |g|) per element, so elements with a small gradient amplify the (stated, `actor_rel` of the
     # tensor max) gradient tolerance.  Each parameter is therefore held to the bound that tolerance implies, element by
-    # element: sum over the two steps of lr * min(2, 2 * 2e-4 * max|g| / |g_ij|), on top of 1e-5 relative and 3x the fp32
+    # element: sum over the two steps of lr * min(2, 2 * actor_rel * max|g| / |g_ij|), on top of 1e-5 relative and 3x the fp32
     # reference's own distance from fp64.
     p = lrn.views()
     sd64, sd32 = res[torch.float64][1], res[torch.float32][1]
@@ -303,7 +303,7 @@ def _epoch_against_oracle(t1_cfg, T, N):
         lr_ep = LR
         for o in outs64:
             g = o["grads"][name].double().reshape(err.shape).abs()
-            bound += lr_ep * torch.clamp(2.0 * 2e-4 * g.max() / g.clamp_min(1e-30), max=2.0)
+            bound += lr_ep * torch.clamp(2.0 * max(actor_rel, 1.5e-4) * g.max() / g.clamp_min(1e-30), max=2.0)
             lr_ep = o["lr"]
         tol = 1e-5 * sd64[name].abs().max().item() + 3 * ref_err + bound
         worst = (err - tol).max().item()
