@@ -34,6 +34,22 @@ def test_config_builder_matches_yaml(t1_cfg):
     assert np.isclose(p.entropy_coef, -0.01) and np.isclose(p.e_clip, 0.2)
 
 
+def test_effort_limit_source_and_build_flag_hash(t1_cfg):
+    """asset.effort_limits: "mjcf" selects the MJCF actuator ctrlrange (play_mujoco.py:753-755, SURVEY 8a note 10) instead of the URDF efforts;
+    object files of the in-tree build are named after their flags, so a -D measurement build can never be re-linked under the default stamp"""
+    import hashlib
+
+    from booster_gym_b200 import _build, config
+
+    cfg = copy.deepcopy(t1_cfg)
+    cfg.setdefault("asset", {})["effort_limits"] = "mjcf"
+    assert list(config.t1_config(cfg).torque_limits) == [45.0, 45.0, 30.0, 65.0, 24.0, 15.0] * 2
+    tag = hashlib.sha256(" ".join(_build.ARCH + _build.COMMON + _build.UNITS["env_kernels.cu"]).encode()).hexdigest()[:10]
+    assert tag != hashlib.sha256(" ".join(_build.ARCH + _build.COMMON + ["-DX"] + _build.UNITS["env_kernels.cu"]).encode()).hexdigest()[:10]
+    if os.path.isdir(_build.OBJ_DIR) and os.path.exists(_build.LIB) and _build.up_to_date():
+        assert os.path.exists(os.path.join(_build.OBJ_DIR, "env_kernels." + tag + ".o"))
+
+
 def test_config_errors_follow_the_reference(t1_cfg):
     from booster_gym_b200 import config
 
