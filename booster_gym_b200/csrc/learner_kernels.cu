@@ -1876,7 +1876,7 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     } else if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
     k_gae<<<(N + 31) / 32, 32, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
-    g_launches += 3;  // memset, k_pack_inputs, k_gae
+    g_launches += 2;  // k_pack_inputs, k_gae (the zeroing kernel is counted by weight_prep)
     if (p->peers) {   // this rank's advantage moments -> peers (summed in epoch_b, behind the actor forward)
         k_xchg_post_stats<<<1, 32, 0, st>>>(p->px, p->dstats, p->xch_counter);
         g_launches += 1;
