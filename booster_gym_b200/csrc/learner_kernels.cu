@@ -121,7 +121,9 @@ struct PeerX {
 struct B200Ppo {
     PeerX px;
     int peers;                    // 1 once b200_ppo_bind_peers succeeded
-    unsigned int* xch_counter;    // device [4]: block counter of the post kernels, gradient / moment exchange sequence numbers
+    bool last_staged = false, last_staged_h2 = false;   // b200_ppo_epoch_a: the post-rollout observations are staged (see there)
+    const float *last_obs_ptr = nullptr, *last_priv_ptr = nullptr;
+    unsigned int* xch_counter;    // device [4]: block counter of the post kernels, gradient / moment exchange sequence numbers, k_adam's block counter
     B200PpoConfig cfg;
     int device;
     float *params, *grads, *adam_m, *adam_v, *scalars;
@@ -1067,35 +1069,9 @@ __global__ void __launch_bounds__(256) k_grad_sumsq(const float* __restrict__ gr
     }
 }
 
-// clip + torch.optim.Adam step (default single-tensor math: lerp for m, mul/addcmul for v, bias corrections in fp64)
-__global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m1,
-                                              float* __restrict__ m2, int n, const float* __restrict__ scalars,
-                                              const double* __restrict__ dstats, float inv_world, float max_norm,
-                                              float beta1, float beta2, float eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float total_norm = (float)sqrt(dstats[DS_GRAD_SQ]);
-    const float coef = fminf(__fdiv_rn(max_norm, __fadd_rn(total_norm, 1.0e-6f)), 1.0f);
-    const double step = (double)scalars[B200_SC_ADAM_STEP] + 1.0;
-    const double lr = (double)scalars[B200_SC_LR];
-    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-    const float step_size = (float)(lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
-    const float g = __fmul_rn(__fmul_rn(grads[i], inv_world), coef);
-    grads[i] = g;  // the reference leaves the clipped gradient in .grad
-    float m = m1[i], v = m2[i];
-    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.0f - beta1));
-    v = __fadd_rn(__fmul_rn(v, beta2), __fmul_rn(__fmul_rn(g, g), 1.0f - beta2));
-    m1[i] = m;
-    m2[i] = v;
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
-    params[i] = __fsub_rn(params[i], __fmul_rn(step_size, __fdiv_rn(m, denom)));
-}
-
 // epoch scalars + KL-adaptive learning rate (utils/runner.py:167-184), one thread
-__global__ void k_post_apply(float* __restrict__ scalars, const double* __restrict__ dstats, float desired_kl, float lr_min,
-                             float lr_max, float lr_factor) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void post_apply_body(float* __restrict__ scalars, const double* __restrict__ dstats, float desired_kl, float lr_min,
+                                float lr_max, float lr_factor) {
     const double S = dstats[DS_SAMPLES];
     const float vl = (float)(dstats[DS_VALUE_LOSS] / S), al = (float)(dstats[DS_ACTOR_LOSS] / S);
     const float bl = (float)(dstats[DS_BOUND_LOSS] / (S * 12.0)), en = (float)(dstats[DS_ENTROPY] / S);
@@ -1119,6 +1095,50 @@ __global__ void k_post_apply(float* __restrict__ scalars, const double* __restri
     if (kl > desired_kl * 2.0f) lr = fmax((double)lr_min, lr / (double)lr_factor);
     else if (kl < desired_kl / 2.0f) lr = fmin((double)lr_max, lr * (double)lr_factor);
     scalars[B200_SC_LR] = (float)lr;
+}
+
+// clip + torch.optim.Adam step (default single-tensor math: lerp for m, mul/addcmul for v, bias corrections in fp64).  The step's
+// scalars (clip coefficient, lr / bias correction 1, sqrt of bias correction 2: two fp64 pow and two fp64 sqrt) are evaluated by one
+// thread per block - every thread used to evaluate them for itself, most of the kernel's 7.5 us - and the epoch's bookkeeping
+// (post_apply_body: loss scalars, Adam step, KL-adaptive lr) runs in the LAST block to finish, i.e. after every block has read lr and the
+// step (it used to be a launch of its own).
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m1,
+                                              float* __restrict__ m2, int n, float* __restrict__ scalars,
+                                              const double* __restrict__ dstats, float inv_world, float max_norm,
+                                              float beta1, float beta2, float eps, unsigned* __restrict__ done, float desired_kl,
+                                              float lr_min, float lr_max, float lr_factor) {
+    __shared__ float s_c[3];
+    if (threadIdx.x == 0) {
+        const float total_norm = (float)sqrt(dstats[DS_GRAD_SQ]);
+        s_c[0] = fminf(__fdiv_rn(max_norm, __fadd_rn(total_norm, 1.0e-6f)), 1.0f);
+        const double step = (double)scalars[B200_SC_ADAM_STEP] + 1.0;
+        const double lr = (double)scalars[B200_SC_LR];
+        const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+        s_c[1] = (float)(lr / bc1);
+        s_c[2] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float coef = s_c[0], step_size = s_c[1], bc2_sqrt = s_c[2];
+        const float g = __fmul_rn(__fmul_rn(grads[i], inv_world), coef);
+        grads[i] = g;  // the reference leaves the clipped gradient in .grad
+        float m = m1[i], v = m2[i];
+        m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.0f - beta1));
+        v = __fadd_rn(__fmul_rn(v, beta2), __fmul_rn(__fmul_rn(g, g), 1.0f - beta2));
+        m1[i] = m;
+        m2[i] = v;
+        const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
+        params[i] = __fsub_rn(params[i], __fmul_rn(step_size, __fdiv_rn(m, denom)));
+    }
+    __syncthreads();   // every thread of this block has read the step's scalars
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {
+            *done = 0u;
+            post_apply_body(scalars, dstats, desired_kl, lr_min, lr_max, lr_factor);
+        }
+    }
 }
 
 // =====================================================================================================================
@@ -1829,6 +1849,7 @@ int b200_ppo_old_dist(B200Ppo* p, const float* obses, const float* privs, const 
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = p->ws;
     const int M = p->cfg.horizon * p->cfg.num_envs;
+    p->last_staged = false;   // a new rollout: the next b200_ppo_epoch_a stages its last_obs / last_priv again
     k_pack_inputs<<<(int)(((size_t)M * 64 + 255) / 256), 256, 0, st>>>(
         obses, privs, M, PackOut{ws + p->w.Xa, ws + p->w.Xah, ws + p->w.Xal, ws + p->w.Xc, ws + p->w.Xch, ws + p->w.Xcl, g_h2_chain ? 1 : 0});
     int rc = weight_prep(p, st);
@@ -1860,11 +1881,15 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     const int T = p->cfg.horizon, N = p->cfg.num_envs, M = T * N;
     int rc = weight_prep(p, st, p->dstats);  // the parameters changed in the previous epoch's b200_ppo_apply; also clears dstats
     if (rc != B200_OK) return rc;
-    // last_values = critic(post-rollout obs): appended as rows [M, M+N) of the critic batch, evaluated in the same GEMMs
-    {
+    // last_values = critic(post-rollout obs): appended as rows [M, M+N) of the critic batch, evaluated in the same GEMMs.  The reference
+    // evaluates est_value on the SAME tensors in every mini-epoch (utils/runner.py:132): they are staged by the first epoch after
+    // b200_ppo_old_dist (or whenever the pointers change) and reused by the following ones
+    if (!(p->last_staged && p->last_obs_ptr == last_obs && p->last_priv_ptr == last_priv && p->last_staged_h2 == g_h2_chain)) {
         const size_t o = (size_t)M * 64;
         k_pack_inputs<<<(int)(((size_t)N * 64 + 255) / 256), 256, 0, st>>>(
             last_obs, last_priv, N, PackOut{nullptr, nullptr, nullptr, ws + p->w.Xc + o, ws + p->w.Xch + o, ws + p->w.Xcl + o, g_h2_chain ? 1 : 0});
+        g_launches += 1;
+        p->last_staged = true; p->last_obs_ptr = last_obs; p->last_priv_ptr = last_priv; p->last_staged_h2 = g_h2_chain;
     }
     if (g_chain) {
         // both nets in ONE persistent launch: 800 critic + 768 actor tiles balance over the SMs better than two launches of ~5.3
@@ -1876,7 +1901,7 @@ int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uin
     } else if ((rc = critic_forward_tc(p, M + N, st)) != B200_OK) return rc;
     k_gae<<<(N + 31) / 32, 32, 0, st>>>(rewards, dones, time_outs, ws + p->w.V, ws + p->w.V + M, (float)p->cfg.gamma,
                                            (float)(p->cfg.gamma * p->cfg.lam), T, N, ws + p->w.ADV, ws + p->w.RET, p->dstats);
-    g_launches += 2;  // k_pack_inputs, k_gae (the zeroing kernel is counted by weight_prep)
+    g_launches += 1;  // k_gae (the zeroing kernel is counted by weight_prep)
     if (p->peers) {   // this rank's advantage moments -> peers (summed in epoch_b, behind the actor forward)
         k_xchg_post_stats<<<1, 32, 0, st>>>(p->px, p->dstats, p->xch_counter);
         g_launches += 1;
@@ -1989,9 +2014,9 @@ int b200_ppo_apply(B200Ppo* p, void* stream) {
     }
     k_adam<<<(NPARAMS_PADDED + 255) / 256, 256, 0, st>>>(p->params, p->grads, p->adam_m, p->adam_v, NPARAMS_PADDED, p->scalars,
                                                          p->dstats, inv_world, p->cfg.max_grad_norm, p->cfg.adam_beta1,
-                                                         p->cfg.adam_beta2, p->cfg.adam_eps);
-    k_post_apply<<<1, 32, 0, st>>>(p->scalars, p->dstats, p->cfg.desired_kl, p->cfg.lr_min, p->cfg.lr_max, p->cfg.lr_factor);
-    g_launches += 3;
+                                                         p->cfg.adam_beta2, p->cfg.adam_eps, p->xch_counter + 3, p->cfg.desired_kl,
+                                                         p->cfg.lr_min, p->cfg.lr_max, p->cfg.lr_factor);
+    g_launches += 2;
     return launch_status("b200_ppo_apply");
 }
 

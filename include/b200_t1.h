@@ -290,6 +290,9 @@ int b200_ppo_epoch(B200Ppo* p, const float* actions, float* rewards, const uint8
                    void* stream);
 /* the two halves of b200_ppo_epoch for multi-GPU runs: stage A = critic forward, time-out bootstrap, GAE and the
  * advantage moments (dstats[0..2], all-reduced by the caller); stage B = actor forward, losses, backward */
+/* last_obs / last_priv (the post-rollout observations, the same tensors in every mini-epoch of the reference, utils/runner.py:132) are
+ * staged by the first b200_ppo_epoch_a after b200_ppo_old_dist - or whenever the pointers change - and reused by the following epochs:
+ * a caller that rewrites them in place between two epochs of one update must call b200_ppo_old_dist again. */
 int b200_ppo_epoch_a(B200Ppo* p, float* rewards, const uint8_t* dones, const uint8_t* time_outs, const float* last_obs,
                      const float* last_priv, void* stream);
 int b200_ppo_epoch_b(B200Ppo* p, const float* actions, const float* old_mu, const float* old_logp, void* stream);
