@@ -92,6 +92,30 @@ int hc_env_post(const B200T1ModelF* m, const B200T1Config* c, const int16_t* hf,
         for (int e = 0; e < n; ++e) time_out_extras[e] = (uint8_t)istate[(size_t)I_time_out_buf * n + e];
     return any;
 }
+// what k_post_pair (env_kernels.cu) does with one env on two warps, serialised in the interleaving that is LEAST like env_post_physics:
+// warp 1's right-foot refresh before warp 0's part A, then the snapshot, then warp 1's reset + tail BEFORE warp 0's reward terms.  If the
+// parts were not independent in the way the kernel assumes, this order would show it (the kernel's barriers allow exactly these orders).
+int hc_env_post_pair(const B200T1ModelF* m, const B200T1Config* c, const int16_t* hf, int rows, int cols, float* fstate,
+                     int32_t* istate, int n, const uint32_t* inject, long long common_step, unsigned long long step, int noise_on,
+                     float* obs, float* priv, float* rew, uint8_t* done, uint8_t* time_out_extras, float* rew_terms) {
+    EnvView v{fstate, istate, n, 0, 42ull, inject};
+    const TerrainView tv = make_tv(c, hf, rows, cols);
+    int any = 0;
+    for (int e = 0; e < n; ++e) {
+        env_refresh_feet<B200T1ModelF, 2>(v, e, *m, tv);                                              // warp 1, before the first barrier
+        const PostA a = env_post_a<B200T1ModelF, 1>(v, e, *m, *c, tv, common_step, step);             // warp 0
+        RewardSnap snap;
+        reward_snapshot(v, e, snap);                                                                  // warp 0, between the barriers
+        if (a.reset) env_reset_one(v, e, *c, tv, step);                                               // warp 1 ...
+        env_post_tail(v, e, *m, *c, tv, step, noise_on, obs + (size_t)e * B200_NOBS, priv + (size_t)e * B200_NPRIV);
+        rew[e] = env_post_rewards(v, e, *c, snap, a.h_base, a.finite, rew_terms);                     // ... and only now warp 0's rewards
+        done[e] = (uint8_t)(a.reset ? 1 : 0);
+        any |= a.reset ? 1 : 0;
+    }
+    if (any)
+        for (int e = 0; e < n; ++e) time_out_extras[e] = (uint8_t)istate[(size_t)I_time_out_buf * n + e];
+    return any;
+}
 // the command-curriculum step (cfg.curriculum): what k_post<1>, k_curriculum_apply, k_post<2> do, serially
 int hc_env_post_curriculum(const B200T1ModelF* m, const B200T1Config* c, float* fstate, int32_t* istate, int n, const uint32_t* inject,
                            long long common_step, unsigned long long step, int noise_on, float* prob, float* obs, float* priv,

@@ -19,7 +19,7 @@ def _cfg_structs(cfg):
     return m, c
 
 
-def run_host_step(z, terrain, name=None):
+def run_host_step(z, terrain, name=None, fn="hc_env_post"):
     cfg = fixture_cfg(name, terrain)
     m, c = _cfg_structs(cfg)
     st = step_inputs(z)
@@ -30,7 +30,7 @@ def run_host_step(z, terrain, name=None):
     obs = np.zeros((n, 47), np.float32); priv = np.zeros((n, 14), np.float32); rew = np.zeros(n, np.float32)
     done = np.zeros(n, np.uint8); touts = np.zeros(n, np.uint8); terms = np.zeros((c.n_rew, n), np.float32)
     P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None  # noqa: E731
-    lib().hc_env_post(C.byref(m), C.byref(c), P(hf), hf.shape[0] if hf is not None else 0, hf.shape[1] if hf is not None else 0,
+    getattr(lib(), fn)(C.byref(m), C.byref(c), P(hf), hf.shape[0] if hf is not None else 0, hf.shape[1] if hf is not None else 0,
                       P(f), P(i), n, P(table), C.c_longlong(int(z["common_step"])), C.c_ulonglong(1), 1, P(obs), P(priv), P(rew),
                       P(done), P(touts), P(terms))
     got = unpack(f, i, ff, fi)
@@ -54,6 +54,21 @@ def test_post_physics_body_matches_reference(name, terrain):
     assert len(names) == 23
     for j, nm in enumerate(names):
         assert close(terms[j], z["out_term_" + nm]), nm
+
+
+@pytest.mark.parametrize("name,terrain", [("env_step_plane.npz", "plane"), ("env_step_trimesh.npz", "trimesh"),
+                                          ("env_step_plane_noreset.npz", "plane"), ("env_step_contacts.npz", "plane")])
+def test_two_warp_decomposition_is_bit_identical(name, terrain):
+    """k_post_pair runs one env on two warps (part A + rewards | right foot + reset + teleport + observations).  Its parts, executed on
+    the host in the interleaving least like the serial body (warp 1's reset and observations BEFORE warp 0's reward terms), must leave
+    exactly the bits of env_post_physics: every state row, observation, reward term and mask."""
+    z = load(name)
+    _, a, ta = run_host_step(z, terrain, name)
+    _, b, tb = run_host_step(z, terrain, name, fn="hc_env_post_pair")
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    for k in a:
+        x, y = np.ascontiguousarray(a[k]), np.ascontiguousarray(b[k])
+        assert x.dtype == y.dtype and np.array_equal(x.view(np.uint8), y.view(np.uint8)), k
 
 
 def test_command_curriculum_body_matches_reference():
